@@ -1,0 +1,275 @@
+"""eidola-b200: B200-native drop-in for the per-frame render loop of
+IwakuraRein/CIS-565-Final-VR-Raytracer (Renderer::run + the acceleration structure it traverses).
+
+This Python layer is plumbing only: it loads the C-ABI shared library built from csrc/ (hand-written
+sm_100a CUDA + C++ host) and mirrors the reference's Scene / AccelStructure / Renderer classes
+(reference src/scene.hpp:60-83, src/accelstruct.hpp:40-46, src/renderer.hpp:52-61) on top of it.
+
+There is no CPU fallback: if libeidola.so is missing or no GPU is usable, calls raise EidolaError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, scenes
+from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, SceneArrays, default_rtx_state)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeidola.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
+_lib = None
+
+
+class EidolaError(RuntimeError):
+    pass
+
+
+# every symbol include/eidola.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "eid_last_error", "eid_version", "eid_device_count",
+    "eid_scene_create", "eid_scene_load_gltf", "eid_scene_load_desc", "eid_scene_destroy", "eid_scene_set_lookat",
+    "eid_scene_update_camera", "eid_scene_set_camera", "eid_scene_get_camera", "eid_scene_get_info",
+    "eid_scene_table_bytes", "eid_scene_read_table",
+    "eid_accel_build", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
+    "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
+    "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
+    "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
+    "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post",
+    "eid_renderer_band_range",
+]
+
+
+def lib():
+    """Load libeidola.so (once).  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EidolaError("libeidola.so not found at %s - build it with `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` (nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_size_t
+    sig = {
+        "eid_last_error": (C.c_char_p, []),
+        "eid_version": (i32, []),
+        "eid_device_count": (i32, []),
+        "eid_scene_create": (i32, [C.POINTER(vp), i32]),
+        "eid_scene_load_gltf": (i32, [vp, C.c_char_p]),
+        "eid_scene_load_desc": (i32, [vp, C.POINTER(abi.SceneDesc)]),
+        "eid_scene_destroy": (None, [vp]),
+        "eid_scene_set_lookat": (i32, [vp, abi.c_float_p, abi.c_float_p, abi.c_float_p, C.c_float]),
+        "eid_scene_update_camera": (i32, [vp, u32, u32]),
+        "eid_scene_set_camera": (i32, [vp, C.POINTER(SceneCamera)]),
+        "eid_scene_get_camera": (i32, [vp, C.POINTER(SceneCamera)]),
+        "eid_scene_get_info": (i32, [vp, C.POINTER(SceneInfo)]),
+        "eid_scene_table_bytes": (C.c_int64, [vp, i32, u32]),
+        "eid_scene_read_table": (i32, [vp, i32, u32, vp, sz]),
+        "eid_accel_build": (i32, [vp, C.POINTER(vp)]),
+        "eid_accel_destroy": (None, [vp]),
+        "eid_accel_get_info": (i32, [vp, C.POINTER(AccelInfo)]),
+        "eid_accel_trace": (i32, [vp, vp, u32, i32, vp]),
+        "eid_renderer_create": (i32, [C.POINTER(vp), vp, vp, u32, u32, vp]),
+        "eid_renderer_resize": (i32, [vp, u32, u32]),
+        "eid_renderer_destroy": (None, [vp]),
+        "eid_renderer_set_env_constant": (i32, [vp, abi.c_float_p]),
+        "eid_renderer_run": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_sync": (i32, [vp]),
+        "eid_renderer_get_outputs": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "eid_renderer_buffer_bytes": (C.c_int64, [vp, i32]),
+        "eid_renderer_read": (i32, [vp, i32, vp, sz]),
+        "eid_renderer_write": (i32, [vp, i32, vp, sz]),
+        "eid_renderer_render_host": (i32, [vp, C.POINTER(SceneCamera), C.POINTER(RtxState), i32, vp, vp]),
+        "eid_renderer_set_profiling": (i32, [vp, i32]),
+        "eid_renderer_get_stats": (i32, [vp, C.POINTER(FrameStats)]),
+        "eid_renderer_set_band": (i32, [vp, u32, u32]),
+        "eid_renderer_run_trace": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_run_post": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_band_range": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().eid_last_error()
+        raise EidolaError("eidola error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class Scene:
+    """Mirror of the reference's Scene (src/scene.hpp:60-83): load / updateCamera / getters / destroy."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().eid_scene_create(C.byref(self._h), device))
+
+    def load(self, filename):            # Scene::load(const std::string&) -> bool (scene.cpp:57)
+        _check(lib().eid_scene_load_gltf(self._h, os.fsencode(filename)))
+        return True
+
+    def load_arrays(self, arrays):       # harness path: arrays already in nvh::GltfScene shape
+        d = arrays.desc()
+        _check(lib().eid_scene_load_desc(self._h, C.byref(d)))
+        return True
+
+    def set_lookat(self, eye, center, up, fov_deg):   # CameraManip.setCamera
+        _check(lib().eid_scene_set_lookat(self._h, _f3(eye), _f3(center), _f3(up), float(fov_deg)))
+
+    def update_camera(self, width, height):           # Scene::updateCamera(cmdBuf, size) (scene.cpp:777)
+        _check(lib().eid_scene_update_camera(self._h, width, height))
+
+    def set_camera(self, cam):
+        _check(lib().eid_scene_set_camera(self._h, C.byref(cam)))
+
+    def get_camera(self):                              # Scene::getCamera
+        cam = SceneCamera()
+        _check(lib().eid_scene_get_camera(self._h, C.byref(cam)))
+        return cam
+
+    def info(self):                                    # Scene::getStat / m_trigLightWeight / m_puncLightWeight
+        i = SceneInfo()
+        _check(lib().eid_scene_get_info(self._h, C.byref(i)))
+        return i
+
+    def table(self, which, index=0):
+        n = lib().eid_scene_table_bytes(self._h, which, index)
+        if n < 0:
+            raise EidolaError("no such table %d[%d]" % (which, index))
+        buf = np.empty(n, np.uint8)
+        if n:
+            _check(lib().eid_scene_read_table(self._h, which, index, buf.ctypes.data, n))
+        return buf.view(abi.TABLE_DTYPES[which])
+
+    def destroy(self):
+        if self._h:
+            lib().eid_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class AccelStructure:
+    """Mirror of AccelStructure (src/accelstruct.hpp:40-46): create(scene) / destroy; plus a batch ray tap."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def create(self, scene):             # AccelStructure::create(gltfScene, vertexBufs, indexBufs)
+        self.destroy()
+        _check(lib().eid_accel_build(scene._h, C.byref(self._h)))
+        self._scene = scene
+
+    def info(self):
+        i = AccelInfo()
+        _check(lib().eid_accel_get_info(self._h, C.byref(i)))
+        return i
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(rays.shape[0], abi.HIT_DT)
+        _check(lib().eid_accel_trace(self._h, rays.ctypes.data, rays.shape[0], int(any_hit), hits.ctypes.data))
+        return hits
+
+    def destroy(self):
+        if self._h:
+            lib().eid_accel_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Renderer:
+    """Mirror of Renderer (src/renderer.hpp:52-61): create / run / update / destroy."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def create(self, size, scene, accel, stream=None):   # Renderer::create(size, layouts, Scene*)
+        self.destroy()
+        w, h = size
+        _check(lib().eid_renderer_create(C.byref(self._h), scene._h, accel._h, w, h, C.c_void_p(stream or 0)))
+        self._scene, self._accel, self.size = scene, accel, (w, h)
+
+    def update(self, size):               # Renderer::update(size) — resize, history dropped
+        _check(lib().eid_renderer_resize(self._h, size[0], size[1]))
+        self.size = tuple(size)
+
+    def set_env_constant(self, rgb):
+        _check(lib().eid_renderer_set_env_constant(self._h, _f3(rgb)))
+
+    def run(self, state, frames):         # Renderer::run(cmdBuf, state, profiler, descSets, frames); async
+        _check(lib().eid_renderer_run(self._h, C.byref(state), frames))
+
+    def run_trace(self, state, frames):
+        _check(lib().eid_renderer_run_trace(self._h, C.byref(state), frames))
+
+    def run_post(self, state, frames):
+        _check(lib().eid_renderer_run_post(self._h, C.byref(state), frames))
+
+    def set_band(self, y0, y1):
+        _check(lib().eid_renderer_set_band(self._h, y0, y1))
+
+    def band_range(self, which):
+        base, off, n = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(lib().eid_renderer_band_range(self._h, which, C.byref(base), C.byref(off), C.byref(n)))
+        return base.value, off.value, n.value
+
+    def sync(self):
+        _check(lib().eid_renderer_sync(self._h))
+
+    def outputs(self):
+        d, i = C.c_void_p(), C.c_void_p()
+        _check(lib().eid_renderer_get_outputs(self._h, C.byref(d), C.byref(i)))
+        return d.value, i.value
+
+    def read(self, which):
+        n = lib().eid_renderer_buffer_bytes(self._h, which)
+        if n < 0:
+            raise EidolaError("no such buffer %d" % which)
+        buf = np.empty(n, np.uint8)
+        _check(lib().eid_renderer_read(self._h, which, buf.ctypes.data, n))
+        return buf.view(abi.BUFFER_DTYPES[which])
+
+    def write(self, which, arr):
+        a = np.ascontiguousarray(arr)
+        _check(lib().eid_renderer_write(self._h, which, a.ctypes.data, a.nbytes))
+
+    def render_host(self, cam, state, frames, direct_out, indirect_out):
+        _check(lib().eid_renderer_render_host(
+            self._h, C.byref(cam) if cam is not None else None, C.byref(state), frames,
+            C.c_void_p(direct_out) if direct_out else None, C.c_void_p(indirect_out) if indirect_out else None))
+
+    def set_profiling(self, on):
+        _check(lib().eid_renderer_set_profiling(self._h, int(on)))
+
+    def stats(self):
+        s = FrameStats()
+        _check(lib().eid_renderer_get_stats(self._h, C.byref(s)))
+        return s
+
+    def destroy(self):
+        if self._h:
+            lib().eid_renderer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -1,0 +1,261 @@
+/*
+ * eidola.h — C-ABI of libeidola.so, the B200-native drop-in for the reference's per-frame
+ * render loop (Renderer::run and the acceleration structure it traverses).
+ *
+ * The reference has no FFI layer; its seam is the C++ class API that SampleExample calls
+ * (SURVEY.md §8b).  Every export below names the reference method it replaces (file:line are
+ * relative to the reference repository).  Conventions:
+ *   - plain pointers and sizes only, no C++/torch types; handles are opaque;
+ *   - return 0 (EID_OK) on success, a negative eid_status otherwise; eid_last_error() returns a
+ *     thread-local message.  No exceptions cross the boundary.  (The reference ignores VkResults
+ *     and uses bool/assert: scene.cpp:164-169, renderer.cpp:48.)
+ *   - host inputs are borrowed for the duration of the call; the library owns all device memory;
+ *   - a handle is used by one thread at a time (reference: loader thread + render thread with the
+ *     m_busy flag, sample_example.cpp:120-156); eid_renderer_run is asynchronous on the
+ *     renderer's CUDA stream, like command-buffer recording.
+ *   - there is NO CPU fallback: every compute entry point fails with EID_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef EIDOLA_H
+#define EIDOLA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "host_device.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EID_API __attribute__((visibility("default")))
+
+typedef enum eid_status {
+  EID_OK = 0,
+  EID_ERR_INVALID = -1,   /* bad argument / null handle */
+  EID_ERR_IO = -2,        /* file not found / unreadable */
+  EID_ERR_PARSE = -3,     /* malformed glTF / JSON */
+  EID_ERR_UNSUPPORTED = -4,
+  EID_ERR_CUDA = -5,      /* CUDA runtime failure, no usable GPU */
+  EID_ERR_STATE = -6      /* call order violated (e.g. run before accel build) */
+} eid_status;
+
+typedef struct eid_scene eid_scene;
+typedef struct eid_accel eid_accel;
+typedef struct eid_renderer eid_renderer;
+
+EID_API const char* eid_last_error(void);
+EID_API int eid_version(void);
+/* number of CUDA devices visible (0 when none); never fails */
+EID_API int eid_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flat scene description == what nvh::GltfScene holds after importMaterials/importDrawableNodes
+ * (reference scene.cpp:72-74; members m_positions/m_normals/m_tangents/m_texcoords0/m_colors0/
+ * m_indices/m_primMeshes/m_nodes/m_materials/m_lights/m_cameras).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct eid_prim_mesh {       /* nvh::GltfPrimMesh */
+  uint32_t firstIndex, indexCount, vertexOffset, vertexCount;
+  int32_t  materialIndex;
+} eid_prim_mesh;
+
+typedef struct eid_node {            /* nvh::GltfNode */
+  float   worldMatrix[16];           /* column-major */
+  int32_t primMesh;
+} eid_node;
+
+typedef struct eid_material_desc {   /* nvh::GltfMaterial, the fields scene.cpp:415-448 reads */
+  float   baseColorFactor[4];
+  int32_t baseColorTexture;
+  float   metallicFactor, roughnessFactor;
+  int32_t metallicRoughnessTexture;
+  int32_t emissiveTexture;
+  float   emissiveFactor[3];
+  int32_t alphaMode;                 /* 0 OPAQUE, 1 MASK, 2 BLEND */
+  float   alphaCutoff;
+  int32_t doubleSided;
+  int32_t normalTexture;
+  float   normalTextureScale;
+  float   transmissionFactor;
+  int32_t transmissionTexture;
+  float   ior;
+} eid_material_desc;
+
+typedef struct eid_light_desc {      /* nvh::GltfLight (KHR_lights_punctual) */
+  float   worldMatrix[16];
+  int32_t type;                      /* LightType_* */
+  float   color[3];
+  float   intensity;
+  float   range;
+  float   innerConeAngle, outerConeAngle;
+} eid_light_desc;
+
+typedef struct eid_scene_desc {
+  const float*    positions;   /* 3 floats / vertex */
+  const float*    normals;     /* 3 */
+  const float*    tangents;    /* 4 (w = handedness) */
+  const float*    texcoords0;  /* 2 */
+  const float*    colors0;     /* 4 */
+  uint32_t        vertexCount;
+  const uint32_t* indices;
+  uint32_t        indexCount;
+  const eid_prim_mesh*     primMeshes;  uint32_t primMeshCount;
+  const eid_node*          nodes;       uint32_t nodeCount;
+  const eid_material_desc* materials;   uint32_t materialCount;
+  const eid_light_desc*    lights;      uint32_t lightCount;
+  int32_t hasCamera;           /* glTF camera 0, scene.cpp:298-308 */
+  float   camEye[3], camCenter[3], camUp[3];
+  float   camYfovRad;
+} eid_scene_desc;
+
+typedef struct eid_scene_info {
+  uint32_t primMeshCount, nodeCount, materialCount, puncLightCount, trigLightCount;
+  uint32_t vertexCount, indexCount;
+  uint64_t triangleInstances;   /* sum over nodes of indexCount/3 == triangles the BVH holds */
+  float    trigLightWeight;     /* Scene::m_trigLightWeight (scene.hpp:82-83) */
+  float    puncLightWeight;     /* Scene::m_puncLightWeight */
+  float    bboxMin[3], bboxMax[3];
+} eid_scene_info;
+
+typedef enum eid_scene_table {
+  EID_TABLE_MATERIALS = 0,     /* GltfShadeMaterial[materialCount]            scene.cpp:415-448 */
+  EID_TABLE_PUNC_LIGHTS = 1,   /* PuncLight[max(1,n)]                         scene.cpp:319-353 */
+  EID_TABLE_TRIG_LIGHTS = 2,   /* TrigLight[max(1,n)]                         scene.cpp:355-409 */
+  EID_TABLE_LIGHT_INFO = 3,    /* LightBufInfo                                scene.cpp:101-105 */
+  EID_TABLE_INSTANCE_DATA = 4, /* InstanceData[primMeshCount]                 scene.cpp:179-195 */
+  EID_TABLE_VERTICES = 5,      /* VertexAttributes[] of prim mesh `index`     scene.cpp:209-289 */
+  EID_TABLE_INDICES = 6,       /* uint32[] of prim mesh `index`                                  */
+  EID_TABLE_CAMERA = 7         /* SceneCamera                                 scene.cpp:777-826 */
+} eid_scene_table;
+
+/* Scene::setup + constructor (scene.hpp:60). device = CUDA ordinal. */
+EID_API int  eid_scene_create(eid_scene** out, int device);
+/* Scene::load(filename) (scene.cpp:57-125): glTF 2.0 (.gltf + external .bin / data: URIs). */
+EID_API int  eid_scene_load_gltf(eid_scene* s, const char* path);
+/* Same import, from arrays already in the GltfScene shape (harness-generated scenes). */
+EID_API int  eid_scene_load_desc(eid_scene* s, const eid_scene_desc* desc);
+/* Scene::destroy (scene.cpp:453-511) */
+EID_API void eid_scene_destroy(eid_scene* s);
+/* CameraManip.setCamera({eye, center, up, fov}) (scene.cpp:298-308, main.cpp:67-68) */
+EID_API int  eid_scene_set_lookat(eid_scene* s, const float eye[3], const float center[3], const float up[3], float fovDeg);
+/* Scene::updateCamera(cmdBuf, size) (scene.cpp:777-826): rolls last* fields, applies the constant
+ * sub-pixel shift, uploads the UBO. */
+EID_API int  eid_scene_update_camera(eid_scene* s, uint32_t width, uint32_t height);
+/* replay path: install a complete SceneCamera verbatim */
+EID_API int  eid_scene_set_camera(eid_scene* s, const SceneCamera* cam);
+EID_API int  eid_scene_get_camera(eid_scene* s, SceneCamera* out);
+/* Scene::getStat / getScene / m_trigLightWeight / m_puncLightWeight (scene.hpp:74-83) */
+EID_API int  eid_scene_get_info(eid_scene* s, eid_scene_info* out);
+/* size in bytes of a table (index only used for VERTICES/INDICES) */
+EID_API int64_t eid_scene_table_bytes(eid_scene* s, int table, uint32_t index);
+/* device -> host copy of one table (debug / parity tap) */
+EID_API int  eid_scene_read_table(eid_scene* s, int table, uint32_t index, void* dst, size_t bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * AccelStructure (accelstruct.hpp:40-46; accelstruct.cpp:55-162).  The Vulkan driver BVH is
+ * replaced by a CUDA LBVH -> 8-wide BVH build over world-space triangles.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct eid_accel_info {
+  uint64_t triangleCount;
+  uint32_t nodeCount;          /* wide nodes */
+  uint32_t maxDepth;
+  uint64_t nodeBytes, triBytes;
+  float    buildMs;
+} eid_accel_info;
+
+typedef struct eid_hit {       /* PtPayload subset (globals.glsl:48-58) */
+  float   hitT;                /* 1e28 on miss */
+  int32_t primitiveID;
+  int32_t instanceID;          /* node index */
+  int32_t instanceCustomIndex; /* prim mesh index */
+  float   baryU, baryV;
+} eid_hit;
+
+/* AccelStructure::create(gltfScene, vertexBufs, indexBufs) */
+EID_API int  eid_accel_build(eid_scene* s, eid_accel** out);
+EID_API void eid_accel_destroy(eid_accel* a);
+EID_API int  eid_accel_get_info(eid_accel* a, eid_accel_info* out);
+/* Batch ray query with HOST buffers (ClosestHit / AnyHit of traceray_rq.glsl:108-185).
+ * rays: 8 floats each {ox,oy,oz,tmax, dx,dy,dz,unused}.  any_hit != 0 -> hits[i].hitT is 0 when
+ * occluded and 1e28 when free, other fields undefined. */
+EID_API int  eid_accel_trace(eid_accel* a, const float* rays, uint32_t n, int any_hit, eid_hit* hits);
+
+/* ---------------------------------------------------------------------------------------------
+ * Renderer (renderer.hpp:52-61; renderer.cpp:97-375)
+ * ------------------------------------------------------------------------------------------- */
+typedef enum eid_buffer {
+  EID_BUF_THIS_GBUFFER = 0,        /* uint32 x4 / pixel  (allocation pitch)               */
+  EID_BUF_LAST_GBUFFER = 1,
+  EID_BUF_MOTION = 2,              /* int16 x2 / pixel                                     */
+  EID_BUF_THIS_DIRECT_RESV = 3,    /* DirectReservoir[size.x*size.y]                       */
+  EID_BUF_LAST_DIRECT_RESV = 4,
+  EID_BUF_THIS_INDIRECT_RESV = 5,  /* IndirectReservoir[(size.x/2)*(size.y/2)]             */
+  EID_BUF_LAST_INDIRECT_RESV = 6,
+  EID_BUF_DIRECT = 7,              /* thisDirectResultImage   float x4 / pixel             */
+  EID_BUF_INDIRECT = 8,            /* thisIndirectResultImage float x4 / pixel             */
+  EID_BUF_DENOISE_DIR_A = 9, EID_BUF_DENOISE_DIR_B = 10,
+  EID_BUF_DENOISE_IND_A = 11, EID_BUF_DENOISE_IND_B = 12
+} eid_buffer;
+
+/* kernels of one Renderer::run, in launch order */
+enum { EID_K_DIRECT = 0, EID_K_INDIRECT = 1, EID_K_DENOISE_DIRECT = 2, EID_K_DENOISE_INDIRECT = 3,
+       EID_K_COMPOSE = 4, EID_K_COUNT = 5 };
+
+typedef struct eid_frame_stats {
+  uint64_t closestHitRays;     /* rays issued by ClosestHit in the last frame (counted on device) */
+  uint64_t anyHitRays;         /* rays issued by AnyHit */
+  uint64_t primaryHits;        /* pixels whose primary ray hit geometry */
+  uint32_t launches;           /* CUDA kernels launched by the last eid_renderer_run */
+  float    kernelMs[EID_K_COUNT];   /* CUDA-event time per stage (sum over its passes); needs profiling on */
+  uint32_t kernelLaunches[EID_K_COUNT];
+} eid_frame_stats;
+
+/* Renderer::setup + create(size, layouts, scene) (renderer.cpp:50-57, 97-148).
+ * cuda_stream: a cudaStream_t to enqueue on, or NULL for a renderer-owned stream.
+ * All history buffers are zero-initialised. */
+EID_API int  eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a,
+                                 uint32_t width, uint32_t height, void* cuda_stream);
+/* Renderer::update(size) (renderer.cpp:209-225): re-allocates, drops history */
+EID_API int  eid_renderer_resize(eid_renderer* r, uint32_t width, uint32_t height);
+EID_API void eid_renderer_destroy(eid_renderer* r);
+/* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR
+ * map is installed; default (0,0,0). */
+EID_API int  eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]);
+/* Renderer::run(cmdBuf, state, profiler, descSets, frames) (renderer.cpp:154-206): enqueues
+ * direct_stage, indirect_stage, denoise_direct x4, denoise_indirect x5, compose and returns.
+ * `frames` selects the ping-pong set exactly as (frames+1)%2 (renderer.cpp:157). */
+EID_API int  eid_renderer_run(eid_renderer* r, const RtxState* state, int frames);
+EID_API int  eid_renderer_sync(eid_renderer* r);
+/* device pointers of thisDirectResultImage / thisIndirectResultImage, valid until the next run */
+EID_API int  eid_renderer_get_outputs(eid_renderer* r, const float** direct_rgba32f, const float** indirect_rgba32f);
+/* size in bytes of a buffer for the size used by the last run (or the allocation when none) */
+EID_API int64_t eid_renderer_buffer_bytes(eid_renderer* r, int which);
+/* synchronising device -> host copy (parity tap / checkpoint of the cross-frame state) */
+EID_API int  eid_renderer_read(eid_renderer* r, int which, void* host_dst, size_t bytes);
+/* host -> device restore of a history buffer (checkpoint/resume, tests) */
+EID_API int  eid_renderer_write(eid_renderer* r, int which, const void* host_src, size_t bytes);
+/* End-to-end convenience used by hosts that keep everything in host memory: uploads `cam`
+ * (may be NULL to keep the scene's camera), runs one frame, copies the two result images into
+ * pinned or pageable host buffers (width*height*16 bytes each, either may be NULL) and syncs. */
+EID_API int  eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
+                                      float* direct_host, float* indirect_host);
+/* per-stage CUDA-event timing + device ray counters for the following runs (off by default) */
+EID_API int  eid_renderer_set_profiling(eid_renderer* r, int enabled);
+EID_API int  eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out);
+
+/* ---- multi-GPU band sharding (new; no reference analogue) --------------------
+ * Rank `rank` of `world` traces (direct_stage + indirect_stage) only full-res rows
+ * [y0, y1) of the frame (band edges multiples of 16 so 8x8 half-res tiles never straddle).
+ * eid_renderer_run_trace enqueues the two trace kernels for the band; the caller then
+ * all-gathers the three exchange buffers below (the ONE collective) and calls
+ * eid_renderer_run_post, which runs denoise+compose on the full frame. */
+EID_API int  eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1);
+EID_API int  eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames);
+EID_API int  eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames);
+/* device pointer + byte range of this rank's band inside buffer `which`
+ * (EID_BUF_THIS_GBUFFER, EID_BUF_DIRECT, EID_BUF_DENOISE_IND_A, EID_BUF_MOTION, reservoirs) */
+EID_API int  eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIDOLA_H */

@@ -1,0 +1,123 @@
+/*
+ * oracle/oracle.h — TEST INFRASTRUCTURE: CPU oracle of the reference's per-frame render loop.
+ *
+ * A plain C++17 restatement (no CUDA, no GPU) of IwakuraRein/CIS-565-Final-VR-Raytracer's
+ * hot path: Scene table builders (src/scene.cpp), the alias table (src/alias_table.hpp),
+ * Renderer::run's dispatch schedule (src/renderer.cpp:154-206) and the five live compute
+ * shaders with all their includes (shaders/ *.glsl and *.comp).  Each function cites the
+ * reference file:line it follows.
+ *
+ * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and cannot be built
+ * or run here (no Vulkan ICD, no glslang, nvpro_core un-vendored — SURVEY.md §8c), so the
+ * whole-frame behaviour of this oracle is "parity unpinned".  What IS pinned:
+ *   - the known-answer vectors of SURVEY.md §4 (tea / pcg / rand / hash8bit / oct-encode /
+ *     alias table / struct sizes), tests/test_oracle_kat.py;
+ *   - the three reference files that compile stand-alone (shaders/host_device.h,
+ *     shaders/compress.glsl C++ branch, src/alias_table.hpp), built by oracle/Makefile into
+ *     oracle/_ref/libref.so and compared against this restatement, with the outputs committed
+ *     as tests/golden/ref_*.npz for machines without /root/reference.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (libeidola.so) never links or calls it.
+ */
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <atomic>
+#include "host_device.h"
+#include "eidola.h"      // eid_scene_desc & friends: the interchange structs only
+#include "glsl_types.h"
+
+namespace orc {
+
+struct OTri {             // world-space triangle prepared for the intersector
+  vec3 v0, e1, e2;
+  int prim, inst;         // primitiveID inside the prim mesh, instanceID (node index)
+  int customIndex;        // prim mesh index
+  int cullDisable;        // VK_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE (accelstruct.cpp:148-149)
+  int flip;               // instance transform mirrors (det < 0): object-space facing is the opposite of world-space
+};
+
+struct Hit {
+  float hitT; int primitiveID, instanceID, instanceCustomIndex; vec2 bary;
+};
+
+struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
+
+struct Bvh {
+  std::vector<BvhNode> nodes;
+  std::vector<int> order;    // triangle indices
+  void build(const std::vector<OTri>& tris, float pad);
+};
+
+struct Scene {
+  // flat glTF-import data (nvh::GltfScene shape)
+  std::vector<float> positions, normals, tangents, texcoords0, colors0;
+  std::vector<uint32_t> indices;
+  std::vector<eid_prim_mesh> primMeshes;
+  std::vector<eid_node> nodes;
+  std::vector<eid_material_desc> materials;
+  std::vector<eid_light_desc> lights;
+  // device tables of the reference
+  std::vector<std::vector<VertexAttributes>> vertexBufs;
+  std::vector<std::vector<uint32_t>> indexBufs;
+  std::vector<int> instMaterial;                 // InstanceData.materialIndex
+  std::vector<GltfShadeMaterial> shadeMaterials;
+  std::vector<PuncLight> puncLights;
+  std::vector<TrigLight> trigLights;
+  LightBufInfo lightBufInfo{};
+  float trigLightWeight = 0.f, puncLightWeight = 0.f;
+  // camera
+  SceneCamera camera{};
+  float eye[3] = {2, 2, -5}, center[3] = {-1, 2, -1}, up[3] = {0, 1, 0};   // main.cpp:68
+  float fovDeg = 60.f;
+  float staticEye[3] = {0, 0, 0};   // function-static `eye` of Scene::updateCamera (scene.cpp:780)
+  // acceleration structure inputs
+  std::vector<mat4x3> objectToWorld, worldToObject;
+  std::vector<OTri> tris;
+  Bvh bvh;
+  bool useBvh = true;
+  float bboxMin[3], bboxMax[3];
+
+  void load(const eid_scene_desc& d);
+  void updateCamera(uint32_t w, uint32_t h);
+  void buildAccel();
+  Hit closestHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const;
+  bool anyHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const;
+};
+
+struct Renderer {
+  const Scene* scene = nullptr;
+  uint32_t width = 0, height = 0;      // allocation size
+  std::vector<uvec4> gbuffer[2];
+  std::vector<int16_t> motion;         // 2 per pixel
+  std::vector<DirectReservoir> directResv[2];
+  std::vector<IndirectReservoir> indirectResv[2];
+  std::vector<vec4> directResult, indirectResult;       // thisDirectResultImage / thisIndirectResultImage
+  std::vector<vec4> denoiseTemp[4];                     // DirTempA, DirTempB, IndTempA, IndTempB
+  vec3 envConstant;
+  int lastSet = 0;
+  std::atomic<uint64_t> closestRays{0}, anyRays{0}, primaryHits{0};
+  double kernelMs[5] = {0, 0, 0, 0, 0};
+
+  void create(const Scene* s, uint32_t w, uint32_t h);
+  void run(const RtxState& st, int frames);
+  // stage-wise entry points (used by the band-sharded tests)
+  void runDirect(const RtxState& st, int frames, int y0, int y1);
+  void runIndirect(const RtxState& st, int frames, int y0, int y1);
+  void runPost(const RtxState& st, int frames);
+};
+
+// alias table (src/alias_table.hpp:21-63)
+void discreteSampler1D(std::vector<float> values, std::vector<float>& prob, std::vector<int>& failId);
+
+// free functions exposed for known-answer tests
+uint tea(uint val0, uint val1);
+uint pcg(uint& state);
+float rnd(uint& seed);
+uint hash8bit(uint a);
+uint compress_unit_vec(vec3 nv);
+vec3 decompress_unit_vec(uint packed);
+vec3 OffsetRay(vec3 p, vec3 n);
+
+}  // namespace orc

@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE: ctypes binding of the CPU oracle (oracle/liboracle.so) and, where it could be
+built (/root/reference present), of oracle/_ref/libref.so.  Mirrors the product's Python classes so parity
+tests drive both with the same code.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs
+import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import eidola_b200 as eid
+from eidola_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref.so")
+_lib = None
+_ref = None
+
+
+def build(force=False):
+    if force or not os.path.exists(ORACLE_SO):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_SO)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(ORACLE_SO)
+        vp, i32, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+        fp = abi.c_float_p
+        sig = {
+            "orc_fp_contract_selftest": (i32, []), "orc_num_threads": (i32, []), "orc_set_num_threads": (None, [i32]),
+            "orc_tea": (u32, [u32, u32]), "orc_rand_chain": (None, [u32, i32, vp, vp]), "orc_hash8bit": (u32, [u32]),
+            "orc_compress_unit_vec": (u32, [C.c_float] * 3), "orc_decompress_unit_vec": (None, [u32, vp]),
+            "orc_offset_ray": (None, [vp, vp, vp]), "orc_alias_table": (None, [vp, i32, vp, vp]),
+            "orc_pack_unorm4x8": (u32, [vp]), "orc_sizeof": (i32, [C.c_char_p]),
+            "orc_detmath": (None, [i32, vp, vp, i32, vp]),
+            "orc_scene_create": (vp, []), "orc_scene_destroy": (None, [vp]), "orc_scene_set_use_bvh": (None, [vp, i32]),
+            "orc_scene_load_desc": (i32, [vp, C.POINTER(abi.SceneDesc)]),
+            "orc_scene_set_lookat": (i32, [vp, fp, fp, fp, C.c_float]), "orc_scene_update_camera": (i32, [vp, u32, u32]),
+            "orc_scene_set_camera": (i32, [vp, C.POINTER(abi.SceneCamera)]),
+            "orc_scene_get_camera": (i32, [vp, C.POINTER(abi.SceneCamera)]),
+            "orc_scene_get_info": (i32, [vp, C.POINTER(abi.SceneInfo)]),
+            "orc_scene_table_bytes": (C.c_int64, [vp, i32, u32]), "orc_scene_read_table": (i32, [vp, i32, u32, vp, sz]),
+            "orc_accel_trace": (i32, [vp, vp, u32, i32, vp]),
+            "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
+            "orc_renderer_set_env_constant": (i32, [vp, fp]),
+            "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
+            "orc_renderer_run_trace": (i32, [vp, C.POINTER(abi.RtxState), i32, i32, i32]),
+            "orc_renderer_run_post": (i32, [vp, C.POINTER(abi.RtxState), i32]),
+            "orc_renderer_get_stats": (i32, [vp, C.POINTER(abi.FrameStats)]),
+            "orc_renderer_buffer_bytes": (C.c_int64, [vp, i32]), "orc_renderer_read": (i32, [vp, i32, vp, sz]),
+            "orc_renderer_write": (i32, [vp, i32, vp, sz]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        assert L.orc_fp_contract_selftest() == 0, "oracle was compiled with FMA contraction"
+        _lib = L
+    return _lib
+
+
+def ref():
+    """oracle/_ref/libref.so (the reference's own compress.glsl / alias_table.hpp / host_device.h) or None."""
+    global _ref
+    if _ref is None:
+        build()
+        if not os.path.exists(REF_SO):
+            return None
+        L = C.CDLL(REF_SO)
+        L.ref_compress_unit_vec.restype, L.ref_compress_unit_vec.argtypes = C.c_uint32, [C.c_float] * 3
+        L.ref_decompress_unit_vec.restype, L.ref_decompress_unit_vec.argtypes = None, [C.c_uint32, C.c_void_p]
+        L.ref_pack_unorm4x8.restype, L.ref_pack_unorm4x8.argtypes = C.c_uint32, [C.c_void_p]
+        L.ref_alias_table.restype, L.ref_alias_table.argtypes = None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_sizeof.restype, L.ref_sizeof.argtypes = C.c_int, [C.c_char_p]
+        _ref = L
+    return _ref
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+class OracleScene:
+    def __init__(self, use_bvh=True):
+        self._h = C.c_void_p(lib().orc_scene_create())
+        lib().orc_scene_set_use_bvh(self._h, int(use_bvh))
+
+    def load_arrays(self, arrays):
+        d = arrays.desc()
+        assert lib().orc_scene_load_desc(self._h, C.byref(d)) == 0
+
+    def set_lookat(self, eye, center, up, fov_deg):
+        lib().orc_scene_set_lookat(self._h, _f3(eye), _f3(center), _f3(up), float(fov_deg))
+
+    def update_camera(self, w, h):
+        lib().orc_scene_update_camera(self._h, w, h)
+
+    def set_camera(self, cam):
+        lib().orc_scene_set_camera(self._h, C.byref(cam))
+
+    def get_camera(self):
+        cam = abi.SceneCamera()
+        lib().orc_scene_get_camera(self._h, C.byref(cam))
+        return cam
+
+    def info(self):
+        i = abi.SceneInfo()
+        lib().orc_scene_get_info(self._h, C.byref(i))
+        return i
+
+    def table(self, which, index=0):
+        n = lib().orc_scene_table_bytes(self._h, which, index)
+        assert n >= 0
+        buf = np.empty(n, np.uint8)
+        if n:
+            assert lib().orc_scene_read_table(self._h, which, index, buf.ctypes.data, n) == 0
+        return buf.view(abi.TABLE_DTYPES[which])
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(rays.shape[0], abi.HIT_DT)
+        lib().orc_accel_trace(self._h, rays.ctypes.data, rays.shape[0], int(any_hit), hits.ctypes.data)
+        return hits
+
+    def __del__(self):
+        try:
+            lib().orc_scene_destroy(self._h)
+        except Exception:
+            pass
+
+
+class OracleRenderer:
+    def __init__(self, scene, size):
+        self._scene = scene
+        self.size = tuple(size)
+        self._h = C.c_void_p(lib().orc_renderer_create(scene._h, size[0], size[1]))
+
+    def set_env_constant(self, rgb):
+        lib().orc_renderer_set_env_constant(self._h, _f3(rgb))
+
+    def run(self, state, frames):
+        lib().orc_renderer_run(self._h, C.byref(state), frames)
+
+    def run_trace(self, state, frames, y0, y1):
+        lib().orc_renderer_run_trace(self._h, C.byref(state), frames, y0, y1)
+
+    def run_post(self, state, frames):
+        lib().orc_renderer_run_post(self._h, C.byref(state), frames)
+
+    def stats(self):
+        s = abi.FrameStats()
+        lib().orc_renderer_get_stats(self._h, C.byref(s))
+        return s
+
+    def read(self, which):
+        n = lib().orc_renderer_buffer_bytes(self._h, which)
+        assert n >= 0
+        buf = np.empty(n, np.uint8)
+        assert lib().orc_renderer_read(self._h, which, buf.ctypes.data, n) == 0
+        return buf.view(abi.BUFFER_DTYPES[which])
+
+    def write(self, which, arr):
+        a = np.ascontiguousarray(arr)
+        assert lib().orc_renderer_write(self._h, which, a.ctypes.data, a.nbytes) == 0
+
+    def __del__(self):
+        try:
+            lib().orc_renderer_destroy(self._h)
+        except Exception:
+            pass
