@@ -1,0 +1,588 @@
+// accel.cu — device upload of the scene tables, the CUDA BVH builder that replaces
+// AccelStructure::create (reference src/accelstruct.cpp:55-162: per-prim-mesh BLAS + one TLAS instance per
+// node, built by the Vulkan driver) and the C-ABI entry points for Scene and AccelStructure.
+//
+// Builder (all on the GPU, one stream):
+//   1. k_emit_triangles   every TLAS instance's triangles -> world space (contract arithmetic), 48 B
+//                         Moller-Trumbore records, padded AABBs, scene bounds (atomics)
+//   2. k_morton           63-bit Morton code of each AABB centre
+//   3. cub radix sort     (key, triangle id)
+//   4. k_reorder          triangles + AABBs into Morton order
+//   5. k_hierarchy        Karras 2012 binary radix tree, one thread per inner node
+//   6. k_refit            bottom-up AABB / leaf-count / height, atomic arrival counters
+//   7. k_pack_nodes       64 B two-box nodes; subtrees with <= 4 triangles collapse into leaves
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <vector>
+#include "accel.h"
+#include "common.h"
+#include "trace.cuh"
+
+namespace eid {
+
+#define LEAF_MAX 4u
+
+// ------------------------------------------------------------------------------------------------
+// scene upload
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static T* uploadVec(const std::vector<T>& v) {
+  T* d = nullptr;
+  size_t bytes = std::max<size_t>(1, v.size()) * sizeof(T);
+  CUDA_CHECK(cudaMalloc(&d, bytes));
+  if (!v.empty()) CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+void SceneDevice::release() {
+  cudaFree(vertices); cudaFree(indices); cudaFree(geoInfo); cudaFree(materials); cudaFree(puncLights);
+  cudaFree(trigLights); cudaFree(instances); cudaFree(instFirstTri);
+  vertices = nullptr; indices = nullptr; geoInfo = nullptr; materials = nullptr; puncLights = nullptr;
+  trigLights = nullptr; instances = nullptr; instFirstTri = nullptr;
+}
+
+void SceneDevice::upload(const SceneHost& h) {
+  release();
+  CUDA_CHECK(cudaSetDevice(device));
+  vertices = uploadVec(h.vertices);
+  indices = uploadVec(h.indices);
+  // InstanceData with real device addresses, like the reference's buffer_reference pointers (scene.cpp:179-195)
+  std::vector<InstanceData> inst(h.gltf.primMeshes.size());
+  for (size_t p = 0; p < inst.size(); ++p) {
+    inst[p].vertexAddress = (uint64_t)(uintptr_t)(vertices + h.vtxBase[p]);
+    inst[p].indexAddress = (uint64_t)(uintptr_t)(indices + h.idxBase[p]);
+    inst[p].materialIndex = h.gltf.primMeshes[p].materialIndex;
+  }
+  geoInfo = uploadVec(inst);
+  materials = uploadVec(h.materials);
+  puncLights = uploadVec(h.puncLights);
+  trigLights = uploadVec(h.trigLights);
+  instances = uploadVec(h.instances);
+  std::vector<uint32_t> first(h.instances.size() + 1, 0);
+  for (size_t i = 0; i < h.instances.size(); ++i) first[i + 1] = first[i] + h.instances[i].triangleCount;
+  instFirstTri = uploadVec(first);
+}
+
+DeviceSceneView SceneDevice::view(const SceneHost& h) const {
+  DeviceSceneView v;
+  v.geoInfo = geoInfo; v.materials = materials; v.puncLights = puncLights; v.trigLights = trigLights;
+  v.instances = instances; v.lightBufInfo = h.lightInfo;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// builder kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floatFlip(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float floatUnflip(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct BuildBounds { int lo[3]; int hi[3]; };
+
+__global__ void k_init_bounds(BuildBounds* b) {
+  for (int k = 0; k < 3; ++k) { b->lo[k] = floatFlip(3.0e38f); b->hi[k] = floatFlip(-3.0e38f); }
+}
+
+__global__ void k_emit_triangles(DeviceSceneView sc, const uint32_t* __restrict__ instFirst, uint32_t nInst, uint32_t nTri,
+                                 float4* __restrict__ triOut, float* __restrict__ boxLo, float* __restrict__ boxHi, BuildBounds* bounds) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (t < nTri) {
+    uint32_t a = 0, b = nInst;                       // instance owning triangle t (upper bound search)
+    while (b - a > 1) { uint32_t m = (a + b) >> 1; if (instFirst[m] <= t) a = m; else b = m; }
+    const InstanceXform& X = sc.instances[a];
+    const uint32_t prim = t - instFirst[a];
+    const InstanceData gi = sc.geoInfo[X.primMesh];
+    const uint32_t* idx = (const uint32_t*)(uintptr_t)gi.indexAddress;
+    const VertexAttributes* vtx = (const VertexAttributes*)(uintptr_t)gi.vertexAddress;
+    f3 p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = xfPoint(X.objectToWorld, ld3(vtx[idx[3 * prim + k]].position));
+    f3 e1 = p[1] - p[0], e2 = p[2] - p[0];
+    triOut[3 * (size_t)t + 0] = make_float4(p[0].x, p[0].y, p[0].z, e1.x);
+    triOut[3 * (size_t)t + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    triOut[3 * (size_t)t + 2] = make_float4(e2.z, __int_as_float((int)prim), __int_as_float((int)a),
+                                            __uint_as_float(X.flags & (INST_CULL_DISABLE | INST_MIRROR)));
+    lo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); hi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x));
+    lo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); hi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y));
+    lo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z)); hi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { boxLo[3 * (size_t)t + k] = lo[k]; boxHi[3 * (size_t)t + k] = hi[k]; }
+  }
+  // warp-reduce the bounds, one atomic per warp
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float l = lo[k], h = hi[k];
+    for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o)); h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&bounds->lo[k], floatFlip(l)); atomicMax(&bounds->hi[k], floatFlip(h)); }
+  }
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long v) {   // spread 21 bits to every 3rd bit
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+// pads every triangle box (conservative w.r.t. the fp32 Moller-Trumbore test) and computes its Morton key
+__global__ void k_morton(uint32_t nTri, float* __restrict__ boxLo, float* __restrict__ boxHi, const BuildBounds* bounds,
+                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nTri) return;
+  float sl[3], sh[3];
+  for (int k = 0; k < 3; ++k) { sl[k] = floatUnflip(bounds->lo[k]); sh[k] = floatUnflip(bounds->hi[k]); }
+  float ex = sh[0] - sl[0], ey = sh[1] - sl[1], ez = sh[2] - sl[2];
+  float diag = sqrtf(ex * ex + ey * ey + ez * ez);
+  float amax = fmaxf(fmaxf(fmaxf(fabsf(sl[0]), fabsf(sh[0])), fmaxf(fabsf(sl[1]), fabsf(sh[1]))), fmaxf(fabsf(sl[2]), fabsf(sh[2])));
+  const float pad = 1e-5f * diag + 4e-7f * amax + 1e-7f;
+  unsigned long long key = 0;
+  for (int k = 0; k < 3; ++k) {
+    float l = boxLo[3 * (size_t)t + k] - pad, h = boxHi[3 * (size_t)t + k] + pad;
+    boxLo[3 * (size_t)t + k] = l; boxHi[3 * (size_t)t + k] = h;
+    float e = sh[k] - sl[k];
+    float c = (e > 0.f) ? (0.5f * (l + h) - sl[k]) / e : 0.5f;
+    c = fminf(fmaxf(c, 0.f), 1.f);
+    unsigned long long q = (unsigned long long)fminf(c * 2097152.0f, 2097151.0f);
+    key |= expand21(q) << (2 - k);
+  }
+  keys[t] = key; vals[t] = t;
+}
+
+__global__ void k_reorder(uint32_t nTri, const uint32_t* __restrict__ order, const float4* __restrict__ triIn, const float* __restrict__ loIn,
+                          const float* __restrict__ hiIn, float4* __restrict__ triOut, float* __restrict__ loOut, float* __restrict__ hiOut) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nTri) return;
+  uint32_t s = order[t];
+  for (int k = 0; k < 3; ++k) { triOut[3 * (size_t)t + k] = triIn[3 * (size_t)s + k]; loOut[3 * (size_t)t + k] = loIn[3 * (size_t)s + k]; hiOut[3 * (size_t)t + k] = hiIn[3 * (size_t)s + k]; }
+}
+
+__device__ __forceinline__ int prefixLen(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+// Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees" (2012).
+// child encoding here: >= 0 inner node, < 0 leaf ~id
+__global__ void k_hierarchy(int n, const unsigned long long* __restrict__ keys, int* __restrict__ left, int* __restrict__ right,
+                            int* __restrict__ parentInner, int* __restrict__ parentLeaf, int* __restrict__ rangeFirst, int* __restrict__ rangeLast) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (prefixLen(keys, n, i, i + 1) - prefixLen(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = prefixLen(keys, n, i, i - d);
+  int lmax = 2;
+  while (prefixLen(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (prefixLen(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = prefixLen(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+    if (prefixLen(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  rangeFirst[i] = lo; rangeLast[i] = hi;
+  if (lo == gamma) { left[i] = ~gamma; parentLeaf[gamma] = i; } else { left[i] = gamma; parentInner[gamma] = i; }
+  if (hi == gamma + 1) { right[i] = ~(gamma + 1); parentLeaf[gamma + 1] = i; } else { right[i] = gamma + 1; parentInner[gamma + 1] = i; }
+  if (i == 0) parentInner[0] = -1;
+}
+
+__global__ void k_refit(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parentInner,
+                        const int* __restrict__ parentLeaf, const float* __restrict__ leafLo, const float* __restrict__ leafHi,
+                        float* nodeLo, float* nodeHi, int* height, unsigned int* __restrict__ arrived) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= n) return;
+  int node = parentLeaf[leaf];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&arrived[node], 1u) == 0u) return;   // first child to arrive stops; the second one owns both boxes
+    __threadfence();
+    float lo[3], hi[3];
+    int h = 0;
+    const int cs[2] = {left[node], right[node]};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const volatile float* cl; const volatile float* ch; int chh;
+      if (cs[c] < 0) { cl = leafLo + 3 * (size_t)(~cs[c]); ch = leafHi + 3 * (size_t)(~cs[c]); chh = 0; }
+      else { cl = nodeLo + 3 * (size_t)cs[c]; ch = nodeHi + 3 * (size_t)cs[c]; chh = ((volatile int*)height)[cs[c]]; }
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = c ? fminf(lo[k], cl[k]) : cl[k];
+        hi[k] = c ? fmaxf(hi[k], ch[k]) : ch[k];
+      }
+      h = max(h, chh);
+    }
+    for (int k = 0; k < 3; ++k) { nodeLo[3 * (size_t)node + k] = lo[k]; nodeHi[3 * (size_t)node + k] = hi[k]; }
+    height[node] = h + 1;
+    node = parentInner[node];
+  }
+}
+
+__global__ void k_pack_nodes(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rangeFirst,
+                             const int* __restrict__ rangeLast, const float* __restrict__ leafLo, const float* __restrict__ leafHi,
+                             const float* __restrict__ nodeLo, const float* __restrict__ nodeHi, float4* __restrict__ out, unsigned int* __restrict__ liveNodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int size = rangeLast[i] - rangeFirst[i] + 1;
+  if (i != 0 && size <= (int)LEAF_MAX) return;   // absorbed into a leaf of its parent
+  atomicAdd(liveNodes, 1u);
+  float b[2][6]; int ref[2];
+  const int cs[2] = {left[i], right[i]};
+  for (int c = 0; c < 2; ++c) {
+    if (cs[c] < 0) {
+      int l = ~cs[c];
+      for (int k = 0; k < 3; ++k) { b[c][k] = leafLo[3 * (size_t)l + k]; b[c][3 + k] = leafHi[3 * (size_t)l + k]; }
+      ref[c] = ~((l << 3) | 1);
+    } else {
+      int ch = cs[c];
+      for (int k = 0; k < 3; ++k) { b[c][k] = nodeLo[3 * (size_t)ch + k]; b[c][3 + k] = nodeHi[3 * (size_t)ch + k]; }
+      int csz = rangeLast[ch] - rangeFirst[ch] + 1;
+      ref[c] = (csz <= (int)LEAF_MAX) ? ~((rangeFirst[ch] << 3) | csz) : ch;
+    }
+  }
+  out[4 * (size_t)i + 0] = make_float4(b[0][0], b[0][1], b[0][2], b[0][3]);
+  out[4 * (size_t)i + 1] = make_float4(b[0][4], b[0][5], b[1][0], b[1][1]);
+  out[4 * (size_t)i + 2] = make_float4(b[1][2], b[1][3], b[1][4], b[1][5]);
+  out[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch ray query (parity tap for ClosestHit / AnyHit)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_trace_batch(AccelView A, const InstanceXform* __restrict__ instances, const float* __restrict__ rays, uint32_t n, int anyHit,
+                              eid_hit* __restrict__ hits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = rays + 8 * (size_t)i;
+  f3 o = mk3(r[0], r[1], r[2]), d = mk3(r[4], r[5], r[6]);
+  RayHit h;
+  eid_hit out;
+  if (anyHit) {
+    bool occ = traverse<true>(A, o, d, r[3], h);
+    out.hitT = occ ? 0.f : 1e28f; out.primitiveID = out.instanceID = out.instanceCustomIndex = -1; out.baryU = out.baryV = 0.f;
+  } else {
+    bool ok = traverse<false>(A, o, d, r[3], h);
+    if (ok) { out.hitT = h.t; out.primitiveID = h.prim; out.instanceID = h.inst; out.instanceCustomIndex = instances[h.inst].primMesh; out.baryU = h.u; out.baryV = h.v; }
+    else { out.hitT = 1e28f; out.primitiveID = out.instanceID = out.instanceCustomIndex = -1; out.baryU = out.baryV = 0.f; }
+  }
+  hits[i] = out;
+}
+
+static void buildAccel(eid_scene* s, eid_accel* a) {
+  const SceneHost& H = s->host;
+  CUDA_CHECK(cudaSetDevice(s->dev.device));
+  const uint32_t nTri = (uint32_t)H.triangleInstances;
+  a->scene = s; a->triCount = nTri;
+  cudaEvent_t ev0, ev1;
+  CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
+  CUDA_CHECK(cudaEventRecord(ev0, 0));
+  if (nTri == 0) {
+    CUDA_CHECK(cudaMalloc(&a->nodes, 64)); CUDA_CHECK(cudaMalloc(&a->tris, 48));
+    a->rootRef = ~0; a->nodeCount = 0; a->maxDepth = 0;   // empty leaf
+    CUDA_CHECK(cudaEventDestroy(ev0)); CUDA_CHECK(cudaEventDestroy(ev1));
+    return;
+  }
+  const int B = 256;
+  const uint32_t G = (nTri + B - 1) / B;
+  float4 *triTmp = nullptr; float *lo0 = nullptr, *hi0 = nullptr, *lo1 = nullptr, *hi1 = nullptr;
+  unsigned long long *keys = nullptr, *keysSorted = nullptr; uint32_t *vals = nullptr, *valsSorted = nullptr;
+  BuildBounds* bounds = nullptr;
+  int *left = nullptr, *right = nullptr, *parI = nullptr, *parL = nullptr, *rf = nullptr, *rl = nullptr, *height = nullptr;
+  float *nlo = nullptr, *nhi = nullptr; unsigned int *arrived = nullptr, *live = nullptr; void* tmp = nullptr;
+  auto freeAll = [&]() {
+    cudaFree(triTmp); cudaFree(lo0); cudaFree(hi0); cudaFree(lo1); cudaFree(hi1); cudaFree(keys); cudaFree(keysSorted); cudaFree(vals);
+    cudaFree(valsSorted); cudaFree(bounds); cudaFree(left); cudaFree(right); cudaFree(parI); cudaFree(parL); cudaFree(rf); cudaFree(rl);
+    cudaFree(height); cudaFree(nlo); cudaFree(nhi); cudaFree(arrived); cudaFree(live); cudaFree(tmp);
+  };
+  try {
+    CUDA_CHECK(cudaMalloc(&triTmp, (size_t)nTri * 48)); CUDA_CHECK(cudaMalloc(&a->tris, (size_t)nTri * 48));
+    CUDA_CHECK(cudaMalloc(&lo0, (size_t)nTri * 12)); CUDA_CHECK(cudaMalloc(&hi0, (size_t)nTri * 12));
+    CUDA_CHECK(cudaMalloc(&lo1, (size_t)nTri * 12)); CUDA_CHECK(cudaMalloc(&hi1, (size_t)nTri * 12));
+    CUDA_CHECK(cudaMalloc(&keys, (size_t)nTri * 8)); CUDA_CHECK(cudaMalloc(&keysSorted, (size_t)nTri * 8));
+    CUDA_CHECK(cudaMalloc(&vals, (size_t)nTri * 4)); CUDA_CHECK(cudaMalloc(&valsSorted, (size_t)nTri * 4));
+    CUDA_CHECK(cudaMalloc(&bounds, sizeof(BuildBounds)));
+    k_init_bounds<<<1, 1>>>(bounds);
+    k_emit_triangles<<<G, B>>>(s->dev.view(H), s->dev.instFirstTri, (uint32_t)H.instances.size(), nTri, triTmp, lo0, hi0, bounds);
+    k_morton<<<G, B>>>(nTri, lo0, hi0, bounds, keys, vals);
+    size_t tmpBytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
+    CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
+    k_reorder<<<G, B>>>(nTri, valsSorted, triTmp, lo0, hi0, a->tris, lo1, hi1);
+    const uint32_t nInner = nTri > 1 ? nTri - 1 : 1;
+    CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)nInner * 64));
+    CUDA_CHECK(cudaMemset(a->nodes, 0, (size_t)nInner * 64));
+    if (nTri == 1) {
+      // single triangle: a root node whose second child is an empty leaf
+      float hl[3], hh[3];
+      CUDA_CHECK(cudaMemcpy(hl, lo1, 12, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(hh, hi1, 12, cudaMemcpyDeviceToHost));
+      int r0 = ~((0 << 3) | 1), r1 = ~0;
+      float node[16] = {hl[0], hl[1], hl[2], hh[0], hh[1], hh[2], 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f, 0, 0, 0, 0};
+      memcpy(&node[12], &r0, 4); memcpy(&node[13], &r1, 4);
+      CUDA_CHECK(cudaMemcpy(a->nodes, node, 64, cudaMemcpyHostToDevice));
+      a->rootRef = 0; a->nodeCount = 1; a->maxDepth = 1;
+    } else {
+      CUDA_CHECK(cudaMalloc(&left, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&right, (size_t)nInner * 4));
+      CUDA_CHECK(cudaMalloc(&parI, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&parL, (size_t)nTri * 4));
+      CUDA_CHECK(cudaMalloc(&rf, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&rl, (size_t)nInner * 4));
+      CUDA_CHECK(cudaMalloc(&height, (size_t)nInner * 4));
+      CUDA_CHECK(cudaMalloc(&nlo, (size_t)nInner * 12)); CUDA_CHECK(cudaMalloc(&nhi, (size_t)nInner * 12));
+      CUDA_CHECK(cudaMalloc(&arrived, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&live, 4));
+      CUDA_CHECK(cudaMemset(arrived, 0, (size_t)nInner * 4)); CUDA_CHECK(cudaMemset(live, 0, 4));
+      k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)nTri, keysSorted, left, right, parI, parL, rf, rl);
+      k_refit<<<G, B>>>((int)nTri, left, right, parI, parL, lo1, hi1, nlo, nhi, height, arrived);
+      k_pack_nodes<<<(nInner + B - 1) / B, B>>>((int)nTri, left, right, rf, rl, lo1, hi1, nlo, nhi, a->nodes, live);
+      int rootHeight = 0; unsigned int liveNodes = 0;
+      CUDA_CHECK(cudaMemcpy(&rootHeight, height, 4, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(&liveNodes, live, 4, cudaMemcpyDeviceToHost));
+      a->rootRef = 0; a->nodeCount = liveNodes; a->maxDepth = (uint32_t)rootHeight;
+      if (rootHeight >= EID_STACK_SIZE) raise(EID_ERR_UNSUPPORTED, "BVH height %d exceeds the traversal stack (%d)", rootHeight, EID_STACK_SIZE);
+    }
+    CUDA_CHECK(cudaEventRecord(ev1, 0));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventElapsedTime(&a->buildMs, ev0, ev1));
+  } catch (...) {
+    freeAll(); cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    throw;
+  }
+  freeAll();
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+}
+
+}  // namespace eid
+
+using namespace eid;
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI: misc + Scene + AccelStructure
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* eid_last_error(void) { return eid::lastError().c_str(); }
+int eid_version(void) { return 100; }
+int eid_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int eid_scene_create(eid_scene** out, int device) {
+  EID_TRY
+  if (!out) raise(EID_ERR_INVALID, "eid_scene_create: out is null");
+  if (device != EID_DEVICE_NONE) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); raise(EID_ERR_CUDA, "no CUDA device is usable (libeidola has no CPU fallback)"); }
+    if (device < 0 || device >= n) raise(EID_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+  }
+  eid_scene* s = new eid_scene();
+  s->dev.device = device;
+  *out = s;
+  return EID_OK;
+  EID_CATCH
+}
+
+static int finishLoad(eid_scene* s) {
+  s->host.build();
+  if (s->host.hasNonOpaque)
+    raise(EID_ERR_UNSUPPORTED, "scene has alpha-tested/blended (non FORCE_OPAQUE) instances: stochastic alpha (traceray_rq.glsl:32-102) is not implemented yet");
+  for (const auto& m : s->host.materials)
+    if (m.pbrBaseColorTexture > -1 || m.pbrMetallicRoughnessTexture > -1 || m.emissiveTexture > -1 || m.normalTexture > -1 || m.transmissionTexture > -1)
+      raise(EID_ERR_UNSUPPORTED, "scene uses textures: texture taps (gltf_material.glsl:138-171) are not implemented yet");
+  if (s->dev.device != EID_DEVICE_NONE) s->dev.upload(s->host);
+  s->loaded = true;
+  return EID_OK;
+}
+
+int eid_scene_load_gltf(eid_scene* s, const char* path) {
+  EID_TRY
+  if (!s || !path) raise(EID_ERR_INVALID, "eid_scene_load_gltf: null argument");
+  s->loaded = false;
+  importGltfFile(path, s->host.gltf);
+  return finishLoad(s);
+  EID_CATCH
+}
+
+int eid_scene_load_desc(eid_scene* s, const eid_scene_desc* desc) {
+  EID_TRY
+  if (!s || !desc) raise(EID_ERR_INVALID, "eid_scene_load_desc: null argument");
+  s->loaded = false;
+  s->host.gltf = HostGltf();
+  s->host.gltf.fromDesc(*desc);
+  return finishLoad(s);
+  EID_CATCH
+}
+
+void eid_scene_destroy(eid_scene* s) {
+  if (!s) return;
+  s->dev.release();
+  delete s;
+}
+
+int eid_scene_set_lookat(eid_scene* s, const float eye[3], const float center[3], const float up[3], float fovDeg) {
+  EID_TRY
+  if (!s || !eye || !center || !up) raise(EID_ERR_INVALID, "eid_scene_set_lookat: null argument");
+  for (int i = 0; i < 3; ++i) { s->host.eye[i] = eye[i]; s->host.center[i] = center[i]; s->host.up[i] = up[i]; }
+  s->host.fovDeg = fovDeg;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_scene_update_camera(eid_scene* s, uint32_t w, uint32_t h) {
+  EID_TRY
+  if (!s || !w || !h) raise(EID_ERR_INVALID, "eid_scene_update_camera: bad argument");
+  s->host.updateCamera(w, h);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_scene_set_camera(eid_scene* s, const SceneCamera* cam) {
+  EID_TRY
+  if (!s || !cam) raise(EID_ERR_INVALID, "eid_scene_set_camera: null argument");
+  s->host.camera = *cam;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_scene_get_camera(eid_scene* s, SceneCamera* out) {
+  EID_TRY
+  if (!s || !out) raise(EID_ERR_INVALID, "eid_scene_get_camera: null argument");
+  *out = s->host.camera;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_scene_get_info(eid_scene* s, eid_scene_info* o) {
+  EID_TRY
+  if (!s || !o) raise(EID_ERR_INVALID, "eid_scene_get_info: null argument");
+  if (!s->loaded) raise(EID_ERR_STATE, "scene not loaded");
+  const SceneHost& H = s->host;
+  memset(o, 0, sizeof(*o));
+  o->primMeshCount = (uint32_t)H.gltf.primMeshes.size(); o->nodeCount = (uint32_t)H.gltf.nodes.size();
+  o->materialCount = (uint32_t)H.materials.size();
+  o->puncLightCount = H.lightInfo.puncLightSize; o->trigLightCount = H.lightInfo.trigLightSize;
+  o->vertexCount = (uint32_t)(H.gltf.positions.size() / 3); o->indexCount = (uint32_t)H.gltf.indices.size();
+  o->triangleInstances = H.triangleInstances;
+  o->trigLightWeight = H.trigLightWeight; o->puncLightWeight = H.puncLightWeight;
+  for (int i = 0; i < 3; ++i) { o->bboxMin[i] = H.gltf.bboxMin[i]; o->bboxMax[i] = H.gltf.bboxMax[i]; }
+  return EID_OK;
+  EID_CATCH
+}
+
+static const void* tableSource(eid_scene* s, int table, uint32_t index, size_t& bytes, bool& onDevice) {
+  const SceneHost& H = s->host;
+  onDevice = true;
+  if (s->dev.device == EID_DEVICE_NONE) {   // host-only scene: serve the host copies (InstanceData carries no addresses)
+    onDevice = false;
+    static thread_local std::vector<InstanceData> hostInst;
+    switch (table) {
+      case EID_TABLE_MATERIALS: bytes = H.materials.size() * sizeof(GltfShadeMaterial); return H.materials.data();
+      case EID_TABLE_PUNC_LIGHTS: bytes = H.puncLights.size() * sizeof(PuncLight); return H.puncLights.data();
+      case EID_TABLE_TRIG_LIGHTS: bytes = H.trigLights.size() * sizeof(TrigLight); return H.trigLights.data();
+      case EID_TABLE_LIGHT_INFO: bytes = sizeof(LightBufInfo); return &H.lightInfo;
+      case EID_TABLE_INSTANCE_DATA:
+        hostInst.assign(H.gltf.primMeshes.size(), InstanceData{});
+        for (size_t p = 0; p < hostInst.size(); ++p) hostInst[p].materialIndex = H.gltf.primMeshes[p].materialIndex;
+        bytes = hostInst.size() * sizeof(InstanceData); return hostInst.data();
+      case EID_TABLE_VERTICES:
+        if (index >= H.gltf.primMeshes.size()) return nullptr;
+        bytes = (size_t)H.gltf.primMeshes[index].vertexCount * sizeof(VertexAttributes); return H.vertices.data() + H.vtxBase[index];
+      case EID_TABLE_INDICES:
+        if (index >= H.gltf.primMeshes.size()) return nullptr;
+        bytes = (size_t)H.gltf.primMeshes[index].indexCount * 4; return H.indices.data() + H.idxBase[index];
+      case EID_TABLE_CAMERA: bytes = sizeof(SceneCamera); return &H.camera;
+      default: return nullptr;
+    }
+  }
+  switch (table) {
+    case EID_TABLE_MATERIALS: bytes = H.materials.size() * sizeof(GltfShadeMaterial); return s->dev.materials;
+    case EID_TABLE_PUNC_LIGHTS: bytes = H.puncLights.size() * sizeof(PuncLight); return s->dev.puncLights;
+    case EID_TABLE_TRIG_LIGHTS: bytes = H.trigLights.size() * sizeof(TrigLight); return s->dev.trigLights;
+    case EID_TABLE_LIGHT_INFO: onDevice = false; bytes = sizeof(LightBufInfo); return &H.lightInfo;
+    case EID_TABLE_INSTANCE_DATA: bytes = H.gltf.primMeshes.size() * sizeof(InstanceData); return s->dev.geoInfo;
+    case EID_TABLE_VERTICES:
+      if (index >= H.gltf.primMeshes.size()) return nullptr;
+      bytes = (size_t)H.gltf.primMeshes[index].vertexCount * sizeof(VertexAttributes); return s->dev.vertices + H.vtxBase[index];
+    case EID_TABLE_INDICES:
+      if (index >= H.gltf.primMeshes.size()) return nullptr;
+      bytes = (size_t)H.gltf.primMeshes[index].indexCount * 4; return s->dev.indices + H.idxBase[index];
+    case EID_TABLE_CAMERA: onDevice = false; bytes = sizeof(SceneCamera); return &H.camera;
+    default: return nullptr;
+  }
+}
+
+int64_t eid_scene_table_bytes(eid_scene* s, int table, uint32_t index) {
+  if (!s || !s->loaded) return -1;
+  size_t b = 0; bool dev;
+  return tableSource(s, table, index, b, dev) ? (int64_t)b : -1;
+}
+
+int eid_scene_read_table(eid_scene* s, int table, uint32_t index, void* dst, size_t bytes) {
+  EID_TRY
+  if (!s || !dst) raise(EID_ERR_INVALID, "eid_scene_read_table: null argument");
+  if (!s->loaded) raise(EID_ERR_STATE, "scene not loaded");
+  size_t b = 0; bool dev;
+  const void* src = tableSource(s, table, index, b, dev);
+  if (!src) raise(EID_ERR_INVALID, "no such table %d[%u]", table, index);
+  if (bytes > b) raise(EID_ERR_INVALID, "read of %zu bytes from a %zu-byte table", bytes, b);
+  if (dev) { CUDA_CHECK(cudaSetDevice(s->dev.device)); CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); }
+  else memcpy(dst, src, bytes);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_accel_build(eid_scene* s, eid_accel** out) {
+  EID_TRY
+  if (!s || !out) raise(EID_ERR_INVALID, "eid_accel_build: null argument");
+  if (!s->loaded) raise(EID_ERR_STATE, "eid_accel_build before a scene was loaded");
+  if (s->dev.device == EID_DEVICE_NONE) raise(EID_ERR_CUDA, "eid_accel_build on a host-only scene: the BVH build and every kernel need a CUDA device (no CPU fallback)");
+  eid_accel* a = new eid_accel();
+  try { buildAccel(s, a); }
+  catch (...) { cudaFree(a->nodes); cudaFree(a->tris); delete a; throw; }
+  *out = a;
+  return EID_OK;
+  EID_CATCH
+}
+
+void eid_accel_destroy(eid_accel* a) {
+  if (!a) return;
+  cudaFree(a->nodes); cudaFree(a->tris);
+  delete a;
+}
+
+int eid_accel_get_info(eid_accel* a, eid_accel_info* o) {
+  EID_TRY
+  if (!a || !o) raise(EID_ERR_INVALID, "eid_accel_get_info: null argument");
+  o->triangleCount = a->triCount; o->nodeCount = a->nodeCount; o->maxDepth = a->maxDepth;
+  o->nodeBytes = (uint64_t)std::max<uint32_t>(1u, a->triCount > 1 ? a->triCount - 1 : 1) * 64; o->triBytes = (uint64_t)a->triCount * 48;
+  o->buildMs = a->buildMs;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_accel_trace(eid_accel* a, const float* rays, uint32_t n, int any_hit, eid_hit* hits) {
+  EID_TRY
+  if (!a || !rays || !hits) raise(EID_ERR_INVALID, "eid_accel_trace: null argument");
+  if (n == 0) return EID_OK;
+  CUDA_CHECK(cudaSetDevice(a->scene->dev.device));
+  float* dr = nullptr; eid_hit* dh = nullptr;
+  CUDA_CHECK(cudaMalloc(&dr, (size_t)n * 32));
+  if (cudaMalloc(&dh, (size_t)n * sizeof(eid_hit)) != cudaSuccess) { cudaFree(dr); raise(EID_ERR_CUDA, "cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(dr, rays, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_trace_batch<<<(n + 127) / 128, 128>>>(a->view(), a->scene->dev.instances, dr, n, any_hit, dh);
+    e = cudaMemcpy(hits, dh, (size_t)n * sizeof(eid_hit), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dr); cudaFree(dh);
+  if (e != cudaSuccess) raise(EID_ERR_CUDA, "eid_accel_trace: %s", cudaGetErrorString(e));
+  return EID_OK;
+  EID_CATCH
+}
+
+}  // extern "C"

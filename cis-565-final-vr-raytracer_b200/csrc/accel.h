@@ -1,0 +1,64 @@
+// accel.h — device-resident scene + acceleration structure shared by accel.cu and render.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "scene_host.h"
+
+namespace eid {
+
+// What a kernel needs to shade: the reference's S_SCENE descriptor set (layouts.glsl:48-54).
+struct DeviceSceneView {
+  const InstanceData* geoInfo;          // per prim mesh: vertex/index device addresses + material
+  const GltfShadeMaterial* materials;
+  const PuncLight* puncLights;
+  const TrigLight* trigLights;
+  const InstanceXform* instances;       // per TLAS instance
+  LightBufInfo lightBufInfo;
+};
+
+// BVH2 node, 64 B = 4 x float4:
+//   q0 = lo0.xyz, hi0.x   q1 = hi0.yz, lo1.xy   q2 = lo1.z, hi1.xyz   q3 = child0, child1, -, -  (as int bits)
+// child >= 0: inner node index; child < 0: leaf, ~child = (firstTriangle << 3) | count  (count 0..4)
+// Triangle record, 48 B = 3 x float4 (world space, Moller-Trumbore ready):
+//   t0 = v0.xyz, e1.x   t1 = e1.yz, e2.xy   t2 = e2.z, primitiveID, instanceID, flags   (as int bits)
+struct AccelView {
+  const float4* nodes;
+  const float4* tris;
+  uint32_t triCount;
+  int32_t rootRef;      // child-style reference of the root
+};
+
+struct SceneDevice {
+  int device = 0;
+  VertexAttributes* vertices = nullptr;
+  uint32_t* indices = nullptr;
+  InstanceData* geoInfo = nullptr;
+  GltfShadeMaterial* materials = nullptr;
+  PuncLight* puncLights = nullptr;
+  TrigLight* trigLights = nullptr;
+  InstanceXform* instances = nullptr;
+  uint32_t* instFirstTri = nullptr;     // exclusive prefix of triangle counts per instance (+ total)
+  void upload(const SceneHost& h);
+  void release();
+  DeviceSceneView view(const SceneHost& h) const;
+};
+
+}  // namespace eid
+
+struct eid_scene {
+  eid::SceneHost host;
+  eid::SceneDevice dev;
+  bool loaded = false;
+};
+
+struct eid_accel {
+  eid_scene* scene = nullptr;
+  float4* nodes = nullptr;
+  float4* tris = nullptr;
+  uint32_t triCount = 0;
+  uint32_t nodeCount = 0;
+  uint32_t maxDepth = 0;
+  int32_t rootRef = -1;
+  float buildMs = 0.f;
+  eid::AccelView view() const { return eid::AccelView{nodes, tris, triCount, rootRef}; }
+};

@@ -1,0 +1,854 @@
+// render.cu — the per-frame render loop: CUDA kernels for the five live compute shaders of the reference
+// and the Renderer object that owns their buffers and launch schedule.
+//
+//   k_direct_stage      shaders/direct_stage.comp    primary ray, G-buffer, motion index, RIS over M light
+//                                                    candidates, shadow ray, temporal reservoir merge, shade
+//   k_indirect_stage    shaders/indirect_stage.comp  quarter-res ReSTIR GI: BSDF-sampled path (NEE+MIS from
+//                                                    depth 2), per-8x8-tile multibounce lottery, temporal reuse
+//   k_denoise<false>    shaders/denoise_direct.comp  A-Trous level 0..3 (one launch per level)
+//   k_denoise<true>     shaders/denoise_indirect.comp A-Trous level 0..4 at quarter res
+//   k_compose           shaders/compose.comp         re-modulate by albedo, 2x nearest upsample of indirect
+//
+// Renderer::run (src/renderer.cpp:154-206) = strict stream order of the above: 1 + 1 + 4 + 5 + 1 launches.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "accel.h"
+#include "common.h"
+#include "shade.cuh"
+
+namespace eid {
+
+struct FrameParams {
+  RtxState st;
+  SceneCamera cam;
+  DeviceSceneView sc;
+  AccelView accel;
+  uint4* thisG; const uint4* lastG;
+  short2* motion;
+  float* thisDR; const float* lastDR;     // DirectReservoir records, 9 floats each, pitch st.size.x
+  float* thisIR; const float* lastIR;     // IndirectReservoir records, 19 floats each, pitch st.size.x/2
+  float4* directImg; float4* indirectImg;
+  float4* dirA; float4* dirB; float4* indA; float4* indB;
+  float env[3];
+  int pitch, allocH;                      // allocation size of the 2-D images
+  int y0, y1;                             // full-res row band traced by this rank
+  unsigned long long* counters;           // [0] closest-hit rays, [1] any-hit rays, [2] primary hits
+};
+
+struct RayCounters { unsigned int closest, any, primary; };
+
+DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
+  unsigned int a = c.closest, b = c.any, d = c.primary;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) {
+    if (a) atomicAdd(&P.counters[0], (unsigned long long)a);
+    if (b) atomicAdd(&P.counters[1], (unsigned long long)b);
+    if (d) atomicAdd(&P.counters[2], (unsigned long long)d);
+  }
+}
+
+// image access: out-of-bounds loads return 0 (Vulkan robust image access), stores are dropped
+DEV uint4 loadG(const uint4* img, const FrameParams& P, int x, int y) {
+  if (x < 0 || y < 0 || x >= P.pitch || y >= P.allocH) return make_uint4(0, 0, 0, 0);
+  return __ldg(img + (size_t)y * P.pitch + x);
+}
+DEV float4 loadImg(const float4* img, const FrameParams& P, int x, int y) {
+  if (x < 0 || y < 0 || x >= P.pitch || y >= P.allocH) return make_float4(0, 0, 0, 0);
+  return img[(size_t)y * P.pitch + x];
+}
+
+// ClosestHit (traceray_rq.glsl:108-147) on opaque geometry
+DEV bool closestHit(const FrameParams& P, f3 o, f3 d, Payload& prd, RayCounters& rc) {
+  rc.closest++;
+  RayHit h;
+  if (!traverse<false>(P.accel, o, d, EID_INFINITY, h)) { prd.hitT = EID_INFINITY; return false; }
+  prd.hitT = h.t; prd.baryU = h.u; prd.baryV = h.v; prd.primitiveID = h.prim; prd.instanceID = h.inst;
+  prd.instanceCustomIndex = P.sc.instances[h.inst].primMesh;
+  return true;
+}
+// Occlusion (pathtrace.glsl:18-22) -> AnyHit (traceray_rq.glsl:153-185)
+DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float dist, RayCounters& rc) {
+  rc.any++;
+  float tmax = __fsub_rn(__fsub_rn(__fsub_rn(dist, fabsf(__fsub_rn(origin.x, surfacePos.x))), fabsf(__fsub_rn(origin.y, surfacePos.y))),
+                         fabsf(__fsub_rn(origin.z, surfacePos.z)));
+  RayHit h;
+  return traverse<true>(P.accel, origin, dir, tmax, h);
+}
+
+DEV f3 envRadiance(const FrameParams& P) { return mk3(P.env[0], P.env[1], P.env[2]) * P.st.hdrMultiplier; }   // pathtrace.glsl:40-47, constant env
+
+// encodeGeometryInfo (direct_stage.comp:37-45)
+DEV uint4 encodeGeometryInfo(const State& s, float depth) {
+  uint4 g;
+  g.x = __float_as_uint(depth);
+  g.y = octEncode(s.normal.x, s.normal.y, s.normal.z);
+  g.z = packUnorm4(s.mat.metallic, s.mat.roughness, __fdiv_rn(__fsub_rn(s.mat.ior, 1.0f), MAX_IOR_MINUS_ONE), s.mat.transmission);
+  g.w = (packUnorm4(s.mat.albedo.x, s.mat.albedo.y, s.mat.albedo.z, 1.0f) & 0xFFFFFFu) + hash8(s.matID);
+  return g;
+}
+
+DEV void loadDResv(const float* base, size_t i, DResv& r) {
+  const float* p = base + 9 * i;
+  r.Li = mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); r.wi = mk3(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5));
+  r.dist = __ldg(p + 6); r.num = __float_as_uint(__ldg(p + 7)); r.weight = __ldg(p + 8);
+}
+DEV void storeDResv(float* base, size_t i, const DResv& r) {
+  float* p = base + 9 * i;
+  p[0] = r.Li.x; p[1] = r.Li.y; p[2] = r.Li.z; p[3] = r.wi.x; p[4] = r.wi.y; p[5] = r.wi.z; p[6] = r.dist; p[7] = __uint_as_float(r.num); p[8] = r.weight;
+}
+
+// =================================================================================================
+// K1 — direct_stage.comp
+// =================================================================================================
+__global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = P.y0 + blockIdx.y * 8 + threadIdx.y;
+  RayCounters rc = {0, 0, 0};
+  const int W = P.st.size.x, H = P.st.size.y;
+  if (x < W && y < H && y < P.y1) {
+    uint32_t seed = tea((uint32_t)W * (uint32_t)y + (uint32_t)x, P.st.time);   // :279
+    f3 ro, rd;
+    raySpawn<true>(P.cam, x, y, W, H, ro, rd);
+    const size_t pix = (size_t)y * P.pitch + x;
+    f3 radiance;
+    Payload prd;
+    if (!closestHit(P, ro, rd, prd, rc)) {                 // :154-158
+      P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
+      P.motion[pix] = make_short2(0, 0);
+      radiance = envRadiance(P);
+    } else {
+      rc.primary++;
+      State st = getState(P.sc, prd, rd);
+      getMaterials(P.sc, st);
+      // createMotionIndex (:125-139)
+      float pr[4];
+      mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
+      const float mvx = __fadd_rn(__fmul_rn(__fdiv_rn(pr[0], pr[3]), 0.5f), 0.5f), mvy = __fadd_rn(__fmul_rn(__fdiv_rn(pr[1], pr[3]), 0.5f), 0.5f);
+      const int mix_ = f2i_sat(__fmul_rn(mvx, (float)W)), miy = f2i_sat(__fmul_rn(mvy, (float)H));
+      P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
+      P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
+
+      if (P.st.debugging_mode > eIndirectStage) {          // DebugInfo (pathtrace.glsl:362-380)
+        switch (P.st.debugging_mode) {
+          case eMetallic: radiance = mk3(st.mat.metallic); break;
+          case eNormal: radiance = (st.normal + mk3(1.0f)) * .5f; break;
+          case eDepth: radiance = mk3(0.0f); break;
+          case eBaseColor: radiance = st.mat.albedo; break;
+          case eEmissive: radiance = st.mat.emission; break;
+          case eRoughness: radiance = mk3(st.mat.roughness); break;
+          case eTexcoord: radiance = mk3(st.u, st.v, 0.f); break;
+          default: radiance = mk3(1000.f, 0.f, 0.f);
+        }
+      } else if (st.isEmitter) {
+        radiance = st.mat.emission;                        // :172-174
+      } else {
+        const f3 wo = -rd;
+        f3 direct = mk3(0.0f);
+        const f3 one = mk3(1.0f);                          // state.mat.albedo = vec3(1.0) (:178-179)
+        const f3 shadowOrigin = offsetRay(st.position, st.ffnormal);
+        if (P.st.ReSTIRState == eNone) {                   // DirectLight (pathtrace.glsl:204-220)
+          LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+          float pdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+          if (!isPdfInvalid(pdf) && !occlusion(P, shadowOrigin, ls.wi, st.position, ls.dist, rc))
+            direct = ((ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * gmax(dot3(st.ffnormal, ls.wi), 0.0f)) / pdf;
+        } else {
+          DResv resv; resv.Li = mk3(0.f); resv.wi = mk3(0.f); resv.dist = 0.f; resv.num = 0; resv.weight = 0.f;
+          for (int i = 0; i < P.st.RISSampleNum; i++) {    // :188-199
+            LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+            float p = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+            f3 pHat = (ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * fabsf(dot3(st.ffnormal, ls.wi));
+            float weight = lum3(pHat / p);
+            if (isPdfInvalid(p) || weight != weight) weight = 0.0f;
+            resvUpdate(resv, ls.Li, ls.wi, ls.dist, weight, rnd(seed));
+          }
+          if (occlusion(P, shadowOrigin, resv.wi, st.position, resv.dist, rc)) resv.weight = 0.0f;   // :200-207
+
+          if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // :209-217, findTemporalNeighbor :47-84
+            const float reprojDepth = len3(ld3(P.cam.lastPosition) - st.position);
+            if (mix_ >= 2 && mix_ < W && miy >= 0 && miy < H) {
+              const uint4 gl = loadG(P.lastG, P, mix_, miy);
+              const f3 pnorm = octDecode(gl.y);
+              const float pdepth = __uint_as_float(gl.x);
+              if (hash8(st.matID) == (gl.w & 0xFF000000u) && dot3(st.normal, pnorm) > 0.9f && reprojDepth < __fmul_rn(pdepth, 1.05f)) {
+                DResv t;
+                loadDResv(P.lastDR, (size_t)miy * W + mix_, t);
+                if (!resvInvalidW(t.weight)) {             // resvMerge (reservoir.glsl:69-75)
+                  const float rv = rnd(seed);
+                  resv.weight = __fadd_rn(resv.weight, t.weight);
+                  resv.num += t.num;
+                  if (__fmul_rn(rv, resv.weight) < t.weight) { resv.Li = t.Li; resv.wi = t.wi; resv.dist = t.dist; }
+                }
+              }
+            }
+          }
+          {                                                // :219-222 stored copy: validity check + clamp
+            DResv tmp = resv;
+            if (resvInvalidW(tmp.weight)) { tmp.num = 0; tmp.weight = 0.f; }
+            const int clampN = P.st.RISSampleNum * P.st.reservoirClamp;
+            if (tmp.num > (uint32_t)clampN) { tmp.weight = __fmul_rn(tmp.weight, __fdiv_rn((float)clampN, (float)tmp.num)); tmp.num = (uint32_t)clampN; }
+            storeDResv(P.thisDR, (size_t)y * W + x, tmp);
+          }
+          if (!resvInvalidW(resv.weight)) {                // :256-261 — shading uses the un-clamped reservoir
+            f3 LiBsdf = resv.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, resv.wi);
+            direct = ((LiBsdf / lum3(LiBsdf)) * resv.weight) / (float)resv.num;
+          }
+        }
+        if (nan3(direct)) direct = mk3(0.0f);
+        radiance = hdrToLdr(clampRadiance(st.mat.emission + direct, P.st.fireflyClampThreshold));
+      }
+    }
+    const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);   // :283
+    P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+  }
+  flushCounters(P, rc);
+}
+
+// =================================================================================================
+// K2 — indirect_stage.comp
+// =================================================================================================
+struct GISampleD { f3 L, xv, nv, xs, ns; float pHat; };
+
+DEV float misWeight(const FrameParams& P, float f, float g) { return (P.st.MIS > 0) ? powerHeuristic(f, g) : 1.0f; }   // :59-61
+DEV bool giSampleValid(const GISampleD& g) { return g.nv.x < 1.1f && !nan3(g.L); }                                       // :117-119
+
+DEV void loadIResv(const float* base, size_t i, GISampleD& g, uint32_t& num, float& weight, float& bigW) {
+  const float* p = base + 19 * i;
+  g.L = mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); g.xv = mk3(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)); g.nv = mk3(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8));
+  g.xs = mk3(__ldg(p + 9), __ldg(p + 10), __ldg(p + 11)); g.ns = mk3(__ldg(p + 12), __ldg(p + 13), __ldg(p + 14)); g.pHat = __ldg(p + 15);
+  num = __float_as_uint(__ldg(p + 16)); weight = __ldg(p + 17); bigW = __ldg(p + 18);
+}
+DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, float weight, float bigW) {
+  float* p = base + 19 * i;
+  p[0] = g.L.x; p[1] = g.L.y; p[2] = g.L.z; p[3] = g.xv.x; p[4] = g.xv.y; p[5] = g.xv.z; p[6] = g.nv.x; p[7] = g.nv.y; p[8] = g.nv.z;
+  p[9] = g.xs.x; p[10] = g.xs.y; p[11] = g.xs.z; p[12] = g.ns.x; p[13] = g.ns.y; p[14] = g.ns.z; p[15] = g.pHat;
+  p[16] = __uint_as_float(num); p[17] = weight; p[18] = bigW;
+}
+
+__global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = P.y0 / 2 + blockIdx.y * 8 + threadIdx.y;
+  RayCounters rc = {0, 0, 0};
+  const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
+  if (x < Wi && y < Hi && y < P.y1 / 2) {
+    uint32_t seed = tea((uint32_t)Wi * (uint32_t)y + (uint32_t)x, P.st.time);   // :280
+    f3 ro, rd;
+    raySpawn<true>(P.cam, x, y, Wi, Hi, ro, rd);
+    // TILED_MULTIBOUNCE (:283-288): invocation (0,0) of each 8x8 group draws once, the flag is group-wide.
+    // Every thread re-derives that draw from the tile origin's seed instead of a shared variable + barrier.
+    bool multiBounce;
+    if (threadIdx.x == 0 && threadIdx.y == 0) multiBounce = rnd(seed) < 0.25f;
+    else {
+      uint32_t s0 = tea((uint32_t)Wi * (uint32_t)(y - (int)threadIdx.y) + (uint32_t)(x - (int)threadIdx.x), P.st.time);
+      multiBounce = rnd(s0) < 0.25f;
+    }
+    const size_t opix = (size_t)y * P.pitch + x;
+    // getIndirectStateFromGBuffer (pathtrace.glsl:296-313) at full-res pixel 2*coord
+    const uint4 gi = loadG(P.thisG, P, 2 * x, 2 * y);
+    const float depth = __uint_as_float(gi.x);
+    if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) {
+      P.indA[opix] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
+    } else {
+      State st;
+      st.position = ro + rd * depth;
+      st.normal = octDecode(gi.y);
+      st.ffnormal = dot3(st.normal, rd) <= 0.0f ? st.normal : -st.normal;
+      st.mat.albedo = mk3(unormToFloat(gi.w & 0xffu), unormToFloat((gi.w >> 8) & 0xffu), unormToFloat((gi.w >> 16) & 0xffu));
+      st.mat.metallic = unormToFloat(gi.z & 0xffu);
+      st.mat.roughness = unormToFloat((gi.z >> 8) & 0xffu);
+      st.mat.ior = __fadd_rn(__fmul_rn(unormToFloat((gi.z >> 16) & 0xffu), MAX_IOR_MINUS_ONE), 1.f);
+      st.mat.transmission = unormToFloat(gi.z >> 24);
+      st.mat.emission = mk3(0.f);
+      st.matID = gi.w >> 24;                                // hashed material id
+      st.isEmitter = false; st.area = 0.f; st.eta = 0.f; st.u = st.v = 0.f;
+      st.position = st.position + st.ffnormal * 2e-2f;      // :299
+
+      // ---- pathTraceIndirect (:129-226)
+      const f3 primWo = -rd;
+      const f3 primPos = st.position, primFfn = st.ffnormal;
+      const float primRough = st.mat.roughness, primMetal = st.mat.metallic;
+      const uint32_t primMatHash = st.matID;
+      float primSamplePdf = 0.f;
+      GISampleD gs; gs.L = mk3(0.f); gs.nv = mk3(100.0f); gs.xv = mk3(0.f); gs.xs = mk3(0.f); gs.ns = mk3(0.f); gs.pHat = 0.f;   // newGISample :110-115
+      f3 throughput = mk3(multiBounce ? 4.0f : 1.0f);
+      st.mat.albedo = mk3(1.0f);
+      f3 rayO = ro, rayD = rd;
+      for (int d = 1; d <= P.st.maxDepth; d++) {
+        const f3 wo = -rayD;
+        if (d > 1 && P.st.MIS > 0) {                        // SampleDirectLight (pathtrace.glsl:185-202)
+          LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+          float lightPdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+          if (!isPdfInvalid(lightPdf)) {
+            if (occlusion(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, rc)) lightPdf = EID_INVALID_PDF;
+          } else lightPdf = EID_INVALID_PDF;
+          if (!isPdfInvalid(lightPdf)) {
+            float bp = bsdfPdf(st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi);
+            float w = misWeight(P, lightPdf, bp);
+            gs.L = gs.L + ((((ls.Li * bsdfEval(st.mat.albedo, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * absDot(st.ffnormal, ls.wi)) * throughput) / lightPdf) * w;
+          }
+        }
+        f3 sampleWi, sampleBSDF;
+        const float samplePdf = bsdfSample(st, st.ffnormal, wo, seed, sampleBSDF, sampleWi);
+        if (isPdfInvalid(samplePdf)) break;
+        if (d > 1) {
+          if (!multiBounce) break;                          // `return` at :164-166 — nothing follows the loop
+          throughput = throughput * ((sampleBSDF / samplePdf) * absDot(st.ffnormal, sampleWi));
+        } else {
+          primSamplePdf = samplePdf;
+          gs.xv = st.position;
+          gs.nv = st.ffnormal;
+        }
+        rayO = offsetRay(st.position, st.ffnormal);
+        rayD = sampleWi;
+        Payload prd;
+        closestHit(P, rayO, rayD, prd, rc);
+        if (prd.hitT >= __fsub_rn(EID_INFINITY, 1e-4f)) {   // miss (:183-198)
+          if (d > 1) {
+            const f3 env = mk3(P.env[0], P.env[1], P.env[2]);                 // EnvEval (pathtrace.glsl:60-72), constant env
+            const float lightPdf = __fmul_rn(__fmul_rn(lum3(env), P.st.envMapLuminIntegInv), P.st.environmentProb);
+            gs.L = gs.L + (env * throughput) * misWeight(P, samplePdf, lightPdf);
+          } else {
+            gs.xs = st.position + (sampleWi * EID_INFINITY) * 0.8f;
+            gs.ns = -sampleWi;
+          }
+          break;
+        }
+        st = getState(P.sc, prd, rayD);
+        getMaterials(P.sc, st);
+        if (st.isEmitter) {                                 // :203-215, LightEval (pathtrace.glsl:74-88)
+          if (d > 1) {
+            const float lightProb = __fsub_rn(1.0f, P.st.environmentProb);
+            float lightPdf = __fmul_rn(__fmul_rn(lum3(st.mat.emission), P.st.lightLuminIntegInv), lightProb);
+            lightPdf = __fmul_rn(lightPdf, __fdiv_rn(__fmul_rn(prd.hitT, prd.hitT), absDot(st.ffnormal, sampleWi)));
+            const f3 Li = st.mat.emission / st.area;
+            gs.L = gs.L + (Li * throughput) * misWeight(P, samplePdf, lightPdf);
+          } else {
+            gs.xs = st.position;
+            gs.ns = st.ffnormal;
+          }
+          break;
+        }
+        if (d == 1) { gs.xs = st.position; gs.ns = st.ffnormal; }
+      }
+
+      // ---- ReSTIRIndirect (:228-268)
+      GISampleD rs; rs.L = mk3(0.f); rs.xv = mk3(0.f); rs.nv = mk3(0.f); rs.xs = mk3(0.f); rs.ns = mk3(0.f); rs.pHat = 0.f;
+      uint32_t rnum = 0; float rweight = 0.f, rbigW = 0.f;
+      if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // findTemporalNeighbor :74-108
+        const float reprojDepth = len3(ld3(P.cam.lastPosition) - primPos);
+        short2 mv = make_short2(0, 0);
+        if (2 * x < P.pitch && 2 * y < P.allocH) mv = P.motion[(size_t)(2 * y) * P.pitch + 2 * x];
+        const uint4 gl = loadG(P.lastG, P, mv.x, mv.y);
+        const f3 pnorm = octDecode(gl.y);
+        const float pdepth = __uint_as_float(gl.x);
+        const int cx = mv.x / 2, cy = mv.y / 2;
+        if (cx >= 0 && cx < Wi && cy >= 0 && cy < Hi && hash8(primMatHash) == (gl.w & 0xFF000000u) && dot3(primFfn, pnorm) > 0.5f &&
+            reprojDepth < __fmul_rn(pdepth, 1.1f))
+          loadIResv(P.lastIR, (size_t)cy * Wi + cx, rs, rnum, rweight, rbigW);
+      }
+      float sampleWeight = 0.0f;
+      if (giSampleValid(gs)) {
+        gs.pHat = lum3(gs.L);                               // pHatIndirect :63-64
+        sampleWeight = __fdiv_rn(gs.pHat, primSamplePdf);
+        if (sampleWeight != sampleWeight || sampleWeight < 0.0f) sampleWeight = 0.0f;
+      }
+      {                                                     // resvUpdate (reservoir.glsl:55-61)
+        const float rv = rnd(seed);
+        rweight = __fadd_rn(rweight, sampleWeight);
+        rnum += 1;
+        if (__fmul_rn(rv, rweight) < sampleWeight) rs = gs;
+      }
+      if (resvInvalidW(rweight)) { rnum = 0; rweight = 0.f; rbigW = 0.f; }
+      const int clampN = P.st.reservoirClamp * 2;
+      if (rnum > (uint32_t)clampN) { rweight = __fmul_rn(rweight, __fdiv_rn((float)clampN, (float)rnum)); rnum = (uint32_t)clampN; }
+      storeIResv(P.thisIR, (size_t)y * Wi + x, rs, rnum, rweight, rbigW);
+
+      f3 indirect = mk3(0.0f);
+      if (!resvInvalidW(rweight) && giSampleValid(rs)) {
+        const f3 primWi = norm3(rs.xs - rs.xv);
+        const float bigW = __fdiv_rn(rweight, __fmul_rn(lum3(rs.L), (float)rnum));   // bigWIndirect :70-72
+        indirect = ((rs.L * bsdfEval(mk3(1.0f), primRough, primMetal, rs.nv, primWo, primWi)) * satDot(rs.nv, primWi)) * bigW;
+      }
+      f3 res = hdrToLdr(clampRadiance(indirect, P.st.fireflyClampThreshold));
+      res = clampRadiance(res, P.st.fireflyClampThreshold);
+      P.indA[opix] = make_float4(res.x, res.y, res.z, 1.0f);
+    }
+  }
+  flushCounters(P, rc);
+}
+
+// =================================================================================================
+// K3 / K4 — denoise_direct.comp / denoise_indirect.comp (edge-avoiding A-Trous, one level per launch)
+// =================================================================================================
+__constant__ float c_gauss5x5[25] = {.0030f, .0133f, .0219f, .0133f, .0030f, .0133f, .0596f, .0983f, .0596f, .0133f, .0219f, .0983f, .1621f,
+                                     .0983f, .0219f, .0133f, .0596f, .0983f, .0596f, .0133f, .0030f, .0133f, .0219f, .0133f, .0030f};
+
+// loadThisGeometry (denoise_common.glsl:42-47): normal, camera-ray position, material hash of G-buffer texel (gx,gy);
+// the camera ray is spawned for pixel (gx,gy) of an image of size (sw,sh) — the indirect pass passes the half-res size
+// together with full-res coordinates (reference quirk, kept).
+DEV void loadThisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, f3& normal, f3& pos, uint32_t& matHash) {
+  const uint4 g = loadG(P.thisG, P, gx, gy);
+  normal = octDecode(g.y);
+  f3 o, d;
+  raySpawn<false>(P.cam, gx, gy, sw, sh, o, d);
+  pos = o + d * __uint_as_float(g.x);
+  matHash = g.w & 0xFF000000u;
+}
+
+template <bool INDIRECT>
+__global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
+  if (x >= bw || y >= bh) return;
+  const int gs = INDIRECT ? 2 : 1;
+  const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
+  const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
+  const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
+  f3 norm, pos; uint32_t matHash;
+  loadThisGeometry(P, x * gs, y * gs, bw, bh, norm, pos, matHash);
+  f3 res = mk3(0.0f);
+  if (matHash != EID_INVALID_MAT) {                        // waveletFilter (denoise_direct.comp:19-71 / denoise_indirect.comp:23-75)
+    const int step = 1 << level;
+    f3 sum = mk3(0.0f);
+    float sumW = 0.0f;
+    const float4 c4 = loadImg(inImg, P, x, y);
+    const f3 color = mk3(c4.x, c4.y, c4.z);
+    const float lumC = lum3(color);
+    for (int j = -2; j <= 2; j++) {
+      for (int i = -2; i <= 2; i++) {
+        const int qx = x + i * step, qy = y + j * step;
+        if (qx >= bw || qy >= bh || qx < 0 || qy < 0) continue;
+        f3 nq, pq; uint32_t hq;
+        loadThisGeometry(P, qx * gs, qy * gs, bw, bh, nq, pq, hq);
+        const float4 q4 = loadImg(inImg, P, qx, qy);
+        const f3 cq = mk3(q4.x, q4.y, q4.z);
+        if (matHash != hq || hq == EID_INVALID_MAT) continue;
+        float distColor;
+        if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
+        else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
+        const float wColor = __fadd_rn(eid_expf(__fdiv_rn(-distColor, sigL)), 1e-2f);
+        const f3 dn = norm - nq;
+        const float wNorm = gmin(1.0f, eid_expf(__fdiv_rn(-dot3(dn, dn), sigN)));
+        const f3 dp = pos - pq;
+        const float wDepth = __fadd_rn(eid_expf(__fdiv_rn(-dot3(dp, dp), sigD)), 1e-2f);
+        const float w = __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), c_gauss5x5[(i + 2) * 5 + (j + 2)]);
+        sum = sum + cq * w;
+        sumW = __fadd_rn(sumW, w);
+      }
+    }
+    res = (sumW < 1e-5f) ? mk3(0.0f) : sum / sumW;
+    if (nan3(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = mk3(0.0f);
+  }
+  if (level == lastLevel) res = ldrToHdr(res);             // denoise_direct.comp:168 / denoise_indirect.comp:169
+  outImg[(size_t)y * P.pitch + x] = make_float4(res.x, res.y, res.z, 1.0f);
+}
+
+// =================================================================================================
+// K5 — compose.comp:23-42
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_compose(const FrameParams P, const float4* __restrict__ indSrc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= P.st.size.x || y >= P.st.size.y) return;
+  const size_t pix = (size_t)y * P.pitch + x;
+  const float4 ind = loadImg(indSrc, P, x / 2, y / 2);
+  if (P.st.modulate == 0) {
+    P.indirectImg[pix] = ind;
+  } else {
+    const uint32_t gw = loadG(P.thisG, P, x, y).w;
+    const f3 albedo = mk3(unormToFloat(gw & 0xffu), unormToFloat((gw >> 8) & 0xffu), unormToFloat((gw >> 16) & 0xffu));
+    const float4 d4 = P.directImg[pix];
+    const f3 d = mk3(d4.x, d4.y, d4.z) * albedo, i = mk3(ind.x, ind.y, ind.z) * albedo;
+    P.directImg[pix] = make_float4(d.x, d.y, d.z, 1.0f);
+    P.indirectImg[pix] = make_float4(i.x, i.y, i.z, 1.0f);
+  }
+}
+
+}  // namespace eid
+
+using namespace eid;
+
+// ------------------------------------------------------------------------------------------------
+// Renderer object
+// ------------------------------------------------------------------------------------------------
+struct eid_renderer {
+  eid_scene* scene = nullptr;
+  eid_accel* accel = nullptr;
+  int device = 0;
+  uint32_t width = 0, height = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  uint4* gbuffer[2] = {nullptr, nullptr};
+  short2* motion = nullptr;
+  float* directResv[2] = {nullptr, nullptr};
+  float* indirectResv[2] = {nullptr, nullptr};
+  float4* directImg = nullptr; float4* indirectImg = nullptr;
+  float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long* counters = nullptr;
+  unsigned long long* countersHost = nullptr;   // pinned
+  float env[3] = {0.f, 0.f, 0.f};
+  int lastSet = 0;
+  RtxState lastState{};
+  bool hasRun = false;
+  uint32_t bandY0 = 0, bandY1 = 0; bool bandSet = false;
+  bool profiling = false;
+  cudaEvent_t ev[EID_K_COUNT + 1] = {};
+  eid_frame_stats stats{};
+  bool statsPending = false;
+
+  void allocate();
+  void release();
+};
+
+void eid_renderer::release() {
+  for (int i = 0; i < 2; ++i) { cudaFree(gbuffer[i]); cudaFree(directResv[i]); cudaFree(indirectResv[i]); gbuffer[i] = nullptr; directResv[i] = nullptr; indirectResv[i] = nullptr; }
+  cudaFree(motion); motion = nullptr;
+  cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
+  for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
+}
+
+// Renderer::createBuffer / createImage (renderer.cpp:227-302): 2 G-buffers, 1 motion image, 2+2 reservoir buffers,
+// 4 denoise temporaries, 2 result images — all zero-initialised (the reference leaves them undefined).
+void eid_renderer::allocate() {
+  const size_t n = (size_t)width * height, ni = (size_t)(width / 2) * (height / 2);
+  auto zalloc = [&](void** p, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 16);
+    CUDA_CHECK(cudaMalloc(p, bytes));
+    CUDA_CHECK(cudaMemsetAsync(*p, 0, bytes, stream));
+  };
+  for (int i = 0; i < 2; ++i) {
+    zalloc((void**)&gbuffer[i], n * 16);
+    zalloc((void**)&directResv[i], n * sizeof(DirectReservoir));
+    zalloc((void**)&indirectResv[i], ni * sizeof(IndirectReservoir));
+  }
+  zalloc((void**)&motion, n * 4);
+  zalloc((void**)&directImg, n * 16); zalloc((void**)&indirectImg, n * 16);
+  for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16);
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  hasRun = false; lastSet = 0;
+  if (!bandSet) { bandY0 = 0; bandY1 = height; }
+}
+
+static void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
+  if (st.size.x <= 0 || st.size.y <= 0 || (uint32_t)st.size.x > r->width || (uint32_t)st.size.y > r->height)
+    raise(EID_ERR_INVALID, "RtxState.size %dx%d outside the renderer allocation %ux%u", st.size.x, st.size.y, r->width, r->height);
+  if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal)
+    raise(EID_ERR_UNSUPPORTED, "spatial reuse (direct_stage.comp:224-255) is racy in the reference and outside the parity contract");
+  if (st.environmentProb > 0.0f)
+    raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs the HDR importance-sampling map (env_sampling.glsl), not implemented yet");
+  if (st.RISSampleNum < 0 || st.maxDepth < 0) raise(EID_ERR_INVALID, "negative RISSampleNum / maxDepth");
+  const int set = (frames + 1) % 2;   // renderer.cpp:157; set i: last* = [i], this* = [!i] (renderer.cpp:341-375)
+  P.st = st;
+  P.cam = r->scene->host.camera;
+  P.sc = r->scene->dev.view(r->scene->host);
+  P.accel = r->accel->view();
+  P.thisG = r->gbuffer[!set]; P.lastG = r->gbuffer[set];
+  P.motion = r->motion;
+  P.thisDR = r->directResv[!set]; P.lastDR = r->directResv[set];
+  P.thisIR = r->indirectResv[!set]; P.lastIR = r->indirectResv[set];
+  P.directImg = r->directImg; P.indirectImg = r->indirectImg;
+  P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
+  for (int k = 0; k < 3; ++k) P.env[k] = r->env[k];
+  P.pitch = (int)r->width; P.allocH = (int)r->height;
+  P.y0 = 0; P.y1 = st.size.y;
+  if (r->bandSet) { P.y0 = (int)std::min<uint32_t>(r->bandY0, (uint32_t)st.size.y); P.y1 = (int)std::min<uint32_t>(r->bandY1, (uint32_t)st.size.y); }
+  P.counters = r->counters;
+  r->lastSet = set; r->lastState = st; r->hasRun = true;
+}
+
+static inline void mark(eid_renderer* r, int i) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[i], r->stream)); }
+
+static void launchTrace(eid_renderer* r, const FrameParams& P) {
+  CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 3 * sizeof(unsigned long long), r->stream));
+  memset(&r->stats, 0, sizeof(r->stats));
+  mark(r, 0);
+  const int rows = P.y1 - P.y0;
+  if (rows > 0) {
+    dim3 b(8, 8), g((P.st.size.x + 7) / 8, (rows + 7) / 8);
+    k_direct_stage<<<g, b, 0, r->stream>>>(P);
+    r->stats.kernelLaunches[EID_K_DIRECT]++;
+  }
+  mark(r, 1);
+  const int irows = P.y1 / 2 - P.y0 / 2;
+  if (irows > 0 && P.st.size.x / 2 > 0) {
+    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, (irows + 7) / 8);
+    k_indirect_stage<<<g, b, 0, r->stream>>>(P);
+    r->stats.kernelLaunches[EID_K_INDIRECT]++;
+  }
+  mark(r, 2);
+}
+
+static void launchPost(eid_renderer* r, const FrameParams& P) {
+  const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
+  if (P.st.denoise > 0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
+    dim3 b(32, 4), g((W + 31) / 32, (H + 3) / 4);
+    const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
+    float4* dst[4] = {P.dirA, P.dirB, P.dirA, P.directImg};
+    for (int i = 0; i < 4; ++i) { k_denoise<false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
+  }
+  mark(r, 3);
+  if (P.st.denoise > 0 && Wi > 0 && Hi > 0) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
+    dim3 b(32, 4), g((Wi + 31) / 32, (Hi + 3) / 4);
+    const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
+    float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
+    for (int i = 0; i < 5; ++i) { k_denoise<true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4); r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++; }
+  }
+  mark(r, 4);
+  {
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA);
+    r->stats.kernelLaunches[EID_K_COMPOSE]++;
+  }
+  mark(r, 5);
+  CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
+  r->statsPending = true;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+static void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
+  const size_t n = (size_t)r->width * r->height, ni = (size_t)(r->width / 2) * (r->height / 2);
+  const int set = r->lastSet;
+  switch (which) {
+    case EID_BUF_THIS_GBUFFER: bytes = n * 16; return r->gbuffer[!set];
+    case EID_BUF_LAST_GBUFFER: bytes = n * 16; return r->gbuffer[set];
+    case EID_BUF_MOTION: bytes = n * 4; return r->motion;
+    case EID_BUF_THIS_DIRECT_RESV: bytes = n * sizeof(DirectReservoir); return r->directResv[!set];
+    case EID_BUF_LAST_DIRECT_RESV: bytes = n * sizeof(DirectReservoir); return r->directResv[set];
+    case EID_BUF_THIS_INDIRECT_RESV: bytes = ni * sizeof(IndirectReservoir); return r->indirectResv[!set];
+    case EID_BUF_LAST_INDIRECT_RESV: bytes = ni * sizeof(IndirectReservoir); return r->indirectResv[set];
+    case EID_BUF_DIRECT: bytes = n * 16; return r->directImg;
+    case EID_BUF_INDIRECT: bytes = n * 16; return r->indirectImg;
+    case EID_BUF_DENOISE_DIR_A: case EID_BUF_DENOISE_DIR_B: case EID_BUF_DENOISE_IND_A: case EID_BUF_DENOISE_IND_B:
+      bytes = n * 16; return r->denoiseTemp[which - EID_BUF_DENOISE_DIR_A];
+    default: return nullptr;
+  }
+}
+
+extern "C" {
+
+int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t width, uint32_t height, void* cuda_stream) {
+  EID_TRY
+  if (!out || !s || !a) raise(EID_ERR_INVALID, "eid_renderer_create: null argument");
+  if (!s->loaded || a->scene != s) raise(EID_ERR_STATE, "eid_renderer_create: scene not loaded or accel built for another scene");
+  if (!width || !height || width > 32768 || height > 32768) raise(EID_ERR_INVALID, "bad render size %ux%u", width, height);
+  eid_renderer* r = new eid_renderer();
+  try {
+    r->scene = s; r->accel = a; r->device = s->dev.device; r->width = width; r->height = height;
+    CUDA_CHECK(cudaSetDevice(r->device));
+    if (cuda_stream) r->stream = (cudaStream_t)cuda_stream;
+    else { CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->ownStream = true; }
+    CUDA_CHECK(cudaMalloc(&r->counters, 3 * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMallocHost(&r->countersHost, 3 * sizeof(unsigned long long)));
+    memset(r->countersHost, 0, 3 * sizeof(unsigned long long));
+    for (auto& e : r->ev) CUDA_CHECK(cudaEventCreate(&e));
+    r->allocate();
+  } catch (...) { eid_renderer_destroy(r); throw; }
+  *out = r;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_resize(eid_renderer* r, uint32_t width, uint32_t height) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_resize: null renderer");
+  if (!width || !height || width > 32768 || height > 32768) raise(EID_ERR_INVALID, "bad render size %ux%u", width, height);
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  r->release();
+  r->width = width; r->height = height; r->bandSet = false;
+  r->allocate();
+  return EID_OK;
+  EID_CATCH
+}
+
+void eid_renderer_destroy(eid_renderer* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  if (r->stream) cudaStreamSynchronize(r->stream);
+  r->release();
+  cudaFree(r->counters);
+  if (r->countersHost) cudaFreeHost(r->countersHost);
+  for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+  if (r->ownStream && r->stream) cudaStreamDestroy(r->stream);
+  delete r;
+}
+
+int eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]) {
+  EID_TRY
+  if (!r || !rgb) raise(EID_ERR_INVALID, "eid_renderer_set_env_constant: null argument");
+  for (int k = 0; k < 3; ++k) r->env[k] = rgb[k];
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  launchTrace(r, P);
+  launchPost(r, P);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_trace: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  launchTrace(r, P);
+  CUDA_CHECK(cudaGetLastError());
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_post: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  if (r->profiling) { mark(r, 2); }
+  launchPost(r, P);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_sync(eid_renderer* r) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_sync: null renderer");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_get_outputs(eid_renderer* r, const float** direct, const float** indirect) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_get_outputs: null renderer");
+  if (direct) *direct = (const float*)r->directImg;
+  if (indirect) *indirect = (const float*)r->indirectImg;
+  return EID_OK;
+  EID_CATCH
+}
+
+int64_t eid_renderer_buffer_bytes(eid_renderer* r, int which) {
+  if (!r) return -1;
+  size_t b = 0;
+  return bufferPtr(r, which, b) ? (int64_t)b : -1;
+}
+
+int eid_renderer_read(eid_renderer* r, int which, void* host_dst, size_t bytes) {
+  EID_TRY
+  if (!r || !host_dst) raise(EID_ERR_INVALID, "eid_renderer_read: null argument");
+  size_t b = 0; void* p = bufferPtr(r, which, b);
+  if (!p) raise(EID_ERR_INVALID, "no such buffer %d", which);
+  if (bytes > b) raise(EID_ERR_INVALID, "read of %zu bytes from a %zu-byte buffer", bytes, b);
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, r->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_write(eid_renderer* r, int which, const void* host_src, size_t bytes) {
+  EID_TRY
+  if (!r || !host_src) raise(EID_ERR_INVALID, "eid_renderer_write: null argument");
+  size_t b = 0; void* p = bufferPtr(r, which, b);
+  if (!p) raise(EID_ERR_INVALID, "no such buffer %d", which);
+  if (bytes > b) raise(EID_ERR_INVALID, "write of %zu bytes into a %zu-byte buffer", bytes, b);
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaMemcpyAsync(p, host_src, bytes, cudaMemcpyHostToDevice, r->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames, float* direct_host, float* indirect_host) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_render_host: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  if (cam) r->scene->host.camera = *cam;
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  launchTrace(r, P);
+  launchPost(r, P);
+  const size_t rowBytes = (size_t)state->size.x * 16;
+  if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->directImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
+  if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->indirectImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_profiling(eid_renderer* r, int enabled) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_profiling: null renderer");
+  r->profiling = enabled != 0;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out) {
+  EID_TRY
+  if (!r || !out) raise(EID_ERR_INVALID, "eid_renderer_get_stats: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  if (r->statsPending) {
+    r->stats.closestHitRays = r->countersHost[0]; r->stats.anyHitRays = r->countersHost[1]; r->stats.primaryHits = r->countersHost[2];
+    r->stats.launches = 0;
+    for (int k = 0; k < EID_K_COUNT; ++k) r->stats.launches += r->stats.kernelLaunches[k];
+    if (r->profiling)
+      for (int k = 0; k < EID_K_COUNT; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r->ev[k], r->ev[k + 1]) == cudaSuccess) r->stats.kernelMs[k] = ms; else cudaGetLastError();
+      }
+    r->statsPending = false;
+  }
+  *out = r->stats;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_band: null renderer");
+  if (y0 > y1 || y1 > r->height) raise(EID_ERR_INVALID, "band [%u,%u) outside 0..%u", y0, y1, r->height);
+  if ((y0 % 16) != 0 || ((y1 % 16) != 0 && y1 != r->height)) raise(EID_ERR_INVALID, "band edges must be multiples of 16 rows (8x8 half-res tiles must not straddle ranks)");
+  r->bandY0 = y0; r->bandY1 = y1; r->bandSet = true;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes) {
+  EID_TRY
+  if (!r || !dev_base || !offset || !bytes) raise(EID_ERR_INVALID, "eid_renderer_band_range: null argument");
+  size_t total = 0; void* p = bufferPtr(r, which, total);
+  if (!p) raise(EID_ERR_INVALID, "no such buffer %d", which);
+  const uint64_t y0 = r->bandSet ? r->bandY0 : 0, y1 = r->bandSet ? r->bandY1 : r->height;
+  const uint64_t W = r->width, Wi = r->width / 2;
+  const uint64_t sw = r->hasRun ? (uint64_t)r->lastState.size.x : W;   // reservoir buffers are pitched by RtxState.size.x
+  uint64_t rowBytes = 0, a = y0, b = y1;
+  switch (which) {
+    case EID_BUF_THIS_GBUFFER: case EID_BUF_LAST_GBUFFER: case EID_BUF_DIRECT: case EID_BUF_INDIRECT:
+    case EID_BUF_DENOISE_DIR_A: case EID_BUF_DENOISE_DIR_B: rowBytes = W * 16; break;
+    case EID_BUF_MOTION: rowBytes = W * 4; break;
+    case EID_BUF_DENOISE_IND_A: case EID_BUF_DENOISE_IND_B: rowBytes = W * 16; a = y0 / 2; b = y1 / 2; break;   // half-res rows, full-res pitch
+    case EID_BUF_THIS_DIRECT_RESV: case EID_BUF_LAST_DIRECT_RESV: rowBytes = sw * sizeof(DirectReservoir); break;
+    case EID_BUF_THIS_INDIRECT_RESV: case EID_BUF_LAST_INDIRECT_RESV: rowBytes = (sw / 2) * sizeof(IndirectReservoir); a = y0 / 2; b = y1 / 2; break;
+    default: raise(EID_ERR_INVALID, "no band layout for buffer %d", which);
+  }
+  (void)Wi;
+  *dev_base = p; *offset = a * rowBytes; *bytes = (b - a) * rowBytes;
+  return EID_OK;
+  EID_CATCH
+}
+
+}  // extern "C"

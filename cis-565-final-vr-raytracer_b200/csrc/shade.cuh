@@ -1,0 +1,317 @@
+// shade.cuh — device-side arithmetic of the reference's shader includes, written for CUDA registers:
+//   random.glsl (tea/pcg/rand), common.glsl (OffsetRay, toConcentricDisk, powerHeuristic, HDR<->LDR),
+//   shade_state.glsl (GetState), gltf_material.glsl (GetMaterials, texture-less),
+//   pbr_metallicworkflow.glsl (BSDF / Pdf / Sample), reservoir.glsl, pathtrace.glsl (light sampling,
+//   Occlusion, clampRadiance, raySpawn, G-buffer decode).
+// RNG draw order and floating-point evaluation order follow SURVEY.md §8 a.3 / DESIGN.md §3 exactly;
+// every function names the reference lines it implements.
+#pragma once
+#include "dmath.cuh"
+#include "trace.cuh"
+
+namespace eid {
+
+#define EID_INFINITY 1e28f          // globals.glsl:29
+#define EID_PI 3.14159265358979323846f
+#define EID_INVALID_PDF (-1.0f)     // common.glsl:30
+#define EID_INVALID_MAT 0xff000000u // globals.glsl:106
+
+// ---- random.glsl ---------------------------------------------------------------------------------
+DEV uint32_t tea(uint32_t v0, uint32_t v1) {            // :34-48
+  uint32_t s0 = 0;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    s0 += 0x9e3779b9u;
+    v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+    v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+  }
+  return v0;
+}
+DEV float rnd(uint32_t& seed) {                         // pcg :59-65 + rand :98-102
+  uint32_t prev = seed * 747796405u + 2891336453u;
+  uint32_t word = ((prev >> ((prev >> 28u) + 4u)) ^ prev) * 277803737u;
+  seed = prev;
+  uint32_t r = (word >> 22u) ^ word;
+  return __fsub_rn(__uint_as_float(0x3f800000u | (r >> 9)), 1.0f);
+}
+
+// ---- common.glsl ---------------------------------------------------------------------------------
+DEV f3 offsetRay(f3 p, f3 n) {                          // :98-113 (Ray Tracing Gems ch. 6)
+  const float intScale = 256.0f, floatScale = 1.0f / 65536.0f, origin = 1.0f / 32.0f;
+  int ox = f2i_sat(__fmul_rn(intScale, n.x)), oy = f2i_sat(__fmul_rn(intScale, n.y)), oz = f2i_sat(__fmul_rn(intScale, n.z));
+  float ix = __int_as_float(__float_as_int(p.x) + ((p.x < 0) ? -ox : ox));
+  float iy = __int_as_float(__float_as_int(p.y) + ((p.y < 0) ? -oy : oy));
+  float iz = __int_as_float(__float_as_int(p.z) + ((p.z < 0) ? -oz : oz));
+  return mk3(fabsf(p.x) < origin ? __fadd_rn(p.x, __fmul_rn(floatScale, n.x)) : ix,
+             fabsf(p.y) < origin ? __fadd_rn(p.y, __fmul_rn(floatScale, n.y)) : iy,
+             fabsf(p.z) < origin ? __fadd_rn(p.z, __fmul_rn(floatScale, n.z)) : iz);
+}
+DEV void toConcentricDisk(float rx_, float ry_, float& dx, float& dy) {   // :171-175 (polar, not Shirley)
+  float rx = __fsqrt_rn(rx_);
+  float theta = __fmul_rn(__fmul_rn(ry_, 2.0f), EID_PI);
+  float s, c;
+  eid_sincosf(theta, &s, &c);
+  dx = __fmul_rn(c, rx); dy = __fmul_rn(s, rx);
+}
+DEV float powerHeuristic(float f, float g) { float f2 = __fmul_rn(f, f); return __fdiv_rn(f2, __fadd_rn(f2, __fmul_rn(g, g))); }   // :177-180
+DEV f3 hdrToLdr(f3 c) { return c / (c + 1.0f); }       // :194-196
+DEV f3 ldrToHdr(f3 c) { return c / (1.01f - c); }      // :198-200
+
+// ---- globals.glsl:64-104 -------------------------------------------------------------------------
+struct Material { f3 albedo, emission; float metallic, ior, roughness, transmission; };
+struct State {
+  f3 position, normal, ffnormal;
+  float u, v;          // texCoord
+  float eta, area;
+  uint32_t matID;
+  bool isEmitter;
+  Material mat;
+};
+
+// ---- pbr_metallicworkflow.glsl -------------------------------------------------------------------
+struct M3 { f3 c0, c1, c2; };   // column-major mat3
+DEV f3 m3mul(const M3& m, f3 v) { return (m.c0 * v.x + m.c1 * v.y) + m.c2 * v.z; }
+DEV M3 localRefMatrix(f3 n) {                           // :11-16
+  f3 t = (fabsf(n.y) > 0.9999f) ? mk3(0.f, 0.f, 1.f) : mk3(0.f, 1.f, 0.f);
+  f3 b = norm3(cross3(n, t));
+  t = cross3(b, n);
+  M3 m = {t, b, n};
+  return m;
+}
+DEV M3 m3inverse(const M3& m) {                          // GLSL inverse(mat3), cofactor form (contract)
+  float a00 = m.c0.x, a01 = m.c0.y, a02 = m.c0.z, a10 = m.c1.x, a11 = m.c1.y, a12 = m.c1.z, a20 = m.c2.x, a21 = m.c2.y, a22 = m.c2.z;
+  float b01 = __fsub_rn(__fmul_rn(a22, a11), __fmul_rn(a12, a21));
+  float b11 = __fsub_rn(__fmul_rn(a12, a20), __fmul_rn(a22, a10));
+  float b21 = __fsub_rn(__fmul_rn(a21, a10), __fmul_rn(a11, a20));
+  float det = __fadd_rn(__fadd_rn(__fmul_rn(a00, b01), __fmul_rn(a01, b11)), __fmul_rn(a02, b21));
+  float id = __fdiv_rn(1.0f, det);
+  M3 r;
+  r.c0 = mk3(__fmul_rn(b01, id), __fmul_rn(__fsub_rn(__fmul_rn(a02, a21), __fmul_rn(a22, a01)), id), __fmul_rn(__fsub_rn(__fmul_rn(a12, a01), __fmul_rn(a02, a11)), id));
+  r.c1 = mk3(__fmul_rn(b11, id), __fmul_rn(__fsub_rn(__fmul_rn(a22, a00), __fmul_rn(a02, a20)), id), __fmul_rn(__fsub_rn(__fmul_rn(a02, a10), __fmul_rn(a12, a00)), id));
+  r.c2 = mk3(__fmul_rn(b21, id), __fmul_rn(__fsub_rn(__fmul_rn(a01, a20), __fmul_rn(a21, a00)), id), __fmul_rn(__fsub_rn(__fmul_rn(a11, a00), __fmul_rn(a01, a10)), id));
+  return r;
+}
+DEV float satDot(f3 a, f3 b) { return gmax(dot3(a, b), 0.0f); }
+DEV float absDot(f3 a, f3 b) { return fabsf(dot3(a, b)); }
+DEV f3 sampleHemisphereCosine(f3 n, float r0, float r1) {   // :22-26 + localToWorld :18-20
+  float dx, dy;
+  toConcentricDisk(r0, r1, dx, dy);
+  float z = __fsqrt_rn(__fsub_rn(1.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+  return norm3(m3mul(localRefMatrix(n), mk3(dx, dy, z)));
+}
+DEV f3 fresnelSchlick(float cosTheta, f3 f0) {           // :36-41
+  float c4 = __fsub_rn(1.0f, cosTheta);
+  c4 = __fmul_rn(c4, c4);
+  c4 = __fmul_rn(c4, c4);
+  return mix3(f0, mk3(1.0f), __fmul_rn(c4, __fsub_rn(1.0f, cosTheta)));
+}
+DEV float schlickG(float cosTheta, float alpha) {        // :43-46
+  float a = __fmul_rn(alpha, 0.5f);
+  return __fdiv_rn(cosTheta, __fadd_rn(__fmul_rn(cosTheta, __fsub_rn(1.0f, a)), a));
+}
+DEV float smithG(float cosWo, float cosWi, float alpha) { return __fmul_rn(schlickG(fabsf(cosWo), alpha), schlickG(fabsf(cosWi), alpha)); }   // :48-50
+DEV float gtr2Distrib(float cosTheta, float alpha) {     // :52-61
+  if (cosTheta < 1e-6f) return 0.0f;
+  float aa = __fmul_rn(alpha, alpha);
+  float denom = __fadd_rn(__fmul_rn(__fmul_rn(cosTheta, cosTheta), __fsub_rn(aa, 1.0f)), 1.0f);
+  denom = __fmul_rn(__fmul_rn(denom, denom), EID_PI);
+  return __fdiv_rn(aa, denom);
+}
+DEV float gtr2Pdf(f3 n, f3 m, f3 wo, float alpha) {      // :63-65
+  return __fdiv_rn(__fmul_rn(__fmul_rn(gtr2Distrib(dot3(n, m), alpha), schlickG(dot3(n, wo), alpha)), absDot(m, wo)), absDot(n, wo));
+}
+DEV f3 gtr2Sample(f3 n, f3 wo, float alpha, float r0, float r1) {   // :67-84
+  M3 transMat = localRefMatrix(n);
+  M3 transInv = m3inverse(transMat);
+  f3 vh = norm3(m3mul(transInv, wo) * mk3(alpha, alpha, 1.0f));
+  float lenSq = __fadd_rn(__fmul_rn(vh.x, vh.x), __fmul_rn(vh.y, vh.y));
+  f3 t = lenSq > 0.0f ? mk3(-vh.y, vh.x, 0.0f) / __fsqrt_rn(lenSq) : mk3(1.0f, 0.0f, 0.0f);
+  f3 b = cross3(vh, t);
+  float px, py;
+  toConcentricDisk(r0, r1, px, py);
+  float s = __fmul_rn(0.5f, __fadd_rn(vh.z, 1.0f));
+  py = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, s), __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(px, px)))), __fmul_rn(s, py));
+  float pp = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+  f3 h = (t * px + b * py) + vh * __fsqrt_rn(gmax(0.0f, __fsub_rn(1.0f, pp)));
+  h = mk3(__fmul_rn(h.x, alpha), __fmul_rn(h.y, alpha), gmax(0.0f, h.z));
+  return norm3(m3mul(transMat, h));
+}
+// metallicWorkflowBSDF :86-106 (== the value of metallicWorkflowEval :123-144; its pdf output is dead on the live path)
+DEV f3 bsdfEval(f3 albedo, float roughness, float metallic, f3 n, f3 wo, f3 wi) {
+  const float PiInv = 1.0f / EID_PI;
+  float alpha = roughness;
+  f3 h = norm3(wo + wi);
+  float cosO = dot3(n, wo), cosI = dot3(n, wi);
+  if (__fmul_rn(cosI, cosO) < 1e-7f) return mk3(0.0f);
+  f3 f = fresnelSchlick(dot3(h, wo), mix3(mk3(.08f), albedo, metallic));
+  float g = smithG(cosO, cosI, alpha);
+  float d = gtr2Distrib(dot3(n, h), alpha);
+  float spec = __fdiv_rn(__fmul_rn(g, d), __fmul_rn(__fmul_rn(4.0f, cosI), cosO));
+  return mix3((albedo * PiInv) * __fsub_rn(1.0f, metallic), mk3(spec), f);
+}
+DEV float bsdfPdf(float roughness, float metallic, f3 n, f3 wo, f3 wi) {   // :108-121
+  const float PiInv = 1.0f / EID_PI;
+  float alpha = roughness;
+  f3 h = norm3(wo + wi);
+  return mixf(__fmul_rn(satDot(n, wi), PiInv), __fdiv_rn(gtr2Pdf(n, h, wo, alpha), __fmul_rn(4.0f, absDot(h, wo))),
+              __fdiv_rn(1.0f, __fsub_rn(2.0f, metallic)));
+}
+// Sample (pathtrace.glsl:36-38) -> metallicWorkflowSample (:146-166): three draws, returns pdf (or InvalidPdf)
+DEV float bsdfSample(const State& s, f3 n, f3 wo, uint32_t& seed, f3& bsdf, f3& dir) {
+  float r0 = rnd(seed), r1 = rnd(seed), r2 = rnd(seed);
+  float roughness = s.mat.roughness, metallic = s.mat.metallic, alpha = roughness;
+  if (r2 > __fdiv_rn(1.0f, __fsub_rn(2.0f, metallic))) {
+    dir = sampleHemisphereCosine(n, r0, r1);
+  } else {
+    f3 h = gtr2Sample(n, wo, alpha, r0, r1);
+    dir = -reflect3(wo, h);
+  }
+  if (dot3(n, dir) < 0.0f) { bsdf = mk3(0.f); return EID_INVALID_PDF; }
+  bsdf = bsdfEval(s.mat.albedo, roughness, metallic, n, wo, dir);
+  return bsdfPdf(roughness, metallic, n, wo, dir);
+}
+
+// ---- reservoir.glsl ------------------------------------------------------------------------------
+DEV bool resvInvalidW(float w) { return (w != w) || w < 0.0f; }   // :28-34
+struct DResv { f3 Li, wi; float dist; uint32_t num; float weight; };
+DEV void resvUpdate(DResv& r, f3 Li, f3 wi, float dist, float newWeight, float rv) {   // :47-53
+  r.weight = __fadd_rn(r.weight, newWeight);
+  r.num += 1;
+  if (__fmul_rn(rv, r.weight) < newWeight) { r.Li = Li; r.wi = wi; r.dist = dist; }
+}
+
+// ---- scene access --------------------------------------------------------------------------------
+struct Payload {       // PtPayload (globals.glsl:48-58) minus the matrices, which are fetched by instanceID
+  float hitT, baryU, baryV;
+  int primitiveID, instanceID, instanceCustomIndex;
+};
+
+// shade_state.glsl:147-221 GetState (tangent frame is only needed by normal mapping: later scope row)
+DEV State getState(const DeviceSceneView& sc, const Payload& h, f3 rayDir) {
+  State st;
+  const InstanceXform& X = sc.instances[h.instanceID];
+  const InstanceData gi = sc.geoInfo[h.instanceCustomIndex];
+  const uint32_t* idx = (const uint32_t*)(uintptr_t)gi.indexAddress + 3 * (size_t)h.primitiveID;
+  const uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+  const float4* vb = (const float4*)(uintptr_t)gi.vertexAddress;   // 32 B / vertex = 2 x float4
+  const float4 a0 = __ldg(vb + 2 * (size_t)i0), a1 = __ldg(vb + 2 * (size_t)i0 + 1);
+  const float4 b0 = __ldg(vb + 2 * (size_t)i1), b1 = __ldg(vb + 2 * (size_t)i1 + 1);
+  const float4 c0 = __ldg(vb + 2 * (size_t)i2), c1 = __ldg(vb + 2 * (size_t)i2 + 1);
+  const float bx = __fsub_rn(__fsub_rn(1.0f, h.baryU), h.baryV), by = h.baryU, bz = h.baryV;
+  const int mi = gi.materialIndex;
+  st.matID = (uint32_t)(mi < 0 ? 0 : mi);
+
+  const f3 pos0 = mk3(a0.x, a0.y, a0.z), pos1 = mk3(b0.x, b0.y, b0.z), pos2 = mk3(c0.x, c0.y, c0.z);
+  const f3 position = (pos0 * bx + pos1 * by) + pos2 * bz;
+  st.position = xfPoint(X.objectToWorld, position);
+  const f3 w0 = xfPoint(X.objectToWorld, pos0), w1 = xfPoint(X.objectToWorld, pos1), w2 = xfPoint(X.objectToWorld, pos2);
+
+  const f3 n0 = octDecode(__float_as_uint(a0.w)), n1 = octDecode(__float_as_uint(b0.w)), n2 = octDecode(__float_as_uint(c0.w));
+  const f3 normal = norm3((n0 * bx + n1 * by) + n2 * bz);
+  const f3 world_normal = norm3(xfTransposed(normal, X.worldToObject));
+  const f3 geom_normal = norm3(cross3(pos1 - pos0, pos2 - pos0));
+  const f3 wgeom_normal = norm3(xfTransposed(geom_normal, X.worldToObject));
+
+  // decode_texture (:53-56): clear the handedness bit of v
+  const float v0 = __uint_as_float(__float_as_uint(a1.y) & ~1u), v1 = __uint_as_float(__float_as_uint(b1.y) & ~1u), v2 = __uint_as_float(__float_as_uint(c1.y) & ~1u);
+  st.u = __fadd_rn(__fadd_rn(__fmul_rn(a1.x, bx), __fmul_rn(b1.x, by)), __fmul_rn(c1.x, bz));
+  st.v = __fadd_rn(__fadd_rn(__fmul_rn(v0, bx), __fmul_rn(v1, by)), __fmul_rn(v2, bz));
+
+  st.normal = (dot3(world_normal, wgeom_normal) > 0.0f) ? world_normal : -world_normal;
+  st.ffnormal = dot3(st.normal, rayDir) <= 0.0f ? st.normal : -st.normal;
+  st.area = __fmul_rn(len3(cross3(w1 - w0, w2 - w0)), 0.5f);
+  return st;
+}
+
+// gltf_material.glsl:130-176 GetMaterials + GetMetallicRoughness :52-91, texture-less materials
+DEV void getMaterials(const DeviceSceneView& sc, State& st) {
+  const float4* m = (const float4*)(sc.materials + st.matID);   // 80 B = 5 x float4
+  const float4 q0 = __ldg(m), q1 = __ldg(m + 1), q2 = __ldg(m + 2), q3 = __ldg(m + 3), q4 = __ldg(m + 4);
+  st.mat.emission = mk3(q2.y, q2.z, q2.w);
+  st.isEmitter = __fadd_rn(__fadd_rn(st.mat.emission.x, st.mat.emission.y), st.mat.emission.z) > 1e-3f;
+  st.mat.albedo = mk3(q0.x, q0.y, q0.z);
+  st.mat.metallic = q1.y;
+  st.mat.roughness = gmax(q1.z, 0.001f);
+  st.mat.transmission = q3.z;
+  st.mat.ior = q4.x;
+  st.eta = dot3(st.normal, st.ffnormal) > 0.0f ? __fdiv_rn(1.0f, st.mat.ior) : st.mat.ior;
+}
+
+// ---- pathtrace.glsl ------------------------------------------------------------------------------
+DEV bool isPdfInvalid(float p) { return p <= 1e-8f || p != p; }   // :14-16
+
+struct LightSampleD { f3 Li, wi; float dist; };
+
+// SampleTriangleLight :103-139 (+ SampleTriangleUniform :90-97): 4 draws
+DEV float sampleTriangleLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, LightSampleD& ls) {
+  const uint32_t n = sc.lightBufInfo.trigLightSize;
+  if (n == 0) return EID_INVALID_PDF;
+  int id = min(f2i_sat(__fmul_rn((float)n, rnd(seed))), (int)n - 1);
+  const float q = __ldg(&sc.trigLights[id].impSamp.q);
+  if (rnd(seed) > q) id = __ldg(&sc.trigLights[id].impSamp.alias);
+  const float4* L = (const float4*)(sc.trigLights + id);   // 96 B = 6 x float4
+  const float4 l0 = __ldg(L), l1 = __ldg(L + 1), l2 = __ldg(L + 2), l4 = __ldg(L + 4);
+  const uint32_t matIndex = __float_as_uint(l0.x);
+  const f3 v0 = mk3(l0.z, l0.w, l1.x), v1 = mk3(l1.y, l1.z, l1.w), v2 = mk3(l2.x, l2.y, l2.z);
+  const float lightPdf = l4.w;   // impSamp.pdf
+  f3 normal = cross3(v1 - v0, v2 - v0);
+  const float area = __fmul_rn(len3(normal), 0.5f);
+  normal = norm3(normal);
+  const float ru = rnd(seed), rv = rnd(seed);
+  const float r = __fsqrt_rn(rv);
+  const float bu = __fsub_rn(1.0f, r), bv = __fmul_rn(ru, r);
+  const f3 y = (bu * v0 + bv * v1) + __fsub_rn(__fsub_rn(1.0f, bu), bv) * v2;
+  const float4 em = __ldg((const float4*)(sc.materials + matIndex) + 2);   // emissiveTexture, emissiveFactor.xyz
+  const f3 emission = mk3(em.y, em.z, em.w);
+  const f3 dir = y - x;
+  const float dist = len3(dir);
+  ls.Li = emission / area;
+  ls.wi = dir / dist;
+  ls.dist = dist;
+  return __fdiv_rn(__fmul_rn(lightPdf, __fmul_rn(dist, dist)), __fmul_rn(area, fabsf(dot3(ls.wi, normal))));
+}
+// SamplePuncLight :141-159: 2 draws; type / range / cone are ignored by the reference
+DEV float samplePuncLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, LightSampleD& ls) {
+  const uint32_t n = sc.lightBufInfo.puncLightSize;
+  if (n == 0) return EID_INVALID_PDF;
+  int id = min(f2i_sat(__fmul_rn((float)n, rnd(seed))), (int)n - 1);
+  if (rnd(seed) > sc.puncLights[id].impSamp.q) id = sc.puncLights[id].impSamp.alias;
+  const PuncLight& L = sc.puncLights[id];
+  const f3 dir = ld3(L.position) - x;
+  const float dist = len3(dir);
+  ls.Li = (ld3(L.color) * L.intensity) / __fmul_rn(dist, dist);
+  ls.wi = dir / dist;
+  ls.dist = dist;
+  return L.impSamp.pdf;
+}
+// SampleDirectLightNoVisibility :161-183
+DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const RtxState& rs, f3 pos, uint32_t& seed, LightSampleD& ls) {
+  const float r = rnd(seed);
+  const float envProb = rs.environmentProb;
+  if (r < envProb) return EID_INVALID_PDF;   // EnvSample (env_sampling.glsl:100-135): HDR alias map is a later scope row
+  const float lightProb = __fsub_rn(1.0f, envProb);
+  const float tsp = sc.lightBufInfo.trigSampProb;
+  if (r < __fadd_rn(envProb, __fmul_rn(lightProb, tsp)))
+    return __fmul_rn(__fmul_rn(lightProb, sampleTriangleLight(sc, pos, seed, ls)), tsp);
+  return __fmul_rn(__fmul_rn(lightProb, samplePuncLight(sc, pos, seed, ls)), __fsub_rn(1.0f, tsp));
+}
+// clampRadiance :222-232
+DEV f3 clampRadiance(f3 radiance, float threshold) {
+  if (nan3(radiance)) return mk3(0.0f);
+  float lum = lum3(radiance);
+  if (lum > threshold) radiance = radiance * __fdiv_rn(threshold, lum);
+  return radiance;
+}
+// raySpawn :260-270 (normalizeDir = true) and the denoiser's variant denoise_common.glsl:27-35 (false)
+template <bool NORMALIZE>
+DEV void raySpawn(const SceneCamera& cam, int cx, int cy, int sw, int sh, f3& origin, f3& dir) {
+  const float ux = __fdiv_rn(__fadd_rn((float)cx, 0.5f), (float)sw), uy = __fdiv_rn(__fadd_rn((float)cy, 0.5f), (float)sh);
+  const float dx = __fsub_rn(__fmul_rn(ux, 2.0f), 1.0f), dy = __fsub_rn(__fmul_rn(uy, 2.0f), 1.0f);
+  origin = mk3(cam.viewInverse.m[12], cam.viewInverse.m[13], cam.viewInverse.m[14]);
+  float tg[4];
+  mat4MulV(cam.projInverse, dx, dy, 1.0f, 1.0f, tg);
+  f3 d = mat4MulDir(cam.viewInverse, norm3(mk3(tg[0], tg[1], tg[2])));
+  dir = NORMALIZE ? norm3(d) : d;
+}
+
+}  // namespace eid

@@ -1,0 +1,114 @@
+// trace.cuh — software replacement for the reference's ray-query traversal (shaders/traceray_rq.glsl:
+// ClosestHit :108-147, AnyHit :153-185), which runs on RT cores inside the Vulkan driver.
+//
+// Semantics: t in (0, tmax) exclusive; back faces culled unless the
+// instance disables culling (accelstruct.cpp:148-149), facing decided in object space; barycentrics (u,v)
+// weight vertices 1 and 2; closest hit = smallest t, ties broken by lowest (instanceID, primitiveID).
+// The triangle test is Moller-Trumbore in individually rounded fp32 operations — the one piece of
+// arithmetic that decides results, identical to the oracle's.  Box tests are conservative (boxes padded at
+// build time) and use fmaf; they only decide which triangles get tested, never the outcome.
+#pragma once
+#include "accel.h"
+#include "dmath.cuh"
+
+namespace eid {
+
+struct RayHit {
+  float t, u, v;
+  int tri;          // index into AccelView::tris, -1 = miss
+  int prim, inst;
+};
+
+#define EID_STACK_SIZE 64
+
+// returns true and fills t,u,v when the ray hits triangle (v0,e1,e2) inside (0, tmax)
+DEV bool triangleTest(f3 v0, f3 e1, f3 e2, uint32_t flags, f3 o, f3 d, float tmax, float& t, float& u, float& v) {
+  f3 pvec = cross3(d, e2);
+  float det = dot3(e1, pvec);
+  if (flags & INST_CULL_DISABLE) { if (det == 0.0f) return false; }
+  else { float fd = (flags & INST_MIRROR) ? -det : det; if (!(fd > 0.0f)) return false; }
+  float inv = __fdiv_rn(1.0f, det);
+  f3 tvec = o - v0;
+  u = __fmul_rn(dot3(tvec, pvec), inv);
+  if (!(u >= 0.0f && u <= 1.0f)) return false;
+  f3 qvec = cross3(tvec, e1);
+  v = __fmul_rn(dot3(d, qvec), inv);
+  if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
+  t = __fmul_rn(dot3(e2, qvec), inv);
+  return t > 0.0f && t < tmax;
+}
+
+struct RayBox {   // per-ray constants of the slab test
+  float ix, iy, iz, ox, oy, oz;   // 1/d and o/d
+};
+DEV RayBox makeRayBox(f3 o, f3 d) {
+  const float tiny = 1e-20f;
+  float dx = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x);
+  float dy = fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y);
+  float dz = fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z);
+  RayBox r;
+  r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+  r.ox = o.x * r.ix; r.oy = o.y * r.iy; r.oz = o.z * r.iz;
+  return r;
+}
+// entry distance of the slab intersection, or +inf when the box is missed within [0, tbest]
+DEV float boxEntry(const RayBox& rb, float lx, float ly, float lz, float hx, float hy, float hz, float tbest) {
+  float x0 = fmaf(lx, rb.ix, -rb.ox), x1 = fmaf(hx, rb.ix, -rb.ox);
+  float y0 = fmaf(ly, rb.iy, -rb.oy), y1 = fmaf(hy, rb.iy, -rb.oy);
+  float z0 = fmaf(lz, rb.iz, -rb.oz), z1 = fmaf(hz, rb.iz, -rb.oz);
+  float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+  float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tbest));
+  return (tn <= tf * 1.0000004f) ? tn : __int_as_float(0x7f800000);
+}
+
+// ANY = true: terminate on the first accepted triangle (AnyHit); false: closest hit with tie-break.
+template <bool ANY>
+DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit) {
+  hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f;
+  if (A.triCount == 0) return false;
+  // a direction with NaN/zero length can never produce det != 0; skip the walk
+  if (!(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) return false;
+  const RayBox rb = makeRayBox(o, d);
+  int stack[EID_STACK_SIZE];
+  int sp = 0;
+  int cur = A.rootRef;
+  const float INF = __int_as_float(0x7f800000);
+  for (;;) {
+    if (cur >= 0) {
+      const float4* n = A.nodes + 4 * (size_t)cur;
+      const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+      float e0 = boxEntry(rb, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, hit.t);
+      float e1 = boxEntry(rb, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, hit.t);
+      int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+      bool h0 = e0 < INF, h1 = e1 < INF;
+      if (h0 && h1) {
+        if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
+        if (sp < EID_STACK_SIZE) stack[sp++] = c1;
+        cur = c0;
+        continue;
+      }
+      if (h0) { cur = c0; continue; }
+      if (h1) { cur = c1; continue; }
+    } else {
+      const uint32_t ref = ~(uint32_t)cur;
+      const uint32_t first = ref >> 3, count = ref & 7u;
+      for (uint32_t k = 0; k < count; ++k) {
+        const float4* tp = A.tris + 3 * (size_t)(first + k);
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        float t, u, v;
+        const uint32_t flags = __float_as_uint(c.w);
+        if (triangleTest(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), flags, o, d, tmax, t, u, v)) {
+          if (ANY) { hit.t = t; hit.tri = (int)(first + k); return true; }
+          const int prim = __float_as_int(c.y), inst = __float_as_int(c.z);
+          bool better = t < hit.t || (t == hit.t && (inst < hit.inst || (inst == hit.inst && prim < hit.prim)));
+          if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; }
+        }
+      }
+    }
+    if (sp == 0) break;
+    cur = stack[--sp];
+  }
+  return hit.tri >= 0;
+}
+
+}  // namespace eid

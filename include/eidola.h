@@ -127,7 +127,11 @@ typedef enum eid_scene_table {
   EID_TABLE_CAMERA = 7         /* SceneCamera                                 scene.cpp:777-826 */
 } eid_scene_table;
 
-/* Scene::setup + constructor (scene.hpp:60). device = CUDA ordinal. */
+/* Scene::setup + constructor (scene.hpp:60). device = CUDA ordinal, or EID_DEVICE_NONE for a host-only
+ * scene: glTF import + table building + camera maths work (and can be read back), nothing is uploaded,
+ * and eid_accel_build / eid_renderer_create on it fail with EID_ERR_CUDA.  This is NOT a CPU render
+ * path — it exists so the host-side logic can be unit-tested on machines without a GPU. */
+#define EID_DEVICE_NONE (-1)
 EID_API int  eid_scene_create(eid_scene** out, int device);
 /* Scene::load(filename) (scene.cpp:57-125): glTF 2.0 (.gltf + external .bin / data: URIs). */
 EID_API int  eid_scene_load_gltf(eid_scene* s, const char* path);

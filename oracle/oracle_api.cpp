@@ -110,6 +110,7 @@ ORC_API int64_t orc_scene_table_bytes(Scene* s, int table, uint32_t index) {
 ORC_API int orc_scene_read_table(Scene* s, int table, uint32_t index, void* dst, size_t bytes) {
   if (table == EID_TABLE_INSTANCE_DATA) {   // addresses are meaningless on the CPU: zero them, keep materialIndex
     std::vector<InstanceData> v(s->primMeshes.size());
+    if (!v.empty()) memset(v.data(), 0, v.size() * sizeof(InstanceData));   // padding bytes too
     for (size_t i = 0; i < v.size(); ++i) { v[i].vertexAddress = 0; v[i].indexAddress = 0; v[i].materialIndex = s->instMaterial[i]; }
     if (bytes > v.size() * sizeof(InstanceData)) return -1;
     memcpy(dst, v.data(), bytes); return 0;

@@ -1,0 +1,84 @@
+"""Regenerates tests/golden/*.npz.
+
+  ref_*.npz     outputs of the REFERENCE's own code (oracle/_ref/libref.so = shaders/compress.glsl C++ branch,
+                src/alias_table.hpp, shaders/host_device.h compiled from /root/reference) on seeded inputs;
+                needs /root/reference, so the vectors are committed for machines that lack it.
+  frames_*.npz  per-buffer dumps of the CPU oracle after N frames of the configs in tests/make_golden_cfg.py
+                (the oracle itself is "parity unpinned" at whole-frame level: the reference cannot run here).
+
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import common  # noqa: E402
+import make_golden_cfg as cfg  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+
+STRUCTS = ["SceneCamera", "VertexAttributes", "GltfShadeMaterial", "RtxState", "InstanceData", "LightSample", "GISample",
+           "DirectReservoir", "IndirectReservoir", "ImptSampData", "PuncLight", "TrigLight", "LightBufInfo", "Tonemapper",
+           "SunAndSky"]
+
+
+def ref_vectors():
+    R = ol.ref()
+    if R is None:
+        print("oracle/_ref/libref.so unavailable (no /root/reference): keeping the committed ref_*.npz")
+        return
+    rng = np.random.default_rng(20221212)
+    v = rng.normal(size=(20000, 3)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0, 0.6, 0.8], [0.5, 0.5, -0.70710678]], np.float32)
+    v = np.concatenate([axes, v]).astype(np.float32)
+    enc = np.array([R.ref_compress_unit_vec(float(a), float(b), float(c)) for a, b, c in v], np.uint32)
+    words = np.concatenate([enc[:4000], rng.integers(0, 2**32 - 1, 4000, dtype=np.uint64).astype(np.uint32)])
+    dec = np.zeros((words.size, 3), np.float32)
+    tmp = np.zeros(3, np.float32)
+    for i, w in enumerate(words):
+        R.ref_decompress_unit_vec(int(w), tmp.ctypes.data)
+        dec[i] = tmp
+    cols = rng.random((4000, 4)).astype(np.float32) * 1.2 - 0.1
+    packed = np.array([R.ref_pack_unorm4x8(np.ascontiguousarray(c).ctypes.data) for c in cols], np.uint32)
+    alias_in, alias_p, alias_f = [], [], []
+    for n in (1, 2, 4, 7, 33, 1000):
+        w = (rng.random(n).astype(np.float32) ** 3 * 20 + 0.01).astype(np.float32)
+        if n == 4:
+            w = np.array([1, 2, 3, 10], np.float32)
+        p, f = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        R.ref_alias_table(w.ctypes.data, n, p.ctypes.data, f.ctypes.data)
+        alias_in.append(w)
+        alias_p.append(p)
+        alias_f.append(f)
+    sizes = np.array([R.ref_sizeof(s.encode()) for s in STRUCTS], np.int32)
+    np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), vec=v, enc=enc, words=words, dec=dec, cols=cols, packed=packed,
+                        alias_in=np.concatenate(alias_in), alias_p=np.concatenate(alias_p), alias_f=np.concatenate(alias_f),
+                        alias_n=np.array([a.size for a in alias_in], np.int32), sizes=sizes)
+    print("wrote ref_vectors.npz")
+
+
+def frame_dumps():
+    for name, (maker, size, frames, over) in cfg.CONFIGS.items():
+        arrays = maker()
+        osc = ol.OracleScene()
+        osc.load_arrays(arrays)
+        orr = ol.OracleRenderer(osc, size)
+        orr.set_env_constant(common.ENV)
+        osc.update_camera(*size)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            orr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        snap = common.snapshot(orr)
+        np.savez_compressed(os.path.join(HERE, "frames_%s.npz" % name), **{k: v.view(np.uint8) if v.dtype.fields else v for k, v in snap.items()})
+        print("wrote frames_%s.npz" % name)
+
+
+if __name__ == "__main__":
+    ref_vectors()
+    frame_dumps()

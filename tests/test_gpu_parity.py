@@ -1,0 +1,301 @@
+"""-m gpu: parity of the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): G-buffer words, motion indices, reservoir `num` and the picked samples
+bit-exact; weights and radiance within 1e-3 relative (absolute floor 1e-6).  With the shared numerical
+contract the deviations are expected to be exactly 0; the tests print what they measured.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import eidola_b200 as eid
+from eidola_b200 import abi, scenes
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _have_gpu():
+    try:
+        return eid.lib().eid_device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if not _have_gpu():
+        pytest.fail("no CUDA device / libeidola.so: the product has no CPU fallback, GPU tests cannot run here")
+
+
+def _random_rays(info, n, seed):
+    rng = np.random.default_rng(seed)
+    lo = np.array(info.bboxMin[:], np.float32)
+    hi = np.array(info.bboxMax[:], np.float32)
+    ext = hi - lo
+    o = lo - 0.1 * ext + rng.random((n, 3), dtype=np.float32) * 1.2 * ext
+    t = lo + rng.random((n, 3), dtype=np.float32) * ext
+    d = t - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3], rays[:, 4:7] = o, d
+    rays[:, 3] = 1e28
+    # axis-parallel and degenerate directions too
+    rays[0, 4:7] = (1, 0, 0)
+    rays[1, 4:7] = (0, -1, 0)
+    rays[2, 4:7] = (0, 0, 0)
+    return rays
+
+
+@pytest.mark.parametrize("maker", [scenes.cube_scene, scenes.cornell_scene, scenes.small_room])
+def test_tables_match_oracle(maker):
+    import oracle_lib as ol
+    arrays = maker()
+    o = ol.OracleScene()
+    o.load_arrays(arrays)
+    p = eid.Scene(0)
+    p.load_arrays(arrays)
+    for t in (abi.TABLE_MATERIALS, abi.TABLE_PUNC_LIGHTS, abi.TABLE_TRIG_LIGHTS, abi.TABLE_LIGHT_INFO):
+        assert o.table(t).tobytes() == p.table(t).tobytes()
+    inst = p.table(abi.TABLE_INSTANCE_DATA)
+    assert np.array_equal(inst["materialIndex"], o.table(abi.TABLE_INSTANCE_DATA)["materialIndex"])
+    assert (inst["vertexAddress"] != 0).all() and (inst["indexAddress"] != 0).all()   # real device addresses
+    for pm in range(p.info().primMeshCount):
+        assert o.table(abi.TABLE_VERTICES, pm).tobytes() == p.table(abi.TABLE_VERTICES, pm).tobytes()
+        assert o.table(abi.TABLE_INDICES, pm).tobytes() == p.table(abi.TABLE_INDICES, pm).tobytes()
+
+
+@pytest.mark.parametrize("maker,n", [(scenes.cube_scene, 20000), (scenes.cornell_scene, 50000), (scenes.small_room, 100000)])
+def test_traversal_equals_brute_force(maker, n):
+    """CUDA BVH traversal == the oracle's brute-force loop over every triangle (closest hit with tie-break, any hit)."""
+    import oracle_lib as ol
+    arrays = maker()
+    o = ol.OracleScene(use_bvh=False)
+    o.load_arrays(arrays)
+    p = eid.Scene(0)
+    p.load_arrays(arrays)
+    acc = eid.AccelStructure()
+    acc.create(p)
+    rays = _random_rays(p.info(), n, 11)
+    hg, ho = acc.trace(rays), o.trace(rays)
+    assert hg.tobytes() == ho.tobytes(), "closest-hit mismatch in %d rays" % int((hg != ho).sum())
+    assert (hg["hitT"] < 1e27).mean() > 0.3
+    rays[:, 3] = np.where(ho["hitT"] < 1e27, ho["hitT"] * np.float32(1.5), 5.0).astype(np.float32)
+    rays[::3, 3] = (ho["hitT"][::3] * np.float32(0.5)).astype(np.float32)   # tmax short of the hit: must be unoccluded
+    ag, ao = acc.trace(rays, any_hit=True), o.trace(rays, any_hit=True)
+    assert np.array_equal(ag["hitT"], ao["hitT"])
+
+
+def test_oracle_bvh_equals_brute_force():
+    """Sanity of the checker itself: the oracle's BVH path and its brute-force path agree."""
+    import oracle_lib as ol
+    arrays = scenes.small_room()
+    a, b = ol.OracleScene(use_bvh=True), ol.OracleScene(use_bvh=False)
+    a.load_arrays(arrays)
+    b.load_arrays(arrays)
+    rays = _random_rays(a.info(), 50000, 5)
+    assert a.trace(rays).tobytes() == b.trace(rays).tobytes()
+
+
+def _run_frames(arrays, size, frames, tag, orbit=False, **state_over):
+    osc, orr, psc, acc, prr = common.make_pair(arrays, size)
+    for s in (osc, psc):
+        s.update_camera(*size)     # contract: one updateCamera before frame 0 so last* matrices are valid
+    info = psc.info()
+    cam = arrays.camera
+    worst = {}
+    for f in range(frames):
+        if orbit:
+            a = np.deg2rad(0.5 * f)
+            e = np.array(cam["eye"], np.float64)
+            eye = (e[0] * np.cos(a) - e[2] * np.sin(a), e[1], e[0] * np.sin(a) + e[2] * np.cos(a))
+            for s in (osc, psc):
+                s.set_lookat(eye, cam["center"], cam["up"], np.rad2deg(cam["yfov"]))
+        for s in (osc, psc):
+            s.update_camera(*size)
+        assert osc.table(abi.TABLE_CAMERA).tobytes() == psc.table(abi.TABLE_CAMERA).tobytes()
+        st = common.frame_state(size[0], size[1], info, f, **state_over)
+        orr.run(st, f)
+        prr.run(st, f)
+        prr.sync()
+        rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "%s frame %d" % (tag, f))
+        for k, v in rep.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+        so, sp = orr.stats(), prr.stats()
+        assert (so.closestHitRays, so.anyHitRays, so.primaryHits) == (sp.closestHitRays, sp.anyHitRays, sp.primaryHits)
+    print("%s: worst relative deviation vs oracle over %d frames: %s" % (tag, frames, worst))
+    return worst
+
+
+def test_c1_cube_direct_only():
+    """BASELINE config 0: single cube, 256x256, RIS M=1, no denoise, direct only."""
+    _run_frames(scenes.cube_scene(), (256, 256), 1, "C1", ReSTIRState=abi.eRIS, RISSampleNum=1, denoise=0)
+
+
+def test_c2_cornell_temporal_di_gi():
+    """BASELINE config 1 scene at a size the oracle renders in seconds: temporal DI + GI + denoise, 4 frames."""
+    _run_frames(scenes.cornell_scene(), (320, 180), 4, "C2", maxDepth=3)
+
+
+def test_small_room_full_pipeline_static_and_orbit():
+    """Miniature of the headline C3 scene (noise height-field room, emissive quads): full pipeline, depth 4."""
+    _run_frames(scenes.small_room(), (256, 144), 3, "room-static")
+    _run_frames(scenes.small_room(), (256, 144), 3, "room-orbit", orbit=True)
+
+
+@pytest.mark.parametrize("over", [dict(ReSTIRState=abi.eNone), dict(ReSTIRState=abi.eRIS, RISSampleNum=8), dict(MIS=0),
+                                  dict(modulate=0), dict(denoise=0), dict(maxDepth=1), dict(debugging_mode=abi.eNormal),
+                                  dict(reservoirClamp=2), dict(fireflyClampThreshold=0.5)])
+def test_state_variants(over):
+    _run_frames(scenes.cornell_scene(), (160, 96), 3, "variant %s" % over, **over)
+
+
+@pytest.mark.parametrize("size", [(8, 8), (17, 9), (130, 70), (64, 2)])
+def test_ragged_sizes(size):
+    """Odd / tiny sizes: partial 8x8 tiles, W/2 truncation, bottom tile row that relies on the early-return."""
+    _run_frames(scenes.cornell_scene(), size, 2, "size %dx%d" % size, maxDepth=2)
+
+
+def test_state_size_smaller_than_allocation():
+    """De-scaling (sample_example.cpp:396-401): RtxState.size below the allocated size; reservoirs are pitched by size.x."""
+    arrays = scenes.cornell_scene()
+    osc, orr, psc, acc, prr = common.make_pair(arrays, (200, 120))
+    info = psc.info()
+    for f in range(3):
+        for s in (osc, psc):
+            s.update_camera(100, 60)
+        st = common.frame_state(100, 60, info, f)
+        orr.run(st, f)
+        prr.run(st, f)
+        common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "descaled frame %d" % f)
+
+
+def test_band_sharded_trace_equals_full_frame():
+    """Multi-GPU decomposition on one device: two renderers trace disjoint row bands, the exchange buffers are
+    stitched (what the all-gather does), post-processing runs on the full frame -> identical to a single run."""
+    arrays = scenes.small_room()
+    size = (256, 144)
+    psc = eid.Scene(0)
+    psc.load_arrays(arrays)
+    acc = eid.AccelStructure()
+    acc.create(psc)
+    full, a, b = eid.Renderer(), eid.Renderer(), eid.Renderer()
+    for r in (full, a, b):
+        r.create(size, psc, acc)
+        r.set_env_constant(common.ENV)
+    a.set_band(0, 80)
+    b.set_band(80, 144)
+    info = psc.info()
+    psc.update_camera(*size)
+    exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_MOTION, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A, abi.BUF_THIS_DIRECT_RESV,
+                abi.BUF_THIS_INDIRECT_RESV]
+    for f in range(3):
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f)
+        full.run(st, f)
+        a.run_trace(st, f)
+        b.run_trace(st, f)
+        for which in exchange:
+            ba, bb = a.read(which).view(np.uint8).copy(), b.read(which).view(np.uint8)
+            _, off, n = b.band_range(which)
+            ba[off:off + n] = bb[off:off + n]
+            a.write(which, ba)
+            b.write(which, ba)
+        a.run_post(st, f)
+        b.run_post(st, f)
+        ref = common.snapshot(full)
+        for r in (a, b):
+            got = common.snapshot(r)
+            for k in ref:
+                assert got[k].tobytes() == ref[k].tobytes(), "band-sharded %s differs from the full-frame run (frame %d)" % (k, f)
+
+
+def test_render_host_end_to_end_and_checkpoint():
+    """eid_renderer_render_host (host buffers in, host images out) == run + read; history write-back resumes bit-exactly."""
+    arrays = scenes.cornell_scene()
+    size = (128, 72)
+    psc = eid.Scene(0)
+    psc.load_arrays(arrays)
+    acc = eid.AccelStructure()
+    acc.create(psc)
+    r1, r2 = eid.Renderer(), eid.Renderer()
+    for r in (r1, r2):
+        r.create(size, psc, acc)
+        r.set_env_constant(common.ENV)
+    info = psc.info()
+    psc.update_camera(*size)
+    d = np.zeros((size[1], size[0], 4), np.float32)
+    i = np.zeros_like(d)
+    for f in range(2):
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f)
+        r1.run(st, f)
+        r2.render_host(psc.get_camera(), st, f, d.ctypes.data, i.ctypes.data)
+        assert r1.read(abi.BUF_DIRECT).tobytes() == d.tobytes() and r1.read(abi.BUF_INDIRECT).tobytes() == i.tobytes()
+    # checkpoint = cross-frame state (G-buffer + reservoirs); restore into a fresh renderer and continue
+    r3 = eid.Renderer()
+    r3.create(size, psc, acc)
+    r3.set_env_constant(common.ENV)
+    psc.update_camera(*size)
+    st = common.frame_state(size[0], size[1], info, 2)
+    # after frame 1 (set 0): this* = [1]; frame 2 uses set 1 -> last* = [1]. Seed r3 so its "last" buffers hold r1's "this".
+    r3.run(common.frame_state(size[0], size[1], info, 1), 1)          # selects the same ping-pong parity as r1
+    for which in (abi.BUF_THIS_GBUFFER, abi.BUF_THIS_DIRECT_RESV, abi.BUF_THIS_INDIRECT_RESV):
+        r3.write(which, r1.read(which))
+    r1.run(st, 2)
+    r3.run(st, 2)
+    for k, which in common.BUFFERS:
+        assert r1.read(which).tobytes() == r3.read(which).tobytes(), k
+
+
+def test_golden_frames():
+    """Committed oracle dumps (tests/golden/frames_*.npz, made by tests/golden/make_golden.py) == CUDA output."""
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    files = sorted(f for f in os.listdir(gdir) if f.startswith("frames_") and f.endswith(".npz"))
+    assert files, "no golden frame fixtures"
+    import make_golden_cfg as cfg
+    for fn in files:
+        z = np.load(os.path.join(gdir, fn))
+        name = fn[len("frames_"):-4]
+        maker, size, frames, over = cfg.CONFIGS[name]
+        arrays = maker()
+        psc = eid.Scene(0)
+        psc.load_arrays(arrays)
+        acc = eid.AccelStructure()
+        acc.create(psc)
+        prr = eid.Renderer()
+        prr.create(size, psc, acc)
+        prr.set_env_constant(common.ENV)
+        psc.update_camera(*size)
+        info = psc.info()
+        for f in range(frames):
+            psc.update_camera(*size)
+            prr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        got = common.snapshot(prr)
+        want = {k: z[k].view(got[k].dtype) if got[k].dtype.fields is None else np.frombuffer(z[k].tobytes(), got[k].dtype) for k in got}
+        common.compare_snapshots(got, want, "golden " + name)
+
+
+def test_error_behaviour_gpu():
+    psc = eid.Scene(0)
+    with pytest.raises(eid.EidolaError):
+        eid.AccelStructure().create(psc)            # no scene loaded
+    psc.load_arrays(scenes.cube_scene())
+    acc = eid.AccelStructure()
+    acc.create(psc)
+    r = eid.Renderer()
+    r.create((64, 64), psc, acc)
+    info = psc.info()
+    psc.update_camera(64, 64)
+    with pytest.raises(eid.EidolaError):
+        r.run(common.frame_state(128, 64, info, 0), 0)                       # size beyond the allocation
+    with pytest.raises(eid.EidolaError):
+        r.run(common.frame_state(64, 64, info, 0, ReSTIRState=abi.eSpatial), 0)   # outside the contract
+    with pytest.raises(eid.EidolaError):
+        r.run(common.frame_state(64, 64, info, 0, environmentProb=0.25), 0)  # needs the HDR map
+    with pytest.raises(eid.EidolaError):
+        r.set_band(8, 64)                                                     # band edges must be multiples of 16
+    r.run(common.frame_state(64, 64, info, 0), 0)                             # still usable after errors
+    r.sync()
