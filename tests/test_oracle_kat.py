@@ -1,0 +1,185 @@
+"""CPU tests that pin the oracle: known-answer vectors derived from the reference source,
+the reference's own stand-alone-compilable files (oracle/_ref/libref.so, built from /root/reference when it
+exists) and the committed outputs of those files (tests/golden/ref_vectors.npz) for machines without it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import oracle_lib as ol  # noqa: E402
+from make_golden import STRUCTS  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz")
+
+
+def test_oracle_compiled_without_fma_contraction():
+    assert ol.lib().orc_fp_contract_selftest() == 0
+
+
+def test_tea_known_answers():     # random.glsl:34-48
+    L = ol.lib()
+    assert [L.orc_tea(a, b) for a, b in ((0, 0), (1, 0), (0, 1), (1037760, 12345))] == [0x741c187d, 0x8da6b311, 0x70d3aef1, 0x6230029f]
+
+
+def test_pcg_rand_chain():        # random.glsl:59-65, 98-102
+    L = ol.lib()
+    st, v = np.zeros(4, np.uint32), np.zeros(4, np.float32)
+    L.orc_rand_chain(L.orc_tea(0, 0), 4, st.ctypes.data, v.ctypes.data)
+    assert list(st) == [0x46dfb666, 0x5477ab23, 0xa3758fc4, 0x92110c99]
+    assert np.allclose(v, [0.560322881, 0.745306849, 0.335232019, 0.887807727], rtol=0, atol=1e-9)
+    assert (v >= 0).all() and (v < 1).all()
+
+
+def test_hash8bit():              # common.glsl:141-143
+    L = ol.lib()
+    assert [L.orc_hash8bit(x) for x in (0, 1, 255, 256, 257, 0x1234)] == [0x0, 0x01000000, 0xff000000, 0x01000000, 0x0, 0x26000000]
+
+
+def test_struct_sizes_match_reference_header():
+    want = dict(SceneCamera=336, VertexAttributes=32, GltfShadeMaterial=80, RtxState=100, InstanceData=24, LightSample=28,
+                GISample=64, DirectReservoir=36, IndirectReservoir=76, ImptSampData=16, PuncLight=80, TrigLight=96,
+                LightBufInfo=16, Tonemapper=48, SunAndSky=96)
+    L = ol.lib()
+    for k, v in want.items():
+        assert L.orc_sizeof(k.encode()) == v, k
+    z = np.load(GOLD)
+    assert dict(zip(STRUCTS, z["sizes"].tolist())) == want          # sizes the reference's own header compiled to
+    R = ol.ref()
+    if R is not None:
+        for k, v in want.items():
+            assert R.ref_sizeof(k.encode()) == v, k
+
+
+def _oracle_codec(z):
+    L = ol.lib()
+    enc = np.array([L.orc_compress_unit_vec(float(a), float(b), float(c)) for a, b, c in z["vec"]], np.uint32)
+    dec = np.zeros((z["words"].size, 3), np.float32)
+    tmp = np.zeros(3, np.float32)
+    for i, w in enumerate(z["words"]):
+        L.orc_decompress_unit_vec(int(w), tmp.ctypes.data)
+        dec[i] = tmp
+    packed = np.array([L.orc_pack_unorm4x8(np.ascontiguousarray(c).ctypes.data) for c in z["cols"]], np.uint32)
+    return enc, dec, packed
+
+
+def test_oct_codec_and_pack_match_reference_vectors():
+    """compress_unit_vec / decompress_unit_vec / packUnorm4x8 (compress.glsl C++ branch) — bit-exact."""
+    z = np.load(GOLD)
+    enc, dec, packed = _oracle_codec(z)
+    assert np.array_equal(enc, z["enc"])
+    assert dec.tobytes() == z["dec"].tobytes()
+    assert np.array_equal(packed, z["packed"])
+    assert enc[6] == 0xb6da7fff                                   # (0, 0.6, 0.8), SURVEY.md §4
+    assert np.allclose(dec[6], (0, 0.6, 0.8), atol=1e-4)
+
+
+def test_alias_table_matches_reference_vectors():
+    """DiscreteSampler1D<float> (alias_table.hpp:21-63) — bit-exact (prob, failId) per cell."""
+    z = np.load(GOLD)
+    L = ol.lib()
+    off = 0
+    for n in z["alias_n"]:
+        w = np.ascontiguousarray(z["alias_in"][off:off + n])
+        p, f = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        L.orc_alias_table(w.ctypes.data, int(n), p.ctypes.data, f.ctypes.data)
+        assert p.tobytes() == z["alias_p"][off:off + n].tobytes() and np.array_equal(f, z["alias_f"][off:off + n])
+        if n == 4:
+            assert list(p) == [0.25, 0.5, 0.75, 1.0] and list(f) == [3, 3, 3, 3]      # {1,2,3,10}, SURVEY.md §4
+        off += n
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_live_reference_library_agrees_with_committed_vectors():
+    """The committed ref_vectors.npz really is what the reference's code produces (re-run it live)."""
+    R = ol.ref()
+    assert R is not None
+    z = np.load(GOLD)
+    enc = np.array([R.ref_compress_unit_vec(float(a), float(b), float(c)) for a, b, c in z["vec"][:3000]], np.uint32)
+    assert np.array_equal(enc, z["enc"][:3000])
+    tmp = np.zeros(3, np.float32)
+    for w, want in zip(z["words"][:3000], z["dec"][:3000]):
+        R.ref_decompress_unit_vec(int(w), tmp.ctypes.data)
+        assert tmp.tobytes() == want.tobytes()
+
+
+def test_offset_ray_properties():  # common.glsl:98-113
+    L = ol.lib()
+    rng = np.random.default_rng(3)
+    out = np.zeros(3, np.float32)
+    for _ in range(200):
+        p = (rng.normal(size=3) * 10).astype(np.float32)
+        n = rng.normal(size=3)
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        L.orc_offset_ray(p.ctypes.data, n.ctypes.data, out.ctypes.data)
+        assert np.dot(out.astype(np.float64) - p, n) > 0            # moved to the normal's side
+        assert np.abs(out - p).max() < 1e-2 * max(1.0, np.abs(p).max())
+
+
+def test_detmath_accuracy():
+    """The deterministic libm stand-ins are accurate enough to be drop-ins for the GLSL built-ins."""
+    L = ol.lib()
+    x = np.linspace(-20, 20, 200001).astype(np.float32)
+    y = np.zeros_like(x)
+    out = np.zeros_like(x)
+    for op, fn, tol in ((0, np.sin, 2e-7), (1, np.cos, 2e-7)):
+        L.orc_detmath(op, x.ctypes.data, y.ctypes.data, x.size, out.ctypes.data)
+        assert np.abs(out - fn(x.astype(np.float64))).max() < tol
+    xe = np.linspace(-80, 80, 200001).astype(np.float32)
+    L.orc_detmath(2, xe.ctypes.data, y.ctypes.data, xe.size, out.ctypes.data)
+    assert np.abs(out / np.exp(xe.astype(np.float64)) - 1).max() < 2e-7
+    xa = np.linspace(-1, 1, 100001).astype(np.float32)
+    o2 = np.zeros_like(xa)
+    L.orc_detmath(5, xa.ctypes.data, xa.ctypes.data, xa.size, o2.ctypes.data)
+    assert np.abs(o2 - np.arcsin(xa.astype(np.float64))).max() < 5e-7
+    L.orc_detmath(6, xa.ctypes.data, xa.ctypes.data, xa.size, o2.ctypes.data)
+    assert np.abs(o2 - np.arccos(xa.astype(np.float64))).max() < 5e-7
+
+
+def test_oracle_golden_frames_are_reproducible():
+    """The committed frame dumps are what the oracle produces today (guards against silent oracle drift)."""
+    import common
+    import make_golden_cfg as cfg
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for name, (maker, size, frames, over) in cfg.CONFIGS.items():
+        z = np.load(os.path.join(gdir, "frames_%s.npz" % name))
+        osc = ol.OracleScene()
+        osc.load_arrays(maker())
+        orr = ol.OracleRenderer(osc, size)
+        orr.set_env_constant(common.ENV)
+        osc.update_camera(*size)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            orr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        for k, v in common.snapshot(orr).items():
+            assert v.view(np.uint8).tobytes() == z[k].view(np.uint8).tobytes(), (name, k)
+
+
+def test_oracle_invariants():
+    """Size-independent properties (SURVEY.md §8c iv): reservoir clamps, finite non-negative images, sky texels."""
+    import common
+    from eidola_b200 import abi, scenes
+    size = (160, 96)
+    osc = ol.OracleScene()
+    osc.load_arrays(scenes.small_room())
+    orr = ol.OracleRenderer(osc, size)
+    orr.set_env_constant(common.ENV)
+    osc.update_camera(*size)
+    info = osc.info()
+    for f in range(4):
+        osc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, reservoirClamp=2)
+        orr.run(st, f)
+        s = common.snapshot(orr)
+        assert s["direct_resv"]["num"].max() <= st.RISSampleNum * st.reservoirClamp
+        assert s["indirect_resv"]["num"].max() <= 2 * st.reservoirClamp
+        for k in ("direct", "indirect"):
+            assert np.isfinite(s[k]).all() and (s[k] >= 0).all()
+        assert (s["direct_resv"]["weight"] >= 0).all() and (s["indirect_resv"]["weight"] >= 0).all()
+    st2 = orr.stats()
+    n, ni = size[0] * size[1], (size[0] // 2) * (size[1] // 2)
+    assert st2.closestHitRays <= n + ni * st.maxDepth and st2.anyHitRays <= n + ni * (st.maxDepth - 1)   # ray model of SURVEY §8(d)
