@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — Mray/s + fps of one Renderer::run frame at 1080p on the procedural 1 M-triangle / 1 k-emissive
+scene (BASELINE.json configs[2]), on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                          the reference algorithm on the host CPU (the oracle;
+                                                                  the Vulkan reference cannot run here)
+
+A step = one frame = the reference's 12 dispatches (direct_stage, indirect_stage, denoise_direct x4,
+denoise_indirect x5, compose).  `value` = rays actually issued (ClosestHit + AnyHit, counted on the device) by all
+ranks / wall time of the K timed frames, inputs resident in HBM.  `e2e` = the same through eid_renderer_render_host
+with HOST buffers: camera + RtxState uploaded and both result images downloaded to pinned memory every frame.
+N > 1 (torchrun): rank r traces row band r (direct + indirect stage), ONE exchange step all-gathers the pre-denoise
+buffers over NCCL, every rank then denoises + composes the full frame (SURVEY.md §8e alternative).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+MAX_DEPTH = 3
+WORKLOAD = "C3: procedural closed room, 707x707-quad noise height-field floor (999,698 tris) + 10 wall tris + 1,000 emissive tris, " \
+           "1920x1080, ReSTIR DI+GI temporal, M=4, maxDepth 3, MIS, denoise on (K1..K5), static camera"
+
+
+def scene_arrays(quick=False):
+    from eidola_b200 import scenes
+    if quick:
+        return scenes.heightfield_room(quads=96, n_light_quads=50)
+    return scenes.heightfield_room()          # 707 quads, 500 light quads = 1000 emissive triangles
+
+
+def frame_state(info, frame, w=W, h=H):
+    from eidola_b200 import abi
+    return abi.default_rtx_state(
+        w, h, environmentProb=0.0, time=1000 + 16 * frame, maxDepth=MAX_DEPTH,
+        fireflyClampThreshold=float(np.float32(4 * np.pi)), envMapLuminIntegInv=float(np.float32(1 / np.pi)),
+        lightLuminIntegInv=float(np.float32(1.0) / (np.float32(info.trigLightWeight) + np.float32(info.puncLightWeight))))
+
+
+ENV = (0.25, 0.25, 0.25)
+
+# Algorithmic screen-space bytes per pixel of each stage (N = W*H, indirect stages per N/4)
+SCREEN_BYTES_PER_PX = {"direct_stage": 124.0, "indirect_stage": 51.0, "denoise_direct": 192.0, "denoise_indirect": 60.0, "compose": 68.0}
+NODE_BYTES, TRI_BYTES, HIT_GATHER_BYTES = 64, 48, 108 + 80
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_run(arrays, w, h, frames, warm):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    osc = ol.OracleScene()
+    t0 = time.time()
+    osc.load_arrays(arrays)
+    load_s = time.time() - t0
+    orr = ol.OracleRenderer(osc, (w, h))
+    orr.set_env_constant(ENV)
+    osc.update_camera(w, h)
+    info = osc.info()
+    rays, secs, per_kernel = 0, 0.0, np.zeros(5)
+    for f in range(warm + frames):
+        osc.update_camera(w, h)
+        st = frame_state(info, f, w, h)
+        t0 = time.time()
+        orr.run(st, f)
+        dt = time.time() - t0
+        if f >= warm:
+            s = orr.stats()
+            rays += s.closestHitRays + s.anyHitRays
+            secs += dt
+            per_kernel += np.array(s.kernelMs[:])
+    return dict(mrays=rays / secs / 1e6, ms_per_frame=1e3 * secs / frames, cores=ol.lib().orc_num_threads(), load_s=load_s,
+                kernel_ms=(per_kernel / frames).tolist(), rays_per_frame=rays / frames)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sw, sh = (W // 4, H // 4) if not args.quick else (W // 8, H // 8)
+    arrays = scene_arrays(args.quick)
+    r = oracle_run(arrays, sw, sh, args.steps, args.warmup)
+    sample = "%d frames of the same scene/state at %dx%d (1/16 of the 1080p pixels per step), all host threads" % (args.steps, sw, sh)
+    line = {
+        "impl": "reference", "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": r["mrays"], "unit": "Mray/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_arm": "CPU oracle (C++/OpenMP restatement of the reference shaders; the Vulkan app cannot run here)",
+                   "sample": sample},
+        "cpu_baseline": {"value": r["mrays"], "unit": "Mray/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["mrays"], "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fps": 1e3 / r["ms_per_frame"], "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------------------------
+class DevBuf:
+    """Minimal __cuda_array_interface__ wrapper so torch can alias library-owned device memory (NCCL plumbing)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_cuda(args):
+    import torch
+    import eidola_b200 as eid
+    from eidola_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available() or eid.lib().eid_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - this framework has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    # a dedicated (non-default) torch stream: its handle is non-null, so the library enqueues on it and the
+    # torch.cuda.Event pair below brackets exactly the kernels of the timed frames
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    w, h = (W, H) if not args.quick else (W // 4, H // 4 // 16 * 16)
+    arrays = scene_arrays(args.quick)
+    scene = eid.Scene(local)
+    scene.load_arrays(arrays)
+    accel = eid.AccelStructure()
+    accel.create(scene)
+    ainfo = accel.info()
+    info = scene.info()
+
+    # band partition: rows per rank rounded up to 16; the allocation is padded so every rank's chunk has equal size
+    band = ((h + world - 1) // world + 15) // 16 * 16
+    alloc_h = band * world if world > 1 else h
+    rr = eid.Renderer()
+    rr.create((w, alloc_h), scene, accel, stream=stream.cuda_stream)
+    rr.set_env_constant(ENV)
+    if world > 1:
+        rr.set_band(min(rank * band, alloc_h), min((rank + 1) * band, alloc_h))
+    exch = []
+    if world > 1:
+        for which in (abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A):
+            base, off, n = rr.band_range(which)
+            total = n * world
+            exch.append((which, total, n))
+
+    def exchange_tensors():
+        out = []
+        for which, total, n in exch:
+            base, off, nb = rr.band_range(which)       # pointers flip with the ping-pong set: re-query per frame
+            full = torch.as_tensor(DevBuf(base, total), device=dev)
+            out.append((full, full[off:off + nb]))
+        return out
+
+    scene.update_camera(w, h)
+
+    def step(frame, e2e_bufs=None):
+        scene.update_camera(w, h)
+        st = frame_state(info, frame, w, h)
+        if world == 1:
+            if e2e_bufs is None:
+                rr.run(st, frame)
+            else:
+                rr.render_host(scene.get_camera(), st, frame, e2e_bufs[0].data_ptr(), e2e_bufs[1].data_ptr())
+        else:
+            rr.run_trace(st, frame)
+            for full, mine in exchange_tensors():
+                dist.all_gather_into_tensor(full, mine)
+            rr.run_post(st, frame)
+            if e2e_bufs is not None:
+                d, i = rr.outputs()
+                n = w * h * 16
+                e2e_bufs[0].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(d, n), device=dev), non_blocking=True)
+                e2e_bufs[1].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(i, n), device=dev), non_blocking=True)
+                stream.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(nsteps, first_frame, e2e_bufs=None, profiling=0):
+        rr.set_profiling(profiling)
+        s0 = rr.stats()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = np.zeros(5)
+        e0.record(stream)
+        for k in range(nsteps):
+            step(first_frame + k, e2e_bufs)
+            if profiling:
+                kms += np.array(rr.stats().kernelMs[:])     # syncs; only used in the separate per-kernel pass
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        s1 = rr.stats()
+        rays = (s1.totalClosestHitRays + s1.totalAnyHitRays) - (s0.totalClosestHitRays + s0.totalAnyHitRays)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            rt = torch.tensor([rays], device=dev, dtype=torch.int64)
+            dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+            rays = int(rt.item())
+        return ms, rays, kms / max(1, nsteps)
+
+    frame = 0
+    for _ in range(max(3, args.warmup)):
+        step(frame)
+        frame += 1
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)
+    ms, rays, _ = timed(args.steps, frame)
+    frame += args.steps
+    clocks = sampler.finish() if sampler else None
+    value = rays / (ms * 1e-3) / 1e6
+
+    # end to end: host buffers, H2D of the per-frame inputs + D2H of both result images inside the timed region
+    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for _ in range(2):
+        step(frame, pinned)
+        frame += 1
+    e2e_steps = max(3, min(args.steps, 16))
+    ems, erays, _ = timed(e2e_steps, frame, pinned)
+    frame += e2e_steps
+    e2e_value = erays / (ems * 1e-3) / 1e6
+
+    # per-kernel pass (CUDA events inside the library around every stage, same frames/state sequence) + visit counters
+    ksteps = max(3, min(args.steps, 16))
+    _, _, kms = timed(ksteps, frame, None, profiling=1)
+    frame += ksteps
+    rr.set_profiling(2)
+    step(frame)
+    vs = rr.stats()
+    frame += 1
+    rr.set_profiling(0)
+
+    line = None
+    if rank == 0:
+        n_px = w * h
+        peak, peak_src = measured_peak_hbm()
+        names = abi.KERNEL_NAMES
+        launches = [max(1, int(v)) for v in vs.kernelLaunches[:]]   # 1, 1, 1 prep + 4 passes, 5 passes, 1
+        dom = int(np.argmax(kms))
+        screen = {k: SCREEN_BYTES_PER_PX[k] * n_px for k in names}
+        band_frac = 1.0 / world
+        trace_bytes = vs.nodeVisits * NODE_BYTES + vs.triangleTests * TRI_BYTES + (vs.closestHitRays * HIT_GATHER_BYTES)
+        # split traversal bytes between K1 and K2 by their ray counts (K1: 1 closest + <=1 any per hit pixel)
+        k1_rays = min(vs.closestHitRays, int(n_px * band_frac)) + vs.primaryHits
+        tot_rays = max(1, vs.closestHitRays + vs.anyHitRays)
+        algo = {}
+        for i, k in enumerate(names):
+            b = screen[k] * (band_frac if i < 2 else 1.0)
+            if i == 0:
+                b += trace_bytes * k1_rays / tot_rays
+            if i == 1:
+                b += trace_bytes * (tot_rays - k1_rays) / tot_rays
+            algo[k] = b / launches[i]            # per launch
+        per_launch_ms = [kms[i] / launches[i] for i in range(5)]
+        achieved = algo[names[dom]] / (per_launch_ms[dom] * 1e-3) / 1e9 if per_launch_ms[dom] > 0 else 0.0
+        kernels = {k: {"ms_per_frame": float(kms[i]), "launches": launches[i], "algorithmic_MB_per_launch": algo[k] / 1e6,
+                       "achieved_GBps": (algo[k] / (per_launch_ms[i] * 1e-3) / 1e9) if per_launch_ms[i] > 0 else None,
+                       "frac_of_hbm_peak": (algo[k] / (per_launch_ms[i] * 1e-3) / 1e9 / peak) if per_launch_ms[i] > 0 else None}
+                   for i, k in enumerate(names)}
+        line = {
+            "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": value, "unit": "Mray/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
+                       "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
+                       "parallelism": "row bands x%d + 1 all-gather step of pre-denoise buffers" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: each frame streams ~1.0 GB of screen-space buffers + ~0.14 GB of BVH/triangles/vertices (L2 = 126 MB)",
+                       "bvh": {"nodes": int(ainfo.nodeCount), "node_MB": ainfo.nodeBytes / 1e6, "tri_MB": ainfo.triBytes / 1e6,
+                               "height": int(ainfo.maxDepth), "build_ms": float(ainfo.buildMs)}},
+            "fps": 1e3 / (ms / args.steps),
+            "rays_per_frame": rays / args.steps,
+            "e2e": {"value": e2e_value, "unit": "Mray/s", "h2d_bytes_per_step": C.sizeof(abi.SceneCamera) + C.sizeof(abi.RtxState),
+                    "d2h_bytes_per_step": 2 * w * h * 16, "ms_per_step": ems / e2e_steps, "fps": 1e3 / (ems / e2e_steps), "steps": e2e_steps},
+            "gpu_launches": int(sum(launches)) * args.steps, "launches_per_frame": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "achieved = algorithmic bytes (screen-space bytes of SURVEY 8d + counted BVH node/triangle fetches + per-hit "
+                                 "vertex/material gathers) / CUDA-event time of that kernel; at 1 M triangles the traversal working set is "
+                                 "L2-resident, so this is an L2/latency-bound kernel measured against the HBM roof"},
+            "kernels": kernels,
+            "visits_per_ray": {"nodes": vs.nodeVisits / tot_rays, "triangles": vs.triangleTests / tot_rays},
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # reference algorithm on the host cores, bounded sample of the same workload (reported, not a target)
+        sw, sh = (w // 4, h // 4)
+        r = oracle_run(arrays, sw, sh, 2, 1)
+        line["cpu_baseline"] = {"value": r["mrays"], "unit": "Mray/s", "cores": r["cores"], "kind": "port",
+                                "sample": "2 frames (after 1 warm-up) of the same scene/state at %dx%d = 1/16 of the pixels; oracle BVH build %.1fs not included" % (sw, sh, r["load_s"]),
+                                "ms_per_frame_at_sample": r["ms_per_frame"]}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="eidola", choices=["eidola", "reference"])
+    ap.add_argument("--quick", action="store_true", help="tiny scene/resolution (plumbing check, not a benchmark)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

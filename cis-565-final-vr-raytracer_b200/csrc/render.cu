@@ -30,24 +30,31 @@ struct FrameParams {
   float* thisIR; const float* lastIR;     // IndirectReservoir records, 19 floats each, pitch st.size.x/2
   float4* directImg; float4* indirectImg;
   float4* dirA; float4* dirB; float4* indA; float4* indB;
+  float4* geomPos; float4* geomNrm;       // denoiser geometry planes (full res): pos.xyz + hash bits / normal.xyz
+  float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
   float env[3];
   int pitch, allocH;                      // allocation size of the 2-D images
   int y0, y1;                             // full-res row band traced by this rank
-  unsigned long long* counters;           // [0] closest-hit rays, [1] any-hit rays, [2] primary hits
+  unsigned long long* counters;           // per frame: [0] closest-hit rays, [1] any-hit rays, [2] primary hits, [3] inner-node
+                                          // visits, [4] triangle tests (STATS kernels only); since creation: [5] closest, [6] any
 };
+#define EID_NUM_COUNTERS 8
 
-struct RayCounters { unsigned int closest, any, primary; };
+struct RayCounters { unsigned int closest, any, primary, nodes, tris; };
 
+template <bool STATS>
 DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
-  unsigned int a = c.closest, b = c.any, d = c.primary;
+  unsigned int a = c.closest, b = c.any, d = c.primary, n = c.nodes, t = c.tris;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (STATS) { n += __shfl_xor_sync(0xffffffffu, n, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
   }
   if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) {
-    if (a) atomicAdd(&P.counters[0], (unsigned long long)a);
-    if (b) atomicAdd(&P.counters[1], (unsigned long long)b);
+    if (a) { atomicAdd(&P.counters[0], (unsigned long long)a); atomicAdd(&P.counters[5], (unsigned long long)a); }
+    if (b) { atomicAdd(&P.counters[1], (unsigned long long)b); atomicAdd(&P.counters[6], (unsigned long long)b); }
     if (d) atomicAdd(&P.counters[2], (unsigned long long)d);
+    if (STATS) { if (n) atomicAdd(&P.counters[3], (unsigned long long)n); if (t) atomicAdd(&P.counters[4], (unsigned long long)t); }
   }
 }
 
@@ -62,21 +69,23 @@ DEV float4 loadImg(const float4* img, const FrameParams& P, int x, int y) {
 }
 
 // ClosestHit (traceray_rq.glsl:108-147) on opaque geometry
+template <bool STATS>
 DEV bool closestHit(const FrameParams& P, f3 o, f3 d, Payload& prd, RayCounters& rc) {
   rc.closest++;
   RayHit h;
-  if (!traverse<false>(P.accel, o, d, EID_INFINITY, h)) { prd.hitT = EID_INFINITY; return false; }
+  if (!traverse<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris)) { prd.hitT = EID_INFINITY; return false; }
   prd.hitT = h.t; prd.baryU = h.u; prd.baryV = h.v; prd.primitiveID = h.prim; prd.instanceID = h.inst;
   prd.instanceCustomIndex = P.sc.instances[h.inst].primMesh;
   return true;
 }
 // Occlusion (pathtrace.glsl:18-22) -> AnyHit (traceray_rq.glsl:153-185)
+template <bool STATS>
 DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float dist, RayCounters& rc) {
   rc.any++;
   float tmax = __fsub_rn(__fsub_rn(__fsub_rn(dist, fabsf(__fsub_rn(origin.x, surfacePos.x))), fabsf(__fsub_rn(origin.y, surfacePos.y))),
                          fabsf(__fsub_rn(origin.z, surfacePos.z)));
   RayHit h;
-  return traverse<true>(P.accel, origin, dir, tmax, h);
+  return traverse<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
 }
 
 DEV f3 envRadiance(const FrameParams& P) { return mk3(P.env[0], P.env[1], P.env[2]) * P.st.hdrMultiplier; }   // pathtrace.glsl:40-47, constant env
@@ -104,10 +113,11 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 // =================================================================================================
 // K1 — direct_stage.comp
 // =================================================================================================
+template <bool STATS>
 __global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = P.y0 + blockIdx.y * 8 + threadIdx.y;
-  RayCounters rc = {0, 0, 0};
+  RayCounters rc = {0, 0, 0, 0, 0};
   const int W = P.st.size.x, H = P.st.size.y;
   if (x < W && y < H && y < P.y1) {
     uint32_t seed = tea((uint32_t)W * (uint32_t)y + (uint32_t)x, P.st.time);   // :279
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
     const size_t pix = (size_t)y * P.pitch + x;
     f3 radiance;
     Payload prd;
-    if (!closestHit(P, ro, rd, prd, rc)) {                 // :154-158
+    if (!closestHit<STATS>(P, ro, rd, prd, rc)) {                 // :154-158
       P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
       P.motion[pix] = make_short2(0, 0);
       radiance = envRadiance(P);
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
         if (P.st.ReSTIRState == eNone) {                   // DirectLight (pathtrace.glsl:204-220)
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
           float pdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
-          if (!isPdfInvalid(pdf) && !occlusion(P, shadowOrigin, ls.wi, st.position, ls.dist, rc))
+          if (!isPdfInvalid(pdf) && !occlusion<STATS>(P, shadowOrigin, ls.wi, st.position, ls.dist, rc))
             direct = ((ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * gmax(dot3(st.ffnormal, ls.wi), 0.0f)) / pdf;
         } else {
           DResv resv; resv.Li = mk3(0.f); resv.wi = mk3(0.f); resv.dist = 0.f; resv.num = 0; resv.weight = 0.f;
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
             if (isPdfInvalid(p) || weight != weight) weight = 0.0f;
             resvUpdate(resv, ls.Li, ls.wi, ls.dist, weight, rnd(seed));
           }
-          if (occlusion(P, shadowOrigin, resv.wi, st.position, resv.dist, rc)) resv.weight = 0.0f;   // :200-207
+          if (occlusion<STATS>(P, shadowOrigin, resv.wi, st.position, resv.dist, rc)) resv.weight = 0.0f;   // :200-207
 
           if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // :209-217, findTemporalNeighbor :47-84
             const float reprojDepth = len3(ld3(P.cam.lastPosition) - st.position);
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
     const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);   // :283
     P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
   }
-  flushCounters(P, rc);
+  flushCounters<STATS>(P, rc);
 }
 
 // =================================================================================================
@@ -228,10 +238,11 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
   p[16] = __uint_as_float(num); p[17] = weight; p[18] = bigW;
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = P.y0 / 2 + blockIdx.y * 8 + threadIdx.y;
-  RayCounters rc = {0, 0, 0};
+  RayCounters rc = {0, 0, 0, 0, 0};
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   if (x < Wi && y < Hi && y < P.y1 / 2) {
     uint32_t seed = tea((uint32_t)Wi * (uint32_t)y + (uint32_t)x, P.st.time);   // :280
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
           float lightPdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
           if (!isPdfInvalid(lightPdf)) {
-            if (occlusion(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, rc)) lightPdf = EID_INVALID_PDF;
+            if (occlusion<STATS>(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, rc)) lightPdf = EID_INVALID_PDF;
           } else lightPdf = EID_INVALID_PDF;
           if (!isPdfInvalid(lightPdf)) {
             float bp = bsdfPdf(st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi);
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
         rayO = offsetRay(st.position, st.ffnormal);
         rayD = sampleWi;
         Payload prd;
-        closestHit(P, rayO, rayD, prd, rc);
+        closestHit<STATS>(P, rayO, rayD, prd, rc);
         if (prd.hitT >= __fsub_rn(EID_INFINITY, 1e-4f)) {   // miss (:183-198)
           if (d > 1) {
             const f3 env = mk3(P.env[0], P.env[1], P.env[2]);                 // EnvEval (pathtrace.glsl:60-72), constant env
@@ -377,7 +388,7 @@ __global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
       P.indA[opix] = make_float4(res.x, res.y, res.z, 1.0f);
     }
   }
-  flushCounters(P, rc);
+  flushCounters<STATS>(P, rc);
 }
 
 // =================================================================================================
@@ -386,55 +397,91 @@ __global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
 __constant__ float c_gauss5x5[25] = {.0030f, .0133f, .0219f, .0133f, .0030f, .0133f, .0596f, .0983f, .0596f, .0133f, .0219f, .0983f, .1621f,
                                      .0983f, .0219f, .0133f, .0596f, .0983f, .0596f, .0133f, .0030f, .0133f, .0219f, .0133f, .0030f};
 
-// loadThisGeometry (denoise_common.glsl:42-47): normal, camera-ray position, material hash of G-buffer texel (gx,gy);
-// the camera ray is spawned for pixel (gx,gy) of an image of size (sw,sh) — the indirect pass passes the half-res size
-// together with full-res coordinates (reference quirk, kept).
-DEV void loadThisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, f3& normal, f3& pos, uint32_t& matHash) {
+// loadThisGeometry (denoise_common.glsl:42-47) evaluates, for every one of the 25 taps of every pass, the octahedral normal
+// decode and a camera-ray spawn (two 4x4 products, a normalize) — ~250 instructions that depend only on the G-buffer texel.
+// k_denoise_prep evaluates it ONCE per texel per frame with the identical arithmetic and stores the result in two float4
+// planes (pos.xyz + material hash bits, normal.xyz); the nine filter passes then only load.  The indirect passes use their
+// own quarter-res planes because the reference spawns that ray with full-res coordinates against the half-res image size
+// (uv runs to ~2 — reference quirk, kept).
+DEV void thisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, float4& posHash, float4& nrm) {
   const uint4 g = loadG(P.thisG, P, gx, gy);
-  normal = octDecode(g.y);
+  const f3 n = octDecode(g.y);
   f3 o, d;
   raySpawn<false>(P.cam, gx, gy, sw, sh, o, d);
-  pos = o + d * __uint_as_float(g.x);
-  matHash = g.w & 0xFF000000u;
+  const f3 pos = o + d * __uint_as_float(g.x);
+  posHash = make_float4(pos.x, pos.y, pos.z, __uint_as_float(g.w & 0xFF000000u));
+  nrm = make_float4(n.x, n.y, n.z, 0.f);
 }
 
-template <bool INDIRECT>
+__global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
+  if (x >= W || y >= H) return;
+  float4 a, b;
+  thisGeometry(P, x, y, W, H, a, b);
+  const size_t pix = (size_t)y * P.pitch + x;
+  P.geomPos[pix] = a; P.geomNrm[pix] = b;
+  if (!(x & 1) && !(y & 1) && (x >> 1) < Wi && (y >> 1) < Hi) {
+    thisGeometry(P, x, y, Wi, Hi, a, b);
+    const size_t hp = (size_t)(y >> 1) * (P.pitch / 2) + (x >> 1);
+    P.geomPosH[hp] = a; P.geomNrmH[hp] = b;
+  }
+}
+
+// exp of the three edge-stopping weights.  STRICT: the bit-reproducible polynomial shared with the oracle (parity runs).
+// Fast (default): MUFU ex2 — relative error ~2^-21, far inside the 1e-3 radiance tolerance of the contract.
+template <bool STRICT> DEV float edgeExp(float num, float sigma, float negInvSigma) {
+  return STRICT ? eid_expf(__fdiv_rn(-num, sigma)) : __expf(num * negInvSigma);
+}
+
+template <bool INDIRECT, bool STRICT>
 __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
   if (x >= bw || y >= bh) return;
-  const int gs = INDIRECT ? 2 : 1;
   const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
   const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
   const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
-  f3 norm, pos; uint32_t matHash;
-  loadThisGeometry(P, x * gs, y * gs, bw, bh, norm, pos, matHash);
+  const float nL = -1.0f / sigL, nN = -1.0f / sigN, nD = -1.0f / sigD;
+  const float4* __restrict__ gPos = INDIRECT ? P.geomPosH : P.geomPos;
+  const float4* __restrict__ gNrm = INDIRECT ? P.geomNrmH : P.geomNrm;
+  const int gp = INDIRECT ? P.pitch / 2 : P.pitch;
+  const float4 cp = __ldg(gPos + (size_t)y * gp + x);
+  const uint32_t matHash = __float_as_uint(cp.w);
   f3 res = mk3(0.0f);
   if (matHash != EID_INVALID_MAT) {                        // waveletFilter (denoise_direct.comp:19-71 / denoise_indirect.comp:23-75)
+    const float4 cn = __ldg(gNrm + (size_t)y * gp + x);
+    const f3 pos = mk3(cp.x, cp.y, cp.z), norm = mk3(cn.x, cn.y, cn.z);
     const int step = 1 << level;
     f3 sum = mk3(0.0f);
     float sumW = 0.0f;
-    const float4 c4 = loadImg(inImg, P, x, y);
+    const float4 c4 = inImg[(size_t)y * P.pitch + x];
     const f3 color = mk3(c4.x, c4.y, c4.z);
     const float lumC = lum3(color);
+#pragma unroll
     for (int j = -2; j <= 2; j++) {
+      const int qy = y + j * step;
+      if (qy >= bh || qy < 0) continue;
+#pragma unroll
       for (int i = -2; i <= 2; i++) {
-        const int qx = x + i * step, qy = y + j * step;
-        if (qx >= bw || qy >= bh || qx < 0 || qy < 0) continue;
-        f3 nq, pq; uint32_t hq;
-        loadThisGeometry(P, qx * gs, qy * gs, bw, bh, nq, pq, hq);
-        const float4 q4 = loadImg(inImg, P, qx, qy);
+        const int qx = x + i * step;
+        if (qx >= bw || qx < 0) continue;
+        const float4 qp = __ldg(gPos + (size_t)qy * gp + qx);
+        const uint32_t hq = __float_as_uint(qp.w);
+        if (matHash != hq) continue;                       // (hq == InvalidMatId implies the mismatch: matHash is valid here)
+        const float4 qn = __ldg(gNrm + (size_t)qy * gp + qx);
+        const float4 q4 = inImg[(size_t)qy * P.pitch + qx];
         const f3 cq = mk3(q4.x, q4.y, q4.z);
-        if (matHash != hq || hq == EID_INVALID_MAT) continue;
         float distColor;
         if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
         else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
-        const float wColor = __fadd_rn(eid_expf(__fdiv_rn(-distColor, sigL)), 1e-2f);
-        const f3 dn = norm - nq;
-        const float wNorm = gmin(1.0f, eid_expf(__fdiv_rn(-dot3(dn, dn), sigN)));
-        const f3 dp = pos - pq;
-        const float wDepth = __fadd_rn(eid_expf(__fdiv_rn(-dot3(dp, dp), sigD)), 1e-2f);
+        const float wColor = __fadd_rn(edgeExp<STRICT>(distColor, sigL, nL), 1e-2f);
+        const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
+        const float wNorm = gmin(1.0f, edgeExp<STRICT>(dot3(dn, dn), sigN, nN));
+        const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
+        const float wDepth = __fadd_rn(edgeExp<STRICT>(dot3(dp, dp), sigD, nD), 1e-2f);
         const float w = __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), c_gauss5x5[(i + 2) * 5 + (j + 2)]);
         sum = sum + cq * w;
         sumW = __fadd_rn(sumW, w);
@@ -488,6 +535,8 @@ struct eid_renderer {
   float* indirectResv[2] = {nullptr, nullptr};
   float4* directImg = nullptr; float4* indirectImg = nullptr;
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
+  float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
+  bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
   unsigned long long* counters = nullptr;
   unsigned long long* countersHost = nullptr;   // pinned
   float env[3] = {0.f, 0.f, 0.f};
@@ -496,6 +545,7 @@ struct eid_renderer {
   bool hasRun = false;
   uint32_t bandY0 = 0, bandY1 = 0; bool bandSet = false;
   bool profiling = false;
+  bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
   cudaEvent_t ev[EID_K_COUNT + 1] = {};
   eid_frame_stats stats{};
   bool statsPending = false;
@@ -509,6 +559,7 @@ void eid_renderer::release() {
   cudaFree(motion); motion = nullptr;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
+  for (auto& t : geom) { cudaFree(t); t = nullptr; }
 }
 
 // Renderer::createBuffer / createImage (renderer.cpp:227-302): 2 G-buffers, 1 motion image, 2+2 reservoir buffers,
@@ -528,6 +579,8 @@ void eid_renderer::allocate() {
   zalloc((void**)&motion, n * 4);
   zalloc((void**)&directImg, n * 16); zalloc((void**)&indirectImg, n * 16);
   for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16);
+  zalloc((void**)&geom[0], n * 16); zalloc((void**)&geom[1], n * 16);
+  zalloc((void**)&geom[2], ni * 16); zalloc((void**)&geom[3], ni * 16);
   CUDA_CHECK(cudaStreamSynchronize(stream));
   hasRun = false; lastSet = 0;
   if (!bandSet) { bandY0 = 0; bandY1 = height; }
@@ -552,6 +605,7 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.thisIR = r->indirectResv[!set]; P.lastIR = r->indirectResv[set];
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
   P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
+  P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
   for (int k = 0; k < 3; ++k) P.env[k] = r->env[k];
   P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.y0 = 0; P.y1 = st.size.y;
@@ -563,20 +617,20 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
 static inline void mark(eid_renderer* r, int i) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[i], r->stream)); }
 
 static void launchTrace(eid_renderer* r, const FrameParams& P) {
-  CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 3 * sizeof(unsigned long long), r->stream));
+  CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
   memset(&r->stats, 0, sizeof(r->stats));
   mark(r, 0);
   const int rows = P.y1 - P.y0;
   if (rows > 0) {
     dim3 b(8, 8), g((P.st.size.x + 7) / 8, (rows + 7) / 8);
-    k_direct_stage<<<g, b, 0, r->stream>>>(P);
+    if (r->countVisits) k_direct_stage<true><<<g, b, 0, r->stream>>>(P); else k_direct_stage<false><<<g, b, 0, r->stream>>>(P);
     r->stats.kernelLaunches[EID_K_DIRECT]++;
   }
   mark(r, 1);
   const int irows = P.y1 / 2 - P.y0 / 2;
   if (irows > 0 && P.st.size.x / 2 > 0) {
     dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, (irows + 7) / 8);
-    k_indirect_stage<<<g, b, 0, r->stream>>>(P);
+    if (r->countVisits) k_indirect_stage<true><<<g, b, 0, r->stream>>>(P); else k_indirect_stage<false><<<g, b, 0, r->stream>>>(P);
     r->stats.kernelLaunches[EID_K_INDIRECT]++;
   }
   mark(r, 2);
@@ -585,17 +639,26 @@ static void launchTrace(eid_renderer* r, const FrameParams& P) {
 static void launchPost(eid_renderer* r, const FrameParams& P) {
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
   if (P.st.denoise > 0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
+    { dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8); k_denoise_prep<<<g, b, 0, r->stream>>>(P); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
     dim3 b(32, 4), g((W + 31) / 32, (H + 3) / 4);
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
     float4* dst[4] = {P.dirA, P.dirB, P.dirA, P.directImg};
-    for (int i = 0; i < 4; ++i) { k_denoise<false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
+    for (int i = 0; i < 4; ++i) {
+      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3);
+      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3);
+      r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
+    }
   }
   mark(r, 3);
   if (P.st.denoise > 0 && Wi > 0 && Hi > 0) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     dim3 b(32, 4), g((Wi + 31) / 32, (Hi + 3) / 4);
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
-    for (int i = 0; i < 5; ++i) { k_denoise<true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4); r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++; }
+    for (int i = 0; i < 5; ++i) {
+      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4);
+      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4);
+      r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
+    }
   }
   mark(r, 4);
   {
@@ -604,7 +667,7 @@ static void launchPost(eid_renderer* r, const FrameParams& P) {
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
   mark(r, 5);
-  CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
+  CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
   r->statsPending = true;
   CUDA_CHECK(cudaGetLastError());
 }
@@ -641,9 +704,10 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
     CUDA_CHECK(cudaSetDevice(r->device));
     if (cuda_stream) r->stream = (cudaStream_t)cuda_stream;
     else { CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->ownStream = true; }
-    CUDA_CHECK(cudaMalloc(&r->counters, 3 * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMallocHost(&r->countersHost, 3 * sizeof(unsigned long long)));
-    memset(r->countersHost, 0, 3 * sizeof(unsigned long long));
+    CUDA_CHECK(cudaMalloc(&r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemset(r->counters, 0, EID_NUM_COUNTERS * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMallocHost(&r->countersHost, EID_NUM_COUNTERS * sizeof(unsigned long long)));
+    memset(r->countersHost, 0, EID_NUM_COUNTERS * sizeof(unsigned long long));
     for (auto& e : r->ev) CUDA_CHECK(cudaEventCreate(&e));
     r->allocate();
   } catch (...) { eid_renderer_destroy(r); throw; }
@@ -788,10 +852,19 @@ int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxS
   EID_CATCH
 }
 
+int eid_renderer_set_strict_math(eid_renderer* r, int enabled) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_strict_math: null renderer");
+  r->strictMath = enabled != 0;
+  return EID_OK;
+  EID_CATCH
+}
+
 int eid_renderer_set_profiling(eid_renderer* r, int enabled) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_profiling: null renderer");
   r->profiling = enabled != 0;
+  r->countVisits = enabled >= 2;
   return EID_OK;
   EID_CATCH
 }
@@ -803,6 +876,8 @@ int eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out) {
   CUDA_CHECK(cudaStreamSynchronize(r->stream));
   if (r->statsPending) {
     r->stats.closestHitRays = r->countersHost[0]; r->stats.anyHitRays = r->countersHost[1]; r->stats.primaryHits = r->countersHost[2];
+    r->stats.nodeVisits = r->countersHost[3]; r->stats.triangleTests = r->countersHost[4];
+    r->stats.totalClosestHitRays = r->countersHost[5]; r->stats.totalAnyHitRays = r->countersHost[6];
     r->stats.launches = 0;
     for (int k = 0; k < EID_K_COUNT; ++k) r->stats.launches += r->stats.kernelLaunches[k];
     if (r->profiling)

@@ -62,8 +62,9 @@ DEV float boxEntry(const RayBox& rb, float lx, float ly, float lz, float hx, flo
 }
 
 // ANY = true: terminate on the first accepted triangle (AnyHit); false: closest hit with tie-break.
-template <bool ANY>
-DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit) {
+// STATS = true additionally counts inner-node visits and triangle tests (profiling builds of the kernels).
+template <bool ANY, bool STATS = false>
+DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsigned int* nodeVisits = nullptr, unsigned int* triTests = nullptr) {
   hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f;
   if (A.triCount == 0) return false;
   // a direction with NaN/zero length can never produce det != 0; skip the walk
@@ -76,6 +77,7 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit) {
   for (;;) {
     if (cur >= 0) {
       const float4* n = A.nodes + 4 * (size_t)cur;
+      if (STATS) ++*nodeVisits;
       const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
       float e0 = boxEntry(rb, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, hit.t);
       float e1 = boxEntry(rb, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, hit.t);
@@ -94,6 +96,7 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit) {
       const uint32_t first = ref >> 3, count = ref & 7u;
       for (uint32_t k = 0; k < count; ++k) {
         const float4* tp = A.tris + 3 * (size_t)(first + k);
+        if (STATS) ++*triTests;
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         float t, u, v;
         const uint32_t flags = __float_as_uint(c.w);

@@ -211,6 +211,10 @@ typedef struct eid_frame_stats {
   uint32_t launches;           /* CUDA kernels launched by the last eid_renderer_run */
   float    kernelMs[EID_K_COUNT];   /* CUDA-event time per stage (sum over its passes); needs profiling on */
   uint32_t kernelLaunches[EID_K_COUNT];
+  uint64_t nodeVisits;         /* BVH inner nodes fetched / triangles tested in the last frame; only counted */
+  uint64_t triangleTests;      /*   at profiling level 2 (instrumented kernel variants)                        */
+  uint64_t totalClosestHitRays;/* rays issued since the renderer was created (never reset) */
+  uint64_t totalAnyHitRays;
 } eid_frame_stats;
 
 /* Renderer::setup + create(size, layouts, scene) (renderer.cpp:50-57, 97-148).
@@ -224,6 +228,10 @@ EID_API void eid_renderer_destroy(eid_renderer* r);
 /* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR
  * map is installed; default (0,0,0). */
 EID_API int  eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]);
+/* Numerics of the denoiser's edge-stopping exponentials.  0 (default): hardware ex2 (MUFU), images within ~1e-6 relative of
+ * the bit-reproducible path.  1: the deterministic polynomial exp shared with the CPU oracle — every buffer of a frame is then
+ * bit-identical to the oracle's (used by the parity tests).  G-buffer, motion indices and reservoirs never depend on this. */
+EID_API int  eid_renderer_set_strict_math(eid_renderer* r, int enabled);
 /* Renderer::run(cmdBuf, state, profiler, descSets, frames) (renderer.cpp:154-206): enqueues
  * direct_stage, indirect_stage, denoise_direct x4, denoise_indirect x5, compose and returns.
  * `frames` selects the ping-pong set exactly as (frames+1)%2 (renderer.cpp:157). */
@@ -242,7 +250,8 @@ EID_API int  eid_renderer_write(eid_renderer* r, int which, const void* host_src
  * pinned or pageable host buffers (width*height*16 bytes each, either may be NULL) and syncs. */
 EID_API int  eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
                                       float* direct_host, float* indirect_host);
-/* per-stage CUDA-event timing + device ray counters for the following runs (off by default) */
+/* 0: off (default; ray counters are always kept), 1: per-stage CUDA-event timing,
+ * 2: additionally run the instrumented trace kernels that count BVH node visits / triangle tests */
 EID_API int  eid_renderer_set_profiling(eid_renderer* r, int enabled);
 EID_API int  eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out);
 

@@ -64,7 +64,7 @@ def compare_snapshots(got, want, tag, tol=1e-3):
     return report
 
 
-def make_pair(arrays, size, use_bvh=True):
+def make_pair(arrays, size, use_bvh=True, strict=True):
     """(oracle scene, oracle renderer, product scene, product accel, product renderer) for one scene."""
     import oracle_lib as ol
     w, h = size
@@ -79,4 +79,5 @@ def make_pair(arrays, size, use_bvh=True):
     prr = eid.Renderer()
     prr.create(size, psc, acc)
     prr.set_env_constant(ENV)
+    prr.set_strict_math(strict)   # strict: deterministic exp in the denoiser -> every buffer bit-identical to the oracle
     return osc, orr, psc, acc, prr
