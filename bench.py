@@ -155,7 +155,7 @@ def run_reference(args):
         "e2e": {"value": r["mrays"], "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps": 1e3 / r["ms_per_frame"], "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -180,7 +180,18 @@ def run_cuda(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        # NCCL prints its version banner on stdout at communicator creation; keep stdout clean for the ONE JSON line by
+        # pointing fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        _saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        _t = torch.zeros(1, device=torch.device("cuda", local))
+        dist.all_reduce(_t)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        os.close(_saved_stdout)
     if not torch.cuda.is_available() or eid.lib().eid_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device - this framework has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
@@ -201,13 +212,14 @@ def run_cuda(args):
     info = scene.info()
 
     # band partition: rows per rank rounded up to 16; the allocation is padded so every rank's chunk has equal size
-    band = ((h + world - 1) // world + 15) // 16 * 16
-    alloc_h = band * world if world > 1 else h
+    from eidola_b200 import sharding
+    band = sharding.band_rows(h, world)
+    alloc_h = sharding.padded_height(h, world)
     rr = eid.Renderer()
     rr.create((w, alloc_h), scene, accel, stream=stream.cuda_stream)
     rr.set_env_constant(ENV)
     if world > 1:
-        rr.set_band(min(rank * band, alloc_h), min((rank + 1) * band, alloc_h))
+        rr.set_band(*sharding.band_range(rank, world, h))
     exch = []
     if world > 1:
         for which in (abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A):
@@ -369,7 +381,7 @@ def run_cuda(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from . import abi, scenes
+from . import abi, scenes, sharding
 from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, SceneArrays, default_rtx_state)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

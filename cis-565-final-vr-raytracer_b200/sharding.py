@@ -1,0 +1,34 @@
+"""Screen-space sharding of one frame across the GPUs of a node (no reference analogue).
+
+Rank r traces (direct_stage + indirect_stage) the full-resolution row band [r*B, (r+1)*B), B = rows per rank rounded
+up to a multiple of 16 so that no 8x8 half-resolution tile (and therefore no shared multi-bounce flag,
+indirect_stage.comp:283-288) straddles two ranks.  Every image is allocated with world*B rows, which makes each
+rank's slice of every exchange buffer the same size, so ONE exchange step of equal-sized all-gathers (in place:
+rank r's slice already sits at offset r*chunk of the full buffer) gives every rank the complete pre-denoise frame.
+Denoise + compose then run on the full frame on every rank; every rank ends with the complete composed image.
+"""
+
+
+def band_rows(height, world):
+    return ((height + world - 1) // world + 15) // 16 * 16
+
+
+def padded_height(height, world):
+    return band_rows(height, world) * world if world > 1 else height
+
+
+def band_range(rank, world, height):
+    b = band_rows(height, world)
+    alloc = padded_height(height, world)
+    return min(rank * b, alloc), min((rank + 1) * b, alloc)
+
+
+def all_gather_bands(dist, full, rank, world, inplace=True):
+    """All-gather a row-banded buffer: `full` is a flat byte tensor whose length is world * chunk; rank r owns chunk r."""
+    chunk = full.numel() // world
+    assert chunk * world == full.numel()
+    mine = full[rank * chunk:(rank + 1) * chunk]
+    if not inplace:
+        mine = mine.clone()
+    dist.all_gather_into_tensor(full, mine)
+    return full
