@@ -1,0 +1,92 @@
+// eidola.hpp — C++17 host-side mirror of the reference's Scene / AccelStructure / Renderer classes on top of the
+// C-ABI (include/eidola.h).  Same method names and argument meaning as the reference (src/scene.hpp:60-83,
+// src/accelstruct.hpp:40-46, src/renderer.hpp:52-61); Vulkan handles are gone, errors surface as eidola::Error
+// (the reference returns bool / asserts, scene.cpp:164-169).  Header-only; link against libeidola.so.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include "eidola.h"
+
+namespace eidola {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const char* what) : std::runtime_error(what ? what : "eidola error"), code(c) {}
+};
+inline void check(int rc) { if (rc != EID_OK) throw Error(rc, eid_last_error()); }
+
+struct Extent2D { uint32_t width, height; };   // VkExtent2D stand-in
+
+class Scene {
+ public:
+  // Scene::setup(device, physicalDevice, queue, allocator) -> a CUDA ordinal is all that is left (scene.cpp:45-51)
+  void setup(int cudaDevice = 0) { destroy(); check(eid_scene_create(&m_h, cudaDevice)); }
+  // Scene::load(filename) -> bool (scene.cpp:57-125)
+  bool load(const std::string& filename) { return eid_scene_load_gltf(m_h, filename.c_str()) == EID_OK; }
+  bool load(const eid_scene_desc& desc) { return eid_scene_load_desc(m_h, &desc) == EID_OK; }
+  // CameraManip.setCamera / setLookat (scene.cpp:298-308, main.cpp:67-68)
+  void setLookat(const float eye[3], const float center[3], const float up[3], float fovDeg) { check(eid_scene_set_lookat(m_h, eye, center, up, fovDeg)); }
+  // Scene::updateCamera(cmdBuf, size) (scene.cpp:777-826)
+  void updateCamera(Extent2D size) { check(eid_scene_update_camera(m_h, size.width, size.height)); }
+  SceneCamera getCamera() const { SceneCamera c; check(eid_scene_get_camera(m_h, &c)); return c; }   // scene.hpp:80
+  void setCamera(const SceneCamera& c) { check(eid_scene_set_camera(m_h, &c)); }
+  eid_scene_info getStat() const { eid_scene_info i; check(eid_scene_get_info(m_h, &i)); return i; }  // getStat / m_*LightWeight
+  void destroy() { if (m_h) { eid_scene_destroy(m_h); m_h = nullptr; } }
+  ~Scene() { destroy(); }
+  eid_scene* handle() const { return m_h; }
+ private:
+  eid_scene* m_h = nullptr;
+};
+
+class AccelStructure {
+ public:
+  // AccelStructure::create(gltfScene, vertexBuffers, indexBuffers) (accelstruct.cpp:55-65): the buffers live in the Scene
+  void create(Scene& scene) { destroy(); check(eid_accel_build(scene.handle(), &m_h)); }
+  eid_accel_info info() const { eid_accel_info i; check(eid_accel_get_info(m_h, &i)); return i; }
+  void destroy() { if (m_h) { eid_accel_destroy(m_h); m_h = nullptr; } }
+  ~AccelStructure() { destroy(); }
+  eid_accel* getTlas() const { return m_h; }   // accelstruct.hpp:44
+ private:
+  eid_accel* m_h = nullptr;
+};
+
+class Renderer {
+ public:
+  // Renderer::create(size, rtDescSetLayouts, scene) (renderer.cpp:97-148): descriptor-set layouts become the two handles
+  void create(Extent2D size, Scene& scene, AccelStructure& accel, void* cudaStream = nullptr) {
+    destroy();
+    check(eid_renderer_create(&m_h, scene.handle(), accel.getTlas(), size.width, size.height, cudaStream));
+  }
+  // Renderer::run(cmdBuf, state, profiler, descSets, frames) (renderer.cpp:154-206): enqueues the 12 dispatches, asynchronous
+  void run(const RtxState& state, int frames) { check(eid_renderer_run(m_h, &state, frames)); }
+  // Renderer::update(size) (renderer.cpp:209-225)
+  void update(Extent2D size) { check(eid_renderer_resize(m_h, size.width, size.height)); }
+  void sync() { check(eid_renderer_sync(m_h)); }
+  void setEnvironmentConstant(const float rgb[3]) { check(eid_renderer_set_env_constant(m_h, rgb)); }
+  void setStrictMath(bool on) { check(eid_renderer_set_strict_math(m_h, on ? 1 : 0)); }
+  // the two RGBA32F images RenderOutput hands to post.frag (render_output.cpp:195-215): device pointers
+  std::pair<const float*, const float*> outputs() const { const float *d, *i; check(eid_renderer_get_outputs(m_h, &d, &i)); return {d, i}; }
+  void renderToHost(const SceneCamera* cam, const RtxState& st, int frames, float* direct, float* indirect) {
+    check(eid_renderer_render_host(m_h, cam, &st, frames, direct, indirect));
+  }
+  eid_frame_stats stats() const { eid_frame_stats s; check(eid_renderer_get_stats(m_h, &s)); return s; }
+  const std::string name() { return std::string("RQ"); }   // renderer.hpp:56
+  void destroy() { if (m_h) { eid_renderer_destroy(m_h); m_h = nullptr; } }
+  ~Renderer() { destroy(); }
+  eid_renderer* handle() const { return m_h; }
+ private:
+  eid_renderer* m_h = nullptr;
+};
+
+// SampleExample::m_rtxState defaults (sample_example.hpp:154-184)
+inline RtxState defaultRtxState(uint32_t w, uint32_t h) {
+  RtxState s{};
+  s.maxDepth = 4; s.modulate = 1; s.fireflyClampThreshold = 1.f; s.hdrMultiplier = 1.f; s.environmentProb = 0.25f;
+  s.ReSTIRState = eTemporal; s.RISSampleNum = 4; s.reservoirClamp = 80; s.size = {(int32_t)w, (int32_t)h}; s.MIS = 1;
+  s.sigLuminDirect = 0.4f; s.sigNormalDirect = 0.1f; s.sigDepthDirect = 0.02f; s.denoise = 1;
+  s.sigLuminIndirect = 4.f; s.sigNormalIndirect = 0.4f; s.sigDepthIndirect = 1.f;
+  return s;
+}
+
+}  // namespace eidola

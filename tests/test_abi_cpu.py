@@ -211,3 +211,20 @@ def test_synthetic_scene_generators_meet_the_contract():
         assert all(((i ^ (i >> 8)) & 0xff) != 0xff for i in range(len(a.materials)))
     c1 = scenes.cube_scene()
     assert c1.indices.size // 3 == 12 and c1.positions.shape[0] == 24
+
+
+def test_cpp_host_mirror_compiles_and_links(tmp_path):
+    """host/eidola.hpp (the C++ mirror of Scene / AccelStructure / Renderer) + the headless harness build against the .so."""
+    import shutil
+    import subprocess
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    pkg = os.path.join(ROOT, "cis-565-final-vr-raytracer_b200")
+    exe = str(tmp_path / "render_gltf")
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(pkg, "host", "render_gltf.cpp"), "-L", pkg, "-leidola", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=pkg)
+    p = subprocess.run([exe, "/nonexistent.gltf", str(tmp_path / "o.pfm"), "64", "64", "1"], env=env, capture_output=True, text=True)
+    if _no_gpu():
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr
+    else:
+        assert p.returncode == 1 and "load failed" in p.stderr
