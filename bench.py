@@ -235,6 +235,14 @@ def run_cuda(args):
             out.append((full, full[off:off + nb]))
         return out
 
+    def final_tensors():
+        out = []
+        for which in (abi.BUF_DIRECT, abi.BUF_INDIRECT):
+            base, off, nb = rr.band_range(which)
+            full = torch.as_tensor(DevBuf(base, nb * world), device=dev)
+            out.append((full, full[off:off + nb]))
+        return out
+
     scene.update_camera(w, h)
 
     def step(frame, e2e_bufs=None):
@@ -249,7 +257,12 @@ def run_cuda(args):
             rr.run_trace(st, frame)
             for full, mine in exchange_tensors():
                 dist.all_gather_into_tensor(full, mine)
-            rr.run_post(st, frame)
+            if args.post == "replicated":
+                rr.run_post(st, frame)                  # mode A: every rank denoises + composes the full frame
+            else:
+                rr.run_post_band(st, frame)             # mode B: band + per-level reach only, then gather the two final images
+                for full, mine in final_tensors():
+                    dist.all_gather_into_tensor(full, mine)
             if e2e_bufs is not None:
                 d, i = rr.outputs()
                 n = w * h * 16
@@ -353,7 +366,9 @@ def run_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
                        "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
-                       "parallelism": "row bands x%d + 1 all-gather step of pre-denoise buffers" % world if world > 1 else "single GPU",
+                       "parallelism": ("row bands x%d; exchange 1: all-gather of pre-denoise G-buffer/direct/indirect; %s" % (
+                           world, "denoise+compose per band, exchange 2: all-gather of the two final images" if args.post == "sharded"
+                           else "denoise+compose replicated on every rank")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: each frame streams ~1.0 GB of screen-space buffers + ~0.14 GB of BVH/triangles/vertices (L2 = 126 MB)",
                        "bvh": {"nodes": int(ainfo.nodeCount), "node_MB": ainfo.nodeBytes / 1e6, "tri_MB": ainfo.triBytes / 1e6,
                                "height": int(ainfo.maxDepth), "build_ms": float(ainfo.buildMs)}},
@@ -395,6 +410,9 @@ def main():
     ap.add_argument("--impl", default="eidola", choices=["eidola", "reference"])
     ap.add_argument("--quick", action="store_true", help="tiny scene/resolution (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
+                    help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
+                         "one exchange step, every rank post-processes the full frame")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

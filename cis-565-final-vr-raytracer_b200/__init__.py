@@ -35,7 +35,7 @@ EXPORTS = [
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
     "eid_renderer_set_strict_math", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
-    "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post",
+    "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band",
     "eid_renderer_band_range",
 ]
 
@@ -86,6 +86,7 @@ def lib():
         "eid_renderer_set_band": (i32, [vp, u32, u32]),
         "eid_renderer_run_trace": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_run_post": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_run_post_band": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_band_range": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -225,6 +226,9 @@ class Renderer:
 
     def run_post(self, state, frames):
         _check(lib().eid_renderer_run_post(self._h, C.byref(state), frames))
+
+    def run_post_band(self, state, frames):
+        _check(lib().eid_renderer_run_post_band(self._h, C.byref(state), frames))
 
     def set_band(self, y0, y1):
         _check(lib().eid_renderer_set_band(self._h, y0, y1))

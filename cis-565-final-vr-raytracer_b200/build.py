@@ -33,6 +33,7 @@ def _newer(src_list, target):
 
 
 def build_library(force=False, verbose=False, extra=()):
+    extra = list(extra) + os.environ.get("EID_NVCC_EXTRA", "").split()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     headers.append(os.path.abspath(__file__))

@@ -10,7 +10,8 @@
 //   4. k_reorder          triangles + AABBs into Morton order
 //   5. k_hierarchy        Karras 2012 binary radix tree, one thread per inner node
 //   6. k_refit            bottom-up AABB / leaf-count / height, atomic arrival counters
-//   7. k_pack_nodes       64 B two-box nodes; subtrees with <= 4 triangles collapse into leaves
+//   7. k_collapse4        level-by-level collapse into 128 B 4-wide nodes (surface-area greedy); subtrees with <= 4
+//                         triangles become leaves.  (EID_BVH_WIDTH=2 keeps the binary tree: k_pack_nodes, 64 B two-box nodes)
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <vector>
@@ -252,6 +253,64 @@ __global__ void k_pack_nodes(int n, const int* __restrict__ left, const int* __r
   out[4 * (size_t)i + 3] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), 0.f, 0.f);
 }
 
+// Collapse of the binary radix tree into 4-wide nodes (EID_BVH_WIDTH == 4), level by level from the root: a wide node starts
+// from a binary node's two children and twice replaces its largest-area expandable child by that child's two children
+// (the surface-area-greedy collapse used by wide-BVH CPU tracers).  Subtrees with <= LEAF_MAX triangles are leaves.
+// 128-byte node = 8 x float4: lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4], child refs[4], unused.
+// Empty slots: box at +3e38 (never entered) and ref ~0 (a leaf of 0 triangles).
+__global__ void k_collapse4(int nIn, const int2* __restrict__ in, int2* __restrict__ out, unsigned int* __restrict__ counters,
+                            const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ rangeFirst,
+                            const int* __restrict__ rangeLast, const float* __restrict__ leafLo, const float* __restrict__ leafHi,
+                            const float* __restrict__ nodeLo, const float* __restrict__ nodeHi, float4* __restrict__ wide) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nIn) return;
+  const int b = in[i].x, w = in[i].y;
+  int c[4] = {left[b], right[b], 0, 0};
+  int n = 2;
+  auto sizeOf = [&](int r) { return r < 0 ? 1 : rangeLast[r] - rangeFirst[r] + 1; };
+  auto boxOf = [&](int r, float* lo, float* hi) {
+    const float* l = r < 0 ? leafLo + 3 * (size_t)(~r) : nodeLo + 3 * (size_t)r;
+    const float* h = r < 0 ? leafHi + 3 * (size_t)(~r) : nodeHi + 3 * (size_t)r;
+    for (int k = 0; k < 3; ++k) { lo[k] = l[k]; hi[k] = h[k]; }
+  };
+  while (n < 4) {
+    int best = -1; float bestA = -1.f;
+    for (int j = 0; j < n; ++j) {
+      if (c[j] >= 0 && sizeOf(c[j]) > (int)LEAF_MAX) {
+        float lo[3], hi[3]; boxOf(c[j], lo, hi);
+        float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        float a = ex * ey + ey * ez + ez * ex;
+        if (a > bestA) { bestA = a; best = j; }
+      }
+    }
+    if (best < 0) break;
+    const int r = c[best];
+    c[best] = left[r];
+    c[n++] = right[r];
+  }
+  int inner = 0;
+  for (int j = 0; j < n; ++j) inner += (c[j] >= 0 && sizeOf(c[j]) > (int)LEAF_MAX) ? 1 : 0;
+  unsigned int wbase = 0, obase = 0;
+  if (inner) { wbase = atomicAdd(&counters[1], (unsigned int)inner); obase = atomicAdd(&counters[0], (unsigned int)inner); }
+  float lo[4][3], hi[4][3]; int ref[4];
+  int k = 0;
+  for (int j = 0; j < 4; ++j) {
+    if (j >= n) { for (int a = 0; a < 3; ++a) { lo[j][a] = 3e38f; hi[j][a] = 3e38f; } ref[j] = ~0; continue; }
+    boxOf(c[j], lo[j], hi[j]);
+    const int sz = sizeOf(c[j]);
+    if (c[j] < 0) ref[j] = ~(((~c[j]) << 3) | 1);
+    else if (sz <= (int)LEAF_MAX) ref[j] = ~((rangeFirst[c[j]] << 3) | sz);
+    else { ref[j] = (int)(wbase + k); out[obase + k] = make_int2(c[j], (int)(wbase + k)); ++k; }
+  }
+  float4* o = wide + 8 * (size_t)w;
+  for (int a = 0; a < 3; ++a) {
+    o[a] = make_float4(lo[0][a], lo[1][a], lo[2][a], lo[3][a]);
+    o[3 + a] = make_float4(hi[0][a], hi[1][a], hi[2][a], hi[3][a]);
+  }
+  o[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+  o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // batch ray query (parity tap for ClosestHit / AnyHit)
 // ------------------------------------------------------------------------------------------------
@@ -283,7 +342,7 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
   CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
   CUDA_CHECK(cudaEventRecord(ev0, 0));
   if (nTri == 0) {
-    CUDA_CHECK(cudaMalloc(&a->nodes, 64)); CUDA_CHECK(cudaMalloc(&a->tris, 48));
+    CUDA_CHECK(cudaMalloc(&a->nodes, EID_NODE_BYTES)); CUDA_CHECK(cudaMalloc(&a->tris, 48));
     a->rootRef = ~0; a->nodeCount = 0; a->maxDepth = 0;   // empty leaf
     CUDA_CHECK(cudaEventDestroy(ev0)); CUDA_CHECK(cudaEventDestroy(ev1));
     return;
@@ -316,17 +375,11 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
     k_reorder<<<G, B>>>(nTri, valsSorted, triTmp, lo0, hi0, a->tris, lo1, hi1);
     const uint32_t nInner = nTri > 1 ? nTri - 1 : 1;
-    CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)nInner * 64));
-    CUDA_CHECK(cudaMemset(a->nodes, 0, (size_t)nInner * 64));
     if (nTri == 1) {
-      // single triangle: a root node whose second child is an empty leaf
-      float hl[3], hh[3];
-      CUDA_CHECK(cudaMemcpy(hl, lo1, 12, cudaMemcpyDeviceToHost)); CUDA_CHECK(cudaMemcpy(hh, hi1, 12, cudaMemcpyDeviceToHost));
-      int r0 = ~((0 << 3) | 1), r1 = ~0;
-      float node[16] = {hl[0], hl[1], hl[2], hh[0], hh[1], hh[2], 3e38f, 3e38f, 3e38f, -3e38f, -3e38f, -3e38f, 0, 0, 0, 0};
-      memcpy(&node[12], &r0, 4); memcpy(&node[13], &r1, 4);
-      CUDA_CHECK(cudaMemcpy(a->nodes, node, 64, cudaMemcpyHostToDevice));
-      a->rootRef = 0; a->nodeCount = 1; a->maxDepth = 1;
+      // single triangle: the root reference is the leaf itself, no inner node exists
+      CUDA_CHECK(cudaMalloc(&a->nodes, EID_NODE_BYTES));
+      CUDA_CHECK(cudaMemset(a->nodes, 0, EID_NODE_BYTES));
+      a->rootRef = ~((0 << 3) | 1); a->nodeCount = 0; a->maxDepth = 0;
     } else {
       CUDA_CHECK(cudaMalloc(&left, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&right, (size_t)nInner * 4));
       CUDA_CHECK(cudaMalloc(&parI, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&parL, (size_t)nTri * 4));
@@ -337,12 +390,43 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
       CUDA_CHECK(cudaMemset(arrived, 0, (size_t)nInner * 4)); CUDA_CHECK(cudaMemset(live, 0, 4));
       k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)nTri, keysSorted, left, right, parI, parL, rf, rl);
       k_refit<<<G, B>>>((int)nTri, left, right, parI, parL, lo1, hi1, nlo, nhi, height, arrived);
+#if EID_BVH_WIDTH == 2
+      CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)nInner * 64));
+      CUDA_CHECK(cudaMemset(a->nodes, 0, (size_t)nInner * 64));
       k_pack_nodes<<<(nInner + B - 1) / B, B>>>((int)nTri, left, right, rf, rl, lo1, hi1, nlo, nhi, a->nodes, live);
       int rootHeight = 0; unsigned int liveNodes = 0;
       CUDA_CHECK(cudaMemcpy(&rootHeight, height, 4, cudaMemcpyDeviceToHost));
       CUDA_CHECK(cudaMemcpy(&liveNodes, live, 4, cudaMemcpyDeviceToHost));
-      a->rootRef = 0; a->nodeCount = liveNodes; a->maxDepth = (uint32_t)rootHeight;
+      a->rootRef = 0; a->nodeCount = liveNodes; a->maxDepth = (uint32_t)rootHeight; a->nodeAlloc = nInner;
       if (rootHeight >= EID_STACK_SIZE) raise(EID_ERR_UNSUPPORTED, "BVH height %d exceeds the traversal stack (%d)", rootHeight, EID_STACK_SIZE);
+#else
+      // level-by-level collapse into 4-wide nodes; queues hold (binary node, wide node index)
+      float4* wideTmp = nullptr; int2 *q0 = nullptr, *q1 = nullptr; unsigned int* counters = nullptr;
+      try {
+        CUDA_CHECK(cudaMalloc(&wideTmp, (size_t)nInner * EID_NODE_BYTES));
+        CUDA_CHECK(cudaMalloc(&q0, (size_t)nInner * 8)); CUDA_CHECK(cudaMalloc(&q1, (size_t)nInner * 8));
+        CUDA_CHECK(cudaMalloc(&counters, 8));
+        const int2 rootItem = make_int2(0, 0);
+        const unsigned int init[2] = {0u, 1u};
+        CUDA_CHECK(cudaMemcpy(q0, &rootItem, 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(counters, init, 8, cudaMemcpyHostToDevice));
+        unsigned int nIn = 1, levels = 0;
+        while (nIn) {
+          CUDA_CHECK(cudaMemsetAsync(counters, 0, 4));
+          k_collapse4<<<(nIn + 127) / 128, 128>>>((int)nIn, q0, q1, counters, left, right, rf, rl, lo1, hi1, nlo, nhi, wideTmp);
+          CUDA_CHECK(cudaMemcpy(&nIn, counters, 4, cudaMemcpyDeviceToHost));
+          std::swap(q0, q1);
+          if (++levels > 200) raise(EID_ERR_UNSUPPORTED, "BVH collapse did not terminate");
+        }
+        unsigned int wideCount = 0;
+        CUDA_CHECK(cudaMemcpy(&wideCount, counters + 1, 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)wideCount * EID_NODE_BYTES));      // trim to the live node count
+        CUDA_CHECK(cudaMemcpy(a->nodes, wideTmp, (size_t)wideCount * EID_NODE_BYTES, cudaMemcpyDeviceToDevice));
+        a->rootRef = 0; a->nodeCount = wideCount; a->maxDepth = levels; a->nodeAlloc = wideCount;
+        if (3 * levels + 1 >= EID_STACK_SIZE) raise(EID_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", levels, EID_STACK_SIZE);
+      } catch (...) { cudaFree(wideTmp); cudaFree(q0); cudaFree(q1); cudaFree(counters); throw; }
+      cudaFree(wideTmp); cudaFree(q0); cudaFree(q1); cudaFree(counters);
+#endif
     }
     CUDA_CHECK(cudaEventRecord(ev1, 0));
     CUDA_CHECK(cudaDeviceSynchronize());
@@ -560,7 +644,7 @@ int eid_accel_get_info(eid_accel* a, eid_accel_info* o) {
   EID_TRY
   if (!a || !o) raise(EID_ERR_INVALID, "eid_accel_get_info: null argument");
   o->triangleCount = a->triCount; o->nodeCount = a->nodeCount; o->maxDepth = a->maxDepth;
-  o->nodeBytes = (uint64_t)std::max<uint32_t>(1u, a->triCount > 1 ? a->triCount - 1 : 1) * 64; o->triBytes = (uint64_t)a->triCount * 48;
+  o->nodeBytes = (uint64_t)std::max<uint32_t>(1u, a->nodeAlloc) * EID_NODE_BYTES; o->triBytes = (uint64_t)a->triCount * 48;
   o->buildMs = a->buildMs;
   return EID_OK;
   EID_CATCH

@@ -4,6 +4,11 @@
 #include <cuda_runtime.h>
 #include "scene_host.h"
 
+#ifndef EID_BVH_WIDTH
+#define EID_BVH_WIDTH 4
+#endif
+#define EID_NODE_BYTES (EID_BVH_WIDTH == 4 ? 128 : 64)
+
 namespace eid {
 
 // What a kernel needs to shade: the reference's S_SCENE descriptor set (layouts.glsl:48-54).
@@ -16,7 +21,8 @@ struct DeviceSceneView {
   LightBufInfo lightBufInfo;
 };
 
-// BVH2 node, 64 B = 4 x float4:
+// EID_BVH_WIDTH == 4 (default): 128 B node = 8 x float4: lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4], child refs[4], -
+// EID_BVH_WIDTH == 2: BVH2 node, 64 B = 4 x float4:
 //   q0 = lo0.xyz, hi0.x   q1 = hi0.yz, lo1.xy   q2 = lo1.z, hi1.xyz   q3 = child0, child1, -, -  (as int bits)
 // child >= 0: inner node index; child < 0: leaf, ~child = (firstTriangle << 3) | count  (count 0..4)
 // Triangle record, 48 B = 3 x float4 (world space, Moller-Trumbore ready):
@@ -57,6 +63,7 @@ struct eid_accel {
   float4* tris = nullptr;
   uint32_t triCount = 0;
   uint32_t nodeCount = 0;
+  uint32_t nodeAlloc = 0;
   uint32_t maxDepth = 0;
   int32_t rootRef = -1;
   float buildMs = 0.f;

@@ -19,6 +19,14 @@
 
 namespace eid {
 
+// minimum resident 64-thread blocks per SM the compiler must allow for (register cap = 65536 / (64 * blocks))
+#ifndef EID_K1_MIN_BLOCKS
+#define EID_K1_MIN_BLOCKS 16
+#endif
+#ifndef EID_K2_MIN_BLOCKS
+#define EID_K2_MIN_BLOCKS 16
+#endif
+
 struct FrameParams {
   RtxState st;
   SceneCamera cam;
@@ -114,7 +122,7 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 // K1 — direct_stage.comp
 // =================================================================================================
 template <bool STATS>
-__global__ void __launch_bounds__(64) k_direct_stage(const FrameParams P) {
+__global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = P.y0 + blockIdx.y * 8 + threadIdx.y;
   RayCounters rc = {0, 0, 0, 0, 0};
@@ -239,7 +247,7 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(64) k_indirect_stage(const FrameParams P) {
+__global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = P.y0 / 2 + blockIdx.y * 8 + threadIdx.y;
   RayCounters rc = {0, 0, 0, 0, 0};
@@ -413,11 +421,11 @@ DEV void thisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, floa
   nrm = make_float4(n.x, n.y, n.z, 0.f);
 }
 
-__global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P) {
+__global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int rowBegin, int rowEnd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
-  if (x >= W || y >= H) return;
+  if (x >= W || y >= H || y >= rowEnd) return;
   float4 a, b;
   thisGeometry(P, x, y, W, H, a, b);
   const size_t pix = (size_t)y * P.pitch + x;
@@ -436,11 +444,12 @@ template <bool STRICT> DEV float edgeExp(float num, float sigma, float negInvSig
 }
 
 template <bool INDIRECT, bool STRICT>
-__global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel) {
+__global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel,
+                                                 int rowBegin, int rowEnd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
   const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
-  if (x >= bw || y >= bh) return;
+  if (x >= bw || y >= bh || y >= rowEnd) return;
   const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
   const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
   const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
@@ -497,10 +506,10 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
 // =================================================================================================
 // K5 — compose.comp:23-42
 // =================================================================================================
-__global__ void __launch_bounds__(256) k_compose(const FrameParams P, const float4* __restrict__ indSrc) {
+__global__ void __launch_bounds__(256) k_compose(const FrameParams P, const float4* __restrict__ indSrc, int rowBegin, int rowEnd) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= P.st.size.x || y >= P.st.size.y) return;
+  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= P.st.size.x || y >= P.st.size.y || y >= rowEnd) return;
   const size_t pix = (size_t)y * P.pitch + x;
   const float4 ind = loadImg(indSrc, P, x / 2, y / 2);
   if (P.st.modulate == 0) {
@@ -636,34 +645,53 @@ static void launchTrace(eid_renderer* r, const FrameParams& P) {
   mark(r, 2);
 }
 
-static void launchPost(eid_renderer* r, const FrameParams& P) {
+// Denoise + compose.  sharded = false: the whole frame (single GPU, or the replicated post of multi-GPU mode A).
+// sharded = true (multi-GPU mode B): only what this rank's band [P.y0, P.y1) of the FINAL images needs.  An A-Trous level l
+// reaches 2*2^l rows, so level l must be evaluated on the band plus the summed reach of the levels after it
+// (direct: 28/24/16/0 rows for levels 0..3; indirect: 60/56/48/32/0 quarter-res rows for levels 0..4); the inputs of level 0
+// (pre-denoise images, G-buffer) are complete on every rank after the first exchange step.  Values are identical to the
+// full-frame evaluation, only the evaluated row ranges shrink.
+static void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
-  if (P.st.denoise > 0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
-    { dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8); k_denoise_prep<<<g, b, 0, r->stream>>>(P); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
-    dim3 b(32, 4), g((W + 31) / 32, (H + 3) / 4);
+  const int y0 = sharded ? P.y0 : 0, y1 = sharded ? P.y1 : H;
+  auto clampRows = [](int a, int b, int lim, int& ra, int& rb) { ra = std::max(0, a); rb = std::min(lim, b); };
+  if (P.st.denoise > 0 && y1 > y0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
+    int pa, pb;
+    clampRows(y0 - 124, y1 + 124, H, pa, pb);   // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124) for K4
+    if (pb > pa) { dim3 b(32, 8), g((W + 31) / 32, (pb - pa + 7) / 8); k_denoise_prep<<<g, b, 0, r->stream>>>(P, pa, pb); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
     float4* dst[4] = {P.dirA, P.dirB, P.dirA, P.directImg};
+    const int halo[4] = {28, 24, 16, 0};
     for (int i = 0; i < 4; ++i) {
-      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3);
-      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3);
+      int ra, rb;
+      clampRows(y0 - halo[i], y1 + halo[i], H, ra, rb);
+      dim3 b(32, 4), g((W + 31) / 32, (rb - ra + 3) / 4);
+      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, ra, rb);
+      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, ra, rb);
       r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
     }
   }
   mark(r, 3);
-  if (P.st.denoise > 0 && Wi > 0 && Hi > 0) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
-    dim3 b(32, 4), g((Wi + 31) / 32, (Hi + 3) / 4);
+  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && y1 / 2 > y0 / 2) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
+    const int halo[5] = {60, 56, 48, 32, 0};
+    const int h0 = y0 / 2, h1 = sharded ? y1 / 2 : Hi;
     for (int i = 0; i < 5; ++i) {
-      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4);
-      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4);
+      int ra, rb;
+      clampRows(h0 - halo[i], h1 + halo[i], Hi, ra, rb);
+      dim3 b(32, 4), g((Wi + 31) / 32, (rb - ra + 3) / 4);
+      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, ra, rb);
+      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, ra, rb);
       r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
     }
   }
   mark(r, 4);
-  {
-    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA);
+  if (y1 > y0) {
+    int ra, rb;
+    clampRows(y0, y1, H, ra, rb);
+    dim3 b(32, 8), g((W + 31) / 32, (rb - ra + 7) / 8);
+    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA, ra, rb);
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
   mark(r, 5);
@@ -756,7 +784,7 @@ int eid_renderer_run(eid_renderer* r, const RtxState* state, int frames) {
   FrameParams P;
   fillParams(r, *state, frames, P);
   launchTrace(r, P);
-  launchPost(r, P);
+  launchPost(r, P, false);
   return EID_OK;
   EID_CATCH
 }
@@ -780,7 +808,19 @@ int eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames) {
   FrameParams P;
   fillParams(r, *state, frames, P);
   if (r->profiling) { mark(r, 2); }
-  launchPost(r, P);
+  launchPost(r, P, false);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_post_band: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  if (r->profiling) { mark(r, 2); }
+  launchPost(r, P, true);
   return EID_OK;
   EID_CATCH
 }
@@ -843,7 +883,7 @@ int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxS
   FrameParams P;
   fillParams(r, *state, frames, P);
   launchTrace(r, P);
-  launchPost(r, P);
+  launchPost(r, P, false);
   const size_t rowBytes = (size_t)state->size.x * 16;
   if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->directImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
   if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->indirectImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));

@@ -19,7 +19,7 @@ struct RayHit {
   int prim, inst;
 };
 
-#define EID_STACK_SIZE 64
+#define EID_STACK_SIZE 128
 
 // returns true and fills t,u,v when the ray hits triangle (v0,e1,e2) inside (0, tmax)
 DEV bool triangleTest(f3 v0, f3 e1, f3 e2, uint32_t flags, f3 o, f3 d, float tmax, float& t, float& u, float& v) {
@@ -76,6 +76,7 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
   const float INF = __int_as_float(0x7f800000);
   for (;;) {
     if (cur >= 0) {
+#if EID_BVH_WIDTH == 2
       const float4* n = A.nodes + 4 * (size_t)cur;
       if (STATS) ++*nodeVisits;
       const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
@@ -91,6 +92,38 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
       }
       if (h0) { cur = c0; continue; }
       if (h1) { cur = c1; continue; }
+#else
+      const float4* n = A.nodes + 8 * (size_t)cur;
+      if (STATS) ++*nodeVisits;
+      const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2), hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
+      const float4 rf = __ldg(n + 6);
+      float e0 = boxEntry(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, hit.t);
+      float e1 = boxEntry(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, hit.t);
+      float e2 = boxEntry(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, hit.t);
+      float e3 = boxEntry(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, hit.t);
+      int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
+      if (ANY) {
+        // occlusion rays: order is irrelevant, just visit every child the ray enters
+        int next = 0; bool have = false;
+        if (e0 < INF) { next = c0; have = true; }
+        if (e1 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c1; } else { next = c1; have = true; } }
+        if (e2 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c2; } else { next = c2; have = true; } }
+        if (e3 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c3; } else { next = c3; have = true; } }
+        if (have) { cur = next; continue; }
+      } else {
+        // sort the four (entry distance, ref) pairs ascending: 5-comparator network
+#define EID_CSWAP(ea, ca, eb, cb) { if (eb < ea) { float te = ea; ea = eb; eb = te; int tc = ca; ca = cb; cb = tc; } }
+        EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2) EID_CSWAP(e1, c1, e3, c3) EID_CSWAP(e1, c1, e2, c2)
+#undef EID_CSWAP
+        if (e0 < INF) {
+          if (e3 < INF && sp < EID_STACK_SIZE) stack[sp++] = c3;
+          if (e2 < INF && sp < EID_STACK_SIZE) stack[sp++] = c2;
+          if (e1 < INF && sp < EID_STACK_SIZE) stack[sp++] = c1;
+          cur = c0;
+          continue;
+        }
+      }
+#endif
     } else {
       const uint32_t ref = ~(uint32_t)cur;
       const uint32_t first = ref >> 3, count = ref & 7u;

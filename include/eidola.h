@@ -264,6 +264,9 @@ EID_API int  eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out);
 EID_API int  eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1);
 EID_API int  eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames);
 EID_API int  eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames);
+/* Mode B (two exchange steps): denoise + compose only what this rank's band of the FINAL images needs (the A-Trous levels are
+ * evaluated on the band plus the reach of the later levels); the caller then all-gathers EID_BUF_DIRECT and EID_BUF_INDIRECT. */
+EID_API int  eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, int frames);
 /* device pointer + byte range of this rank's band inside buffer `which`
  * (EID_BUF_THIS_GBUFFER, EID_BUF_DIRECT, EID_BUF_DENOISE_IND_A, EID_BUF_MOTION, reservoirs) */
 EID_API int  eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes);

@@ -221,6 +221,52 @@ def test_band_sharded_trace_equals_full_frame():
                 assert got[k].tobytes() == ref[k].tobytes(), "band-sharded %s differs from the full-frame run (frame %d)" % (k, f)
 
 
+def test_band_sharded_post_equals_full_frame():
+    """Mode B: trace bands, exchange, then each rank denoises/composes only its band (levels evaluated on band + reach of the
+    later levels); the final band rows equal the single-GPU frame bit for bit."""
+    arrays = scenes.small_room()
+    size = (256, 160)
+    psc = eid.Scene(0)
+    psc.load_arrays(arrays)
+    acc = eid.AccelStructure()
+    acc.create(psc)
+    full = eid.Renderer()
+    full.create(size, psc, acc)
+    full.set_env_constant(common.ENV)
+    bands = [(0, 48), (48, 112), (112, 160)]
+    ranks = []
+    for y0, y1 in bands:
+        r = eid.Renderer()
+        r.create(size, psc, acc)
+        r.set_env_constant(common.ENV)
+        r.set_band(y0, y1)
+        ranks.append(r)
+    info = psc.info()
+    psc.update_camera(*size)
+    exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A]
+    for f in range(3):
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f)
+        full.run(st, f)
+        for r in ranks:
+            r.run_trace(st, f)
+        for which in exchange:
+            stitched = ranks[0].read(which).view(np.uint8).copy()
+            for r in ranks[1:]:
+                _, off, n = r.band_range(which)
+                stitched[off:off + n] = r.read(which).view(np.uint8)[off:off + n]
+            for r in ranks:
+                r.write(which, stitched)
+        for r in ranks:
+            r.run_post_band(st, f)
+        for which in (abi.BUF_DIRECT, abi.BUF_INDIRECT):
+            want = full.read(which).view(np.uint8)
+            for r in ranks:
+                _, off, n = r.band_range(which)
+                got = r.read(which).view(np.uint8)
+                assert got[off:off + n].tobytes() == want[off:off + n].tobytes(), "mode B band rows differ (buffer %d, frame %d)" % (which, f)
+
+
 def test_render_host_end_to_end_and_checkpoint():
     """eid_renderer_render_host (host buffers in, host images out) == run + read; history write-back resumes bit-exactly."""
     arrays = scenes.cornell_scene()
