@@ -213,35 +213,28 @@ def run_cuda(args):
 
     # band partition: rows per rank rounded up to 16; the allocation is padded so every rank's chunk has equal size
     from eidola_b200 import sharding
-    band = sharding.band_rows(h, world)
-    alloc_h = sharding.padded_height(h, world)
+    stripe_rows, alloc_h = sharding.stripe_layout(h, world, args.stripe_groups)
     rr = eid.Renderer()
     rr.create((w, alloc_h), scene, accel, stream=stream.cuda_stream)
     rr.set_env_constant(ENV)
     if world > 1:
-        rr.set_band(*sharding.band_range(rank, world, h))
-    exch = []
-    if world > 1:
-        for which in (abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A):
-            base, off, n = rr.band_range(which)
-            total = n * world
-            exch.append((which, total, n))
+        rr.set_stripes(rank, world, stripe_rows)
+
+    def gather_views(buffers):
+        """(group region, my chunk) torch views of the library's buffers, one pair per buffer and exchange group."""
+        out = []
+        for which in buffers:
+            for g in range(rr.exchange_groups()):
+                base, off, nb = rr.exchange_range(which, g)     # pointers flip with the ping-pong set: re-query per frame
+                region = torch.as_tensor(DevBuf(base + off - rank * nb, nb * world), device=dev)
+                out.append((region, region[rank * nb:(rank + 1) * nb]))
+        return out
 
     def exchange_tensors():
-        out = []
-        for which, total, n in exch:
-            base, off, nb = rr.band_range(which)       # pointers flip with the ping-pong set: re-query per frame
-            full = torch.as_tensor(DevBuf(base, total), device=dev)
-            out.append((full, full[off:off + nb]))
-        return out
+        return gather_views((abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A))
 
     def final_tensors():
-        out = []
-        for which in (abi.BUF_DIRECT, abi.BUF_INDIRECT):
-            base, off, nb = rr.band_range(which)
-            full = torch.as_tensor(DevBuf(base, nb * world), device=dev)
-            out.append((full, full[off:off + nb]))
-        return out
+        return gather_views((abi.BUF_DIRECT, abi.BUF_INDIRECT))
 
     scene.update_camera(w, h)
 
@@ -341,7 +334,7 @@ def run_cuda(args):
         launches = [max(1, int(v)) for v in vs.kernelLaunches[:]]   # 1, 1, 1 prep + 4 passes, 5 passes, 1
         dom = int(np.argmax(kms))
         screen = {k: SCREEN_BYTES_PER_PX[k] * n_px for k in names}
-        band_frac = 1.0 / world
+        band_frac = 1.0 / world   # rank 0's share of the trace work
         trace_bytes = vs.nodeVisits * NODE_BYTES + vs.triangleTests * TRI_BYTES + (vs.closestHitRays * HIT_GATHER_BYTES)
         # split traversal bytes between K1 and K2 by their ray counts (K1: 1 closest + <=1 any per hit pixel)
         k1_rays = min(vs.closestHitRays, int(n_px * band_frac)) + vs.primaryHits
@@ -366,8 +359,8 @@ def run_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
                        "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
-                       "parallelism": ("row bands x%d; exchange 1: all-gather of pre-denoise G-buffer/direct/indirect; %s" % (
-                           world, "denoise+compose per band, exchange 2: all-gather of the two final images" if args.post == "sharded"
+                       "parallelism": ("%d interleaved row stripes per rank x%d ranks; exchange 1: all-gather of pre-denoise G-buffer/direct/indirect; %s" % (
+                           args.stripe_groups, world, "denoise+compose per band, exchange 2: all-gather of the two final images" if args.post == "sharded"
                            else "denoise+compose replicated on every rank")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: each frame streams ~1.0 GB of screen-space buffers + ~0.14 GB of BVH/triangles/vertices (L2 = 126 MB)",
                        "bvh": {"nodes": int(ainfo.nodeCount), "node_MB": ainfo.nodeBytes / 1e6, "tri_MB": ainfo.triBytes / 1e6,
@@ -410,6 +403,7 @@ def main():
     ap.add_argument("--impl", default="eidola", choices=["eidola", "reference"])
     ap.add_argument("--quick", action="store_true", help="tiny scene/resolution (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stripe-groups", type=int, default=2, help="N>1: interleaved stripes per rank (1 = one contiguous band per rank)")
     ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
                     help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
                          "one exchange step, every rank post-processes the full frame")

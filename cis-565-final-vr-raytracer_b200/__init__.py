@@ -36,7 +36,7 @@ EXPORTS = [
     "eid_renderer_set_strict_math", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band",
-    "eid_renderer_band_range",
+    "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
 ]
 
 
@@ -88,6 +88,9 @@ def lib():
         "eid_renderer_run_post": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_run_post_band": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_band_range": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
+        "eid_renderer_set_stripes": (i32, [vp, u32, u32, u32]),
+        "eid_renderer_exchange_groups": (i32, [vp]),
+        "eid_renderer_exchange_range": (i32, [vp, i32, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -232,6 +235,17 @@ class Renderer:
 
     def set_band(self, y0, y1):
         _check(lib().eid_renderer_set_band(self._h, y0, y1))
+
+    def set_stripes(self, rank, world, stripe_rows):
+        _check(lib().eid_renderer_set_stripes(self._h, rank, world, stripe_rows))
+
+    def exchange_groups(self):
+        return lib().eid_renderer_exchange_groups(self._h)
+
+    def exchange_range(self, which, group):
+        base, off, n = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(lib().eid_renderer_exchange_range(self._h, which, group, C.byref(base), C.byref(off), C.byref(n)))
+        return base.value, off.value, n.value
 
     def band_range(self, which):
         base, off, n = C.c_void_p(), C.c_uint64(), C.c_uint64()

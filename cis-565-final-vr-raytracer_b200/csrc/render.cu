@@ -42,13 +42,23 @@ struct FrameParams {
   float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
   float env[3];
   int pitch, allocH;                      // allocation size of the 2-D images
-  int y0, y1;                             // full-res row band traced by this rank
+  // rows owned by this rank: stripes k = 0..sCount-1 of sRows full-res rows starting at sFirst + k*sStride (all multiples of 16,
+  // so no 8x8 quarter-res tile straddles two ranks).  Single GPU: one stripe covering the frame.
+  int sFirst, sStride, sRows, sCount;
   unsigned long long* counters;           // per frame: [0] closest-hit rays, [1] any-hit rays, [2] primary hits, [3] inner-node
                                           // visits, [4] triangle tests (STATS kernels only); since creation: [5] closest, [6] any
 };
 #define EID_NUM_COUNTERS 8
 
 struct RayCounters { unsigned int closest, any, primary, nodes, tris; };
+
+// blockIdx.y (blocks of `bh` rows) -> image row for a stripe layout given in the kernel's own resolution; rows >= limit are culled by the caller
+DEV int stripeRow(int first, int stride, int rows, int bh) {
+  const int bps = (rows + bh - 1) / bh;                  // blocks per stripe
+  const int k = blockIdx.y / bps, j = blockIdx.y - k * bps;
+  const int r = j * bh + threadIdx.y;
+  return (r < rows) ? first + k * stride + r : 0x3fffffff;
+}
 
 template <bool STATS>
 DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
@@ -124,10 +134,10 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 template <bool STATS>
 __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = P.y0 + blockIdx.y * 8 + threadIdx.y;
+  const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
   RayCounters rc = {0, 0, 0, 0, 0};
   const int W = P.st.size.x, H = P.st.size.y;
-  if (x < W && y < H && y < P.y1) {
+  if (x < W && y < H) {
     uint32_t seed = tea((uint32_t)W * (uint32_t)y + (uint32_t)x, P.st.time);   // :279
     f3 ro, rd;
     raySpawn<true>(P.cam, x, y, W, H, ro, rd);
@@ -249,10 +259,10 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
 template <bool STATS>
 __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = P.y0 / 2 + blockIdx.y * 8 + threadIdx.y;
+  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
   RayCounters rc = {0, 0, 0, 0, 0};
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
-  if (x < Wi && y < Hi && y < P.y1 / 2) {
+  if (x < Wi && y < Hi) {
     uint32_t seed = tea((uint32_t)Wi * (uint32_t)y + (uint32_t)x, P.st.time);   // :280
     f3 ro, rd;
     raySpawn<true>(P.cam, x, y, Wi, Hi, ro, rd);
@@ -421,11 +431,11 @@ DEV void thisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, floa
   nrm = make_float4(n.x, n.y, n.z, 0.f);
 }
 
-__global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int rowBegin, int rowEnd) {
+__global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int first, int stride, int rows) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = stripeRow(first, stride, rows, 8);
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
-  if (x >= W || y >= H || y >= rowEnd) return;
+  if (x >= W || y >= H || y < 0) return;
   float4 a, b;
   thisGeometry(P, x, y, W, H, a, b);
   const size_t pix = (size_t)y * P.pitch + x;
@@ -445,11 +455,11 @@ template <bool STRICT> DEV float edgeExp(float num, float sigma, float negInvSig
 
 template <bool INDIRECT, bool STRICT>
 __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel,
-                                                 int rowBegin, int rowEnd) {
+                                                 int first, int stride, int rows) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = stripeRow(first, stride, rows, 4);
   const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
-  if (x >= bw || y >= bh || y >= rowEnd) return;
+  if (x >= bw || y >= bh || y < 0) return;
   const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
   const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
   const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
@@ -506,10 +516,10 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
 // =================================================================================================
 // K5 — compose.comp:23-42
 // =================================================================================================
-__global__ void __launch_bounds__(256) k_compose(const FrameParams P, const float4* __restrict__ indSrc, int rowBegin, int rowEnd) {
+__global__ void __launch_bounds__(256) k_compose(const FrameParams P, const float4* __restrict__ indSrc, int first, int stride, int rows) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = rowBegin + blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= P.st.size.x || y >= P.st.size.y || y >= rowEnd) return;
+  const int y = stripeRow(first, stride, rows, 8);
+  if (x >= P.st.size.x || y >= P.st.size.y || y < 0) return;
   const size_t pix = (size_t)y * P.pitch + x;
   const float4 ind = loadImg(indSrc, P, x / 2, y / 2);
   if (P.st.modulate == 0) {
@@ -552,7 +562,7 @@ struct eid_renderer {
   int lastSet = 0;
   RtxState lastState{};
   bool hasRun = false;
-  uint32_t bandY0 = 0, bandY1 = 0; bool bandSet = false;
+  uint32_t sFirst = 0, sStride = 0, sRows = 0; bool stripesSet = false;   // multi-GPU row ownership (see FrameParams)
   bool profiling = false;
   bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
   cudaEvent_t ev[EID_K_COUNT + 1] = {};
@@ -592,7 +602,7 @@ void eid_renderer::allocate() {
   zalloc((void**)&geom[2], ni * 16); zalloc((void**)&geom[3], ni * 16);
   CUDA_CHECK(cudaStreamSynchronize(stream));
   hasRun = false; lastSet = 0;
-  if (!bandSet) { bandY0 = 0; bandY1 = height; }
+  if (!stripesSet) { sFirst = 0; sRows = (height + 15) / 16 * 16; sStride = 1u << 20; }
 }
 
 static void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
@@ -617,8 +627,8 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
   for (int k = 0; k < 3; ++k) P.env[k] = r->env[k];
   P.pitch = (int)r->width; P.allocH = (int)r->height;
-  P.y0 = 0; P.y1 = st.size.y;
-  if (r->bandSet) { P.y0 = (int)std::min<uint32_t>(r->bandY0, (uint32_t)st.size.y); P.y1 = (int)std::min<uint32_t>(r->bandY1, (uint32_t)st.size.y); }
+  P.sFirst = (int)r->sFirst; P.sStride = (int)r->sStride; P.sRows = (int)r->sRows;
+  P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
   P.counters = r->counters;
   r->lastSet = set; r->lastState = st; r->hasRun = true;
 }
@@ -629,16 +639,14 @@ static void launchTrace(eid_renderer* r, const FrameParams& P) {
   CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
   memset(&r->stats, 0, sizeof(r->stats));
   mark(r, 0);
-  const int rows = P.y1 - P.y0;
-  if (rows > 0) {
-    dim3 b(8, 8), g((P.st.size.x + 7) / 8, (rows + 7) / 8);
+  if (P.sCount > 0) {
+    dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     if (r->countVisits) k_direct_stage<true><<<g, b, 0, r->stream>>>(P); else k_direct_stage<false><<<g, b, 0, r->stream>>>(P);
     r->stats.kernelLaunches[EID_K_DIRECT]++;
   }
   mark(r, 1);
-  const int irows = P.y1 / 2 - P.y0 / 2;
-  if (irows > 0 && P.st.size.x / 2 > 0) {
-    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, (irows + 7) / 8);
+  if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
+    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
     if (r->countVisits) k_indirect_stage<true><<<g, b, 0, r->stream>>>(P); else k_indirect_stage<false><<<g, b, 0, r->stream>>>(P);
     r->stats.kernelLaunches[EID_K_INDIRECT]++;
   }
@@ -653,45 +661,46 @@ static void launchTrace(eid_renderer* r, const FrameParams& P) {
 // full-frame evaluation, only the evaluated row ranges shrink.
 static void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
-  const int y0 = sharded ? P.y0 : 0, y1 = sharded ? P.y1 : H;
-  auto clampRows = [](int a, int b, int lim, int& ra, int& rb) { ra = std::max(0, a); rb = std::min(lim, b); };
-  if (P.st.denoise > 0 && y1 > y0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
-    int pa, pb;
-    clampRows(y0 - 124, y1 + 124, H, pa, pb);   // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124) for K4
-    if (pb > pa) { dim3 b(32, 8), g((W + 31) / 32, (pb - pa + 7) / 8); k_denoise_prep<<<g, b, 0, r->stream>>>(P, pa, pb); r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++; }
+  // stripe layout the post kernels cover: this rank's stripes (sharded) or one stripe = the whole frame
+  const int first = sharded ? P.sFirst : 0, stride = sharded ? P.sStride : (1 << 20), srows = sharded ? P.sRows : (H + 15) / 16 * 16;
+  const int count = sharded ? P.sCount : 1;
+  // a level evaluated with `halo` extra rows on both sides of every stripe (overlaps between stripes recompute identical values)
+  auto gridRows = [&](int rows, int bh) { return count * ((rows + bh - 1) / bh); };
+  if (P.st.denoise > 0 && count > 0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
+    { // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4
+      const int rows = srows + 2 * 124;
+      dim3 b(32, 8), g((W + 31) / 32, gridRows(rows, 8));
+      k_denoise_prep<<<g, b, 0, r->stream>>>(P, first - 124, stride, rows);
+      r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
+    }
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
     float4* dst[4] = {P.dirA, P.dirB, P.dirA, P.directImg};
     const int halo[4] = {28, 24, 16, 0};
     for (int i = 0; i < 4; ++i) {
-      int ra, rb;
-      clampRows(y0 - halo[i], y1 + halo[i], H, ra, rb);
-      dim3 b(32, 4), g((W + 31) / 32, (rb - ra + 3) / 4);
-      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, ra, rb);
-      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, ra, rb);
+      const int h = sharded ? halo[i] : 0, rows = srows + 2 * h;
+      dim3 b(32, 4), g((W + 31) / 32, gridRows(rows, 4));
+      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, first - h, stride, rows);
+      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, first - h, stride, rows);
       r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
     }
   }
   mark(r, 3);
-  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && y1 / 2 > y0 / 2) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
+  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && count > 0) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
     const int halo[5] = {60, 56, 48, 32, 0};
-    const int h0 = y0 / 2, h1 = sharded ? y1 / 2 : Hi;
     for (int i = 0; i < 5; ++i) {
-      int ra, rb;
-      clampRows(h0 - halo[i], h1 + halo[i], Hi, ra, rb);
-      dim3 b(32, 4), g((Wi + 31) / 32, (rb - ra + 3) / 4);
-      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, ra, rb);
-      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, ra, rb);
+      const int h = sharded ? halo[i] : 0, rows = srows / 2 + 2 * h;
+      dim3 b(32, 4), g((Wi + 31) / 32, gridRows(rows, 4));
+      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, first / 2 - h, stride / 2, rows);
+      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, first / 2 - h, stride / 2, rows);
       r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
     }
   }
   mark(r, 4);
-  if (y1 > y0) {
-    int ra, rb;
-    clampRows(y0, y1, H, ra, rb);
-    dim3 b(32, 8), g((W + 31) / 32, (rb - ra + 7) / 8);
-    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA, ra, rb);
+  if (count > 0) {
+    dim3 b(32, 8), g((W + 31) / 32, gridRows(srows, 8));
+    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA, first, stride, srows);
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
   mark(r, 5);
@@ -751,7 +760,7 @@ int eid_renderer_resize(eid_renderer* r, uint32_t width, uint32_t height) {
   CUDA_CHECK(cudaSetDevice(r->device));
   CUDA_CHECK(cudaStreamSynchronize(r->stream));
   r->release();
-  r->width = width; r->height = height; r->bandSet = false;
+  r->width = width; r->height = height; r->stripesSet = false;
   r->allocate();
   return EID_OK;
   EID_CATCH
@@ -936,19 +945,42 @@ int eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_band: null renderer");
   if (y0 > y1 || y1 > r->height) raise(EID_ERR_INVALID, "band [%u,%u) outside 0..%u", y0, y1, r->height);
-  if ((y0 % 16) != 0 || ((y1 % 16) != 0 && y1 != r->height)) raise(EID_ERR_INVALID, "band edges must be multiples of 16 rows (8x8 half-res tiles must not straddle ranks)");
-  r->bandY0 = y0; r->bandY1 = y1; r->bandSet = true;
+  if ((y0 % 16) != 0 || (y1 % 16) != 0) raise(EID_ERR_INVALID, "band edges must be multiples of 16 rows (8x8 half-res tiles must not straddle ranks)");
+  if (y1 == y0) raise(EID_ERR_INVALID, "empty band");
+  r->sFirst = y0; r->sRows = y1 - y0; r->sStride = 1u << 20; r->stripesSet = true;
   return EID_OK;
   EID_CATCH
 }
 
-int eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes) {
+int eid_renderer_set_stripes(eid_renderer* r, uint32_t rank, uint32_t world, uint32_t stripeRows) {
   EID_TRY
-  if (!r || !dev_base || !offset || !bytes) raise(EID_ERR_INVALID, "eid_renderer_band_range: null argument");
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_stripes: null renderer");
+  if (!world || rank >= world) raise(EID_ERR_INVALID, "rank %u outside world %u", rank, world);
+  if (!stripeRows || (stripeRows % 16) != 0) raise(EID_ERR_INVALID, "stripeRows must be a positive multiple of 16");
+  if (r->height % (world * stripeRows) != 0) raise(EID_ERR_INVALID, "renderer height %u is not a multiple of world*stripeRows = %u (pad the allocation)", r->height, world * stripeRows);
+  r->sFirst = rank * stripeRows; r->sRows = stripeRows; r->sStride = world * stripeRows; r->stripesSet = true;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_exchange_groups(eid_renderer* r) {
+  if (!r) return -1;
+  if (!r->stripesSet || r->sStride >= (1u << 20)) return 1;
+  return (int)(r->height / r->sStride);
+}
+
+// Byte range of this rank's stripe in exchange group `group` of buffer `which`: the group occupies
+// [groupOffset, groupOffset + world*chunkBytes) and rank k's chunk starts at groupOffset + k*chunkBytes, so an in-place
+// all-gather over that region (equal chunks) completes the group on every rank.
+int eid_renderer_exchange_range(eid_renderer* r, int which, uint32_t group, void** dev_base, uint64_t* offset, uint64_t* bytes) {
+  EID_TRY
+  if (!r || !dev_base || !offset || !bytes) raise(EID_ERR_INVALID, "eid_renderer_exchange_range: null argument");
   size_t total = 0; void* p = bufferPtr(r, which, total);
   if (!p) raise(EID_ERR_INVALID, "no such buffer %d", which);
-  const uint64_t y0 = r->bandSet ? r->bandY0 : 0, y1 = r->bandSet ? r->bandY1 : r->height;
-  const uint64_t W = r->width, Wi = r->width / 2;
+  if ((int)group >= eid_renderer_exchange_groups(r)) raise(EID_ERR_INVALID, "exchange group %u out of range", group);
+  const bool single = r->sStride >= (1u << 20);
+  const uint64_t y0 = (uint64_t)r->sFirst + (single ? 0 : (uint64_t)group * r->sStride), y1 = y0 + r->sRows;
+  const uint64_t W = r->width;
   const uint64_t sw = r->hasRun ? (uint64_t)r->lastState.size.x : W;   // reservoir buffers are pitched by RtxState.size.x
   uint64_t rowBytes = 0, a = y0, b = y1;
   switch (which) {
@@ -960,10 +992,14 @@ int eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_
     case EID_BUF_THIS_INDIRECT_RESV: case EID_BUF_LAST_INDIRECT_RESV: rowBytes = (sw / 2) * sizeof(IndirectReservoir); a = y0 / 2; b = y1 / 2; break;
     default: raise(EID_ERR_INVALID, "no band layout for buffer %d", which);
   }
-  (void)Wi;
+  if (b * rowBytes > total) raise(EID_ERR_INVALID, "stripe exceeds the buffer (allocation not padded to the stripe layout?)");
   *dev_base = p; *offset = a * rowBytes; *bytes = (b - a) * rowBytes;
   return EID_OK;
   EID_CATCH
+}
+
+int eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes) {
+  return eid_renderer_exchange_range(r, which, 0, dev_base, offset, bytes);
 }
 
 }  // extern "C"

@@ -32,3 +32,18 @@ def all_gather_bands(dist, full, rank, world, inplace=True):
         mine = mine.clone()
     dist.all_gather_into_tensor(full, mine)
     return full
+
+
+def stripe_layout(height, world, groups=2):
+    """Interleaved ownership (load balance: image regions differ a lot in tracing cost).  Rows are cut into stripes of S rows
+    (multiple of 16); stripe i belongs to rank i % world; `world` consecutive stripes form one exchange group.
+    Returns (S, padded allocation height = S * world * groups)."""
+    if world == 1:
+        return (height + 15) // 16 * 16, height
+    s = ((height + world * groups - 1) // (world * groups) + 15) // 16 * 16
+    return s, s * world * groups
+
+
+def stripes_of(rank, world, height, groups=2):
+    s, alloc = stripe_layout(height, world, groups)
+    return [(g * world * s + rank * s, g * world * s + (rank + 1) * s) for g in range(groups)]

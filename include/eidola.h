@@ -262,12 +262,19 @@ EID_API int  eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out);
  * all-gathers the three exchange buffers below (the ONE collective) and calls
  * eid_renderer_run_post, which runs denoise+compose on the full frame. */
 EID_API int  eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1);
+/* Interleaved ownership for load balance: rows are cut into stripes of `stripeRows` (multiple of 16); stripe i belongs to
+ * rank i % world.  `world` consecutive stripes form an exchange group: a contiguous region of equal-sized chunks, completed on
+ * every rank by one in-place all-gather.  The renderer's allocation height must be a multiple of world*stripeRows. */
+EID_API int  eid_renderer_set_stripes(eid_renderer* r, uint32_t rank, uint32_t world, uint32_t stripeRows);
+EID_API int  eid_renderer_exchange_groups(eid_renderer* r);
+/* device pointer, byte offset and byte size of this rank's chunk in exchange group `group` of buffer `which` */
+EID_API int  eid_renderer_exchange_range(eid_renderer* r, int which, uint32_t group, void** dev_base, uint64_t* offset, uint64_t* bytes);
 EID_API int  eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames);
 EID_API int  eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames);
 /* Mode B (two exchange steps): denoise + compose only what this rank's band of the FINAL images needs (the A-Trous levels are
  * evaluated on the band plus the reach of the later levels); the caller then all-gathers EID_BUF_DIRECT and EID_BUF_INDIRECT. */
 EID_API int  eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, int frames);
-/* device pointer + byte range of this rank's band inside buffer `which`
+/* = eid_renderer_exchange_range(group 0): device pointer + byte range of this rank's band inside buffer `which`
  * (EID_BUF_THIS_GBUFFER, EID_BUF_DIRECT, EID_BUF_DENOISE_IND_A, EID_BUF_MOTION, reservoirs) */
 EID_API int  eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes);
 

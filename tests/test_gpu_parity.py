@@ -355,3 +355,65 @@ def test_error_behaviour_gpu():
         r.set_band(8, 64)                                                     # band edges must be multiples of 16
     r.run(common.frame_state(64, 64, info, 0), 0)                             # still usable after errors
     r.sync()
+
+
+@pytest.mark.parametrize("mode", ["replicated", "sharded"])
+def test_interleaved_stripes_equal_full_frame(mode):
+    """Interleaved stripe ownership (load balance): 3 ranks x 2 exchange groups emulated on one device; the per-group
+    in-place all-gather is played by read/stitch/write through eid_renderer_exchange_range."""
+    from eidola_b200 import sharding
+    arrays = scenes.small_room()
+    w, h, world, groups = 192, 150, 3, 2
+    srows, alloc_h = sharding.stripe_layout(h, world, groups)
+    assert srows % 16 == 0 and alloc_h == srows * world * groups and alloc_h >= h
+    psc = eid.Scene(0)
+    psc.load_arrays(arrays)
+    acc = eid.AccelStructure()
+    acc.create(psc)
+    full = eid.Renderer()
+    full.create((w, alloc_h), psc, acc)
+    full.set_env_constant(common.ENV)
+    ranks = []
+    for k in range(world):
+        r = eid.Renderer()
+        r.create((w, alloc_h), psc, acc)
+        r.set_env_constant(common.ENV)
+        r.set_stripes(k, world, srows)
+        assert r.exchange_groups() == groups
+        ranks.append(r)
+    info = psc.info()
+    psc.update_camera(w, h)
+
+    def all_gather(buffers):
+        for which in buffers:
+            stitched = ranks[0].read(which).view(np.uint8).copy()
+            for r in ranks[1:]:
+                mine = r.read(which).view(np.uint8)
+                for g in range(groups):
+                    _, off, n = r.exchange_range(which, g)
+                    stitched[off:off + n] = mine[off:off + n]
+            for r in ranks:
+                r.write(which, stitched)
+
+    for f in range(3):
+        psc.update_camera(w, h)
+        st = common.frame_state(w, h, info, f)
+        full.run(st, f)
+        for r in ranks:
+            r.run_trace(st, f)
+        all_gather([abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A])
+        if mode == "replicated":
+            for r in ranks:
+                r.run_post(st, f)
+        else:
+            for r in ranks:
+                r.run_post_band(st, f)
+            all_gather([abi.BUF_DIRECT, abi.BUF_INDIRECT])
+        for which in (abi.BUF_DIRECT, abi.BUF_INDIRECT):
+            want = full.read(which).view(np.uint8).reshape(alloc_h, -1)[:h]
+            for r in ranks:
+                got = r.read(which).view(np.uint8).reshape(alloc_h, -1)[:h]
+                assert got.tobytes() == want.tobytes(), "%s stripes: buffer %d differs from the full-frame run (frame %d)" % (mode, which, f)
+    # ray counters: the ranks together issue exactly the rays of the single-GPU frame
+    tot = [sum(getattr(r.stats(), k) for r in ranks) for k in ("closestHitRays", "anyHitRays")]
+    assert tot == [full.stats().closestHitRays, full.stats().anyHitRays]
