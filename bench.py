@@ -217,6 +217,7 @@ def run_cuda(args):
     rr = eid.Renderer()
     rr.create((w, alloc_h), scene, accel, stream=stream.cuda_stream)
     rr.set_env_constant(ENV)
+    rr.set_overlap(not args.no_overlap)
     if world > 1:
         rr.set_stripes(rank, world, stripe_rows)
 
@@ -318,7 +319,9 @@ def run_cuda(args):
 
     # per-kernel pass (CUDA events inside the library around every stage, same frames/state sequence) + visit counters
     ksteps = max(3, min(args.steps, 16))
+    rr.set_overlap(False)                       # isolated per-stage times: strict K1..K5 order on one stream
     _, _, kms = timed(ksteps, frame, None, profiling=1)
+    rr.set_overlap(not args.no_overlap)
     frame += ksteps
     rr.set_profiling(2)
     step(frame)
@@ -377,6 +380,9 @@ def run_cuda(args):
                                  "vertex/material gathers) / CUDA-event time of that kernel; at 1 M triangles the traversal working set is "
                                  "L2-resident, so this is an L2/latency-bound kernel measured against the HBM roof"},
             "kernels": kernels,
+            "kernels_note": "per-stage times are measured in a separate pass with the stages serialised on one stream; the timed frames "
+                            + ("run K3 concurrently with K2+K4 on a second stream, so their sum exceeds ms_per_step" if not args.no_overlap else "are serialised too"),
+            "exchange1_ms": float(vs.exchangeMs) if world > 1 else None,
             "visits_per_ray": {"nodes": vs.nodeVisits / tot_rays, "triangles": vs.triangleTests / tot_rays},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -403,7 +409,8 @@ def main():
     ap.add_argument("--impl", default="eidola", choices=["eidola", "reference"])
     ap.add_argument("--quick", action="store_true", help="tiny scene/resolution (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stripe-groups", type=int, default=2, help="N>1: interleaved stripes per rank (1 = one contiguous band per rank)")
+    ap.add_argument("--no-overlap", action="store_true", help="strict K1..K5 order on one stream (default: K3 runs beside K2/K4 on a second stream)")
+    ap.add_argument("--stripe-groups", type=int, default=1, help="N>1: interleaved stripes per rank (1 = one contiguous band per rank)")
     ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
                     help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
                          "one exchange step, every rank post-processes the full frame")

@@ -33,7 +33,7 @@ EXPORTS = [
     "eid_scene_table_bytes", "eid_scene_read_table",
     "eid_accel_build", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
-    "eid_renderer_set_strict_math", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
+    "eid_renderer_set_strict_math", "eid_renderer_set_overlap", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
@@ -74,6 +74,7 @@ def lib():
         "eid_renderer_destroy": (None, [vp]),
         "eid_renderer_set_env_constant": (i32, [vp, abi.c_float_p]),
         "eid_renderer_set_strict_math": (i32, [vp, i32]),
+        "eid_renderer_set_overlap": (i32, [vp, i32]),
         "eid_renderer_run": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_sync": (i32, [vp]),
         "eid_renderer_get_outputs": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -220,6 +221,9 @@ class Renderer:
 
     def set_strict_math(self, on):        # bit-reproducible denoiser exp (parity runs); default is the fast MUFU path
         _check(lib().eid_renderer_set_strict_math(self._h, int(on)))
+
+    def set_overlap(self, on):            # K3 on a second stream beside K2/K4 (default on)
+        _check(lib().eid_renderer_set_overlap(self._h, int(on)))
 
     def run(self, state, frames):         # Renderer::run(cmdBuf, state, profiler, descSets, frames); async
         _check(lib().eid_renderer_run(self._h, C.byref(state), frames))

@@ -122,7 +122,8 @@ class FrameStats(C.Structure):
     _fields_ = [("closestHitRays", C.c_uint64), ("anyHitRays", C.c_uint64), ("primaryHits", C.c_uint64),
                 ("launches", C.c_uint32), ("kernelMs", C.c_float * EID_K_COUNT),
                 ("kernelLaunches", C.c_uint32 * EID_K_COUNT), ("nodeVisits", C.c_uint64),
-                ("triangleTests", C.c_uint64), ("totalClosestHitRays", C.c_uint64), ("totalAnyHitRays", C.c_uint64)]
+                ("triangleTests", C.c_uint64), ("totalClosestHitRays", C.c_uint64), ("totalAnyHitRays", C.c_uint64),
+                ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64)]
 
 
 # eid_scene_table

@@ -74,6 +74,7 @@ DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
     if (d) atomicAdd(&P.counters[2], (unsigned long long)d);
     if (STATS) { if (n) atomicAdd(&P.counters[3], (unsigned long long)n); if (t) atomicAdd(&P.counters[4], (unsigned long long)t); }
   }
+  if (STATS) atomicMax(&P.counters[7], (unsigned long long)c.nodes);   // worst thread (all its rays) since the renderer was created
 }
 
 // image access: out-of-bounds loads return 0 (Vulkan robust image access), stores are dropped
@@ -565,7 +566,11 @@ struct eid_renderer {
   uint32_t sFirst = 0, sStride = 0, sRows = 0; bool stripesSet = false;   // multi-GPU row ownership (see FrameParams)
   bool profiling = false;
   bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
-  cudaEvent_t ev[EID_K_COUNT + 1] = {};
+  cudaEvent_t ev[2 * EID_K_COUNT] = {};   // start/stop per stage
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evPost = nullptr;
+  cudaStream_t aux = nullptr;             // second stream: K3 runs beside K2/K4 (see launchFrame)
+  bool overlap = true;
+  bool postStarted = false;
   eid_frame_stats stats{};
   bool statsPending = false;
 
@@ -633,80 +638,158 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   r->lastSet = set; r->lastState = st; r->hasRun = true;
 }
 
-static inline void mark(eid_renderer* r, int i) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[i], r->stream)); }
+// ---- stage launchers -----------------------------------------------------------------------------------------------------------
+// Every stage records a start/stop CUDA-event pair on the stream it runs on when profiling is enabled (stage k: ev[2k], ev[2k+1]).
+static inline void markStart(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage], st)); }
+static inline void markStop(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage + 1], st)); }
 
-static void launchTrace(eid_renderer* r, const FrameParams& P) {
+static void beginFrame(eid_renderer* r) {
   CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
   memset(&r->stats, 0, sizeof(r->stats));
-  mark(r, 0);
-  if (P.sCount > 0) {
-    dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
-    if (r->countVisits) k_direct_stage<true><<<g, b, 0, r->stream>>>(P); else k_direct_stage<false><<<g, b, 0, r->stream>>>(P);
-    r->stats.kernelLaunches[EID_K_DIRECT]++;
-  }
-  mark(r, 1);
-  if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
-    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
-    if (r->countVisits) k_indirect_stage<true><<<g, b, 0, r->stream>>>(P); else k_indirect_stage<false><<<g, b, 0, r->stream>>>(P);
-    r->stats.kernelLaunches[EID_K_INDIRECT]++;
-  }
-  mark(r, 2);
+  r->postStarted = false;
 }
 
-// Denoise + compose.  sharded = false: the whole frame (single GPU, or the replicated post of multi-GPU mode A).
-// sharded = true (multi-GPU mode B): only what this rank's band [P.y0, P.y1) of the FINAL images needs.  An A-Trous level l
-// reaches 2*2^l rows, so level l must be evaluated on the band plus the summed reach of the levels after it
-// (direct: 28/24/16/0 rows for levels 0..3; indirect: 60/56/48/32/0 quarter-res rows for levels 0..4); the inputs of level 0
-// (pre-denoise images, G-buffer) are complete on every rank after the first exchange step.  Values are identical to the
-// full-frame evaluation, only the evaluated row ranges shrink.
-static void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
-  const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
-  // stripe layout the post kernels cover: this rank's stripes (sharded) or one stripe = the whole frame
-  const int first = sharded ? P.sFirst : 0, stride = sharded ? P.sStride : (1 << 20), srows = sharded ? P.sRows : (H + 15) / 16 * 16;
-  const int count = sharded ? P.sCount : 1;
-  // a level evaluated with `halo` extra rows on both sides of every stripe (overlaps between stripes recompute identical values)
-  auto gridRows = [&](int rows, int bh) { return count * ((rows + bh - 1) / bh); };
-  if (P.st.denoise > 0 && count > 0) {   // renderer.cpp:178-189: thisDirect -> A -> B -> A -> thisDirect
-    { // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4
-      const int rows = srows + 2 * 124;
-      dim3 b(32, 8), g((W + 31) / 32, gridRows(rows, 8));
-      k_denoise_prep<<<g, b, 0, r->stream>>>(P, first - 124, stride, rows);
-      r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
-    }
+static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
+  markStart(r, EID_K_DIRECT, st);
+  if (P.sCount > 0) {
+    dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
+    if (r->countVisits) k_direct_stage<true><<<g, b, 0, st>>>(P); else k_direct_stage<false><<<g, b, 0, st>>>(P);
+    r->stats.kernelLaunches[EID_K_DIRECT]++;
+  }
+  markStop(r, EID_K_DIRECT, st);
+}
+
+static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
+  markStart(r, EID_K_INDIRECT, st);
+  if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
+    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
+    if (r->countVisits) k_indirect_stage<true><<<g, b, 0, st>>>(P); else k_indirect_stage<false><<<g, b, 0, st>>>(P);
+    r->stats.kernelLaunches[EID_K_INDIRECT]++;
+  }
+  markStop(r, EID_K_INDIRECT, st);
+}
+
+// Row layout of the post stages.  sharded = false: the whole frame (single GPU, or the replicated post of multi-GPU mode A).
+// sharded = true (multi-GPU mode B): only what this rank's stripes of the FINAL images need.  An A-Trous level l reaches 2*2^l
+// rows, so level l is evaluated on the stripe plus the summed reach of the levels after it (direct: 28/24/16/0 rows for levels
+// 0..3; indirect: 60/56/48/32/0 quarter-res rows for levels 0..4); the inputs of level 0 (pre-denoise images, G-buffer) are
+// complete on every rank after the first exchange step.  Values are identical to the full-frame evaluation, only the evaluated
+// row ranges shrink (overlapping ranges of neighbouring stripes recompute identical values).
+struct PostLayout { int first, stride, srows, count; bool sharded; };
+static PostLayout postLayout(const FrameParams& P, bool sharded) {
+  PostLayout L;
+  L.sharded = sharded;
+  L.first = sharded ? P.sFirst : 0; L.stride = sharded ? P.sStride : (1 << 20);
+  L.srows = sharded ? P.sRows : (P.st.size.y + 15) / 16 * 16; L.count = sharded ? P.sCount : 1;
+  return L;
+}
+static inline unsigned gridRows(const PostLayout& L, int rows, int bh) { return (unsigned)(L.count * ((rows + bh - 1) / bh)); }
+
+// geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4; accounted to the direct denoiser
+static void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
+  if (P.st.denoise <= 0 || L.count <= 0) return;
+  const int rows = L.srows + 2 * 124, W = P.st.size.x;
+  dim3 b(32, 8), g((W + 31) / 32, gridRows(L, rows, 8));
+  k_denoise_prep<<<g, b, 0, st>>>(P, L.first - 124, L.stride, rows);
+  r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
+}
+
+static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
+  if (P.st.denoise > 0 && L.count > 0) {   // thisDirect -> A -> B -> A -> thisDirect
+    const int W = P.st.size.x;
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
     float4* dst[4] = {P.dirA, P.dirB, P.dirA, P.directImg};
     const int halo[4] = {28, 24, 16, 0};
     for (int i = 0; i < 4; ++i) {
-      const int h = sharded ? halo[i] : 0, rows = srows + 2 * h;
-      dim3 b(32, 4), g((W + 31) / 32, gridRows(rows, 4));
-      if (r->strictMath) k_denoise<false, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, first - h, stride, rows);
-      else k_denoise<false, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 3, first - h, stride, rows);
+      const int h = L.sharded ? halo[i] : 0, rows = L.srows + 2 * h;
+      dim3 b(32, 4), g((W + 31) / 32, gridRows(L, rows, 4));
+      if (r->strictMath) k_denoise<false, true><<<g, b, 0, st>>>(P, src[i], dst[i], i, 3, L.first - h, L.stride, rows);
+      else k_denoise<false, false><<<g, b, 0, st>>>(P, src[i], dst[i], i, 3, L.first - h, L.stride, rows);
       r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
     }
   }
-  mark(r, 3);
-  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && count > 0) {   // renderer.cpp:191-202: IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
+}
+
+static void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:191-202
+  const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
+  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && L.count > 0) {   // IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
     const int halo[5] = {60, 56, 48, 32, 0};
     for (int i = 0; i < 5; ++i) {
-      const int h = sharded ? halo[i] : 0, rows = srows / 2 + 2 * h;
-      dim3 b(32, 4), g((Wi + 31) / 32, gridRows(rows, 4));
-      if (r->strictMath) k_denoise<true, true><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, first / 2 - h, stride / 2, rows);
-      else k_denoise<true, false><<<g, b, 0, r->stream>>>(P, src[i], dst[i], i, 4, first / 2 - h, stride / 2, rows);
+      const int h = L.sharded ? halo[i] : 0, rows = L.srows / 2 + 2 * h;
+      dim3 b(32, 4), g((Wi + 31) / 32, gridRows(L, rows, 4));
+      if (r->strictMath) k_denoise<true, true><<<g, b, 0, st>>>(P, src[i], dst[i], i, 4, L.first / 2 - h, L.stride / 2, rows);
+      else k_denoise<true, false><<<g, b, 0, st>>>(P, src[i], dst[i], i, 4, L.first / 2 - h, L.stride / 2, rows);
       r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
     }
   }
-  mark(r, 4);
-  if (count > 0) {
-    dim3 b(32, 8), g((W + 31) / 32, gridRows(srows, 8));
-    k_compose<<<g, b, 0, r->stream>>>(P, P.st.denoise > 0 ? P.indB : P.indA, first, stride, srows);
+}
+
+static void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
+  markStart(r, EID_K_COMPOSE, st);
+  if (L.count > 0) {
+    dim3 b(32, 8), g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 8));
+    k_compose<<<g, b, 0, st>>>(P, P.st.denoise > 0 ? P.indB : P.indA, L.first, L.stride, L.srows);
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
-  mark(r, 5);
+  markStop(r, EID_K_COMPOSE, st);
+}
+
+static void endFrame(eid_renderer* r) {
   CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
   r->statsPending = true;
   CUDA_CHECK(cudaGetLastError());
+}
+
+// run `work` on the auxiliary stream between a fork after everything enqueued so far on the main stream and a later join
+static void forkAux(eid_renderer* r) { CUDA_CHECK(cudaEventRecord(r->evFork, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(r->aux, r->evFork, 0)); }
+static void joinAux(eid_renderer* r) { CUDA_CHECK(cudaEventRecord(r->evJoin, r->aux)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evJoin, 0)); }
+
+// The reference's schedule is K1, K2, K3x4, K4x5, K5 in strict order (renderer.cpp:154-206), but its true dependencies are
+// K1 -> {K2, K3}, K2 -> K4, {K3, K4} -> K5.  K2 (quarter-res, long dependent chains, few threads) leaves most issue slots
+// idle, so with `overlap` the direct denoiser K3 runs on a second stream concurrently with K2 + K4.  Results are identical.
+static void launchTrace(eid_renderer* r, const FrameParams& P) {
+  beginFrame(r);
+  stageDirect(r, P, r->stream);
+  stageIndirect(r, P, r->stream);
+}
+
+static void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
+  const PostLayout L = postLayout(P, sharded);
+  if (r->profiling) CUDA_CHECK(cudaEventRecord(r->evPost, r->stream));   // everything between the trace stages and here = exchange
+  r->postStarted = true;
+  cudaStream_t sd = r->overlap ? r->aux : r->stream;
+  markStart(r, EID_K_DENOISE_DIRECT, r->stream);
+  stagePrep(r, P, L, r->stream);
+  if (r->overlap) forkAux(r);
+  stageDenoiseDirect(r, P, L, sd);
+  markStop(r, EID_K_DENOISE_DIRECT, sd);
+  markStart(r, EID_K_DENOISE_INDIRECT, r->stream);
+  stageDenoiseIndirect(r, P, L, r->stream);
+  markStop(r, EID_K_DENOISE_INDIRECT, r->stream);
+  if (r->overlap) joinAux(r);
+  stageCompose(r, P, L, r->stream);
+  endFrame(r);
+}
+
+static void launchFrame(eid_renderer* r, const FrameParams& P) {
+  if (!r->overlap) { launchTrace(r, P); launchPost(r, P, false); return; }
+  const PostLayout L = postLayout(P, false);
+  beginFrame(r);
+  stageDirect(r, P, r->stream);
+  markStart(r, EID_K_DENOISE_DIRECT, r->stream);
+  stagePrep(r, P, L, r->stream);
+  forkAux(r);
+  stageDenoiseDirect(r, P, L, r->aux);
+  markStop(r, EID_K_DENOISE_DIRECT, r->aux);
+  stageIndirect(r, P, r->stream);
+  markStart(r, EID_K_DENOISE_INDIRECT, r->stream);
+  stageDenoiseIndirect(r, P, L, r->stream);
+  markStop(r, EID_K_DENOISE_INDIRECT, r->stream);
+  joinAux(r);
+  stageCompose(r, P, L, r->stream);
+  endFrame(r);
 }
 
 static void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
@@ -746,6 +829,9 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
     CUDA_CHECK(cudaMallocHost(&r->countersHost, EID_NUM_COUNTERS * sizeof(unsigned long long)));
     memset(r->countersHost, 0, EID_NUM_COUNTERS * sizeof(unsigned long long));
     for (auto& e : r->ev) CUDA_CHECK(cudaEventCreate(&e));
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&r->evJoin, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreate(&r->evPost));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&r->aux, cudaStreamNonBlocking));
     r->allocate();
   } catch (...) { eid_renderer_destroy(r); throw; }
   *out = r;
@@ -774,6 +860,8 @@ void eid_renderer_destroy(eid_renderer* r) {
   cudaFree(r->counters);
   if (r->countersHost) cudaFreeHost(r->countersHost);
   for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+  if (r->evFork) cudaEventDestroy(r->evFork); if (r->evJoin) cudaEventDestroy(r->evJoin); if (r->evPost) cudaEventDestroy(r->evPost);
+  if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
   if (r->ownStream && r->stream) cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -792,8 +880,7 @@ int eid_renderer_run(eid_renderer* r, const RtxState* state, int frames) {
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
   fillParams(r, *state, frames, P);
-  launchTrace(r, P);
-  launchPost(r, P, false);
+  launchFrame(r, P);
   return EID_OK;
   EID_CATCH
 }
@@ -816,7 +903,6 @@ int eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames) {
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
   fillParams(r, *state, frames, P);
-  if (r->profiling) { mark(r, 2); }
   launchPost(r, P, false);
   return EID_OK;
   EID_CATCH
@@ -828,7 +914,6 @@ int eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, int frame
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
   fillParams(r, *state, frames, P);
-  if (r->profiling) { mark(r, 2); }
   launchPost(r, P, true);
   return EID_OK;
   EID_CATCH
@@ -838,7 +923,7 @@ int eid_renderer_sync(eid_renderer* r) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_sync: null renderer");
   CUDA_CHECK(cudaSetDevice(r->device));
-  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));   // the aux stream is always joined into the main stream before a frame ends
   return EID_OK;
   EID_CATCH
 }
@@ -891,8 +976,7 @@ int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxS
   if (cam) r->scene->host.camera = *cam;
   FrameParams P;
   fillParams(r, *state, frames, P);
-  launchTrace(r, P);
-  launchPost(r, P, false);
+  launchFrame(r, P);
   const size_t rowBytes = (size_t)state->size.x * 16;
   if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->directImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
   if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->indirectImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
@@ -905,6 +989,14 @@ int eid_renderer_set_strict_math(eid_renderer* r, int enabled) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_strict_math: null renderer");
   r->strictMath = enabled != 0;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_overlap(eid_renderer* r, int enabled) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_overlap: null renderer");
+  r->overlap = enabled != 0;
   return EID_OK;
   EID_CATCH
 }
@@ -927,13 +1019,18 @@ int eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out) {
     r->stats.closestHitRays = r->countersHost[0]; r->stats.anyHitRays = r->countersHost[1]; r->stats.primaryHits = r->countersHost[2];
     r->stats.nodeVisits = r->countersHost[3]; r->stats.triangleTests = r->countersHost[4];
     r->stats.totalClosestHitRays = r->countersHost[5]; r->stats.totalAnyHitRays = r->countersHost[6];
+    r->stats.maxNodeVisitsPerThread = r->countersHost[7];
     r->stats.launches = 0;
     for (int k = 0; k < EID_K_COUNT; ++k) r->stats.launches += r->stats.kernelLaunches[k];
-    if (r->profiling)
+    if (r->profiling) {
+      CUDA_CHECK(cudaStreamSynchronize(r->aux));
       for (int k = 0; k < EID_K_COUNT; ++k) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r->ev[k], r->ev[k + 1]) == cudaSuccess) r->stats.kernelMs[k] = ms; else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, r->ev[2 * k], r->ev[2 * k + 1]) == cudaSuccess) r->stats.kernelMs[k] = ms; else cudaGetLastError();
       }
+      float ms = 0.f;   // multi-GPU: time between the end of the trace stages and the start of the post stages = exchange step 1
+      if (r->postStarted && cudaEventElapsedTime(&ms, r->ev[2 * EID_K_INDIRECT + 1], r->evPost) == cudaSuccess) r->stats.exchangeMs = ms; else cudaGetLastError();
+    }
     r->statsPending = false;
   }
   *out = r->stats;

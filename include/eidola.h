@@ -215,6 +215,8 @@ typedef struct eid_frame_stats {
   uint64_t triangleTests;      /*   at profiling level 2 (instrumented kernel variants)                        */
   uint64_t totalClosestHitRays;/* rays issued since the renderer was created (never reset) */
   uint64_t totalAnyHitRays;
+  float    exchangeMs;             /* profiling: gap between the end of run_trace and the start of run_post* (multi-GPU exchange 1) */
+  uint64_t maxNodeVisitsPerThread; /* profiling level 2: most inner-node visits any single thread (pixel) needed so far */
 } eid_frame_stats;
 
 /* Renderer::setup + create(size, layouts, scene) (renderer.cpp:50-57, 97-148).
@@ -250,6 +252,10 @@ EID_API int  eid_renderer_write(eid_renderer* r, int which, const void* host_src
  * pinned or pageable host buffers (width*height*16 bytes each, either may be NULL) and syncs. */
 EID_API int  eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
                                       float* direct_host, float* indirect_host);
+/* 1 (default): run the direct denoiser (K3) on a second CUDA stream concurrently with indirect_stage (K2) + the indirect
+ * denoiser (K4) — the reference's true dependencies are K1->{K2,K3}, K2->K4, {K3,K4}->K5.  0: strict K1..K5 order on one stream.
+ * Results are identical either way; per-stage times (kernelMs) overlap when enabled. */
+EID_API int  eid_renderer_set_overlap(eid_renderer* r, int enabled);
 /* 0: off (default; ray counters are always kept), 1: per-stage CUDA-event timing,
  * 2: additionally run the instrumented trace kernels that count BVH node visits / triangle tests */
 EID_API int  eid_renderer_set_profiling(eid_renderer* r, int enabled);
