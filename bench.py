@@ -33,11 +33,22 @@ WORKLOAD = "C3: procedural closed room, 707x707-quad noise height-field floor (9
            "1920x1080, ReSTIR DI+GI temporal, M=4, maxDepth 3, MIS, denoise on (K1..K5), static camera"
 
 
+WORKLOADS = {   # BASELINE.json configs[2..4]; the default / headline is c3
+    "c3": dict(size=(1920, 1080), quads=707, light_quads=500, light_seed=566, text=WORKLOAD),
+    "c4": dict(size=(3840, 2160), quads=707, light_quads=500, light_seed=566,
+               text=WORKLOAD.replace("C3:", "C4:").replace("1920x1080", "3840x2160")),
+    "c5": dict(size=(1920, 1080), quads=2236, light_quads=5000, light_seed=567,
+               text="C5: same generator at 2236x2236 quads (9,999,402 floor tris) + 10,000 emissive tris, 1920x1080, full pipeline"),
+}
+_ACTIVE = "c3"
+
+
 def scene_arrays(quick=False):
     from eidola_b200 import scenes
     if quick:
         return scenes.heightfield_room(quads=96, n_light_quads=50)
-    return scenes.heightfield_room()          # 707 quads, 500 light quads = 1000 emissive triangles
+    c = WORKLOADS[_ACTIVE]
+    return scenes.heightfield_room(quads=c["quads"], n_light_quads=c["light_quads"], light_seed=c["light_seed"])
 
 
 def frame_state(info, frame, w=W, h=H):
@@ -141,15 +152,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sw, sh = (W // 4, H // 4) if not args.quick else (W // 8, H // 8)
+    fw, fh = WORKLOADS[_ACTIVE]["size"]
+    sw, sh = (fw // 4, fh // 4) if not args.quick else (W // 8, H // 8)
     arrays = scene_arrays(args.quick)
     r = oracle_run(arrays, sw, sh, args.steps, args.warmup)
-    sample = "%d frames of the same scene/state at %dx%d (1/16 of the 1080p pixels per step), all host threads" % (args.steps, sw, sh)
+    sample = "%d frames of the same scene/state at %dx%d (1/16 of the workload's pixels per step), all host threads" % (args.steps, sw, sh)
     line = {
         "impl": "reference", "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": r["mrays"], "unit": "Mray/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "CPU oracle (C++/OpenMP restatement of the reference shaders; the Vulkan app cannot run here)",
+        "config": {"workload": WORKLOADS[_ACTIVE]["text"], "reference_arm": "CPU oracle (C++/OpenMP restatement of the reference shaders; the Vulkan app cannot run here)",
                    "sample": sample},
         "cpu_baseline": {"value": r["mrays"], "unit": "Mray/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["mrays"], "unit": "Mray/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,7 +214,7 @@ def run_cuda(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
 
-    w, h = (W, H) if not args.quick else (W // 4, H // 4 // 16 * 16)
+    w, h = WORKLOADS[_ACTIVE]["size"] if not args.quick else (W // 4, H // 4 // 16 * 16)
     arrays = scene_arrays(args.quick)
     scene = eid.Scene(local)
     scene.load_arrays(arrays)
@@ -360,7 +372,7 @@ def run_cuda(args):
             "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": value, "unit": "Mray/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
+            "config": {"workload": WORKLOADS[_ACTIVE]["text"] if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
                        "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
                        "parallelism": ("%d interleaved row stripes per rank x%d ranks; exchange 1: all-gather of pre-denoise G-buffer/direct/indirect; %s" % (
                            args.stripe_groups, world, "denoise+compose per band, exchange 2: all-gather of the two final images" if args.post == "sharded"
@@ -414,7 +426,10 @@ def main():
     ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
                     help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
                          "one exchange step, every rank post-processes the full frame")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = headline (BASELINE.json metric); c4 = 4K; c5 = 10 M triangles")
     args = ap.parse_args()
+    global _ACTIVE
+    _ACTIVE = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:
