@@ -260,15 +260,23 @@ def run_cuda(args):
             else:
                 rr.render_host(scene.get_camera(), st, frame, e2e_bufs[0].data_ptr(), e2e_bufs[1].data_ptr())
         else:
-            rr.run_trace(st, frame)
-            for full, mine in exchange_tensors():
-                dist.all_gather_into_tensor(full, mine)
+            # exchange step 1, pipelined: the G-buffer and the direct image are complete after direct_stage, so their all-gathers
+            # (NCCL's own stream) run while indirect_stage computes; the indirect image follows
+            rr.run_direct(st, frame)
+            pending = [dist.all_gather_into_tensor(full, mine, async_op=True)
+                       for full, mine in gather_views((abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT))]
+            rr.run_indirect(st, frame)
+            pending += [dist.all_gather_into_tensor(full, mine, async_op=True) for full, mine in gather_views((abi.BUF_DENOISE_IND_A,))]
+            for wk in pending:
+                wk.wait()                               # stream-level wait (no host sync)
             if args.post == "replicated":
                 rr.run_post(st, frame)                  # mode A: every rank denoises + composes the full frame
             else:
                 rr.run_post_band(st, frame)             # mode B: band + per-level reach only, then gather the two final images
                 for full, mine in final_tensors():
                     dist.all_gather_into_tensor(full, mine)
+            if e2e_bufs is not None and rank != 0:
+                e2e_bufs = None                         # the composed frame is delivered to the host once, by rank 0
             if e2e_bufs is not None:
                 d, i = rr.outputs()
                 n = w * h * 16

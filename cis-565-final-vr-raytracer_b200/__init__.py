@@ -35,7 +35,7 @@ EXPORTS = [
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
     "eid_renderer_set_strict_math", "eid_renderer_set_overlap", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
-    "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band",
+    "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
 ]
 
@@ -87,6 +87,8 @@ def lib():
         "eid_renderer_set_band": (i32, [vp, u32, u32]),
         "eid_renderer_run_trace": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_run_post": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_run_direct": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_renderer_run_indirect": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_run_post_band": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_band_range": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
         "eid_renderer_set_stripes": (i32, [vp, u32, u32, u32]),
@@ -230,6 +232,12 @@ class Renderer:
 
     def run_trace(self, state, frames):
         _check(lib().eid_renderer_run_trace(self._h, C.byref(state), frames))
+
+    def run_direct(self, state, frames):
+        _check(lib().eid_renderer_run_direct(self._h, C.byref(state), frames))
+
+    def run_indirect(self, state, frames):
+        _check(lib().eid_renderer_run_indirect(self._h, C.byref(state), frames))
 
     def run_post(self, state, frames):
         _check(lib().eid_renderer_run_post(self._h, C.byref(state), frames))

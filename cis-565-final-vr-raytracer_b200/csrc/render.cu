@@ -897,6 +897,32 @@ int eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames) {
   EID_CATCH
 }
 
+// run_trace split in two so a multi-GPU host can start exchanging the G-buffer + direct image while indirect_stage runs
+int eid_renderer_run_direct(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_direct: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  beginFrame(r);
+  stageDirect(r, P, r->stream);
+  CUDA_CHECK(cudaGetLastError());
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run_indirect(eid_renderer* r, const RtxState* state, int frames) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_indirect: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  stageIndirect(r, P, r->stream);
+  CUDA_CHECK(cudaGetLastError());
+  return EID_OK;
+  EID_CATCH
+}
+
 int eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames) {
   EID_TRY
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_post: null argument");

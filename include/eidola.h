@@ -276,6 +276,10 @@ EID_API int  eid_renderer_exchange_groups(eid_renderer* r);
 /* device pointer, byte offset and byte size of this rank's chunk in exchange group `group` of buffer `which` */
 EID_API int  eid_renderer_exchange_range(eid_renderer* r, int which, uint32_t group, void** dev_base, uint64_t* offset, uint64_t* bytes);
 EID_API int  eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames);
+/* eid_renderer_run_trace == run_direct followed by run_indirect; split so the host can overlap the exchange of the G-buffer and
+ * the direct image (complete after run_direct) with indirect_stage */
+EID_API int  eid_renderer_run_direct(eid_renderer* r, const RtxState* state, int frames);
+EID_API int  eid_renderer_run_indirect(eid_renderer* r, const RtxState* state, int frames);
 EID_API int  eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames);
 /* Mode B (two exchange steps): denoise + compose only what this rank's band of the FINAL images needs (the A-Trous levels are
  * evaluated on the band plus the reach of the later levels); the caller then all-gathers EID_BUF_DIRECT and EID_BUF_INDIRECT. */
