@@ -32,6 +32,8 @@ EXPORTS = [
     "eid_scene_update_camera", "eid_scene_set_camera", "eid_scene_get_camera", "eid_scene_get_info",
     "eid_scene_table_bytes", "eid_scene_read_table",
     "eid_accel_build", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
+    "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
+    "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
     "eid_renderer_set_strict_math", "eid_renderer_set_overlap", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
@@ -69,6 +71,14 @@ def lib():
         "eid_accel_destroy": (None, [vp]),
         "eid_accel_get_info": (i32, [vp, C.POINTER(AccelInfo)]),
         "eid_accel_trace": (i32, [vp, vp, u32, i32, vp]),
+        "eid_env_create": (i32, [C.POINTER(vp), i32, vp, u32, u32]),
+        "eid_env_load_hdr": (i32, [C.POINTER(vp), i32, C.c_char_p]),
+        "eid_env_destroy": (None, [vp]),
+        "eid_env_integral": (C.c_float, [vp]),
+        "eid_env_average": (C.c_float, [vp]),
+        "eid_env_get_size": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "eid_env_read": (i32, [vp, i32, vp, sz]),
+        "eid_renderer_set_env": (i32, [vp, vp]),
         "eid_renderer_create": (i32, [C.POINTER(vp), vp, vp, u32, u32, vp]),
         "eid_renderer_resize": (i32, [vp, u32, u32]),
         "eid_renderer_destroy": (None, [vp]),
@@ -202,6 +212,58 @@ class AccelStructure:
             pass
 
 
+class HdrSampling:
+    """Mirror of HdrSampling (src/hdr_sampling.hpp:43-48): loadEnvironment / getIntegral / getAverage."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self.device = device
+
+    def load_environment(self, path):               # HdrSampling::loadEnvironment(hdrImage): Radiance .hdr
+        self.destroy()
+        _check(lib().eid_env_load_hdr(C.byref(self._h), self.device, os.fsencode(path)))
+
+    def set_pixels(self, rgba):                     # RGBA32F texels already in memory, shape (h, w, 4)
+        self.destroy()
+        a = np.ascontiguousarray(rgba, np.float32)
+        h, w = a.shape[0], a.shape[1]
+        _check(lib().eid_env_create(C.byref(self._h), self.device, a.ctypes.data, w, h))
+
+    def get_integral(self):
+        return float(lib().eid_env_integral(self._h))
+
+    def get_average(self):
+        return float(lib().eid_env_average(self._h))
+
+    def size(self):
+        w, h = C.c_uint32(), C.c_uint32()
+        _check(lib().eid_env_get_size(self._h, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def accel(self):
+        w, h = self.size()
+        out = np.zeros(w * h, abi.IMPT_DT)
+        _check(lib().eid_env_read(self._h, 0, out.ctypes.data, out.nbytes))
+        return out
+
+    def pixels(self):
+        w, h = self.size()
+        out = np.zeros((h, w, 4), np.float32)
+        _check(lib().eid_env_read(self._h, 1, out.ctypes.data, out.nbytes))
+        return out
+
+    def destroy(self):
+        if self._h:
+            lib().eid_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class Renderer:
     """Mirror of Renderer (src/renderer.hpp:52-61): create / run / update / destroy."""
 
@@ -217,6 +279,10 @@ class Renderer:
     def update(self, size):               # Renderer::update(size) — resize, history dropped
         _check(lib().eid_renderer_resize(self._h, size[0], size[1]))
         self.size = tuple(size)
+
+    def set_env(self, env):               # install an HdrSampling environment (None -> constant environment)
+        _check(lib().eid_renderer_set_env(self._h, env._h if env is not None else None))
+        self._env = env
 
     def set_env_constant(self, rgb):
         _check(lib().eid_renderer_set_env_constant(self._h, _f3(rgb)))

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(HERE, "libeidola.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["accel.cu", "render.cu", "gltf_import.cpp", "scene_host.cpp"]
+SOURCES = ["accel.cu", "render.cu", "gltf_import.cpp", "scene_host.cpp", "env_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall,-Wno-unused-function",

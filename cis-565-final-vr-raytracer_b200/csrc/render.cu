@@ -16,6 +16,7 @@
 #include "accel.h"
 #include "common.h"
 #include "shade.cuh"
+#include "env_host.h"
 
 namespace eid {
 
@@ -40,7 +41,7 @@ struct FrameParams {
   float4* dirA; float4* dirB; float4* indA; float4* indB;
   float4* geomPos; float4* geomNrm;       // denoiser geometry planes (full res): pos.xyz + hash bits / normal.xyz
   float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
-  float env[3];
+  EnvView env;                            // HDR lat-long map + alias table, or the constant environment
   int pitch, allocH;                      // allocation size of the 2-D images
   // rows owned by this rank: stripes k = 0..sCount-1 of sRows full-res rows starting at sFirst + k*sStride (all multiples of 16,
   // so no 8x8 quarter-res tile straddles two ranks).  Single GPU: one stripe covering the frame.
@@ -107,7 +108,7 @@ DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float
   return traverse<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
 }
 
-DEV f3 envRadiance(const FrameParams& P) { return mk3(P.env[0], P.env[1], P.env[2]) * P.st.hdrMultiplier; }   // pathtrace.glsl:40-47, constant env
+DEV f3 envRadiance(const FrameParams& P, f3 dir) { return envTextureDir(P.env, dir) * P.st.hdrMultiplier; }   // EnvRadiance (pathtrace.glsl:40-47), HDR branch
 
 // encodeGeometryInfo (direct_stage.comp:37-45)
 DEV uint4 encodeGeometryInfo(const State& s, float depth) {
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     if (!closestHit<STATS>(P, ro, rd, prd, rc)) {                 // :154-158
       P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
       P.motion[pix] = make_short2(0, 0);
-      radiance = envRadiance(P);
+      radiance = envRadiance(P, rd);
     } else {
       rc.primary++;
       State st = getState(P.sc, prd, rd);
@@ -181,14 +182,14 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
         const f3 shadowOrigin = offsetRay(st.position, st.ffnormal);
         if (P.st.ReSTIRState == eNone) {                   // DirectLight (pathtrace.glsl:204-220)
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-          float pdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+          float pdf = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
           if (!isPdfInvalid(pdf) && !occlusion<STATS>(P, shadowOrigin, ls.wi, st.position, ls.dist, rc))
             direct = ((ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * gmax(dot3(st.ffnormal, ls.wi), 0.0f)) / pdf;
         } else {
           DResv resv; resv.Li = mk3(0.f); resv.wi = mk3(0.f); resv.dist = 0.f; resv.num = 0; resv.weight = 0.f;
           for (int i = 0; i < P.st.RISSampleNum; i++) {    // :188-199
             LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-            float p = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+            float p = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
             f3 pHat = (ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * fabsf(dot3(st.ffnormal, ls.wi));
             float weight = lum3(pHat / p);
             if (isPdfInvalid(p) || weight != weight) weight = 0.0f;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         const f3 wo = -rayD;
         if (d > 1 && P.st.MIS > 0) {                        // SampleDirectLight (pathtrace.glsl:185-202)
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-          float lightPdf = sampleDirectLightNoVisibility(P.sc, P.st, st.position, seed, ls);
+          float lightPdf = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
           if (!isPdfInvalid(lightPdf)) {
             if (occlusion<STATS>(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, rc)) lightPdf = EID_INVALID_PDF;
           } else lightPdf = EID_INVALID_PDF;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         closestHit<STATS>(P, rayO, rayD, prd, rc);
         if (prd.hitT >= __fsub_rn(EID_INFINITY, 1e-4f)) {   // miss (:183-198)
           if (d > 1) {
-            const f3 env = mk3(P.env[0], P.env[1], P.env[2]);                 // EnvEval (pathtrace.glsl:60-72), constant env
+            const f3 env = envTextureDir(P.env, sampleWi);                    // EnvEval (pathtrace.glsl:60-72), HDR branch
             const float lightPdf = __fmul_rn(__fmul_rn(lum3(env), P.st.envMapLuminIntegInv), P.st.environmentProb);
             gs.L = gs.L + (env * throughput) * misWeight(P, samplePdf, lightPdf);
           } else {
@@ -560,6 +561,7 @@ struct eid_renderer {
   unsigned long long* counters = nullptr;
   unsigned long long* countersHost = nullptr;   // pinned
   float env[3] = {0.f, 0.f, 0.f};
+  eid_env* envMap = nullptr;
   int lastSet = 0;
   RtxState lastState{};
   bool hasRun = false;
@@ -615,8 +617,8 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
     raise(EID_ERR_INVALID, "RtxState.size %dx%d outside the renderer allocation %ux%u", st.size.x, st.size.y, r->width, r->height);
   if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal)
     raise(EID_ERR_UNSUPPORTED, "spatial reuse (direct_stage.comp:224-255) is racy in the reference and outside the parity contract");
-  if (st.environmentProb > 0.0f)
-    raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs the HDR importance-sampling map (env_sampling.glsl), not implemented yet");
+  if (st.environmentProb > 0.0f && !r->envMap)
+    raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs an HDR environment map (eid_env_create + eid_renderer_set_env); sun & sky is not implemented");
   if (st.RISSampleNum < 0 || st.maxDepth < 0) raise(EID_ERR_INVALID, "negative RISSampleNum / maxDepth");
   const int set = (frames + 1) % 2;   // renderer.cpp:157; set i: last* = [i], this* = [!i] (renderer.cpp:341-375)
   P.st = st;
@@ -630,7 +632,9 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
   P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
   P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
-  for (int k = 0; k < 3; ++k) P.env[k] = r->env[k];
+  for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
+  P.env.tex = r->envMap ? r->envMap->tex : nullptr; P.env.accel = r->envMap ? r->envMap->accel : nullptr;
+  P.env.width = r->envMap ? (int)r->envMap->host.width : 0; P.env.height = r->envMap ? (int)r->envMap->host.height : 0;
   P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.sFirst = (int)r->sFirst; P.sStride = (int)r->sStride; P.sRows = (int)r->sRows;
   P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
@@ -864,6 +868,84 @@ void eid_renderer_destroy(eid_renderer* r) {
   if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
   if (r->ownStream && r->stream) cudaStreamDestroy(r->stream);
   delete r;
+}
+
+// ---- HdrSampling (hdr_sampling.hpp:43-48) ---------------------------------------------------------------------------------
+static int envUpload(eid_env* e) {
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->host.width * e->host.height;
+  CUDA_CHECK(cudaMalloc(&e->tex, n * 16));
+  CUDA_CHECK(cudaMalloc(&e->accel, n * sizeof(ImptSampData)));
+  CUDA_CHECK(cudaMemcpy(e->tex, e->host.pixels.data(), n * 16, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(e->accel, e->host.accel.data(), n * sizeof(ImptSampData), cudaMemcpyHostToDevice));
+  return EID_OK;
+}
+
+int eid_env_create(eid_env** out, int device, const float* rgba, uint32_t width, uint32_t height) {
+  EID_TRY
+  if (!out) raise(EID_ERR_INVALID, "eid_env_create: out is null");
+  eid_env* e = new eid_env();
+  try {
+    e->device = device;
+    e->host.build(rgba, width, height);
+    if (device != EID_DEVICE_NONE) envUpload(e);
+  } catch (...) { eid_env_destroy(e); throw; }
+  *out = e;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_env_load_hdr(eid_env** out, int device, const char* path) {
+  EID_TRY
+  if (!out || !path) raise(EID_ERR_INVALID, "eid_env_load_hdr: null argument");
+  eid_env* e = new eid_env();
+  try {
+    e->device = device;
+    e->host.loadRadianceHdr(path);
+    if (device != EID_DEVICE_NONE) envUpload(e);
+  } catch (...) { eid_env_destroy(e); throw; }
+  *out = e;
+  return EID_OK;
+  EID_CATCH
+}
+
+void eid_env_destroy(eid_env* e) {
+  if (!e) return;
+  if (e->tex || e->accel) { cudaSetDevice(e->device); cudaFree(e->tex); cudaFree(e->accel); }
+  delete e;
+}
+
+float eid_env_integral(eid_env* e) { return e ? e->host.integral : 0.f; }
+float eid_env_average(eid_env* e) { return e ? e->host.average : 0.f; }
+
+int eid_env_get_size(eid_env* e, uint32_t* width, uint32_t* height) {
+  EID_TRY
+  if (!e || !width || !height) raise(EID_ERR_INVALID, "eid_env_get_size: null argument");
+  *width = e->host.width; *height = e->host.height;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_env_read(eid_env* e, int what, void* dst, size_t bytes) {
+  EID_TRY
+  if (!e || !dst) raise(EID_ERR_INVALID, "eid_env_read: null argument");
+  const size_t n = (size_t)e->host.width * e->host.height;
+  const void* src = what == 0 ? (const void*)e->host.accel.data() : (const void*)e->host.pixels.data();
+  const size_t total = what == 0 ? n * sizeof(ImptSampData) : n * 16;
+  if (what != 0 && what != 1) raise(EID_ERR_INVALID, "eid_env_read: what must be 0 (alias table) or 1 (pixels)");
+  if (bytes > total) raise(EID_ERR_INVALID, "read of %zu bytes from %zu", bytes, total);
+  memcpy(dst, src, bytes);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_env(eid_renderer* r, eid_env* e) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_env: null renderer");
+  if (e && (e->device != r->device || !e->tex)) raise(EID_ERR_INVALID, "environment map lives on another device (or is host-only)");
+  r->envMap = e;
+  return EID_OK;
+  EID_CATCH
 }
 
 int eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]) {

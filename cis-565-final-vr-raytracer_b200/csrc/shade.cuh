@@ -237,6 +237,65 @@ DEV void getMaterials(const DeviceSceneView& sc, State& st) {
   st.eta = dot3(st.normal, st.ffnormal) > 0.0f ? __fdiv_rn(1.0f, st.mat.ior) : st.mat.ior;
 }
 
+// ---- environment (env_sampling.glsl, common.glsl:69-76, hdr_sampling.cpp sampler state) ------------------------
+struct EnvView {
+  const float4* tex;                 // RGBA32F lat-long map, null = constant environment `constant`
+  const ImptSampData* accel;
+  int width, height;
+  float constant[3];
+};
+DEV void sphericalUv(f3 v, float& u, float& w) {                     // GetSphericalUv (common.glsl:69-76)
+  const float gamma = eid_asinf(-v.y);
+  const float theta = eid_atan2f(v.z, v.x);
+  const float M_1_OVER_PI = 0.318309886183790671538f;
+  u = __fadd_rn(__fmul_rn(__fmul_rn(theta, M_1_OVER_PI), 0.5f), 0.5f);
+  w = __fadd_rn(__fmul_rn(gamma, M_1_OVER_PI), 0.5f);
+}
+// texture(environmentTexture, uv).rgb: LINEAR, REPEAT in u, CLAMP_TO_EDGE in v, LOD 0; full-float bilinear weights (contract)
+DEV f3 envTexel(const EnvView& E, int x, int y) { const float4 t = __ldg(E.tex + (size_t)y * E.width + x); return mk3(t.x, t.y, t.z); }
+DEV f3 envTextureUv(const EnvView& E, float u, float v) {
+  const float x = __fsub_rn(__fmul_rn(u, (float)E.width), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)E.height), 0.5f);
+  const float x0f = eid_floorf(x), y0f = eid_floorf(y);
+  const float fx = __fsub_rn(x, x0f), fy = __fsub_rn(y, y0f);
+  const int x0 = f2i_sat(x0f), y0 = f2i_sat(y0f);
+  int xa = x0 % E.width; if (xa < 0) xa += E.width;
+  int xb = (x0 + 1) % E.width; if (xb < 0) xb += E.width;
+  const int ya = y0 < 0 ? 0 : (y0 >= E.height ? E.height - 1 : y0);
+  const int y1 = y0 + 1;
+  const int yb = y1 < 0 ? 0 : (y1 >= E.height ? E.height - 1 : y1);
+  return mix3(mix3(envTexel(E, xa, ya), envTexel(E, xb, ya), fx), mix3(envTexel(E, xa, yb), envTexel(E, xb, yb), fx), fy);
+}
+DEV f3 envTextureDir(const EnvView& E, f3 dir) {
+  if (!E.tex) return mk3(E.constant[0], E.constant[1], E.constant[2]);
+  float u, v;
+  sphericalUv(dir, u, v);
+  return envTextureUv(E, u, v);
+}
+// EnvSample (env_sampling.glsl:100-135) -> Environment_sample (:38-94): three draws; returns the texel pdf, fills direction + radiance
+DEV float envSample(const EnvView& E, float hdrMultiplier, uint32_t& seed, f3& radiance, f3& toLight) {
+  float xx = rnd(seed), xy = rnd(seed), xz = rnd(seed);
+  const uint32_t width = (uint32_t)E.width, height = (uint32_t)E.height, size = width * height;
+  const uint32_t idx = (uint32_t)min((int)f2u_sat(__fmul_rn(xx, (float)size)), (int)size - 1);
+  const ImptSampData sd = E.accel[idx];
+  uint32_t envIdx; float pdf;
+  if (xy < sd.q) { envIdx = idx; xy = __fdiv_rn(xy, sd.q); pdf = sd.pdf; }
+  else { envIdx = (uint32_t)sd.alias; xy = __fdiv_rn(__fsub_rn(xy, sd.q), __fsub_rn(1.0f, sd.q)); pdf = sd.aliasPdf; }
+  const uint32_t px = envIdx % width, py = envIdx / width;
+  const float u = __fdiv_rn(__fadd_rn((float)px, xy), (float)width);
+  const float phi = __fsub_rn(__fmul_rn(u, __fmul_rn(2.0f, EID_PI)), EID_PI);
+  float sinPhi, cosPhi;
+  eid_sincosf(phi, &sinPhi, &cosPhi);
+  const float stepTheta = __fdiv_rn(EID_PI, (float)height);
+  const float theta0 = __fmul_rn((float)py, stepTheta);
+  const float cosTheta = __fadd_rn(__fmul_rn(eid_cosf(theta0), __fsub_rn(1.0f, xz)), __fmul_rn(eid_cosf(__fadd_rn(theta0, stepTheta)), xz));
+  const float theta = eid_acosf(cosTheta);
+  const float sinTheta = eid_sinf(theta);
+  const float v = __fmul_rn(theta, 0.318309886183790671538f);
+  toLight = mk3(__fmul_rn(cosPhi, sinTheta), cosTheta, __fmul_rn(sinPhi, sinTheta));
+  radiance = envTextureUv(E, u, v) * hdrMultiplier;
+  return pdf;
+}
+
 // ---- pathtrace.glsl ------------------------------------------------------------------------------
 DEV bool isPdfInvalid(float p) { return p <= 1e-8f || p != p; }   // :14-16
 
@@ -285,10 +344,16 @@ DEV float samplePuncLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, Light
   return L.impSamp.pdf;
 }
 // SampleDirectLightNoVisibility :161-183
-DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const RtxState& rs, f3 pos, uint32_t& seed, LightSampleD& ls) {
+DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const EnvView& env, const RtxState& rs, f3 pos, uint32_t& seed, LightSampleD& ls) {
   const float r = rnd(seed);
   const float envProb = rs.environmentProb;
-  if (r < envProb) return EID_INVALID_PDF;   // EnvSample (env_sampling.glsl:100-135): HDR alias map is a later scope row
+  if (r < envProb) {                         // sample the environment (:163-172)
+    if (!env.tex) return EID_INVALID_PDF;    // (unreachable: the host refuses environmentProb > 0 without an HDR map)
+    const float pdf = envSample(env, rs.hdrMultiplier, seed, ls.Li, ls.wi);
+    if (isPdfInvalid(pdf)) return EID_INVALID_PDF;
+    ls.dist = EID_INFINITY;
+    return __fmul_rn(pdf, envProb);
+  }
   const float lightProb = __fsub_rn(1.0f, envProb);
   const float tsp = sc.lightBufInfo.trigSampProb;
   if (r < __fadd_rn(envProb, __fmul_rn(lightProb, tsp)))

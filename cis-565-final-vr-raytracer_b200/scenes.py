@@ -350,3 +350,51 @@ def write_gltf(scene, path, embed=False):
     with open(path, "w") as f:
         json.dump(doc, f)
     return path
+
+
+def synthetic_sky(width=64, height=32, seed=9, sun=True):
+    """Synthetic RGBA32F lat-long environment: blue-ish gradient sky, dark ground, a small very bright 'sun' block."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    v = (np.arange(height, dtype=np.float64) + 0.5) / height          # 0 = +Y pole
+    sky = np.clip(1.0 - v * 1.6, 0.02, 1.0)[:, None]
+    img = np.zeros((height, width, 4), np.float32)
+    img[..., 0] = 0.35 * sky + 0.05
+    img[..., 1] = 0.55 * sky + 0.06
+    img[..., 2] = 0.95 * sky + 0.08
+    img[..., :3] *= (0.8 + 0.4 * rng.random((height, width, 1))).astype(np.float32)
+    if sun:
+        y0, x0 = height // 5, (2 * width) // 3
+        img[y0:y0 + 2, x0:x0 + 2, :3] = (220.0, 200.0, 160.0)
+    img[..., 3] = 1.0
+    return img
+
+
+def write_radiance_hdr(path, rgba, rle=True):
+    """Write RGBA32F (h, w, 4) as a Radiance .hdr (RGBE); returns the texels a decoder will reproduce."""
+    rgb = np.asarray(rgba, np.float32)[..., :3]
+    h, w, _ = rgb.shape
+    m = rgb.max(axis=-1)
+    e = np.where(m > 1e-32, np.ceil(np.log2(np.maximum(m, 1e-38))).astype(np.int32), -128)
+    e = np.where(np.ldexp(1.0, e) <= m, e + 1, e)                       # ensure m / 2^e < 1
+    scale = np.where(m > 1e-32, np.ldexp(256.0, -e), 0.0)
+    mant = np.clip((rgb * scale[..., None]).astype(np.int32), 0, 255).astype(np.uint8)
+    rgbe = np.concatenate([mant, np.where(m > 1e-32, e + 128, 0).astype(np.uint8)[..., None]], axis=-1)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (h, w))
+        for y in range(h):
+            if rle and 8 <= w < 32768:
+                f.write(bytes([2, 2, (w >> 8) & 0xff, w & 0xff]))
+                for c in range(4):
+                    row = rgbe[y, :, c]
+                    x = 0
+                    while x < w:                                        # literal runs only (valid, simple)
+                        n = min(128, w - x)
+                        f.write(bytes([n]) + row[x:x + n].tobytes())
+                        x += n
+            else:
+                f.write(rgbe[y].tobytes())
+    dec = np.zeros((h, w, 4), np.float32)
+    s = np.where(rgbe[..., 3] > 0, np.ldexp(1.0, rgbe[..., 3].astype(np.int32) - 136), 0.0).astype(np.float32)
+    dec[..., :3] = rgbe[..., :3].astype(np.float32) * s[..., None]
+    dec[..., 3] = 1.0
+    return dec

@@ -42,6 +42,7 @@ typedef enum eid_status {
 typedef struct eid_scene eid_scene;
 typedef struct eid_accel eid_accel;
 typedef struct eid_renderer eid_renderer;
+typedef struct eid_env eid_env;
 
 EID_API const char* eid_last_error(void);
 EID_API int eid_version(void);
@@ -227,6 +228,22 @@ EID_API int  eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a,
 /* Renderer::update(size) (renderer.cpp:209-225): re-allocates, drops history */
 EID_API int  eid_renderer_resize(eid_renderer* r, uint32_t width, uint32_t height);
 EID_API void eid_renderer_destroy(eid_renderer* r);
+/* ---- HdrSampling (hdr_sampling.hpp:43-48; hdr_sampling.cpp:55-242) -------------------------------------------------------
+ * loadEnvironment(file) = eid_env_load_hdr (Radiance .hdr / RGBE; replaces stbi_loadf) or eid_env_create from RGBA32F texels
+ * already in memory (row 0 = +Y pole).  Builds the per-texel alias table exactly like createEnvironmentAccel/buildAliasmap.
+ * getIntegral()/getAverage() feed RtxState.fireflyClampThreshold / envMapLuminIntegInv (sample_example.cpp:104-105).
+ * device = CUDA ordinal or EID_DEVICE_NONE (host tables only, for tests). */
+EID_API int   eid_env_create(eid_env** out, int device, const float* rgba, uint32_t width, uint32_t height);
+EID_API int   eid_env_load_hdr(eid_env** out, int device, const char* path);
+EID_API void  eid_env_destroy(eid_env* e);
+EID_API float eid_env_integral(eid_env* e);
+EID_API float eid_env_average(eid_env* e);
+EID_API int   eid_env_get_size(eid_env* e, uint32_t* width, uint32_t* height);
+/* what = 0: ImptSampData[w*h] alias table, 1: RGBA32F texels (host copies; parity taps) */
+EID_API int   eid_env_read(eid_env* e, int what, void* dst, size_t bytes);
+/* install / remove (NULL) the HDR environment: EnvRadiance, EnvEval and EnvSample (pathtrace.glsl:40-72, env_sampling.glsl) then
+ * use it; RtxState.environmentProb > 0 requires one */
+EID_API int   eid_renderer_set_env(eid_renderer* r, eid_env* e);
 /* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR
  * map is installed; default (0,0,0). */
 EID_API int  eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]);

@@ -86,8 +86,19 @@ struct Scene {
   bool anyHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const;
 };
 
+// HdrSampling (src/hdr_sampling.{hpp,cpp}): RGBA32F lat-long environment + per-texel alias map
+struct Environment {
+  uint32_t width = 0, height = 0;
+  std::vector<float> pixels;              // rgba
+  std::vector<ImptSampData> accel;
+  float integral = 1.f, average = 1.f;
+  void create(const float* rgba, uint32_t w, uint32_t h);
+  vec3 texture(vec2 uv) const;            // sampler: LINEAR, REPEAT in u, CLAMP_TO_EDGE in v (hdr_sampling.cpp:67-75)
+};
+
 struct Renderer {
   const Scene* scene = nullptr;
+  const Environment* env = nullptr;      // null: constant environment `envConstant`
   uint32_t width = 0, height = 0;      // allocation size
   std::vector<uvec4> gbuffer[2];
   std::vector<int16_t> motion;         // 2 per pixel

@@ -138,6 +138,18 @@ ORC_API int orc_accel_trace(Scene* s, const float* rays, uint32_t n, int any_hit
 // ---- renderer ---------------------------------------------------------------------------------------
 ORC_API Renderer* orc_renderer_create(Scene* s, uint32_t w, uint32_t h) { Renderer* r = new Renderer(); r->create(s, w, h); return r; }
 ORC_API void orc_renderer_destroy(Renderer* r) { delete r; }
+ORC_API Environment* orc_env_create(const float* rgba, uint32_t w, uint32_t h) { Environment* e = new Environment(); e->create(rgba, w, h); return e; }
+ORC_API void orc_env_destroy(Environment* e) { delete e; }
+ORC_API float orc_env_integral(Environment* e) { return e->integral; }
+ORC_API float orc_env_average(Environment* e) { return e->average; }
+ORC_API int orc_env_read_accel(Environment* e, void* dst, size_t bytes) {
+  if (bytes > e->accel.size() * sizeof(ImptSampData)) return -1;
+  memcpy(dst, e->accel.data(), bytes); return 0;
+}
+ORC_API void orc_env_texture(Environment* e, const float* uv, int n, float* out) {
+  for (int i = 0; i < n; ++i) { vec3 c = e->texture(vec2(uv[2 * i], uv[2 * i + 1])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
+}
+ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; return 0; }
 ORC_API int orc_renderer_set_env_constant(Renderer* r, const float* rgb) { r->envConstant = vec3(rgb[0], rgb[1], rgb[2]); return 0; }
 static RtxState g_lastState{};
 ORC_API int orc_renderer_run(Renderer* r, const RtxState* st, int frames) {

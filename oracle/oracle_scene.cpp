@@ -404,6 +404,77 @@ bool Scene::anyHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const
   return false;
 }
 
+// ---- hdr_sampling.cpp:107-176 buildAliasmap --------------------------------------------------------------
+static float buildAliasmap(const std::vector<float>& data, std::vector<ImptSampData>& accel) {
+  auto size = static_cast<uint32_t>(data.size());
+  float sum = 0.f;
+  for (float d : data) sum += d;                      // std::accumulate(..., 0.f)
+  auto fSize = static_cast<float>(size);
+  float inverseAverage = fSize / sum;
+  for (uint32_t i = 0; i < size; ++i) { accel[i].q = data[i] * inverseAverage; accel[i].alias = (int)i; }
+  std::vector<uint32_t> partitionTable(size);
+  uint32_t s = 0u, large = size;
+  for (uint32_t i = 0; i < size; ++i) {
+    if (accel[i].q < 1.f) partitionTable[s++] = i;
+    else partitionTable[--large] = i;
+  }
+  for (s = 0; s < large && large < size; ++s) {
+    const uint32_t smallEnergyIndex = partitionTable[s];
+    const uint32_t highEnergyIndex = partitionTable[large];
+    accel[smallEnergyIndex].alias = (int)highEnergyIndex;
+    const float differenceWithAverage = 1.f - accel[smallEnergyIndex].q;
+    accel[highEnergyIndex].q -= differenceWithAverage;
+    if (accel[highEnergyIndex].q < 1.0f) large++;
+  }
+  return sum;
+}
+
+// ---- hdr_sampling.cpp:181-242 createEnvironmentAccel ----------------------------------------------------
+void Environment::create(const float* rgba, uint32_t w, uint32_t h) {
+  width = w; height = h;
+  pixels.assign(rgba, rgba + 4 * (size_t)w * h);
+  const uint32_t rx = w, ry = h;
+  accel.assign((size_t)rx * ry, ImptSampData{});
+  std::vector<float> importanceData((size_t)rx * ry);
+  float cosTheta0 = 1.0f;
+  const float stepPhi = float(2.0 * M_PI) / float(rx);
+  const float stepTheta = float(M_PI) / float(ry);
+  double total = 0;
+  for (uint32_t y = 0; y < ry; ++y) {
+    const float theta1 = float(y + 1) * stepTheta;
+    const float cosTheta1 = std::cos(theta1);
+    const float area = (cosTheta0 - cosTheta1) * stepPhi;
+    cosTheta0 = cosTheta1;
+    for (uint32_t x = 0; x < rx; ++x) {
+      const uint32_t idx = y * rx + x, idx4 = idx * 4;
+      float cieLuminance = luminanceHost(&pixels[idx4]);
+      importanceData[idx] = area * std::max(pixels[idx4], std::max(pixels[idx4 + 1], pixels[idx4 + 2]));
+      total += cieLuminance;
+    }
+  }
+  average = static_cast<float>(total) / static_cast<float>(rx * ry);
+  integral = buildAliasmap(importanceData, accel);
+  const float invEnvIntegral = 1.0f / integral;
+  for (uint32_t i = 0; i < rx * ry; ++i) {
+    const uint32_t idx4 = i * 4;
+    accel[i].pdf = std::max(pixels[idx4], std::max(pixels[idx4 + 1], pixels[idx4 + 2])) * invEnvIntegral;
+  }
+  for (uint32_t i = 0; i < rx * ry; ++i) accel[i].aliasPdf = accel[accel[i].alias].pdf;
+}
+
+// texture(environmentTexture, uv): bilinear, REPEAT in u / CLAMP_TO_EDGE in v, full-float weights (contract)
+vec3 Environment::texture(vec2 uv) const {
+  const float x = uv.x * float(width) - 0.5f, y = uv.y * float(height) - 0.5f;
+  const float x0f = eid_floorf(x), y0f = eid_floorf(y);
+  const float fx = x - x0f, fy = y - y0f;
+  int x0 = f2i(x0f), y0 = f2i(y0f);
+  auto wrap = [&](int v) { int m = v % (int)width; return m < 0 ? m + (int)width : m; };
+  auto clampv = [&](int v) { return v < 0 ? 0 : (v >= (int)height ? (int)height - 1 : v); };
+  const int xa = wrap(x0), xb = wrap(x0 + 1), ya = clampv(y0), yb = clampv(y0 + 1);
+  auto tex = [&](int xx, int yy) { const float* p = &pixels[4 * ((size_t)yy * width + xx)]; return vec3(p[0], p[1], p[2]); };
+  return mix(mix(tex(xa, ya), tex(xb, ya), fx), mix(tex(xa, yb), tex(xb, yb), fx), fy);
+}
+
 // ---- binned-SAH BVH2 (oracle-only acceleration; results do not depend on it) ------------------
 void Bvh::build(const std::vector<OTri>& tris, float pad) {
   const int N = (int)tris.size();

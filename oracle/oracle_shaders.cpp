@@ -349,12 +349,61 @@ struct Ctx {
     pdf = metallicWorkflowSample(s, N, Vv, vec3(r0, r1, r2), bsdf, L);
     return bsdf;
   }
-  // constant environment in place of the HDR lookup / sun&sky (:40-72)
-  vec3 EnvRadiance(vec3) { return rr.envConstant * rtxState.hdrMultiplier; }
-  vec3 EnvEval(vec3, float& pdf) {
-    vec3 radiance = rr.envConstant;
+  // common.glsl:69-76
+  static vec2 GetSphericalUv(vec3 v) {
+    float gamma = eid_asinf(-v.y);
+    float theta = eid_atan2f(v.z, v.x);
+    const float M_1_OVER_PI = 0.318309886183790671538f;
+    return vec2(theta * M_1_OVER_PI * 0.5f, gamma * M_1_OVER_PI) + 0.5f;
+  }
+  // texture(environmentTexture, uv).rgb — or the constant environment when no HDR map is installed (sun & sky: later row)
+  vec3 envTexture(vec3 dir) { return rr.env ? rr.env->texture(GetSphericalUv(dir)) : rr.envConstant; }
+  vec3 EnvRadiance(vec3 dir) { return envTexture(dir) * rtxState.hdrMultiplier; }                  // pathtrace.glsl:40-47
+  vec3 EnvEval(vec3 dir, float& pdf) {                                                               // pathtrace.glsl:60-72
+    vec3 radiance = envTexture(dir);
     pdf = luminance(radiance) * rtxState.envMapLuminIntegInv * rtxState.environmentProb;
     return radiance;
+  }
+  // env_sampling.glsl:38-94 Environment_sample
+  vec3 Environment_sample(vec3 randVal, vec3& to_light, float& pdf) {
+    const Environment& E = *rr.env;
+    vec3 xi = randVal;
+    const uint width = E.width, height = E.height;
+    const uint size = width * height;
+    const uint idx = (uint)imin((int)f2u(xi.x * float(size)), (int)size - 1);
+    const ImptSampData sample_data = E.accel[idx];
+    uint env_idx;
+    if (xi.y < sample_data.q) {
+      env_idx = idx;
+      xi.y /= sample_data.q;
+      pdf = sample_data.pdf;
+    } else {
+      env_idx = (uint)sample_data.alias;
+      xi.y = (xi.y - sample_data.q) / (1.0f - sample_data.q);
+      pdf = sample_data.aliasPdf;
+    }
+    const uint px = env_idx % width;
+    uint py = env_idx / width;
+    const float u = (float(px) + xi.y) / float(width);
+    const float phi = u * (2.0f * M_PI_F) - M_PI_F;
+    float sin_phi, cos_phi;
+    eid_sincosf(phi, &sin_phi, &cos_phi);
+    const float step_theta = M_PI_F / float(height);
+    const float theta0 = float(py) * step_theta;
+    const float cos_theta = eid_cosf(theta0) * (1.0f - xi.z) + eid_cosf(theta0 + step_theta) * xi.z;
+    const float theta = eid_acosf(cos_theta);
+    const float sin_theta = eid_sinf(theta);
+    const float v = theta * 0.318309886183790671538f;
+    to_light = vec3(cos_phi * sin_theta, cos_theta, sin_phi * sin_theta);
+    return E.texture(vec2(u, v));
+  }
+  // env_sampling.glsl:100-135 EnvSample (HDR branch; sun & sky is a later scope row)
+  vec4 EnvSample(vec3& radiance) {
+    vec3 lightDir; float pdf;
+    float r0 = rand(); float r1 = rand(); float r2 = rand();
+    radiance = Environment_sample(vec3(r0, r1, r2), lightDir, pdf);
+    radiance *= rtxState.hdrMultiplier;
+    return vec4(lightDir, pdf);
   }
   vec3 LightEval(const State& state, float dist, vec3 dir, float& pdf) {                      // :74-88
     float lightProb = (1.0f - rtxState.environmentProb);
@@ -407,8 +456,14 @@ struct Ctx {
   float SampleDirectLightNoVisibility(vec3 pos, LightSample& lightSample) {                   // :161-183
     float r = rand();
     if (r < rtxState.environmentProb) {
-      // EnvSample (env_sampling.glsl:100-135) needs the HDR alias map: later scope row.
-      return InvalidPdf;
+      if (!rr.env) return InvalidPdf;   // no HDR map installed: the C-ABI refuses environmentProb > 0 in that case
+      vec3 Li;
+      vec4 dirAndPdf = EnvSample(Li);
+      lightSample.Li = E(Li);
+      if (IsPdfInvalid(dirAndPdf.w)) return InvalidPdf;
+      lightSample.wi = E(dirAndPdf.xyz());
+      lightSample.dist = INFINITY_;
+      return dirAndPdf.w * rtxState.environmentProb;
     } else {
       if (r < rtxState.environmentProb + (1.0f - rtxState.environmentProb) * sc.lightBufInfo.trigSampProb)
         return (1.0f - rtxState.environmentProb) * SampleTriangleLight(pos, lightSample) * sc.lightBufInfo.trigSampProb;

@@ -64,7 +64,14 @@ def compare_snapshots(got, want, tag, tol=1e-3):
     return report
 
 
-def make_pair(arrays, size, use_bvh=True, strict=True):
+def env_state_overrides(integral, prob=0.25):
+    """RtxState fields SampleExample::loadEnvironmentHdr derives from the HDR map (sample_example.cpp:104-105) + the default
+    environmentProb (sample_example.hpp:161)."""
+    return dict(environmentProb=prob, fireflyClampThreshold=float(np.float32(integral) * np.float32(4.0)),
+                envMapLuminIntegInv=float(np.float32(1.0) / np.float32(integral)))
+
+
+def make_pair(arrays, size, use_bvh=True, strict=True, env_img=None):
     """(oracle scene, oracle renderer, product scene, product accel, product renderer) for one scene."""
     import oracle_lib as ol
     w, h = size
@@ -80,4 +87,11 @@ def make_pair(arrays, size, use_bvh=True, strict=True):
     prr.create(size, psc, acc)
     prr.set_env_constant(ENV)
     prr.set_strict_math(strict)   # strict: deterministic exp in the denoiser -> every buffer bit-identical to the oracle
+    if env_img is not None:
+        oenv = ol.OracleEnv(env_img)
+        penv = eid.HdrSampling(0)
+        penv.set_pixels(env_img)
+        assert oenv.accel().tobytes() == penv.accel().tobytes() and oenv.get_integral() == penv.get_integral()
+        orr.set_env(oenv)
+        prr.set_env(penv)
     return osc, orr, psc, acc, prr

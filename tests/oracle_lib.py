@@ -48,6 +48,9 @@ def lib():
             "orc_scene_get_info": (i32, [vp, C.POINTER(abi.SceneInfo)]),
             "orc_scene_table_bytes": (C.c_int64, [vp, i32, u32]), "orc_scene_read_table": (i32, [vp, i32, u32, vp, sz]),
             "orc_accel_trace": (i32, [vp, vp, u32, i32, vp]),
+            "orc_env_create": (vp, [vp, u32, u32]), "orc_env_destroy": (None, [vp]), "orc_env_integral": (C.c_float, [vp]),
+            "orc_env_average": (C.c_float, [vp]), "orc_env_read_accel": (i32, [vp, vp, sz]), "orc_env_texture": (None, [vp, vp, i32, vp]),
+            "orc_renderer_set_env": (i32, [vp, vp]),
             "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
             "orc_renderer_set_env_constant": (i32, [vp, fp]),
             "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
@@ -135,6 +138,36 @@ class OracleScene:
             pass
 
 
+class OracleEnv:
+    def __init__(self, rgba):
+        a = np.ascontiguousarray(rgba, np.float32)
+        self.h, self.w = a.shape[0], a.shape[1]
+        self._h = C.c_void_p(lib().orc_env_create(a.ctypes.data, self.w, self.h))
+
+    def get_integral(self):
+        return float(lib().orc_env_integral(self._h))
+
+    def get_average(self):
+        return float(lib().orc_env_average(self._h))
+
+    def accel(self):
+        out = np.zeros(self.w * self.h, abi.IMPT_DT)
+        assert lib().orc_env_read_accel(self._h, out.ctypes.data, out.nbytes) == 0
+        return out
+
+    def texture(self, uv):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        lib().orc_env_texture(self._h, uv.ctypes.data, uv.shape[0], out.ctypes.data)
+        return out
+
+    def __del__(self):
+        try:
+            lib().orc_env_destroy(self._h)
+        except Exception:
+            pass
+
+
 class OracleRenderer:
     def __init__(self, scene, size):
         self._scene = scene
@@ -143,6 +176,10 @@ class OracleRenderer:
 
     def set_env_constant(self, rgb):
         lib().orc_renderer_set_env_constant(self._h, _f3(rgb))
+
+    def set_env(self, env):
+        lib().orc_renderer_set_env(self._h, env._h if env is not None else None)
+        self._env = env
 
     def run(self, state, frames):
         lib().orc_renderer_run(self._h, C.byref(state), frames)

@@ -228,3 +228,38 @@ def test_cpp_host_mirror_compiles_and_links(tmp_path):
         assert p.returncode == 1 and "no CPU fallback" in p.stderr
     else:
         assert p.returncode == 1 and "load failed" in p.stderr
+
+
+def test_hdr_environment_tables_and_loader(tmp_path):
+    """HdrSampling host side (hdr_sampling.cpp:107-242): alias map, integral, average == oracle bit for bit; .hdr (RGBE) reader."""
+    img = scenes.synthetic_sky()
+    o = ol.OracleEnv(img)
+    p = eid.HdrSampling(device=-1)
+    p.set_pixels(img)
+    assert o.accel().tobytes() == p.accel().tobytes()
+    assert (o.get_integral(), o.get_average()) == (p.get_integral(), p.get_average())
+    a = p.accel()
+    n = a.size
+    assert ((a["alias"] >= 0) & (a["alias"] < n)).all() and (a["q"] >= 0).all() and (a["q"] <= 1.0001).all()
+    # the alias table reproduces the target distribution: P(i) = (q_i + sum_{j: alias_j = i} (1 - q_j)) / n == pdf_i * solid angle ~ importance
+    mass = a["q"].astype(np.float64).copy()
+    np.add.at(mass, a["alias"], 1.0 - a["q"].astype(np.float64))
+    assert abs(mass.sum() / n - 1.0) < 1e-4
+    # constant map: integral = 4*pi*value (SURVEY.md 8(d))
+    c = eid.HdrSampling(device=-1)
+    c.set_pixels(np.full((8, 16, 4), 0.25, np.float32))
+    assert abs(c.get_integral() - np.pi) < 1e-4
+    for rle in (True, False):
+        path = str(tmp_path / ("sky_%d.hdr" % rle))
+        dec = scenes.write_radiance_hdr(path, img, rle=rle)
+        q = eid.HdrSampling(device=-1)
+        q.load_environment(path)
+        assert np.array_equal(q.pixels(), dec) and q.size() == (img.shape[1], img.shape[0])
+        assert np.abs(dec[..., :3] - img[..., :3]).max() <= 0.01 * img[..., :3].max()       # RGBE quantisation only
+    L = eid.lib()
+    h = C.c_void_p()
+    assert L.eid_env_load_hdr(C.byref(h), -1, b"/nonexistent.hdr") == -2
+    bad = tmp_path / "bad.hdr"
+    bad.write_bytes(b"P6 not an hdr")
+    assert L.eid_env_load_hdr(C.byref(h), -1, str(bad).encode()) == -3
+    assert L.eid_env_create(C.byref(h), -1, None, 4, 4) == -1

@@ -99,8 +99,10 @@ def test_oracle_bvh_equals_brute_force():
     assert a.trace(rays).tobytes() == b.trace(rays).tobytes()
 
 
-def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, **state_over):
-    osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict)
+def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=None, **state_over):
+    osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict, env_img=env_img)
+    if env_img is not None:
+        state_over = dict(common.env_state_overrides(prr._env.get_integral()), **state_over)
     for s in (osc, psc):
         s.update_camera(*size)     # contract: one updateCamera before frame 0 so last* matrices are valid
     info = psc.info()
@@ -136,6 +138,15 @@ def test_fast_math_denoiser_within_tolerance():
     worst = _run_frames(scenes.small_room(), (256, 144), 3, "room-fastmath", strict=False)
     assert max(worst.values()) <= 1e-3
     assert worst["direct_resv.weight"] == 0.0 and worst["indirect_resv.weight"] == 0.0 and worst["indirect_resv.L"] == 0.0
+
+
+@pytest.mark.parametrize("maker,size", [(scenes.cube_scene, (192, 192)), (scenes.cornell_scene, (224, 128))])
+def test_hdr_environment_default_state(maker, size):
+    """Scope row (f.2): HDR environment importance sampling with the reference's DEFAULT RtxState (environmentProb 0.25):
+    EnvSample / Environment_sample / EnvRadiance / EnvEval + alias map, open scenes where the sky is visible and lights the GI."""
+    worst = _run_frames(maker(), size, 4, "hdr-env " + maker.__name__, env_img=scenes.synthetic_sky())
+    assert max(worst.values()) == 0.0
+    _run_frames(maker(), size, 2, "hdr-env no sun, prob 0.6", env_img=scenes.synthetic_sky(sun=False), environmentProb=0.6, hdrMultiplier=2.0)
 
 
 def test_c1_cube_direct_only():
@@ -350,7 +361,7 @@ def test_error_behaviour_gpu():
     with pytest.raises(eid.EidolaError):
         r.run(common.frame_state(64, 64, info, 0, ReSTIRState=abi.eSpatial), 0)   # outside the contract
     with pytest.raises(eid.EidolaError):
-        r.run(common.frame_state(64, 64, info, 0, environmentProb=0.25), 0)  # needs the HDR map
+        r.run(common.frame_state(64, 64, info, 0, environmentProb=0.25), 0)  # needs an HDR map (sun & sky not implemented)
     with pytest.raises(eid.EidolaError):
         r.set_band(8, 64)                                                     # band edges must be multiples of 16
     r.run(common.frame_state(64, 64, info, 0), 0)                             # still usable after errors
