@@ -258,7 +258,10 @@ def run_cuda(args):
             if e2e_bufs is None:
                 rr.run(st, frame)
             else:
-                rr.render_host(scene.get_camera(), st, frame, e2e_bufs[0].data_ptr(), e2e_bufs[1].data_ptr())
+                # public host-buffer API, pipelined: camera + RtxState go up, both result images come down to pinned memory on a
+                # copy stream while the next frame renders (two buffer pairs alternate); timed() waits for the last copy
+                pair = e2e_bufs[frame & 1]
+                rr.render_host_async(scene.get_camera(), st, frame, pair[0].data_ptr(), pair[1].data_ptr())
         else:
             # exchange step 1, pipelined: the G-buffer and the direct image are complete after direct_stage, so their all-gathers
             # (NCCL's own stream) run while indirect_stage computes; the indirect image follows
@@ -280,8 +283,9 @@ def run_cuda(args):
             if e2e_bufs is not None:
                 d, i = rr.outputs()
                 n = w * h * 16
-                e2e_bufs[0].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(d, n), device=dev), non_blocking=True)
-                e2e_bufs[1].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(i, n), device=dev), non_blocking=True)
+                pair = e2e_bufs[frame & 1]
+                pair[0].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(d, n), device=dev), non_blocking=True)
+                pair[1].view(torch.uint8).reshape(-1)[:n].copy_(torch.as_tensor(DevBuf(i, n), device=dev), non_blocking=True)
                 stream.synchronize()
 
     def barrier():
@@ -300,6 +304,8 @@ def run_cuda(args):
             step(first_frame + k, e2e_bufs)
             if profiling:
                 kms += np.array(rr.stats().kernelMs[:])     # syncs; only used in the separate per-kernel pass
+        if e2e_bufs is not None and world == 1:
+            rr.wait_host()                           # the last frame's device->host copies are inside the timed region
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -328,7 +334,7 @@ def run_cuda(args):
     value = rays / (ms * 1e-3) / 1e6
 
     # end to end: host buffers, H2D of the per-frame inputs + D2H of both result images inside the timed region
-    pinned = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pinned = [[torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
     for _ in range(2):
         step(frame, pinned)
         frame += 1
@@ -391,7 +397,8 @@ def run_cuda(args):
             "fps": 1e3 / (ms / args.steps),
             "rays_per_frame": rays / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mray/s", "h2d_bytes_per_step": C.sizeof(abi.SceneCamera) + C.sizeof(abi.RtxState),
-                    "d2h_bytes_per_step": 2 * w * h * 16, "ms_per_step": ems / e2e_steps, "fps": 1e3 / (ems / e2e_steps), "steps": e2e_steps},
+                    "d2h_bytes_per_step": 2 * w * h * 16, "pipelined": "D2H of frame f overlaps the kernels of frame f+1 (copy stream, 2 pinned buffer pairs)" if world == 1 else "rank 0 downloads the gathered frame, not pipelined",
+                    "ms_per_step": ems / e2e_steps, "fps": 1e3 / (ems / e2e_steps), "steps": e2e_steps},
             "gpu_launches": int(sum(launches)) * args.steps, "launches_per_frame": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -36,7 +36,7 @@ EXPORTS = [
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
     "eid_renderer_set_strict_math", "eid_renderer_set_overlap", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
-    "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_set_profiling",
+    "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_render_host_async", "eid_renderer_wait_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
 ]
@@ -92,6 +92,8 @@ def lib():
         "eid_renderer_read": (i32, [vp, i32, vp, sz]),
         "eid_renderer_write": (i32, [vp, i32, vp, sz]),
         "eid_renderer_render_host": (i32, [vp, C.POINTER(SceneCamera), C.POINTER(RtxState), i32, vp, vp]),
+        "eid_renderer_render_host_async": (i32, [vp, C.POINTER(SceneCamera), C.POINTER(RtxState), i32, vp, vp]),
+        "eid_renderer_wait_host": (i32, [vp]),
         "eid_renderer_set_profiling": (i32, [vp, i32]),
         "eid_renderer_get_stats": (i32, [vp, C.POINTER(FrameStats)]),
         "eid_renderer_set_band": (i32, [vp, u32, u32]),
@@ -354,6 +356,14 @@ class Renderer:
         _check(lib().eid_renderer_render_host(
             self._h, C.byref(cam) if cam is not None else None, C.byref(state), frames,
             C.c_void_p(direct_out) if direct_out else None, C.c_void_p(indirect_out) if indirect_out else None))
+
+    def render_host_async(self, cam, state, frames, direct_out, indirect_out):
+        _check(lib().eid_renderer_render_host_async(
+            self._h, C.byref(cam) if cam is not None else None, C.byref(state), frames,
+            C.c_void_p(direct_out) if direct_out else None, C.c_void_p(indirect_out) if indirect_out else None))
+
+    def wait_host(self):
+        _check(lib().eid_renderer_wait_host(self._h))
 
     def set_profiling(self, on):
         _check(lib().eid_renderer_set_profiling(self._h, int(on)))

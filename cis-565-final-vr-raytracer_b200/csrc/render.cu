@@ -573,6 +573,10 @@ struct eid_renderer {
   cudaStream_t aux = nullptr;             // second stream: K3 runs beside K2/K4 (see launchFrame)
   bool overlap = true;
   bool postStarted = false;
+  cudaStream_t copyStream = nullptr;      // eid_renderer_render_host_async: D2H of frame f overlaps the kernels of frame f+1
+  cudaEvent_t evFrameDone = nullptr, evCopyDone = nullptr;
+  float4* staging[2] = {nullptr, nullptr};
+  bool copyPending = false;
   eid_frame_stats stats{};
   bool statsPending = false;
 
@@ -849,6 +853,8 @@ int eid_renderer_resize(eid_renderer* r, uint32_t width, uint32_t height) {
   if (!width || !height || width > 32768 || height > 32768) raise(EID_ERR_INVALID, "bad render size %ux%u", width, height);
   CUDA_CHECK(cudaSetDevice(r->device));
   CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  if (r->copyStream) CUDA_CHECK(cudaStreamSynchronize(r->copyStream));
+  cudaFree(r->staging[0]); cudaFree(r->staging[1]); r->staging[0] = r->staging[1] = nullptr; r->copyPending = false;
   r->release();
   r->width = width; r->height = height; r->stripesSet = false;
   r->allocate();
@@ -866,6 +872,9 @@ void eid_renderer_destroy(eid_renderer* r) {
   for (auto& e : r->ev) if (e) cudaEventDestroy(e);
   if (r->evFork) cudaEventDestroy(r->evFork); if (r->evJoin) cudaEventDestroy(r->evJoin); if (r->evPost) cudaEventDestroy(r->evPost);
   if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
+  if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
+  if (r->evFrameDone) cudaEventDestroy(r->evFrameDone); if (r->evCopyDone) cudaEventDestroy(r->evCopyDone);
+  cudaFree(r->staging[0]); cudaFree(r->staging[1]);
   if (r->ownStream && r->stream) cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -1089,6 +1098,50 @@ int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxS
   if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->directImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
   if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->indirectImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  return EID_OK;
+  EID_CATCH
+}
+
+// Pipelined variant: the frame is enqueued, its two result images are snapshotted device-to-device into staging buffers (so the
+// next frame may overwrite the live images at once) and the device-to-host copies run on a dedicated copy stream, overlapping the
+// next frame's kernels.  The host buffers are complete after eid_renderer_wait_host (or the next *_async call for the SAME
+// buffers, which waits first).  Use two host buffer pairs alternately for full overlap.
+int eid_renderer_render_host_async(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames, float* direct_host, float* indirect_host) {
+  EID_TRY
+  if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_render_host_async: null argument");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  if (!r->copyStream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evFrameDone, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evCopyDone, cudaEventDisableTiming));
+  }
+  const size_t n = (size_t)r->width * r->height * 16;
+  if (!r->staging[0]) { CUDA_CHECK(cudaMalloc(&r->staging[0], n)); CUDA_CHECK(cudaMalloc(&r->staging[1], n)); }
+  if (cam) r->scene->host.camera = *cam;
+  FrameParams P;
+  fillParams(r, *state, frames, P);
+  launchFrame(r, P);
+  // the previous frame's D2H copies must have drained the staging buffers before they are overwritten
+  if (r->copyPending) CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evCopyDone, 0));
+  if (direct_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[0], r->directImg, n, cudaMemcpyDeviceToDevice, r->stream));
+  if (indirect_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[1], r->indirectImg, n, cudaMemcpyDeviceToDevice, r->stream));
+  CUDA_CHECK(cudaEventRecord(r->evFrameDone, r->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, r->evFrameDone, 0));
+  const size_t rowBytes = (size_t)state->size.x * 16;
+  if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->staging[0], (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
+  if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->staging[1], (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
+  CUDA_CHECK(cudaEventRecord(r->evCopyDone, r->copyStream));
+  r->copyPending = true;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_wait_host(eid_renderer* r) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_wait_host: null renderer");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  if (r->copyStream) CUDA_CHECK(cudaStreamSynchronize(r->copyStream));
+  r->copyPending = false;
   return EID_OK;
   EID_CATCH
 }

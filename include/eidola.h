@@ -269,6 +269,11 @@ EID_API int  eid_renderer_write(eid_renderer* r, int which, const void* host_src
  * pinned or pageable host buffers (width*height*16 bytes each, either may be NULL) and syncs. */
 EID_API int  eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
                                       float* direct_host, float* indirect_host);
+/* Pipelined form of eid_renderer_render_host: returns after enqueueing; the device->host copies of frame f run on a copy stream
+ * while frame f+1 renders.  The host buffers are valid after eid_renderer_wait_host.  Alternate two host buffer pairs. */
+EID_API int  eid_renderer_render_host_async(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
+                                            float* direct_host, float* indirect_host);
+EID_API int  eid_renderer_wait_host(eid_renderer* r);
 /* 1 (default): run the direct denoiser (K3) on a second CUDA stream concurrently with indirect_stage (K2) + the indirect
  * denoiser (K4) — the reference's true dependencies are K1->{K2,K3}, K2->K4, {K3,K4}->K5.  0: strict K1..K5 order on one stream.
  * Results are identical either way; per-stage times (kernelMs) overlap when enabled. */

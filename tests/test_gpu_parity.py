@@ -300,6 +300,31 @@ def test_render_host_end_to_end_and_checkpoint():
         r1.run(st, f)
         r2.render_host(psc.get_camera(), st, f, d.ctypes.data, i.ctypes.data)
         assert r1.read(abi.BUF_DIRECT).tobytes() == d.tobytes() and r1.read(abi.BUF_INDIRECT).tobytes() == i.tobytes()
+    # pipelined host API: same images, delivered after wait_host; two buffer pairs alternate
+    r4 = eid.Renderer()
+    r4.create(size, psc, acc)
+    r4.set_env_constant(common.ENV)
+    bufs = [[np.zeros_like(d), np.zeros_like(d)] for _ in range(2)]
+    cams = []
+    psc2 = eid.Scene(0)
+    psc2.load_arrays(arrays)
+    psc2.update_camera(*size)
+    for f in range(3):
+        psc2.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f)
+        r4.render_host_async(psc2.get_camera(), st, f, bufs[f & 1][0].ctypes.data, bufs[f & 1][1].ctypes.data)
+    r4.wait_host()
+    r5 = eid.Renderer()
+    r5.create(size, psc2, acc)
+    r5.set_env_constant(common.ENV)
+    psc3 = eid.Scene(0)
+    psc3.load_arrays(arrays)
+    psc3.update_camera(*size)
+    for f in range(3):
+        psc3.update_camera(*size)
+        r5.render_host(psc3.get_camera(), common.frame_state(size[0], size[1], info, f), f, d.ctypes.data, i.ctypes.data)
+        if f >= 1:
+            assert bufs[f & 1][0].tobytes() == d.tobytes() and bufs[f & 1][1].tobytes() == i.tobytes(), "async host frame %d differs" % f
     # checkpoint = cross-frame state (G-buffer + reservoirs); restore into a fresh renderer and continue
     r3 = eid.Renderer()
     r3.create(size, psc, acc)
