@@ -315,7 +315,7 @@ def test_render_host_end_to_end_and_checkpoint():
         r4.render_host_async(psc2.get_camera(), st, f, bufs[f & 1][0].ctypes.data, bufs[f & 1][1].ctypes.data)
     r4.wait_host()
     r5 = eid.Renderer()
-    r5.create(size, psc2, acc)
+    r5.create(size, psc, acc)
     r5.set_env_constant(common.ENV)
     psc3 = eid.Scene(0)
     psc3.load_arrays(arrays)
