@@ -28,7 +28,7 @@ class EidolaError(RuntimeError):
 # every symbol include/eidola.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "eid_last_error", "eid_version", "eid_device_count",
-    "eid_scene_create", "eid_scene_load_gltf", "eid_scene_load_desc", "eid_scene_destroy", "eid_scene_set_lookat",
+    "eid_scene_create", "eid_scene_load_gltf", "eid_scene_load_desc", "eid_scene_provide_image", "eid_scene_destroy", "eid_scene_set_lookat",
     "eid_scene_update_camera", "eid_scene_set_camera", "eid_scene_get_camera", "eid_scene_get_info",
     "eid_scene_table_bytes", "eid_scene_read_table",
     "eid_accel_build", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
@@ -59,6 +59,7 @@ def lib():
         "eid_scene_create": (i32, [C.POINTER(vp), i32]),
         "eid_scene_load_gltf": (i32, [vp, C.c_char_p]),
         "eid_scene_load_desc": (i32, [vp, C.POINTER(abi.SceneDesc)]),
+        "eid_scene_provide_image": (i32, [vp, u32, vp, u32, u32]),
         "eid_scene_destroy": (None, [vp]),
         "eid_scene_set_lookat": (i32, [vp, abi.c_float_p, abi.c_float_p, abi.c_float_p, C.c_float]),
         "eid_scene_update_camera": (i32, [vp, u32, u32]),
@@ -134,6 +135,10 @@ class Scene:
     def load(self, filename):            # Scene::load(const std::string&) -> bool (scene.cpp:57)
         _check(lib().eid_scene_load_gltf(self._h, os.fsencode(filename)))
         return True
+
+    def provide_image(self, index, rgba8):   # decoded image `index` for the next load(): (h, w, 4) uint8
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        _check(lib().eid_scene_provide_image(self._h, index, a.ctypes.data, a.shape[1], a.shape[0]))
 
     def load_arrays(self, arrays):       # harness path: arrays already in nvh::GltfScene shape
         d = arrays.desc()

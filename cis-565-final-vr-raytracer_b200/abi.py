@@ -90,6 +90,15 @@ class LightDesc(C.Structure):
                 ("outerConeAngle", C.c_float)]
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba8", C.c_void_p)]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("image", C.c_int32), ("hasSampler", C.c_int32), ("magFilter", C.c_int32), ("minFilter", C.c_int32),
+                ("wrapS", C.c_int32), ("wrapT", C.c_int32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("positions", c_float_p), ("normals", c_float_p), ("tangents", c_float_p),
                 ("texcoords0", c_float_p), ("colors0", c_float_p), ("vertexCount", C.c_uint32),
@@ -99,7 +108,9 @@ class SceneDesc(C.Structure):
                 ("materials", C.POINTER(MaterialDesc)), ("materialCount", C.c_uint32),
                 ("lights", C.POINTER(LightDesc)), ("lightCount", C.c_uint32),
                 ("hasCamera", C.c_int32), ("camEye", C.c_float * 3), ("camCenter", C.c_float * 3),
-                ("camUp", C.c_float * 3), ("camYfovRad", C.c_float)]
+                ("camUp", C.c_float * 3), ("camYfovRad", C.c_float),
+                ("images", C.POINTER(ImageDesc)), ("imageCount", C.c_uint32),
+                ("textures", C.POINTER(TextureDesc)), ("textureCount", C.c_uint32)]
 
 
 class SceneInfo(C.Structure):
@@ -189,7 +200,7 @@ class SceneArrays:
     """
 
     def __init__(self, positions, normals, tangents, texcoords0, colors0, indices, prim_meshes, nodes,
-                 materials, lights=(), camera=None, name="scene"):
+                 materials, lights=(), camera=None, name="scene", images=(), textures=()):
         f32 = lambda a, k: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1, k))
         self.positions, self.normals, self.tangents = f32(positions, 3), f32(normals, 3), f32(tangents, 4)
         self.texcoords0, self.colors0 = f32(texcoords0, 2), f32(colors0, 4)
@@ -200,18 +211,21 @@ class SceneArrays:
         self.lights = list(lights)             # dicts of LightDesc fields
         self.camera = camera                   # dict eye, center, up, yfov (rad) or None
         self.name = name
+        self.images = [np.ascontiguousarray(i, np.uint8) for i in images]     # (h, w, 4) uint8 each
+        self.textures = list(textures)         # dicts: image, and optionally magFilter/minFilter/wrapS/wrapT (sampler present)
         n = self.positions.shape[0]
         assert self.normals.shape[0] == n and self.tangents.shape[0] == n
         assert self.texcoords0.shape[0] == n and self.colors0.shape[0] == n
 
     @staticmethod
     def material(base=(1, 1, 1, 1), metallic=1.0, roughness=1.0, emissive=(0, 0, 0), double_sided=0,
-                 ior=1.5, transmission=0.0, alpha_mode=0, alpha_cutoff=0.5):
-        return dict(baseColorFactor=tuple(base), baseColorTexture=-1, metallicFactor=metallic,
-                    roughnessFactor=roughness, metallicRoughnessTexture=-1, emissiveTexture=-1,
+                 ior=1.5, transmission=0.0, alpha_mode=0, alpha_cutoff=0.5, base_tex=-1, mr_tex=-1, emissive_tex=-1,
+                 normal_tex=-1, normal_scale=1.0, transmission_tex=-1):
+        return dict(baseColorFactor=tuple(base), baseColorTexture=base_tex, metallicFactor=metallic,
+                    roughnessFactor=roughness, metallicRoughnessTexture=mr_tex, emissiveTexture=emissive_tex,
                     emissiveFactor=tuple(emissive), alphaMode=alpha_mode, alphaCutoff=alpha_cutoff,
-                    doubleSided=double_sided, normalTexture=-1, normalTextureScale=1.0,
-                    transmissionFactor=transmission, transmissionTexture=-1, ior=ior)
+                    doubleSided=double_sided, normalTexture=normal_tex, normalTextureScale=normal_scale,
+                    transmissionFactor=transmission, transmissionTexture=transmission_tex, ior=ior)
 
     def desc(self):
         d = SceneDesc()
@@ -257,5 +271,14 @@ class SceneArrays:
             d.camCenter = (C.c_float * 3)(*self.camera["center"])
             d.camUp = (C.c_float * 3)(*self.camera["up"])
             d.camYfovRad = self.camera["yfov"]
-        self._keep = [pm, nd, mt, lt]
+        im = (ImageDesc * max(1, len(self.images)))()
+        for i, a in enumerate(self.images):
+            im[i] = ImageDesc(a.shape[1], a.shape[0], a.ctypes.data if a.size else None)
+        tx = (TextureDesc * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            has = any(k in t for k in ("magFilter", "minFilter", "wrapS", "wrapT"))
+            tx[i] = TextureDesc(t["image"], int(has), t.get("magFilter", -1), t.get("minFilter", -1), t.get("wrapS", 10497), t.get("wrapT", 10497))
+        d.images, d.imageCount = im, len(self.images)
+        d.textures, d.textureCount = tx, len(self.textures)
+        self._keep = [pm, nd, mt, lt, im, tx]
         return d

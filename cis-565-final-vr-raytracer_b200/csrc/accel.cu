@@ -37,7 +37,8 @@ static T* uploadVec(const std::vector<T>& v) {
 
 void SceneDevice::release() {
   cudaFree(vertices); cudaFree(indices); cudaFree(geoInfo); cudaFree(materials); cudaFree(puncLights);
-  cudaFree(trigLights); cudaFree(instances); cudaFree(instFirstTri);
+  cudaFree(trigLights); cudaFree(instances); cudaFree(instFirstTri); cudaFree(textures); cudaFree(texels);
+  textures = nullptr; texels = nullptr;
   vertices = nullptr; indices = nullptr; geoInfo = nullptr; materials = nullptr; puncLights = nullptr;
   trigLights = nullptr; instances = nullptr; instFirstTri = nullptr;
 }
@@ -59,6 +60,12 @@ void SceneDevice::upload(const SceneHost& h) {
   puncLights = uploadVec(h.puncLights);
   trigLights = uploadVec(h.trigLights);
   instances = uploadVec(h.instances);
+  texels = uploadVec(h.texels);
+  std::vector<TextureDev> td(h.textures.size());
+  for (size_t i = 0; i < td.size(); ++i)
+    td[i] = TextureDev{texels + h.textures[i].texelOffset, (int32_t)h.textures[i].width, (int32_t)h.textures[i].height, h.textures[i].linear,
+                       h.textures[i].wrapS, h.textures[i].wrapT, 0};
+  textures = uploadVec(td);
   std::vector<uint32_t> first(h.instances.size() + 1, 0);
   for (size_t i = 0; i < h.instances.size(); ++i) first[i + 1] = first[i] + h.instances[i].triangleCount;
   instFirstTri = uploadVec(first);
@@ -66,6 +73,7 @@ void SceneDevice::upload(const SceneHost& h) {
 
 DeviceSceneView SceneDevice::view(const SceneHost& h) const {
   DeviceSceneView v;
+  v.textures = textures;
   v.geoInfo = geoInfo; v.materials = materials; v.puncLights = puncLights; v.trigLights = trigLights;
   v.instances = instances; v.lightBufInfo = h.lightInfo;
   return v;
@@ -476,9 +484,6 @@ static int finishLoad(eid_scene* s) {
   s->host.build();
   if (s->host.hasNonOpaque)
     raise(EID_ERR_UNSUPPORTED, "scene has alpha-tested/blended (non FORCE_OPAQUE) instances: stochastic alpha (traceray_rq.glsl:32-102) is not implemented yet");
-  for (const auto& m : s->host.materials)
-    if (m.pbrBaseColorTexture > -1 || m.pbrMetallicRoughnessTexture > -1 || m.emissiveTexture > -1 || m.normalTexture > -1 || m.transmissionTexture > -1)
-      raise(EID_ERR_UNSUPPORTED, "scene uses textures: texture taps (gltf_material.glsl:138-171) are not implemented yet");
   if (s->dev.device != EID_DEVICE_NONE) s->dev.upload(s->host);
   s->loaded = true;
   return EID_OK;
@@ -488,8 +493,20 @@ int eid_scene_load_gltf(eid_scene* s, const char* path) {
   EID_TRY
   if (!s || !path) raise(EID_ERR_INVALID, "eid_scene_load_gltf: null argument");
   s->loaded = false;
-  importGltfFile(path, s->host.gltf);
+  importGltfFile(path, s->host.gltf, s->providedImages);
   return finishLoad(s);
+  EID_CATCH
+}
+
+int eid_scene_provide_image(eid_scene* s, uint32_t imageIndex, const uint8_t* rgba8, uint32_t width, uint32_t height) {
+  EID_TRY
+  if (!s || !rgba8 || !width || !height) raise(EID_ERR_INVALID, "eid_scene_provide_image: bad argument");
+  if (imageIndex >= 65536) raise(EID_ERR_INVALID, "image index %u too large", imageIndex);
+  if (s->providedImages.size() <= imageIndex) s->providedImages.resize(imageIndex + 1);
+  auto& im = s->providedImages[imageIndex];
+  im.width = width; im.height = height;
+  im.rgba8.assign(rgba8, rgba8 + 4 * (size_t)width * height);
+  return EID_OK;
   EID_CATCH
 }
 

@@ -12,7 +12,13 @@
 namespace eid {
 
 // What a kernel needs to shade: the reference's S_SCENE descriptor set (layouts.glsl:48-54).
+struct TextureDev {                     // device twin of TextureHost with a resolved texel pointer
+  const uint32_t* texels;
+  int32_t width, height, linear, wrapS, wrapT, pad;
+};
+
 struct DeviceSceneView {
+  const TextureDev* textures;           // texturesMap[]
   const InstanceData* geoInfo;          // per prim mesh: vertex/index device addresses + material
   const GltfShadeMaterial* materials;
   const PuncLight* puncLights;
@@ -43,6 +49,8 @@ struct SceneDevice {
   PuncLight* puncLights = nullptr;
   TrigLight* trigLights = nullptr;
   InstanceXform* instances = nullptr;
+  TextureDev* textures = nullptr;
+  uint32_t* texels = nullptr;
   uint32_t* instFirstTri = nullptr;     // exclusive prefix of triangle counts per instance (+ total)
   void upload(const SceneHost& h);
   void release();
@@ -52,6 +60,7 @@ struct SceneDevice {
 }  // namespace eid
 
 struct eid_scene {
+  std::vector<eid::HostGltf::Image> providedImages;   // eid_scene_provide_image: decoded by the host before eid_scene_load_gltf
   eid::SceneHost host;
   eid::SceneDevice dev;
   bool loaded = false;

@@ -520,6 +520,14 @@ void HostGltf::fromDesc(const eid_scene_desc& d) {
   nodes.assign(d.nodes, d.nodes + d.nodeCount);
   materials.assign(d.materials, d.materials + d.materialCount);
   lights.assign(d.lights, d.lights + d.lightCount);
+  images.clear(); textures.clear();
+  for (uint32_t i = 0; i < d.imageCount; ++i) {
+    Image im;
+    const eid_image_desc& src = d.images[i];
+    if (src.rgba8 && src.width && src.height) { im.width = src.width; im.height = src.height; im.rgba8.assign(src.rgba8, src.rgba8 + 4 * (size_t)src.width * src.height); }
+    images.push_back(std::move(im));
+  }
+  if (d.textureCount) textures.assign(d.textures, d.textures + d.textureCount);
   for (const auto& pm : primMeshes) {
     if ((uint64_t)pm.firstIndex + pm.indexCount > indices.size() || (uint64_t)pm.vertexOffset + pm.vertexCount > d.vertexCount)
       raise(EID_ERR_INVALID, "prim mesh range outside the vertex/index arrays");
@@ -537,7 +545,7 @@ void HostGltf::fromDesc(const eid_scene_desc& d) {
   computeDimensions();
 }
 
-void importGltfFile(const std::string& path, HostGltf& g) {
+void importGltfFile(const std::string& path, HostGltf& g, const std::vector<HostGltf::Image>& provided) {
   g = HostGltf();
   std::vector<uint8_t> file = readFile(path);
   Doc d;
@@ -575,6 +583,34 @@ void importGltfFile(const std::string& path, HostGltf& g) {
     }
   }
   importMaterials(d, g);
+  {   // textures / samplers / images (tinygltf::Model::textures, samplers, images)
+    const JValue& imgs = d.top("images");
+    g.images.resize(imgs.size());
+    for (size_t i = 0; i < imgs.size() && i < provided.size(); ++i) g.images[i] = provided[i];
+    const JValue& texs = d.top("textures");
+    const JValue& samps = d.top("samplers");
+    for (size_t i = 0; i < texs.size(); ++i) {
+      eid_texture_desc t{};
+      t.image = texs.at(i).integer("source", -1);
+      int si = texs.at(i).integer("sampler", -1);
+      t.hasSampler = (si >= 0 && (size_t)si < samps.size()) ? 1 : 0;
+      t.magFilter = t.minFilter = -1; t.wrapS = t.wrapT = 10497;
+      if (t.hasSampler) {
+        const JValue& sm = samps.at(si);
+        t.magFilter = sm.integer("magFilter", -1); t.minFilter = sm.integer("minFilter", -1);
+        t.wrapS = sm.integer("wrapS", 10497); t.wrapT = sm.integer("wrapT", 10497);
+      }
+      g.textures.push_back(t);
+    }
+    auto used = [&](int tex) {
+      if (tex < 0 || (size_t)tex >= g.textures.size()) return;
+      int im = g.textures[tex].image;
+      if (im >= 0 && (size_t)im < g.images.size() && g.images[im].rgba8.empty())
+        raise(EID_ERR_UNSUPPORTED, "texture %d uses image %d, which must be decoded by the host first (eid_scene_provide_image): "
+                                   "no PNG/JPEG decoder is available in this build", tex, im);
+    };
+    for (const auto& m : g.materials) { used(m.baseColorTexture); used(m.metallicRoughnessTexture); used(m.emissiveTexture); used(m.normalTexture); used(m.transmissionTexture); }
+  }
   ImportCtx c{d, g, {}, {}, {}};
   int sceneIdx = d.root->integer("scene", 0);
   const JValue& scenes = d.top("scenes");

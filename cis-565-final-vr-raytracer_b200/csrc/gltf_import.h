@@ -16,6 +16,9 @@ struct HostGltf {
   std::vector<eid_node> nodes;
   std::vector<eid_material_desc> materials;
   std::vector<eid_light_desc> lights;
+  struct Image { uint32_t width = 0, height = 0; std::vector<uint8_t> rgba8; };   // decoded, empty = not available
+  std::vector<Image> images;
+  std::vector<eid_texture_desc> textures;
   bool hasCamera = false;
   float camEye[3] = {0, 0, 0}, camCenter[3] = {0, 0, -1}, camUp[3] = {0, 1, 0};
   float camYfovRad = 1.0471975512f;
@@ -26,6 +29,8 @@ struct HostGltf {
 };
 
 // throws eid::Error (EID_ERR_IO / EID_ERR_PARSE / EID_ERR_UNSUPPORTED)
-void importGltfFile(const std::string& path, HostGltf& out);
+// `provided` = images the host decoded beforehand (index -> texels); this image has no PNG/JPEG decoder (the reference uses
+// FreeImage / stb through tinygltf), so a file whose used textures reference undecoded images is rejected with EID_ERR_UNSUPPORTED.
+void importGltfFile(const std::string& path, HostGltf& out, const std::vector<HostGltf::Image>& provided);
 
 }  // namespace eid

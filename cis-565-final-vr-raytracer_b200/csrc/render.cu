@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     } else {
       rc.primary++;
       State st = getState(P.sc, prd, rd);
-      getMaterials(P.sc, st);
+      getMaterials(P.sc, st, rd);
       // createMotionIndex (:125-139)
       float pr[4];
       mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
@@ -348,12 +348,14 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
           break;
         }
         st = getState(P.sc, prd, rayD);
-        getMaterials(P.sc, st);
+        getMaterials(P.sc, st, rayD);
         if (st.isEmitter) {                                 // :203-215, LightEval (pathtrace.glsl:74-88)
           if (d > 1) {
             const float lightProb = __fsub_rn(1.0f, P.st.environmentProb);
-            float lightPdf = __fmul_rn(__fmul_rn(lum3(st.mat.emission), P.st.lightLuminIntegInv), lightProb);
+            const float4 em = __ldg((const float4*)(P.sc.materials + st.matID) + 2);   // emissiveFactor (untextured) drives the pdf
+            float lightPdf = __fmul_rn(__fmul_rn(lum709(em.y, em.z, em.w), P.st.lightLuminIntegInv), lightProb);
             lightPdf = __fmul_rn(lightPdf, __fdiv_rn(__fmul_rn(prd.hitT, prd.hitT), absDot(st.ffnormal, sampleWi)));
+            // LightEval (pathtrace.glsl:74-88): pdf from the emissive FACTOR, radiance from factor x texture (st.mat.emission has both)
             const f3 Li = st.mat.emission / st.area;
             gs.L = gs.L + (Li * throughput) * misWeight(P, samplePdf, lightPdf);
           } else {

@@ -48,8 +48,40 @@ static inline void xformPoint(const float* m /*4x4 col-major*/, const float* p, 
   for (int r = 0; r < 3; ++r) o[r] = ((m[r] * p[0] + m[4 + r] * p[1]) + m[8 + r] * p[2]) + m[12 + r];
 }
 
+// Scene::createTextureImages + gltfSamplerToVulkan (scene.cpp:513-646): missing images / bad sources become a 1x1 white texel,
+// a file without images gets one default texture, sampler enums outside the filter map fall back to NEAREST (std::map default).
+static void buildTextureTable(const HostGltf& g, std::vector<TextureHost>& out, std::vector<uint32_t>& texels) {
+  out.clear(); texels.clear();
+  texels.push_back(0xFFFFFFFFu);                       // texel 0: the shared white default
+  if (g.images.empty()) { out.push_back(TextureHost{}); return; }
+  auto isLinear = [](int f) { return (f == 9729 || f == 9985 || f == 9987) ? 1 : 0; };
+  auto wrapMode = [](int w) { return w == 33071 ? 2 : (w == 33648 ? 1 : 0); };
+  std::vector<int64_t> imageOffset(g.images.size(), -1);
+  for (const auto& t : g.textures) {
+    TextureHost h;
+    if (t.image >= 0 && (size_t)t.image < g.images.size()) {
+      const auto& im = g.images[t.image];
+      if (!im.rgba8.empty()) {
+        if (imageOffset[t.image] < 0) {
+          imageOffset[t.image] = (int64_t)texels.size();
+          const size_t n = (size_t)im.width * im.height;
+          texels.resize(texels.size() + n);
+          memcpy(&texels[imageOffset[t.image]], im.rgba8.data(), 4 * n);
+        }
+        h.width = im.width; h.height = im.height; h.texelOffset = (uint64_t)imageOffset[t.image];
+      }
+      if (t.hasSampler) { h.linear = isLinear(t.magFilter); h.wrapS = wrapMode(t.wrapS); h.wrapT = wrapMode(t.wrapT); }
+    }
+    out.push_back(h);
+  }
+}
+
 void SceneHost::build() {
   const HostGltf& g = gltf;
+  buildTextureTable(g, textures, texels);
+  for (const auto& m : g.materials)
+    for (int t : {m.baseColorTexture, m.metallicRoughnessTexture, m.emissiveTexture, m.normalTexture, m.transmissionTexture})
+      if (t >= (int)textures.size()) raise(EID_ERR_INVALID, "material references texture %d but only %zu exist", t, textures.size());
   // ---- materials (scene.cpp:415-448)
   materials.clear();
   for (const auto& m : g.materials) {

@@ -19,8 +19,18 @@ struct InstanceXform {
 };
 enum { INST_CULL_DISABLE = 1u, INST_MIRROR = 2u, INST_FORCE_OPAQUE = 4u };
 
+// one entry of texturesMap[] (layouts.glsl:51): 8-bit UNORM texels + sampler state (Scene::createTextureImages, scene.cpp:513-646)
+struct TextureHost {
+  uint32_t width = 1, height = 1;
+  uint64_t texelOffset = 0;      // into SceneHost::texels (uint32 RGBA8 each)
+  int32_t linear = 1;            // magnification filter; every tap is textureLod(..., 0)
+  int32_t wrapS = 0, wrapT = 0;  // 0 REPEAT, 1 MIRRORED_REPEAT, 2 CLAMP_TO_EDGE
+};
+
 struct SceneHost {
   HostGltf gltf;
+  std::vector<TextureHost> textures;
+  std::vector<uint32_t> texels;
   // concatenated vertex / index storage; prim mesh p owns vertices [vtxBase[p], +vertexCount) and
   // indices [idxBase[p], +indexCount).  Prim meshes sharing an accessor set share the vertex range
   // (the reference's m_cachePrimitive, scene.cpp:223-234).

@@ -61,6 +61,7 @@ DEV f3 ldrToHdr(f3 c) { return c / (1.01f - c); }      // :198-200
 struct Material { f3 albedo, emission; float metallic, ior, roughness, transmission; };
 struct State {
   f3 position, normal, ffnormal;
+  f3 tangent, bitangent;   // only filled (and only needed) when the material has a normal map
   float u, v;          // texCoord
   float eta, area;
   uint32_t matID;
@@ -180,6 +181,40 @@ DEV void resvUpdate(DResv& r, f3 Li, f3 wi, float dist, float newWeight, float r
   if (__fmul_rn(rv, r.weight) < newWeight) { r.Li = Li; r.wi = wi; r.dist = dist; }
 }
 
+// ---- texturesMap[] taps (layouts.glsl:51): textureLod(sampler2D, uv, 0) on RGBA8 UNORM ------------------------------------
+DEV int wrapCoord(int i, int n, int mode) {              // 0 REPEAT, 1 MIRRORED_REPEAT, 2 CLAMP_TO_EDGE
+  if (mode == 2) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+  if (mode == 1) { const int p = 2 * n; int m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
+  int m = i % n; return m < 0 ? m + n : m;
+}
+DEV float4 texel8(const TextureDev& T, int x, int y) {
+  const uint32_t t = __ldg(T.texels + (size_t)y * T.width + x);
+  return make_float4(unormToFloat(t & 0xffu), unormToFloat((t >> 8) & 0xffu), unormToFloat((t >> 16) & 0xffu), unormToFloat(t >> 24));
+}
+DEV float4 mix4(float4 a, float4 b, float t) { return make_float4(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t), mixf(a.w, b.w, t)); }
+DEV float4 textureLod0(const DeviceSceneView& sc, int index, float u, float v) {
+  const TextureDev T = sc.textures[index];
+  if (!T.linear) {
+    const int x = wrapCoord(f2i_sat(eid_floorf(__fmul_rn(u, (float)T.width))), T.width, T.wrapS);
+    const int y = wrapCoord(f2i_sat(eid_floorf(__fmul_rn(v, (float)T.height))), T.height, T.wrapT);
+    return texel8(T, x, y);
+  }
+  const float x = __fsub_rn(__fmul_rn(u, (float)T.width), 0.5f), y = __fsub_rn(__fmul_rn(v, (float)T.height), 0.5f);
+  const float x0f = eid_floorf(x), y0f = eid_floorf(y);
+  const float fx = __fsub_rn(x, x0f), fy = __fsub_rn(y, y0f);
+  const int x0 = f2i_sat(x0f), y0 = f2i_sat(y0f);
+  const int xa = wrapCoord(x0, T.width, T.wrapS), xb = wrapCoord(x0 + 1, T.width, T.wrapS);
+  const int ya = wrapCoord(y0, T.height, T.wrapT), yb = wrapCoord(y0 + 1, T.height, T.wrapT);
+  return mix4(mix4(texel8(T, xa, ya), texel8(T, xb, ya), fx), mix4(texel8(T, xa, yb), texel8(T, xb, yb), fx), fy);
+}
+DEV f3 srgbToLinear3(float4 c) { return mk3(eid_powf(c.x, 2.2f), eid_powf(c.y, 2.2f), eid_powf(c.z, 2.2f)); }   // gltf_material.glsl:36-46
+DEV void createCoordinateSystem(f3 N, f3& Nt, f3& Nb) {   // common.glsl:81-93
+  const f3 a = (fabsf(N.z) > 0.99999f) ? mk3(__fmul_rn(-N.x, N.y), __fsub_rn(1.0f, __fmul_rn(N.y, N.y)), __fmul_rn(-N.y, N.z))
+                                        : mk3(__fmul_rn(-N.x, N.z), __fmul_rn(-N.y, N.z), __fsub_rn(1.0f, __fmul_rn(N.z, N.z)));
+  Nt = norm3(a);
+  Nb = cross3(Nt, N);
+}
+
 // ---- scene access --------------------------------------------------------------------------------
 struct Payload {       // PtPayload (globals.glsl:48-58) minus the matrices, which are fetched by instanceID
   float hitT, baryU, baryV;
@@ -217,22 +252,53 @@ DEV State getState(const DeviceSceneView& sc, const Payload& h, f3 rayDir) {
   st.u = __fadd_rn(__fadd_rn(__fmul_rn(a1.x, bx), __fmul_rn(b1.x, by)), __fmul_rn(c1.x, bz));
   st.v = __fadd_rn(__fadd_rn(__fmul_rn(v0, bx), __fmul_rn(v1, by)), __fmul_rn(v2, bz));
 
+  // Tangent and binormal (:194-204) feed only the TBN of normal mapping (gltf_material.glsl:135-146): evaluated on demand
+  if (__ldg(&sc.materials[st.matID].normalTexture) > -1) {
+    const float h0 = (__float_as_int(a1.y) & 1) == 1 ? 1.0f : -1.0f;
+    const f3 t0 = octDecode(__float_as_uint(a1.z)), t1 = octDecode(__float_as_uint(b1.z)), t2 = octDecode(__float_as_uint(c1.z));
+    f3 tangent = norm3((t0 * bx + t1 * by) + t2 * bz);
+    f3 world_tangent = norm3(xfVector(X.objectToWorld, tangent));
+    world_tangent = norm3(world_tangent - world_normal * dot3(world_tangent, world_normal));
+    st.tangent = world_tangent;
+    st.bitangent = cross3(world_normal, world_tangent) * h0;
+  } else { st.tangent = mk3(0.f); st.bitangent = mk3(0.f); }
+
   st.normal = (dot3(world_normal, wgeom_normal) > 0.0f) ? world_normal : -world_normal;
   st.ffnormal = dot3(st.normal, rayDir) <= 0.0f ? st.normal : -st.normal;
   st.area = __fmul_rn(len3(cross3(w1 - w0, w2 - w0)), 0.5f);
   return st;
 }
 
-// gltf_material.glsl:130-176 GetMaterials + GetMetallicRoughness :52-91, texture-less materials
-DEV void getMaterials(const DeviceSceneView& sc, State& st) {
+// gltf_material.glsl:130-176 GetMaterials + GetMetallicRoughness :52-91
+DEV void getMaterials(const DeviceSceneView& sc, State& st, f3 rayDir) {
   const float4* m = (const float4*)(sc.materials + st.matID);   // 80 B = 5 x float4
   const float4 q0 = __ldg(m), q1 = __ldg(m + 1), q2 = __ldg(m + 2), q3 = __ldg(m + 3), q4 = __ldg(m + 4);
+  const int baseTex = __float_as_int(q1.x), mrTex = __float_as_int(q1.w), emisTex = __float_as_int(q2.x);
+  const int nrmTex = __float_as_int(q3.x), transTex = __float_as_int(q3.w);
+  if (nrmTex > -1) {                                    // :135-146 normal mapping
+    const float4 t = textureLod0(sc, nrmTex, st.u, st.v);
+    f3 nv = norm3(mk3(t.x, t.y, t.z) * 2.0f + (-1.0f));
+    nv = nv * mk3(q3.y, q3.y, 1.0f);
+    const M3 TBN = {st.tangent, st.bitangent, st.normal};
+    st.normal = norm3(m3mul(TBN, nv));
+    st.ffnormal = dot3(st.normal, rayDir) <= 0.0f ? st.normal : -st.normal;
+    createCoordinateSystem(st.ffnormal, st.tangent, st.bitangent);
+  }
   st.mat.emission = mk3(q2.y, q2.z, q2.w);
+  if (emisTex > -1) st.mat.emission = st.mat.emission * srgbToLinear3(textureLod0(sc, emisTex, st.u, st.v));
   st.isEmitter = __fadd_rn(__fadd_rn(st.mat.emission.x, st.mat.emission.y), st.mat.emission.z) > 1e-3f;
+  float roughness = q1.z, metallic = q1.y;
+  if (mrTex > -1) {
+    const float4 t = textureLod0(sc, mrTex, st.u, st.v);
+    roughness = __fmul_rn(t.y, roughness);
+    metallic = __fmul_rn(t.z, metallic);
+  }
   st.mat.albedo = mk3(q0.x, q0.y, q0.z);
-  st.mat.metallic = q1.y;
-  st.mat.roughness = gmax(q1.z, 0.001f);
+  if (baseTex > -1) st.mat.albedo = st.mat.albedo * srgbToLinear3(textureLod0(sc, baseTex, st.u, st.v));
+  st.mat.metallic = metallic;
+  st.mat.roughness = gmax(roughness, 0.001f);
   st.mat.transmission = q3.z;
+  if (transTex > -1) st.mat.transmission = __fmul_rn(st.mat.transmission, textureLod0(sc, transTex, st.u, st.v).x);
   st.mat.ior = q4.x;
   st.eta = dot3(st.normal, st.ffnormal) > 0.0f ? __fdiv_rn(1.0f, st.mat.ior) : st.mat.ior;
 }
@@ -258,11 +324,8 @@ DEV f3 envTextureUv(const EnvView& E, float u, float v) {
   const float x0f = eid_floorf(x), y0f = eid_floorf(y);
   const float fx = __fsub_rn(x, x0f), fy = __fsub_rn(y, y0f);
   const int x0 = f2i_sat(x0f), y0 = f2i_sat(y0f);
-  int xa = x0 % E.width; if (xa < 0) xa += E.width;
-  int xb = (x0 + 1) % E.width; if (xb < 0) xb += E.width;
-  const int ya = y0 < 0 ? 0 : (y0 >= E.height ? E.height - 1 : y0);
-  const int y1 = y0 + 1;
-  const int yb = y1 < 0 ? 0 : (y1 >= E.height ? E.height - 1 : y1);
+  const int xa = wrapCoord(x0, E.width, 0), xb = wrapCoord(x0 + 1, E.width, 0);
+  const int ya = wrapCoord(y0, E.height, 2), yb = wrapCoord(y0 + 1, E.height, 2);
   return mix3(mix3(envTexel(E, xa, ya), envTexel(E, xb, ya), fx), mix3(envTexel(E, xa, yb), envTexel(E, xb, yb), fx), fy);
 }
 DEV f3 envTextureDir(const EnvView& E, f3 dir) {
@@ -321,7 +384,14 @@ DEV float sampleTriangleLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, L
   const float bu = __fsub_rn(1.0f, r), bv = __fmul_rn(ru, r);
   const f3 y = (bu * v0 + bv * v1) + __fsub_rn(__fsub_rn(1.0f, bu), bv) * v2;
   const float4 em = __ldg((const float4*)(sc.materials + matIndex) + 2);   // emissiveTexture, emissiveFactor.xyz
-  const f3 emission = mk3(em.y, em.z, em.w);
+  f3 emission = mk3(em.y, em.z, em.w);
+  if (__float_as_int(em.x) > -1) {                       // :127-132 textured emitter: uv from the light's own uv0..2
+    const float4 l3 = __ldg(L + 3);
+    const float w2 = __fsub_rn(__fsub_rn(1.0f, bu), bv);
+    const float tu = __fadd_rn(__fadd_rn(__fmul_rn(bu, l2.w), __fmul_rn(bv, l3.y)), __fmul_rn(w2, l3.w));
+    const float tv = __fadd_rn(__fadd_rn(__fmul_rn(bu, l3.x), __fmul_rn(bv, l3.z)), __fmul_rn(w2, l4.x));
+    emission = emission * srgbToLinear3(textureLod0(sc, __float_as_int(em.x), tu, tv));
+  }
   const f3 dir = y - x;
   const float dist = len3(dir);
   ls.Li = emission / area;

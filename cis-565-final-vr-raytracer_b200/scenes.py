@@ -80,11 +80,11 @@ class _Builder:
                       np.concatenate([np.repeat(tan, 3, axis=0), np.ones((3 * n, 1))], axis=1), uv,
                       np.arange(3 * n, dtype=np.uint32), material, matrix)
 
-    def build(self, camera, name):
+    def build(self, camera, name, images=(), textures=()):
         pos = np.concatenate(self.pos)
         return SceneArrays(pos, np.concatenate(self.nrm), np.concatenate(self.tan), np.concatenate(self.uv),
                            np.ones((pos.shape[0], 4), np.float32), np.concatenate(self.idx), self.prims,
-                           self.nodes, self.materials, self.lights, camera, name)
+                           self.nodes, self.materials, self.lights, camera, name, images=images, textures=textures)
 
 
 def _box_quads(lo, hi, faces="xXyYzZ", inward=False):
@@ -138,6 +138,67 @@ def cornell_scene():
     b.add_tris([[(0.35, 1.98, 0.45), (0.75, 1.98, 0.45), (0.35, 1.98, 0.85)]], l1)
     cam = dict(eye=(0.0, 1.0, -3.6), center=(0.0, 1.0, 0.0), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(45.0)))
     return b.build(cam, "c2_cornell")
+
+
+def _procedural_images(seed=21):
+    """Five small RGBA8 images: colour checker, metallic-roughness map, tangent-space normal map, emissive pattern, transmission."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = 32
+    yy, xx = np.mgrid[0:n, 0:n]
+    checker = np.zeros((n, n, 4), np.uint8)
+    c = ((xx // 4 + yy // 4) % 2).astype(bool)
+    checker[c] = (220, 60, 40, 255)
+    checker[~c] = (40, 90, 220, 255)
+    checker[..., :3] = np.clip(checker[..., :3].astype(np.int32) + rng.integers(-20, 20, (n, n, 3)), 0, 255)
+    mr = np.zeros((n, n, 4), np.uint8)
+    mr[..., 1] = (60 + 180 * (xx / (n - 1))).astype(np.uint8)          # roughness ramp in g
+    mr[..., 2] = np.where(yy < n // 2, 255, 20)                          # metallic split in b
+    mr[..., 3] = 255
+    h = np.sin(xx * 0.8) * np.cos(yy * 0.6)
+    gx, gy = np.gradient(h)
+    nm = np.stack([-gy * 0.8, -gx * 0.8, np.ones_like(h)], axis=-1)
+    nm /= np.linalg.norm(nm, axis=-1, keepdims=True)
+    normal = np.concatenate([(nm * 0.5 + 0.5) * 255, np.full((n, n, 1), 255.0)], axis=-1).astype(np.uint8)
+    emis = np.zeros((16, 16, 4), np.uint8)
+    emis[..., 0] = rng.integers(120, 255, (16, 16))
+    emis[..., 1] = rng.integers(60, 255, (16, 16))
+    emis[..., 2] = rng.integers(30, 200, (16, 16))
+    emis[..., 3] = 255
+    trans = np.zeros((8, 8, 4), np.uint8)
+    trans[..., 0] = rng.integers(0, 255, (8, 8))
+    trans[..., 3] = 255
+    return [checker, mr, normal, emis, trans]
+
+
+def textured_scene():
+    """Cornell-style box exercising every texture tap of the live path: base colour (sRGB), metallic-roughness, normal map,
+    emissive map on an area light, transmission map, with LINEAR/NEAREST filters and REPEAT/MIRRORED/CLAMP wrap modes."""
+    b = _Builder()
+    images = _procedural_images()
+    textures = [dict(image=0),                                                        # 0: no sampler -> LINEAR / REPEAT
+                dict(image=1, magFilter=9729, minFilter=9987, wrapS=33648, wrapT=10497),  # 1: LINEAR, mirrored / repeat
+                dict(image=2, magFilter=9729, minFilter=9729, wrapS=10497, wrapT=10497),  # 2: normal map, LINEAR / REPEAT
+                dict(image=3, magFilter=9728, minFilter=9728, wrapS=33071, wrapT=33071),  # 3: NEAREST, clamp
+                dict(image=4, magFilter=-1, minFilter=-1, wrapS=10497, wrapT=33648),      # 4: sampler without filters -> NEAREST
+                dict(image=7)]                                                            # 5: bad source -> white default texture
+    floor = b.add_material(base=(1, 1, 1, 1), metallic=1.0, roughness=1.0, base_tex=0, mr_tex=1, normal_tex=2, normal_scale=0.8)
+    wall = b.add_material(base=(0.9, 0.9, 0.9, 1), metallic=0.0, roughness=0.9, base_tex=0)
+    bumpy = b.add_material(base=(0.8, 0.7, 0.3, 1), metallic=0.6, roughness=0.4, normal_tex=2, normal_scale=1.5, transmission=0.7, transmission_tex=4)
+    plain = b.add_material(base=(0.7, 0.7, 0.7, 1), metallic=0.0, roughness=1.0, base_tex=5)
+    lamp = b.add_material(base=(0, 0, 0, 1), metallic=0.0, roughness=1.0, emissive=(14.0, 14.0, 14.0), emissive_tex=3)
+    lamp2 = b.add_material(base=(0, 0, 0, 1), metallic=0.0, roughness=1.0, emissive=(6.0, 7.0, 9.0))
+    lo, hi = (-1.0, 0.0, -1.0), (1.0, 2.0, 1.0)
+    b.add_quads(_box_quads(lo, hi, "y", inward=True), floor)
+    b.add_quads(_box_quads(lo, hi, "YZ", inward=True), plain)
+    b.add_quads(_box_quads(lo, hi, "xX", inward=True), wall)
+    b.add_quads(_box_quads((-0.6, 0.0, -0.2), (-0.05, 1.0, 0.4), "xXYzZ"), bumpy)
+    b.add_quads(_box_quads((0.2, 0.0, -0.6), (0.7, 0.5, -0.1), "xXYzZ"), floor)
+    b.add_quads([[(-0.4, 1.97, -0.3), (0.3, 1.97, -0.3), (0.3, 1.97, 0.3), (-0.4, 1.97, 0.3)]], lamp)      # faces down, textured emitter
+    b.add_tris([[(0.4, 1.98, 0.45), (0.8, 1.98, 0.45), (0.4, 1.98, 0.85)]], lamp2)
+    # scale uvs of the floor so the wrap modes are exercised (values outside [0,1] and negative)
+    b.uv[0] = b.uv[0] * 3.0 - 1.0
+    cam = dict(eye=(0.0, 1.0, -3.6), center=(0.0, 1.0, 0.0), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(45.0)))
+    return b.build(cam, "textured_box", images=images, textures=textures)
 
 
 def _value_noise(x, z, seed, octaves=4, base_cells=8):

@@ -90,6 +90,18 @@ typedef struct eid_light_desc {      /* nvh::GltfLight (KHR_lights_punctual) */
   float   innerConeAngle, outerConeAngle;
 } eid_light_desc;
 
+typedef struct eid_image_desc {      /* tinygltf::Image after decoding: 4 bytes per texel, row 0 first */
+  uint32_t       width, height;
+  const uint8_t* rgba8;              /* NULL / 0x0 = "image not present" -> 1x1 white (scene.cpp:575-582) */
+} eid_image_desc;
+
+typedef struct eid_texture_desc {    /* tinygltf::Texture + its Sampler (glTF enums; -1 = no sampler object) */
+  int32_t image;                     /* index into images[]; out of range -> 1x1 white default texture (scene.cpp:604-610) */
+  int32_t hasSampler;                /* 0: Vulkan defaults LINEAR / REPEAT (scene.cpp:613-616) */
+  int32_t magFilter, minFilter;      /* 9728 NEAREST, 9729 LINEAR, 9984..9987 mip variants; anything else -> NEAREST (scene.cpp:519-525) */
+  int32_t wrapS, wrapT;              /* 10497 REPEAT, 33648 MIRRORED_REPEAT, 33071 CLAMP_TO_EDGE */
+} eid_texture_desc;
+
 typedef struct eid_scene_desc {
   const float*    positions;   /* 3 floats / vertex */
   const float*    normals;     /* 3 */
@@ -106,6 +118,8 @@ typedef struct eid_scene_desc {
   int32_t hasCamera;           /* glTF camera 0, scene.cpp:298-308 */
   float   camEye[3], camCenter[3], camUp[3];
   float   camYfovRad;
+  const eid_image_desc*   images;    uint32_t imageCount;     /* Scene::createTextureImages (scene.cpp:554-646) */
+  const eid_texture_desc* textures;  uint32_t textureCount;
 } eid_scene_desc;
 
 typedef struct eid_scene_info {
@@ -136,6 +150,9 @@ typedef enum eid_scene_table {
 EID_API int  eid_scene_create(eid_scene** out, int device);
 /* Scene::load(filename) (scene.cpp:57-125): glTF 2.0 (.gltf + external .bin / data: URIs). */
 EID_API int  eid_scene_load_gltf(eid_scene* s, const char* path);
+/* Hands the loader image `imageIndex` of the next eid_scene_load_gltf already decoded (RGBA8, row 0 first).  The reference decodes
+ * PNG/JPEG with FreeImage/stb (scene.cpp:152,159); this build has no image decoder, so the host decodes and provides. */
+EID_API int  eid_scene_provide_image(eid_scene* s, uint32_t imageIndex, const uint8_t* rgba8, uint32_t width, uint32_t height);
 /* Same import, from arrays already in the GltfScene shape (harness-generated scenes). */
 EID_API int  eid_scene_load_desc(eid_scene* s, const eid_scene_desc* desc);
 /* Scene::destroy (scene.cpp:453-511) */

@@ -50,7 +50,17 @@ struct Bvh {
   void build(const std::vector<OTri>& tris, float pad);
 };
 
+// one entry of texturesMap[] (layouts.glsl:51): BGRA8/RGBA8 UNORM image + the sampler state the reference derives from glTF
+struct Texture {
+  int width = 1, height = 1;
+  std::vector<uint8_t> rgba{255, 255, 255, 255};
+  int linear = 1;           // magnification filter (all taps are textureLod(..., 0))
+  int wrapS = 0, wrapT = 0; // 0 REPEAT, 1 MIRRORED_REPEAT, 2 CLAMP_TO_EDGE
+  vec4 sample(vec2 uv) const;
+};
+
 struct Scene {
+  std::vector<Texture> textures;
   // flat glTF-import data (nvh::GltfScene shape)
   std::vector<float> positions, normals, tangents, texcoords0, colors0;
   std::vector<uint32_t> indices;

@@ -111,7 +111,55 @@ static mat4x3 toMat4x3(const float* m) {   // upper 3 rows of a column-major 4x4
   return r;
 }
 
+// textureLod(sampler2D, uv, 0) on an 8-bit UNORM image: LOD 0 selects the magnification filter; unnormalised coordinates
+// u*w - 0.5, floor / fract, per-axis wrap, full-float bilinear weights (contract)
+static int wrapCoord(int i, int n, int mode) {
+  if (mode == 2) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+  if (mode == 1) { int p = 2 * n; int m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
+  int m = i % n; return m < 0 ? m + n : m;
+}
+vec4 Texture::sample(vec2 uv) const {
+  auto texel = [&](int x, int y) {
+    const uint8_t* p = &rgba[4 * ((size_t)y * width + x)];
+    return vec4(float(p[0]) / 255.0f, float(p[1]) / 255.0f, float(p[2]) / 255.0f, float(p[3]) / 255.0f);
+  };
+  if (!linear) {
+    int x = wrapCoord(f2i(eid_floorf(uv.x * float(width))), width, wrapS);
+    int y = wrapCoord(f2i(eid_floorf(uv.y * float(height))), height, wrapT);
+    return texel(x, y);
+  }
+  const float x = uv.x * float(width) - 0.5f, y = uv.y * float(height) - 0.5f;
+  const float x0f = eid_floorf(x), y0f = eid_floorf(y);
+  const float fx = x - x0f, fy = y - y0f;
+  const int x0 = f2i(x0f), y0 = f2i(y0f);
+  const int xa = wrapCoord(x0, width, wrapS), xb = wrapCoord(x0 + 1, width, wrapS);
+  const int ya = wrapCoord(y0, height, wrapT), yb = wrapCoord(y0 + 1, height, wrapT);
+  auto mix4 = [](vec4 a, vec4 b, float t) { return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t)); };
+  return mix4(mix4(texel(xa, ya), texel(xb, ya), fx), mix4(texel(xa, yb), texel(xb, yb), fx), fy);
+}
+
+// Scene::createTextureImages + gltfSamplerToVulkan (scene.cpp:513-646)
+static void buildTextures(const eid_scene_desc& d, std::vector<Texture>& out) {
+  out.clear();
+  if (d.imageCount == 0) { out.push_back(Texture{}); return; }   // "No images, add a default one" (:570-576)
+  auto filt = [](int f) { return (f == 9729 || f == 9985 || f == 9987) ? 1 : 0; };   // std::map default = NEAREST for unknown keys
+  auto wrap = [](int w) { return w == 33071 ? 2 : (w == 33648 ? 1 : 0); };
+  for (uint32_t i = 0; i < d.textureCount; ++i) {
+    const eid_texture_desc& t = d.textures[i];
+    Texture tex;
+    if (t.image < 0 || (uint32_t)t.image >= d.imageCount) { out.push_back(tex); continue; }   // default white texture
+    const eid_image_desc& im = d.images[t.image];
+    if (im.rgba8 && im.width && im.height) {
+      tex.width = (int)im.width; tex.height = (int)im.height;
+      tex.rgba.assign(im.rgba8, im.rgba8 + 4 * (size_t)im.width * im.height);
+    }
+    if (t.hasSampler) { tex.linear = filt(t.magFilter); tex.wrapS = wrap(t.wrapS); tex.wrapT = wrap(t.wrapT); }
+    out.push_back(tex);
+  }
+}
+
 void Scene::load(const eid_scene_desc& d) {
+  buildTextures(d, textures);
   positions.assign(d.positions, d.positions + 3 * (size_t)d.vertexCount);
   normals.assign(d.normals, d.normals + 3 * (size_t)d.vertexCount);
   tangents.assign(d.tangents, d.tangents + 4 * (size_t)d.vertexCount);

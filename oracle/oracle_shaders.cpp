@@ -317,21 +317,56 @@ struct Ctx {
     return state;
   }
 
-  // ---- gltf_material.glsl:130-176 (texture taps are a later scope row) -------------------------
+  // textureLod(texturesMap[i], uv, 0)
+  vec4 textureLod(int i, vec2 uv) const {
+    if (i < 0 || (size_t)i >= sc.textures.size()) return vec4(1.0f);   // robustness: unbound slot reads the white default
+    return sc.textures[i].sample(uv);
+  }
+  // gltf_material.glsl:36-46 (SRGB_FAST_APPROXIMATION): pow(rgb, 2.2), alpha untouched
+  static vec4 SRGBtoLINEAR(vec4 c) { return vec4(eid_powf(c.x, 2.2f), eid_powf(c.y, 2.2f), eid_powf(c.z, 2.2f), c.w); }
+  // common.glsl:81-93
+  static void CreateCoordinateSystem(vec3 N, vec3& Nt, vec3& Nb) {
+    Nt = normalize((gabs(N.z) > 0.99999f) ? vec3(-N.x * N.y, 1.0f - N.y * N.y, -N.y * N.z) : vec3(-N.x * N.z, -N.y * N.z, 1.0f - N.z * N.z));
+    Nb = cross(Nt, N);
+  }
+  // ---- gltf_material.glsl:130-176 GetMaterials + GetMetallicRoughness :52-91 --------------------
   void GetMaterials(State& state, const Ray& r) {
     const GltfShadeMaterial& material = sc.shadeMaterials[state.matID];
+    mat3 TBN(state.tangent, state.bitangent, state.normal);
+    if (material.normalTexture > -1) {
+      vec3 normalVector = textureLod(material.normalTexture, state.texCoord).xyz();
+      normalVector = normalize(normalVector * 2.0f - 1.0f);
+      normalVector *= vec3(material.normalTextureScale, material.normalTextureScale, 1.0f);
+      state.normal = normalize(TBN * normalVector);
+      state.ffnormal = dot(state.normal, r.direction) <= 0.0f ? state.normal : -state.normal;
+      CreateCoordinateSystem(state.ffnormal, state.tangent, state.bitangent);
+    }
     state.mat.emission = V(material.emissiveFactor);
+    if (material.emissiveTexture > -1)
+      state.mat.emission *= SRGBtoLINEAR(textureLod(material.emissiveTexture, state.texCoord)).xyz();
     if ((state.mat.emission.x + state.mat.emission.y + state.mat.emission.z) > 1e-3f) state.isEmitter = true;
     else state.isEmitter = false;
     // GetMetallicRoughness (:52-91)
-    state.mat.albedo = vec3(material.pbrBaseColorFactor.x, material.pbrBaseColorFactor.y, material.pbrBaseColorFactor.z);
-    state.mat.metallic = material.pbrMetallicFactor;
-    state.mat.roughness = material.pbrRoughnessFactor;
+    float perceptualRoughness = material.pbrRoughnessFactor;
+    float metallic = material.pbrMetallicFactor;
+    if (material.pbrMetallicRoughnessTexture > -1) {
+      vec4 mrSample = textureLod(material.pbrMetallicRoughnessTexture, state.texCoord);
+      perceptualRoughness = mrSample.y * perceptualRoughness;
+      metallic = mrSample.z * metallic;
+    }
+    vec4 baseColor(material.pbrBaseColorFactor.x, material.pbrBaseColorFactor.y, material.pbrBaseColorFactor.z, material.pbrBaseColorFactor.w);
+    if (material.pbrBaseColorTexture > -1) {
+      vec4 t = SRGBtoLINEAR(textureLod(material.pbrBaseColorTexture, state.texCoord));
+      baseColor = vec4(baseColor.x * t.x, baseColor.y * t.y, baseColor.z * t.z, baseColor.w * t.w);
+    }
+    state.mat.albedo = baseColor.xyz();
+    state.mat.metallic = metallic;
+    state.mat.roughness = perceptualRoughness;
     state.mat.roughness = gmax(state.mat.roughness, 0.001f);
     state.mat.transmission = material.transmissionFactor;
+    if (material.transmissionTexture > -1) state.mat.transmission *= textureLod(material.transmissionTexture, state.texCoord).x;
     state.mat.ior = material.ior;
     state.eta = dot(state.normal, state.ffnormal) > 0.0f ? (1.0f / state.mat.ior) : state.mat.ior;
-    (void)r;
   }
 
   // ---- pathtrace.glsl ---------------------------------------------------------------------------
@@ -411,6 +446,7 @@ struct Ctx {
     vec3 emission = V(mat.emissiveFactor);
     pdf = luminance(emission) * rtxState.lightLuminIntegInv * lightProb;
     pdf *= dist * dist / absDot(state.ffnormal, dir);
+    if (mat.emissiveTexture > -1) emission *= SRGBtoLINEAR(textureLod(mat.emissiveTexture, state.texCoord)).xyz();
     return emission / state.area;
   }
   vec2 SampleTriangleUniform() {                                                              // :90-97
@@ -434,6 +470,11 @@ struct Ctx {
     vec3 y = (baryCoord.x * v0 + baryCoord.y * v1) + (1 - baryCoord.x - baryCoord.y) * v2;
     const GltfShadeMaterial& mat = sc.shadeMaterials[light.matIndex];
     vec3 emission = V(mat.emissiveFactor);
+    if (mat.emissiveTexture > -1) {
+      vec2 uv = (baryCoord.x * vec2(light.uv0.x, light.uv0.y) + baryCoord.y * vec2(light.uv1.x, light.uv1.y)) +
+                (1 - baryCoord.x - baryCoord.y) * vec2(light.uv2.x, light.uv2.y);
+      emission *= SRGBtoLINEAR(textureLod(mat.emissiveTexture, uv)).xyz();
+    }
     vec3 dir = y - x;
     float dist = length(dir);
     lightSample.Li = E(emission / area);

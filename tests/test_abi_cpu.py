@@ -175,8 +175,8 @@ def test_error_behaviour_host(tmp_path):
     arrays.indices[0] = 999                                                      # index out of range
     assert L.eid_scene_load_desc(s._h, C.byref(arrays.desc())) == -1
     tex = scenes.cube_scene()
-    tex.materials[0]["baseColorTexture"] = 0
-    assert L.eid_scene_load_desc(s._h, C.byref(tex.desc())) == -4                # EID_ERR_UNSUPPORTED (textures: later row)
+    tex.materials[0]["baseColorTexture"] = 3
+    assert L.eid_scene_load_desc(s._h, C.byref(tex.desc())) == -1                # texture index beyond the texture table
     blend = scenes.cube_scene()
     blend.materials[0]["alphaMode"] = 2
     blend.materials[0]["baseColorFactor"] = (1, 1, 1, 0.5)
@@ -263,3 +263,36 @@ def test_hdr_environment_tables_and_loader(tmp_path):
     bad.write_bytes(b"P6 not an hdr")
     assert L.eid_env_load_hdr(C.byref(h), -1, str(bad).encode()) == -3
     assert L.eid_env_create(C.byref(h), -1, None, 4, 4) == -1
+
+
+def test_texture_table_semantics(tmp_path):
+    """Scene::createTextureImages (scene.cpp:554-646): textured scene loads on the host path, tables match the oracle, a glTF
+    that references undecoded images is refused until the host provides them (no PNG/JPEG decoder in this build)."""
+    arrays = scenes.textured_scene()
+    o = ol.OracleScene()
+    o.load_arrays(arrays)
+    p = eid.Scene(device=-1)
+    p.load_arrays(arrays)
+    assert o.table(abi.TABLE_MATERIALS).tobytes() == p.table(abi.TABLE_MATERIALS).tobytes()
+    m = p.table(abi.TABLE_MATERIALS)
+    assert m["pbrBaseColorTexture"][0] == 0 and m["normalTexture"][0] == 2 and m["emissiveTexture"][4] == 3
+    # glTF with an external image: refused, then accepted once the decoded texels are provided
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "images": [{"uri": "albedo.png"}], "samplers": [{"magFilter": 9728, "wrapS": 33071}],
+           "textures": [{"source": 0, "sampler": 0}],
+           "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}]}
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes()
+    doc["meshes"] = [{"primitives": [{"attributes": {"POSITION": 0}, "material": 0}]}]
+    doc["accessors"] = [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}]
+    doc["bufferViews"] = [{"buffer": 0, "byteOffset": 0, "byteLength": 36}]
+    doc["buffers"] = [{"byteLength": 36, "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]
+    path = tmp_path / "tex.gltf"
+    path.write_text(json.dumps(doc))
+    s = eid.Scene(device=-1)
+    L = eid.lib()
+    assert L.eid_scene_load_gltf(s._h, str(path).encode()) == -4 and b"eid_scene_provide_image" in L.eid_last_error()
+    s.provide_image(0, np.full((4, 4, 4), 200, np.uint8))
+    s.load(str(path))
+    assert s.table(abi.TABLE_MATERIALS)["pbrBaseColorTexture"][0] == 0

@@ -149,6 +149,15 @@ def test_hdr_environment_default_state(maker, size):
     _run_frames(maker(), size, 2, "hdr-env no sun, prob 0.6", env_img=scenes.synthetic_sky(sun=False), environmentProb=0.6, hdrMultiplier=2.0)
 
 
+def test_textured_materials_normal_maps_and_textured_emitters():
+    """Scope row (f.1), texture half: every textureLod tap of GetMaterials / LightEval / SampleTriangleLight (base colour with
+    sRGB decode, metallic-roughness, normal map + tangent frame, emissive map, transmission map), NEAREST/LINEAR filters and
+    REPEAT / MIRRORED_REPEAT / CLAMP_TO_EDGE wrap modes, default-white fallbacks."""
+    worst = _run_frames(scenes.textured_scene(), (256, 160), 4, "textured")
+    assert max(worst.values()) == 0.0
+    _run_frames(scenes.textured_scene(), (160, 96), 2, "textured-env", env_img=scenes.synthetic_sky(), maxDepth=3)
+
+
 def test_c1_cube_direct_only():
     """BASELINE config 0: single cube, 256x256, RIS M=1, no denoise, direct only."""
     _run_frames(scenes.cube_scene(), (256, 256), 1, "C1", ReSTIRState=abi.eRIS, RISSampleNum=1, denoise=0)
