@@ -110,7 +110,7 @@ __global__ void k_emit_triangles(DeviceSceneView sc, const uint32_t* __restrict_
     triOut[3 * (size_t)t + 0] = make_float4(p[0].x, p[0].y, p[0].z, e1.x);
     triOut[3 * (size_t)t + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
     triOut[3 * (size_t)t + 2] = make_float4(e2.z, __int_as_float((int)prim), __int_as_float((int)a),
-                                            __uint_as_float(X.flags & (INST_CULL_DISABLE | INST_MIRROR)));
+                                            __uint_as_float(X.flags & (INST_CULL_DISABLE | INST_MIRROR | INST_FORCE_OPAQUE)));
     lo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); hi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x));
     lo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); hi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y));
     lo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z)); hi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
@@ -482,8 +482,6 @@ int eid_scene_create(eid_scene** out, int device) {
 
 static int finishLoad(eid_scene* s) {
   s->host.build();
-  if (s->host.hasNonOpaque)
-    raise(EID_ERR_UNSUPPORTED, "scene has alpha-tested/blended (non FORCE_OPAQUE) instances: stochastic alpha (traceray_rq.glsl:32-102) is not implemented yet");
   if (s->dev.device != EID_DEVICE_NONE) s->dev.upload(s->host);
   s->loaded = true;
   return EID_OK;

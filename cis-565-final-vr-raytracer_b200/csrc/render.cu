@@ -42,6 +42,7 @@ struct FrameParams {
   float4* geomPos; float4* geomNrm;       // denoiser geometry planes (full res): pos.xyz + hash bits / normal.xyz
   float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
   EnvView env;                            // HDR lat-long map + alias table, or the constant environment
+  int hasNonOpaque;                       // scene has alpha MASK / BLEND instances: ray queries run the stochastic HitTest loop
   int pitch, allocH;                      // allocation size of the 2-D images
   // rows owned by this rank: stripes k = 0..sCount-1 of sRows full-res rows starting at sFirst + k*sStride (all multiples of 16,
   // so no 8x8 quarter-res tile straddles two ranks).  Single GPU: one stripe covering the frame.
@@ -88,23 +89,62 @@ DEV float4 loadImg(const float4* img, const FrameParams& P, int x, int y) {
   return img[(size_t)y * P.pitch + x];
 }
 
-// ClosestHit (traceray_rq.glsl:108-147) on opaque geometry
+// HitTest (traceray_rq.glsl:32-102): stochastic alpha for a candidate of a non-FORCE_OPAQUE instance; exactly one draw
+DEV bool hitTest(const FrameParams& P, const RayHit& c, uint32_t& seed) {
+  const int customIndex = P.sc.instances[c.inst].primMesh;
+  const InstanceData gi = P.sc.geoInfo[customIndex];
+  const int mi = gi.materialIndex < 0 ? 0 : gi.materialIndex;
+  const float4* m = (const float4*)(P.sc.materials + mi);
+  const float4 q0 = __ldg(m), q1 = __ldg(m + 1), q4 = __ldg(m + 4);
+  float alpha = q0.w;
+  const int baseTex = __float_as_int(q1.x);
+  if (baseTex > -1) {
+    const uint32_t* idx = (const uint32_t*)(uintptr_t)gi.indexAddress + 3 * (size_t)c.prim;
+    const float4* vb = (const float4*)(uintptr_t)gi.vertexAddress;
+    const float4 a1 = __ldg(vb + 2 * (size_t)__ldg(idx) + 1), b1 = __ldg(vb + 2 * (size_t)__ldg(idx + 1) + 1), c1 = __ldg(vb + 2 * (size_t)__ldg(idx + 2) + 1);
+    const float bx = __fsub_rn(__fsub_rn(1.0f, c.u), c.v);
+    // raw texcoords, handedness bit included, exactly like the reference (traceray_rq.glsl:76-79)
+    const float tu = __fadd_rn(__fadd_rn(__fmul_rn(a1.x, bx), __fmul_rn(b1.x, c.u)), __fmul_rn(c1.x, c.v));
+    const float tv = __fadd_rn(__fadd_rn(__fmul_rn(a1.y, bx), __fmul_rn(b1.y, c.u)), __fmul_rn(c1.y, c.v));
+    alpha = __fmul_rn(alpha, textureLod0(P.sc, baseTex, tu, tv).w);
+  }
+  const float opacity = (__float_as_int(q4.y) == ALPHA_MASK) ? (alpha > q4.z ? 1.0f : 0.0f) : alpha;
+  return !(rnd(seed) > opacity);
+}
+
+// First accepted hit in front-to-back candidate order (t, instanceID, primitiveID): opaque candidates are accepted at once,
+// others go through HitTest; a rejected candidate becomes the exclusive lower bound of the next query.
 template <bool STATS>
-DEV bool closestHit(const FrameParams& P, f3 o, f3 d, Payload& prd, RayCounters& rc) {
+DEV bool firstAcceptedHit(const FrameParams& P, f3 o, f3 d, float tmax, uint32_t& seed, RayHit& h, RayCounters& rc) {
+  if (!traverse<false, STATS>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris)) return false;
+  while (!(h.flags & INST_FORCE_OPAQUE)) {
+    if (hitTest(P, h, seed)) return true;
+    const HitKey low = {h.t, h.inst, h.prim};
+    if (!traverse<false, STATS, true>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris, low)) return false;
+  }
+  return true;
+}
+
+// ClosestHit (traceray_rq.glsl:108-147).  FULL = the scene has non-opaque instances (alpha MASK / BLEND)
+template <bool STATS, bool FULL>
+DEV bool closestHit(const FrameParams& P, f3 o, f3 d, Payload& prd, uint32_t& seed, RayCounters& rc) {
   rc.closest++;
   RayHit h;
-  if (!traverse<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris)) { prd.hitT = EID_INFINITY; return false; }
+  const bool hit = (FULL && P.hasNonOpaque) ? firstAcceptedHit<STATS>(P, o, d, EID_INFINITY, seed, h, rc)
+                                            : traverse<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris);
+  if (!hit) { prd.hitT = EID_INFINITY; return false; }
   prd.hitT = h.t; prd.baryU = h.u; prd.baryV = h.v; prd.primitiveID = h.prim; prd.instanceID = h.inst;
   prd.instanceCustomIndex = P.sc.instances[h.inst].primMesh;
   return true;
 }
 // Occlusion (pathtrace.glsl:18-22) -> AnyHit (traceray_rq.glsl:153-185)
-template <bool STATS>
-DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float dist, RayCounters& rc) {
+template <bool STATS, bool FULL>
+DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float dist, uint32_t& seed, RayCounters& rc) {
   rc.any++;
   float tmax = __fsub_rn(__fsub_rn(__fsub_rn(dist, fabsf(__fsub_rn(origin.x, surfacePos.x))), fabsf(__fsub_rn(origin.y, surfacePos.y))),
                          fabsf(__fsub_rn(origin.z, surfacePos.z)));
   RayHit h;
+  if (FULL && P.hasNonOpaque) return firstAcceptedHit<STATS>(P, origin, dir, tmax, seed, h, rc);
   return traverse<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
 }
 
@@ -133,7 +173,7 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 // =================================================================================================
 // K1 — direct_stage.comp
 // =================================================================================================
-template <bool STATS>
+template <bool STATS, bool TEX>
 __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
@@ -146,14 +186,14 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     const size_t pix = (size_t)y * P.pitch + x;
     f3 radiance;
     Payload prd;
-    if (!closestHit<STATS>(P, ro, rd, prd, rc)) {                 // :154-158
+    if (!closestHit<STATS, TEX>(P, ro, rd, prd, seed, rc)) {                 // :154-158
       P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
       P.motion[pix] = make_short2(0, 0);
       radiance = envRadiance(P, rd);
     } else {
       rc.primary++;
-      State st = getState(P.sc, prd, rd);
-      getMaterials(P.sc, st, rd);
+      State st = getState<TEX>(P.sc, prd, rd);
+      getMaterials<TEX>(P.sc, st, rd);
       // createMotionIndex (:125-139)
       float pr[4];
       mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
@@ -182,20 +222,20 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
         const f3 shadowOrigin = offsetRay(st.position, st.ffnormal);
         if (P.st.ReSTIRState == eNone) {                   // DirectLight (pathtrace.glsl:204-220)
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-          float pdf = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
-          if (!isPdfInvalid(pdf) && !occlusion<STATS>(P, shadowOrigin, ls.wi, st.position, ls.dist, rc))
+          float pdf = sampleDirectLightNoVisibility<TEX>(P.sc, P.env, P.st, st.position, seed, ls);
+          if (!isPdfInvalid(pdf) && !occlusion<STATS, TEX>(P, shadowOrigin, ls.wi, st.position, ls.dist, seed, rc))
             direct = ((ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * gmax(dot3(st.ffnormal, ls.wi), 0.0f)) / pdf;
         } else {
           DResv resv; resv.Li = mk3(0.f); resv.wi = mk3(0.f); resv.dist = 0.f; resv.num = 0; resv.weight = 0.f;
           for (int i = 0; i < P.st.RISSampleNum; i++) {    // :188-199
             LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-            float p = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
+            float p = sampleDirectLightNoVisibility<TEX>(P.sc, P.env, P.st, st.position, seed, ls);
             f3 pHat = (ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * fabsf(dot3(st.ffnormal, ls.wi));
             float weight = lum3(pHat / p);
             if (isPdfInvalid(p) || weight != weight) weight = 0.0f;
             resvUpdate(resv, ls.Li, ls.wi, ls.dist, weight, rnd(seed));
           }
-          if (occlusion<STATS>(P, shadowOrigin, resv.wi, st.position, resv.dist, rc)) resv.weight = 0.0f;   // :200-207
+          if (occlusion<STATS, TEX>(P, shadowOrigin, resv.wi, st.position, resv.dist, seed, rc)) resv.weight = 0.0f;   // :200-207
 
           if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // :209-217, findTemporalNeighbor :47-84
             const float reprojDepth = len3(ld3(P.cam.lastPosition) - st.position);
@@ -258,7 +298,7 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
   p[16] = __uint_as_float(num); p[17] = weight; p[18] = bigW;
 }
 
-template <bool STATS>
+template <bool STATS, bool TEX>
 __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
   const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
@@ -311,9 +351,9 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         const f3 wo = -rayD;
         if (d > 1 && P.st.MIS > 0) {                        // SampleDirectLight (pathtrace.glsl:185-202)
           LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
-          float lightPdf = sampleDirectLightNoVisibility(P.sc, P.env, P.st, st.position, seed, ls);
+          float lightPdf = sampleDirectLightNoVisibility<TEX>(P.sc, P.env, P.st, st.position, seed, ls);
           if (!isPdfInvalid(lightPdf)) {
-            if (occlusion<STATS>(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, rc)) lightPdf = EID_INVALID_PDF;
+            if (occlusion<STATS, TEX>(P, offsetRay(st.position, st.ffnormal), ls.wi, st.position, ls.dist, seed, rc)) lightPdf = EID_INVALID_PDF;
           } else lightPdf = EID_INVALID_PDF;
           if (!isPdfInvalid(lightPdf)) {
             float bp = bsdfPdf(st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi);
@@ -335,7 +375,7 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         rayO = offsetRay(st.position, st.ffnormal);
         rayD = sampleWi;
         Payload prd;
-        closestHit<STATS>(P, rayO, rayD, prd, rc);
+        closestHit<STATS, TEX>(P, rayO, rayD, prd, seed, rc);
         if (prd.hitT >= __fsub_rn(EID_INFINITY, 1e-4f)) {   // miss (:183-198)
           if (d > 1) {
             const f3 env = envTextureDir(P.env, sampleWi);                    // EnvEval (pathtrace.glsl:60-72), HDR branch
@@ -347,8 +387,8 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
           }
           break;
         }
-        st = getState(P.sc, prd, rayD);
-        getMaterials(P.sc, st, rayD);
+        st = getState<TEX>(P.sc, prd, rayD);
+        getMaterials<TEX>(P.sc, st, rayD);
         if (st.isEmitter) {                                 // :203-215, LightEval (pathtrace.glsl:74-88)
           if (d > 1) {
             const float lightProb = __fsub_rn(1.0f, P.st.environmentProb);
@@ -641,6 +681,7 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
   P.env.tex = r->envMap ? r->envMap->tex : nullptr; P.env.accel = r->envMap ? r->envMap->accel : nullptr;
   P.env.width = r->envMap ? (int)r->envMap->host.width : 0; P.env.height = r->envMap ? (int)r->envMap->host.height : 0;
+  P.hasNonOpaque = r->scene->host.hasNonOpaque ? 1 : 0;
   P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.sFirst = (int)r->sFirst; P.sStride = (int)r->sStride; P.sRows = (int)r->sRows;
   P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
@@ -663,7 +704,10 @@ static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) 
   markStart(r, EID_K_DIRECT, st);
   if (P.sCount > 0) {
     dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
-    if (r->countVisits) k_direct_stage<true><<<g, b, 0, st>>>(P); else k_direct_stage<false><<<g, b, 0, st>>>(P);
+    // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
+    if (r->countVisits) { if (tex) k_direct_stage<true, true><<<g, b, 0, st>>>(P); else k_direct_stage<true, false><<<g, b, 0, st>>>(P); }
+    else { if (tex) k_direct_stage<false, true><<<g, b, 0, st>>>(P); else k_direct_stage<false, false><<<g, b, 0, st>>>(P); }
     r->stats.kernelLaunches[EID_K_DIRECT]++;
   }
   markStop(r, EID_K_DIRECT, st);
@@ -673,7 +717,9 @@ static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st
   markStart(r, EID_K_INDIRECT, st);
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
     dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
-    if (r->countVisits) k_indirect_stage<true><<<g, b, 0, st>>>(P); else k_indirect_stage<false><<<g, b, 0, st>>>(P);
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
+    if (r->countVisits) { if (tex) k_indirect_stage<true, true><<<g, b, 0, st>>>(P); else k_indirect_stage<true, false><<<g, b, 0, st>>>(P); }
+    else { if (tex) k_indirect_stage<false, true><<<g, b, 0, st>>>(P); else k_indirect_stage<false, false><<<g, b, 0, st>>>(P); }
     r->stats.kernelLaunches[EID_K_INDIRECT]++;
   }
   markStop(r, EID_K_INDIRECT, st);

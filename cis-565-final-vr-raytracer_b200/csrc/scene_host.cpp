@@ -79,9 +79,12 @@ static void buildTextureTable(const HostGltf& g, std::vector<TextureHost>& out, 
 void SceneHost::build() {
   const HostGltf& g = gltf;
   buildTextureTable(g, textures, texels);
+  hasTextures = false;
   for (const auto& m : g.materials)
-    for (int t : {m.baseColorTexture, m.metallicRoughnessTexture, m.emissiveTexture, m.normalTexture, m.transmissionTexture})
+    for (int t : {m.baseColorTexture, m.metallicRoughnessTexture, m.emissiveTexture, m.normalTexture, m.transmissionTexture}) {
       if (t >= (int)textures.size()) raise(EID_ERR_INVALID, "material references texture %d but only %zu exist", t, textures.size());
+      if (t > -1) hasTextures = true;
+    }
   // ---- materials (scene.cpp:415-448)
   materials.clear();
   for (const auto& m : g.materials) {

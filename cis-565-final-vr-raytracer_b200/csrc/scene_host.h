@@ -45,6 +45,7 @@ struct SceneHost {
   std::vector<InstanceXform> instances;
   uint64_t triangleInstances = 0;
   bool hasNonOpaque = false;
+  bool hasTextures = false;      // any material with a texture index > -1 (selects the texture-aware kernel variants)
 
   // camera (CameraManip state + Scene::m_camera)
   SceneCamera camera{};

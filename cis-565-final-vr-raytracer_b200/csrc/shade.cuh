@@ -222,6 +222,7 @@ struct Payload {       // PtPayload (globals.glsl:48-58) minus the matrices, whi
 };
 
 // shade_state.glsl:147-221 GetState (tangent frame is only needed by normal mapping: later scope row)
+template <bool TEX>
 DEV State getState(const DeviceSceneView& sc, const Payload& h, f3 rayDir) {
   State st;
   const InstanceXform& X = sc.instances[h.instanceID];
@@ -253,7 +254,7 @@ DEV State getState(const DeviceSceneView& sc, const Payload& h, f3 rayDir) {
   st.v = __fadd_rn(__fadd_rn(__fmul_rn(v0, bx), __fmul_rn(v1, by)), __fmul_rn(v2, bz));
 
   // Tangent and binormal (:194-204) feed only the TBN of normal mapping (gltf_material.glsl:135-146): evaluated on demand
-  if (__ldg(&sc.materials[st.matID].normalTexture) > -1) {
+  if (TEX && __ldg(&sc.materials[st.matID].normalTexture) > -1) {
     const float h0 = (__float_as_int(a1.y) & 1) == 1 ? 1.0f : -1.0f;
     const f3 t0 = octDecode(__float_as_uint(a1.z)), t1 = octDecode(__float_as_uint(b1.z)), t2 = octDecode(__float_as_uint(c1.z));
     f3 tangent = norm3((t0 * bx + t1 * by) + t2 * bz);
@@ -270,12 +271,13 @@ DEV State getState(const DeviceSceneView& sc, const Payload& h, f3 rayDir) {
 }
 
 // gltf_material.glsl:130-176 GetMaterials + GetMetallicRoughness :52-91
+template <bool TEX>
 DEV void getMaterials(const DeviceSceneView& sc, State& st, f3 rayDir) {
   const float4* m = (const float4*)(sc.materials + st.matID);   // 80 B = 5 x float4
   const float4 q0 = __ldg(m), q1 = __ldg(m + 1), q2 = __ldg(m + 2), q3 = __ldg(m + 3), q4 = __ldg(m + 4);
   const int baseTex = __float_as_int(q1.x), mrTex = __float_as_int(q1.w), emisTex = __float_as_int(q2.x);
   const int nrmTex = __float_as_int(q3.x), transTex = __float_as_int(q3.w);
-  if (nrmTex > -1) {                                    // :135-146 normal mapping
+  if (TEX && nrmTex > -1) {                             // :135-146 normal mapping
     const float4 t = textureLod0(sc, nrmTex, st.u, st.v);
     f3 nv = norm3(mk3(t.x, t.y, t.z) * 2.0f + (-1.0f));
     nv = nv * mk3(q3.y, q3.y, 1.0f);
@@ -285,20 +287,20 @@ DEV void getMaterials(const DeviceSceneView& sc, State& st, f3 rayDir) {
     createCoordinateSystem(st.ffnormal, st.tangent, st.bitangent);
   }
   st.mat.emission = mk3(q2.y, q2.z, q2.w);
-  if (emisTex > -1) st.mat.emission = st.mat.emission * srgbToLinear3(textureLod0(sc, emisTex, st.u, st.v));
+  if (TEX && emisTex > -1) st.mat.emission = st.mat.emission * srgbToLinear3(textureLod0(sc, emisTex, st.u, st.v));
   st.isEmitter = __fadd_rn(__fadd_rn(st.mat.emission.x, st.mat.emission.y), st.mat.emission.z) > 1e-3f;
   float roughness = q1.z, metallic = q1.y;
-  if (mrTex > -1) {
+  if (TEX && mrTex > -1) {
     const float4 t = textureLod0(sc, mrTex, st.u, st.v);
     roughness = __fmul_rn(t.y, roughness);
     metallic = __fmul_rn(t.z, metallic);
   }
   st.mat.albedo = mk3(q0.x, q0.y, q0.z);
-  if (baseTex > -1) st.mat.albedo = st.mat.albedo * srgbToLinear3(textureLod0(sc, baseTex, st.u, st.v));
+  if (TEX && baseTex > -1) st.mat.albedo = st.mat.albedo * srgbToLinear3(textureLod0(sc, baseTex, st.u, st.v));
   st.mat.metallic = metallic;
   st.mat.roughness = gmax(roughness, 0.001f);
   st.mat.transmission = q3.z;
-  if (transTex > -1) st.mat.transmission = __fmul_rn(st.mat.transmission, textureLod0(sc, transTex, st.u, st.v).x);
+  if (TEX && transTex > -1) st.mat.transmission = __fmul_rn(st.mat.transmission, textureLod0(sc, transTex, st.u, st.v).x);
   st.mat.ior = q4.x;
   st.eta = dot3(st.normal, st.ffnormal) > 0.0f ? __fdiv_rn(1.0f, st.mat.ior) : st.mat.ior;
 }
@@ -365,6 +367,7 @@ DEV bool isPdfInvalid(float p) { return p <= 1e-8f || p != p; }   // :14-16
 struct LightSampleD { f3 Li, wi; float dist; };
 
 // SampleTriangleLight :103-139 (+ SampleTriangleUniform :90-97): 4 draws
+template <bool TEX>
 DEV float sampleTriangleLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, LightSampleD& ls) {
   const uint32_t n = sc.lightBufInfo.trigLightSize;
   if (n == 0) return EID_INVALID_PDF;
@@ -385,7 +388,7 @@ DEV float sampleTriangleLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, L
   const f3 y = (bu * v0 + bv * v1) + __fsub_rn(__fsub_rn(1.0f, bu), bv) * v2;
   const float4 em = __ldg((const float4*)(sc.materials + matIndex) + 2);   // emissiveTexture, emissiveFactor.xyz
   f3 emission = mk3(em.y, em.z, em.w);
-  if (__float_as_int(em.x) > -1) {                       // :127-132 textured emitter: uv from the light's own uv0..2
+  if (TEX && __float_as_int(em.x) > -1) {                // :127-132 textured emitter: uv from the light's own uv0..2
     const float4 l3 = __ldg(L + 3);
     const float w2 = __fsub_rn(__fsub_rn(1.0f, bu), bv);
     const float tu = __fadd_rn(__fadd_rn(__fmul_rn(bu, l2.w), __fmul_rn(bv, l3.y)), __fmul_rn(w2, l3.w));
@@ -414,6 +417,7 @@ DEV float samplePuncLight(const DeviceSceneView& sc, f3 x, uint32_t& seed, Light
   return L.impSamp.pdf;
 }
 // SampleDirectLightNoVisibility :161-183
+template <bool TEX>
 DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const EnvView& env, const RtxState& rs, f3 pos, uint32_t& seed, LightSampleD& ls) {
   const float r = rnd(seed);
   const float envProb = rs.environmentProb;
@@ -427,7 +431,7 @@ DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const EnvView
   const float lightProb = __fsub_rn(1.0f, envProb);
   const float tsp = sc.lightBufInfo.trigSampProb;
   if (r < __fadd_rn(envProb, __fmul_rn(lightProb, tsp)))
-    return __fmul_rn(__fmul_rn(lightProb, sampleTriangleLight(sc, pos, seed, ls)), tsp);
+    return __fmul_rn(__fmul_rn(lightProb, sampleTriangleLight<TEX>(sc, pos, seed, ls)), tsp);
   return __fmul_rn(__fmul_rn(lightProb, samplePuncLight(sc, pos, seed, ls)), __fsub_rn(1.0f, tsp));
 }
 // clampRadiance :222-232

@@ -17,7 +17,11 @@ struct RayHit {
   float t, u, v;
   int tri;          // index into AccelView::tris, -1 = miss
   int prim, inst;
+  uint32_t flags;   // triangle flags of the hit (INST_FORCE_OPAQUE ...)
 };
+// Candidates are totally ordered by (t, instanceID, primitiveID).  LOWER traversals only accept candidates strictly after `low`:
+// the stochastic-alpha loop visits candidates front to back by re-querying with the last rejected candidate as the bound.
+struct HitKey { float t; int inst, prim; };
 
 #define EID_STACK_SIZE 128
 
@@ -63,9 +67,10 @@ DEV float boxEntry(const RayBox& rb, float lx, float ly, float lz, float hx, flo
 
 // ANY = true: terminate on the first accepted triangle (AnyHit); false: closest hit with tie-break.
 // STATS = true additionally counts inner-node visits and triangle tests (profiling builds of the kernels).
-template <bool ANY, bool STATS = false>
-DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsigned int* nodeVisits = nullptr, unsigned int* triTests = nullptr) {
-  hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f;
+template <bool ANY, bool STATS = false, bool LOWER = false>
+DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsigned int* nodeVisits = nullptr, unsigned int* triTests = nullptr,
+                  HitKey low = HitKey{0.f, 0, 0}) {
+  hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
   if (A.triCount == 0) return false;
   // a direction with NaN/zero length can never produce det != 0; skip the walk
   if (!(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) return false;
@@ -136,8 +141,9 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
         if (triangleTest(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), flags, o, d, tmax, t, u, v)) {
           if (ANY) { hit.t = t; hit.tri = (int)(first + k); return true; }
           const int prim = __float_as_int(c.y), inst = __float_as_int(c.z);
+          if (LOWER && (t < low.t || (t == low.t && (inst < low.inst || (inst == low.inst && prim <= low.prim))))) continue;
           bool better = t < hit.t || (t == hit.t && (inst < hit.inst || (inst == hit.inst && prim < hit.prim)));
-          if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; }
+          if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; hit.flags = flags; }
         }
       }
     }

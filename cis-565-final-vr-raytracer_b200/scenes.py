@@ -201,6 +201,42 @@ def textured_scene():
     return b.build(cam, "textured_box", images=images, textures=textures)
 
 
+def alpha_scene():
+    """textured_scene() plus alpha-tested (MASK, texture alpha) and blended (BLEND, factor + texture alpha) panes in front of the
+    boxes, one of them double sided: exercises HitTest (stochastic alpha) for primary, shadow and bounce rays."""
+    base = textured_scene()
+    b = _Builder()
+    rng = np.random.Generator(np.random.PCG64(77))
+    leaf = np.zeros((16, 16, 4), np.uint8)
+    leaf[..., :3] = (60, 170, 70)
+    yy, xx = np.mgrid[0:16, 0:16]
+    leaf[..., 3] = np.where(((xx - 8) ** 2 + (yy - 8) ** 2) < 40, 255, 0)      # disc cut-out
+    leaf[..., 3] = np.where(rng.random((16, 16)) < 0.1, 128, leaf[..., 3])
+    smoke = np.zeros((8, 8, 4), np.uint8)
+    smoke[..., :3] = (200, 200, 210)
+    smoke[..., 3] = rng.integers(30, 230, (8, 8))
+    images = list(base.images) + [leaf, smoke]
+    textures = list(base.textures) + [dict(image=5, magFilter=9728, minFilter=9728, wrapS=10497, wrapT=10497),   # 6: leaf, NEAREST
+                                      dict(image=6)]                                                              # 7: smoke, LINEAR
+    b.materials = list(base.materials)
+    mask = b.add_material(base=(1, 1, 1, 1), metallic=0.0, roughness=0.8, base_tex=6, alpha_mode=1, alpha_cutoff=0.5, double_sided=1)
+    blend = b.add_material(base=(0.9, 0.9, 1.0, 0.6), metallic=0.0, roughness=0.5, base_tex=7, alpha_mode=2)
+    blend_flat = b.add_material(base=(1.0, 0.8, 0.8, 0.35), metallic=0.0, roughness=0.9, alpha_mode=2, double_sided=1)
+    # panes between the camera and the boxes (camera looks down +z from z = -3.6)
+    b.add_quads([[(-0.9, 0.1, -0.7), (-0.9, 1.3, -0.7), (-0.1, 1.3, -0.7), (-0.1, 0.1, -0.7)]], mask)          # faces the camera (-z)
+    b.add_quads([[(0.1, 0.2, -0.8), (0.1, 1.0, -0.8), (0.85, 1.0, -0.8), (0.85, 0.2, -0.8)]], blend)
+    b.add_quads([[(-0.5, 1.4, -0.3), (0.5, 1.4, -0.3), (0.5, 1.4, 0.5), (-0.5, 1.4, 0.5)]], blend_flat)         # horizontal, under the lamp: shadow rays cross it
+    extra = b.build(base.camera, "alpha_box", images=images, textures=textures)
+    # merge: base geometry first, then the panes (vertex / index offsets shift)
+    nv, ni = base.positions.shape[0], base.indices.shape[0]
+    prims = list(base.prim_meshes) + [dict(p, firstIndex=p["firstIndex"] + ni, vertexOffset=p["vertexOffset"] + nv) for p in extra.prim_meshes]
+    nodes = list(base.nodes) + [dict(n, primMesh=n["primMesh"] + len(base.prim_meshes)) for n in extra.nodes]
+    cat = lambda a, c: np.concatenate([a, c])
+    return SceneArrays(cat(base.positions, extra.positions), cat(base.normals, extra.normals), cat(base.tangents, extra.tangents),
+                       cat(base.texcoords0, extra.texcoords0), cat(base.colors0, extra.colors0), cat(base.indices, extra.indices),
+                       prims, nodes, extra.materials, base.lights, base.camera, "alpha_box", images=images, textures=textures)
+
+
 def _value_noise(x, z, seed, octaves=4, base_cells=8):
     """Sum of `octaves` smooth value-noise layers over the unit square (x,z in [0,1])."""
     rng = np.random.Generator(np.random.PCG64(seed))

@@ -35,12 +35,15 @@ struct OTri {             // world-space triangle prepared for the intersector
   int prim, inst;         // primitiveID inside the prim mesh, instanceID (node index)
   int customIndex;        // prim mesh index
   int cullDisable;        // VK_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE (accelstruct.cpp:148-149)
+  int opaque;             // VK_GEOMETRY_INSTANCE_FORCE_OPAQUE (accelstruct.cpp:145-147)
   int flip;               // instance transform mirrors (det < 0): object-space facing is the opposite of world-space
 };
 
 struct Hit {
-  float hitT; int primitiveID, instanceID, instanceCustomIndex; vec2 bary;
+  float hitT; int primitiveID, instanceID, instanceCustomIndex; vec2 bary; int opaque;
 };
+// candidates are ordered by (t, instanceID, primitiveID); `after` = only candidates strictly greater than this key
+struct HitKey { float t; int inst, prim; };
 
 struct BvhNode { float lo[3], hi[3]; int left, right, first, count; };
 
@@ -92,7 +95,8 @@ struct Scene {
   void load(const eid_scene_desc& d);
   void updateCamera(uint32_t w, uint32_t h);
   void buildAccel();
-  Hit closestHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const;
+  Hit closestHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr, const HitKey* after = nullptr) const;
+  bool hasNonOpaque = false;
   bool anyHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const;
 };
 

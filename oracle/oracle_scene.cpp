@@ -330,7 +330,7 @@ void Scene::updateCamera(uint32_t w, uint32_t h) {
 
 // accelstruct.cpp:132-162 — one instance per node, world-space triangle soup
 void Scene::buildAccel() {
-  objectToWorld.clear(); worldToObject.clear(); tris.clear();
+  objectToWorld.clear(); worldToObject.clear(); tris.clear(); hasNonOpaque = false;
   for (int k = 0; k < 3; ++k) { bboxMin[k] = 1e30f; bboxMax[k] = -1e30f; }
   for (size_t n = 0; n < nodes.size(); ++n) {
     const auto& node = nodes[n];
@@ -356,6 +356,8 @@ void Scene::buildAccel() {
       tr.v0 = p[0]; tr.e1 = p[1] - p[0]; tr.e2 = p[2] - p[0];
       tr.prim = (int)(t / 3); tr.inst = (int)n; tr.customIndex = node.primMesh;
       tr.cullDisable = (mat.doubleSided == 1) ? 1 : 0;
+      tr.opaque = (mat.alphaMode == 0 || (mat.baseColorFactor[3] == 1.0f && mat.baseColorTexture == -1)) ? 1 : 0;   // accelstruct.cpp:145-147
+      if (!tr.opaque) hasNonOpaque = true;
       tr.flip = flip;
       tris.push_back(tr);
     }
@@ -404,16 +406,21 @@ static inline bool boxTest(const BvhNode& n, vec3 o, vec3 id, float tmax) {
   return tn <= tf * 1.0000004f + 1e-30f;
 }
 
-Hit Scene::closestHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr) const {
+Hit Scene::closestHit(vec3 o, vec3 d, float tmax, std::atomic<uint64_t>* ctr, const HitKey* after) const {
   if (ctr) ctr->fetch_add(1, std::memory_order_relaxed);
-  Hit h; h.hitT = tmax; h.primitiveID = h.instanceID = h.instanceCustomIndex = -1; h.bary = vec2(0, 0);
+  Hit h; h.hitT = tmax; h.primitiveID = h.instanceID = h.instanceCustomIndex = -1; h.bary = vec2(0, 0); h.opaque = 1;
   bool found = false;
   auto consider = [&](const OTri& T) {
     float t, u, v;
     // candidates at exactly the current best t must still be examined for the tie-break
     if (triTest(T, o, d, tmax, t, u, v)) {
+      if (after) {   // only candidates strictly after the key (t, inst, prim)
+        if (t < after->t) return;
+        if (t == after->t && (T.inst < after->inst || (T.inst == after->inst && T.prim <= after->prim))) return;
+      }
       if (!found || better(t, T.inst, T.prim, h)) {
         h.hitT = t; h.primitiveID = T.prim; h.instanceID = T.inst; h.instanceCustomIndex = T.customIndex; h.bary = vec2(u, v);
+        h.opaque = T.opaque;
         found = true;
       }
     }

@@ -253,11 +253,48 @@ struct Ctx {
     img[(size_t)c.y * pitch + c.x] = v;
   }
 
-  // ---- traceray_rq.glsl:108-147 (opaque geometry: HitTest never rejects, draws nothing) --------
+  // ---- traceray_rq.glsl:32-102 HitTest: stochastic alpha for candidates of non-FORCE_OPAQUE instances; one draw each ------
+  bool HitTest(const Hit& c) {
+    const uint matIndex = (uint)imax(0, sc.instMaterial[c.instanceCustomIndex]);
+    const GltfShadeMaterial& mat = sc.shadeMaterials[matIndex];
+    float baseColorAlpha = mat.pbrBaseColorFactor.w;
+    if (mat.pbrBaseColorTexture > -1) {
+      const auto& indices = sc.indexBufs[c.instanceCustomIndex];
+      const auto& vertices = sc.vertexBufs[c.instanceCustomIndex];
+      const VertexAttributes& a0 = vertices[indices[3 * c.primitiveID]];
+      const VertexAttributes& a1 = vertices[indices[3 * c.primitiveID + 1]];
+      const VertexAttributes& a2 = vertices[indices[3 * c.primitiveID + 2]];
+      const vec3 barycentrics = vec3(1.0f - c.bary.x - c.bary.y, c.bary.x, c.bary.y);
+      // (the reference interpolates the RAW texcoord here, handedness bit included: traceray_rq.glsl:76-79)
+      vec2 texcoord0 = (vec2(a0.texcoord.x, a0.texcoord.y) * barycentrics.x + vec2(a1.texcoord.x, a1.texcoord.y) * barycentrics.y) +
+                       vec2(a2.texcoord.x, a2.texcoord.y) * barycentrics.z;
+      baseColorAlpha *= textureLod(mat.pbrBaseColorTexture, texcoord0).w;
+    }
+    float opacity;
+    if (mat.alphaMode == ALPHA_MASK) opacity = baseColorAlpha > mat.alphaCutoff ? 1.0f : 0.0f;
+    else opacity = baseColorAlpha;
+    if (rand() > opacity) return false;
+    return true;
+  }
+  // Candidate order is implementation-defined in Vulkan; the contract fixes it to front-to-back:
+  // candidates are visited in increasing (t, instanceID, primitiveID) until one is opaque or passes HitTest.
+  bool firstAcceptedHit(const Ray& r, float tmax, Hit& out) {
+    HitKey key{-1.0f, -1, -1};
+    bool haveKey = false;
+    for (;;) {
+      Hit h = sc.closestHit(r.origin, r.direction, tmax, nullptr, haveKey ? &key : nullptr);
+      if (!(h.hitT < INFINITY_) || h.primitiveID < 0) return false;
+      if (h.opaque || HitTest(h)) { out = h; return true; }
+      key = HitKey{h.hitT, h.instanceID, h.primitiveID};
+      haveKey = true;
+    }
+  }
+  // ---- traceray_rq.glsl:108-147 ------------------------------------------------------------------
   void ClosestHit(const Ray& r) {
     prd.hitT = INFINITY_;
-    Hit h = sc.closestHit(r.origin, r.direction, INFINITY_, &rr.closestRays);
-    if (h.hitT < INFINITY_) {
+    rr.closestRays.fetch_add(1, std::memory_order_relaxed);
+    Hit h;
+    if (firstAcceptedHit(r, INFINITY_, h)) {
       prd.hitT = h.hitT; prd.primitiveID = h.primitiveID; prd.instanceID = h.instanceID;
       prd.instanceCustomIndex = h.instanceCustomIndex; prd.baryCoord = h.bary;
       prd.objectToWorld = sc.objectToWorld[h.instanceID];
@@ -265,7 +302,12 @@ struct Ctx {
     }
   }
   // ---- traceray_rq.glsl:153-185 ----------------------------------------------------------------
-  bool AnyHit(const Ray& r, float maxDist) { return sc.anyHit(r.origin, r.direction, maxDist, &rr.anyRays); }
+  bool AnyHit(const Ray& r, float maxDist) {
+    if (!sc.hasNonOpaque) return sc.anyHit(r.origin, r.direction, maxDist, &rr.anyRays);
+    rr.anyRays.fetch_add(1, std::memory_order_relaxed);
+    Hit h;
+    return firstAcceptedHit(r, maxDist, h);
+  }
 
   // ---- shade_state.glsl:147-221 ----------------------------------------------------------------
   State GetState(const PtPayload& hstate, vec3 rayDir) {

@@ -180,7 +180,7 @@ def test_error_behaviour_host(tmp_path):
     blend = scenes.cube_scene()
     blend.materials[0]["alphaMode"] = 2
     blend.materials[0]["baseColorFactor"] = (1, 1, 1, 0.5)
-    assert L.eid_scene_load_desc(s._h, C.byref(blend.desc())) == -4              # stochastic alpha: later row
+    assert L.eid_scene_load_desc(s._h, C.byref(blend.desc())) == 0               # BLEND instances load (stochastic alpha is implemented)
     assert L.eid_scene_table_bytes(None, 0, 0) == -1 and L.eid_renderer_buffer_bytes(None, 0) == -1
     assert L.eid_renderer_run(None, None, 0) == -1
 

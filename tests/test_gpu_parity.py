@@ -158,6 +158,14 @@ def test_textured_materials_normal_maps_and_textured_emitters():
     _run_frames(scenes.textured_scene(), (160, 96), 2, "textured-env", env_img=scenes.synthetic_sky(), maxDepth=3)
 
 
+def test_stochastic_alpha_mask_and_blend():
+    """Scope row (f.1), alpha half: HitTest (traceray_rq.glsl:32-102) on MASK / BLEND instances for primary, shadow and bounce
+    rays, with the candidate order pinned to front-to-back (t, instanceID, primitiveID); one RNG draw per tested candidate."""
+    worst = _run_frames(scenes.alpha_scene(), (256, 160), 4, "alpha")
+    assert max(worst.values()) == 0.0
+    _run_frames(scenes.alpha_scene(), (128, 96), 2, "alpha-eNone", ReSTIRState=abi.eNone, maxDepth=2)
+
+
 def test_c1_cube_direct_only():
     """BASELINE config 0: single cube, 256x256, RIS M=1, no denoise, direct only."""
     _run_frames(scenes.cube_scene(), (256, 256), 1, "C1", ReSTIRState=abi.eRIS, RISSampleNum=1, denoise=0)
