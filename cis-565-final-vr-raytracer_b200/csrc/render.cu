@@ -493,8 +493,8 @@ __global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int f
 
 // exp of the three edge-stopping weights.  STRICT: the bit-reproducible polynomial shared with the oracle (parity runs).
 // Fast (default): MUFU ex2 — relative error ~2^-21, far inside the 1e-3 radiance tolerance of the contract.
-template <bool STRICT> DEV float edgeExp(float num, float sigma, float negInvSigma) {
-  return STRICT ? eid_expf(__fdiv_rn(-num, sigma)) : __expf(num * negInvSigma);
+template <bool STRICT> DEV float edgeExp(float num, float sigma, float negLog2eOverSigma) {
+  return STRICT ? eid_expf(__fdiv_rn(-num, sigma)) : exp2f(num * negLog2eOverSigma);
 }
 
 template <bool INDIRECT, bool STRICT>
@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
   const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
   const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
   const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
-  const float nL = -1.0f / sigL, nN = -1.0f / sigN, nD = -1.0f / sigD;
+  const float LOG2E = 1.44269504088896341f;
+  const float nL = -LOG2E / sigL, nN = -LOG2E / sigN, nD = -LOG2E / sigD;   // fast path: exp(-d/sigma) = exp2(d * nX)
   const float4* __restrict__ gPos = INDIRECT ? P.geomPosH : P.geomPos;
   const float4* __restrict__ gNrm = INDIRECT ? P.geomNrmH : P.geomNrm;
   const int gp = INDIRECT ? P.pitch / 2 : P.pitch;
@@ -537,16 +538,32 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
         const float4 qn = __ldg(gNrm + (size_t)qy * gp + qx);
         const float4 q4 = inImg[(size_t)qy * P.pitch + qx];
         const f3 cq = mk3(q4.x, q4.y, q4.z);
-        float distColor;
-        if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
-        else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
-        const float wColor = __fadd_rn(edgeExp<STRICT>(distColor, sigL, nL), 1e-2f);
-        const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
-        const float wNorm = gmin(1.0f, edgeExp<STRICT>(dot3(dn, dn), sigN, nN));
-        const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
-        const float wDepth = __fadd_rn(edgeExp<STRICT>(dot3(dp, dp), sigD, nD), 1e-2f);
-        const float w = __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), c_gauss5x5[(i + 2) * 5 + (j + 2)]);
-        sum = sum + cq * w;
+        float w;
+        if (STRICT) {
+          float distColor;
+          if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
+          else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
+          const float wColor = __fadd_rn(edgeExp<true>(distColor, sigL, nL), 1e-2f);
+          const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
+          const float wNorm = gmin(1.0f, edgeExp<true>(dot3(dn, dn), sigN, nN));
+          const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
+          const float wDepth = __fadd_rn(edgeExp<true>(dot3(dp, dp), sigD, nD), 1e-2f);
+          w = __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), c_gauss5x5[(i + 2) * 5 + (j + 2)]);
+          sum = sum + cq * w;
+        } else {
+          // fast path (default): same formula with fused multiply-adds and ex2 on pre-scaled exponents (nL/nN/nD carry log2 e);
+          // deviates from the strict path by ~1e-6 relative, the contract allows 1e-3
+          float distColor;
+          if (INDIRECT) { const float dx = color.x - cq.x, dy = color.y - cq.y, dz = color.z - cq.z; distColor = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); }
+          else distColor = fabsf(lumC - fmaf(0.0722f, cq.z, fmaf(0.7152f, cq.y, 0.2126f * cq.x)));
+          const float wColor = exp2f(distColor * nL) + 1e-2f;
+          const float nx = norm.x - qn.x, ny = norm.y - qn.y, nz = norm.z - qn.z;
+          const float wNorm = fminf(1.0f, exp2f(fmaf(nz, nz, fmaf(ny, ny, nx * nx)) * nN));
+          const float px = pos.x - qp.x, py = pos.y - qp.y, pz = pos.z - qp.z;
+          const float wDepth = exp2f(fmaf(pz, pz, fmaf(py, py, px * px)) * nD) + 1e-2f;
+          w = wColor * wNorm * wDepth * c_gauss5x5[(i + 2) * 5 + (j + 2)];
+          sum = mk3(fmaf(cq.x, w, sum.x), fmaf(cq.y, w, sum.y), fmaf(cq.z, w, sum.z));
+        }
         sumW = __fadd_rn(sumW, w);
       }
     }
