@@ -492,18 +492,53 @@ __global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int f
 }
 
 // exp of the three edge-stopping weights.  STRICT: the bit-reproducible polynomial shared with the oracle (parity runs).
-// Fast (default): MUFU ex2 — relative error ~2^-21, far inside the 1e-3 radiance tolerance of the contract.
+// Fast (default): one MUFU ex2 on a pre-scaled exponent — relative error ~2^-21, far inside the 1e-3 radiance tolerance.
 template <bool STRICT> DEV float edgeExp(float num, float sigma, float negLog2eOverSigma) {
-  return STRICT ? eid_expf(__fdiv_rn(-num, sigma)) : exp2f(num * negLog2eOverSigma);
+  if (STRICT) return eid_expf(__fdiv_rn(-num, sigma));
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(num * negLog2eOverSigma));   // exponent <= 0: no range fix-up needed
+  return y;
 }
 
+// weight of one tap (denoise_direct.comp:40-62 / denoise_indirect.comp:44-66)
 template <bool INDIRECT, bool STRICT>
-__global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel,
-                                                 int first, int stride, int rows) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = stripeRow(first, stride, rows, 4);
-  const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
-  if (x >= bw || y >= bh || y < 0) return;
+DEV float tapWeight(const f3& color, float lumC, const f3& norm, const f3& pos, const float4& qp, const float4& qn, const f3& cq,
+                    float sigL, float sigN, float sigD, float nL, float nN, float nD, float gauss) {
+  if (STRICT) {
+    float distColor;
+    if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
+    else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
+    const float wColor = __fadd_rn(edgeExp<true>(distColor, sigL, nL), 1e-2f);
+    const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
+    const float wNorm = gmin(1.0f, edgeExp<true>(dot3(dn, dn), sigN, nN));
+    const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
+    const float wDepth = __fadd_rn(edgeExp<true>(dot3(dp, dp), sigD, nD), 1e-2f);
+    return __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), gauss);
+  } else {
+    // fast path (default): same formula with fused multiply-adds; deviates from the strict path by ~1e-6 relative
+    float distColor;
+    if (INDIRECT) { const float dx = color.x - cq.x, dy = color.y - cq.y, dz = color.z - cq.z; distColor = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); }
+    else distColor = fabsf(lumC - fmaf(0.0722f, cq.z, fmaf(0.7152f, cq.y, 0.2126f * cq.x)));
+    const float wColor = edgeExp<false>(distColor, sigL, nL) + 1e-2f;
+    const float nx = norm.x - qn.x, ny = norm.y - qn.y, nz = norm.z - qn.z;
+    const float wNorm = edgeExp<false>(fmaf(nz, nz, fmaf(ny, ny, nx * nx)), sigN, nN);   // <= 1 by construction: min(1, .) is the identity
+    const float px = pos.x - qp.x, py = pos.y - qp.y, pz = pos.z - qp.z;
+    const float wDepth = edgeExp<false>(fmaf(pz, pz, fmaf(py, py, px * px)), sigD, nD) + 1e-2f;
+    return (wColor * wNorm) * (wDepth * gauss);
+  }
+}
+
+// One A-Trous level.  A thread filters R pixels of one column that are `step` rows apart (the same phase of the dilated
+// lattice), so the 5 tap rows of neighbouring pixels overlap: R+4 tap rows are loaded for R pixels instead of 5R, every load
+// still a fully coalesced 16-B access along x.  Each pixel receives its taps in the reference's j-major / i-minor order, so
+// the sums are bit-identical for every R.  Virtual row v of a stripe of `rows` rows: phase p = v % step, chunk c = v / step
+// -> stripe rows p + (R c + k) step, k < R.
+// CHECK = false is the interior variant (block-uniform choice): every tap of every pixel of the block is inside the image,
+// so no bounds tests are emitted.  The fast path accumulates branch-free (mismatching taps get weight 0).
+template <bool INDIRECT, bool STRICT, int R, bool CHECK>
+DEV void atrousBody(const FrameParams& P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level, int lastLevel, int x, int y0,
+                    int lr0, int rows, int bw, int bh) {
+  const int step = 1 << level;
   const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
   const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
   const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
@@ -511,67 +546,104 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
   const float nL = -LOG2E / sigL, nN = -LOG2E / sigN, nD = -LOG2E / sigD;   // fast path: exp(-d/sigma) = exp2(d * nX)
   const float4* __restrict__ gPos = INDIRECT ? P.geomPosH : P.geomPos;
   const float4* __restrict__ gNrm = INDIRECT ? P.geomNrmH : P.geomNrm;
-  const int gp = INDIRECT ? P.pitch / 2 : P.pitch;
-  const float4 cp = __ldg(gPos + (size_t)y * gp + x);
-  const uint32_t matHash = __float_as_uint(cp.w);
-  f3 res = mk3(0.0f);
-  if (matHash != EID_INVALID_MAT) {                        // waveletFilter (denoise_direct.comp:19-71 / denoise_indirect.comp:23-75)
-    const float4 cn = __ldg(gNrm + (size_t)y * gp + x);
-    const f3 pos = mk3(cp.x, cp.y, cp.z), norm = mk3(cn.x, cn.y, cn.z);
-    const int step = 1 << level;
-    f3 sum = mk3(0.0f);
-    float sumW = 0.0f;
-    const float4 c4 = inImg[(size_t)y * P.pitch + x];
-    const f3 color = mk3(c4.x, c4.y, c4.z);
-    const float lumC = lum3(color);
+  const unsigned gp = INDIRECT ? P.pitch / 2 : P.pitch, ip = P.pitch;
+
+  f3 pos[R], norm[R], color[R], sum[R];
+  float lumC[R], sumW[R];
+  uint32_t hash[R];
+  bool inside[R];
 #pragma unroll
-    for (int j = -2; j <= 2; j++) {
-      const int qy = y + j * step;
-      if (qy >= bh || qy < 0) continue;
-#pragma unroll
-      for (int i = -2; i <= 2; i++) {
-        const int qx = x + i * step;
-        if (qx >= bw || qx < 0) continue;
-        const float4 qp = __ldg(gPos + (size_t)qy * gp + qx);
-        const uint32_t hq = __float_as_uint(qp.w);
-        if (matHash != hq) continue;                       // (hq == InvalidMatId implies the mismatch: matHash is valid here)
-        const float4 qn = __ldg(gNrm + (size_t)qy * gp + qx);
-        const float4 q4 = inImg[(size_t)qy * P.pitch + qx];
-        const f3 cq = mk3(q4.x, q4.y, q4.z);
-        float w;
-        if (STRICT) {
-          float distColor;
-          if (INDIRECT) { f3 dc = color - cq; distColor = dot3(dc, dc); }
-          else distColor = fabsf(__fsub_rn(lumC, lum3(cq)));
-          const float wColor = __fadd_rn(edgeExp<true>(distColor, sigL, nL), 1e-2f);
-          const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
-          const float wNorm = gmin(1.0f, edgeExp<true>(dot3(dn, dn), sigN, nN));
-          const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
-          const float wDepth = __fadd_rn(edgeExp<true>(dot3(dp, dp), sigD, nD), 1e-2f);
-          w = __fmul_rn(__fmul_rn(__fmul_rn(wColor, wNorm), wDepth), c_gauss5x5[(i + 2) * 5 + (j + 2)]);
-          sum = sum + cq * w;
-        } else {
-          // fast path (default): same formula with fused multiply-adds and ex2 on pre-scaled exponents (nL/nN/nD carry log2 e);
-          // deviates from the strict path by ~1e-6 relative, the contract allows 1e-3
-          float distColor;
-          if (INDIRECT) { const float dx = color.x - cq.x, dy = color.y - cq.y, dz = color.z - cq.z; distColor = fmaf(dz, dz, fmaf(dy, dy, dx * dx)); }
-          else distColor = fabsf(lumC - fmaf(0.0722f, cq.z, fmaf(0.7152f, cq.y, 0.2126f * cq.x)));
-          const float wColor = exp2f(distColor * nL) + 1e-2f;
-          const float nx = norm.x - qn.x, ny = norm.y - qn.y, nz = norm.z - qn.z;
-          const float wNorm = fminf(1.0f, exp2f(fmaf(nz, nz, fmaf(ny, ny, nx * nx)) * nN));
-          const float px = pos.x - qp.x, py = pos.y - qp.y, pz = pos.z - qp.z;
-          const float wDepth = exp2f(fmaf(pz, pz, fmaf(py, py, px * px)) * nD) + 1e-2f;
-          w = wColor * wNorm * wDepth * c_gauss5x5[(i + 2) * 5 + (j + 2)];
-          sum = mk3(fmaf(cq.x, w, sum.x), fmaf(cq.y, w, sum.y), fmaf(cq.z, w, sum.z));
-        }
-        sumW = __fadd_rn(sumW, w);
+  for (int k = 0; k < R; ++k) {
+    const int y = y0 + k * step;
+    inside[k] = !CHECK || ((lr0 + k * step < rows) && y >= 0 && y < bh);
+    hash[k] = EID_INVALID_MAT;
+    sum[k] = mk3(0.0f); sumW[k] = 0.0f;
+    pos[k] = norm[k] = color[k] = mk3(0.0f); lumC[k] = 0.0f;
+    if (inside[k]) {
+      const float4 cp = __ldg(gPos + ((unsigned)y * gp + (unsigned)x));
+      hash[k] = __float_as_uint(cp.w);
+      if (!STRICT || hash[k] != EID_INVALID_MAT) {
+        const float4 cn = __ldg(gNrm + ((unsigned)y * gp + (unsigned)x));
+        const float4 c4 = inImg[(unsigned)y * ip + (unsigned)x];
+        pos[k] = mk3(cp.x, cp.y, cp.z); norm[k] = mk3(cn.x, cn.y, cn.z); color[k] = mk3(c4.x, c4.y, c4.z);
+        lumC[k] = lum3(color[k]);
       }
     }
-    res = (sumW < 1e-5f) ? mk3(0.0f) : sum / sumW;
-    if (nan3(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = mk3(0.0f);
   }
-  if (level == lastLevel) res = ldrToHdr(res);             // denoise_direct.comp:168 / denoise_indirect.comp:169
-  outImg[(size_t)y * P.pitch + x] = make_float4(res.x, res.y, res.z, 1.0f);
+#pragma unroll
+  for (int rr = 0; rr < R + 4; ++rr) {                    // tap row rr serves pixel k as j = rr - 2 - k
+    const int qy = y0 + (rr - 2) * step;
+    if (CHECK && (qy >= bh || qy < 0)) continue;
+#pragma unroll
+    for (int i = -2; i <= 2; i++) {
+      const int qx = x + i * step;
+      if (CHECK && (qx >= bw || qx < 0)) continue;
+      const unsigned gi = (unsigned)qy * gp + (unsigned)qx, ii = (unsigned)qy * ip + (unsigned)qx;
+      const float4 qp = __ldg(gPos + gi);
+      const uint32_t hq = __float_as_uint(qp.w);
+      if (STRICT) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if (rr - 2 - k >= -2 && rr - 2 - k <= 2) any = any || (hash[k] == hq);
+        if (!any || hq == EID_INVALID_MAT) continue;
+      }
+      const float4 qn = __ldg(gNrm + gi);
+      const float4 q4 = inImg[ii];
+      const f3 cq = mk3(q4.x, q4.y, q4.z);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int j = rr - 2 - k;
+        if (j < -2 || j > 2) continue;
+        if (STRICT) {
+          if (hash[k] != hq) continue;
+          const float w = tapWeight<INDIRECT, true>(color[k], lumC[k], norm[k], pos[k], qp, qn, cq, sigL, sigN, sigD, nL, nN, nD,
+                                                    c_gauss5x5[(i + 2) * 5 + (j + 2)]);
+          sum[k] = sum[k] + cq * w;
+          sumW[k] = __fadd_rn(sumW[k], w);
+        } else {
+          float w = tapWeight<INDIRECT, false>(color[k], lumC[k], norm[k], pos[k], qp, qn, cq, sigL, sigN, sigD, nL, nN, nD,
+                                               c_gauss5x5[(i + 2) * 5 + (j + 2)]);
+          w = (hash[k] == hq) ? w : 0.0f;                 // (an invalid centre is zeroed below, whatever it accumulated)
+          sum[k] = mk3(fmaf(cq.x, w, sum[k].x), fmaf(cq.y, w, sum[k].y), fmaf(cq.z, w, sum[k].z));
+          sumW[k] += w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    if (!inside[k]) continue;
+    f3 res = mk3(0.0f);
+    if (hash[k] != EID_INVALID_MAT) {                      // waveletFilter (denoise_direct.comp:19-71 / denoise_indirect.comp:23-75)
+      res = (sumW[k] < 1e-5f) ? mk3(0.0f) : sum[k] / sumW[k];
+      if (nan3(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = mk3(0.0f);
+    }
+    if (level == lastLevel) res = ldrToHdr(res);           // denoise_direct.comp:168 / denoise_indirect.comp:169
+    outImg[(unsigned)(y0 + k * step) * ip + (unsigned)x] = make_float4(res.x, res.y, res.z, 1.0f);
+  }
+}
+
+template <bool INDIRECT, bool STRICT, int R>
+__global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int level,
+                                                 int lastLevel, int first, int stride, int rows) {
+  const int step = 1 << level;
+  const int vrows = step * ((((rows + step - 1) >> level) + R - 1) / R);
+  const int bps = (vrows + 3) / 4;
+  const int ks = blockIdx.y / bps, v0 = (blockIdx.y - ks * bps) * 4;
+  const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
+  const int x0 = blockIdx.x * 32, base = first + ks * stride;
+  // interior test over the whole block (4 virtual rows v0..v0+3, 32 columns): block-uniform
+  bool interior = x0 - 2 * step >= 0 && x0 + 31 + 2 * step < bw && v0 + 3 < vrows;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int v = v0 + t, lr = (v & (step - 1)) + ((v >> level) * R) * step;
+    interior = interior && lr + (R - 1) * step < rows && base + lr - 2 * step >= 0 && base + lr + (R + 1) * step < bh;
+  }
+  const int x = x0 + threadIdx.x, v = v0 + threadIdx.y;
+  const int lr0 = (v & (step - 1)) + ((v >> level) * R) * step;     // row of pixel 0 inside the stripe
+  if (interior) atrousBody<INDIRECT, STRICT, R, false>(P, inImg, outImg, level, lastLevel, x, base + lr0, lr0, rows, bw, bh);
+  else if (x < bw && v < vrows) atrousBody<INDIRECT, STRICT, R, true>(P, inImg, outImg, level, lastLevel, x, base + lr0, lr0, rows, bw, bh);
 }
 
 // =================================================================================================
@@ -616,6 +688,7 @@ struct eid_renderer {
   float4* directImg = nullptr; float4* indirectImg = nullptr;
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
+  int denoiseRowBlock = 2;    // pixels of one column filtered per thread in the A-Trous passes (1, 2 or 4; 2 measured fastest)
   bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
   unsigned long long* counters = nullptr;
   unsigned long long* countersHost = nullptr;   // pinned
@@ -758,6 +831,11 @@ static PostLayout postLayout(const FrameParams& P, bool sharded) {
 }
 static inline unsigned gridRows(const PostLayout& L, int rows, int bh) { return (unsigned)(L.count * ((rows + bh - 1) / bh)); }
 
+// one A-Trous level; `rowBlock` (default 4) selects the row-blocked kernel, 1 the one-pixel-per-thread kernel
+template <bool INDIRECT>
+static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
+                          const PostLayout& L, int first, int stride, int rows, cudaStream_t st);
+
 // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4; accounted to the direct denoiser
 static void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
   if (P.st.denoise <= 0 || L.count <= 0) return;
@@ -765,6 +843,22 @@ static void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L
   dim3 b(32, 8), g((W + 31) / 32, gridRows(L, rows, 8));
   k_denoise_prep<<<g, b, 0, st>>>(P, L.first - 124, L.stride, rows);
   r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
+}
+
+template <bool INDIRECT, int R>
+static void launchDenoiseR(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
+                           const PostLayout& L, int first, int stride, int rows, cudaStream_t st) {
+  const int step = 1 << level, vrows = step * ((((rows + step - 1) >> level) + R - 1) / R);
+  dim3 b(32, 4), g((width + 31) / 32, gridRows(L, vrows, 4));
+  if (r->strictMath) k_denoise<INDIRECT, true, R><<<g, b, 0, st>>>(P, src, dst, level, lastLevel, first, stride, rows);
+  else k_denoise<INDIRECT, false, R><<<g, b, 0, st>>>(P, src, dst, level, lastLevel, first, stride, rows);
+}
+template <bool INDIRECT>
+static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
+                          const PostLayout& L, int first, int stride, int rows, cudaStream_t st) {
+  if (r->denoiseRowBlock == 4) launchDenoiseR<INDIRECT, 4>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
+  else if (r->denoiseRowBlock == 2) launchDenoiseR<INDIRECT, 2>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
+  else launchDenoiseR<INDIRECT, 1>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
 }
 
 static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
@@ -775,9 +869,7 @@ static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const Post
     const int halo[4] = {28, 24, 16, 0};
     for (int i = 0; i < 4; ++i) {
       const int h = L.sharded ? halo[i] : 0, rows = L.srows + 2 * h;
-      dim3 b(32, 4), g((W + 31) / 32, gridRows(L, rows, 4));
-      if (r->strictMath) k_denoise<false, true><<<g, b, 0, st>>>(P, src[i], dst[i], i, 3, L.first - h, L.stride, rows);
-      else k_denoise<false, false><<<g, b, 0, st>>>(P, src[i], dst[i], i, 3, L.first - h, L.stride, rows);
+      launchDenoise<false>(r, P, src[i], dst[i], i, 3, W, L, L.first - h, L.stride, rows, st);
       r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
     }
   }
@@ -791,9 +883,7 @@ static void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const Po
     const int halo[5] = {60, 56, 48, 32, 0};
     for (int i = 0; i < 5; ++i) {
       const int h = L.sharded ? halo[i] : 0, rows = L.srows / 2 + 2 * h;
-      dim3 b(32, 4), g((Wi + 31) / 32, gridRows(L, rows, 4));
-      if (r->strictMath) k_denoise<true, true><<<g, b, 0, st>>>(P, src[i], dst[i], i, 4, L.first / 2 - h, L.stride / 2, rows);
-      else k_denoise<true, false><<<g, b, 0, st>>>(P, src[i], dst[i], i, 4, L.first / 2 - h, L.stride / 2, rows);
+      launchDenoise<true>(r, P, src[i], dst[i], i, 4, Wi, L, L.first / 2 - h, L.stride / 2, rows, st);
       r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
     }
   }
@@ -1215,6 +1305,15 @@ int eid_renderer_set_strict_math(eid_renderer* r, int enabled) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_strict_math: null renderer");
   r->strictMath = enabled != 0;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: null renderer");
+  if (rowsPerThread != 1 && rowsPerThread != 2 && rowsPerThread != 4) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: 1, 2 or 4");
+  r->denoiseRowBlock = rowsPerThread;
   return EID_OK;
   EID_CATCH
 }

@@ -268,6 +268,10 @@ EID_API int  eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]);
  * the bit-reproducible path.  1: the deterministic polynomial exp shared with the CPU oracle — every buffer of a frame is then
  * bit-identical to the oracle's (used by the parity tests).  G-buffer, motion indices and reservoirs never depend on this. */
 EID_API int  eid_renderer_set_strict_math(eid_renderer* r, int enabled);
+/* A-Trous kernel shape: every thread filters `rowsPerThread` pixels of one column that are 2^level rows apart and shares their
+ * overlapping tap rows: 1 = 25 loads per pixel, 2 (default, measured fastest on B200) = 15, 4 = 10 but 110 registers.
+ * Results are bit-identical for every setting. */
+EID_API int  eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread);
 /* Renderer::run(cmdBuf, state, profiler, descSets, frames) (renderer.cpp:154-206): enqueues
  * direct_stage, indirect_stage, denoise_direct x4, denoise_indirect x5, compose and returns.
  * `frames` selects the ping-pong set exactly as (frames+1)%2 (renderer.cpp:157). */

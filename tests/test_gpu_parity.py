@@ -140,6 +140,28 @@ def test_fast_math_denoiser_within_tolerance():
     assert worst["direct_resv.weight"] == 0.0 and worst["indirect_resv.weight"] == 0.0 and worst["indirect_resv.L"] == 0.0
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("size", [(256, 144), (130, 70), (64, 2)])
+def test_row_blocked_denoiser_equals_per_pixel_kernel(strict, size):
+    """The default A-Trous kernel filters 4 pixels of one column per thread (shared tap rows); every pixel still receives its
+    taps in the reference's order, so it must be BIT-identical to the one-pixel-per-thread kernel in both numerics modes."""
+    arrays = scenes.small_room()
+    snaps = []
+    for rows in (4, 2, 1):
+        osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict)
+        prr.set_denoise_rows(rows)
+        psc.update_camera(*size)
+        for f in range(3):
+            psc.update_camera(*size)
+            prr.run(common.frame_state(size[0], size[1], psc.info(), f), f)
+        prr.sync()
+        snaps.append(common.snapshot(prr))
+    for name in ("direct", "indirect", "ind_tmp_a", "ind_tmp_b"):
+        assert snaps[0][name].tobytes() == snaps[2][name].tobytes() and snaps[1][name].tobytes() == snaps[2][name].tobytes(), name
+    with pytest.raises(eid.EidolaError):
+        prr.set_denoise_rows(3)
+
+
 @pytest.mark.parametrize("maker,size", [(scenes.cube_scene, (192, 192)), (scenes.cornell_scene, (224, 128))])
 def test_hdr_environment_default_state(maker, size):
     """Scope row (f.2): HDR environment importance sampling with the reference's DEFAULT RtxState (environmentProb 0.25):
