@@ -344,6 +344,8 @@ __global__ void k_trace_batch(AccelView A, const InstanceXform* __restrict__ ins
 static void buildAccel(eid_scene* s, eid_accel* a) {
   const SceneHost& H = s->host;
   CUDA_CHECK(cudaSetDevice(s->dev.device));
+  // leaf references carry (firstTriangle << 3 | count) in 31 bits, and 0x80000000 is the traversal's "done" sentinel
+  if (H.triangleInstances >= (1ull << 28) - 8) raise(EID_ERR_UNSUPPORTED, "eid_accel_build: more than 2^28 - 8 triangle instances");
   const uint32_t nTri = (uint32_t)H.triangleInstances;
   a->scene = s; a->triCount = nTri;
   cudaEvent_t ev0, ev1;

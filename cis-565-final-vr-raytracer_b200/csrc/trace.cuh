@@ -79,8 +79,12 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
   int sp = 0;
   int cur = A.rootRef;
   const float INF = __int_as_float(0x7f800000);
+  const int DONE = (int)0x80000000;            // never a valid reference (it would be a leaf starting at triangle 2^28 - 1)
+#define EID_POP() (sp ? stack[--sp] : DONE)
+  // "while-while" walk: every lane first descends inner nodes until it holds a leaf (or is done); the warp then reconverges
+  // and intersects leaves together.  In the interleaved form the triangle tests ran with ~5 of 32 lanes active (ncu source page).
   for (;;) {
-    if (cur >= 0) {
+    while (cur >= 0) {
 #if EID_BVH_WIDTH == 2
       const float4* n = A.nodes + 4 * (size_t)cur;
       if (STATS) ++*nodeVisits;
@@ -93,10 +97,9 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
         if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
         if (sp < EID_STACK_SIZE) stack[sp++] = c1;
         cur = c0;
-        continue;
-      }
-      if (h0) { cur = c0; continue; }
-      if (h1) { cur = c1; continue; }
+      } else if (h0) cur = c0;
+      else if (h1) cur = c1;
+      else cur = EID_POP();
 #else
       const float4* n = A.nodes + 8 * (size_t)cur;
       if (STATS) ++*nodeVisits;
@@ -114,7 +117,7 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
         if (e1 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c1; } else { next = c1; have = true; } }
         if (e2 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c2; } else { next = c2; have = true; } }
         if (e3 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c3; } else { next = c3; have = true; } }
-        if (have) { cur = next; continue; }
+        cur = have ? next : EID_POP();
       } else {
         // sort the four (entry distance, ref) pairs ascending: 5-comparator network
 #define EID_CSWAP(ea, ca, eb, cb) { if (eb < ea) { float te = ea; ea = eb; eb = te; int tc = ca; ca = cb; cb = tc; } }
@@ -125,11 +128,12 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
           if (e2 < INF && sp < EID_STACK_SIZE) stack[sp++] = c2;
           if (e1 < INF && sp < EID_STACK_SIZE) stack[sp++] = c1;
           cur = c0;
-          continue;
-        }
+        } else cur = EID_POP();
       }
 #endif
-    } else {
+    }
+    if (cur == DONE) break;
+    {
       const uint32_t ref = ~(uint32_t)cur;
       const uint32_t first = ref >> 3, count = ref & 7u;
       for (uint32_t k = 0; k < count; ++k) {
@@ -147,9 +151,9 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
         }
       }
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
+    cur = EID_POP();
   }
+#undef EID_POP
   return hit.tri >= 0;
 }
 
