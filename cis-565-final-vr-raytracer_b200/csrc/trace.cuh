@@ -27,6 +27,21 @@ struct HitKey { float t; int inst, prim; };
 
 // returns true and fills t,u,v when the ray hits triangle (v0,e1,e2) inside (0, tmax)
 DEV bool triangleTest(f3 v0, f3 e1, f3 e2, uint32_t flags, f3 o, f3 d, float tmax, float& t, float& u, float& v) {
+#ifndef EID_TRI_EARLYOUT
+  // every quantity evaluated, one combined accept predicate: the same booleans as the early-out form below (a rejected
+  // candidate's u, v, t are never used), without the four divergence points inside the leaf loop
+  const f3 pvec = cross3(d, e2);
+  const float det = dot3(e1, pvec);
+  const float fd = (flags & INST_MIRROR) ? -det : det;
+  const bool okDet = (flags & INST_CULL_DISABLE) ? (det != 0.0f) : (fd > 0.0f);
+  const float inv = __fdiv_rn(1.0f, det);
+  const f3 tvec = o - v0;
+  u = __fmul_rn(dot3(tvec, pvec), inv);
+  const f3 qvec = cross3(tvec, e1);
+  v = __fmul_rn(dot3(d, qvec), inv);
+  t = __fmul_rn(dot3(e2, qvec), inv);
+  return okDet && (u >= 0.0f && u <= 1.0f) && (v >= 0.0f && __fadd_rn(u, v) <= 1.0f) && (t > 0.0f && t < tmax);
+#else
   f3 pvec = cross3(d, e2);
   float det = dot3(e1, pvec);
   if (flags & INST_CULL_DISABLE) { if (det == 0.0f) return false; }
@@ -40,6 +55,7 @@ DEV bool triangleTest(f3 v0, f3 e1, f3 e2, uint32_t flags, f3 o, f3 d, float tma
   if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return false;
   t = __fmul_rn(dot3(e2, qvec), inv);
   return t > 0.0f && t < tmax;
+#endif
 }
 
 struct RayBox {   // per-ray constants of the slab test
