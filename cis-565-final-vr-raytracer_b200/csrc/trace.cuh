@@ -60,6 +60,8 @@ DEV bool triangleTest(f3 v0, f3 e1, f3 e2, uint32_t flags, f3 o, f3 d, float tma
 
 struct RayBox {   // per-ray constants of the slab test
   float ix, iy, iz, ox, oy, oz;   // 1/d and o/d
+  int nx, ny, nz;                 // BVH4 node: float4 index of the NEAR plane per axis (0..2 = lo x/y/z, 3..5 = hi x/y/z); far = near ^ 3 ...
+  int fx, fy, fz;                 // ... kept explicit: {0,3} {1,4} {2,5}
 };
 DEV RayBox makeRayBox(f3 o, f3 d) {
   const float tiny = 1e-20f;
@@ -69,6 +71,9 @@ DEV RayBox makeRayBox(f3 o, f3 d) {
   RayBox r;
   r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
   r.ox = o.x * r.ix; r.oy = o.y * r.iy; r.oz = o.z * r.iz;
+  r.nx = r.ix < 0.0f ? 3 : 0; r.fx = 3 - r.nx;
+  r.ny = r.iy < 0.0f ? 4 : 1; r.fy = 5 - r.ny;
+  r.nz = r.iz < 0.0f ? 5 : 2; r.fz = 7 - r.nz;
   return r;
 }
 // entry distance of the slab intersection, or +inf when the box is missed within [0, tbest]
@@ -78,6 +83,13 @@ DEV float boxEntry(const RayBox& rb, float lx, float ly, float lz, float hx, flo
   float z0 = fmaf(lz, rb.iz, -rb.oz), z1 = fmaf(hz, rb.iz, -rb.oz);
   float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
   float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tbest));
+  return (tn <= tf * 1.0000004f) ? tn : __int_as_float(0x7f800000);
+}
+// the same test with the near / far plane of each axis already selected by the ray's direction signs (the BVH4 walk picks the
+// float4 it loads by address, so the six min/max of the generic form disappear)
+DEV float boxEntryNF(const RayBox& rb, float nx, float ny, float nz, float fx, float fy, float fz, float tbest) {
+  const float tn = fmaxf(fmaxf(fmaf(nx, rb.ix, -rb.ox), fmaf(ny, rb.iy, -rb.oy)), fmaxf(fmaf(nz, rb.iz, -rb.oz), 0.0f));
+  const float tf = fminf(fminf(fmaf(fx, rb.ix, -rb.ox), fmaf(fy, rb.iy, -rb.oy)), fminf(fmaf(fz, rb.iz, -rb.oz), tbest));
   return (tn <= tf * 1.0000004f) ? tn : __int_as_float(0x7f800000);
 }
 
@@ -119,12 +131,13 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
 #else
       const float4* n = A.nodes + 8 * (size_t)cur;
       if (STATS) ++*nodeVisits;
-      const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2), hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
+      const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);   // near planes of the 4 children
+      const float4 hx = __ldg(n + rb.fx), hy = __ldg(n + rb.fy), hz = __ldg(n + rb.fz);   // far planes
       const float4 rf = __ldg(n + 6);
-      float e0 = boxEntry(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, hit.t);
-      float e1 = boxEntry(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, hit.t);
-      float e2 = boxEntry(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, hit.t);
-      float e3 = boxEntry(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, hit.t);
+      float e0 = boxEntryNF(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, hit.t);
+      float e1 = boxEntryNF(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, hit.t);
+      float e2 = boxEntryNF(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, hit.t);
+      float e3 = boxEntryNF(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, hit.t);
       int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
       if (ANY) {
         // occlusion rays: order is irrelevant, just visit every child the ray enters
