@@ -451,6 +451,21 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
   }
   freeAll();
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+#if EID_FETCH_TEX
+  int maxLinear = 0;
+  CUDA_CHECK(cudaDeviceGetAttribute(&maxLinear, cudaDevAttrMaxTexture1DLinearWidth, s->dev.device));
+  auto mkTex = [&](const float4* p, size_t count) {
+    if (count > (size_t)maxLinear) raise(EID_ERR_UNSUPPORTED, "eid_accel_build: BVH array of %zu float4 exceeds the linear-texture limit (%d)", count, maxLinear);
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = (void*)p;
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = std::max<size_t>(count, 1) * 16;
+    cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t t = 0;
+    CUDA_CHECK(cudaCreateTextureObject(&t, &rd, &td, nullptr));
+    return t;
+  };
+  a->nodeTex = mkTex(a->nodes, (size_t)std::max(a->nodeAlloc, 1u) * (EID_NODE_BYTES / 16));
+  a->triTex = mkTex(a->tris, (size_t)std::max(nTri, 1u) * 3);
+#endif
 }
 
 }  // namespace eid
@@ -656,6 +671,8 @@ int eid_accel_build(eid_scene* s, eid_accel** out) {
 
 void eid_accel_destroy(eid_accel* a) {
   if (!a) return;
+  if (a->nodeTex) cudaDestroyTextureObject(a->nodeTex);
+  if (a->triTex) cudaDestroyTextureObject(a->triTex);
   cudaFree(a->nodes); cudaFree(a->tris);
   delete a;
 }

@@ -38,6 +38,7 @@ struct AccelView {
   const float4* tris;
   uint32_t triCount;
   int32_t rootRef;      // child-style reference of the root
+  cudaTextureObject_t nodeTex, triTex;   // the same two arrays as linear float4 textures (TEX-pipe fetch experiments, EID_FETCH_TEX)
 };
 
 struct SceneDevice {
@@ -76,5 +77,6 @@ struct eid_accel {
   uint32_t maxDepth = 0;
   int32_t rootRef = -1;
   float buildMs = 0.f;
-  eid::AccelView view() const { return eid::AccelView{nodes, tris, triCount, rootRef}; }
+  cudaTextureObject_t nodeTex = 0, triTex = 0;
+  eid::AccelView view() const { return eid::AccelView{nodes, tris, triCount, rootRef, nodeTex, triTex}; }
 };

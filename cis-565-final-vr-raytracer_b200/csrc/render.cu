@@ -28,6 +28,26 @@ namespace eid {
 #define EID_K2_MIN_BLOCKS 16
 #endif
 
+// Scratch of the wavefront form of K2 (k_gi_begin / k_trace_queue / k_gi_bounce / k_gi_finish): one slot per thread of the K2
+// launch grid (8x8 tiles of quarter-res pixels), planes of float4 indexed by slot; ray queues are compact (filled through counters).
+struct WaveView {
+  uint32_t slots;          // capacity of every per-slot plane and of every queue
+  float4* rayQ[2];         // closest-hit queue, ping-pong by depth parity; entry = (origin.xyz, samplePdf), (direction.xyz, slot bits)
+  float4* hitQ;            // result of queue entry j: (hitT, baryU, baryV, triangle index bits; -1 = miss)
+  uint4* misc;             // per slot: RNG state, flags (GI_* bits), -, -
+  float4* thr;             // per slot: path throughput
+  float4* gsXv; float4* gsNv; float4* gsXs; float4* gsNs;   // GISample: (xv, primSamplePdf), nv, xs, ns
+  float4* hitL;            // radiance added by the path's terminal emitter hit / environment miss (depth >= 2)
+  float4* neeTerm;         // [k * slots + slot]: next-event-estimation term of depth k + 2 (added iff its shadow ray is unoccluded)
+  float4* shadowQ;         // any-hit queue of all depths; entry = (origin.xyz, tmax), (direction.xyz, id = k * slots + slot)
+  uint32_t* occl;          // [id]: 1 = shadow ray occluded
+  uint32_t* ctr;           // [p] entries of the depth-p closest-hit queue (p >= 1), [0] entries of the shadow queue, [64 + i] fetch cursors
+};
+#define GI_MULTIBOUNCE 1u
+#define GI_HITL 2u
+#define GI_NEE_SHIFT 8
+#define GI_MAX_WAVE_DEPTH 25   // flag bits 8..31 hold the NEE terms of depths 2..25
+
 struct FrameParams {
   RtxState st;
   SceneCamera cam;
@@ -47,6 +67,7 @@ struct FrameParams {
   // rows owned by this rank: stripes k = 0..sCount-1 of sRows full-res rows starting at sFirst + k*sStride (all multiples of 16,
   // so no 8x8 quarter-res tile straddles two ranks).  Single GPU: one stripe covering the frame.
   int sFirst, sStride, sRows, sCount;
+  WaveView wv;
   unsigned long long* counters;           // per frame: [0] closest-hit rays, [1] any-hit rays, [2] primary hits, [3] inner-node
                                           // visits, [4] triangle tests (STATS kernels only); since creation: [5] closest, [6] any
 };
@@ -298,6 +319,77 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
   p[16] = __uint_as_float(num); p[17] = weight; p[18] = bigW;
 }
 
+// State of the primary surface rebuilt from the G-buffer texel of full-res pixel 2*coord (getIndirectStateFromGBuffer,
+// pathtrace.glsl:296-313) with the +2e-2 push along ffnormal (indirect_stage.comp:299).  false = sky pixel.
+struct GIPrimary { f3 ro, rd; State st; };
+DEV bool giPrimary(const FrameParams& P, int x, int y, int Wi, int Hi, GIPrimary& pr) {
+  raySpawn<true>(P.cam, x, y, Wi, Hi, pr.ro, pr.rd);
+  const uint4 gi = loadG(P.thisG, P, 2 * x, 2 * y);
+  const float depth = __uint_as_float(gi.x);
+  if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) return false;
+  State& st = pr.st;
+  st.position = pr.ro + pr.rd * depth;
+  st.normal = octDecode(gi.y);
+  st.ffnormal = dot3(st.normal, pr.rd) <= 0.0f ? st.normal : -st.normal;
+  st.mat.albedo = mk3(unormToFloat(gi.w & 0xffu), unormToFloat((gi.w >> 8) & 0xffu), unormToFloat((gi.w >> 16) & 0xffu));
+  st.mat.metallic = unormToFloat(gi.z & 0xffu);
+  st.mat.roughness = unormToFloat((gi.z >> 8) & 0xffu);
+  st.mat.ior = __fadd_rn(__fmul_rn(unormToFloat((gi.z >> 16) & 0xffu), MAX_IOR_MINUS_ONE), 1.f);
+  st.mat.transmission = unormToFloat(gi.z >> 24);
+  st.mat.emission = mk3(0.f);
+  st.matID = gi.w >> 24;                                // hashed material id
+  st.isEmitter = false; st.area = 0.f; st.eta = 0.f; st.u = st.v = 0.f;
+  st.tangent = mk3(0.f); st.bitangent = mk3(0.f);
+  st.position = st.position + st.ffnormal * 2e-2f;      // :299
+  return true;
+}
+
+// ReSTIRIndirect (indirect_stage.comp:228-268) + the tail of main (:296-309): temporal reuse, reservoir update with the new
+// sample `gs`, validity check, clamp, store, shade, tone-compress, write the pre-denoise indirect image.
+DEV void giFinish(const FrameParams& P, int x, int y, int Wi, int Hi, uint32_t& seed, GISampleD gs, float primSamplePdf,
+                  f3 primPos, f3 primFfn, float primRough, float primMetal, uint32_t primMatHash, f3 primWo) {
+  GISampleD rs; rs.L = mk3(0.f); rs.xv = mk3(0.f); rs.nv = mk3(0.f); rs.xs = mk3(0.f); rs.ns = mk3(0.f); rs.pHat = 0.f;
+  uint32_t rnum = 0; float rweight = 0.f, rbigW = 0.f;
+  if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // findTemporalNeighbor :74-108
+    const float reprojDepth = len3(ld3(P.cam.lastPosition) - primPos);
+    short2 mv = make_short2(0, 0);
+    if (2 * x < P.pitch && 2 * y < P.allocH) mv = P.motion[(size_t)(2 * y) * P.pitch + 2 * x];
+    const uint4 gl = loadG(P.lastG, P, mv.x, mv.y);
+    const f3 pnorm = octDecode(gl.y);
+    const float pdepth = __uint_as_float(gl.x);
+    const int cx = mv.x / 2, cy = mv.y / 2;
+    if (cx >= 0 && cx < Wi && cy >= 0 && cy < Hi && hash8(primMatHash) == (gl.w & 0xFF000000u) && dot3(primFfn, pnorm) > 0.5f &&
+        reprojDepth < __fmul_rn(pdepth, 1.1f))
+      loadIResv(P.lastIR, (size_t)cy * Wi + cx, rs, rnum, rweight, rbigW);
+  }
+  float sampleWeight = 0.0f;
+  if (giSampleValid(gs)) {
+    gs.pHat = lum3(gs.L);                               // pHatIndirect :63-64
+    sampleWeight = __fdiv_rn(gs.pHat, primSamplePdf);
+    if (sampleWeight != sampleWeight || sampleWeight < 0.0f) sampleWeight = 0.0f;
+  }
+  {                                                     // resvUpdate (reservoir.glsl:55-61)
+    const float rv = rnd(seed);
+    rweight = __fadd_rn(rweight, sampleWeight);
+    rnum += 1;
+    if (__fmul_rn(rv, rweight) < sampleWeight) rs = gs;
+  }
+  if (resvInvalidW(rweight)) { rnum = 0; rweight = 0.f; rbigW = 0.f; }
+  const int clampN = P.st.reservoirClamp * 2;
+  if (rnum > (uint32_t)clampN) { rweight = __fmul_rn(rweight, __fdiv_rn((float)clampN, (float)rnum)); rnum = (uint32_t)clampN; }
+  storeIResv(P.thisIR, (size_t)y * Wi + x, rs, rnum, rweight, rbigW);
+
+  f3 indirect = mk3(0.0f);
+  if (!resvInvalidW(rweight) && giSampleValid(rs)) {
+    const f3 primWi = norm3(rs.xs - rs.xv);
+    const float bigW = __fdiv_rn(rweight, __fmul_rn(lum3(rs.L), (float)rnum));   // bigWIndirect :70-72
+    indirect = ((rs.L * bsdfEval(mk3(1.0f), primRough, primMetal, rs.nv, primWo, primWi)) * satDot(rs.nv, primWi)) * bigW;
+  }
+  f3 res = hdrToLdr(clampRadiance(indirect, P.st.fireflyClampThreshold));
+  res = clampRadiance(res, P.st.fireflyClampThreshold);
+  P.indA[(size_t)y * P.pitch + x] = make_float4(res.x, res.y, res.z, 1.0f);
+}
+
 template <bool STATS, bool TEX>
 __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
@@ -306,8 +398,6 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   if (x < Wi && y < Hi) {
     uint32_t seed = tea((uint32_t)Wi * (uint32_t)y + (uint32_t)x, P.st.time);   // :280
-    f3 ro, rd;
-    raySpawn<true>(P.cam, x, y, Wi, Hi, ro, rd);
     // TILED_MULTIBOUNCE (:283-288): invocation (0,0) of each 8x8 group draws once, the flag is group-wide.
     // Every thread re-derives that draw from the tile origin's seed instead of a shared variable + barrier.
     bool multiBounce;
@@ -316,27 +406,12 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
       uint32_t s0 = tea((uint32_t)Wi * (uint32_t)(y - (int)threadIdx.y) + (uint32_t)(x - (int)threadIdx.x), P.st.time);
       multiBounce = rnd(s0) < 0.25f;
     }
-    const size_t opix = (size_t)y * P.pitch + x;
-    // getIndirectStateFromGBuffer (pathtrace.glsl:296-313) at full-res pixel 2*coord
-    const uint4 gi = loadG(P.thisG, P, 2 * x, 2 * y);
-    const float depth = __uint_as_float(gi.x);
-    if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) {
-      P.indA[opix] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
+    GIPrimary pr;
+    if (!giPrimary(P, x, y, Wi, Hi, pr)) {
+      P.indA[(size_t)y * P.pitch + x] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
     } else {
-      State st;
-      st.position = ro + rd * depth;
-      st.normal = octDecode(gi.y);
-      st.ffnormal = dot3(st.normal, rd) <= 0.0f ? st.normal : -st.normal;
-      st.mat.albedo = mk3(unormToFloat(gi.w & 0xffu), unormToFloat((gi.w >> 8) & 0xffu), unormToFloat((gi.w >> 16) & 0xffu));
-      st.mat.metallic = unormToFloat(gi.z & 0xffu);
-      st.mat.roughness = unormToFloat((gi.z >> 8) & 0xffu);
-      st.mat.ior = __fadd_rn(__fmul_rn(unormToFloat((gi.z >> 16) & 0xffu), MAX_IOR_MINUS_ONE), 1.f);
-      st.mat.transmission = unormToFloat(gi.z >> 24);
-      st.mat.emission = mk3(0.f);
-      st.matID = gi.w >> 24;                                // hashed material id
-      st.isEmitter = false; st.area = 0.f; st.eta = 0.f; st.u = st.v = 0.f;
-      st.position = st.position + st.ffnormal * 2e-2f;      // :299
-
+      State st = pr.st;
+      const f3 ro = pr.ro, rd = pr.rd;
       // ---- pathTraceIndirect (:129-226)
       const f3 primWo = -rd;
       const f3 primPos = st.position, primFfn = st.ffnormal;
@@ -406,51 +481,217 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         }
         if (d == 1) { gs.xs = st.position; gs.ns = st.ffnormal; }
       }
-
-      // ---- ReSTIRIndirect (:228-268)
-      GISampleD rs; rs.L = mk3(0.f); rs.xv = mk3(0.f); rs.nv = mk3(0.f); rs.xs = mk3(0.f); rs.ns = mk3(0.f); rs.pHat = 0.f;
-      uint32_t rnum = 0; float rweight = 0.f, rbigW = 0.f;
-      if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // findTemporalNeighbor :74-108
-        const float reprojDepth = len3(ld3(P.cam.lastPosition) - primPos);
-        short2 mv = make_short2(0, 0);
-        if (2 * x < P.pitch && 2 * y < P.allocH) mv = P.motion[(size_t)(2 * y) * P.pitch + 2 * x];
-        const uint4 gl = loadG(P.lastG, P, mv.x, mv.y);
-        const f3 pnorm = octDecode(gl.y);
-        const float pdepth = __uint_as_float(gl.x);
-        const int cx = mv.x / 2, cy = mv.y / 2;
-        if (cx >= 0 && cx < Wi && cy >= 0 && cy < Hi && hash8(primMatHash) == (gl.w & 0xFF000000u) && dot3(primFfn, pnorm) > 0.5f &&
-            reprojDepth < __fmul_rn(pdepth, 1.1f))
-          loadIResv(P.lastIR, (size_t)cy * Wi + cx, rs, rnum, rweight, rbigW);
-      }
-      float sampleWeight = 0.0f;
-      if (giSampleValid(gs)) {
-        gs.pHat = lum3(gs.L);                               // pHatIndirect :63-64
-        sampleWeight = __fdiv_rn(gs.pHat, primSamplePdf);
-        if (sampleWeight != sampleWeight || sampleWeight < 0.0f) sampleWeight = 0.0f;
-      }
-      {                                                     // resvUpdate (reservoir.glsl:55-61)
-        const float rv = rnd(seed);
-        rweight = __fadd_rn(rweight, sampleWeight);
-        rnum += 1;
-        if (__fmul_rn(rv, rweight) < sampleWeight) rs = gs;
-      }
-      if (resvInvalidW(rweight)) { rnum = 0; rweight = 0.f; rbigW = 0.f; }
-      const int clampN = P.st.reservoirClamp * 2;
-      if (rnum > (uint32_t)clampN) { rweight = __fmul_rn(rweight, __fdiv_rn((float)clampN, (float)rnum)); rnum = (uint32_t)clampN; }
-      storeIResv(P.thisIR, (size_t)y * Wi + x, rs, rnum, rweight, rbigW);
-
-      f3 indirect = mk3(0.0f);
-      if (!resvInvalidW(rweight) && giSampleValid(rs)) {
-        const f3 primWi = norm3(rs.xs - rs.xv);
-        const float bigW = __fdiv_rn(rweight, __fmul_rn(lum3(rs.L), (float)rnum));   // bigWIndirect :70-72
-        indirect = ((rs.L * bsdfEval(mk3(1.0f), primRough, primMetal, rs.nv, primWo, primWi)) * satDot(rs.nv, primWi)) * bigW;
-      }
-      f3 res = hdrToLdr(clampRadiance(indirect, P.st.fireflyClampThreshold));
-      res = clampRadiance(res, P.st.fireflyClampThreshold);
-      P.indA[opix] = make_float4(res.x, res.y, res.z, 1.0f);
+      giFinish(P, x, y, Wi, Hi, seed, gs, primSamplePdf, primPos, primFfn, primRough, primMetal, primMatHash, primWo);
     }
   }
   flushCounters<STATS>(P, rc);
+}
+
+// =================================================================================================
+// K2, wavefront form (scenes without stochastic alpha).  The same per-path arithmetic and RNG draw order as k_indirect_stage,
+// cut at the ray queries:
+//   k_gi_begin              primary state, multibounce lottery, BSDF sample of depth 1 -> closest-hit queue 1
+//   k_trace_queue<false>    closest hits of queue d                                     (dynamic fetch, trace.cuh)
+//   k_gi_bounce(d)          miss / emitter / surface of the depth-d hit; for depth d+1: light sample -> shadow queue + its
+//                           MIS-weighted term, BSDF sample, throughput, next ray -> closest-hit queue d+1
+//   k_trace_queue<true>     every shadow ray of every depth in ONE launch (a shadow result only gates one addition)
+//   k_gi_finish             L = ordered sum of the unoccluded NEE terms (+ the terminal emitter/environment term), ReSTIR GI
+// A shadow ray of an opaque scene consumes no RNG draw, so deferring it does not change any other value; the radiance terms
+// are added in the mega-kernel's order (NEE of depth 2, 3, ..., then the terminal term, which always comes last).
+// =================================================================================================
+// one queue slot per lane that wants one: a single atomicAdd per warp; must be called by all 32 lanes
+DEV uint32_t warpEnqueue(uint32_t* counter, bool want) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (!m) return 0;
+  const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+template <bool TEX>
+__global__ void __launch_bounds__(64) k_gi_begin(const FrameParams P) {
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
+  const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
+  const uint32_t slot = (blockIdx.y * gridDim.x + blockIdx.x) * 64u + threadIdx.y * 8u + threadIdx.x;
+  const WaveView& V = P.wv;
+  bool wantRay = false;
+  f3 rayO = mk3(0.f), rayD = mk3(0.f);
+  float samplePdf = 0.f;
+  if (x < Wi && y < Hi) {
+    uint32_t seed = tea((uint32_t)Wi * (uint32_t)y + (uint32_t)x, P.st.time);   // :280
+    bool multiBounce;                                                          // TILED_MULTIBOUNCE, see k_indirect_stage
+    if (threadIdx.x == 0 && threadIdx.y == 0) multiBounce = rnd(seed) < 0.25f;
+    else {
+      uint32_t s0 = tea((uint32_t)Wi * (uint32_t)(y - (int)threadIdx.y) + (uint32_t)(x - (int)threadIdx.x), P.st.time);
+      multiBounce = rnd(s0) < 0.25f;
+    }
+    GIPrimary pr;
+    if (!giPrimary(P, x, y, Wi, Hi, pr)) {
+      P.indA[(size_t)y * P.pitch + x] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
+    } else {
+      State& st = pr.st;
+      st.mat.albedo = mk3(1.0f);
+      f3 xv = mk3(0.f), nv = mk3(100.0f);                  // newGISample :110-115
+      float primSamplePdf = 0.f;
+      if (P.st.maxDepth >= 1) {
+        f3 sampleWi, sampleBSDF;
+        samplePdf = bsdfSample(st, st.ffnormal, -pr.rd, seed, sampleBSDF, sampleWi);
+        if (!isPdfInvalid(samplePdf)) {
+          primSamplePdf = samplePdf; xv = st.position; nv = st.ffnormal;
+          rayO = offsetRay(st.position, st.ffnormal); rayD = sampleWi;
+          wantRay = true;
+        }
+      }
+      const float t0 = multiBounce ? 4.0f : 1.0f;
+      V.misc[slot] = make_uint4(seed, multiBounce ? GI_MULTIBOUNCE : 0u, 0u, 0u);
+      V.thr[slot] = make_float4(t0, t0, t0, 0.f);
+      V.gsXv[slot] = make_float4(xv.x, xv.y, xv.z, primSamplePdf);
+      V.gsNv[slot] = make_float4(nv.x, nv.y, nv.z, 0.f);
+      V.gsXs[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      V.gsNs[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const uint32_t j = warpEnqueue(&V.ctr[1], wantRay);
+  if (wantRay) {
+    V.rayQ[1][2 * (size_t)j] = make_float4(rayO.x, rayO.y, rayO.z, samplePdf);
+    V.rayQ[1][2 * (size_t)j + 1] = make_float4(rayD.x, rayD.y, rayD.z, __uint_as_float(slot));
+  }
+}
+
+template <bool TEX>
+__global__ void __launch_bounds__(128) k_gi_bounce(const FrameParams P, int d) {
+  const WaveView& V = P.wv;
+  const uint32_t n = V.ctr[d];
+  const float4* __restrict__ inQ = V.rayQ[d & 1];
+  float4* __restrict__ outQ = V.rayQ[(d + 1) & 1];
+  const uint32_t nRound = (n + 31u) & ~31u;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nRound; j += gridDim.x * blockDim.x) {
+    bool wantRay = false, wantShadow = false;
+    f3 rayO = mk3(0.f), rayD2 = mk3(0.f), shO = mk3(0.f), shD = mk3(0.f);
+    float nextPdf = 0.f, shTmax = 0.f;
+    uint32_t slot = 0;
+    if (j < n) {
+      const float4 r0 = __ldg(inQ + 2 * (size_t)j), r1 = __ldg(inQ + 2 * (size_t)j + 1), h = __ldg(V.hitQ + j);
+      const f3 rayD = mk3(r1.x, r1.y, r1.z);               // = sampleWi of depth d
+      const float samplePdf = r0.w;
+      slot = __float_as_uint(r1.w);
+      uint4 misc = V.misc[slot];
+      uint32_t seed = misc.x;
+      const bool multiBounce = (misc.y & GI_MULTIBOUNCE) != 0u;
+      const float4 t4 = V.thr[slot];
+      f3 throughput = mk3(t4.x, t4.y, t4.z);
+      const int tri = __float_as_int(h.w);
+      if (tri < 0) {                                        // miss (:183-198)
+        if (d > 1) {
+          const f3 env = envTextureDir(P.env, rayD);                        // EnvEval (pathtrace.glsl:60-72), HDR branch
+          const float lightPdf = __fmul_rn(__fmul_rn(lum3(env), P.st.envMapLuminIntegInv), P.st.environmentProb);
+          const f3 add = (env * throughput) * misWeight(P, samplePdf, lightPdf);
+          V.hitL[slot] = make_float4(add.x, add.y, add.z, 0.f);
+          misc.y |= GI_HITL;
+        } else {
+          const float4 xv = V.gsXv[slot];                   // = the primary position (the depth-1 sample was valid)
+          const f3 xs = mk3(xv.x, xv.y, xv.z) + (rayD * EID_INFINITY) * 0.8f, ns = -rayD;
+          V.gsXs[slot] = make_float4(xs.x, xs.y, xs.z, 0.f);
+          V.gsNs[slot] = make_float4(ns.x, ns.y, ns.z, 0.f);
+        }
+      } else {
+        const float4 tc = __ldg(P.accel.tris + 3 * (size_t)tri + 2);          // primitiveID, instanceID of the hit triangle
+        Payload prd;
+        prd.hitT = h.x; prd.baryU = h.y; prd.baryV = h.z; prd.primitiveID = __float_as_int(tc.y); prd.instanceID = __float_as_int(tc.z);
+        prd.instanceCustomIndex = P.sc.instances[prd.instanceID].primMesh;
+        State st = getState<TEX>(P.sc, prd, rayD);
+        getMaterials<TEX>(P.sc, st, rayD);
+        if (st.isEmitter) {                                 // :203-215, LightEval (pathtrace.glsl:74-88)
+          if (d > 1) {
+            const float lightProb = __fsub_rn(1.0f, P.st.environmentProb);
+            const float4 em = __ldg((const float4*)(P.sc.materials + st.matID) + 2);
+            float lightPdf = __fmul_rn(__fmul_rn(lum709(em.y, em.z, em.w), P.st.lightLuminIntegInv), lightProb);
+            lightPdf = __fmul_rn(lightPdf, __fdiv_rn(__fmul_rn(prd.hitT, prd.hitT), absDot(st.ffnormal, rayD)));
+            const f3 Li = st.mat.emission / st.area;
+            const f3 add = (Li * throughput) * misWeight(P, samplePdf, lightPdf);
+            V.hitL[slot] = make_float4(add.x, add.y, add.z, 0.f);
+            misc.y |= GI_HITL;
+          } else {
+            V.gsXs[slot] = make_float4(st.position.x, st.position.y, st.position.z, 0.f);
+            V.gsNs[slot] = make_float4(st.ffnormal.x, st.ffnormal.y, st.ffnormal.z, 0.f);
+          }
+        } else {
+          if (d == 1) {
+            V.gsXs[slot] = make_float4(st.position.x, st.position.y, st.position.z, 0.f);
+            V.gsNs[slot] = make_float4(st.ffnormal.x, st.ffnormal.y, st.ffnormal.z, 0.f);
+          }
+          if (d + 1 <= P.st.maxDepth) {                     // ---- loop iteration d + 1 up to its ray query
+            const f3 wo = -rayD;
+            if (P.st.MIS > 0) {                             // SampleDirectLight (pathtrace.glsl:185-202), visibility deferred
+              LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+              const float lightPdf = sampleDirectLightNoVisibility<TEX>(P.sc, P.env, P.st, st.position, seed, ls);
+              if (!isPdfInvalid(lightPdf)) {
+                shO = offsetRay(st.position, st.ffnormal); shD = ls.wi;
+                shTmax = __fsub_rn(__fsub_rn(__fsub_rn(ls.dist, fabsf(__fsub_rn(shO.x, st.position.x))), fabsf(__fsub_rn(shO.y, st.position.y))),
+                                   fabsf(__fsub_rn(shO.z, st.position.z)));                       // Occlusion (pathtrace.glsl:18-22)
+                wantShadow = true;
+                const float bp = bsdfPdf(st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi);
+                const float w = misWeight(P, lightPdf, bp);
+                const f3 term = ((((ls.Li * bsdfEval(st.mat.albedo, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * absDot(st.ffnormal, ls.wi)) * throughput) / lightPdf) * w;
+                V.neeTerm[(size_t)(d - 1) * V.slots + slot] = make_float4(term.x, term.y, term.z, 0.f);
+                misc.y |= 1u << (GI_NEE_SHIFT + d - 1);
+              }
+            }
+            f3 sampleWi, sampleBSDF;
+            nextPdf = bsdfSample(st, st.ffnormal, wo, seed, sampleBSDF, sampleWi);
+            if (!isPdfInvalid(nextPdf) && multiBounce) {    // ordinary tiles `return` here (:164-166)
+              throughput = throughput * ((sampleBSDF / nextPdf) * absDot(st.ffnormal, sampleWi));
+              rayO = offsetRay(st.position, st.ffnormal); rayD2 = sampleWi;
+              wantRay = true;
+              V.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, 0.f);
+            }
+          }
+        }
+      }
+      misc.x = seed;
+      V.misc[slot] = misc;
+    }
+    const uint32_t js = warpEnqueue(&V.ctr[0], wantShadow);
+    if (wantShadow) {
+      V.shadowQ[2 * (size_t)js] = make_float4(shO.x, shO.y, shO.z, shTmax);
+      V.shadowQ[2 * (size_t)js + 1] = make_float4(shD.x, shD.y, shD.z, __uint_as_float((uint32_t)(d - 1) * V.slots + slot));
+    }
+    const uint32_t jr = warpEnqueue(&V.ctr[d + 1], wantRay);
+    if (wantRay) {
+      outQ[2 * (size_t)jr] = make_float4(rayO.x, rayO.y, rayO.z, nextPdf);
+      outQ[2 * (size_t)jr + 1] = make_float4(rayD2.x, rayD2.y, rayD2.z, __uint_as_float(slot));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(64) k_gi_finish(const FrameParams P) {
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
+  const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
+  if (x >= Wi || y >= Hi) return;
+  const uint32_t slot = (blockIdx.y * gridDim.x + blockIdx.x) * 64u + threadIdx.y * 8u + threadIdx.x;
+  const WaveView& V = P.wv;
+  GIPrimary pr;
+  if (!giPrimary(P, x, y, Wi, Hi, pr)) return;              // sky: k_gi_begin wrote the pixel
+  const uint4 misc = V.misc[slot];
+  uint32_t seed = misc.x;
+  const float4 xv = V.gsXv[slot], nv = V.gsNv[slot], xs = V.gsXs[slot], ns = V.gsNs[slot];
+  GISampleD gs;
+  gs.xv = mk3(xv.x, xv.y, xv.z); gs.nv = mk3(nv.x, nv.y, nv.z); gs.xs = mk3(xs.x, xs.y, xs.z); gs.ns = mk3(ns.x, ns.y, ns.z); gs.pHat = 0.f;
+  gs.L = mk3(0.f);
+  uint32_t nee = misc.y >> GI_NEE_SHIFT;
+  for (int k = 0; nee; ++k, nee >>= 1) {
+    if ((nee & 1u) && V.occl[(size_t)k * V.slots + slot] == 0u) {
+      const float4 t = V.neeTerm[(size_t)k * V.slots + slot];
+      gs.L = gs.L + mk3(t.x, t.y, t.z);
+    }
+  }
+  if (misc.y & GI_HITL) { const float4 t = V.hitL[slot]; gs.L = gs.L + mk3(t.x, t.y, t.z); }
+  giFinish(P, x, y, Wi, Hi, seed, gs, xv.w, pr.st.position, pr.st.ffnormal, pr.st.mat.roughness, pr.st.mat.metallic, pr.st.matID, -pr.rd);
 }
 
 // =================================================================================================
@@ -688,6 +929,11 @@ struct eid_renderer {
   float4* directImg = nullptr; float4* indirectImg = nullptr;
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
+  // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
+  void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
+  int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
+  int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
+  int smCount = 0;
   int denoiseRowBlock = 2;    // pixels of one column filtered per thread in the A-Trous passes (1, 2 or 4; 2 measured fastest)
   bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
   unsigned long long* counters = nullptr;
@@ -714,11 +960,14 @@ struct eid_renderer {
 
   void allocate();
   void release();
+  void ensureWave(int terms);
+  WaveView waveView() const;
 };
 
 void eid_renderer::release() {
   for (int i = 0; i < 2; ++i) { cudaFree(gbuffer[i]); cudaFree(directResv[i]); cudaFree(indirectResv[i]); gbuffer[i] = nullptr; directResv[i] = nullptr; indirectResv[i] = nullptr; }
   cudaFree(motion); motion = nullptr;
+  cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
   for (auto& t : geom) { cudaFree(t); t = nullptr; }
@@ -746,6 +995,33 @@ void eid_renderer::allocate() {
   CUDA_CHECK(cudaStreamSynchronize(stream));
   hasRun = false; lastSet = 0;
   if (!stripesSet) { sFirst = 0; sRows = (height + 15) / 16 * 16; sStride = 1u << 20; }
+}
+
+// Scratch of the wavefront K2: planes of `waveSlots` float4 (one slot per thread of the largest possible K2 grid of this
+// allocation).  Layout of waveMem in float4 units: rayQ0 2S | rayQ1 2S | hitQ S | misc S | thr S | gsXv S | gsNv S | gsXs S |
+// gsNs S | hitL S | neeTerm T*S | shadowQ 2*T*S | occl (T*S uint32).  1080p, maxDepth 3: ~125 MB.
+void eid_renderer::ensureWave(int terms) {
+  terms = std::max(terms, 1);
+  const uint32_t tilesX = (width / 2 + 7) / 8, tilesY = ((height + 15) / 16 * 16 / 2 + 7) / 8 + 1;
+  const uint32_t S = tilesX * tilesY * 64u;
+  if (waveMem && waveSlots == S && waveTerms >= terms) return;
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  cudaFree(waveMem); waveMem = nullptr;
+  const size_t f4 = (size_t)S * (12 + 3 * (size_t)terms);
+  CUDA_CHECK(cudaMalloc(&waveMem, f4 * 16 + (size_t)S * terms * 4));
+  if (!waveCtr) CUDA_CHECK(cudaMalloc(&waveCtr, 128 * sizeof(uint32_t)));
+  waveSlots = S; waveTerms = terms;
+}
+WaveView eid_renderer::waveView() const {
+  WaveView V;
+  const size_t S = waveSlots, T = (size_t)waveTerms;
+  float4* b = (float4*)waveMem;
+  V.slots = waveSlots;
+  V.rayQ[0] = b; V.rayQ[1] = b + 2 * S; V.hitQ = b + 4 * S; V.misc = (uint4*)(b + 5 * S); V.thr = b + 6 * S;
+  V.gsXv = b + 7 * S; V.gsNv = b + 8 * S; V.gsXs = b + 9 * S; V.gsNs = b + 10 * S; V.hitL = b + 11 * S;
+  V.neeTerm = b + 12 * S; V.shadowQ = b + (12 + T) * S; V.occl = (uint32_t*)(b + (12 + 3 * T) * S);
+  V.ctr = waveCtr;
+  return V;
 }
 
 static void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
@@ -776,6 +1052,8 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.sFirst = (int)r->sFirst; P.sStride = (int)r->sStride; P.sRows = (int)r->sRows;
   P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
   P.counters = r->counters;
+  memset(&P.wv, 0, sizeof(P.wv));
+  if (r->wavefront && !P.hasNonOpaque && st.maxDepth <= GI_MAX_WAVE_DEPTH) { r->ensureWave(st.maxDepth - 1); P.wv = r->waveView(); }
   r->lastSet = set; r->lastState = st; r->hasRun = true;
 }
 
@@ -803,14 +1081,38 @@ static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) 
   markStop(r, EID_K_DIRECT, st);
 }
 
+template <bool ANY>
+static void launchTraceQueue(eid_renderer* r, const FrameParams& P, const float4* rays, const uint32_t* count, uint32_t* cursor, cudaStream_t st) {
+  const int g = r->traceBlocks > 0 ? r->traceBlocks : r->smCount * EID_TQ_MIN_BLOCKS;
+  if (r->countVisits) k_trace_queue<ANY, true><<<g, 128, 0, st>>>(P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
+  else k_trace_queue<ANY, false><<<g, 128, 0, st>>>(P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
+  r->stats.kernelLaunches[EID_K_INDIRECT]++;
+}
+
 static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_INDIRECT, st);
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
     dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
-    if (r->countVisits) { if (tex) k_indirect_stage<true, true><<<g, b, 0, st>>>(P); else k_indirect_stage<true, false><<<g, b, 0, st>>>(P); }
-    else { if (tex) k_indirect_stage<false, true><<<g, b, 0, st>>>(P); else k_indirect_stage<false, false><<<g, b, 0, st>>>(P); }
-    r->stats.kernelLaunches[EID_K_INDIRECT]++;
+    if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
+      // wavefront form: begin, then per depth (closest-hit queue, bounce), all shadow rays at once, finish
+      CUDA_CHECK(cudaMemsetAsync(P.wv.ctr, 0, 128 * sizeof(uint32_t), st));
+      if (tex) k_gi_begin<true><<<g, b, 0, st>>>(P); else k_gi_begin<false><<<g, b, 0, st>>>(P);
+      r->stats.kernelLaunches[EID_K_INDIRECT]++;
+      const int gb = r->smCount * 8;
+      for (int d = 1; d <= P.st.maxDepth; ++d) {
+        launchTraceQueue<false>(r, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
+        if (tex) k_gi_bounce<true><<<gb, 128, 0, st>>>(P, d); else k_gi_bounce<false><<<gb, 128, 0, st>>>(P, d);
+        r->stats.kernelLaunches[EID_K_INDIRECT]++;
+      }
+      if (P.st.maxDepth >= 2 && P.st.MIS > 0) launchTraceQueue<true>(r, P, P.wv.shadowQ, P.wv.ctr, P.wv.ctr + 64, st);
+      k_gi_finish<<<g, b, 0, st>>>(P);
+      r->stats.kernelLaunches[EID_K_INDIRECT]++;
+    } else {
+      if (r->countVisits) { if (tex) k_indirect_stage<true, true><<<g, b, 0, st>>>(P); else k_indirect_stage<true, false><<<g, b, 0, st>>>(P); }
+      else { if (tex) k_indirect_stage<false, true><<<g, b, 0, st>>>(P); else k_indirect_stage<false, false><<<g, b, 0, st>>>(P); }
+      r->stats.kernelLaunches[EID_K_INDIRECT]++;
+    }
   }
   markStop(r, EID_K_INDIRECT, st);
 }
@@ -985,6 +1287,7 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
   try {
     r->scene = s; r->accel = a; r->device = s->dev.device; r->width = width; r->height = height;
     CUDA_CHECK(cudaSetDevice(r->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&r->smCount, cudaDevAttrMultiProcessorCount, r->device));
     if (cuda_stream) r->stream = (cudaStream_t)cuda_stream;
     else { CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->ownStream = true; }
     CUDA_CHECK(cudaMalloc(&r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long)));
@@ -1314,6 +1617,16 @@ int eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread) {
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: null renderer");
   if (rowsPerThread != 1 && rowsPerThread != 2 && rowsPerThread != 4) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: 1, 2 or 4");
   r->denoiseRowBlock = rowsPerThread;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_wavefront: null renderer");
+  if (traceBlocks < 0 || traceBlocks > 65535) raise(EID_ERR_INVALID, "eid_renderer_set_wavefront: traceBlocks out of range");
+  r->wavefront = enabled != 0;
+  r->traceBlocks = traceBlocks;
   return EID_OK;
   EID_CATCH
 }

@@ -93,6 +93,128 @@ DEV float boxEntryNF(const RayBox& rb, float nx, float ny, float nz, float fx, f
   return (tn <= tf * 1.0000004f) ? tn : __int_as_float(0x7f800000);
 }
 
+// 256-bit global load (sm_100a LDG.E.256): one L1 wavefront per lane for 32 B instead of two
+DEV void ldg256(const float4* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+#ifndef EID_FETCH_TEX
+#define EID_FETCH_TEX 2     // 0: every BVH fetch is an LDG; 2: far planes of a node come through tex1Dfetch (default); 1/3/4: experiments
+#endif
+
+#define EID_TRAV_DONE ((int)0x80000000)   // never a valid reference (it would be a leaf starting at triangle 2^28 - 1)
+
+// One inner-node visit: box tests of the children, `cur` becomes the next reference to look at (nearest entered child, or the
+// top of the stack, or EID_TRAV_DONE), the other entered children go onto the stack.  ANY = occlusion ray: child order is irrelevant.
+template <bool ANY>
+DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, int* stack, int& sp) {
+  const float INF = __int_as_float(0x7f800000);
+#define EID_POP() (sp ? stack[--sp] : EID_TRAV_DONE)
+#if EID_BVH_WIDTH == 2
+  const float4* n = A.nodes + 4 * (size_t)cur;
+  const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+  float e0 = boxEntry(rb, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tbest);
+  float e1 = boxEntry(rb, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tbest);
+  int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+  bool h0 = e0 < INF, h1 = e1 < INF;
+  if (h0 && h1) {
+    if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
+    if (sp < EID_STACK_SIZE) stack[sp++] = c1;
+    cur = c0;
+  } else if (h0) cur = c0;
+  else if (h1) cur = c1;
+  else cur = EID_POP();
+#else
+  const float4* n = A.nodes + 8 * (size_t)cur;
+#ifdef EID_NODE_LDG256
+  // the whole 128-byte node in four 256-bit loads (4 L1 wavefronts per lane instead of 7); near/far by min/max
+  float4 lx, ly, lz, hx, hy, hz, rf, pad_;
+  ldg256(n, lx, ly); ldg256(n + 2, lz, hx); ldg256(n + 4, hy, hz); ldg256(n + 6, rf, pad_);
+  float e0 = boxEntry(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, tbest);
+  float e1 = boxEntry(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, tbest);
+  float e2 = boxEntry(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, tbest);
+  float e3 = boxEntry(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, tbest);
+#elif EID_FETCH_TEX
+  // Far planes through the TEX pipe, near planes + references through the LSU pipe: an incoherent node visit is one L1 data
+  // wavefront per lane per 16 bytes, and with all seven loads on the LSU pipe that pipe ran at 72-81 % of its peak in the trace
+  // kernels (ncu l1tex__data_pipe_lsu_wavefronts); split over both pipes K1 went 0.995 -> 0.926 ms (profiles/README.md).
+  const int nb = 8 * cur;
+#if EID_FETCH_TEX >= 2
+  const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);
+#else
+  const float4 lx = tex1Dfetch<float4>(A.nodeTex, nb + rb.nx), ly = tex1Dfetch<float4>(A.nodeTex, nb + rb.ny), lz = tex1Dfetch<float4>(A.nodeTex, nb + rb.nz);
+#endif
+  const float4 hx = tex1Dfetch<float4>(A.nodeTex, nb + rb.fx), hy = tex1Dfetch<float4>(A.nodeTex, nb + rb.fy), hz = tex1Dfetch<float4>(A.nodeTex, nb + rb.fz);
+  const float4 rf = __ldg(n + 6);
+  float e0 = boxEntryNF(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, tbest);
+  float e1 = boxEntryNF(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, tbest);
+  float e2 = boxEntryNF(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, tbest);
+  float e3 = boxEntryNF(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, tbest);
+#else
+  const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);   // near planes of the 4 children
+  const float4 hx = __ldg(n + rb.fx), hy = __ldg(n + rb.fy), hz = __ldg(n + rb.fz);   // far planes
+  const float4 rf = __ldg(n + 6);
+  float e0 = boxEntryNF(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, tbest);
+  float e1 = boxEntryNF(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, tbest);
+  float e2 = boxEntryNF(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, tbest);
+  float e3 = boxEntryNF(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, tbest);
+#endif
+  int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
+  if (ANY) {
+    // occlusion rays: order is irrelevant, just visit every child the ray enters
+    int next = 0; bool have = false;
+    if (e0 < INF) { next = c0; have = true; }
+    if (e1 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c1; } else { next = c1; have = true; } }
+    if (e2 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c2; } else { next = c2; have = true; } }
+    if (e3 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c3; } else { next = c3; have = true; } }
+    cur = have ? next : EID_POP();
+  } else {
+    // sort the four (entry distance, ref) pairs ascending: 5-comparator network
+#define EID_CSWAP(ea, ca, eb, cb) { if (eb < ea) { float te = ea; ea = eb; eb = te; int tc = ca; ca = cb; cb = tc; } }
+    EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2) EID_CSWAP(e1, c1, e3, c3) EID_CSWAP(e1, c1, e2, c2)
+#undef EID_CSWAP
+    if (e0 < INF) {
+      if (e3 < INF && sp < EID_STACK_SIZE) stack[sp++] = c3;
+      if (e2 < INF && sp < EID_STACK_SIZE) stack[sp++] = c2;
+      if (e1 < INF && sp < EID_STACK_SIZE) stack[sp++] = c1;
+      cur = c0;
+    } else cur = EID_POP();
+  }
+#endif
+}
+
+// All triangles of leaf reference `cur` (< 0, != EID_TRAV_DONE).  Returns true when an ANY ray is finished (first accepted triangle).
+template <bool ANY, bool STATS, bool LOWER>
+DEV bool leafStep(const AccelView& A, int cur, f3 o, f3 d, float tmax, RayHit& hit, unsigned int* triTests, const HitKey& low) {
+  const uint32_t ref = ~(uint32_t)cur;
+  const uint32_t first = ref >> 3, count = ref & 7u;
+  for (uint32_t k = 0; k < count; ++k) {
+    const float4* tp = A.tris + 3 * (size_t)(first + k);
+    if (STATS) ++*triTests;
+#if EID_FETCH_TEX >= 3
+    const int tb = 3 * (int)(first + k);
+#if EID_FETCH_TEX == 4
+    const float4 a = __ldg(tp), b = tex1Dfetch<float4>(A.triTex, tb + 1), c = __ldg(tp + 2);
+#else
+    const float4 a = tex1Dfetch<float4>(A.triTex, tb), b = tex1Dfetch<float4>(A.triTex, tb + 1), c = tex1Dfetch<float4>(A.triTex, tb + 2);
+#endif
+#else
+    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+#endif
+    float t, u, v;
+    const uint32_t flags = __float_as_uint(c.w);
+    if (triangleTest(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), flags, o, d, tmax, t, u, v)) {
+      if (ANY) { hit.t = t; hit.tri = (int)(first + k); return true; }
+      const int prim = __float_as_int(c.y), inst = __float_as_int(c.z);
+      if (LOWER && (t < low.t || (t == low.t && (inst < low.inst || (inst == low.inst && prim <= low.prim))))) continue;
+      bool better = t < hit.t || (t == hit.t && (inst < hit.inst || (inst == hit.inst && prim < hit.prim)));
+      if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; hit.flags = flags; }
+    }
+  }
+  return false;
+}
+
 // ANY = true: terminate on the first accepted triangle (AnyHit); false: closest hit with tie-break.
 // STATS = true additionally counts inner-node visits and triangle tests (profiling builds of the kernels).
 template <bool ANY, bool STATS = false, bool LOWER = false>
@@ -106,84 +228,111 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
   int stack[EID_STACK_SIZE];
   int sp = 0;
   int cur = A.rootRef;
-  const float INF = __int_as_float(0x7f800000);
-  const int DONE = (int)0x80000000;            // never a valid reference (it would be a leaf starting at triangle 2^28 - 1)
-#define EID_POP() (sp ? stack[--sp] : DONE)
   // "while-while" walk: every lane first descends inner nodes until it holds a leaf (or is done); the warp then reconverges
   // and intersects leaves together.  In the interleaved form the triangle tests ran with ~5 of 32 lanes active (ncu source page).
   for (;;) {
     while (cur >= 0) {
-#if EID_BVH_WIDTH == 2
-      const float4* n = A.nodes + 4 * (size_t)cur;
       if (STATS) ++*nodeVisits;
-      const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
-      float e0 = boxEntry(rb, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, hit.t);
-      float e1 = boxEntry(rb, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, hit.t);
-      int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-      bool h0 = e0 < INF, h1 = e1 < INF;
-      if (h0 && h1) {
-        if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
-        if (sp < EID_STACK_SIZE) stack[sp++] = c1;
-        cur = c0;
-      } else if (h0) cur = c0;
-      else if (h1) cur = c1;
-      else cur = EID_POP();
-#else
-      const float4* n = A.nodes + 8 * (size_t)cur;
-      if (STATS) ++*nodeVisits;
-      const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);   // near planes of the 4 children
-      const float4 hx = __ldg(n + rb.fx), hy = __ldg(n + rb.fy), hz = __ldg(n + rb.fz);   // far planes
-      const float4 rf = __ldg(n + 6);
-      float e0 = boxEntryNF(rb, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, hit.t);
-      float e1 = boxEntryNF(rb, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, hit.t);
-      float e2 = boxEntryNF(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, hit.t);
-      float e3 = boxEntryNF(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, hit.t);
-      int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
-      if (ANY) {
-        // occlusion rays: order is irrelevant, just visit every child the ray enters
-        int next = 0; bool have = false;
-        if (e0 < INF) { next = c0; have = true; }
-        if (e1 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c1; } else { next = c1; have = true; } }
-        if (e2 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c2; } else { next = c2; have = true; } }
-        if (e3 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c3; } else { next = c3; have = true; } }
-        cur = have ? next : EID_POP();
-      } else {
-        // sort the four (entry distance, ref) pairs ascending: 5-comparator network
-#define EID_CSWAP(ea, ca, eb, cb) { if (eb < ea) { float te = ea; ea = eb; eb = te; int tc = ca; ca = cb; cb = tc; } }
-        EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2) EID_CSWAP(e1, c1, e3, c3) EID_CSWAP(e1, c1, e2, c2)
-#undef EID_CSWAP
-        if (e0 < INF) {
-          if (e3 < INF && sp < EID_STACK_SIZE) stack[sp++] = c3;
-          if (e2 < INF && sp < EID_STACK_SIZE) stack[sp++] = c2;
-          if (e1 < INF && sp < EID_STACK_SIZE) stack[sp++] = c1;
-          cur = c0;
-        } else cur = EID_POP();
-      }
-#endif
+      nodeStep<ANY>(A, rb, hit.t, cur, stack, sp);
     }
-    if (cur == DONE) break;
-    {
-      const uint32_t ref = ~(uint32_t)cur;
-      const uint32_t first = ref >> 3, count = ref & 7u;
-      for (uint32_t k = 0; k < count; ++k) {
-        const float4* tp = A.tris + 3 * (size_t)(first + k);
-        if (STATS) ++*triTests;
-        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        float t, u, v;
-        const uint32_t flags = __float_as_uint(c.w);
-        if (triangleTest(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), flags, o, d, tmax, t, u, v)) {
-          if (ANY) { hit.t = t; hit.tri = (int)(first + k); return true; }
-          const int prim = __float_as_int(c.y), inst = __float_as_int(c.z);
-          if (LOWER && (t < low.t || (t == low.t && (inst < low.inst || (inst == low.inst && prim <= low.prim))))) continue;
-          bool better = t < hit.t || (t == hit.t && (inst < hit.inst || (inst == hit.inst && prim < hit.prim)));
-          if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; hit.flags = flags; }
+    if (cur == EID_TRAV_DONE) break;
+    if (leafStep<ANY, STATS, LOWER>(A, cur, o, d, tmax, hit, triTests, low)) return true;
+    cur = EID_POP();
+  }
+  return hit.tri >= 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Ray-queue traversal with dynamic fetch (wavefront stages): a persistent grid; every lane walks one ray of the queue at a
+// time and, when its ray ends, takes the next queue entry, so a warp keeps (nearly) all lanes busy although the rays' visit
+// counts differ by 10x (mean 13.5 nodes, worst ~150 on the C3 scene; in the one-ray-per-thread kernels a warp runs as long as
+// its slowest lane and traversal executes with ~10 of 32 lanes active — ncu source page, profiles/README.md).
+// Queue entry = 2 x float4: (origin.xyz, w0), (direction.xyz, id bits).  ANY: w0 = tmax, result occl[id] = 1/0.
+// Closest: tmax = 1e28 (w0 is the producer's payload), result hits[entry] = (t, u, v, triangle index bits or -1).
+// ------------------------------------------------------------------------------------------------------------------------------
+#ifndef EID_TQ_MIN_BLOCKS
+#define EID_TQ_MIN_BLOCKS 6
+#endif
+// Inner-node visits per round before the warp reconverges for the leaf phase.  The one-ray-per-thread kernels use the
+// "while-while" form (descend until a leaf); with the lanes refilled from the queue that form wastes ~70 % of the issue
+// slots on lanes waiting at a leaf (a warp-level model of this loop with the measured 13.5 node / 2.2 leaf visits per ray gives
+// 24 % lane efficiency, ncu measured 11-12 of 32), while a short bounded node phase keeps ~70 % of the lanes busy.
+#ifndef EID_TQ_NODE_STEPS
+#define EID_TQ_NODE_STEPS 4
+#endif
+#ifndef EID_TQ_REFILL
+#define EID_TQ_REFILL 1          // idle lanes that trigger a queue fetch
+#endif
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const AccelView A, const float4* __restrict__ rays, const uint32_t* __restrict__ countPtr,
+                                                                        uint32_t* __restrict__ cursor, float4* __restrict__ hits, uint32_t* __restrict__ occl,
+                                                                        unsigned long long* __restrict__ counters) {
+  const uint32_t n = *countPtr;
+  const unsigned lane = threadIdx.x & 31u;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) {   // ray counters of the frame ([0] closest, [1] any) and since creation ([5], [6])
+    atomicAdd(&counters[ANY ? 1 : 0], (unsigned long long)n); atomicAdd(&counters[ANY ? 6 : 5], (unsigned long long)n);
+  }
+  int stack[EID_STACK_SIZE];
+  int sp = 0, cur = EID_TRAV_DONE;
+  bool active = false, more = true;
+  uint32_t entry = 0, id = 0;
+  f3 o = mk3(0.f), d = mk3(0.f);
+  float tmax = 0.f;
+  RayBox rb = makeRayBox(o, mk3(1.f));
+  RayHit hit; hit.t = 0.f; hit.tri = -1; hit.prim = hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
+  unsigned int nodeVisits = 0, triTests = 0;
+  const HitKey low = {0.f, 0, 0};
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (more && __popc(idle) >= EID_TQ_REFILL) {
+      const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)nIdle);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + (uint32_t)nIdle >= n) more = false;
+      if (!active) {
+        const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (my < n) {
+          const float4 r0 = __ldg(rays + 2 * (size_t)my), r1 = __ldg(rays + 2 * (size_t)my + 1);
+          entry = my; id = __float_as_uint(r1.w);
+          o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z);
+          tmax = ANY ? r0.w : 1e28f;
+          hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
+          rb = makeRayBox(o, d);
+          sp = 0; active = true;
+          // no triangles, or a direction with NaN / zero length (det can never be != 0): finished at once, as in traverse()
+          cur = (A.triCount == 0 || !(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) ? EID_TRAV_DONE : A.rootRef;
         }
       }
     }
-    cur = EID_POP();
+    if (!__ballot_sync(0xffffffffu, active)) break;
+#pragma unroll 1
+    for (int it = 0; it < EID_TQ_NODE_STEPS; ++it) {
+      const bool inner = active && cur >= 0;
+      if (!__any_sync(0xffffffffu, inner)) break;
+      if (inner) {
+        if (STATS) ++nodeVisits;
+        nodeStep<ANY>(A, rb, hit.t, cur, stack, sp);
+      }
+    }
+    if (active && cur < 0) {
+      if (cur != EID_TRAV_DONE) {
+        if (leafStep<ANY, STATS, false>(A, cur, o, d, tmax, hit, &triTests, low)) cur = EID_TRAV_DONE;
+        else cur = EID_POP();
+      }
+      if (cur == EID_TRAV_DONE) {
+        if (ANY) occl[id] = hit.tri >= 0 ? 1u : 0u;
+        else hits[entry] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+        active = false;
+      }
+    }
   }
-#undef EID_POP
-  return hit.tri >= 0;
+  if (STATS) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { nodeVisits += __shfl_xor_sync(0xffffffffu, nodeVisits, s); triTests += __shfl_xor_sync(0xffffffffu, triTests, s); }
+    if (lane == 0) { if (nodeVisits) atomicAdd(&counters[3], (unsigned long long)nodeVisits); if (triTests) atomicAdd(&counters[4], (unsigned long long)triTests); }
+  }
 }
+#undef EID_POP
 
 }  // namespace eid

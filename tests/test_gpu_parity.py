@@ -99,8 +99,9 @@ def test_oracle_bvh_equals_brute_force():
     assert a.trace(rays).tobytes() == b.trace(rays).tobytes()
 
 
-def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=None, **state_over):
+def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=None, wavefront=True, **state_over):
     osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict, env_img=env_img)
+    prr.set_wavefront(wavefront)
     if env_img is not None:
         state_over = dict(common.env_state_overrides(prr._env.get_integral()), **state_over)
     for s in (osc, psc):
@@ -209,6 +210,45 @@ def test_small_room_full_pipeline_static_and_orbit():
                                   dict(reservoirClamp=2), dict(fireflyClampThreshold=0.5)])
 def test_state_variants(over):
     _run_frames(scenes.cornell_scene(), (160, 96), 3, "variant %s" % over, **over)
+
+
+@pytest.mark.parametrize("over", [dict(), dict(maxDepth=1), dict(maxDepth=6), dict(MIS=0), dict(ReSTIRState=abi.eRIS)])
+def test_indirect_stage_megakernel_form(over):
+    """indirect_stage has two forms (ray queues + dynamic-fetch traversal, default; one thread per pixel): the default form is
+    what every other test runs, this one pins the one-thread-per-pixel kernel to the oracle as well."""
+    _run_frames(scenes.small_room(), (192, 112), 3, "megakernel %s" % over, wavefront=False, **over)
+    _run_frames(scenes.small_room(), (192, 112), 2, "wavefront %s" % over, wavefront=True, **over)
+
+
+def test_indirect_stage_forms_bit_identical_large():
+    """Both forms of indirect_stage on a frame too large for the oracle: every buffer bit-identical over 4 frames (moving camera),
+    for several grids of the persistent traversal kernel."""
+    arrays = scenes.small_room()
+    size = (960, 544)
+    psc = eid.Scene(0); psc.load_arrays(arrays)
+    acc = eid.AccelStructure(); acc.create(psc)
+    rrs = []
+    for on, blocks in ((0, 0), (1, 0), (1, 7), (1, 2000)):
+        rr = eid.Renderer(); rr.create(size, psc, acc); rr.set_env_constant(common.ENV); rr.set_wavefront(on, blocks)
+        rrs.append(rr)
+    info = psc.info()
+    cam = arrays.camera
+    psc.update_camera(*size)
+    for f in range(4):
+        a = np.deg2rad(0.7 * f)
+        e = np.array(cam["eye"], np.float64)
+        psc.set_lookat((e[0] * np.cos(a) - e[2] * np.sin(a), e[1], e[0] * np.sin(a) + e[2] * np.cos(a)), cam["center"], cam["up"], np.rad2deg(cam["yfov"]))
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, maxDepth=4)
+        snaps = []
+        for rr in rrs:
+            rr.run(st, f); rr.sync()
+            snaps.append(common.snapshot(rr))
+            s = rr.stats()
+            snaps[-1]["rays"] = np.array([s.closestHitRays, s.anyHitRays, s.primaryHits])
+        for other in snaps[1:]:
+            for k in snaps[0]:
+                assert np.asarray(snaps[0][k]).tobytes() == np.asarray(other[k]).tobytes(), "frame %d: %s differs between the two forms" % (f, k)
 
 
 @pytest.mark.parametrize("size", [(8, 8), (17, 9), (130, 70), (64, 2)])

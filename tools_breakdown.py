@@ -18,7 +18,7 @@ variants = [("default", {}), ("debug_normal(primary only)", dict(debugging_mode=
             ("maxDepth=1", dict(maxDepth=1)), ("maxDepth=2", dict(maxDepth=2)), ("maxDepth=4", dict(maxDepth=4)), ("MIS=0", dict(MIS=0))]
 frame = 0
 for name, over in variants:
-    rr.set_profiling(2)
+    rr.set_profiling(1)
     acc = np.zeros(5); n = 0
     for k in range(6):
         scene.update_camera(W, H)

@@ -1,10 +1,12 @@
 #!/bin/bash
-# usage (on the GPU box): tools_libsweep.sh <variant> ...   -> quick parity subset + per-kernel ms of bench.py for each prebuilt
-# cis-565-final-vr-raytracer_b200/libeidola_<variant>.so (EID_VARIANT=<variant> python .../build.py); "base" = libeidola.so
+# usage (on the GPU box): tools_libsweep.sh [-a "<bench args>"] <variant> ...   -> quick parity subset + per-kernel ms of bench.py for each
+# prebuilt cis-565-final-vr-raytracer_b200/libeidola_<variant>.so (EID_VARIANT=<variant> python .../build.py); "base" = libeidola.so
+ARGS=""
+if [ "$1" = "-a" ]; then ARGS="$2"; shift 2; fi
 for l in "$@"; do
   lib="$PWD/cis-565-final-vr-raytracer_b200/libeidola_$l.so"; [ "$l" = base ] && lib="$PWD/cis-565-final-vr-raytracer_b200/libeidola.so"
-  par=$(EIDOLA_LIB=$lib timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "traversal or c2 or alpha or small_room" 2>&1 | tail -1)
-  EIDOLA_LIB=$lib timeout 300 python bench.py --steps 16 --warmup 4 --no-cpu-baseline 2> gpurun_out/bench_$l.err | tail -1 > gpurun_out/bench_$l.json
+  par=$(EIDOLA_LIB=$lib timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "traversal or c2 or alpha or small_room or forms" 2>&1 | tail -1)
+  EIDOLA_LIB=$lib timeout 300 python bench.py --steps 16 --warmup 4 --no-cpu-baseline $ARGS 2> gpurun_out/bench_$l.err | tail -1 > gpurun_out/bench_$l.json
   python - "$l" "$par" <<'PY'
 import json,sys
 l,par=sys.argv[1],sys.argv[2]
