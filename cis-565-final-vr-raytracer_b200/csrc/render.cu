@@ -39,9 +39,10 @@ struct WaveView {
   float4* gsXv; float4* gsNv; float4* gsXs; float4* gsNs;   // GISample: (xv, primSamplePdf), nv, xs, ns
   float4* hitL;            // radiance added by the path's terminal emitter hit / environment miss (depth >= 2)
   float4* neeTerm;         // [k * slots + slot]: next-event-estimation term of depth k + 2 (added iff its shadow ray is unoccluded)
-  float4* shadowQ;         // any-hit queue of all depths; entry = (origin.xyz, tmax), (direction.xyz, id = k * slots + slot)
+  float4* shadowQ;         // any-hit queues, one of `slots` entries per NEE depth k; entry = (origin.xyz, tmax), (direction.xyz, id = k * slots + slot)
   uint32_t* occl;          // [id]: 1 = shadow ray occluded
-  uint32_t* ctr;           // [p] entries of the depth-p closest-hit queue (p >= 1), [0] entries of the shadow queue, [64 + i] fetch cursors
+  uint32_t* ctr;           // [p] entries of the depth-p closest-hit queue (p >= 1), [32 + k] entries of the shadow queue of NEE depth k + 2,
+                           // [64 + p] / [96 + k] the fetch cursors of those queues
 };
 #define GI_MULTIBOUNCE 1u
 #define GI_HITL 2u
@@ -494,7 +495,8 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
 //   k_trace_queue<false>    closest hits of queue d                                     (dynamic fetch, trace.cuh)
 //   k_gi_bounce(d)          miss / emitter / surface of the depth-d hit; for depth d+1: light sample -> shadow queue + its
 //                           MIS-weighted term, BSDF sample, throughput, next ray -> closest-hit queue d+1
-//   k_trace_queue<true>     every shadow ray of every depth in ONE launch (a shadow result only gates one addition)
+//   k_trace_queue<true>     the shadow rays of depth d+1, on a second stream beside the closest-hit chain of the deeper bounces
+//                           (a shadow result only gates one addition in k_gi_finish)
 //   k_gi_finish             L = ordered sum of the unoccluded NEE terms (+ the terminal emitter/environment term), ReSTIR GI
 // A shadow ray of an opaque scene consumes no RNG draw, so deferring it does not change any other value; the radiance terms
 // are added in the mega-kernel's order (NEE of depth 2, 3, ..., then the terminal term, which always comes last).
@@ -655,10 +657,11 @@ __global__ void __launch_bounds__(128) k_gi_bounce(const FrameParams P, int d) {
       misc.x = seed;
       V.misc[slot] = misc;
     }
-    const uint32_t js = warpEnqueue(&V.ctr[0], wantShadow);
+    const uint32_t js = warpEnqueue(&V.ctr[32 + d - 1], wantShadow);
     if (wantShadow) {
-      V.shadowQ[2 * (size_t)js] = make_float4(shO.x, shO.y, shO.z, shTmax);
-      V.shadowQ[2 * (size_t)js + 1] = make_float4(shD.x, shD.y, shD.z, __uint_as_float((uint32_t)(d - 1) * V.slots + slot));
+      float4* q = V.shadowQ + 2 * (size_t)(d - 1) * V.slots;
+      q[2 * (size_t)js] = make_float4(shO.x, shO.y, shO.z, shTmax);
+      q[2 * (size_t)js + 1] = make_float4(shD.x, shD.y, shD.z, __uint_as_float((uint32_t)(d - 1) * V.slots + slot));
     }
     const uint32_t jr = warpEnqueue(&V.ctr[d + 1], wantRay);
     if (wantRay) {
@@ -931,6 +934,7 @@ struct eid_renderer {
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
   // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
   void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
+  cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
   int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
   int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
   int smCount = 0;
@@ -1095,17 +1099,25 @@ static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st
     dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
     if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
-      // wavefront form: begin, then per depth (closest-hit queue, bounce), all shadow rays at once, finish
+      // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
+      // `shadow` stream while the main stream goes on with the next depth (small queues are latency-bound: the longest ray
+      // of the C3 scene needs ~150 dependent node visits, ~80 us, however few rays there are); join before finish
+      cudaStream_t sh = r->waveOverlap ? r->shadowStream : st;
       CUDA_CHECK(cudaMemsetAsync(P.wv.ctr, 0, 128 * sizeof(uint32_t), st));
       if (tex) k_gi_begin<true><<<g, b, 0, st>>>(P); else k_gi_begin<false><<<g, b, 0, st>>>(P);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
       const int gb = r->smCount * 8;
+      bool forked = false;
       for (int d = 1; d <= P.st.maxDepth; ++d) {
         launchTraceQueue<false>(r, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
         if (tex) k_gi_bounce<true><<<gb, 128, 0, st>>>(P, d); else k_gi_bounce<false><<<gb, 128, 0, st>>>(P, d);
         r->stats.kernelLaunches[EID_K_INDIRECT]++;
+        if (d + 1 <= P.st.maxDepth && P.st.MIS > 0) {
+          if (sh != st) { CUDA_CHECK(cudaEventRecord(r->evWave, st)); CUDA_CHECK(cudaStreamWaitEvent(sh, r->evWave, 0)); forked = true; }
+          launchTraceQueue<true>(r, P, P.wv.shadowQ + 2 * (size_t)(d - 1) * P.wv.slots, P.wv.ctr + 32 + d - 1, P.wv.ctr + 96 + d - 1, sh);
+        }
       }
-      if (P.st.maxDepth >= 2 && P.st.MIS > 0) launchTraceQueue<true>(r, P, P.wv.shadowQ, P.wv.ctr, P.wv.ctr + 64, st);
+      if (forked) { CUDA_CHECK(cudaEventRecord(r->evWaveJoin, sh)); CUDA_CHECK(cudaStreamWaitEvent(st, r->evWaveJoin, 0)); }
       k_gi_finish<<<g, b, 0, st>>>(P);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
     } else {
@@ -1298,6 +1310,8 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
     CUDA_CHECK(cudaEventCreateWithFlags(&r->evFork, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&r->evJoin, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreate(&r->evPost));
     CUDA_CHECK(cudaStreamCreateWithFlags(&r->aux, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&r->shadowStream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evWave, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&r->evWaveJoin, cudaEventDisableTiming));
     r->allocate();
   } catch (...) { eid_renderer_destroy(r); throw; }
   *out = r;
@@ -1330,6 +1344,8 @@ void eid_renderer_destroy(eid_renderer* r) {
   for (auto& e : r->ev) if (e) cudaEventDestroy(e);
   if (r->evFork) cudaEventDestroy(r->evFork); if (r->evJoin) cudaEventDestroy(r->evJoin); if (r->evPost) cudaEventDestroy(r->evPost);
   if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
+  if (r->shadowStream) { cudaStreamSynchronize(r->shadowStream); cudaStreamDestroy(r->shadowStream); }
+  if (r->evWave) cudaEventDestroy(r->evWave); if (r->evWaveJoin) cudaEventDestroy(r->evWaveJoin);
   if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
   if (r->evFrameDone) cudaEventDestroy(r->evFrameDone); if (r->evCopyDone) cudaEventDestroy(r->evCopyDone);
   cudaFree(r->staging[0]); cudaFree(r->staging[1]);
@@ -1626,6 +1642,7 @@ int eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks) {
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_wavefront: null renderer");
   if (traceBlocks < 0 || traceBlocks > 65535) raise(EID_ERR_INVALID, "eid_renderer_set_wavefront: traceBlocks out of range");
   r->wavefront = enabled != 0;
+  r->waveOverlap = enabled != 2;      // 2: wavefront with every queue on the main stream (strictly serial stages)
   r->traceBlocks = traceBlocks;
   return EID_OK;
   EID_CATCH

@@ -275,7 +275,8 @@ EID_API int  eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread);
 /* Form of indirect_stage (K2).  enabled = 1 (default): wavefront — the stage is cut at its ray queries into ray queues that a
  * persistent dynamic-fetch traversal kernel drains (every lane takes the next queued ray when its own ends); used whenever the
  * scene has no stochastic-alpha instance and maxDepth <= 25, otherwise (and with enabled = 0) the one-thread-per-pixel kernel
- * runs.  Both forms produce bit-identical buffers.  traceBlocks = grid of the traversal kernel in 128-thread blocks (0 = default). */
+ * runs.  enabled = 2: wavefront with the shadow-ray queues on the main stream too (default: a second stream, beside the deeper
+ * bounces).  All forms produce bit-identical buffers.  traceBlocks = grid of the traversal kernel in 128-thread blocks (0 = default). */
 EID_API int  eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks);
 /* Renderer::run(cmdBuf, state, profiler, descSets, frames) (renderer.cpp:154-206): enqueues
  * direct_stage, indirect_stage, denoise_direct x4, denoise_indirect x5, compose and returns.

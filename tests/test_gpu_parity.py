@@ -228,7 +228,7 @@ def test_indirect_stage_forms_bit_identical_large():
     psc = eid.Scene(0); psc.load_arrays(arrays)
     acc = eid.AccelStructure(); acc.create(psc)
     rrs = []
-    for on, blocks in ((0, 0), (1, 0), (1, 7), (1, 2000)):
+    for on, blocks in ((0, 0), (1, 0), (2, 0), (1, 7), (1, 2000)):
         rr = eid.Renderer(); rr.create(size, psc, acc); rr.set_env_constant(common.ENV); rr.set_wavefront(on, blocks)
         rrs.append(rr)
     info = psc.info()
