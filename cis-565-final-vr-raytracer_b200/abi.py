@@ -66,6 +66,24 @@ def default_rtx_state(width, height, **over):
     return s
 
 
+class SunAndSky(C.Structure):  # host_device.h:353-376
+    _fields_ = [("rgb_unit_conversion", Vec3), ("multiplier", C.c_float), ("haze", C.c_float), ("redblueshift", C.c_float),
+                ("saturation", C.c_float), ("horizon_height", C.c_float), ("ground_color", Vec3), ("horizon_blur", C.c_float),
+                ("night_color", Vec3), ("sun_disk_intensity", C.c_float), ("sun_direction", Vec3), ("sun_disk_scale", C.c_float),
+                ("sun_glow_intensity", C.c_float), ("y_is_up", C.c_int32), ("physically_scaled_sun", C.c_int32), ("in_use", C.c_int32)]
+
+
+def default_sun_and_sky(**over):
+    """SampleExample::m_sunAndSky defaults (sample_example.hpp:186-203); in_use = 0."""
+    s = SunAndSky(rgb_unit_conversion=Vec3(1, 1, 1), multiplier=0.0000101320, haze=0.0, redblueshift=0.0, saturation=1.0,
+                  horizon_height=0.0, ground_color=Vec3(0.4, 0.4, 0.4), horizon_blur=0.1, night_color=Vec3(0.0, 0.0, 0.01),
+                  sun_disk_intensity=0.8, sun_direction=Vec3(0.0, 0.78, 0.62), sun_disk_scale=5.0, sun_glow_intensity=1.0,
+                  y_is_up=1, physically_scaled_sun=1, in_use=0)
+    for k, v in over.items():
+        setattr(s, k, v)
+    return s
+
+
 class PrimMesh(C.Structure):
     _fields_ = [("firstIndex", C.c_uint32), ("indexCount", C.c_uint32), ("vertexOffset", C.c_uint32),
                 ("vertexCount", C.c_uint32), ("materialIndex", C.c_int32)]

@@ -170,7 +170,8 @@ DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float
   return traverse<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
 }
 
-DEV f3 envRadiance(const FrameParams& P, f3 dir) { return envTextureDir(P.env, dir) * P.st.hdrMultiplier; }   // EnvRadiance (pathtrace.glsl:40-47), HDR branch
+template <bool FULL>
+DEV f3 envRadiance(const FrameParams& P, f3 dir) { return envRadianceOf<FULL>(P.env, P.st, dir); }   // EnvRadiance (pathtrace.glsl:40-47)
 
 // encodeGeometryInfo (direct_stage.comp:37-45)
 DEV uint4 encodeGeometryInfo(const State& s, float depth) {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     if (!closestHit<STATS, TEX>(P, ro, rd, prd, seed, rc)) {                 // :154-158
       P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
       P.motion[pix] = make_short2(0, 0);
-      radiance = envRadiance(P, rd);
+      radiance = envRadiance<TEX>(P, rd);
     } else {
       rc.primary++;
       State st = getState<TEX>(P.sc, prd, rd);
@@ -454,8 +455,8 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
         closestHit<STATS, TEX>(P, rayO, rayD, prd, seed, rc);
         if (prd.hitT >= __fsub_rn(EID_INFINITY, 1e-4f)) {   // miss (:183-198)
           if (d > 1) {
-            const f3 env = envTextureDir(P.env, sampleWi);                    // EnvEval (pathtrace.glsl:60-72), HDR branch
-            const float lightPdf = __fmul_rn(__fmul_rn(lum3(env), P.st.envMapLuminIntegInv), P.st.environmentProb);
+            float lightPdf;
+            const f3 env = envEvalOf<TEX>(P.env, P.st, sampleWi, lightPdf);         // EnvEval (pathtrace.glsl:60-72)
             gs.L = gs.L + (env * throughput) * misWeight(P, samplePdf, lightPdf);
           } else {
             gs.xs = st.position + (sampleWi * EID_INFINITY) * 0.8f;
@@ -589,8 +590,8 @@ __global__ void __launch_bounds__(128) k_gi_bounce(const FrameParams P, int d) {
       const int tri = __float_as_int(h.w);
       if (tri < 0) {                                        // miss (:183-198)
         if (d > 1) {
-          const f3 env = envTextureDir(P.env, rayD);                        // EnvEval (pathtrace.glsl:60-72), HDR branch
-          const float lightPdf = __fmul_rn(__fmul_rn(lum3(env), P.st.envMapLuminIntegInv), P.st.environmentProb);
+          float lightPdf;
+          const f3 env = envEvalOf<TEX>(P.env, P.st, rayD, lightPdf);              // EnvEval (pathtrace.glsl:60-72)
           const f3 add = (env * throughput) * misWeight(P, samplePdf, lightPdf);
           V.hitL[slot] = make_float4(add.x, add.y, add.z, 0.f);
           misc.y |= GI_HITL;
@@ -911,6 +912,14 @@ __global__ void __launch_bounds__(256) k_compose(const FrameParams P, const floa
   }
 }
 
+// parity tap of sun_and_sky (sun_and_sky.glsl:453-601): one direction per thread
+__global__ void k_sun_and_sky(const SunAndSky ss, const float* __restrict__ dirs, uint32_t n, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const f3 c = sunAndSky(ss, mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]));
+  out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
 }  // namespace eid
 
 using namespace eid;
@@ -944,6 +953,7 @@ struct eid_renderer {
   unsigned long long* countersHost = nullptr;   // pinned
   float env[3] = {0.f, 0.f, 0.f};
   eid_env* envMap = nullptr;
+  SunAndSky sunSky{};         // SampleExample::m_sunAndSky (sample_example.hpp:186-203); in_use = 0 until the host sets it
   int lastSet = 0;
   RtxState lastState{};
   bool hasRun = false;
@@ -1033,8 +1043,8 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
     raise(EID_ERR_INVALID, "RtxState.size %dx%d outside the renderer allocation %ux%u", st.size.x, st.size.y, r->width, r->height);
   if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal)
     raise(EID_ERR_UNSUPPORTED, "spatial reuse (direct_stage.comp:224-255) is racy in the reference and outside the parity contract");
-  if (st.environmentProb > 0.0f && !r->envMap)
-    raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs an HDR environment map (eid_env_create + eid_renderer_set_env); sun & sky is not implemented");
+  if (st.environmentProb > 0.0f && !r->envMap && r->sunSky.in_use != 1)
+    raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs an environment to sample: an HDR map (eid_env_create + eid_renderer_set_env) or sun & sky (eid_renderer_set_sun_and_sky with in_use = 1)");
   if (st.RISSampleNum < 0 || st.maxDepth < 0) raise(EID_ERR_INVALID, "negative RISSampleNum / maxDepth");
   const int set = (frames + 1) % 2;   // renderer.cpp:157; set i: last* = [i], this* = [!i] (renderer.cpp:341-375)
   P.st = st;
@@ -1049,6 +1059,7 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
   P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
   for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
+  P.env.sunSky = r->sunSky;
   P.env.tex = r->envMap ? r->envMap->tex : nullptr; P.env.accel = r->envMap ? r->envMap->accel : nullptr;
   P.env.width = r->envMap ? (int)r->envMap->host.width : 0; P.env.height = r->envMap ? (int)r->envMap->host.height : 0;
   P.hasNonOpaque = r->scene->host.hasNonOpaque ? 1 : 0;
@@ -1077,7 +1088,7 @@ static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) 
   if (P.sCount > 0) {
     dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
-    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     if (r->countVisits) { if (tex) k_direct_stage<true, true><<<g, b, 0, st>>>(P); else k_direct_stage<true, false><<<g, b, 0, st>>>(P); }
     else { if (tex) k_direct_stage<false, true><<<g, b, 0, st>>>(P); else k_direct_stage<false, false><<<g, b, 0, st>>>(P); }
     r->stats.kernelLaunches[EID_K_DIRECT]++;
@@ -1097,7 +1108,7 @@ static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st
   markStart(r, EID_K_INDIRECT, st);
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
     dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
-    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque;
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
       // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
       // `shadow` stream while the main stream goes on with the next depth (small queues are latency-bound: the longest ray
@@ -1427,6 +1438,33 @@ int eid_renderer_set_env(eid_renderer* r, eid_env* e) {
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_env: null renderer");
   if (e && (e->device != r->device || !e->tex)) raise(EID_ERR_INVALID, "environment map lives on another device (or is host-only)");
   r->envMap = e;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_sun_and_sky(eid_renderer* r, const SunAndSky* ss) {
+  EID_TRY
+  if (!r || !ss) raise(EID_ERR_INVALID, "eid_renderer_set_sun_and_sky: null argument");
+  r->sunSky = *ss;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_sun_and_sky_eval(int device, const SunAndSky* ss, const float* dirs, uint32_t n, float* rgb) {
+  EID_TRY
+  if (!ss || !dirs || !rgb) raise(EID_ERR_INVALID, "eid_sun_and_sky_eval: null argument");
+  if (n == 0) return EID_OK;
+  CUDA_CHECK(cudaSetDevice(device));
+  float *dd = nullptr, *dout = nullptr;
+  CUDA_CHECK(cudaMalloc(&dd, (size_t)n * 12));
+  if (cudaMalloc(&dout, (size_t)n * 12) != cudaSuccess) { cudaFree(dd); raise(EID_ERR_CUDA, "cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(dd, dirs, (size_t)n * 12, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_sun_and_sky<<<(n + 63) / 64, 64>>>(*ss, dd, n, dout);
+    e = cudaMemcpy(rgb, dout, (size_t)n * 12, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(dd); cudaFree(dout);
+  if (e != cudaSuccess) raise(EID_ERR_CUDA, "eid_sun_and_sky_eval: %s", cudaGetErrorString(e));
   return EID_OK;
   EID_CATCH
 }

@@ -7,6 +7,7 @@
 // every function names the reference lines it implements.
 #pragma once
 #include "dmath.cuh"
+#include "sunsky.cuh"
 #include "trace.cuh"
 
 namespace eid {
@@ -305,12 +306,13 @@ DEV void getMaterials(const DeviceSceneView& sc, State& st, f3 rayDir) {
   st.eta = dot3(st.normal, st.ffnormal) > 0.0f ? __fdiv_rn(1.0f, st.mat.ior) : st.mat.ior;
 }
 
-// ---- environment (env_sampling.glsl, common.glsl:69-76, hdr_sampling.cpp sampler state) ------------------------
+// ---- environment (env_sampling.glsl, common.glsl:69-76, hdr_sampling.cpp sampler state; sun & sky in sunsky.cuh) --
 struct EnvView {
   const float4* tex;                 // RGBA32F lat-long map, null = constant environment `constant`
   const ImptSampData* accel;
   int width, height;
   float constant[3];
+  SunAndSky sunSky;                  // _sunAndSky uniform (layouts.glsl:53); in_use == 1 replaces the map / the constant
 };
 DEV void sphericalUv(f3 v, float& u, float& w) {                     // GetSphericalUv (common.glsl:69-76)
   const float gamma = eid_asinf(-v.y);
@@ -336,8 +338,39 @@ DEV f3 envTextureDir(const EnvView& E, f3 dir) {
   sphericalUv(dir, u, v);
   return envTextureUv(E, u, v);
 }
+// Sun & sky is compiled into the FULL kernel variants only (the ones that also carry texture taps and stochastic alpha): the host
+// selects them whenever SunAndSky.in_use == 1, and the lean variants keep their register / stack budget.
+// EnvRadiance (pathtrace.glsl:40-47)
+template <bool FULL>
+DEV f3 envRadianceOf(const EnvView& E, const RtxState& rs, f3 dir) {
+  if (FULL && E.sunSky.in_use == 1) return sunAndSky(E.sunSky, dir) * rs.hdrMultiplier;
+  return envTextureDir(E, dir) * rs.hdrMultiplier;
+}
+// EnvEval (pathtrace.glsl:60-72): the sun & sky branch returns radiance x hdrMultiplier and pdf 0.5, the HDR branch the bare texel
+template <bool FULL>
+DEV f3 envEvalOf(const EnvView& E, const RtxState& rs, f3 dir, float& pdf) {
+  if (FULL && E.sunSky.in_use == 1) {
+    pdf = __fmul_rn(0.5f, rs.environmentProb);
+    return sunAndSky(E.sunSky, dir) * rs.hdrMultiplier;
+  }
+  const f3 radiance = envTextureDir(E, dir);
+  pdf = __fmul_rn(__fmul_rn(lum3(radiance), rs.envMapLuminIntegInv), rs.environmentProb);
+  return radiance;
+}
 // EnvSample (env_sampling.glsl:100-135) -> Environment_sample (:38-94): three draws; returns the texel pdf, fills direction + radiance
+template <bool FULL>
 DEV float envSample(const EnvView& E, float hdrMultiplier, uint32_t& seed, f3& radiance, f3& toLight) {
+  if (FULL && E.sunSky.in_use == 1) {                              // env_sampling.glsl:111-125: a direction inside the sun's glow disc, two draws
+    const float sunRadius = __fmul_rn(__fmul_rn(0.00465f, 10.0f), E.sunSky.sun_disk_scale);
+    const f3 sd = ld3(E.sunSky.sun_direction);
+    f3 T, B;
+    createCoordinateSystem(sd, T, B);
+    const float dx = __fmul_rn(rnd(seed), sunRadius), dy = __fmul_rn(rnd(seed), sunRadius);
+    const float dz = __fsqrt_rn(gmax(0.0f, __fsub_rn(__fsub_rn(1.0f, __fmul_rn(dx, dx)), __fmul_rn(dy, dy))));
+    toLight = norm3((T * dx + B * dy) + sd * dz);
+    radiance = sunAndSky(E.sunSky, toLight) * hdrMultiplier;
+    return 0.5f;
+  }
   float xx = rnd(seed), xy = rnd(seed), xz = rnd(seed);
   const uint32_t width = (uint32_t)E.width, height = (uint32_t)E.height, size = width * height;
   const uint32_t idx = (uint32_t)min((int)f2u_sat(__fmul_rn(xx, (float)size)), (int)size - 1);
@@ -422,8 +455,8 @@ DEV float sampleDirectLightNoVisibility(const DeviceSceneView& sc, const EnvView
   const float r = rnd(seed);
   const float envProb = rs.environmentProb;
   if (r < envProb) {                         // sample the environment (:163-172)
-    if (!env.tex) return EID_INVALID_PDF;    // (unreachable: the host refuses environmentProb > 0 without an HDR map)
-    const float pdf = envSample(env, rs.hdrMultiplier, seed, ls.Li, ls.wi);
+    if (!env.tex && !(TEX && env.sunSky.in_use == 1)) return EID_INVALID_PDF;    // (unreachable: the host refuses environmentProb > 0 without an environment)
+    const float pdf = envSample<TEX>(env, rs.hdrMultiplier, seed, ls.Li, ls.wi);
     if (isPdfInvalid(pdf)) return EID_INVALID_PDF;
     ls.dist = EID_INFINITY;
     return __fmul_rn(pdf, envProb);

@@ -261,6 +261,12 @@ EID_API int   eid_env_read(eid_env* e, int what, void* dst, size_t bytes);
 /* install / remove (NULL) the HDR environment: EnvRadiance, EnvEval and EnvSample (pathtrace.glsl:40-72, env_sampling.glsl) then
  * use it; RtxState.environmentProb > 0 requires one */
 EID_API int   eid_renderer_set_env(eid_renderer* r, eid_env* e);
+/* the `_sunAndSky` uniform (layouts.glsl:53; SampleExample::m_sunAndSky, updated every frame at sample_example.cpp:172): with
+ * in_use == 1 the procedural sun & sky of shaders/sun_and_sky.glsl replaces the HDR map in EnvRadiance, EnvEval and EnvSample
+ * (pathtrace.glsl:40-72, env_sampling.glsl:111-125).  The struct is copied; default in_use = 0. */
+EID_API int   eid_renderer_set_sun_and_sky(eid_renderer* r, const SunAndSky* ss);
+/* parity tap: sun_and_sky(ss, dir) (sun_and_sky.glsl:453-601) for n host directions (3 floats each) -> n RGB triples, on `device` */
+EID_API int   eid_sun_and_sky_eval(int device, const SunAndSky* ss, const float* dirs, uint32_t n, float* rgb);
 /* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR
  * map is installed; default (0,0,0). */
 EID_API int  eid_renderer_set_env_constant(eid_renderer* r, const float rgb[3]);

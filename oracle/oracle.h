@@ -121,6 +121,7 @@ struct Renderer {
   std::vector<vec4> directResult, indirectResult;       // thisDirectResultImage / thisIndirectResultImage
   std::vector<vec4> denoiseTemp[4];                     // DirTempA, DirTempB, IndTempA, IndTempB
   vec3 envConstant;
+  SunAndSky sunSky{};                  // _sunAndSky uniform (layouts.glsl:53); in_use == 1 replaces the HDR map
   int lastSet = 0;
   std::atomic<uint64_t> closestRays{0}, anyRays{0}, primaryHits{0};
   double kernelMs[5] = {0, 0, 0, 0, 0};
@@ -132,6 +133,9 @@ struct Renderer {
   void runIndirect(const RtxState& st, int frames, int y0, int y1);
   void runPost(const RtxState& st, int frames);
 };
+
+// shaders/sun_and_sky.glsl:453-601 (oracle_sunsky.cpp)
+vec3 sun_and_sky(const SunAndSky& ss, vec3 in_direction);
 
 // alias table (src/alias_table.hpp:21-63)
 void discreteSampler1D(std::vector<float> values, std::vector<float>& prob, std::vector<int>& failId);

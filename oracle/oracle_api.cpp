@@ -150,6 +150,10 @@ ORC_API void orc_env_texture(Environment* e, const float* uv, int n, float* out)
   for (int i = 0; i < n; ++i) { vec3 c = e->texture(vec2(uv[2 * i], uv[2 * i + 1])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
 ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; return 0; }
+ORC_API int orc_renderer_set_sun_and_sky(Renderer* r, const SunAndSky* ss) { r->sunSky = *ss; return 0; }
+ORC_API void orc_sun_and_sky(const SunAndSky* ss, const float* dirs, int n, float* out) {   // known-answer tap
+  for (int i = 0; i < n; ++i) { vec3 c = sun_and_sky(*ss, vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
+}
 ORC_API int orc_renderer_set_env_constant(Renderer* r, const float* rgb) { r->envConstant = vec3(rgb[0], rgb[1], rgb[2]); return 0; }
 static RtxState g_lastState{};
 ORC_API int orc_renderer_run(Renderer* r, const RtxState* st, int frames) {

@@ -435,8 +435,15 @@ struct Ctx {
   }
   // texture(environmentTexture, uv).rgb — or the constant environment when no HDR map is installed (sun & sky: later row)
   vec3 envTexture(vec3 dir) { return rr.env ? rr.env->texture(GetSphericalUv(dir)) : rr.envConstant; }
-  vec3 EnvRadiance(vec3 dir) { return envTexture(dir) * rtxState.hdrMultiplier; }                  // pathtrace.glsl:40-47
+  vec3 EnvRadiance(vec3 dir) {                                                                       // pathtrace.glsl:40-47
+    if (rr.sunSky.in_use == 1) return sun_and_sky(rr.sunSky, dir) * rtxState.hdrMultiplier;
+    return envTexture(dir) * rtxState.hdrMultiplier;
+  }
   vec3 EnvEval(vec3 dir, float& pdf) {                                                               // pathtrace.glsl:60-72
+    if (rr.sunSky.in_use == 1) {
+      pdf = 0.5f * rtxState.environmentProb;
+      return sun_and_sky(rr.sunSky, dir) * rtxState.hdrMultiplier;
+    }
     vec3 radiance = envTexture(dir);
     pdf = luminance(radiance) * rtxState.envMapLuminIntegInv * rtxState.environmentProb;
     return radiance;
@@ -474,9 +481,25 @@ struct Ctx {
     to_light = vec3(cos_phi * sin_theta, cos_theta, sin_phi * sin_theta);
     return E.texture(vec2(u, v));
   }
-  // env_sampling.glsl:100-135 EnvSample (HDR branch; sun & sky is a later scope row)
+  // env_sampling.glsl:100-135 EnvSample
   vec4 EnvSample(vec3& radiance) {
     vec3 lightDir; float pdf;
+    if (rr.sunSky.in_use == 1) {                                                                     // :111-125
+      const SunAndSky& ss = rr.sunSky;
+      float sun_radius = (0.00465f * 10.0f) * ss.sun_disk_scale;
+      vec3 sunDirection = V(ss.sun_direction);
+      vec3 T, B;
+      CreateCoordinateSystem(sunDirection, T, B);
+      vec3 dir;
+      dir.x = rand() * sun_radius;
+      dir.y = rand() * sun_radius;
+      dir.z = sqrtf(gmax(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+      lightDir = normalize(T * dir.x + B * dir.y + sunDirection * dir.z);
+      radiance = sun_and_sky(ss, lightDir);
+      pdf = 0.5f;
+      radiance *= rtxState.hdrMultiplier;
+      return vec4(lightDir, pdf);
+    }
     float r0 = rand(); float r1 = rand(); float r2 = rand();
     radiance = Environment_sample(vec3(r0, r1, r2), lightDir, pdf);
     radiance *= rtxState.hdrMultiplier;
@@ -539,7 +562,7 @@ struct Ctx {
   float SampleDirectLightNoVisibility(vec3 pos, LightSample& lightSample) {                   // :161-183
     float r = rand();
     if (r < rtxState.environmentProb) {
-      if (!rr.env) return InvalidPdf;   // no HDR map installed: the C-ABI refuses environmentProb > 0 in that case
+      if (!rr.env && rr.sunSky.in_use != 1) return InvalidPdf;   // nothing to sample: the C-ABI refuses environmentProb > 0 in that case
       vec3 Li;
       vec4 dirAndPdf = EnvSample(Li);
       lightSample.Li = E(Li);

@@ -99,9 +99,12 @@ def test_oracle_bvh_equals_brute_force():
     assert a.trace(rays).tobytes() == b.trace(rays).tobytes()
 
 
-def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=None, wavefront=True, **state_over):
+def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=None, wavefront=True, sun_sky=None, **state_over):
     osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict, env_img=env_img)
     prr.set_wavefront(wavefront)
+    if sun_sky is not None:
+        orr.set_sun_and_sky(sun_sky)
+        prr.set_sun_and_sky(sun_sky)
     if env_img is not None:
         state_over = dict(common.env_state_overrides(prr._env.get_integral()), **state_over)
     for s in (osc, psc):
@@ -170,6 +173,49 @@ def test_hdr_environment_default_state(maker, size):
     worst = _run_frames(maker(), size, 4, "hdr-env " + maker.__name__, env_img=scenes.synthetic_sky())
     assert max(worst.values()) == 0.0
     _run_frames(maker(), size, 2, "hdr-env no sun, prob 0.6", env_img=scenes.synthetic_sky(sun=False), environmentProb=0.6, hdrMultiplier=2.0)
+
+
+@pytest.mark.parametrize("over", [dict(), dict(ReSTIRState=abi.eNone, denoise=0), dict(maxDepth=2, MIS=0)])
+@pytest.mark.parametrize("wavefront", [True, False])
+def test_sun_and_sky_environment(over, wavefront):
+    """SunAndSky.in_use = 1 (shaders/sun_and_sky.glsl): EnvRadiance on primary misses, EnvSample (two draws inside the sun's glow
+    disc, pdf 0.5) for 25 % of the light candidates, EnvEval on bounce misses; defaults of sample_example.hpp:186-203 and a low sun."""
+    for ss in (abi.default_sun_and_sky(in_use=1),
+               abi.default_sun_and_sky(in_use=1, sun_direction=abi.Vec3(0.6, 0.08, 0.35), haze=3.0, redblueshift=0.1, saturation=1.3, horizon_height=0.5)):
+        worst = _run_frames(scenes.cube_scene(), (160, 128), 3, "sun&sky %s" % over, sun_sky=ss, wavefront=wavefront,
+                            environmentProb=0.25, fireflyClampThreshold=50.0, **over)
+        assert max(worst.values()) == 0.0
+
+
+def test_sun_and_sky_function_matches_oracle():
+    """sun_and_sky(ss, dir) on the device == the oracle's restatement, bit for bit, over random directions and parameter sets."""
+    import ctypes as C
+    import oracle_lib as ol
+    rng = np.random.default_rng(11)
+    d = rng.normal(size=(20000, 3)).astype(np.float32)
+    d = np.ascontiguousarray(d / np.linalg.norm(d, axis=1, keepdims=True))
+    d[:2000] = (np.array([0.0, 0.78, 0.62], np.float32) / np.float32(0.99639) + 0.05 * d[:2000]).astype(np.float32)   # around the sun
+    d = np.ascontiguousarray(d / np.linalg.norm(d, axis=1, keepdims=True))
+    for ss in (abi.default_sun_and_sky(in_use=1), abi.default_sun_and_sky(in_use=1, haze=5.0, saturation=1.4, redblueshift=-0.2, horizon_height=-0.7, horizon_blur=0.0),
+               abi.default_sun_and_sky(in_use=1, sun_direction=abi.Vec3(0.7, -0.1, 0.2), physically_scaled_sun=0, y_is_up=0)):
+        want = np.zeros_like(d); got = np.zeros_like(d)
+        ol.lib().orc_sun_and_sky(C.byref(ss), d.ctypes.data, len(d), want.ctypes.data)
+        assert eid.lib().eid_sun_and_sky_eval(0, C.byref(ss), d.ctypes.data, len(d), got.ctypes.data) == 0
+        bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
+        assert bad.size == 0, "%d of %d directions differ, first: dir %s got %s want %s" % (bad.size, len(d), d[bad[0]], got[bad[0]], want[bad[0]])
+
+
+def test_sun_and_sky_off_needs_an_environment():
+    psc = eid.Scene(0); psc.load_arrays(scenes.cube_scene())
+    acc = eid.AccelStructure(); acc.create(psc)
+    rr = eid.Renderer(); rr.create((64, 64), psc, acc)
+    psc.update_camera(64, 64)
+    st = common.frame_state(64, 64, psc.info(), 0, environmentProb=0.25)
+    with pytest.raises(eid.EidolaError):
+        rr.run(st, 0)
+    rr.set_sun_and_sky(abi.default_sun_and_sky(in_use=1))
+    rr.run(st, 0); rr.sync()
+    assert np.isfinite(rr.read(abi.BUF_DIRECT)).all()
 
 
 def test_textured_materials_normal_maps_and_textured_emitters():

@@ -183,3 +183,29 @@ def test_oracle_invariants():
     st2 = orr.stats()
     n, ni = size[0] * size[1], (size[0] // 2) * (size[1] // 2)
     assert st2.closestHitRays <= n + ni * st.maxDepth and st2.anyHitRays <= n + ni * (st.maxDepth - 1)   # ray model of SURVEY §8(d)
+
+
+def test_sun_and_sky_known_behaviour():
+    """oracle/oracle_sunsky.cpp (shaders/sun_and_sky.glsl): no reference vectors exist for it, so pin its qualitative behaviour."""
+    from eidola_b200 import abi
+    L = ol.lib()
+
+    def sky(ss, dirs):
+        d = np.asarray(dirs, np.float32)
+        d = np.ascontiguousarray(d / np.linalg.norm(d, axis=1, keepdims=True))
+        out = np.zeros_like(d)
+        L.orc_sun_and_sky(C.byref(ss), d.ctypes.data, len(d), out.ctypes.data)
+        return out
+
+    ss = abi.default_sun_and_sky(in_use=1)
+    up, horizon, ground = sky(ss, [[0, 1, 0], [1, 0.02, 0], [0.3, -0.8, 0.1]])
+    assert np.isfinite([up, horizon, ground]).all() and (up > 0).all()
+    assert up[2] > up[0], "clear-sky zenith is blue"
+    assert horizon.sum() > up.sum(), "Perez sky brightens towards the horizon"
+    assert abs(ground[0] / ground[2] - 1.0) < 0.3, "below the horizon: grey ground colour times irradiance"
+    sd = np.array([0.0, 0.78, 0.62], np.float64); sd /= np.linalg.norm(sd)
+    off = sd + np.array([0.02, 0.0, 0.0])
+    assert sky(ss, [off])[0].sum() > 100 * up.sum(), "sun disc dominates"
+    assert (sky(abi.default_sun_and_sky(in_use=1, multiplier=0.0), [[0, 1, 0]]) == 0).all()          # sun_and_sky.glsl:475-478
+    night = sky(abi.default_sun_and_sky(in_use=1, sun_direction=abi.Vec3(0.0, -1.0, 0.0)), [[0, 1, 0]])[0]
+    assert np.allclose(night, np.float32(3.1415926535) * np.array([0.0, 0.0, 0.01], np.float32)), "midnight: night_color * pi"
