@@ -36,7 +36,7 @@ EXPORTS = [
     "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
-    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_overlap", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
+    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_overlap", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_renderer_run_output", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_render_host_async", "eid_renderer_wait_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
@@ -90,6 +90,7 @@ def lib():
         "eid_renderer_set_wavefront": (i32, [vp, i32, i32]),
         "eid_renderer_set_sun_and_sky": (i32, [vp, vp]),
         "eid_sun_and_sky_eval": (i32, [i32, vp, vp, u32, vp]),
+        "eid_renderer_run_output": (i32, [vp, vp]),
         "eid_renderer_set_overlap": (i32, [vp, i32]),
         "eid_renderer_run": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_sync": (i32, [vp]),
@@ -301,6 +302,9 @@ class Renderer:
 
     def set_denoise_rows(self, n):        # A-Trous pixels per thread sharing tap rows: 1, 2 (default) or 4
         _check(lib().eid_renderer_set_denoise_rows(self._h, int(n)))
+
+    def run_output(self, tm):             # RenderOutput::run -> post.frag; results in BUF_DISPLAY_F32 / BUF_DISPLAY_RGBA8
+        _check(lib().eid_renderer_run_output(self._h, C.byref(tm)))
 
     def set_sun_and_sky(self, ss):        # abi.SunAndSky (host_device.h:353-376); in_use = 1 selects the procedural sky
         _check(lib().eid_renderer_set_sun_and_sky(self._h, C.byref(ss)))

@@ -66,6 +66,25 @@ def default_rtx_state(width, height, **over):
     return s
 
 
+class Vec2(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float)]
+
+
+class Tonemapper(C.Structure):  # host_device.h:336-351
+    _fields_ = [("brightness", C.c_float), ("contrast", C.c_float), ("saturation", C.c_float), ("vignette", C.c_float),
+                ("avgLum", C.c_float), ("zoom", C.c_float), ("renderingRatio", Vec2), ("autoExposure", C.c_int32),
+                ("Ywhite", C.c_float), ("key", C.c_float), ("pad", C.c_int32)]
+
+
+def default_tonemapper(**over):
+    """RenderOutput::m_tm defaults (render_output.hpp:44-55)."""
+    t = Tonemapper(brightness=1.0, contrast=1.0, saturation=1.0, vignette=0.0, avgLum=1.0, zoom=1.0, renderingRatio=Vec2(1.0, 1.0),
+                   autoExposure=0, Ywhite=0.5, key=0.5, pad=0)
+    for k, v in over.items():
+        setattr(t, k, v)
+    return t
+
+
 class SunAndSky(C.Structure):  # host_device.h:353-376
     _fields_ = [("rgb_unit_conversion", Vec3), ("multiplier", C.c_float), ("haze", C.c_float), ("redblueshift", C.c_float),
                 ("saturation", C.c_float), ("horizon_height", C.c_float), ("ground_color", Vec3), ("horizon_blur", C.c_float),
@@ -161,7 +180,7 @@ class FrameStats(C.Structure):
 # eid_buffer
 (BUF_THIS_GBUFFER, BUF_LAST_GBUFFER, BUF_MOTION, BUF_THIS_DIRECT_RESV, BUF_LAST_DIRECT_RESV,
  BUF_THIS_INDIRECT_RESV, BUF_LAST_INDIRECT_RESV, BUF_DIRECT, BUF_INDIRECT, BUF_DENOISE_DIR_A,
- BUF_DENOISE_DIR_B, BUF_DENOISE_IND_A, BUF_DENOISE_IND_B) = range(13)
+ BUF_DENOISE_DIR_B, BUF_DENOISE_IND_A, BUF_DENOISE_IND_B, BUF_DISPLAY_F32, BUF_DISPLAY_RGBA8) = range(15)
 
 # ---- numpy views of the device tables --------------------------------------------------------------
 IMPT_DT = np.dtype([("alias", "<i4"), ("q", "<f4"), ("pdf", "<f4"), ("aliasPdf", "<f4")])
@@ -208,7 +227,7 @@ BUFFER_DTYPES = {BUF_THIS_GBUFFER: np.dtype("<u4"), BUF_LAST_GBUFFER: np.dtype("
                  BUF_LAST_INDIRECT_RESV: INDIRECT_RESV_DT, BUF_DIRECT: np.dtype("<f4"),
                  BUF_INDIRECT: np.dtype("<f4"), BUF_DENOISE_DIR_A: np.dtype("<f4"),
                  BUF_DENOISE_DIR_B: np.dtype("<f4"), BUF_DENOISE_IND_A: np.dtype("<f4"),
-                 BUF_DENOISE_IND_B: np.dtype("<f4")}
+                 BUF_DENOISE_IND_B: np.dtype("<f4"), BUF_DISPLAY_F32: np.dtype("<f4"), BUF_DISPLAY_RGBA8: np.dtype("u1")}
 
 
 class SceneArrays:

@@ -912,6 +912,75 @@ __global__ void __launch_bounds__(256) k_compose(const FrameParams P, const floa
   }
 }
 
+// =================================================================================================
+// Display pass — shaders/post.frag (RenderOutput::run, render_output.cpp:224-240) as a compute kernel: one thread per rendered
+// pixel (uvCoords = (pixel + 0.5) / size, tm.zoom = 1, tm.renderingRatio = (1, 1); the reference's sampler is NEAREST, so
+// texture(img, uvCoords) is texel (x, y)), direct + indirect, Uncharted-2 tonemap (tonemapping.glsl:39-95), pcg3d-noise dither at
+// 1/255 (post.frag:50-57, random.glsl:81-92), contrast / brightness / saturation / vignette.  Writes the float colour and its
+// RGBA8 packing (what a UNORM swapchain stores).  tm.autoExposure needs the blit-generated mip chain: not supported.
+// =================================================================================================
+DEV f3 pPow3(f3 c, float e) { return mk3(eid_powf(c.x, e), eid_powf(c.y, e), eid_powf(c.z, e)); }
+DEV f3 pUncharted2(f3 c) {
+  const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+  return ((c * ((A * c) + C * B)) + D * E) / ((c * ((A * c) + B)) + D * F) + (-(E / F));
+}
+DEV f3 pClamp01(f3 c) { return mk3(gmin(gmax(c.x, 0.0f), 1.0f), gmin(gmax(c.y, 0.0f), 1.0f), gmin(gmax(c.z, 0.0f), 1.0f)); }
+
+__global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemapper tm, float4* __restrict__ outF, uchar4* __restrict__ out8) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int W = P.st.size.x, H = P.st.size.y;
+  if (x >= W || y >= H) return;
+  const size_t pix = (size_t)y * P.pitch + x;
+  const float4 d4 = P.directImg[pix], i4 = P.indirectImg[pix];
+  const int mode = P.st.debugging_mode;
+  f3 color;
+  if (mode == eDepth) {
+    float depth = d4.w;
+    depth = depth * eid_powf(2.0f, tm.brightness);
+    depth = depth + tm.saturation;
+    depth = gmin(gmax(eid_powf(depth, 1.0f / tm.contrast), 0.0f), 1.0f);
+    color = mk3(depth);
+  } else if (mode > eIndirectStage) {
+    color = mk3(d4.x, d4.y, d4.z);
+    if (mode == eBaseColor) color = pClamp01(pPow3(color, 0.45454545454545f));
+  } else {
+    f3 hdr;
+    if (mode == eDirectStage) hdr = mk3(d4.x, d4.y, d4.z);
+    else if (mode == eIndirectStage) hdr = mk3(i4.x, i4.y, i4.z);
+    else hdr = mk3(d4.x, d4.y, d4.z) + mk3(i4.x, i4.y, i4.z);
+    // toneMap (TONEMAP_UNCHARTED): exposure, Uncharted 2 with white scale, linear -> sRGB
+    const float GAMMA = 2.2f, INV_GAMMA = 1.0f / 2.2f;
+    f3 c = hdr * tm.avgLum;
+    c = pUncharted2(c * 2.0f);
+    const f3 whiteScale = mk3(1.0f) / pUncharted2(mk3(11.2f));
+    color = pPow3(c * whiteScale, INV_GAMMA);
+    // dither (post.frag:50-57) with pcg3d noise of the pixel
+    uint32_t rx = (uint32_t)x, ry = (uint32_t)y, rz = 0u;
+    rx = rx * 1664525u + 1013904223u; ry = ry * 1664525u + 1013904223u; rz = rz * 1664525u + 1013904223u;
+    rx += ry * rz; ry += rz * rx; rz += rx * ry;
+    rx ^= rx >> 16; ry ^= ry >> 16; rz ^= rz >> 16;
+    rx += ry * rz; ry += rz * rx; rz += rx * ry;
+    const f3 noise = mk3(__uint_as_float(0x3f800000u | (rx >> 9)), __uint_as_float(0x3f800000u | (ry >> 9)), __uint_as_float(0x3f800000u | (rz >> 9))) + (-1.0f);
+    const f3 lin = pPow3(color, GAMMA);
+    const float quant = 1.0f / 255.0f;
+    const f3 q = pPow3(lin, INV_GAMMA) / quant;
+    const f3 c0 = mk3(eid_floorf(q.x), eid_floorf(q.y), eid_floorf(q.z)) * quant;
+    const f3 c1 = c0 + quant;
+    const f3 discr = mix3(pPow3(c0, GAMMA), pPow3(c1, GAMMA), noise);
+    color = mk3(discr.x < lin.x ? c1.x : c0.x, discr.y < lin.y ? c1.y : c0.y, discr.z < lin.z ? c1.z : c0.z);
+    color = pClamp01(mix3(mk3(0.5f), color, tm.contrast));                       // contrast
+    color = pPow3(color, 1.0f / tm.brightness);                                  // brightness
+    const float lumI = dot3(color, mk3(0.299f, 0.587f, 0.114f));                 // saturation
+    color = mix3(mk3(lumI), color, tm.saturation);
+    const float ux = ((((float)x + 0.5f) / (float)W) * tm.renderingRatio.x - 0.5f) * 2.0f;   // vignette
+    const float uy = ((((float)y + 0.5f) / (float)H) * tm.renderingRatio.y - 0.5f) * 2.0f;
+    color = color * (1.0f - (ux * ux + uy * uy) * tm.vignette);
+  }
+  outF[pix] = make_float4(color.x, color.y, color.z, 1.0f);
+  const uint32_t p8 = packUnorm4(color.x, color.y, color.z, 1.0f);
+  out8[pix] = make_uchar4((unsigned char)(p8 & 0xffu), (unsigned char)((p8 >> 8) & 0xffu), (unsigned char)((p8 >> 16) & 0xffu), (unsigned char)(p8 >> 24));
+}
+
 // parity tap of sun_and_sky (sun_and_sky.glsl:453-601): one direction per thread
 __global__ void k_sun_and_sky(const SunAndSky ss, const float* __restrict__ dirs, uint32_t n, float* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -941,6 +1010,7 @@ struct eid_renderer {
   float4* directImg = nullptr; float4* indirectImg = nullptr;
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
+  float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
   // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
   void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
   cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
@@ -981,6 +1051,7 @@ struct eid_renderer {
 void eid_renderer::release() {
   for (int i = 0; i < 2; ++i) { cudaFree(gbuffer[i]); cudaFree(directResv[i]); cudaFree(indirectResv[i]); gbuffer[i] = nullptr; directResv[i] = nullptr; indirectResv[i] = nullptr; }
   cudaFree(motion); motion = nullptr;
+  cudaFree(displayF); cudaFree(display8); displayF = nullptr; display8 = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
@@ -1295,6 +1366,8 @@ static void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
     case EID_BUF_INDIRECT: bytes = n * 16; return r->indirectImg;
     case EID_BUF_DENOISE_DIR_A: case EID_BUF_DENOISE_DIR_B: case EID_BUF_DENOISE_IND_A: case EID_BUF_DENOISE_IND_B:
       bytes = n * 16; return r->denoiseTemp[which - EID_BUF_DENOISE_DIR_A];
+    case EID_BUF_DISPLAY_F32: bytes = n * 16; return r->displayF;
+    case EID_BUF_DISPLAY_RGBA8: bytes = n * 4; return r->display8;
     default: return nullptr;
   }
 }
@@ -1446,6 +1519,28 @@ int eid_renderer_set_sun_and_sky(eid_renderer* r, const SunAndSky* ss) {
   EID_TRY
   if (!r || !ss) raise(EID_ERR_INVALID, "eid_renderer_set_sun_and_sky: null argument");
   r->sunSky = *ss;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
+  EID_TRY
+  if (!r || !tm) raise(EID_ERR_INVALID, "eid_renderer_run_output: null argument");
+  if (!r->hasRun) raise(EID_ERR_STATE, "eid_renderer_run_output: no frame has been rendered");
+  if (tm->autoExposure & 1) raise(EID_ERR_UNSUPPORTED, "post.frag auto exposure reads the blit-generated mip chain of the result images: not implemented");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  const size_t n = (size_t)r->width * r->height;
+  if (!r->displayF) {
+    CUDA_CHECK(cudaMalloc(&r->displayF, n * 16)); CUDA_CHECK(cudaMalloc(&r->display8, n * 4));
+    CUDA_CHECK(cudaMemsetAsync(r->displayF, 0, n * 16, r->stream)); CUDA_CHECK(cudaMemsetAsync(r->display8, 0, n * 4, r->stream));
+  }
+  FrameParams P;
+  memset(&P, 0, sizeof(P));
+  P.st = r->lastState; P.pitch = (int)r->width; P.allocH = (int)r->height;
+  P.directImg = r->directImg; P.indirectImg = r->indirectImg;
+  dim3 b(32, 8), g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
+  k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8);
+  CUDA_CHECK(cudaGetLastError());
   return EID_OK;
   EID_CATCH
 }

@@ -64,6 +64,7 @@ class Renderer {
   void update(Extent2D size) { check(eid_renderer_resize(m_h, size.width, size.height)); }
   void sync() { check(eid_renderer_sync(m_h)); }
   void setEnvironmentConstant(const float rgb[3]) { check(eid_renderer_set_env_constant(m_h, rgb)); }
+  void runOutput(const Tonemapper& tm) { check(eid_renderer_run_output(m_h, &tm)); }   // RenderOutput::run -> post.frag (render_output.cpp:224-240)
   void setSunAndSky(const SunAndSky& ss) { check(eid_renderer_set_sun_and_sky(m_h, &ss)); }   // SampleExample::m_sunAndSky (sample_example.cpp:172)
   void setWavefront(bool on, int traceBlocks = 0) { check(eid_renderer_set_wavefront(m_h, on ? 1 : 0, traceBlocks)); }
   void setStrictMath(bool on) { check(eid_renderer_set_strict_math(m_h, on ? 1 : 0)); }

@@ -215,7 +215,9 @@ typedef enum eid_buffer {
   EID_BUF_DIRECT = 7,              /* thisDirectResultImage   float x4 / pixel             */
   EID_BUF_INDIRECT = 8,            /* thisIndirectResultImage float x4 / pixel             */
   EID_BUF_DENOISE_DIR_A = 9, EID_BUF_DENOISE_DIR_B = 10,
-  EID_BUF_DENOISE_IND_A = 11, EID_BUF_DENOISE_IND_B = 12
+  EID_BUF_DENOISE_IND_A = 11, EID_BUF_DENOISE_IND_B = 12,
+  EID_BUF_DISPLAY_F32 = 13,        /* output of eid_renderer_run_output: float x4 / pixel    */
+  EID_BUF_DISPLAY_RGBA8 = 14       /* ... and its UNORM8 packing, 4 bytes / pixel            */
 } eid_buffer;
 
 /* kernels of one Renderer::run, in launch order */
@@ -278,6 +280,11 @@ EID_API int  eid_renderer_set_strict_math(eid_renderer* r, int enabled);
  * overlapping tap rows: 1 = 25 loads per pixel, 2 (default, measured fastest on B200) = 15, 4 = 10 but 110 registers.
  * Results are bit-identical for every setting. */
 EID_API int  eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread);
+/* RenderOutput::run (render_output.cpp:224-240) -> shaders/post.frag as a compute pass over the frame rendered last: direct +
+ * indirect (or the debug view selected by that frame's RtxState.debugging_mode), Uncharted-2 tonemap, dither, contrast /
+ * brightness / saturation / vignette, evaluated 1:1 (one output pixel per rendered pixel, zoom 1, renderingRatio (1,1) unless set
+ * in `tm`).  Enqueued on the renderer's stream; results in EID_BUF_DISPLAY_F32 / EID_BUF_DISPLAY_RGBA8.  tm->autoExposure must be 0. */
+EID_API int  eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm);
 /* Form of indirect_stage (K2).  enabled = 1 (default): wavefront — the stage is cut at its ray queries into ray queues that a
  * persistent dynamic-fetch traversal kernel drains (every lane takes the next queued ray when its own ends); used whenever the
  * scene has no stochastic-alpha instance and maxDepth <= 25, otherwise (and with enabled = 0) the one-thread-per-pixel kernel

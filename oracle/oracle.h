@@ -134,6 +134,8 @@ struct Renderer {
   void runPost(const RtxState& st, int frames);
 };
 
+// shaders/post.frag main for one pixel (oracle_post.cpp)
+vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height);
 // shaders/sun_and_sky.glsl:453-601 (oracle_sunsky.cpp)
 vec3 sun_and_sky(const SunAndSky& ss, vec3 in_direction);
 

@@ -150,6 +150,18 @@ ORC_API void orc_env_texture(Environment* e, const float* uv, int n, float* out)
   for (int i = 0; i < n; ++i) { vec3 c = e->texture(vec2(uv[2 * i], uv[2 * i + 1])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
 ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; return 0; }
+// RenderOutput::run over the frame rendered last: out = width*height RGBA32F at the allocation pitch
+ORC_API int orc_renderer_run_output(Renderer* r, const Tonemapper* tm, const RtxState* st, float* out) {
+  const int W = st->size.x, H = st->size.y;
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const size_t pix = (size_t)y * r->width + x;
+      const vec4 c = post_frag(*tm, st->debugging_mode, r->directResult[pix], r->indirectResult[pix], x, y, W, H);
+      out[4 * pix] = c.x; out[4 * pix + 1] = c.y; out[4 * pix + 2] = c.z; out[4 * pix + 3] = c.w;
+    }
+  return 0;
+}
 ORC_API int orc_renderer_set_sun_and_sky(Renderer* r, const SunAndSky* ss) { r->sunSky = *ss; return 0; }
 ORC_API void orc_sun_and_sky(const SunAndSky* ss, const float* dirs, int n, float* out) {   // known-answer tap
   for (int i = 0; i < n; ++i) { vec3 c = sun_and_sky(*ss, vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }

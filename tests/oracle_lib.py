@@ -53,7 +53,7 @@ def lib():
             "orc_renderer_set_env": (i32, [vp, vp]),
             "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
             "orc_renderer_set_env_constant": (i32, [vp, fp]),
-            "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
+            "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_renderer_run_output": (i32, [vp, vp, vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
             "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
             "orc_renderer_run_trace": (i32, [vp, C.POINTER(abi.RtxState), i32, i32, i32]),
             "orc_renderer_run_post": (i32, [vp, C.POINTER(abi.RtxState), i32]),
@@ -180,6 +180,11 @@ class OracleRenderer:
 
     def set_sun_and_sky(self, ss):
         lib().orc_renderer_set_sun_and_sky(self._h, C.byref(ss))
+
+    def run_output(self, tm, state):
+        out = np.zeros((self.size[1], self.size[0], 4), np.float32)
+        lib().orc_renderer_run_output(self._h, C.byref(tm), C.byref(state), out.ctypes.data)
+        return out
 
     def set_env(self, env):
         lib().orc_renderer_set_env(self._h, env._h if env is not None else None)

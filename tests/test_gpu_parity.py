@@ -187,6 +187,36 @@ def test_sun_and_sky_environment(over, wavefront):
         assert max(worst.values()) == 0.0
 
 
+@pytest.mark.parametrize("mode", [abi.eNoDebug, abi.eDirectStage, abi.eIndirectStage, abi.eBaseColor, abi.eDepth])
+def test_display_pass_post_frag(mode):
+    """RenderOutput::run -> post.frag (tonemap, dither, contrast / brightness / saturation / vignette) on the frame rendered last:
+    float output bit-identical to the oracle's restatement, RGBA8 = round-half-away packing of it."""
+    size = (200, 120)
+    osc, orr, psc, acc, prr = common.make_pair(scenes.cornell_scene(), size)
+    for s_ in (osc, psc):
+        s_.update_camera(*size)
+    info = psc.info()
+    for f in range(2):
+        for s_ in (osc, psc):
+            s_.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, maxDepth=3, debugging_mode=mode)
+        orr.run(st, f); prr.run(st, f)
+    for tm in (abi.default_tonemapper(), abi.default_tonemapper(brightness=1.3, contrast=0.8, saturation=0.6, vignette=0.4, avgLum=2.5)):
+        if mode == abi.eDepth:
+            tm = abi.default_tonemapper(brightness=0.0, contrast=2.2, saturation=0.0)     # RenderOutput::m_depthTm (render_output.hpp:56-60)
+        want = orr.run_output(tm, st)
+        prr.run_output(tm); prr.sync()
+        got = prr.read(abi.BUF_DISPLAY_F32).reshape(size[1], size[0], 4)
+        assert np.isfinite(want[..., :3]).all() or mode == abi.eDepth
+        assert got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes(), "display pass differs from the oracle (max abs %g)" % np.nanmax(np.abs(got - want))
+        got8 = prr.read(abi.BUF_DISPLAY_RGBA8).reshape(size[1], size[0], 4)
+        c = np.nan_to_num(np.clip(want.astype(np.float32), 0.0, 1.0), nan=0.0)
+        want8 = np.floor(c * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+        assert np.array_equal(got8, want8)
+    with pytest.raises(eid.EidolaError):
+        prr.run_output(abi.default_tonemapper(autoExposure=1))
+
+
 def test_sun_and_sky_function_matches_oracle():
     """sun_and_sky(ss, dir) on the device == the oracle's restatement, bit for bit, over random directions and parameter sets."""
     import ctypes as C
