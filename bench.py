@@ -108,6 +108,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per frame and stage, from the committed `ncu --set full` capture of this workload
+# (profiles/r01_g_ncu_full_summary.txt); the dominant stage is a single launch, so per frame == per launch there
+NCU_DRAM_SOURCE = "profiles/r01_g_ncu_full_summary.txt (ncu --set full, one C3 frame, single GPU)"
+NCU_DRAM_BYTES_PER_FRAME = {"c3": {"direct_stage": 298.9e6, "indirect_stage": 484.9e6, "denoise_direct": 531.2e6, "denoise_indirect": 125.0e6, "compose": 90.8e6}}
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -404,7 +410,8 @@ def run_cuda(args):
             "gpu_launches": int(sum(launches)) * args.steps, "launches_per_frame": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (NCU_DRAM_BYTES_PER_FRAME.get(_ACTIVE, {}).get(names[dom], None) if world == 1 and not args.quick else None),
+                         "traffic_source": NCU_DRAM_SOURCE, "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes (screen-space bytes of SURVEY 8d + counted BVH node/triangle fetches + per-hit "
                                  "vertex/material gathers) / CUDA-event time of that kernel; at 1 M triangles the traversal working set is "
                                  "L2-resident, so this is an L2/latency-bound kernel measured against the HBM roof"},

@@ -103,6 +103,17 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 #define EID_FETCH_TEX 2     // 0: every BVH fetch is an LDG; 2: far planes of a node come through tex1Dfetch (default); 1/3/4: experiments
 #endif
 
+// eid_accel_build refuses a BVH whose depth could overflow the traversal stack (3 * levels + 1 < EID_STACK_SIZE), so the pushes
+// need no bound check; -DEID_STACK_CHECK=1 puts the checks back (debug builds)
+#ifndef EID_STACK_CHECK
+#define EID_STACK_CHECK 0
+#endif
+#if EID_STACK_CHECK
+#define EID_SP_OK(sp) ((sp) < EID_STACK_SIZE)
+#else
+#define EID_SP_OK(sp) true
+#endif
+
 #define EID_TRAV_DONE ((int)0x80000000)   // never a valid reference (it would be a leaf starting at triangle 2^28 - 1)
 
 // One inner-node visit: box tests of the children, `cur` becomes the next reference to look at (nearest entered child, or the
@@ -120,7 +131,7 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
   bool h0 = e0 < INF, h1 = e1 < INF;
   if (h0 && h1) {
     if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
-    if (sp < EID_STACK_SIZE) stack[sp++] = c1;
+    if (EID_SP_OK(sp)) stack[sp++] = c1;
     cur = c0;
   } else if (h0) cur = c0;
   else if (h1) cur = c1;
@@ -165,9 +176,9 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
     // occlusion rays: order is irrelevant, just visit every child the ray enters
     int next = 0; bool have = false;
     if (e0 < INF) { next = c0; have = true; }
-    if (e1 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c1; } else { next = c1; have = true; } }
-    if (e2 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c2; } else { next = c2; have = true; } }
-    if (e3 < INF) { if (have) { if (sp < EID_STACK_SIZE) stack[sp++] = c3; } else { next = c3; have = true; } }
+    if (e1 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c1; } else { next = c1; have = true; } }
+    if (e2 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c2; } else { next = c2; have = true; } }
+    if (e3 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c3; } else { next = c3; have = true; } }
     cur = have ? next : EID_POP();
   } else {
     // sort the four (entry distance, ref) pairs ascending: 5-comparator network
@@ -175,9 +186,9 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
     EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2) EID_CSWAP(e1, c1, e3, c3) EID_CSWAP(e1, c1, e2, c2)
 #undef EID_CSWAP
     if (e0 < INF) {
-      if (e3 < INF && sp < EID_STACK_SIZE) stack[sp++] = c3;
-      if (e2 < INF && sp < EID_STACK_SIZE) stack[sp++] = c2;
-      if (e1 < INF && sp < EID_STACK_SIZE) stack[sp++] = c1;
+      if (e3 < INF && EID_SP_OK(sp)) stack[sp++] = c3;
+      if (e2 < INF && EID_SP_OK(sp)) stack[sp++] = c2;
+      if (e1 < INF && EID_SP_OK(sp)) stack[sp++] = c1;
       cur = c0;
     } else cur = EID_POP();
   }
