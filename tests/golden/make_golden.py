@@ -63,18 +63,25 @@ def ref_vectors():
 
 
 def frame_dumps():
-    for name, (maker, size, frames, over) in cfg.CONFIGS.items():
+    from eidola_b200 import abi
+    for name, entry in cfg.CONFIGS.items():
+        maker, size, frames, over = entry[:4]
         arrays = maker()
         osc = ol.OracleScene()
         osc.load_arrays(arrays)
         orr = ol.OracleRenderer(osc, size)
         orr.set_env_constant(common.ENV)
+        ss = cfg.sun_sky_of(entry)
+        if ss is not None:
+            orr.set_sun_and_sky(ss)
         osc.update_camera(*size)
         info = osc.info()
         for f in range(frames):
             osc.update_camera(*size)
-            orr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+            st = common.frame_state(size[0], size[1], info, f, **over)
+            orr.run(st, f)
         snap = common.snapshot(orr)
+        snap["display"] = orr.run_output(abi.default_tonemapper(), st)
         np.savez_compressed(os.path.join(HERE, "frames_%s.npz" % name), **{k: v.view(np.uint8) if v.dtype.fields else v for k, v in snap.items()})
         print("wrote frames_%s.npz" % name)
 

@@ -505,7 +505,7 @@ def test_golden_frames():
     for fn in files:
         z = np.load(os.path.join(gdir, fn))
         name = fn[len("frames_"):-4]
-        maker, size, frames, over = cfg.CONFIGS[name]
+        maker, size, frames, over = cfg.CONFIGS[name][:4]
         arrays = maker()
         psc = eid.Scene(0)
         psc.load_arrays(arrays)
@@ -515,12 +515,20 @@ def test_golden_frames():
         prr.create(size, psc, acc)
         prr.set_env_constant(common.ENV)
         prr.set_strict_math(True)
+        ss = cfg.sun_sky_of(cfg.CONFIGS[name])
+        if ss is not None:
+            prr.set_sun_and_sky(ss)
         psc.update_camera(*size)
         info = psc.info()
         for f in range(frames):
             psc.update_camera(*size)
             prr.run(common.frame_state(size[0], size[1], info, f, **over), f)
         got = common.snapshot(prr)
+        if "display" in z.files:
+            prr.run_output(abi.default_tonemapper())
+            prr.sync()
+            disp = prr.read(abi.BUF_DISPLAY_F32).reshape(size[1], size[0], 4)
+            assert disp.view(np.uint32).tobytes() == z["display"].view(np.uint32).tobytes(), "golden %s: display pass differs" % name
         want = {k: z[k].view(got[k].dtype) if got[k].dtype.fields is None else np.frombuffer(z[k].tobytes(), got[k].dtype) for k in got}
         common.compare_snapshots(got, want, "golden " + name)
 

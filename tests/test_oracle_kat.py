@@ -144,19 +144,28 @@ def test_oracle_golden_frames_are_reproducible():
     import common
     import make_golden_cfg as cfg
     gdir = os.path.join(os.path.dirname(__file__), "golden")
-    for name, (maker, size, frames, over) in cfg.CONFIGS.items():
+    from eidola_b200 import abi
+    for name, entry in cfg.CONFIGS.items():
+        maker, size, frames, over = entry[:4]
         z = np.load(os.path.join(gdir, "frames_%s.npz" % name))
         osc = ol.OracleScene()
         osc.load_arrays(maker())
         orr = ol.OracleRenderer(osc, size)
         orr.set_env_constant(common.ENV)
+        ss = cfg.sun_sky_of(entry)
+        if ss is not None:
+            orr.set_sun_and_sky(ss)
         osc.update_camera(*size)
         info = osc.info()
         for f in range(frames):
             osc.update_camera(*size)
-            orr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+            st = common.frame_state(size[0], size[1], info, f, **over)
+            orr.run(st, f)
         for k, v in common.snapshot(orr).items():
             assert v.view(np.uint8).tobytes() == z[k].view(np.uint8).tobytes(), (name, k)
+        disp = orr.run_output(abi.default_tonemapper(), st)
+        assert disp.view(np.uint8).tobytes() == z["display"].view(np.uint8).tobytes(), (name, "display")
+        assert np.isfinite(disp).all() and disp[..., :3].min() >= 0.0 and disp[..., :3].max() <= 1.0 + 1.0 / 255.0
 
 
 def test_oracle_invariants():
