@@ -333,6 +333,35 @@ def test_ragged_sizes(size):
     _run_frames(scenes.cornell_scene(), size, 2, "size %dx%d" % size, maxDepth=2)
 
 
+def _tiny_scene(n_tris, with_light=True, emissive=False):
+    _Builder, IDENTITY = scenes._Builder, scenes.IDENTITY
+    b = _Builder()
+    mat = b.add_material(base=(0.7, 0.6, 0.5, 1.0), metallic=0.2, roughness=0.6, **(dict(emissive=(4.0, 3.0, 2.0)) if emissive else {}))
+    tris = [[(-1.0, -0.5 + 0.3 * k, 0.2 * k), (1.0, -0.5 + 0.3 * k, 0.2 * k), (0.0, 0.8 + 0.1 * k, 0.2 * k + 0.1)] for k in range(n_tris)]
+    if n_tris:
+        b.add_tris(np.array(tris)[:, ::-1], mat)      # facing the camera at -z
+    if with_light:
+        m = list(IDENTITY); m[12], m[13], m[14] = 0.5, 2.0, -3.0
+        b.lights.append(dict(worldMatrix=m, type=1, color=(1.0, 0.9, 0.8), intensity=20.0))
+    cam = dict(eye=(0.2, 0.4, -4.0), center=(0.0, 0.2, 0.0), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(50.0)))
+    return b.build(cam, "tiny%d" % n_tris)
+
+
+@pytest.mark.parametrize("wavefront", [True, False])
+@pytest.mark.parametrize("n_tris,with_light,emissive", [(1, True, False), (2, False, False), (3, False, True), (5, True, True)])
+def test_degenerate_scenes(n_tris, with_light, emissive, wavefront):
+    """One-leaf BVHs (the root reference is a leaf), scenes without any light (every light sample is InvalidPdf), emissive-only scenes:
+    the queue traversal and both K2 forms against the oracle."""
+    _run_frames(_tiny_scene(n_tris, with_light, emissive), (96, 64), 3, "tiny %d %s %s" % (n_tris, with_light, emissive), wavefront=wavefront, maxDepth=3)
+
+
+@pytest.mark.parametrize("over", [dict(maxDepth=0), dict(RISSampleNum=0), dict(maxDepth=25), dict(maxDepth=26)])
+def test_extreme_state_values(over):
+    """maxDepth 0 (no bounce at all), no light candidates, the deepest wavefront depth (25) and the first one that falls back to the
+    one-thread-per-pixel kernel (26)."""
+    _run_frames(scenes.cornell_scene(), (64, 48), 2, "extreme %s" % over, **over)
+
+
 def test_state_size_smaller_than_allocation():
     """De-scaling (sample_example.cpp:396-401): RtxState.size below the allocated size; reservoirs are pitched by size.x."""
     arrays = scenes.cornell_scene()
