@@ -924,6 +924,13 @@ DEV f3 pUncharted2(f3 c) {
   const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
   return ((c * ((A * c) + C * B)) + D * E) / ((c * ((A * c) + B)) + D * F) + (-(E / F));
 }
+// toneMap (tonemapping.glsl:78-95, TONEMAP_UNCHARTED): exposure, Uncharted 2 with white scale, linear -> sRGB
+DEV f3 pToneMap(f3 hdr, float exposure) {
+  f3 c = hdr * exposure;
+  c = pUncharted2(c * 2.0f);
+  const f3 whiteScale = mk3(1.0f) / pUncharted2(mk3(11.2f));
+  return pPow3(c * whiteScale, 1.0f / 2.2f);
+}
 DEV f3 pClamp01(f3 c) { return mk3(gmin(gmax(c.x, 0.0f), 1.0f), gmin(gmax(c.y, 0.0f), 1.0f), gmin(gmax(c.z, 0.0f), 1.0f)); }
 
 __global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemapper tm, float4* __restrict__ outF, uchar4* __restrict__ out8) {
@@ -950,10 +957,7 @@ __global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemap
     else hdr = mk3(d4.x, d4.y, d4.z) + mk3(i4.x, i4.y, i4.z);
     // toneMap (TONEMAP_UNCHARTED): exposure, Uncharted 2 with white scale, linear -> sRGB
     const float GAMMA = 2.2f, INV_GAMMA = 1.0f / 2.2f;
-    f3 c = hdr * tm.avgLum;
-    c = pUncharted2(c * 2.0f);
-    const f3 whiteScale = mk3(1.0f) / pUncharted2(mk3(11.2f));
-    color = pPow3(c * whiteScale, INV_GAMMA);
+    color = pToneMap(hdr, tm.avgLum);
     // dither (post.frag:50-57) with pcg3d noise of the pixel
     uint32_t rx = (uint32_t)x, ry = (uint32_t)y, rz = 0u;
     rx = rx * 1664525u + 1013904223u; ry = ry * 1664525u + 1013904223u; rz = rz * 1664525u + 1013904223u;
@@ -979,6 +983,37 @@ __global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemap
   outF[pix] = make_float4(color.x, color.y, color.z, 1.0f);
   const uint32_t p8 = packUnorm4(color.x, color.y, color.z, 1.0f);
   out8[pix] = make_uchar4((unsigned char)(p8 & 0xffu), (unsigned char)((p8 >> 8) & 0xffu), (unsigned char)((p8 >> 16) & 0xffu), (unsigned char)(p8 >> 24));
+}
+
+// parity taps of the device-side shader functions (same numbering and arity as the oracle's orc_fn / the reference-GLSL ref_fn of
+// oracle/ref_shim): 0 toConcentricDisk, 1 powerHeuristic, 2 GetSphericalUv, 3 CreateCoordinateSystem, 4 HDRToLDR, 5 LDRToHDR,
+// 6 metallicWorkflowBSDF, 7 metallicWorkflowPdf, 8 metallicWorkflowSample, 11 toneMap, 12 OffsetRay, 13 tea, 14 rand x2
+// (9 / 10, the reservoir operations, are written inline in the stage kernels and are covered by the frame-level parity tests)
+__global__ void k_fn_tap(int which, int ni, int no, const float* __restrict__ in, uint32_t n, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = in + (size_t)i * ni;
+  float* o = out + (size_t)i * no;
+  auto v3 = [](const float* q) { return mk3(q[0], q[1], q[2]); };
+  auto put = [](float* q, f3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; };
+  State st;
+  st.mat.albedo = v3(p); st.mat.roughness = ni >= 14 ? p[3] : 0.f; st.mat.metallic = ni >= 14 ? p[4] : 0.f;
+  switch (which) {
+    case 0: toConcentricDisk(p[0], p[1], o[0], o[1]); break;
+    case 1: o[0] = powerHeuristic(p[0], p[1]); break;
+    case 2: sphericalUv(v3(p), o[0], o[1]); break;
+    case 3: { f3 t, b; createCoordinateSystem(v3(p), t, b); put(o, t); put(o + 3, b); break; }
+    case 4: put(o, hdrToLdr(v3(p))); break;
+    case 5: put(o, ldrToHdr(v3(p))); break;
+    case 6: put(o, bsdfEval(st.mat.albedo, st.mat.roughness, st.mat.metallic, v3(p + 5), v3(p + 8), v3(p + 11))); break;
+    case 7: o[0] = bsdfPdf(st.mat.roughness, st.mat.metallic, v3(p + 5), v3(p + 8), v3(p + 11)); break;
+    case 8: { f3 bsdf = mk3(0.f), dir = mk3(0.f); o[0] = bsdfSampleR(st, v3(p + 5), v3(p + 8), p[11], p[12], p[13], bsdf, dir); put(o + 1, bsdf); put(o + 4, dir); break; }
+    case 11: put(o, pToneMap(v3(p), p[3])); break;
+    case 12: put(o, offsetRay(v3(p), v3(p + 3))); break;
+    case 13: o[0] = __uint_as_float(tea(__float_as_uint(p[0]), __float_as_uint(p[1]))); break;
+    case 14: { uint32_t s = __float_as_uint(p[0]); const float a = rnd(s), b = rnd(s); o[0] = a; o[1] = b; o[2] = __uint_as_float(s); break; }
+    default: break;
+  }
 }
 
 // parity tap of sun_and_sky (sun_and_sky.glsl:453-601): one direction per thread
@@ -1541,6 +1576,29 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
   dim3 b(32, 8), g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
   k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8);
   CUDA_CHECK(cudaGetLastError());
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_fn_tap(int device, int which, const float* in, uint32_t n, float* out) {
+  EID_TRY
+  static const int A[][2] = {{2, 2}, {2, 1}, {3, 2}, {3, 6}, {3, 3}, {3, 3}, {14, 3}, {14, 1}, {14, 7}, {0, 0}, {0, 0}, {4, 3}, {6, 3}, {2, 1}, {2, 3}};
+  if (!in || !out) raise(EID_ERR_INVALID, "eid_fn_tap: null argument");
+  if (which < 0 || which >= (int)(sizeof(A) / sizeof(A[0])) || A[which][0] == 0) raise(EID_ERR_INVALID, "eid_fn_tap: no device tap %d", which);
+  if (n == 0) return EID_OK;
+  const int ni = A[which][0], no = A[which][1];
+  CUDA_CHECK(cudaSetDevice(device));
+  float *din = nullptr, *dout = nullptr;
+  CUDA_CHECK(cudaMalloc(&din, (size_t)n * ni * 4));
+  if (cudaMalloc(&dout, (size_t)n * no * 4) != cudaSuccess) { cudaFree(din); raise(EID_ERR_CUDA, "cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(din, in, (size_t)n * ni * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(dout, 0, (size_t)n * no * 4);
+  if (e == cudaSuccess) {
+    k_fn_tap<<<(n + 63) / 64, 64>>>(which, ni, no, din, n, dout);
+    e = cudaMemcpy(out, dout, (size_t)n * no * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(din); cudaFree(dout);
+  if (e != cudaSuccess) raise(EID_ERR_CUDA, "eid_fn_tap: %s", cudaGetErrorString(e));
   return EID_OK;
   EID_CATCH
 }

@@ -159,8 +159,8 @@ DEV float bsdfPdf(float roughness, float metallic, f3 n, f3 wo, f3 wi) {   // :1
               __fdiv_rn(1.0f, __fsub_rn(2.0f, metallic)));
 }
 // Sample (pathtrace.glsl:36-38) -> metallicWorkflowSample (:146-166): three draws, returns pdf (or InvalidPdf)
-DEV float bsdfSample(const State& s, f3 n, f3 wo, uint32_t& seed, f3& bsdf, f3& dir) {
-  float r0 = rnd(seed), r1 = rnd(seed), r2 = rnd(seed);
+// metallicWorkflowSample :146-166 with the three random numbers given
+DEV float bsdfSampleR(const State& s, f3 n, f3 wo, float r0, float r1, float r2, f3& bsdf, f3& dir) {
   float roughness = s.mat.roughness, metallic = s.mat.metallic, alpha = roughness;
   if (r2 > __fdiv_rn(1.0f, __fsub_rn(2.0f, metallic))) {
     dir = sampleHemisphereCosine(n, r0, r1);
@@ -171,6 +171,10 @@ DEV float bsdfSample(const State& s, f3 n, f3 wo, uint32_t& seed, f3& bsdf, f3& 
   if (dot3(n, dir) < 0.0f) { bsdf = mk3(0.f); return EID_INVALID_PDF; }
   bsdf = bsdfEval(s.mat.albedo, roughness, metallic, n, wo, dir);
   return bsdfPdf(roughness, metallic, n, wo, dir);
+}
+DEV float bsdfSample(const State& s, f3 n, f3 wo, uint32_t& seed, f3& bsdf, f3& dir) {
+  const float r0 = rnd(seed), r1 = rnd(seed), r2 = rnd(seed);   // GLSL evaluates the vec3(rand, rand, rand) constructor left to right
+  return bsdfSampleR(s, n, wo, r0, r1, r2, bsdf, dir);
 }
 
 // ---- reservoir.glsl ------------------------------------------------------------------------------

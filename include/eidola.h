@@ -267,6 +267,11 @@ EID_API int   eid_renderer_set_env(eid_renderer* r, eid_env* e);
  * in_use == 1 the procedural sun & sky of shaders/sun_and_sky.glsl replaces the HDR map in EnvRadiance, EnvEval and EnvSample
  * (pathtrace.glsl:40-72, env_sampling.glsl:111-125).  The struct is copied; default in_use = 0. */
 EID_API int   eid_renderer_set_sun_and_sky(eid_renderer* r, const SunAndSky* ss);
+/* parity tap of the device-side shader functions, n items of a fixed number of floats each (which: 0 toConcentricDisk, 1 powerHeuristic,
+ * 2 GetSphericalUv, 3 CreateCoordinateSystem, 4 HDRToLDR, 5 LDRToHDR, 6 metallicWorkflowBSDF, 7 metallicWorkflowPdf,
+ * 8 metallicWorkflowSample, 11 toneMap, 12 OffsetRay, 13 tea, 14 rand x2; layouts in tests/ref_fn_inputs.py): compared bit for bit
+ * with the reference's own GLSL text compiled as C++ (oracle/ref_shim) */
+EID_API int   eid_fn_tap(int device, int which, const float* in, uint32_t n, float* out);
 /* parity tap: sun_and_sky(ss, dir) (sun_and_sky.glsl:453-601) for n host directions (3 floats each) -> n RGB triples, on `device` */
 EID_API int   eid_sun_and_sky_eval(int device, const SunAndSky* ss, const float* dirs, uint32_t n, float* rgb);
 /* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR

@@ -28,6 +28,8 @@ struct vec3 {
   vec3(vec2 v, float c) : x(v.x), y(v.y), z(c) {}
   float& operator[](int i) { return (&x)[i]; }
   float operator[](int i) const { return (&x)[i]; }
+  vec2 xy() const { return vec2(x, y); }
+  vec3 xyz() const { return *this; }
 };
 struct vec4 {
   float x, y, z, w;

@@ -134,6 +134,12 @@ struct Renderer {
   void runPost(const RtxState& st, int frames);
 };
 
+// function taps (oracle_shaders.cpp): which = 0 toConcentricDisk, 1 powerHeuristic, 2 GetSphericalUv, 3 CreateCoordinateSystem, 4 HDRToLDR,
+// 5 LDRToHDR, 6 metallicWorkflowBSDF, 7 metallicWorkflowPdf, 8 metallicWorkflowSample, 9 DirectReservoir update/merge/validity/clamp,
+// 10 IndirectReservoir update/validity/clamp, 11 toneMap, 12 OffsetRay, 13 tea, 14 rand x2
+int fn_arity(int which, int* nin, int* nout);
+int fn(int which, const float* in, int n, float* out);
+vec3 post_toneMap(vec3 color, float exposure);   // tonemapping.glsl:78-95 (oracle_post.cpp)
 // shaders/post.frag main for one pixel (oracle_post.cpp)
 vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height);
 // shaders/sun_and_sky.glsl:453-601 (oracle_sunsky.cpp)

@@ -37,6 +37,8 @@ ORC_API void orc_decompress_unit_vec(uint32_t p, float* out) { vec3 v = decompre
 ORC_API void orc_offset_ray(const float* p, const float* n, float* out) {
   vec3 r = OffsetRay(vec3(p[0], p[1], p[2]), vec3(n[0], n[1], n[2])); out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
+ORC_API int orc_fn_arity(int which, int* nin, int* nout) { return fn_arity(which, nin, nout); }
+ORC_API int orc_fn(int which, const float* in, int n, float* out) { return fn(which, in, n, out); }
 ORC_API void orc_alias_table(const float* values, int n, float* prob, int* failId) {
   std::vector<float> v(values, values + n), p; std::vector<int> f;
   discreteSampler1D(v, p, f);

@@ -39,6 +39,8 @@ static vec3 toneMap(vec3 color, float u_Exposure) {
   return toneMapUncharted(color);
 }
 
+vec3 post_toneMap(vec3 color, float exposure) { return toneMap(color, exposure); }
+
 // post.frag:50-57
 static vec3 dither(vec3 linear_color, vec3 noise, float quant) {
   vec3 c0 = vfloor(linearTosRGB(linear_color) / quant) * quant;

@@ -1122,4 +1122,62 @@ void Renderer::run(const RtxState& st, int frames) {   // renderer.cpp:154-206, 
   runPost(st, frames);
 }
 
+// ---- function taps: the restated shader functions, one call per item, for the bit-for-bit comparison against the reference's own
+// GLSL text compiled as C++ (oracle/ref_shim/ref_glsl.cpp, same numbering and arity) and for the golden vectors made from it
+int fn_arity(int which, int* nin, int* nout) {
+  static const int A[][2] = {{2, 2}, {2, 1}, {3, 2}, {3, 6}, {3, 3}, {3, 3}, {14, 3}, {14, 1}, {14, 7}, {30, 27}, {39, 19}, {4, 3}, {6, 3}, {2, 1}, {2, 3}};
+  if (which < 0 || which >= (int)(sizeof(A) / sizeof(A[0]))) return -1;
+  *nin = A[which][0]; *nout = A[which][1];
+  return 0;
+}
+static State tapState(const float* p) { State s{}; s.mat.albedo = vec3(p[0], p[1], p[2]); s.mat.roughness = p[3]; s.mat.metallic = p[4]; return s; }
+static vec3 tv3(const float* p) { return vec3(p[0], p[1], p[2]); }
+static void tput(float* o, vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+static DirectReservoir tapD(const float* p) {
+  DirectReservoir r{}; r.lightSample.Li = E(tv3(p)); r.lightSample.wi = E(tv3(p + 3)); r.lightSample.dist = p[6]; r.num = floatBitsToUint(p[7]); r.weight = p[8]; return r;
+}
+static void tputD(float* o, const DirectReservoir& r) {
+  tput(o, V(r.lightSample.Li)); tput(o + 3, V(r.lightSample.wi)); o[6] = r.lightSample.dist; o[7] = uintBitsToFloat(r.num); o[8] = r.weight;
+}
+static GISample tapG(const float* p) { GISample g{}; g.L = E(tv3(p)); g.xv = E(tv3(p + 3)); g.nv = E(tv3(p + 6)); g.xs = E(tv3(p + 9)); g.ns = E(tv3(p + 12)); g.pHat = p[15]; return g; }
+int fn(int which, const float* in, int n, float* out) {
+  int ni, no;
+  if (fn_arity(which, &ni, &no)) return -1;
+  for (int i = 0; i < n; ++i) {
+    const float* p = in + (size_t)i * ni;
+    float* o = out + (size_t)i * no;
+    switch (which) {
+      case 0: { vec2 d = toConcentricDisk(vec2(p[0], p[1])); o[0] = d.x; o[1] = d.y; break; }
+      case 1: o[0] = powerHeuristic(p[0], p[1]); break;
+      case 2: { vec2 uv = Ctx::GetSphericalUv(tv3(p)); o[0] = uv.x; o[1] = uv.y; break; }
+      case 3: { vec3 t, b; Ctx::CreateCoordinateSystem(tv3(p), t, b); tput(o, t); tput(o + 3, b); break; }
+      case 4: tput(o, HDRToLDR(tv3(p))); break;
+      case 5: tput(o, LDRToHDR(tv3(p))); break;
+      case 6: tput(o, metallicWorkflowBSDF(tapState(p), tv3(p + 5), tv3(p + 8), tv3(p + 11))); break;
+      case 7: o[0] = metallicWorkflowPdf(tapState(p), tv3(p + 5), tv3(p + 8), tv3(p + 11)); break;
+      case 8: { vec3 bsdf(0.0f), dir(0.0f); o[0] = metallicWorkflowSample(tapState(p), tv3(p + 5), tv3(p + 8), tv3(p + 11), bsdf, dir); tput(o + 1, bsdf); tput(o + 4, dir); break; }
+      case 9: {
+        DirectReservoir r = tapD(p);
+        LightSample s{}; s.Li = E(tv3(p + 9)); s.wi = E(tv3(p + 12)); s.dist = p[15];
+        resvUpdate(r, s, p[16], p[17]); tputD(o, r);
+        resvMerge(r, tapD(p + 18), p[27]); tputD(o + 9, r);
+        resvCheckValidity(r); resvClamp(r, (int)p[28]); tputD(o + 18, r);
+        break;
+      }
+      case 10: {
+        IndirectReservoir r{}; r.giSample = tapG(p); r.num = floatBitsToUint(p[16]); r.weight = p[17]; r.bigW = p[18];
+        resvUpdate(r, tapG(p + 19), p[35], p[36]); resvCheckValidity(r); resvClamp(r, (int)p[37]);
+        tput(o, V(r.giSample.L)); tput(o + 3, V(r.giSample.xv)); tput(o + 6, V(r.giSample.nv)); tput(o + 9, V(r.giSample.xs)); tput(o + 12, V(r.giSample.ns));
+        o[15] = r.giSample.pHat; o[16] = uintBitsToFloat(r.num); o[17] = r.weight; o[18] = r.bigW;
+        break;
+      }
+      case 11: tput(o, post_toneMap(tv3(p), p[3])); break;
+      case 12: tput(o, OffsetRay(tv3(p), tv3(p + 3))); break;
+      case 13: o[0] = uintBitsToFloat(tea(floatBitsToUint(p[0]), floatBitsToUint(p[1]))); break;
+      case 14: { uint s = floatBitsToUint(p[0]); float a = rnd(s); float b = rnd(s); o[0] = a; o[1] = b; o[2] = uintBitsToFloat(s); break; }
+    }
+  }
+  return 0;
+}
+
 }  // namespace orc

@@ -6,6 +6,8 @@
  *   shaders/host_device.h  -> sizeof of every shared struct
  *   shaders/compress.glsl  -> compress_unit_vec / decompress_unit_vec / packUnorm4x8 (C++ branch)
  *   src/alias_table.hpp    -> DiscreteSampler1D<float>
+ *   src/hdr_sampling.cpp   -> HdrSampling::createEnvironmentAccel / buildAliasmap (the environment alias map, integral, average);
+ *                             the file is compiled whole against inert Vulkan / nvvk / stb stand-ins (vk_shim.h, nvvk/, nvh/, stb_image.h)
  */
 #include "nvmath/nvmath.h"
 #include <string>
@@ -13,7 +15,25 @@
 #include "compress.glsl"   // /root/reference/shaders/compress.glsl
 #include "alias_table.hpp" // /root/reference/src/alias_table.hpp
 
+#include <array>
+#include <chrono>
+#include <cstdio>
+#include <ios>
+#include <sstream>
+#include <vector>
+#define private public     // createEnvironmentAccel / buildAliasmap are private members (std headers are already in, above)
+#include "hdr_sampling.hpp" // /root/reference/src/hdr_sampling.hpp
+#undef private
+
 #define REF_API extern "C" __attribute__((visibility("default")))
+
+REF_API void ref_env_accel(const float* rgba, uint32_t w, uint32_t h, ImptSampData* accel, float* integral, float* average) {
+  HdrSampling hs;
+  VkExtent2D size{w, h};
+  std::vector<ImptSampData> a = hs.createEnvironmentAccel(rgba, size);
+  for (size_t i = 0; i < a.size(); ++i) accel[i] = a[i];
+  *integral = hs.getIntegral(); *average = hs.getAverage();
+}
 
 REF_API uint32_t ref_compress_unit_vec(float x, float y, float z) { return compress_unit_vec(vec3(x, y, z)); }
 REF_API void ref_decompress_unit_vec(uint32_t p, float* out) { vec3 v = decompress_unit_vec(p); out[0] = v.x; out[1] = v.y; out[2] = v.z; }

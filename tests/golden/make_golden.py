@@ -55,10 +55,37 @@ def ref_vectors():
         alias_in.append(w)
         alias_p.append(p)
         alias_f.append(f)
+    # HdrSampling::createEnvironmentAccel (src/hdr_sampling.cpp:173-242, compiled where it lies) on two synthetic skies
+    import ctypes as C
+    from eidola_b200 import abi, scenes
+    env = {}
+    for tag, (w, h, seed, sun) in (("a", (32, 16, 9, True)), ("b", (24, 10, 4, False))):
+        img = np.ascontiguousarray(scenes.synthetic_sky(w, h, seed, sun), np.float32)
+        acc = np.zeros(w * h, abi.IMPT_DT)
+        integ, avg = C.c_float(), C.c_float()
+        R.ref_env_accel(img.ctypes.data, w, h, acc.ctypes.data, C.byref(integ), C.byref(avg))
+        env["env_%s_img" % tag] = img
+        env["env_%s_accel" % tag] = acc.view(np.uint8)
+        env["env_%s_stats" % tag] = np.array([integ.value, avg.value], np.float32)
+    # the reference's own GLSL text (random / common / pbr_metallicworkflow / reservoir / tonemapping / sun_and_sky .glsl) compiled as
+    # C++ by oracle/ref_shim (glsl_prep.py + ref_glsl.cpp) on the seeded inputs of tests/ref_fn_inputs.py
+    import ref_fn_inputs as fi
+    for w, (ni, no) in enumerate(fi.ARITY):
+        env["fn_%d_out" % w] = ol.call_fn(R, "ref_fn", w, fi.inputs(w, n=1500), no)
+    drng = np.random.default_rng(77)
+    dirs = drng.normal(size=(3000, 3))
+    dirs[:600] = np.array([0.0, 0.78, 0.62]) / 0.99639 + 0.06 * dirs[:600]
+    dirs = np.ascontiguousarray((dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32))
+    env["sky_dirs"] = dirs
+    for k, kw in enumerate(fi.SKY_PARAMS):
+        ss = fi.sun_sky(abi, kw)
+        out = np.zeros_like(dirs)
+        R.ref_sun_and_sky(C.byref(ss), dirs.ctypes.data, len(dirs), out.ctypes.data)
+        env["sky_%d_out" % k] = out
     sizes = np.array([R.ref_sizeof(s.encode()) for s in STRUCTS], np.int32)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), vec=v, enc=enc, words=words, dec=dec, cols=cols, packed=packed,
                         alias_in=np.concatenate(alias_in), alias_p=np.concatenate(alias_p), alias_f=np.concatenate(alias_f),
-                        alias_n=np.array([a.size for a in alias_in], np.int32), sizes=sizes)
+                        alias_n=np.array([a.size for a in alias_in], np.int32), sizes=sizes, **env)
     print("wrote ref_vectors.npz")
 
 

@@ -53,6 +53,7 @@ def lib():
             "orc_renderer_set_env": (i32, [vp, vp]),
             "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
             "orc_renderer_set_env_constant": (i32, [vp, fp]),
+            "orc_fn": (i32, [i32, vp, i32, vp]),
             "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_renderer_run_output": (i32, [vp, vp, vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
             "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
             "orc_renderer_run_trace": (i32, [vp, C.POINTER(abi.RtxState), i32, i32, i32]),
@@ -82,8 +83,20 @@ def ref():
         L.ref_pack_unorm4x8.restype, L.ref_pack_unorm4x8.argtypes = C.c_uint32, [C.c_void_p]
         L.ref_alias_table.restype, L.ref_alias_table.argtypes = None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_sizeof.restype, L.ref_sizeof.argtypes = C.c_int, [C.c_char_p]
+        L.ref_env_accel.restype, L.ref_env_accel.argtypes = None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_fn.restype, L.ref_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _ref = L
     return _ref
+
+
+def call_fn(L, name, which, x, nout):
+    """orc_fn / ref_fn / eid_fn_tap: one row of `x` per item -> (n, nout) float32."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros((x.shape[0], nout), np.float32)
+    rc = getattr(L, name)(which, x.ctypes.data, x.shape[0], out.ctypes.data)
+    assert rc == 0, (name, which, rc)
+    return out
 
 
 def _f3(v):

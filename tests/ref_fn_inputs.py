@@ -1,0 +1,77 @@
+"""Seeded inputs of the function taps (orc_fn / ref_fn): shared by tests/golden/make_golden.py and tests/test_oracle_kat.py."""
+import numpy as np
+
+NAMES = ["toConcentricDisk", "powerHeuristic", "GetSphericalUv", "CreateCoordinateSystem", "HDRToLDR", "LDRToHDR", "metallicWorkflowBSDF",
+         "metallicWorkflowPdf", "metallicWorkflowSample", "DirectReservoir ops", "IndirectReservoir ops", "toneMap", "OffsetRay", "tea", "rand"]
+ARITY = [(2, 2), (2, 1), (3, 2), (3, 6), (3, 3), (3, 3), (14, 3), (14, 1), (14, 7), (30, 27), (39, 19), (4, 3), (6, 3), (2, 1), (2, 3)]
+
+
+def _unit(rng, n):
+    v = rng.normal(size=(n, 3))
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _bits(u):
+    return np.asarray(u, np.uint32).view(np.float32)
+
+
+def inputs(which, n=4000, seed=2022):
+    rng = np.random.default_rng(seed + which)
+    f = lambda *shape: rng.random(shape).astype(np.float32)   # noqa: E731
+    if which == 0:
+        return f(n, 2)
+    if which == 1:
+        return (f(n, 2) * np.float32(50.0)).astype(np.float32)
+    if which in (2, 3):
+        v = _unit(rng, n)
+        v[:6] = np.array([[0, 0, 1], [0, 0, -1], [0, 1, 0], [1, 0, 0], [0, 0.001, 0.9999995], [0.6, 0, 0.8]], np.float32)
+        return v
+    if which in (4, 5):
+        return (f(n, 3) * np.float32(4.0) if which == 4 else f(n, 3)).astype(np.float32)
+    if which in (6, 7, 8):
+        albedo, rough, metal = f(n, 3), np.maximum(f(n, 1), np.float32(0.001)), f(n, 1)
+        metal[: n // 4] = 0.0
+        metal[n // 4: n // 2] = 1.0
+        nrm = _unit(rng, n)
+        wo = _unit(rng, n)
+        wo = np.where((np.sum(wo * nrm, axis=1, keepdims=True) < 0) & (rng.random((n, 1)) < 0.8), -wo, wo).astype(np.float32)
+        last = _unit(rng, n) if which != 8 else f(n, 3)
+        return np.concatenate([albedo, rough, metal, nrm, wo, last], axis=1).astype(np.float32)
+    if which == 9:
+        x = (f(n, 30) * np.float32(3.0)).astype(np.float32)
+        x[:, 7] = _bits(rng.integers(0, 400, n))
+        x[:, 25] = _bits(rng.integers(0, 400, n))
+        x[:, 17], x[:, 27] = f(n), f(n)
+        x[:, 28] = rng.integers(1, 330, n).astype(np.float32)
+        x[: n // 10, 8] = np.nan
+        x[n // 10: n // 5, 26] = -1.0
+        return x
+    if which == 10:
+        x = (f(n, 39) * np.float32(3.0)).astype(np.float32)
+        x[:, 16] = _bits(rng.integers(0, 400, n))
+        x[:, 36] = f(n)
+        x[:, 37] = rng.integers(1, 170, n).astype(np.float32)
+        x[: n // 10, 17] = np.nan
+        return x
+    if which == 11:
+        x = (f(n, 4) * np.float32(6.0)).astype(np.float32)
+        x[:, 3] = f(n) * np.float32(2.0) + np.float32(0.1)
+        return x
+    if which == 12:
+        p = ((f(n, 3) - np.float32(0.5)) * np.float32(40.0)).astype(np.float32)
+        p[: n // 4] *= np.float32(0.001)
+        return np.concatenate([p, _unit(rng, n)], axis=1).astype(np.float32)
+    if which in (13, 14):
+        return _bits(rng.integers(0, 2**32 - 1, (n, 2), dtype=np.uint64).astype(np.uint32))
+    raise ValueError(which)
+
+
+SKY_PARAMS = [dict(), dict(haze=5.0, saturation=1.4, redblueshift=-0.2, horizon_height=-0.7, horizon_blur=0.0),
+              dict(sun_direction=(0.7, -0.1, 0.2), physically_scaled_sun=0, y_is_up=0), dict(sun_direction=(0.2, -0.6, 0.3), haze=2.0)]
+
+
+def sun_sky(abi, kw):
+    kw = dict(kw, in_use=1)
+    if "sun_direction" in kw:
+        kw["sun_direction"] = abi.Vec3(*kw["sun_direction"])
+    return abi.default_sun_and_sky(**kw)

@@ -217,6 +217,31 @@ def test_display_pass_post_frag(mode):
         prr.run_output(abi.default_tonemapper(autoExposure=1))
 
 
+def test_device_functions_match_reference_glsl_vectors():
+    """The device-side shader functions and sun_and_sky() against the committed outputs of the reference's OWN GLSL text compiled as C++
+    (tests/golden/ref_vectors.npz, made by oracle/ref_shim from /root/reference): bit for bit."""
+    import ctypes as C
+    import ref_fn_inputs as fi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+    L = eid.lib()
+    for w, (ni, no) in enumerate(fi.ARITY):
+        if w in (9, 10):
+            continue                      # reservoir operations are inline in the stage kernels (frame-level parity covers them)
+        x = np.ascontiguousarray(fi.inputs(w, n=1500))
+        got = np.zeros((x.shape[0], no), np.float32)
+        assert L.eid_fn_tap(0, w, x.ctypes.data, x.shape[0], got.ctypes.data) == 0
+        want = z["fn_%d_out" % w]
+        bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
+        assert bad.size == 0, "%s: %d of %d items differ from the reference GLSL, first: in %s got %s want %s" % (
+            fi.NAMES[w], bad.size, len(got), x[bad[0]], got[bad[0]], want[bad[0]])
+    dirs = np.ascontiguousarray(z["sky_dirs"])
+    for k, kw in enumerate(fi.SKY_PARAMS):
+        ss = fi.sun_sky(abi, kw)
+        got = np.zeros_like(dirs)
+        assert L.eid_sun_and_sky_eval(0, C.byref(ss), dirs.ctypes.data, len(dirs), got.ctypes.data) == 0
+        assert got.view(np.uint32).tobytes() == z["sky_%d_out" % k].view(np.uint32).tobytes(), "sun_and_sky, parameter set %d" % k
+
+
 def test_sun_and_sky_function_matches_oracle():
     """sun_and_sky(ss, dir) on the device == the oracle's restatement, bit for bit, over random directions and parameter sets."""
     import ctypes as C

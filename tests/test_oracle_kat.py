@@ -92,6 +92,45 @@ def test_alias_table_matches_reference_vectors():
         off += n
 
 
+def test_shader_functions_match_reference_glsl_vectors():
+    """The oracle's restatement of the reference's shader functions vs the reference's OWN GLSL text compiled as C++ (oracle/ref_shim:
+    glsl_prep.py transliterates qualifiers / literals / swizzles / built-in names, the expressions stay the reference's): RNG, sampling
+    helpers, the metallic-workflow BSDF (eval, pdf, sample), reservoir update / merge / validity / clamp, OffsetRay, the Uncharted-2
+    tonemap and sun_and_sky() — bit for bit on seeded inputs (committed outputs: tests/golden/ref_vectors.npz)."""
+    import ctypes as C
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi
+    z = np.load(GOLD)
+    L = ol.lib()
+    for w, (ni, no) in enumerate(fi.ARITY):
+        got = ol.call_fn(L, "orc_fn", w, fi.inputs(w, n=1500), no)
+        want = z["fn_%d_out" % w]
+        bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
+        assert bad.size == 0, "%s: %d of %d items differ from the reference GLSL" % (fi.NAMES[w], bad.size, len(got))
+    dirs = np.ascontiguousarray(z["sky_dirs"])
+    for k, kw in enumerate(fi.SKY_PARAMS):
+        ss = fi.sun_sky(abi, kw)
+        got = np.zeros_like(dirs)
+        L.orc_sun_and_sky(C.byref(ss), dirs.ctypes.data, len(dirs), got.ctypes.data)
+        assert got.view(np.uint32).tobytes() == z["sky_%d_out" % k].view(np.uint32).tobytes(), "sun_and_sky, parameter set %d" % k
+
+
+def test_environment_alias_map_matches_reference_vectors():
+    """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
+    lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
+    import eidola_b200 as eid
+    z = np.load(GOLD)
+    for tag in ("a", "b"):
+        img = z["env_%s_img" % tag]
+        want = z["env_%s_accel" % tag].tobytes()
+        integral, average = (float(v) for v in z["env_%s_stats" % tag])
+        o = ol.OracleEnv(img)
+        assert o.accel().tobytes() == want and o.get_integral() == integral and o.get_average() == average
+        p = eid.HdrSampling(-1)      # host-only environment: the table builders run on the CPU
+        p.set_pixels(img)
+        assert p.accel().tobytes() == want and p.get_integral() == integral and p.get_average() == average
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
 def test_live_reference_library_agrees_with_committed_vectors():
     """The committed ref_vectors.npz really is what the reference's code produces (re-run it live)."""
@@ -104,6 +143,17 @@ def test_live_reference_library_agrees_with_committed_vectors():
     for w, want in zip(z["words"][:3000], z["dec"][:3000]):
         R.ref_decompress_unit_vec(int(w), tmp.ctypes.data)
         assert tmp.tobytes() == want.tobytes()
+    import ctypes as C
+    from eidola_b200 import abi
+    for tag in ("a", "b"):
+        img = np.ascontiguousarray(z["env_%s_img" % tag])
+        acc = np.zeros(img.shape[0] * img.shape[1], abi.IMPT_DT)
+        integ, avg = C.c_float(), C.c_float()
+        R.ref_env_accel(img.ctypes.data, img.shape[1], img.shape[0], acc.ctypes.data, C.byref(integ), C.byref(avg))
+        assert acc.tobytes() == z["env_%s_accel" % tag].tobytes() and [integ.value, avg.value] == list(z["env_%s_stats" % tag])
+    import ref_fn_inputs as fi
+    for w, (ni, no) in enumerate(fi.ARITY):
+        assert ol.call_fn(R, "ref_fn", w, fi.inputs(w, n=1500), no).view(np.uint32).tobytes() == z["fn_%d_out" % w].view(np.uint32).tobytes(), fi.NAMES[w]
 
 
 def test_offset_ray_properties():  # common.glsl:98-113
