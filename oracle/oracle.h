@@ -9,13 +9,26 @@
  *
  * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and cannot be built
  * or run here (no Vulkan ICD, no glslang, nvpro_core un-vendored — SURVEY.md §8c), so the
- * whole-frame behaviour of this oracle is "parity unpinned".  What IS pinned:
- *   - the known-answer vectors of SURVEY.md §4 (tea / pcg / rand / hash8bit / oct-encode /
- *     alias table / struct sizes), tests/test_oracle_kat.py;
- *   - the three reference files that compile stand-alone (shaders/host_device.h,
- *     shaders/compress.glsl C++ branch, src/alias_table.hpp), built by oracle/Makefile into
- *     oracle/_ref/libref.so and compared against this restatement, with the outputs committed
- *     as tests/golden/ref_*.npz for machines without /root/reference.
+ * WHOLE-FRAME behaviour of this oracle is "parity unpinned" (traversal order of the driver, the
+ * un-vendored nvpro_core loaders).  What IS pinned, by the reference's own source compiled where
+ * it lies into oracle/_ref/libref.so (oracle/Makefile; outputs committed as
+ * tests/golden/ref_vectors.npz for machines without /root/reference):
+ *   - shaders/host_device.h (struct sizes), shaders/compress.glsl C++ branch (oct codec,
+ *     packUnorm4x8), src/alias_table.hpp (light alias tables);
+ *   - src/hdr_sampling.cpp (HdrSampling::createEnvironmentAccel / buildAliasmap: environment
+ *     alias map, integral, average) against inert Vulkan / nvvk stand-ins;
+ *   - the pure-arithmetic GLSL include files — random.glsl (tea, pcg, rand), common.glsl
+ *     (GetSphericalUv, CreateCoordinateSystem, OffsetRay, hash8bit, toConcentricDisk,
+ *     powerHeuristic, HDRToLDR, LDRToHDR), pbr_metallicworkflow.glsl (whole file),
+ *     reservoir.glsl (whole file), tonemapping.glsl (whole file), sun_and_sky.glsl (whole
+ *     file) — transliterated token by token (parameter qualifiers, literal suffixes, swizzle
+ *     calls, built-in names; oracle/ref_shim/glsl_prep.py) and compiled as C++ with the
+ *     built-ins bound to the numerical contract: every one of these functions of this oracle is
+ *     bit-identical to the reference's text on seeded inputs (tests/test_oracle_kat.py), and so
+ *     are the device functions of the product (tests/test_gpu_parity.py);
+ *   - the known-answer vectors of SURVEY.md §4.
+ * Not pinnable here: the stage mains (direct_stage.comp ...; they need the descriptor sets and
+ * ray queries), GetState / GetMaterials (buffer references), the glTF import of nvpro_core.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libeidola.so) never links or calls it.

@@ -6,7 +6,8 @@
  * rendered pixel: uvCoords = (pixel + 0.5) / size, tm.zoom = 1, tm.renderingRatio = (1, 1) — the 1:1 presentation.  The
  * reference's sampler is NEAREST / REPEAT (zero-initialised VkSamplerCreateInfo, render_output.cpp:123-128), so
  * texture(img, uvCoords) is texel (x, y).  autoExposure (needs the blit-generated mip chain) is outside the contract.
- * Numerics: DESIGN.md §3 (fp32, one rounding per operation, pow from eid_detmath.h).  Parity: unpinned (no reference vectors).
+ * Numerics: DESIGN.md §3 (fp32, one rounding per operation, pow from eid_detmath.h).  Parity: toneMap is pinned to tonemapping.glsl compiled as C++ (oracle/ref_shim);
+ * the rest of post.frag (a fragment shader with samplers) is unpinned.
  */
 #include "oracle.h"
 

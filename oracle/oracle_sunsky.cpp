@@ -8,7 +8,8 @@
  * Numerics: fp32, one rounding per written operation, GLSL precedence and left-to-right association,
  * GLSL float literals are fp32; exp / pow / acos / sin / cos are the deterministic ones of include/eid_detmath.h,
  * tan(x) = sin(x) / cos(x), smoothstep = t*t*(3-2t) on the clamped ratio.  Compiled with -ffp-contract=off.
- * Parity: unpinned (the reference ships no vectors for this path); checked for physical sanity in tests/test_oracle_kat.py.
+ * Parity: PINNED — bit-identical to sun_and_sky.glsl itself compiled as C++ (oracle/ref_shim, tests/test_oracle_kat.py), given the
+ * contract's built-ins; also checked for physical sanity there.
  */
 #include "oracle.h"
 
