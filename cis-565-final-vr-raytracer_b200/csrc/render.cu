@@ -1016,6 +1016,40 @@ __global__ void k_fn_tap(int which, int ni, int no, const float* __restrict__ in
   }
 }
 
+// scene-dependent parity taps (same numbering as orc_ctx_fn / ref_ctx_fn): 0 SampleDirectLightNoVisibility (seed, pos -> pdf, Li, wi, dist,
+// seed'), 2 EnvEval, 3 EnvRadiance, 4 raySpawn, 5 clampRadiance, 6 Sample (seed, albedo, roughness, metallic, V, N -> bsdf, L, pdf, seed');
+// 1 (LightEval) is written inline in the indirect stage
+__global__ void k_ctx_tap(const FrameParams P, int which, int ni, int no, const float* __restrict__ in, uint32_t n, float* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = in + (size_t)i * ni;
+  float* o = out + (size_t)i * no;
+  auto v3 = [](const float* q) { return mk3(q[0], q[1], q[2]); };
+  auto put = [](float* q, f3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; };
+  switch (which) {
+    case 0: {
+      uint32_t seed = __float_as_uint(p[0]);
+      LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+      o[0] = sampleDirectLightNoVisibility<true>(P.sc, P.env, P.st, v3(p + 1), seed, ls);
+      put(o + 1, ls.Li); put(o + 4, ls.wi); o[7] = ls.dist; o[8] = __uint_as_float(seed);
+      break;
+    }
+    case 2: { float pdf = 0.f; put(o, envEvalOf<true>(P.env, P.st, v3(p), pdf)); o[3] = pdf; break; }
+    case 3: put(o, envRadianceOf<true>(P.env, P.st, v3(p))); break;
+    case 4: { f3 ro, rd; raySpawn<true>(P.cam, (int)p[0], (int)p[1], (int)p[2], (int)p[3], ro, rd); put(o, ro); put(o + 3, rd); break; }
+    case 5: put(o, clampRadiance(v3(p), P.st.fireflyClampThreshold)); break;
+    case 6: {
+      uint32_t seed = __float_as_uint(p[0]);
+      State st; st.mat.albedo = v3(p + 1); st.mat.roughness = p[4]; st.mat.metallic = p[5];
+      f3 bsdf = mk3(0.f), dir = mk3(0.f);
+      const float pdf = bsdfSample(st, v3(p + 9), v3(p + 6), seed, bsdf, dir);
+      put(o, bsdf); put(o + 3, dir); o[6] = pdf; o[7] = __uint_as_float(seed);
+      break;
+    }
+    default: break;
+  }
+}
+
 // parity tap of sun_and_sky (sun_and_sky.glsl:453-601): one direction per thread
 __global__ void k_sun_and_sky(const SunAndSky ss, const float* __restrict__ dirs, uint32_t n, float* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1576,6 +1610,36 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
   dim3 b(32, 8), g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
   k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8);
   CUDA_CHECK(cudaGetLastError());
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_fn_tap(eid_renderer* r, const RtxState* st, int which, const float* in, uint32_t n, float* out) {
+  EID_TRY
+  static const int A[][2] = {{4, 9}, {0, 0}, {3, 4}, {3, 3}, {4, 6}, {3, 3}, {12, 8}};
+  if (!r || !st || !in || !out) raise(EID_ERR_INVALID, "eid_renderer_fn_tap: null argument");
+  if (which < 0 || which >= (int)(sizeof(A) / sizeof(A[0])) || A[which][0] == 0) raise(EID_ERR_INVALID, "eid_renderer_fn_tap: no device tap %d", which);
+  if (n == 0) return EID_OK;
+  const int ni = A[which][0], no = A[which][1];
+  CUDA_CHECK(cudaSetDevice(r->device));
+  FrameParams P;
+  memset(&P, 0, sizeof(P));
+  P.st = *st; P.cam = r->scene->host.camera; P.sc = r->scene->dev.view(r->scene->host);
+  for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
+  P.env.sunSky = r->sunSky;
+  P.env.tex = r->envMap ? r->envMap->tex : nullptr; P.env.accel = r->envMap ? r->envMap->accel : nullptr;
+  P.env.width = r->envMap ? (int)r->envMap->host.width : 0; P.env.height = r->envMap ? (int)r->envMap->host.height : 0;
+  float *din = nullptr, *dout = nullptr;
+  CUDA_CHECK(cudaMalloc(&din, (size_t)n * ni * 4));
+  if (cudaMalloc(&dout, (size_t)n * no * 4) != cudaSuccess) { cudaFree(din); raise(EID_ERR_CUDA, "cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(din, in, (size_t)n * ni * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(dout, 0, (size_t)n * no * 4);
+  if (e == cudaSuccess) {
+    k_ctx_tap<<<(n + 63) / 64, 64>>>(P, which, ni, no, din, n, dout);
+    e = cudaMemcpy(out, dout, (size_t)n * no * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(din); cudaFree(dout);
+  if (e != cudaSuccess) raise(EID_ERR_CUDA, "eid_renderer_fn_tap: %s", cudaGetErrorString(e));
   return EID_OK;
   EID_CATCH
 }

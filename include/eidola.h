@@ -272,6 +272,9 @@ EID_API int   eid_renderer_set_sun_and_sky(eid_renderer* r, const SunAndSky* ss)
  * 8 metallicWorkflowSample, 11 toneMap, 12 OffsetRay, 13 tea, 14 rand x2; layouts in tests/ref_fn_inputs.py): compared bit for bit
  * with the reference's own GLSL text compiled as C++ (oracle/ref_shim) */
 EID_API int   eid_fn_tap(int device, int which, const float* in, uint32_t n, float* out);
+/* the scene-dependent ones, evaluated with the renderer's scene, camera, environment and the given RtxState (which: 0
+ * SampleDirectLightNoVisibility, 2 EnvEval, 3 EnvRadiance, 4 raySpawn, 5 clampRadiance, 6 Sample) */
+EID_API int   eid_renderer_fn_tap(eid_renderer* r, const RtxState* state, int which, const float* in, uint32_t n, float* out);
 /* parity tap: sun_and_sky(ss, dir) (sun_and_sky.glsl:453-601) for n host directions (3 floats each) -> n RGB triples, on `device` */
 EID_API int   eid_sun_and_sky_eval(int device, const SunAndSky* ss, const float* dirs, uint32_t n, float* rgb);
 /* constant environment radiance used by EnvRadiance/EnvEval (pathtrace.glsl:40-72) until an HDR

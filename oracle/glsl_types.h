@@ -18,8 +18,14 @@ namespace orc {
 
 typedef unsigned int uint;
 
-struct vec2 { float x, y; vec2() : x(0), y(0) {} vec2(float a) : x(a), y(a) {} vec2(float a, float b) : x(a), y(b) {} };
-struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b) {} };
+struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b) {} ivec2 xy() const { return *this; } };
+struct vec2 {
+  float x, y;
+  vec2() : x(0), y(0) {}
+  vec2(float a) : x(a), y(a) {}
+  vec2(float a, float b) : x(a), y(b) {}
+  explicit vec2(ivec2 v) : x((float)v.x), y((float)v.y) {}   // GLSL vec2(ivec2)
+};
 struct vec3 {
   float x, y, z;
   vec3() : x(0), y(0), z(0) {}
@@ -38,6 +44,7 @@ struct vec4 {
   vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
   vec4(vec3 v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
   vec3 xyz() const { return vec3(x, y, z); }
+  vec3 rgb() const { return vec3(x, y, z); }
 };
 struct uvec4 { uint x, y, z, w; uvec4() : x(0), y(0), z(0), w(0) {} uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {} };
 

@@ -152,6 +152,7 @@ struct Renderer {
 // 10 IndirectReservoir update/validity/clamp, 11 toneMap, 12 OffsetRay, 13 tea, 14 rand x2
 int fn_arity(int which, int* nin, int* nout);
 int fn(int which, const float* in, int n, float* out);
+int ctx_fn(Renderer& rr, const RtxState& st, int which, const float* in, int n, float* out);   // scene-dependent taps
 vec3 post_toneMap(vec3 color, float exposure);   // tonemapping.glsl:78-95 (oracle_post.cpp)
 // shaders/post.frag main for one pixel (oracle_post.cpp)
 vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height);

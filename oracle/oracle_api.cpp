@@ -39,6 +39,7 @@ ORC_API void orc_offset_ray(const float* p, const float* n, float* out) {
 }
 ORC_API int orc_fn_arity(int which, int* nin, int* nout) { return fn_arity(which, nin, nout); }
 ORC_API int orc_fn(int which, const float* in, int n, float* out) { return fn(which, in, n, out); }
+ORC_API int orc_ctx_fn(Renderer* r, const RtxState* st, int which, const float* in, int n, float* out) { return ctx_fn(*r, *st, which, in, n, out); }
 ORC_API void orc_alias_table(const float* values, int n, float* prob, int* failId) {
   std::vector<float> v(values, values + n), p; std::vector<int> f;
   discreteSampler1D(v, p, f);

@@ -1180,4 +1180,38 @@ int fn(int which, const float* in, int n, float* out) {
   return 0;
 }
 
+// scene-dependent taps (same numbering as ref_ctx_fn of oracle/ref_shim/ref_glsl.cpp): 0 SampleDirectLightNoVisibility, 1 LightEval,
+// 2 EnvEval, 3 EnvRadiance, 4 raySpawn, 5 clampRadiance, 6 Sample
+int ctx_fn(Renderer& rr, const RtxState& st, int which, const float* in, int n, float* out) {
+  static const int A[][2] = {{4, 9}, {9, 4}, {3, 4}, {3, 3}, {4, 6}, {3, 3}, {12, 8}};
+  if (which < 0 || which >= 7) return -1;
+  const int ni = A[which][0], no = A[which][1];
+  for (int i = 0; i < n; ++i) {
+    const float* p = in + (size_t)i * ni;
+    float* o = out + (size_t)i * no;
+    Ctx c(*rr.scene, rr, st, 0);
+    switch (which) {
+      case 0: {
+        c.prd.seed = floatBitsToUint(p[0]);
+        LightSample ls{};
+        o[0] = c.SampleDirectLightNoVisibility(tv3(p + 1), ls);
+        tput(o + 1, V(ls.Li)); tput(o + 4, V(ls.wi)); o[7] = ls.dist; o[8] = uintBitsToFloat(c.prd.seed);
+        break;
+      }
+      case 1: { State s{}; s.matID = floatBitsToUint(p[0]); s.ffnormal = tv3(p + 5); s.area = p[8]; float pdf = 0.0f; tput(o, c.LightEval(s, p[1], tv3(p + 2), pdf)); o[3] = pdf; break; }
+      case 2: { float pdf = 0.0f; tput(o, c.EnvEval(tv3(p), pdf)); o[3] = pdf; break; }
+      case 3: tput(o, c.EnvRadiance(tv3(p))); break;
+      case 4: { Ray r = c.raySpawn(ivec2((int)p[0], (int)p[1]), ivec2((int)p[2], (int)p[3])); tput(o, r.origin); tput(o + 3, r.direction); break; }
+      case 5: tput(o, c.clampRadiance(tv3(p))); break;
+      case 6: {
+        c.prd.seed = floatBitsToUint(p[0]);
+        State s = tapState(p + 1); vec3 L(0.0f); float pdf = 0.0f;
+        tput(o, c.Sample(s, tv3(p + 6), tv3(p + 9), L, pdf)); tput(o + 3, L); o[6] = pdf; o[7] = uintBitsToFloat(c.prd.seed);
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
 }  // namespace orc

@@ -4,6 +4,7 @@
  * of oracle/glsl_types.h.  The EXPRESSIONS evaluated with them are the reference's own text. */
 #pragma once
 #include "../../glsl_types.h"
+#include "nvmath/nvmath.h"
 using mat3 = orc::mat3;
 struct ivec3 { int x, y, z; ivec3(int a, int b, int c) : x(a), y(b), z(c) {} };
 struct mat4x3 { float m[12]; };
@@ -43,3 +44,6 @@ inline orc::vec3 GLSL_pow(orc::vec3 a, orc::vec3 b) { return orc::vec3(eid_powf(
 inline orc::vec3 GLSL_exp(orc::vec3 a) { return orc::vec3(eid_expf(a.x), eid_expf(a.y), eid_expf(a.z)); }
 inline orc::vec3 GLSL_max(orc::vec3 a, orc::vec3 b) { return orc::vec3(orc::gmax(a.x, b.x), orc::gmax(a.y, b.y), orc::gmax(a.z, b.z)); }
 inline orc::vec3 GLSL_clamp(orc::vec3 a, float lo, float hi) { return orc::vec3(orc::gclamp(a.x, lo, hi), orc::gclamp(a.y, lo, hi), orc::gclamp(a.z, lo, hi)); }
+inline int GLSL_min(int a, int b) { return b < a ? b : a; }
+inline unsigned int GLSL_min(unsigned int a, unsigned int b) { return b < a ? b : a; }
+inline orc::vec4 operator*(const nvmath::mat4f& M, orc::vec4 v) { return orc::mul(*reinterpret_cast<const orc::mat4*>(&M), v); }   // ((c0 x + c1 y) + c2 z) + c3 w

@@ -29,6 +29,24 @@ using orc::vec2; using orc::vec3; using orc::vec4; using orc::ivec2;
 #define TONEMAP_UNCHARTED                   // post.frag:30 defines it before including tonemapping.glsl
 #include "../_ref/gen/tonemapping.hpp"
 
+// ---- what layouts.glsl binds (descriptor sets, push constant, UBOs): plain globals set through ref_scene_set ----------------------
+RtxState rtxState; SceneCamera sceneCamera; SunAndSky _sunAndSky; LightBufInfo lightBufInfo;
+const GltfShadeMaterial* materials; const TrigLight* trigLights; const PuncLight* puncLights; const ImptSampData* envSamplingData;
+PtPayload prd;
+// samplers are NOT the reference's arithmetic (fixed-function hardware): texture() of the environment map goes through a function the
+// test installs (the contract's bilinear sampler); material textures are not bound in these tests
+typedef void (*EnvSamplerFn)(void* env, const float* uv, int n, float* rgb);
+struct sampler2D { EnvSamplerFn fn; void* env; unsigned int width, height; };
+struct uvec2 { unsigned int x, y; };
+sampler2D environmentTexture; sampler2D texturesMap[1];
+#define nonuniformEXT(x) (x)
+static uvec2 textureSize(const sampler2D& s, int) { return uvec2{s.width, s.height}; }
+static vec4 texture(const sampler2D& s, vec2 uv) { float in[2] = {uv.x, uv.y}, o[3] = {0, 0, 0}; if (s.fn) s.fn(s.env, in, 1, o); return vec4(o[0], o[1], o[2], 1.0f); }
+static vec4 textureLod(const sampler2D& s, vec2 uv, float) { return texture(s, uv); }
+#include "../_ref/gen/gltf_material.hpp"   // SRGBtoLINEAR only
+#include "../_ref/gen/env_sampling.hpp"    // Environment_sample, EnvSample
+#include "../_ref/gen/pathtrace.hpp"       // EnvRadiance, EnvPdf, EnvEval, LightEval, SampleTriangleLight, SamplePuncLight, SampleDirectLightNoVisibility, clampRadiance, raySpawn
+
 static State mkState(const float* p) {   // albedo.xyz, roughness, metallic
   State s{};
   s.mat.albedo = vec3(p[0], p[1], p[2]); s.mat.roughness = p[3]; s.mat.metallic = p[4];
@@ -98,6 +116,38 @@ REF_API int ref_fn(int which, const float* in, int n, float* out) {
       case 12: put(o, OffsetRay(v3(p), v3(p + 3))); break;
       case 13: o[0] = floatOf(tea(bitsOf(p[0]), bitsOf(p[1]))); break;
       case 14: { uint s = bitsOf(p[0]); float a = rand(s); float b = rand(s); o[0] = a; o[1] = b; o[2] = floatOf(s); (void)p[1]; break; }
+    }
+  }
+  return 0;
+}
+
+REF_API void ref_scene_set(const RtxState* st, const SceneCamera* cam, const SunAndSky* ss, const LightBufInfo* lbi, const GltfShadeMaterial* mats,
+                           const TrigLight* trig, const PuncLight* punc, const ImptSampData* envAccel, void* envSamplerFn, void* env, uint32_t envW, uint32_t envH) {
+  rtxState = *st; sceneCamera = *cam; _sunAndSky = *ss; lightBufInfo = *lbi; materials = mats; trigLights = trig; puncLights = punc; envSamplingData = envAccel;
+  environmentTexture = sampler2D{(EnvSamplerFn)envSamplerFn, env, envW, envH};
+}
+// scene-dependent functions (same numbering as orc_ctx_fn): 0 SampleDirectLightNoVisibility (seed, pos -> pdf, Li, wi, dist, seed'),
+// 1 LightEval (matID, dist, dir, ffnormal, area -> Li, pdf), 2 EnvEval (dir -> radiance, pdf), 3 EnvRadiance, 4 raySpawn (coord, size ->
+// origin, direction), 5 clampRadiance, 6 Sample (seed, albedo, roughness, metallic, V, N -> bsdf, L, pdf, seed')
+REF_API int ref_ctx_fn(int which, const float* in, int n, float* out) {
+  static const int A[][2] = {{4, 9}, {9, 4}, {3, 4}, {3, 3}, {4, 6}, {3, 3}, {12, 8}};
+  if (which < 0 || which >= 7) return -1;
+  const int ni = A[which][0], no = A[which][1];
+  for (int i = 0; i < n; ++i) {
+    const float* p = in + (size_t)i * ni;
+    float* o = out + (size_t)i * no;
+    switch (which) {
+      case 6: {   // Sample (pathtrace.glsl:36-38): seed, albedo, roughness, metallic, V, N -> bsdf, L, pdf, seed'
+        uint seed = bitsOf(p[0]); State s = mkState(p + 1); vec3 L(0.0f); float pdf = 0.0f;
+        put(o, Sample(s, v3(p + 6), v3(p + 9), L, pdf, seed)); put(o + 3, L); o[6] = pdf; o[7] = floatOf(seed);
+        break;
+      }
+      case 0: { prd.seed = bitsOf(p[0]); LightSample ls{}; o[0] = SampleDirectLightNoVisibility(v3(p + 1), ls); put(o + 1, ls.Li); put(o + 4, ls.wi); o[7] = ls.dist; o[8] = floatOf(prd.seed); break; }
+      case 1: { State s{}; s.matID = bitsOf(p[0]); s.ffnormal = v3(p + 5); s.area = p[8]; float pdf = 0.0f; put(o, LightEval(s, p[1], v3(p + 2), pdf)); o[3] = pdf; break; }
+      case 2: { float pdf = 0.0f; put(o, EnvEval(v3(p), pdf)); o[3] = pdf; break; }
+      case 3: put(o, EnvRadiance(v3(p))); break;
+      case 4: { Ray r = raySpawn(ivec2((int)p[0], (int)p[1]), ivec2((int)p[2], (int)p[3])); put(o, r.origin); put(o + 3, r.direction); break; }
+      case 5: put(o, clampRadiance(v3(p))); break;
     }
   }
   return 0;

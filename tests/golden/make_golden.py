@@ -82,6 +82,16 @@ def ref_vectors():
         out = np.zeros_like(dirs)
         R.ref_sun_and_sky(C.byref(ss), dirs.ctypes.data, len(dirs), out.ctypes.data)
         env["sky_%d_out" % k] = out
+    # scene-dependent functions of pathtrace.glsl / env_sampling.glsl (light sampling, environment, camera rays) on three scenes
+    for tag, maker_name, kind in fi.CTX_CONFIGS:
+        osc, orr, oenv, ss, st = ol.ctx_setup(scenes, abi, common, maker_name, kind)
+        keep = ol.ref_scene_set(R, osc, oenv, ss, st, abi)
+        nmat = len(osc.table(abi.TABLE_MATERIALS))
+        for w, (ni, no) in enumerate(fi.CTX_ARITY):
+            if kind == "none" and w in (2, 3):
+                continue          # no environment bound in the reference build (the constant environment is this repo's extension)
+            env["ctx_%s_%d_out" % (tag, w)] = ol.call_fn(R, "ref_ctx_fn", w, fi.ctx_inputs(w, nmat), no)
+        del keep
     sizes = np.array([R.ref_sizeof(s.encode()) for s in STRUCTS], np.int32)
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), vec=v, enc=enc, words=words, dec=dec, cols=cols, packed=packed,
                         alias_in=np.concatenate(alias_in), alias_p=np.concatenate(alias_p), alias_f=np.concatenate(alias_f),

@@ -53,7 +53,7 @@ def lib():
             "orc_renderer_set_env": (i32, [vp, vp]),
             "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
             "orc_renderer_set_env_constant": (i32, [vp, fp]),
-            "orc_fn": (i32, [i32, vp, i32, vp]),
+            "orc_fn": (i32, [i32, vp, i32, vp]), "orc_ctx_fn": (i32, [vp, vp, i32, vp, i32, vp]),
             "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_renderer_run_output": (i32, [vp, vp, vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
             "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
             "orc_renderer_run_trace": (i32, [vp, C.POINTER(abi.RtxState), i32, i32, i32]),
@@ -86,6 +86,8 @@ def ref():
         L.ref_env_accel.restype, L.ref_env_accel.argtypes = None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_fn.restype, L.ref_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_scene_set.restype, L.ref_scene_set.argtypes = None, [C.c_void_p] * 10 + [C.c_uint32, C.c_uint32]
+        L.ref_ctx_fn.restype, L.ref_ctx_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref = L
     return _ref
 
@@ -97,6 +99,37 @@ def call_fn(L, name, which, x, nout):
     rc = getattr(L, name)(which, x.ctypes.data, x.shape[0], out.ctypes.data)
     assert rc == 0, (name, which, rc)
     return out
+
+
+def ctx_setup(scenes, abi, common, maker_name, kind):
+    """Oracle scene + renderer (+ environment) of a tests/ref_fn_inputs.CTX_CONFIGS entry -> (scene, renderer, env or None, SunAndSky, RtxState)."""
+    import ref_fn_inputs as fi
+    osc = OracleScene()
+    osc.load_arrays(getattr(scenes, maker_name)())
+    orr = OracleRenderer(osc, fi.CTX_SIZE)
+    orr.set_env_constant(common.ENV)
+    osc.update_camera(*fi.CTX_SIZE)
+    osc.update_camera(*fi.CTX_SIZE)
+    ss = abi.default_sun_and_sky(in_use=0)
+    env = None
+    if kind == "hdr":
+        env = OracleEnv(fi.ctx_env_image(scenes))
+        orr.set_env(env)
+    elif kind == "sky":
+        ss = fi.sun_sky(abi, fi.CTX_SKY)
+        orr.set_sun_and_sky(ss)
+    st = fi.ctx_state(common, abi, osc.info(), kind, env.get_integral() if env else None)
+    return osc, orr, env, ss, st
+
+
+def ref_scene_set(R, osc, env, ss, st, abi):
+    """Binds the oracle scene's tables (what layouts.glsl binds) to the reference-GLSL library; returns the arrays to keep alive."""
+    tabs = [np.ascontiguousarray(osc.table(t)) for t in (abi.TABLE_CAMERA, abi.TABLE_LIGHT_INFO, abi.TABLE_MATERIALS, abi.TABLE_TRIG_LIGHTS, abi.TABLE_PUNC_LIGHTS)]
+    acc = env.accel() if env else np.zeros(1, abi.IMPT_DT)
+    fnp = C.cast(lib().orc_env_texture, C.c_void_p) if env else None     # the sampler is the contract's, not the reference's arithmetic
+    R.ref_scene_set(C.addressof(st), tabs[0].ctypes.data, C.addressof(ss), tabs[1].ctypes.data, tabs[2].ctypes.data, tabs[3].ctypes.data, tabs[4].ctypes.data,
+                    acc.ctypes.data, fnp, env._h if env else None, env.w if env else 0, env.h if env else 0)
+    return tabs, acc
 
 
 def _f3(v):

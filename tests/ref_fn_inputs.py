@@ -75,3 +75,53 @@ def sun_sky(abi, kw):
     if "sun_direction" in kw:
         kw["sun_direction"] = abi.Vec3(*kw["sun_direction"])
     return abi.default_sun_and_sky(**kw)
+
+
+# ---- scene-dependent functions (orc_ctx_fn / ref_ctx_fn / eid_renderer_fn_tap) ------------------------------------------------------
+CTX_NAMES = ["SampleDirectLightNoVisibility", "LightEval", "EnvEval", "EnvRadiance", "raySpawn", "clampRadiance", "Sample"]
+CTX_ARITY = [(4, 9), (9, 4), (3, 4), (3, 3), (4, 6), (3, 3), (12, 8)]
+CTX_SIZE = (96, 64)
+# (tag, scene maker name, environment kind): lights only / HDR map + point light / sun & sky + emissive triangles
+CTX_CONFIGS = [("cornell_none", "cornell_scene", "none"), ("cube_hdr", "cube_scene", "hdr"), ("room_sky", "small_room", "sky")]
+CTX_SKY = dict(sun_direction=(0.3, 0.5, 0.4), haze=1.0)
+
+
+def ctx_env_image(scenes):
+    return np.ascontiguousarray(scenes.synthetic_sky(32, 16, 9, True), np.float32)
+
+
+def ctx_inputs(which, n_materials, n=1200, seed=99):
+    rng = np.random.default_rng(seed + which)
+    unit = lambda: _unit(rng, n)   # noqa: E731
+    bits = rng.integers(0, 2**32 - 1, (n, 1), dtype=np.uint64).astype(np.uint32).view(np.float32)
+    w, h = CTX_SIZE
+    if which == 0:
+        return np.concatenate([bits, ((rng.random((n, 3)) - 0.5) * 4).astype(np.float32)], axis=1)
+    if which == 1:
+        mat = rng.integers(0, n_materials, (n, 1)).astype(np.uint32).view(np.float32)
+        return np.concatenate([mat, (rng.random((n, 1)) * 5 + 0.1).astype(np.float32), unit(), unit(), (rng.random((n, 1)) + 0.01).astype(np.float32)], axis=1)
+    if which in (2, 3):
+        return unit()
+    if which == 4:
+        return np.concatenate([rng.integers(0, w, (n, 1)), rng.integers(0, h, (n, 1)), np.full((n, 1), w), np.full((n, 1), h)], axis=1).astype(np.float32)
+    if which == 5:
+        x = (rng.random((n, 3)) * 30).astype(np.float32)
+        x[:20, 1] = np.nan
+        return x
+    if which == 6:
+        nrm = unit()
+        v = unit()
+        v = np.where(np.sum(v * nrm, axis=1, keepdims=True) < 0, -v, v).astype(np.float32)
+        return np.concatenate([bits, rng.random((n, 3)).astype(np.float32), np.maximum(rng.random((n, 1)), 0.001).astype(np.float32),
+                               rng.random((n, 1)).astype(np.float32), v, nrm], axis=1).astype(np.float32)
+    raise ValueError(which)
+
+
+def ctx_state(common, abi, info, kind, integral=None):
+    """RtxState of a CTX_CONFIGS entry (frame 3 of the standard sequence)."""
+    over = dict(environmentProb=0.0)
+    if kind == "hdr":
+        over = dict(common.env_state_overrides(integral))
+    elif kind == "sky":
+        over = dict(environmentProb=0.25)
+    return common.frame_state(CTX_SIZE[0], CTX_SIZE[1], info, 3, **over)

@@ -242,6 +242,38 @@ def test_device_functions_match_reference_glsl_vectors():
         assert got.view(np.uint32).tobytes() == z["sky_%d_out" % k].view(np.uint32).tobytes(), "sun_and_sky, parameter set %d" % k
 
 
+def test_device_light_sampling_matches_reference_glsl_vectors():
+    """The device's light sampling (triangle / punctual lights, HDR alias map, sun & sky), EnvEval, EnvRadiance, raySpawn, clampRadiance and
+    Sample, evaluated with the renderer's own scene tables, against the committed outputs of pathtrace.glsl / env_sampling.glsl compiled
+    as C++ (tests/golden/ref_vectors.npz): bit for bit, including the RNG state after the draws."""
+    import ctypes as C
+    import ref_fn_inputs as fi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+    for tag, maker_name, kind in fi.CTX_CONFIGS:
+        psc = eid.Scene(0); psc.load_arrays(getattr(scenes, maker_name)())
+        acc = eid.AccelStructure(); acc.create(psc)
+        rr = eid.Renderer(); rr.create(fi.CTX_SIZE, psc, acc); rr.set_env_constant(common.ENV)
+        psc.update_camera(*fi.CTX_SIZE); psc.update_camera(*fi.CTX_SIZE)
+        integral = None
+        if kind == "hdr":
+            penv = eid.HdrSampling(0); penv.set_pixels(fi.ctx_env_image(scenes)); rr.set_env(penv); integral = penv.get_integral()
+        elif kind == "sky":
+            rr.set_sun_and_sky(fi.sun_sky(abi, fi.CTX_SKY))
+        st = fi.ctx_state(common, abi, psc.info(), kind, integral)
+        nmat = len(psc.table(abi.TABLE_MATERIALS))
+        for w, (ni, no) in enumerate(fi.CTX_ARITY):
+            key = "ctx_%s_%d_out" % (tag, w)
+            if w == 1 or key not in z.files:
+                continue
+            x = np.ascontiguousarray(fi.ctx_inputs(w, nmat))
+            got = np.zeros((x.shape[0], no), np.float32)
+            assert eid.lib().eid_renderer_fn_tap(rr._h, C.byref(st), w, x.ctypes.data, x.shape[0], got.ctypes.data) == 0
+            want = z[key]
+            bad = np.nonzero((got.view(np.uint32) != want.view(np.uint32)).any(axis=1))[0]
+            assert bad.size == 0, "%s / %s: %d of %d items differ from the reference GLSL, first: in %s got %s want %s" % (
+                tag, fi.CTX_NAMES[w], bad.size, len(got), x[bad[0]], got[bad[0]], want[bad[0]])
+
+
 def test_sun_and_sky_function_matches_oracle():
     """sun_and_sky(ss, dir) on the device == the oracle's restatement, bit for bit, over random directions and parameter sets."""
     import ctypes as C

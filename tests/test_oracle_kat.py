@@ -115,6 +115,29 @@ def test_shader_functions_match_reference_glsl_vectors():
         assert got.view(np.uint32).tobytes() == z["sky_%d_out" % k].view(np.uint32).tobytes(), "sun_and_sky, parameter set %d" % k
 
 
+def test_light_sampling_and_environment_match_reference_glsl_vectors():
+    """pathtrace.glsl / env_sampling.glsl compiled as C++ against the oracle scene's own tables: SampleDirectLightNoVisibility (triangle
+    lights, punctual lights, HDR alias map, sun & sky: pdf, Li, wi, dist and the RNG state after the draws), LightEval, EnvEval,
+    EnvRadiance, raySpawn, clampRadiance, Sample — bit for bit on three scenes."""
+    import common
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    z = np.load(GOLD)
+    L = ol.lib()
+    for tag, maker_name, kind in fi.CTX_CONFIGS:
+        osc, orr, oenv, ss, st = ol.ctx_setup(scenes, abi, common, maker_name, kind)
+        nmat = len(osc.table(abi.TABLE_MATERIALS))
+        for w, (ni, no) in enumerate(fi.CTX_ARITY):
+            key = "ctx_%s_%d_out" % (tag, w)
+            if key not in z.files:
+                continue
+            x = np.ascontiguousarray(fi.ctx_inputs(w, nmat))
+            got = np.zeros((x.shape[0], no), np.float32)
+            assert L.orc_ctx_fn(orr._h, C.byref(st), w, x.ctypes.data, x.shape[0], got.ctypes.data) == 0
+            bad = np.nonzero((got.view(np.uint32) != z[key].view(np.uint32)).any(axis=1))[0]
+            assert bad.size == 0, "%s / %s: %d of %d items differ from the reference GLSL" % (tag, fi.CTX_NAMES[w], bad.size, len(got))
+
+
 def test_environment_alias_map_matches_reference_vectors():
     """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
     lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
@@ -151,9 +174,20 @@ def test_live_reference_library_agrees_with_committed_vectors():
         integ, avg = C.c_float(), C.c_float()
         R.ref_env_accel(img.ctypes.data, img.shape[1], img.shape[0], acc.ctypes.data, C.byref(integ), C.byref(avg))
         assert acc.tobytes() == z["env_%s_accel" % tag].tobytes() and [integ.value, avg.value] == list(z["env_%s_stats" % tag])
+    import common
     import ref_fn_inputs as fi
+    from eidola_b200 import scenes
     for w, (ni, no) in enumerate(fi.ARITY):
         assert ol.call_fn(R, "ref_fn", w, fi.inputs(w, n=1500), no).view(np.uint32).tobytes() == z["fn_%d_out" % w].view(np.uint32).tobytes(), fi.NAMES[w]
+    for tag, maker_name, kind in fi.CTX_CONFIGS:
+        osc, orr, oenv, ss, st = ol.ctx_setup(scenes, abi, common, maker_name, kind)
+        keep = ol.ref_scene_set(R, osc, oenv, ss, st, abi)
+        nmat = len(osc.table(abi.TABLE_MATERIALS))
+        for w, (ni, no) in enumerate(fi.CTX_ARITY):
+            key = "ctx_%s_%d_out" % (tag, w)
+            if key in z.files:
+                assert ol.call_fn(R, "ref_ctx_fn", w, fi.ctx_inputs(w, nmat), no).view(np.uint32).tobytes() == z[key].view(np.uint32).tobytes(), (tag, w)
+        del keep
 
 
 def test_offset_ray_properties():  # common.glsl:98-113
