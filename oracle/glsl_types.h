@@ -18,7 +18,8 @@ namespace orc {
 
 typedef unsigned int uint;
 
-struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b) {} ivec2 xy() const { return *this; } };
+struct vec2;
+struct ivec2 { int x, y; ivec2() : x(0), y(0) {} ivec2(int a, int b) : x(a), y(b) {} explicit ivec2(const vec2& v); ivec2 xy() const { return *this; } };
 struct vec2 {
   float x, y;
   vec2() : x(0), y(0) {}
@@ -26,9 +27,11 @@ struct vec2 {
   vec2(float a, float b) : x(a), y(b) {}
   explicit vec2(ivec2 v) : x((float)v.x), y((float)v.y) {}   // GLSL vec2(ivec2)
 };
+struct vec4;
 struct vec3 {
   float x, y, z;
   vec3() : x(0), y(0), z(0) {}
+  explicit vec3(const vec4& v);        // GLSL vec3(vec4): xyz
   vec3(float a) : x(a), y(a), z(a) {}
   vec3(float a, float b, float c) : x(a), y(b), z(c) {}
   vec3(vec2 v, float c) : x(v.x), y(v.y), z(c) {}
@@ -36,6 +39,8 @@ struct vec3 {
   float operator[](int i) const { return (&x)[i]; }
   vec2 xy() const { return vec2(x, y); }
   vec3 xyz() const { return *this; }
+  vec3& xyz() { return *this; }          // lvalue swizzle `v.xyz = ...`
+  vec3 rgb() const { return *this; }
 };
 struct vec4 {
   float x, y, z, w;
@@ -45,8 +50,14 @@ struct vec4 {
   vec4(vec3 v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
   vec3 xyz() const { return vec3(x, y, z); }
   vec3 rgb() const { return vec3(x, y, z); }
+  vec2 xy() const { return vec2(x, y); }
 };
-struct uvec4 { uint x, y, z, w; uvec4() : x(0), y(0), z(0), w(0) {} uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {} };
+inline vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
+inline vec4 operator+(vec4 a, vec4 b) { return vec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline vec4 operator*(vec4 a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline vec4& operator*=(vec4& a, vec4 b) { a = vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); return a; }
+struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} };
+struct uvec4 { uint x, y, z, w; uvec4() : x(0), y(0), z(0), w(0) {} uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {} uvec2 xy() const { return uvec2(x, y); } };
 
 inline vec2 operator+(vec2 a, vec2 b) { return vec2(a.x + b.x, a.y + b.y); }
 inline vec2 operator-(vec2 a, vec2 b) { return vec2(a.x - b.x, a.y - b.y); }
@@ -104,6 +115,7 @@ inline int f2i(float f) {
   if (f <= -2147483648.0f) return (int)0x80000000;
   return (int)f;
 }
+inline ivec2::ivec2(const vec2& v) : x(f2i(v.x)), y(f2i(v.y)) {}   // GLSL ivec2(vec2): truncation (saturating / NaN -> 0 by the contract)
 inline uint f2u(float f) {
   if (f != f || f <= 0.0f) return 0u;
   if (f >= 4294967040.0f) return 4294967040u;

@@ -7,7 +7,7 @@
 #include "nvmath/nvmath.h"
 using mat3 = orc::mat3;
 struct ivec3 { int x, y, z; ivec3(int a, int b, int c) : x(a), y(b), z(c) {} };
-struct mat4x3 { float m[12]; };
+using mat4x3 = orc::mat4x3;
 inline float GLSL_abs(float a) { return fabsf(a); }
 inline float GLSL_max(float a, float b) { return orc::gmax(a, b); }
 inline float GLSL_min(float a, float b) { return orc::gmin(a, b); }
@@ -47,3 +47,12 @@ inline orc::vec3 GLSL_clamp(orc::vec3 a, float lo, float hi) { return orc::vec3(
 inline int GLSL_min(int a, int b) { return b < a ? b : a; }
 inline unsigned int GLSL_min(unsigned int a, unsigned int b) { return b < a ? b : a; }
 inline orc::vec4 operator*(const nvmath::mat4f& M, orc::vec4 v) { return orc::mul(*reinterpret_cast<const orc::mat4*>(&M), v); }   // ((c0 x + c1 y) + c2 z) + c3 w
+inline orc::vec4 GLSL_unpackUnorm4x8(unsigned int p) { return orc::unpackUnorm4x8(p); }
+inline int GLSL_max(int a, int b) { return a < b ? b : a; }
+inline bool GLSL_isnan(orc::vec3 v) { return v.x != v.x || v.y != v.y || v.z != v.z; }
+// matrix products of shade_state.glsl: mat4x3 * vec4 -> vec3, vec3 * mat4x3 -> vec4 (one dot per column), mat4(mat4x3) * vec4
+inline orc::vec3 operator*(const orc::mat4x3& m, orc::vec4 v) { return ((m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z) + m.c[3] * v.w; }
+inline orc::vec4 operator*(orc::vec3 v, const orc::mat4x3& m) { return orc::vec4(orc::dot(v, m.c[0]), orc::dot(v, m.c[1]), orc::dot(v, m.c[2]), orc::dot(v, m.c[3])); }
+inline float GLSL_max(float a, int b) { return orc::gmax(a, (float)b); }
+inline float GLSL_max(int a, float b) { return orc::gmax((float)a, b); }
+inline float GLSL_min(float a, int b) { return orc::gmin(a, (float)b); }

@@ -13,17 +13,18 @@ source is stored in the repository).  The transliteration never touches an expre
   * a vector constructor whose arguments are all rand() calls, `vec3(rand(s), rand(s), rand(s))`, becomes a brace initialiser
     `vec3{rand(s), rand(s), rand(s)}`: GLSL evaluates constructor arguments left to right, C++ only guarantees that order inside braces
     (GCC evaluates parenthesised arguments right to left), and the RNG draw order is part of the result
-  * `#include`, `precision`, `#extension` lines are dropped; optionally only the named top-level functions are kept
+  * `#include`, `precision`, `#extension`, `#version` lines and a stage's interface declarations (`layout(push_constant) uniform ...`,
+    `layout(local_size_x ...) in;`) are dropped; optionally only the named top-level functions are kept
 
-usage: glsl_prep.py <in.glsl> <out.hpp> [--only name1,name2,...] [--drop name1,...]
+usage: glsl_prep.py <in.glsl> <out.hpp> [--only name1,name2,...] [--drop name1,...] [--strip <regex of whole lines to drop>]
 """
 import re
 import sys
 
 BUILTINS = ["abs", "acos", "asin", "atan", "clamp", "cos", "cross", "dot", "exp", "floor", "inverse", "isnan", "isinf", "length", "max", "min",
             "mix", "normalize", "pow", "reflect", "sin", "smoothstep", "sqrt", "tan", "intBitsToFloat", "floatBitsToInt", "uintBitsToFloat",
-            "floatBitsToUint"]
-TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|ivec2|ivec3|uvec2|uvec3|mat3|mat4|State|Material|Ray|SunAndSky|DirectReservoir|IndirectReservoir|LightSample|GISample|RngStateType|sampler2D|GltfShadeMaterial|TrigLight|PuncLight)"
+            "floatBitsToUint", "unpackUnorm4x8", "packUnorm4x8"]
+TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|ivec2|ivec3|uvec2|uvec3|mat3|mat4|State|Material|Ray|SunAndSky|DirectReservoir|IndirectReservoir|LightSample|GISample|RngStateType|sampler2D|GltfShadeMaterial|TrigLight|PuncLight|PtPayload|uimage2D|image2D|rayQueryEXT|ShadeState)"
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
 
 
@@ -62,24 +63,33 @@ def transliterate(text):
     text = re.sub(r"\bin\s+(" + TYPES + r")\s+(\w+)", r"\1 \2", text)
     text = FLOAT_LIT.sub(lambda m: m.group(1) + "f", text)
     text = re.sub(r"\b(vec[234])\(\s*(rand\([\w.]+\)(?:\s*,\s*rand\([\w.]+\))+)\s*\)", r"\1{\2}", text)
+    text = re.sub(r"\b(attr\d\.tangent)\.x\b", r"\1", text)      # `.x` of a uint (VertexAttributes.tangent): a scalar swizzle, not C++
     text = re.sub(r"\.(xy|xyz|rgb)\b(?!\s*\()", r".\1()", text)
+    text = re.sub(r"(?<=[\w\)\]])\.([rgba])\b(?!\s*\()", lambda m: "." + "xyzw"["rgba".index(m.group(1))], text)   # colour component names
     text = re.sub(r"\b(" + "|".join(BUILTINS) + r")\s*\(", r"GLSL_\1(", text)
     return text
 
 
 def main():
     src_path, out_path = sys.argv[1], sys.argv[2]
-    only = drop = None
+    only = drop = strip = None
     args = sys.argv[3:]
     while args:
         if args[0] == "--only":
             only = set(args[1].split(","))
         elif args[0] == "--drop":
             drop = set(args[1].split(","))
+        elif args[0] == "--strip":
+            strip = args[1]
         args = args[2:]
     src = strip_comments(open(src_path).read())
     lines = [l for l in src.split("\n") if not re.match(r"\s*#\s*(include|extension|version)\b", l) and not re.match(r"\s*precision\s", l)]
+    if strip:
+        lines = [l for l in lines if not re.match(strip, l.strip())]
     src = "\n".join(lines)
+    # interface declarations of a shader stage (bound by the wrapper as plain globals): push-constant blocks, local_size
+    src = re.sub(r"layout\s*\(\s*push_constant\s*\)\s*uniform\s+\w+\s*\{[^}]*\}\s*;", "", src)
+    src = re.sub(r"layout\s*\([^)]*\)\s*in\s*;", "", src)
     keep = []
     for name, text in top_level_chunks(src):
         if name is not None and ((only is not None and name not in only) or (drop is not None and name in drop)):

@@ -1,0 +1,83 @@
+/*
+ * oracle/ref_shim/ref_post.cpp — TEST INFRASTRUCTURE.
+ * The reference's three post stages — shaders/denoise_direct.comp, denoise_indirect.comp, compose.comp with denoise_common.glsl and
+ * compress.glsl — compiled WHOLE (their main() included) as C++ from the transliterations of glsl_prep.py, and run over a frame with
+ * the dispatch schedule of Renderer::run (src/renderer.cpp:178-205).  What a shader build binds is provided here as plain globals: the
+ * storage images (imageLoad / imageStore on arrays; out-of-bounds loads return 0, stores are dropped — Vulkan robust access), the
+ * push constant, the camera UBO, gl_GlobalInvocationID.  Every expression evaluated is the reference's own text.
+ */
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include "glsl/glsl_builtins.h"
+#include "host_device.h"          // /root/reference/shaders/host_device.h (C++ branch)
+namespace refpost_compress {      // (its non-inline functions also exist in ref_wrap.cpp's translation unit)
+#include "compress.glsl"          // /root/reference/shaders/compress.glsl: decompress_unit_vec as the shaders see it
+}
+#undef M_PI
+#undef M_PI_2
+#undef M_PI_4
+#undef INFINITY
+#undef PI
+
+namespace refpost {
+using orc::vec2; using orc::vec3; using orc::vec4; using orc::ivec2; using orc::uvec4;
+using refpost_compress::decompress_unit_vec;
+
+struct image2D { vec4* data; int w, h, pitch; };
+struct uimage2D { uvec4* data; int w, h, pitch; };
+static vec4 imageLoad(const image2D& im, ivec2 c) { return (c.x < 0 || c.y < 0 || c.x >= im.w || c.y >= im.h) ? vec4() : im.data[(size_t)c.y * im.pitch + c.x]; }
+static uvec4 imageLoad(const uimage2D& im, ivec2 c) { return (c.x < 0 || c.y < 0 || c.x >= im.w || c.y >= im.h) ? uvec4() : im.data[(size_t)c.y * im.pitch + c.x]; }
+static void imageStore(const image2D& im, ivec2 c, vec4 v) { if (c.x >= 0 && c.y >= 0 && c.x < im.w && c.y < im.h) im.data[(size_t)c.y * im.pitch + c.x] = v; }
+struct GlobalId { unsigned int x, y, z; ivec2 xy() const { return ivec2((int)x, (int)y); } };
+
+// layouts.glsl bindings used by the post stages + the push constant
+static uimage2D thisGbuffer;
+static image2D thisDirectResultImage, thisIndirectResultImage, denoiseDirTempA, denoiseDirTempB, denoiseIndTempA, denoiseIndTempB;
+static RtxState rtxState;
+static SceneCamera sceneCamera;
+static GlobalId gl_GlobalInvocationID;
+
+#include "../_ref/gen/globals.hpp"
+#include "../_ref/gen/common_post.hpp"
+namespace dd {
+#include "../_ref/gen/denoise_common.hpp"
+#include "../_ref/gen/denoise_direct.hpp"
+}
+#undef DENOISE_COMMON_GLSL
+namespace di {
+#include "../_ref/gen/denoise_common.hpp"
+#include "../_ref/gen/denoise_indirect.hpp"
+}
+namespace cp {
+#include "../_ref/gen/compose.hpp"
+}
+
+template <class F>
+static void dispatch(int w, int h, F&& mainFn) {   // vkCmdDispatch(CEIL_DIV(w, 8), CEIL_DIV(h, 8), 1) of 8x8 groups
+  const int gw = (w + 7) / 8 * 8, gh = (h + 7) / 8 * 8;
+  for (int y = 0; y < gh; ++y)
+    for (int x = 0; x < gw; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; mainFn(); }
+}
+}  // namespace refpost
+
+using namespace refpost;
+
+// Renderer::run, renderer.cpp:178-205: denoise_direct x4, denoise_indirect x5 (denoiseLevel = i), compose with the caller's state
+extern "C" __attribute__((visibility("default")))
+void ref_post_run(const RtxState* st, const SceneCamera* cam, int allocW, int allocH, void* gbuffer, void* direct, void* indirect,
+                  void* dirA, void* dirB, void* indA, void* indB) {
+  thisGbuffer = uimage2D{(uvec4*)gbuffer, allocW, allocH, allocW};
+  auto img = [&](void* p) { return image2D{(vec4*)p, allocW, allocH, allocW}; };
+  thisDirectResultImage = img(direct); thisIndirectResultImage = img(indirect);
+  denoiseDirTempA = img(dirA); denoiseDirTempB = img(dirB); denoiseIndTempA = img(indA); denoiseIndTempB = img(indB);
+  sceneCamera = *cam;
+  rtxState = *st;
+  const int W = st->size.x, H = st->size.y;
+  if (st->denoise > 0)
+    for (int i = 0; i < 4; ++i) { rtxState.denoiseLevel = i; dispatch(W, H, [] { dd::main(); }); }
+  if (st->denoise > 0)
+    for (int i = 0; i < 5; ++i) { rtxState.denoiseLevel = i; dispatch(W / 2, H / 2, [] { di::main(); }); }
+  rtxState = *st;
+  dispatch(W, H, [] { cp::main(); });
+}

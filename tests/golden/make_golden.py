@@ -123,6 +123,66 @@ def frame_dumps():
         print("wrote frames_%s.npz" % name)
 
 
+def ref_post_vectors():
+    """tests/golden/ref_post.npz: the reference's post-stage shaders (mains included, compiled as C++) run on the oracle's pre-denoise
+    buffers of the last frame of two golden configs."""
+    from eidola_b200 import abi
+    R = ol.ref()
+    if R is None:
+        print("oracle/_ref/libref.so unavailable: keeping the committed ref_post.npz")
+        return
+    out = {}
+    for name in ("c2_cornell", "room"):
+        maker, size, frames, over = cfg.CONFIGS[name][:4]
+        osc = ol.OracleScene()
+        osc.load_arrays(maker())
+        orr = ol.OracleRenderer(osc, size)
+        orr.set_env_constant(common.ENV)
+        osc.update_camera(*size)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            st = common.frame_state(size[0], size[1], info, f, **over)
+            orr.run_trace(st, f, 0, size[1])
+            if f == frames - 1:
+                pre = {k: orr.read(getattr(abi, k)).copy() for k in ol.POST_BUFS}
+                post = ol.ref_post_run(R, abi, osc.table(abi.TABLE_CAMERA), st, size, pre)
+                for k in ("BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B"):
+                    out["%s_%s" % (name, k)] = post[k]
+                assert post["BUF_DIRECT"].tobytes() != pre["BUF_DIRECT"].tobytes()
+            orr.run_post(st, f)
+    np.savez_compressed(os.path.join(HERE, "ref_post.npz"), **out)
+    print("wrote ref_post.npz")
+
+
+def ref_trace_vectors():
+    """tests/golden/ref_trace.npz: what the reference's direct_stage.comp / indirect_stage.comp (main() included, compiled as C++ by
+    oracle/ref_shim/ref_trace.cpp, ray queries answered by the oracle's intersector) leave after the last frame of each
+    tests/ref_fn_inputs.TRACE_CONFIGS entry: G-buffer, motion vectors, both reservoir buffers, the two pre-denoise images, ray counts."""
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    R = ol.ref()
+    if R is None:
+        print("oracle/_ref/libref.so unavailable: keeping the committed ref_trace.npz")
+        return
+    out = {}
+    for c in fi.TRACE_CONFIGS:
+        tag, maker_name, size, frames, kind, _ = c
+        arrays, osc, orr, env, ss, over = ol.trace_setup(scenes, abi, common, c)
+        rt = ol.RefTracer(R, abi, arrays, osc, size, env=env, sun_sky=ss)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            got = rt.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        for k in fi.TRACE_KEYS:
+            out["%s_%s" % (tag, k)] = np.ascontiguousarray(got[k]).view(np.uint8).reshape(-1).copy()
+        out["%s_rays" % tag] = rt.rays.copy()
+    np.savez_compressed(os.path.join(HERE, "ref_trace.npz"), **out)
+    print("wrote ref_trace.npz")
+
+
 if __name__ == "__main__":
     ref_vectors()
+    ref_post_vectors()
+    ref_trace_vectors()
     frame_dumps()

@@ -86,6 +86,8 @@ def ref():
         L.ref_env_accel.restype, L.ref_env_accel.argtypes = None, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_fn.restype, L.ref_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_trace_run.restype, L.ref_trace_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_post_run.restype, L.ref_post_run.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.ref_scene_set.restype, L.ref_scene_set.argtypes = None, [C.c_void_p] * 10 + [C.c_uint32, C.c_uint32]
         L.ref_ctx_fn.restype, L.ref_ctx_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref = L
@@ -130,6 +132,98 @@ def ref_scene_set(R, osc, env, ss, st, abi):
     R.ref_scene_set(C.addressof(st), tabs[0].ctypes.data, C.addressof(ss), tabs[1].ctypes.data, tabs[2].ctypes.data, tabs[3].ctypes.data, tabs[4].ctypes.data,
                     acc.ctypes.data, fnp, env._h if env else None, env.w if env else 0, env.h if env else 0)
     return tabs, acc
+
+
+class RefTraceBind(C.Structure):      # oracle/ref_shim/ref_trace.cpp
+    _fields_ = [(n, C.c_void_p) for n in ("state", "camera", "sunSky", "lightInfo", "geoInfo", "materials", "trigLights", "puncLights", "envAccel",
+                                          "envSamplerFn", "env")] + [("envW", C.c_uint32), ("envH", C.c_uint32), ("traceFn", C.c_void_p), ("scene", C.c_void_p),
+                                                                     ("allocW", C.c_int32), ("allocH", C.c_int32)] + [
+        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA")]
+
+
+class RefTracer:
+    """Runs the reference's direct_stage.comp / indirect_stage.comp (compiled as C++, oracle/ref_shim/ref_trace.cpp) frame after frame on the
+    tables of an oracle scene, with the oracle's intersector standing in for the driver's ray queries.  Buffers ping-pong like
+    Renderer::run (frame f uses descriptor set (f+1)%2: last* = [set], this* = [!set])."""
+
+    def __init__(self, R, abi, arrays, osc, size, env=None, sun_sky=None):
+        self.R, self.abi, self.osc, self.size, self.env = R, abi, osc, size, env
+        w, h = size
+        self.tabs = {k: np.ascontiguousarray(osc.table(getattr(abi, k))) for k in ("TABLE_MATERIALS", "TABLE_TRIG_LIGHTS", "TABLE_PUNC_LIGHTS", "TABLE_LIGHT_INFO")}
+        # one vertex / index buffer per prim mesh (scene.cpp:209-289), addressed through InstanceData like the shaders do
+        self.vbufs = [np.ascontiguousarray(osc.table(abi.TABLE_VERTICES, i)) for i in range(len(arrays.prim_meshes))]
+        self.ibufs = [np.ascontiguousarray(osc.table(abi.TABLE_INDICES, i)) for i in range(len(arrays.prim_meshes))]
+        geo = np.zeros(len(arrays.prim_meshes), abi.INSTANCE_DT)
+        for i, p in enumerate(arrays.prim_meshes):
+            geo[i]["vertexAddress"] = self.vbufs[i].ctypes.data
+            geo[i]["indexAddress"] = self.ibufs[i].ctypes.data
+            geo[i]["materialIndex"] = p["materialIndex"]
+        self.geo = geo
+        self.ss = sun_sky if sun_sky is not None else abi.default_sun_and_sky(in_use=0)
+        self.acc = env.accel() if env else np.zeros(1, abi.IMPT_DT)
+        self.G = [np.zeros((h, w, 4), np.uint32) for _ in range(2)]
+        self.DR = [np.zeros(w * h, abi.DIRECT_RESV_DT) for _ in range(2)]
+        self.IR = [np.zeros((w // 2) * (h // 2), abi.INDIRECT_RESV_DT) for _ in range(2)]
+        self.motion = np.zeros((h, w, 2), np.int16)
+        self.direct, self.indirect, self.indA = (np.zeros((h, w, 4), np.float32) for _ in range(3))
+        self.rays = np.zeros(2, np.uint64)
+
+    def run(self, st, frame, direct=True, indirect=True):
+        abi, s = self.abi, (frame + 1) % 2
+        cam = np.ascontiguousarray(self.osc.table(abi.TABLE_CAMERA))
+        b = RefTraceBind()
+        b.state, b.camera, b.sunSky, b.lightInfo = C.addressof(st), cam.ctypes.data, C.addressof(self.ss), self.tabs["TABLE_LIGHT_INFO"].ctypes.data
+        b.geoInfo, b.materials = self.geo.ctypes.data, self.tabs["TABLE_MATERIALS"].ctypes.data
+        b.trigLights, b.puncLights, b.envAccel = self.tabs["TABLE_TRIG_LIGHTS"].ctypes.data, self.tabs["TABLE_PUNC_LIGHTS"].ctypes.data, self.acc.ctypes.data
+        if self.env:
+            b.envSamplerFn, b.env, b.envW, b.envH = C.cast(lib().orc_env_texture, C.c_void_p), self.env._h, self.env.w, self.env.h
+        b.traceFn, b.scene = C.cast(lib().orc_accel_trace, C.c_void_p), self.osc._h
+        b.allocW, b.allocH = self.size
+        b.thisG, b.lastG, b.motion = self.G[1 - s].ctypes.data, self.G[s].ctypes.data, self.motion.ctypes.data
+        b.thisDR, b.lastDR, b.thisIR, b.lastIR = self.DR[1 - s].ctypes.data, self.DR[s].ctypes.data, self.IR[1 - s].ctypes.data, self.IR[s].ctypes.data
+        b.direct, b.indirect, b.indA = self.direct.ctypes.data, self.indirect.ctypes.data, self.indA.ctypes.data
+        self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
+        return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
+                "direct": self.direct, "ind_tmp_a": self.indA}
+
+
+def trace_setup(scenes, abi, common, cfg):
+    """Oracle scene + renderer (+ environment / sun & sky) of a tests/ref_fn_inputs.TRACE_CONFIGS entry."""
+    import ref_fn_inputs as fi
+    tag, maker_name, size, frames, kind, over = cfg
+    arrays = getattr(scenes, maker_name)()
+    osc = OracleScene()
+    osc.load_arrays(arrays)
+    orr = OracleRenderer(osc, size)
+    orr.set_env_constant((0.0, 0.0, 0.0))
+    env, ss = None, None
+    if kind == "hdr":
+        env = OracleEnv(fi.ctx_env_image(scenes))
+        orr.set_env(env)
+    elif kind == "sky":
+        ss = fi.sun_sky(abi, fi.CTX_SKY)
+        orr.set_sun_and_sky(ss)
+    over = fi.trace_state_overrides(common, kind, env.get_integral() if env else None, over)
+    osc.update_camera(*size)
+    return arrays, osc, orr, env, ss, over
+
+
+def trace_snapshot(abi, renderer):
+    ids = (("gbuffer", abi.BUF_THIS_GBUFFER), ("motion", abi.BUF_MOTION), ("direct_resv", abi.BUF_THIS_DIRECT_RESV),
+           ("indirect_resv", abi.BUF_THIS_INDIRECT_RESV), ("direct", abi.BUF_DIRECT), ("ind_tmp_a", abi.BUF_DENOISE_IND_A))
+    return {k: renderer.read(w).copy() for k, w in ids}
+
+
+POST_BUFS = ("BUF_THIS_GBUFFER", "BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_DIR_A", "BUF_DENOISE_DIR_B", "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B")
+
+
+def ref_post_run(R, abi, camera_table, state, size, pre):
+    """The reference's denoise_direct.comp x4, denoise_indirect.comp x5, compose.comp (oracle/ref_shim/ref_post.cpp) on copies of the
+    pre-post buffers `pre` (dict keyed by POST_BUFS) -> dict of the buffers afterwards."""
+    bufs = {k: np.ascontiguousarray(pre[k].copy()) for k in POST_BUFS}
+    cam = np.ascontiguousarray(camera_table)
+    R.ref_post_run(C.addressof(state), cam.ctypes.data, size[0], size[1], *[bufs[k].ctypes.data for k in POST_BUFS])
+    return bufs
 
 
 def _f3(v):

@@ -125,3 +125,23 @@ def ctx_state(common, abi, info, kind, integral=None):
     elif kind == "sky":
         over = dict(environmentProb=0.25)
     return common.frame_state(CTX_SIZE[0], CTX_SIZE[1], info, 3, **over)
+
+
+# ---- whole trace stages (direct_stage.comp / indirect_stage.comp mains, oracle/ref_shim/ref_trace.cpp) ------------------------------
+# (tag, scene maker name, (W, H), frames, environment kind, RtxState overrides)
+TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth=3)),
+                 ("cube_hdr", "cube_scene", (48, 32), 2, "hdr", dict()),
+                 ("room_sky", "small_room", (64, 48), 2, "sky", dict()),
+                 ("cornell_none", "cornell_scene", (40, 24), 2, "none", dict(ReSTIRState=0, maxDepth=2)),
+                 ("room_ragged", "small_room", (50, 34), 2, "none", dict(RISSampleNum=2, maxDepth=4, MIS=0))]
+TRACE_KEYS = ("gbuffer", "motion", "direct_resv", "indirect_resv", "direct", "ind_tmp_a")
+
+
+def trace_state_overrides(common, kind, integral=None, over=None):
+    o = dict(environmentProb=0.0)
+    if kind == "hdr":
+        o = dict(common.env_state_overrides(integral))
+    elif kind == "sky":
+        o = dict(environmentProb=0.25)
+    o.update(over or {})
+    return o

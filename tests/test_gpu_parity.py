@@ -242,6 +242,60 @@ def test_device_functions_match_reference_glsl_vectors():
         assert got.view(np.uint32).tobytes() == z["sky_%d_out" % k].view(np.uint32).tobytes(), "sun_and_sky, parameter set %d" % k
 
 
+def test_cuda_trace_stages_match_reference_shader_mains():
+    """The CUDA direct / indirect stages (both forms of the indirect stage) against the committed output of the reference's OWN
+    direct_stage.comp / indirect_stage.comp (main() included, compiled as C++ by oracle/ref_shim/ref_trace.cpp): G-buffer, motion vectors,
+    reservoirs and pre-denoise images after the last frame of every configuration, bit for bit."""
+    import ref_fn_inputs as fi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_trace.npz"))
+    for c in fi.TRACE_CONFIGS:
+        tag, maker_name, size, frames, kind, over = c
+        for wavefront in (1, 0):
+            psc = eid.Scene(0); psc.load_arrays(getattr(scenes, maker_name)())
+            acc = eid.AccelStructure(); acc.create(psc)
+            prr = eid.Renderer(); prr.create(size, psc, acc); prr.set_env_constant((0.0, 0.0, 0.0)); prr.set_strict_math(True); prr.set_wavefront(wavefront)
+            integral = None
+            if kind == "hdr":
+                penv = eid.HdrSampling(0); penv.set_pixels(fi.ctx_env_image(scenes)); prr.set_env(penv); integral = penv.get_integral()
+            elif kind == "sky":
+                prr.set_sun_and_sky(fi.sun_sky(abi, fi.CTX_SKY))
+            o = fi.trace_state_overrides(common, kind, integral, over)
+            psc.update_camera(*size)
+            info = psc.info()
+            for f in range(frames):
+                psc.update_camera(*size)
+                st = common.frame_state(size[0], size[1], info, f, **o)
+                if f < frames - 1:
+                    prr.run(st, f)
+                else:
+                    prr.run_trace(st, f)          # the last frame stops before the denoisers: the pre-denoise images are compared
+            prr.sync()
+            got = {"gbuffer": prr.read(abi.BUF_THIS_GBUFFER), "motion": prr.read(abi.BUF_MOTION), "direct_resv": prr.read(abi.BUF_THIS_DIRECT_RESV),
+                   "indirect_resv": prr.read(abi.BUF_THIS_INDIRECT_RESV), "direct": prr.read(abi.BUF_DIRECT), "ind_tmp_a": prr.read(abi.BUF_DENOISE_IND_A)}
+            for k in fi.TRACE_KEYS:
+                assert np.ascontiguousarray(got[k]).view(np.uint8).reshape(-1).tobytes() == z["%s_%s" % (tag, k)].tobytes(), (tag, k, "wavefront" if wavefront else "mega")
+
+
+def test_cuda_post_stages_match_reference_shader_mains():
+    """The CUDA denoisers + compose (strict math) against the committed output of the reference's OWN denoise_direct.comp x4,
+    denoise_indirect.comp x5, compose.comp (main() included, compiled as C++ by oracle/ref_shim/ref_post.cpp): bit for bit."""
+    import make_golden_cfg as cfg
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_post.npz"))
+    for name in ("c2_cornell", "room"):
+        maker, size, frames, over = cfg.CONFIGS[name][:4]
+        psc = eid.Scene(0); psc.load_arrays(maker())
+        acc = eid.AccelStructure(); acc.create(psc)
+        prr = eid.Renderer(); prr.create(size, psc, acc); prr.set_env_constant(common.ENV); prr.set_strict_math(True)
+        psc.update_camera(*size)
+        info = psc.info()
+        for f in range(frames):
+            psc.update_camera(*size)
+            prr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        prr.sync()
+        for k in ("BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B"):
+            assert prr.read(getattr(abi, k)).tobytes() == z["%s_%s" % (name, k)].tobytes(), (name, k)
+
+
 def test_device_light_sampling_matches_reference_glsl_vectors():
     """The device's light sampling (triangle / punctual lights, HDR alias map, sun & sky), EnvEval, EnvRadiance, raySpawn, clampRadiance and
     Sample, evaluated with the renderer's own scene tables, against the committed outputs of pathtrace.glsl / env_sampling.glsl compiled

@@ -138,6 +138,68 @@ def test_light_sampling_and_environment_match_reference_glsl_vectors():
             assert bad.size == 0, "%s / %s: %d of %d items differ from the reference GLSL" % (tag, fi.CTX_NAMES[w], bad.size, len(got))
 
 
+def _final_frame(renderer_factory, name):
+    """Runs a golden config to its last frame with the given (scene, renderer) factory; returns the renderer and the last state."""
+    import common
+    import make_golden_cfg as cfg
+    maker, size, frames, over = cfg.CONFIGS[name][:4]
+    sc, rr = renderer_factory(maker(), size)
+    sc.update_camera(*size)
+    info = sc.info()
+    for f in range(frames):
+        sc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, **over)
+        rr.run(st, f)
+    return sc, rr, st, size
+
+
+def test_post_stages_match_reference_shader_mains():
+    """denoise_direct.comp x4, denoise_indirect.comp x5 and compose.comp — the reference's shader text INCLUDING main(), compiled as C++ and
+    dispatched like Renderer::run (oracle/ref_shim/ref_post.cpp) — leave exactly the images the oracle's post stages leave
+    (committed outputs: tests/golden/ref_post.npz; re-run live where /root/reference exists)."""
+    import common
+    from eidola_b200 import abi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_post.npz"))
+
+    def factory(arrays, size):
+        osc = ol.OracleScene()
+        osc.load_arrays(arrays)
+        orr = ol.OracleRenderer(osc, size)
+        orr.set_env_constant(common.ENV)
+        return osc, orr
+    for name in ("c2_cornell", "room"):
+        osc, orr, st, size = _final_frame(factory, name)
+        for k in ("BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B"):
+            assert orr.read(getattr(abi, k)).tobytes() == z["%s_%s" % (name, k)].tobytes(), (name, k)
+
+
+def test_trace_stages_match_reference_shader_mains():
+    """direct_stage.comp and indirect_stage.comp — the reference's shader text with everything it includes and its main(), compiled as C++
+    and dispatched in 8x8 work groups like Renderer::run (oracle/ref_shim/ref_trace.cpp; the ray queries, which run inside the Vulkan
+    driver, are answered by the oracle's intersector) — leave exactly the G-buffer, motion vectors, reservoirs and pre-denoise images the
+    oracle leaves, frame after frame (temporal reuse included), with the same number of rays.  Committed outputs:
+    tests/golden/ref_trace.npz; re-run live where /root/reference exists (test_live_reference_library_...)."""
+    import common
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_trace.npz"))
+    for c in fi.TRACE_CONFIGS:
+        tag, maker_name, size, frames, kind, _ = c
+        arrays, osc, orr, env, ss, over = ol.trace_setup(scenes, abi, common, c)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            st = common.frame_state(size[0], size[1], info, f, **over)
+            orr.run_trace(st, f, 0, size[1])
+            if f < frames - 1:
+                orr.run_post(st, f)
+        got = ol.trace_snapshot(abi, orr)
+        for k in fi.TRACE_KEYS:
+            assert np.ascontiguousarray(got[k]).view(np.uint8).reshape(-1).tobytes() == z["%s_%s" % (tag, k)].tobytes(), (tag, k)
+        s = orr.stats()
+        assert [s.closestHitRays, s.anyHitRays] == [int(v) for v in z["%s_rays" % tag]], tag
+
+
 def test_environment_alias_map_matches_reference_vectors():
     """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
     lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
@@ -188,6 +250,27 @@ def test_live_reference_library_agrees_with_committed_vectors():
             if key in z.files:
                 assert ol.call_fn(R, "ref_ctx_fn", w, fi.ctx_inputs(w, nmat), no).view(np.uint32).tobytes() == z[key].view(np.uint32).tobytes(), (tag, w)
         del keep
+    # whole frames: the reference's five stage shaders (mains included) against the oracle, every frame, live
+    zt = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_trace.npz"))
+    for c in fi.TRACE_CONFIGS:
+        tag, maker_name, size, frames, kind, _ = c
+        arrays, osc, orr, env, ss, over = ol.trace_setup(scenes, abi, common, c)
+        rt = ol.RefTracer(R, abi, arrays, osc, size, env=env, sun_sky=ss)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            st = common.frame_state(size[0], size[1], info, f, **over)
+            orr.run_trace(st, f, 0, size[1])
+            got, want = rt.run(st, f), ol.trace_snapshot(abi, orr)
+            for k in fi.TRACE_KEYS:
+                assert np.ascontiguousarray(got[k]).view(np.uint8).reshape(-1).tobytes() == np.ascontiguousarray(want[k]).view(np.uint8).reshape(-1).tobytes(), (tag, f, k)
+            pre = {k: orr.read(getattr(abi, k)).copy() for k in ol.POST_BUFS}
+            orr.run_post(st, f)
+            post = ol.ref_post_run(R, abi, osc.table(abi.TABLE_CAMERA), st, size, pre)
+            for k in ol.POST_BUFS:
+                assert post[k].tobytes() == orr.read(getattr(abi, k)).tobytes(), (tag, f, k)
+        for k in fi.TRACE_KEYS:
+            assert np.ascontiguousarray(got[k]).view(np.uint8).reshape(-1).tobytes() == zt["%s_%s" % (tag, k)].tobytes(), (tag, k)
 
 
 def test_offset_ray_properties():  # common.glsl:98-113
