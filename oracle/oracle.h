@@ -7,28 +7,26 @@
  * shaders with all their includes (shaders/ *.glsl and *.comp).  Each function cites the
  * reference file:line it follows.
  *
- * PARITY PINNING: the reference ships no tests, golden vectors or fixtures and cannot be built
- * or run here (no Vulkan ICD, no glslang, nvpro_core un-vendored — SURVEY.md §8c), so the
- * WHOLE-FRAME behaviour of this oracle is "parity unpinned" (traversal order of the driver, the
- * un-vendored nvpro_core loaders).  What IS pinned, by the reference's own source compiled where
- * it lies into oracle/_ref/libref.so (oracle/Makefile; outputs committed as
- * tests/golden/ref_vectors.npz for machines without /root/reference):
- *   - shaders/host_device.h (struct sizes), shaders/compress.glsl C++ branch (oct codec,
- *     packUnorm4x8), src/alias_table.hpp (light alias tables);
- *   - src/hdr_sampling.cpp (HdrSampling::createEnvironmentAccel / buildAliasmap: environment
- *     alias map, integral, average) against inert Vulkan / nvvk stand-ins;
- *   - the pure-arithmetic GLSL include files — random.glsl (tea, pcg, rand), common.glsl
- *     (GetSphericalUv, CreateCoordinateSystem, OffsetRay, hash8bit, toConcentricDisk,
- *     powerHeuristic, HDRToLDR, LDRToHDR), pbr_metallicworkflow.glsl (whole file),
- *     reservoir.glsl (whole file), tonemapping.glsl (whole file), sun_and_sky.glsl (whole
- *     file) — transliterated token by token (parameter qualifiers, literal suffixes, swizzle
- *     calls, built-in names; oracle/ref_shim/glsl_prep.py) and compiled as C++ with the
- *     built-ins bound to the numerical contract: every one of these functions of this oracle is
- *     bit-identical to the reference's text on seeded inputs (tests/test_oracle_kat.py), and so
- *     are the device functions of the product (tests/test_gpu_parity.py);
- *   - the known-answer vectors of SURVEY.md §4.
- * Not pinnable here: the stage mains (direct_stage.comp ...; they need the descriptor sets and
- * ray queries), GetState / GetMaterials (buffer references), the glTF import of nvpro_core.
+ * PARITY PINNING.  The reference ships no tests, golden vectors or fixtures, and its application cannot be built or
+ * run here (no Vulkan ICD, no glslang, nvpro_core un-vendored — SURVEY.md §8c).  But its SOURCE can be compiled where
+ * it lies, and this oracle is pinned to it (oracle/Makefile target `ref` -> oracle/_ref/libref.so; outputs committed as
+ * tests/golden/ref_vectors.npz, ref_post.npz, ref_trace.npz for machines without /root/reference):
+ *   - shaders/host_device.h (struct sizes), shaders/compress.glsl C++ branch (oct codec, packUnorm4x8),
+ *     src/alias_table.hpp (light alias tables), src/hdr_sampling.cpp (environment alias map, integral, average);
+ *   - ALL FIVE STAGE SHADERS, main() included, with everything they include — direct_stage.comp, indirect_stage.comp,
+ *     denoise_direct.comp, denoise_indirect.comp, compose.comp; globals, random, common, pathtrace,
+ *     pbr_metallicworkflow, gltf_material, env_sampling, sun_and_sky, shade_state, reservoir, denoise_common,
+ *     compress, tonemapping — transliterated token by token into compilable C++ (oracle/ref_shim/glsl_prep.py:
+ *     parameter qualifiers, literal suffixes, swizzle calls, built-in names; the expressions are the reference's text)
+ *     and dispatched over whole frames in 8x8 work groups like Renderer::run (ref_trace.cpp, ref_post.cpp).  Every
+ *     buffer this oracle leaves after every frame — G-buffer, motion vectors, both reservoir buffers, pre-denoise and
+ *     final images — is BIT-IDENTICAL to what the reference's text leaves (tests/test_oracle_kat.py), for point /
+ *     triangle / HDR / sun & sky lighting, ReSTIR off / RIS / temporal, ragged sizes; and so is the CUDA path
+ *     (tests/test_gpu_parity.py).
+ * What remains the numerical CONTRACT of DESIGN.md §3 rather than the reference's own arithmetic: the ray queries
+ * (they run inside the Vulkan driver: hit acceptance, tie-break, candidate order), the rounding of the GLSL built-ins
+ * (pow, exp, sin, normalize ...), the fixed-function samplers, and the un-vendored glTF import of nvpro_core.  The pin
+ * scenes are opaque, untextured, with identity node transforms.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libeidola.so) never links or calls it.
