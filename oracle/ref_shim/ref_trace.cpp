@@ -7,6 +7,8 @@
  * is not the reference's text is traceray_rq.glsl: its ray queries run inside the Vulkan driver, so ClosestHit / AnyHit call an
  * intersector the test installs (the oracle's, i.e. the hit contract of DESIGN.md §3); opaque geometry only (HitTest is never reached).
  * Node transforms of the test scenes are identity, so objectToWorld / worldToObject are identity matrices.
+ * Compiled with -ftrivial-auto-var-init=zero: a GLSL local that is read before it is written (`LightSample lsample;` of a rejected
+ * candidate) is undefined in the shader; the contract defines it as zero.
  */
 #include <cmath>
 #include <cstdint>
