@@ -1,372 +1,286 @@
 /*
  * oracle/oracle_sunsky.cpp — TEST INFRASTRUCTURE (CPU oracle), not product code.
  *
- * Restatement of the reference's procedural sun & sky environment, shaders/sun_and_sky.glsl (603 lines), function by
- * function; each function cites the GLSL lines it follows.  Selected by SunAndSky.in_use == 1 in EnvRadiance / EnvEval /
- * EnvSample (pathtrace.glsl:40-72, env_sampling.glsl:111-125), see oracle_shaders.cpp.
+ * The reference's procedural sun & sky environment (shaders/sun_and_sky.glsl; selected by SunAndSky.in_use == 1 in EnvRadiance /
+ * EnvEval / EnvSample, pathtrace.glsl:40-72, env_sampling.glsl:111-125), restated for the CPU: one function per GLSL function (each
+ * cites its lines), the Perez term that sky_color_xyz and sky_luminance share factored into one helper.
  *
- * Numerics: fp32, one rounding per written operation, GLSL precedence and left-to-right association,
- * GLSL float literals are fp32; exp / pow / acos / sin / cos are the deterministic ones of include/eid_detmath.h,
- * tan(x) = sin(x) / cos(x), smoothstep = t*t*(3-2t) on the clamped ratio.  Compiled with -ffp-contract=off.
+ * Numerics: fp32, one rounding per written operation in the GLSL's evaluation order; exp / pow / acos / sin / cos from
+ * include/eid_detmath.h, tan(x) = sin(x) / cos(x), smoothstep = t*t*(3-2t) on the clamped ratio.  Compiled with -ffp-contract=off.
  * Parity: PINNED — bit-identical to sun_and_sky.glsl itself compiled as C++ (oracle/ref_shim, tests/test_oracle_kat.py), given the
- * contract's built-ins; also checked for physical sanity there.
+ * contract's built-ins.
  */
 #include "oracle.h"
 
 namespace orc {
 
-static const float SS_M_PI = 3.1415926535f;   // sun_and_sky.glsl:25-27: its own M_PI
+static inline float ssLuminance(vec3 c) { return (0.2126f * c.x + 0.7152f * c.y) + 0.0722f * c.z; }   // :31-34
+static inline vec3 ssV(const eid_vec3& v) { return vec3(v.x, v.y, v.z); }
 
-static inline float ss_luminance(vec3 rgb) { return (0.2126f * rgb.x + 0.7152f * rgb.y) + 0.0722f * rgb.z; }   // :31-34
-static inline float ss_tan(float x) { float s, c; eid_sincosf(x, &s, &c); return s / c; }
-static inline float ss_smoothstep(float e0, float e1, float x) {
-  float t = gclamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
+static const float SS_PI = 3.1415926535f;   // sun_and_sky.glsl:26 (its own, shorter M_PI)
+
+static inline float ssSmoothstep(float a, float b, float x) {
+  float t = (x - a) / (b - a);
+  t = gmin(gmax(t, 0.0f), 1.0f);
   return t * t * (3.0f - 2.0f * t);
 }
-static inline vec3 ss_exp(vec3 v) { return vec3(eid_expf(v.x), eid_expf(v.y), eid_expf(v.z)); }
-static inline vec3 ss_pow(vec3 v, vec3 e) { return vec3(eid_powf(v.x, e.x), eid_powf(v.y, e.y), eid_powf(v.z, e.z)); }
+static inline vec3 ssExp3(vec3 v) { return vec3(eid_expf(v.x), eid_expf(v.y), eid_expf(v.z)); }
+static inline vec3 ssPow3(vec3 v, float e) { return vec3(eid_powf(v.x, e), eid_powf(v.y, e), eid_powf(v.z, e)); }
 
-// :37-71
-static vec3 xyz2dir(vec3 in_main, float x, float y, float z) {
-  vec3 u, v;
-  vec3 omain = in_main;
-  if (gabs(omain.x) < gabs(omain.y)) u = vec3(0.0f, -omain.z, omain.y);   // u = n x x_axis
-  else u = vec3(omain.z, 0.0f, -omain.x);                                 // u = n x y_axis
-  if (length(u) == 0.0f) {                                                // degenerate transform
-    if (gabs(in_main.x) < gabs(in_main.y)) u = vec3(0.0f, -in_main.z, in_main.y);
-    else u = vec3(in_main.z, 0.0f, -in_main.x);
-  }
+// xyz2dir :37-71
+static inline vec3 ssXyz2dir(vec3 m, float x, float y, float z) {
+  vec3 u;
+  if (fabsf(m.x) < fabsf(m.y)) u = vec3(0.0f, -m.z, m.y);
+  else u = vec3(m.z, 0.0f, -m.x);
+  // (the "degenerate transform" branch at :55-65 recomputes the same u from the same vector)
   u = normalize(u);
-  v = cross(in_main, u);
-  return x * u + y * v + z * in_main;
+  const vec3 v = cross(m, u);
+  return (x * u + y * v) + z * m;
 }
 
-// :74-115
-static vec2 mi_lib_square_to_disk(float inout_r, float inout_phi, float in_x, float in_y) {
-  float local_x = 2.0f * in_x - 1.0f;
-  float local_y = 2.0f * in_y - 1.0f;
-  if (local_x == 0.0f && local_y == 0.0f) {
-    inout_phi = 0.0f;
-    inout_r = 0.0f;
+// mi_lib_square_to_disk :74-115 -> (r, phi)
+static inline void ssSquareToDisk(float inX, float inY, float& r, float& phi) {
+  const float lx = 2.0f * inX - 1.0f, ly = 2.0f * inY - 1.0f;
+  if (lx == 0.0f && ly == 0.0f) { phi = 0.0f; r = 0.0f; return; }
+  if (lx > -ly) {
+    if (lx > ly) { r = lx; phi = (SS_PI / 4.0f) * (1.0f + ly / lx); }
+    else { r = ly; phi = (SS_PI / 4.0f) * (3.0f - lx / ly); }
   } else {
-    if (local_x > -local_y) {
-      if (local_x > local_y) {
-        inout_r = local_x;
-        inout_phi = (SS_M_PI / 4.0f) * (1.0f + local_y / local_x);
-      } else {
-        inout_r = local_y;
-        inout_phi = (SS_M_PI / 4.0f) * (3.0f - local_x / local_y);
-      }
-    } else {
-      if (local_x < local_y) {
-        inout_r = -local_x;
-        inout_phi = (SS_M_PI / 4.0f) * (5.0f + local_y / local_x);
-      } else {
-        inout_r = -local_y;
-        inout_phi = (SS_M_PI / 4.0f) * (7.0f - local_x / local_y);
-      }
-    }
+    if (lx < ly) { r = -lx; phi = (SS_PI / 4.0f) * (5.0f + ly / lx); }
+    else { r = -ly; phi = (SS_PI / 4.0f) * (7.0f - lx / ly); }
   }
-  return vec2(inout_r, inout_phi);
 }
 
-// :118-138
-static vec3 mi_reflection_dir_diffuse_x(vec3 in_normal, vec2 in_sample) {
-  vec2 r_phi = mi_lib_square_to_disk(0.0f, 0.0f, in_sample.x, in_sample.y);
-  float x = r_phi.x * eid_cosf(r_phi.y);
-  float y = r_phi.x * eid_sinf(r_phi.y);
-  float z2 = 1.0f - x * x - y * y;
-  float z;
-  if (z2 > 0.0f) z = sqrtf(z2);
-  else z = 0.0f;
-  return xyz2dir(in_normal, x, y, z);
+// mi_reflection_dir_diffuse_x :118-138
+static inline vec3 ssDiffuseDir(vec3 normal, float sx, float sy) {
+  float r, phi;
+  ssSquareToDisk(sx, sy, r, phi);
+  const float x = r * eid_cosf(phi), y = r * eid_sinf(phi);
+  const float z2 = (1.0f - x * x) - y * y;
+  const float z = z2 > 0.0f ? sqrtf(z2) : 0.0f;
+  return ssXyz2dir(normal, x, y, z);
 }
 
-// :141-164
-static vec3 calc_sun_color(vec3 sun_dir, float turbidity) {
-  vec3 sun_color = vec3(0.0f);
-  vec3 ko = vec3(12.0f, 8.5f, 0.9f);
-  vec3 wavelength = vec3(0.610f, 0.550f, 0.470f);
-  vec3 solRad = vec3(1.0f * 127500.0f / 0.9878f, 0.992f * 127500.0f / 0.9878f, 0.911f * 127500.0f / 0.9878f);
-  if (sun_dir.z > 0.0f) {
-    float m = (1.0f / (sun_dir.z + 0.15f * eid_powf(93.885f - eid_acosf(sun_dir.z) * 180.0f / SS_M_PI, -1.253f)));
-    float beta = 0.04608f * turbidity - 0.04586f;
-    float alpha = 1.3f;
-    vec3 ta, to, tr;
-    ta = ss_exp(-m * beta * ss_pow(wavelength, vec3(-alpha)));          // aerosol (water + dust) attenuation
-    float l = 0.0035f;
-    to = ss_exp(-m * ko * l);                                           // ozone absorption
-    tr = ss_exp(-m * 0.008735f * ss_pow(wavelength, vec3(-4.08f)));     // Rayleigh scattering
-    sun_color = tr * ta * to * solRad;
+// calc_sun_color :141-164
+static inline vec3 ssSunColor(vec3 sunDir, float turbidity) {
+  vec3 sunColor = vec3(0.0f);
+  const vec3 ko = vec3(12.0f, 8.5f, 0.9f);
+  const vec3 wavelength = vec3(0.610f, 0.550f, 0.470f);
+  const vec3 solRad = vec3(1.0f * 127500.0f / 0.9878f, 0.992f * 127500.0f / 0.9878f, 0.911f * 127500.0f / 0.9878f);
+  if (sunDir.z > 0.0f) {
+    const float m = 1.0f / (sunDir.z + 0.15f * eid_powf(93.885f - eid_acosf(sunDir.z) * 180.0f / SS_PI, -1.253f));
+    const float beta = 0.04608f * turbidity - 0.04586f;
+    const float alpha = 1.3f;
+    const vec3 ta = ssExp3((-m * beta) * ssPow3(wavelength, -alpha));   // aerosol attenuation
+    const float l = 0.0035f;
+    const vec3 to = ssExp3(((-m) * ko) * l);                            // ozone absorption
+    const vec3 tr = ssExp3((-m * 0.008735f) * ssPow3(wavelength, -4.08f));   // Rayleigh scattering
+    sunColor = ((tr * ta) * to) * solRad;
   }
-  return sun_color;
+  return sunColor;
 }
 
-// :167-221
-static vec3 sky_color_xyz(vec3 in_dir, vec3 in_sun_pos, float in_turbidity, float in_luminance) {
+// the Perez term shared by sky_color_xyz and sky_luminance
+static inline float ssPerez(float A, float B, float C, float D, float E, float cosTheta, float gamma, float cosGamma, float thetaSun, float cosThetaSun) {
+  return ((1.0f + A * eid_expf(B / cosTheta)) * ((1.0f + C * eid_expf(D * gamma)) + (E * cosGamma) * cosGamma)) /
+         ((1.0f + A * eid_expf(B / 1.0f)) * ((1.0f + C * eid_expf(D * thetaSun)) + (E * cosThetaSun) * cosThetaSun));
+}
+
+// sky_color_xyz :167-221
+static inline vec3 ssSkyColorXyz(vec3 dir, vec3 sunPos, float T, float lum) {
+  float cosGamma = dot(sunPos, dir);
+  if (cosGamma > 1.0f) cosGamma = 2.0f - cosGamma;
+  const float gamma = eid_acosf(cosGamma);
+  const float cosTheta = dir.z, cosThetaSun = sunPos.z;
+  const float thetaSun = eid_acosf(cosThetaSun);
+  const float t2 = T * T, ts2 = thetaSun * thetaSun, ts3 = ts2 * thetaSun;
+  const float zenithX = (((0.001650f * ts3 - 0.003742f * ts2) + 0.002088f * thetaSun) + 0.0f) * t2 +
+                        (((-0.029028f * ts3 + 0.063773f * ts2) - 0.032020f * thetaSun) + 0.003948f) * T +
+                        (((0.116936f * ts3 - 0.211960f * ts2) + 0.060523f * thetaSun) + 0.258852f);
+  const float zenithY = (((0.002759f * ts3 - 0.006105f * ts2) + 0.003162f * thetaSun) + 0.0f) * t2 +
+                        (((-0.042149f * ts3 + 0.089701f * ts2) - 0.041536f * thetaSun) + 0.005158f) * T +
+                        (((0.153467f * ts3 - 0.267568f * ts2) + 0.066698f * thetaSun) + 0.266881f);
+  float A = -0.019257f * T - (0.29f - eid_powf(cosThetaSun, 0.5f) * 0.09f);
+  float B = -0.066513f * T + 0.000818f, C = -0.000417f * T + 0.212479f, D = -0.064097f * T - 0.898875f, E = -0.003251f * T + 0.045178f;
+  float x = ssPerez(A, B, C, D, E, cosTheta, gamma, cosGamma, thetaSun, cosThetaSun);
+  A = -0.016698f * T - 0.260787f; B = -0.094958f * T + 0.009213f; C = -0.007928f * T + 0.210230f; D = -0.044050f * T - 1.653694f;
+  E = -0.010922f * T + 0.052919f;
+  float y = ssPerez(A, B, C, D, E, cosTheta, gamma, cosGamma, thetaSun, cosThetaSun);
+  const float sat = 1.0f;
+  x = zenithX * (x * sat + (1.0f - sat));
+  y = zenithY * (y * sat + (1.0f - sat));
   vec3 xyz;
-  float A, B, C, D, E;
-  float cos_gamma = dot(in_sun_pos, in_dir);
-  if (cos_gamma > 1.0f) cos_gamma = 2.0f - cos_gamma;
-  float gamma = eid_acosf(cos_gamma);
-  float cos_theta = in_dir.z;
-  float cos_theta_sun = in_sun_pos.z;
-  float theta_sun = eid_acosf(cos_theta_sun);
-  float t2 = in_turbidity * in_turbidity;
-  float ts2 = theta_sun * theta_sun;
-  float ts3 = ts2 * theta_sun;
-  float zenith_x = ((+0.001650f * ts3 - 0.003742f * ts2 + 0.002088f * theta_sun + 0.0f) * t2
-                    + (-0.029028f * ts3 + 0.063773f * ts2 - 0.032020f * theta_sun + 0.003948f) * in_turbidity
-                    + (+0.116936f * ts3 - 0.211960f * ts2 + 0.060523f * theta_sun + 0.258852f));
-  float zenith_y = ((+0.002759f * ts3 - 0.006105f * ts2 + 0.003162f * theta_sun + 0.0f) * t2
-                    + (-0.042149f * ts3 + 0.089701f * ts2 - 0.041536f * theta_sun + 0.005158f) * in_turbidity
-                    + (+0.153467f * ts3 - 0.267568f * ts2 + 0.066698f * theta_sun + 0.266881f));
-  xyz.y = in_luminance;
-  A = -0.019257f * in_turbidity - (0.29f - eid_powf(cos_theta_sun, 0.5f) * 0.09f);
-  B = -0.066513f * in_turbidity + 0.000818f;
-  C = -0.000417f * in_turbidity + 0.212479f;
-  D = -0.064097f * in_turbidity - 0.898875f;
-  E = -0.003251f * in_turbidity + 0.045178f;
-  float x = (((1.f + A * eid_expf(B / cos_theta)) * (1.f + C * eid_expf(D * gamma) + E * cos_gamma * cos_gamma))
-             / ((1.f + A * eid_expf(B / 1.0f)) * (1.f + C * eid_expf(D * theta_sun) + E * cos_theta_sun * cos_theta_sun)));
-  A = -0.016698f * in_turbidity - 0.260787f;
-  B = -0.094958f * in_turbidity + 0.009213f;
-  C = -0.007928f * in_turbidity + 0.210230f;
-  D = -0.044050f * in_turbidity - 1.653694f;
-  E = -0.010922f * in_turbidity + 0.052919f;
-  float y = (((1.f + A * eid_expf(B / cos_theta)) * (1.f + C * eid_expf(D * gamma) + E * cos_gamma * cos_gamma))
-             / ((1.f + A * eid_expf(B / 1.0f)) * (1.f + C * eid_expf(D * theta_sun) + E * cos_theta_sun * cos_theta_sun)));
-  float local_saturation = 1.0f;
-  x = zenith_x * ((x * local_saturation) + (1.0f - local_saturation));
-  y = zenith_y * ((y * local_saturation) + (1.0f - local_saturation));
-  xyz.x = (x / y) * xyz.y;                      // chromaticities x and y to CIE
-  xyz.z = ((1.0f - x - y) / y) * xyz.y;
+  xyz.y = lum;
+  xyz.x = (x / y) * xyz.y;
+  xyz.z = (((1.0f - x) - y) / y) * xyz.y;
   return xyz;
 }
 
-// :224-250
-static float sky_luminance(vec3 in_dir, vec3 in_sun_pos, float in_turbidity) {
-  float cos_gamma = dot(in_sun_pos, in_dir);
-  if (cos_gamma < 0.0f) cos_gamma = 0.0f;
-  if (cos_gamma > 1.0f) cos_gamma = 2.0f - cos_gamma;
-  float gamma = eid_acosf(cos_gamma);
-  float cos_theta = in_dir.z;
-  float cos_theta_sun = in_sun_pos.z;
-  float theta_sun = eid_acosf(cos_theta_sun);
-  float A = 0.178721f * in_turbidity - 1.463037f;
-  float B = -0.355402f * in_turbidity + 0.427494f;
-  float C = -0.022669f * in_turbidity + 5.325056f;
-  float D = 0.120647f * in_turbidity - 2.577052f;
-  float E = -0.066967f * in_turbidity + 0.370275f;
-  float Y = (((1.f + A * eid_expf(B / cos_theta)) * (1.f + C * eid_expf(D * gamma) + E * cos_gamma * cos_gamma))
-             / ((1.f + A * eid_expf(B / 1.0f)) * (1.f + C * eid_expf(D * theta_sun) + E * cos_theta_sun * cos_theta_sun)));
-  return Y;
+// sky_luminance :224-250
+static inline float ssSkyLuminance(vec3 dir, vec3 sunPos, float T) {
+  float cosGamma = dot(sunPos, dir);
+  if (cosGamma < 0.0f) cosGamma = 0.0f;
+  if (cosGamma > 1.0f) cosGamma = 2.0f - cosGamma;
+  const float gamma = eid_acosf(cosGamma);
+  const float cosTheta = dir.z, cosThetaSun = sunPos.z;
+  const float thetaSun = eid_acosf(cosThetaSun);
+  const float A = 0.178721f * T - 1.463037f, B = -0.355402f * T + 0.427494f, C = -0.022669f * T + 5.325056f;
+  const float D = 0.120647f * T - 2.577052f, E = -0.066967f * T + 0.370275f;
+  return ssPerez(A, B, C, D, E, cosTheta, gamma, cosGamma, thetaSun, cosThetaSun);
 }
 
-// :253-266
-static vec3 calc_env_color(vec3 in_sun_dir, vec3 in_dir, float in_turbidity) {
-  float theta_sun = eid_acosf(in_sun_dir.z);
-  float chi = (4.0f / 9.0f - in_turbidity / 120.0f) * (SS_M_PI - 2.0f * theta_sun);
-  float lum = 1000.0f * ((4.0453f * in_turbidity - 4.9710f) * ss_tan(chi) - 0.2155f * in_turbidity + 2.4192f);
-  lum *= sky_luminance(in_dir, in_sun_dir, in_turbidity);
-  vec3 XYZ = sky_color_xyz(in_dir, in_sun_dir, in_turbidity, lum);
-  vec3 env_color = vec3(3.241f * XYZ.x - 1.537f * XYZ.y - 0.499f * XYZ.z, -0.969f * XYZ.x + 1.876f * XYZ.y + 0.042f * XYZ.z,
-                        0.056f * XYZ.x - 0.204f * XYZ.y + 1.057f * XYZ.z);
-  env_color *= SS_M_PI;
-  return env_color;
+// calc_env_color :253-266
+static inline vec3 ssEnvColor(vec3 sunDir, vec3 dir, float T) {
+  const float thetaSun = eid_acosf(sunDir.z);
+  const float chi = (4.0f / 9.0f - T / 120.0f) * (SS_PI - 2.0f * thetaSun);
+  float s, c;
+  eid_sincosf(chi, &s, &c);
+  float lum = 1000.0f * (((4.0453f * T - 4.9710f) * (s / c) - 0.2155f * T) + 2.4192f);
+  lum = lum * ssSkyLuminance(dir, sunDir, T);
+  const vec3 X = ssSkyColorXyz(dir, sunDir, T, lum);
+  vec3 env = vec3((3.241f * X.x - 1.537f * X.y) - 0.499f * X.z, (-0.969f * X.x + 1.876f * X.y) + 0.042f * X.z, (0.056f * X.x - 0.204f * X.y) + 1.057f * X.z);
+  return env * SS_PI;
 }
 
-// :269-289
-static vec3 calc_irrad(vec3 in_data_sun_dir, float in_data_sun_dir_haze) {
-  vec3 colaccu = vec3(0.0f);
-  vec3 nuState_normal = vec3(0.0f, 0.0f, 1.0f);
-  vec3 sun_dir = in_data_sun_dir;
-  vec3 work = vec3(0.0f);
-  for (float u = 1.f / 10.f; u < 1.f; u += 1.f / 5.f) {
-    for (float v = 1.f / 10.f; v < 1.f; v += 1.f / 5.f) {
-      vec3 diff = mi_reflection_dir_diffuse_x(nuState_normal, vec2(u, v));
-      work = calc_env_color(sun_dir, diff, in_data_sun_dir_haze);
-      colaccu += work;
-    }
+// calc_irrad :269-289 (5 x 5 stratified directions of the upper hemisphere; float loop counters as in the GLSL)
+static inline vec3 ssIrrad(vec3 sunDir, float haze) {
+  vec3 acc = vec3(0.0f);
+  const vec3 n = vec3(0.0f, 0.0f, 1.0f);
+  for (float u = 1.0f / 10.0f; u < 1.0f; u += 1.0f / 5.0f)
+    for (float v = 1.0f / 10.0f; v < 1.0f; v += 1.0f / 5.0f)
+      acc = acc + ssEnvColor(sunDir, ssDiffuseDir(n, u, v), haze);
+  return acc / 25.0f;
+}
+
+// tweak_saturation :292-308
+static inline float ssTweakSaturation(float sat, float haze) {
+  const float lowsat = eid_powf(sat, 3.0f);
+  if (sat <= 1.0f) {
+    float h = haze;
+    h = h - 2.0f;
+    h = h / 15.0f;
+    if (h < 0.0f) h = 0.0f;
+    if (h > 1.0f) h = 1.0f;
+    h = eid_powf(h, 3.0f);
+    return sat * (1.0f - h) + lowsat * h;
   }
-  colaccu /= 25.0f;
-  return colaccu;
+  return 1.0f;
 }
 
-// :292-308
-static float tweak_saturation(float inout_saturation, float in_haze) {
-  float lowsat = eid_powf(inout_saturation, 3.0f);
-  if (inout_saturation <= 1.0f) {
-    float local_haze = in_haze;
-    local_haze -= 2.0f;
-    local_haze /= 15.0f;
-    if (local_haze < 0.0f) local_haze = 0.0f;
-    if (local_haze > 1.0f) local_haze = 1.0f;
-    local_haze = eid_powf(local_haze, 3.0f);
-    return ((inout_saturation * (1.0f - local_haze)) + lowsat * local_haze);
-  }
-  return 1.f;
+// arch_vectortweak :311-324
+static inline vec3 ssVectorTweak(vec3 dir, int yIsUp, float horizHeight) {
+  vec3 o = dir;
+  if (yIsUp == 1) o = vec3(dir.x, dir.z, dir.y);
+  if (horizHeight != 0.0f) { o.z = o.z - horizHeight; o = normalize(o); }
+  return o;
 }
 
-// :311-324
-static vec3 arch_vectortweak(vec3 dir, int y_is_up, float horiz_height) {
-  vec3 out_dir = dir;
-  if (y_is_up == 1) out_dir = vec3(dir.x, dir.z, dir.y);
-  if (horiz_height != 0.0f) {
-    out_dir.z -= horiz_height;
-    out_dir = normalize(out_dir);
-  }
-  return out_dir;
+// arch_colortweak :327-356 (the clamp of negative components at :342-352 only touches a dead copy of `tint`)
+static inline vec3 ssColorTweak(vec3 tint, float saturation, float redness) {
+  const float intensity = ssLuminance(tint);
+  vec3 o;
+  if (saturation <= 0.0f) o = vec3(intensity);
+  else o = tint * saturation + vec3(intensity * (1.0f - saturation));
+  return o * vec3(1.0f + redness, 1.0f, 1.0f - redness);
 }
 
-// :327-356
-static vec3 arch_colortweak(vec3 tint, float saturation, float redness) {
-  float intensity = ss_luminance(tint);
-  vec3 out_tint;
-  if (saturation <= 0.0f) {
-    out_tint = vec3(intensity);
-  } else {
-    out_tint = tint * saturation + intensity * (1.0f - saturation);
-    if (saturation > 1.0f) {             // boosted saturation can cause negatives — clamps a copy that is never read again
-      vec3 rgb_color = tint;
-      if (rgb_color.x < 0.0f) rgb_color.x = 0.0f;
-      if (rgb_color.y < 0.0f) rgb_color.y = 0.0f;
-      if (rgb_color.z < 0.0f) rgb_color.z = 0.0f;
-      tint = rgb_color;
-    }
-  }
-  out_tint *= vec3(1.0f + redness, 1.f, 1.0f - redness);
-  return out_tint;
+// calc_physical_scale :359-438 -> (sun disk scale, sun glow scale)
+static inline void ssPhysicalScale(float diskScale, float glowIntensity, float diskIntensity, float& sundiskScale, float& sunglowScale) {
+  const float sunAngularRadius = 0.00465f;
+  const float diskRadius = sunAngularRadius * diskScale;
+  const float glowRadius = diskRadius * 10.0f;
+  const float glowIntegral = glowIntensity * (((4.0f * SS_PI) - (24.0f * SS_PI) / (glowRadius * glowRadius)) +
+                                              ((24.0f * SS_PI) * eid_sinf(glowRadius)) / ((glowRadius * glowRadius) * glowRadius));
+  float target = diskIntensity * SS_PI;
+  sunglowScale = 1.0f;
+  const float maxGlow = 0.5f * target;
+  if (glowIntegral > maxGlow) { sunglowScale = sunglowScale * (maxGlow / glowIntegral); target = target - maxGlow; }
+  else target = target - glowIntegral;
+  const float area = (2.0f * SS_PI) * (1.0f - eid_cosf(diskRadius));
+  const float targetIntensity = target / area;
+  const float actualIntegral = 1.0f * area;
+  const float actualIntensity = ((diskIntensity * 100.0f) * actualIntegral) / area;
+  sundiskScale = (targetIntensity == 0.0f) ? 0.0f : targetIntensity / actualIntensity;
 }
 
-// :359-438
-static vec2 calc_physical_scale(float sun_disk_scale, float sun_glow_intensity, float sun_disk_intensity) {
-  float sun_angular_radius = 0.00465f;
-  float sun_disk_radius = sun_angular_radius * sun_disk_scale;
-  float sun_glow_radius = sun_disk_radius * 10.0f;
-  float glow_func_integral = sun_glow_intensity
-                             * ((4.f * SS_M_PI) - (24.f * SS_M_PI) / (sun_glow_radius * sun_glow_radius)
-                                + (24.f * SS_M_PI) * eid_sinf(sun_glow_radius) / (sun_glow_radius * sun_glow_radius * sun_glow_radius));
-  float target_sundisk_integral = sun_disk_intensity * SS_M_PI;
-  float sky_sunglow_scale = 1.0f;
-  float max_glow_integral = 0.5f * target_sundisk_integral;
-  if (glow_func_integral > max_glow_integral) {
-    sky_sunglow_scale *= max_glow_integral / glow_func_integral;
-    target_sundisk_integral -= max_glow_integral;
-  } else {
-    target_sundisk_integral -= glow_func_integral;
-  }
-  float sundisk_area = 2.f * SS_M_PI * (1.f - eid_cosf(sun_disk_radius));
-  float target_sundisk_intensity = target_sundisk_integral / sundisk_area;
-  float actual_sundisk_integral = 1.0f * sundisk_area;
-  float actual_sundisk_intensity = sun_disk_intensity * 100.0f * actual_sundisk_integral / sundisk_area;
-  return vec2((target_sundisk_intensity == 0.0f) ? 0.0f : target_sundisk_intensity / actual_sundisk_intensity, sky_sunglow_scale);
+// night_brightness_adjustment :441-450
+static inline float ssNightBrightness(vec3 sunDir) {
+  const float lmt = 0.30901699437494742410229341718282f;
+  if (sunDir.z <= -lmt) return 0.0f;
+  float f = (sunDir.z + lmt) / lmt;
+  f = f * f;
+  f = f * f;
+  return f;
 }
 
-// :441-450
-static float night_brightness_adjustment(vec3 sun_dir) {
-  float lmt = 0.30901699437494742410229341718282f;
-  if (sun_dir.z <= -lmt) return 0.0f;
-  float factor = (sun_dir.z + lmt) / lmt;
-  factor *= factor;
-  factor *= factor;
-  return factor;
-}
-
-// :453-601
-vec3 sun_and_sky(const SunAndSky& ss, vec3 in_direction) {
-  vec3 result = vec3(0.0f);
-  float factor = 1.0f;
-  float night_factor = 1.0f;
-  vec3 out_color = vec3(0.0f);
-  vec3 rgb_scale = vec3(ss.rgb_unit_conversion.x, ss.rgb_unit_conversion.y, ss.rgb_unit_conversion.z);
-  vec3 dir = in_direction;
-  float horiz_height = ss.horizon_height / 10.0f;
-  dir = arch_vectortweak(dir, ss.y_is_up, horiz_height);
-  float local_haze = 2.0f + ss.haze;
-  if (local_haze < 2.0f) local_haze = 2.0f;
-  float local_saturation = tweak_saturation(ss.saturation, local_haze);
-  if (ss_luminance(rgb_scale) < 0.0f) rgb_scale = vec3(1.0f / 80000.0f);
-  rgb_scale *= ss.multiplier;
+// sun_and_sky :453-601
+vec3 sun_and_sky(const SunAndSky& ss, vec3 inDirection) {
+  float factor = 1.0f, nightFactor = 1.0f;
+  vec3 rgbScale = ssV(ss.rgb_unit_conversion);
+  const float horizHeight = ss.horizon_height / 10.0f;
+  vec3 dir = ssVectorTweak(inDirection, ss.y_is_up, horizHeight);
+  float localHaze = 2.0f + ss.haze;
+  if (localHaze < 2.0f) localHaze = 2.0f;
+  const float localSaturation = ssTweakSaturation(ss.saturation, localHaze);
+  if (ssLuminance(rgbScale) < 0.0f) rgbScale = vec3(1.0f / 80000.0f);
+  rgbScale = rgbScale * ss.multiplier;
   if (ss.multiplier <= 0.0f) return vec3(0.0f);
 
-  float downness = dir.z;
-  vec3 real_dir = dir;
-  if (dir.z < 0.001f) {                        // only calc for above-the-horizon
-    dir.z = 0.001f;
-    dir = normalize(dir);
-  }
+  const float downness = dir.z;
+  const vec3 realDir = dir;
+  if (dir.z < 0.001f) { dir.z = 0.001f; dir = normalize(dir); }   // only calc for above-the-horizon
 
-  vec3 sun_dir = vec3(ss.sun_direction.x, ss.sun_direction.y, ss.sun_direction.z);
-  sun_dir = normalize(sun_dir);
-  sun_dir = arch_vectortweak(sun_dir, ss.y_is_up, horiz_height);
-  vec3 real_sun_dir = sun_dir;
-  if (sun_dir.z < 0.001f) {
-    if (sun_dir.z < 0.0f) factor = night_brightness_adjustment(sun_dir);
-    sun_dir.z = 0.001f;
-    sun_dir = normalize(sun_dir);
+  vec3 sunDir = normalize(ssV(ss.sun_direction));
+  sunDir = ssVectorTweak(sunDir, ss.y_is_up, horizHeight);
+  const vec3 realSunDir = sunDir;
+  if (sunDir.z < 0.001f) {
+    if (sunDir.z < 0.0f) factor = ssNightBrightness(sunDir);
+    sunDir.z = 0.001f;
+    sunDir = normalize(sunDir);
   }
 
   vec3 tint;
   if (factor > 0.0f) {
-    tint = calc_env_color(sun_dir, dir, local_haze);
-    if (factor < 1.0f) tint *= factor;
-  } else {
-    tint = vec3(0.f);
-  }
-  vec3 data_sun_color = calc_sun_color(sun_dir, downness > 0.0f ? local_haze : 2.0f);
+    tint = ssEnvColor(sunDir, dir, localHaze);
+    if (factor < 1.0f) tint = tint * factor;
+  } else tint = vec3(0.0f);
+  const vec3 sunColor = ssSunColor(sunDir, downness > 0.0f ? localHaze : 2.0f);
   if (ss.sun_disk_intensity > 0.0f && ss.sun_disk_scale > 0.0f) {
-    float sun_angle = eid_acosf(dot(real_dir, real_sun_dir));
-    float sun_radius = 0.00465f * ss.sun_disk_scale * 10.0f;
-    if (sun_angle < sun_radius) {
-      float sky_sundisk_scale = 1.0f;
-      float sky_sunglow_scale = 1.0f;
-      if (ss.physically_scaled_sun == 1) {
-        vec2 return_value = calc_physical_scale(ss.sun_disk_scale, ss.sun_glow_intensity, ss.sun_disk_intensity);
-        sky_sundisk_scale = return_value.x;
-        sky_sunglow_scale = return_value.y;
-      }
-      float sun_factor = (1.0f - sun_angle / sun_radius) * 10.0f;
-      sun_factor = (eid_powf(sun_factor / 10.0f, 3.0f) * 2.0f * ss.sun_glow_intensity * sky_sunglow_scale
-                    + ss_smoothstep(8.5f, 9.5f + (local_haze / 50.0f), sun_factor) * 100.0f * ss.sun_disk_intensity * sky_sundisk_scale);
-      tint += data_sun_color * sun_factor;
+    const float sunAngle = eid_acosf(dot(realDir, realSunDir));
+    const float sunRadius = (0.00465f * ss.sun_disk_scale) * 10.0f;
+    if (sunAngle < sunRadius) {
+      float sundiskScale = 1.0f, sunglowScale = 1.0f;
+      if (ss.physically_scaled_sun == 1) ssPhysicalScale(ss.sun_disk_scale, ss.sun_glow_intensity, ss.sun_disk_intensity, sundiskScale, sunglowScale);
+      float sunFactor = (1.0f - sunAngle / sunRadius) * 10.0f;
+      sunFactor = ((eid_powf(sunFactor / 10.0f, 3.0f) * 2.0f) * ss.sun_glow_intensity) * sunglowScale +
+                  ((ssSmoothstep(8.5f, 9.5f + (localHaze / 50.0f), sunFactor) * 100.0f) * ss.sun_disk_intensity) * sundiskScale;
+      tint = tint + sunColor * sunFactor;
     }
   }
-  out_color = tint * rgb_scale;
+  vec3 outColor = tint * rgbScale;
   if (downness <= 0.0f) {
-    vec3 irrad = vec3(0.0f);
-    vec3 downcolor = vec3(ss.ground_color.x, ss.ground_color.y, ss.ground_color.z);
-    irrad = calc_irrad(sun_dir, 2.0f);
-    downcolor *= (irrad + data_sun_color * sun_dir.z) * rgb_scale;
-    if (factor < 1.0f) downcolor *= factor;
-    float hor_blur = ss.horizon_blur / 10.0f;
-    if (hor_blur > 0.0f) {
+    vec3 downColor = ssV(ss.ground_color);
+    const vec3 irrad = ssIrrad(sunDir, 2.0f);
+    downColor = downColor * ((irrad + sunColor * sunDir.z) * rgbScale);
+    if (factor < 1.0f) downColor = downColor * factor;
+    const float horBlur = ss.horizon_blur / 10.0f;
+    if (horBlur > 0.0f) {
       float dness = -downness;
-      dness /= hor_blur;
+      dness = dness / horBlur;
       if (dness > 1.0f) dness = 1.0f;
-      dness = ss_smoothstep(0.0f, 1.0f, dness);
-      out_color = out_color * (1.0f - dness) + downcolor * dness;
-      night_factor = 1.0f - dness;
-    } else {
-      out_color = downcolor;
-      night_factor = 0.0f;
-    }
+      dness = ssSmoothstep(0.0f, 1.0f, dness);
+      outColor = outColor * (1.0f - dness) + downColor * dness;
+      nightFactor = 1.0f - dness;
+    } else { outColor = downColor; nightFactor = 0.0f; }
   }
-
-  out_color = arch_colortweak(out_color, local_saturation, ss.redblueshift);
-  result = out_color;
-  if (night_factor > 0.0f) {
-    vec3 night = vec3(ss.night_color.x, ss.night_color.y, ss.night_color.z);
-    night *= night_factor;
-    vec3 rgb_result = result;
-    vec3 rgb_night = night;
-    if (rgb_result.x < rgb_night.x) rgb_result.x = rgb_night.x;
-    if (rgb_result.y < rgb_night.y) rgb_result.y = rgb_night.y;
-    if (rgb_result.z < rgb_night.z) rgb_result.z = rgb_night.z;
-    result = rgb_result;
+  vec3 result = ssColorTweak(outColor, localSaturation, ss.redblueshift);
+  if (nightFactor > 0.0f) {
+    const vec3 night = ssV(ss.night_color) * nightFactor;
+    if (result.x < night.x) result.x = night.x;
+    if (result.y < night.y) result.y = night.y;
+    if (result.z < night.z) result.z = night.z;
   }
-  result *= SS_M_PI;
-  return result;
+  return result * SS_PI;
 }
 
 }  // namespace orc
