@@ -140,6 +140,39 @@ def cornell_scene():
     return b.build(cam, "c2_cornell")
 
 
+def _trs(translate=(0, 0, 0), rot_y_deg=0.0, rot_x_deg=0.0, scale=(1, 1, 1)):
+    """Column-major 4x4 = T * Ry * Rx * S (float64 maths, stored as the float32 glTF matrix)."""
+    cy, sy = np.cos(np.deg2rad(rot_y_deg)), np.sin(np.deg2rad(rot_y_deg))
+    cx, sx = np.cos(np.deg2rad(rot_x_deg)), np.sin(np.deg2rad(rot_x_deg))
+    ry = np.array([[cy, 0, sy, 0], [0, 1, 0, 0], [-sy, 0, cy, 0], [0, 0, 0, 1]])
+    rx = np.array([[1, 0, 0, 0], [0, cx, -sx, 0], [0, sx, cx, 0], [0, 0, 0, 1]])
+    sc = np.diag([scale[0], scale[1], scale[2], 1.0])
+    t = np.eye(4)
+    t[:3, 3] = translate
+    m = t @ ry @ rx @ sc
+    return [float(np.float32(v)) for v in m.T.reshape(-1)]
+
+
+def instanced_scene():
+    """Node transforms: a room at identity, ONE unit-box prim mesh instanced by three nodes (rotation + non-uniform scale, a second
+    placement, a mirroring transform = negative determinant), and an emissive triangle on a rotated, scaled node."""
+    b = _Builder()
+    white = b.add_material(base=(0.75, 0.75, 0.75, 1), metallic=0.0, roughness=1.0)
+    blue = b.add_material(base=(0.2, 0.3, 0.8, 1), metallic=0.3, roughness=0.5)
+    lamp = b.add_material(base=(0, 0, 0, 1), metallic=0.0, roughness=1.0, emissive=(12.0, 11.0, 9.0))
+    b.add_quads(_box_quads((-1.5, 0.0, -1.5), (1.5, 2.2, 1.5), "yYZxX", inward=True), white)
+    b.add_quads(_box_quads((-0.5, 0.0, -0.5), (0.5, 1.0, 0.5), "xXYzZ"), blue, matrix=_trs((-0.6, 0.0, 0.3), 30.0, 0.0, (0.6, 1.2, 0.5)))
+    box = len(b.prims) - 1
+    b.nodes.append(dict(worldMatrix=_trs((0.7, 0.0, -0.2), -20.0, 0.0, (0.5, 0.6, 0.7)), primMesh=box))
+    b.nodes.append(dict(worldMatrix=_trs((0.1, 0.9, 0.9), 10.0, 25.0, (-0.4, 0.4, 0.4)), primMesh=box))      # mirrored instance
+    b.add_tris([[(-0.5, 0.0, -0.5), (0.5, 0.0, -0.5), (-0.5, 0.0, 0.5)]], lamp, matrix=_trs((0.0, 2.15, 0.0), 45.0, 180.0, (0.8, 1.0, 1.3)))
+    m = list(IDENTITY)
+    m[12], m[13], m[14] = -1.0, 1.6, -1.0
+    b.lights.append(dict(worldMatrix=m, type=1, color=(1.0, 0.9, 0.8), intensity=6.0))
+    cam = dict(eye=(0.0, 1.1, -4.2), center=(0.0, 0.9, 0.0), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(45.0)))
+    return b.build(cam, "instanced_box")
+
+
 def _procedural_images(seed=21):
     """Five small RGBA8 images: colour checker, metallic-roughness map, tangent-space normal map, emissive pattern, transmission."""
     rng = np.random.Generator(np.random.PCG64(seed))

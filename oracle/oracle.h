@@ -21,12 +21,12 @@
  *     and dispatched over whole frames in 8x8 work groups like Renderer::run (ref_trace.cpp, ref_post.cpp).  Every
  *     buffer this oracle leaves after every frame — G-buffer, motion vectors, both reservoir buffers, pre-denoise and
  *     final images — is BIT-IDENTICAL to what the reference's text leaves (tests/test_oracle_kat.py), for point /
- *     triangle / HDR / sun & sky lighting, ReSTIR off / RIS / temporal, ragged sizes; and so is the CUDA path
- *     (tests/test_gpu_parity.py).
+ *     triangle / HDR / sun & sky lighting, ReSTIR off / RIS / temporal, ragged sizes, textured materials, instanced /
+ *     rotated / mirrored nodes; and so is the CUDA path (tests/test_gpu_parity.py).
  * What remains the numerical CONTRACT of DESIGN.md §3 rather than the reference's own arithmetic: the ray queries
  * (they run inside the Vulkan driver: hit acceptance, tie-break, candidate order), the rounding of the GLSL built-ins
  * (pow, exp, sin, normalize ...), the fixed-function samplers, and the un-vendored glTF import of nvpro_core.  The pin
- * scenes are opaque, untextured, with identity node transforms.
+ * scenes are opaque (HitTest, the stochastic-alpha callback, lives with the ray queries in traceray_rq.glsl).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libeidola.so) never links or calls it.

@@ -152,6 +152,32 @@ ORC_API int orc_env_read_accel(Environment* e, void* dst, size_t bytes) {
 ORC_API void orc_env_texture(Environment* e, const float* uv, int n, float* out) {
   for (int i = 0; i < n; ++i) { vec3 c = e->texture(vec2(uv[2 * i], uv[2 * i + 1])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
+// sampler tap used by oracle/ref_shim (the reference's shader text compiled as C++): index < 0: obj = Environment*, lat-long map; else
+// obj = Scene*, texturesMap[index]; textureLod(..., 0) of the contract's samplers -> RGBA
+ORC_API void orc_sample(void* obj, int index, const float* uv, int n, float* rgba) {
+  for (int i = 0; i < n; ++i) {
+    const vec2 t(uv[2 * i], uv[2 * i + 1]);
+    vec4 c;
+    if (index < 0) c = vec4(static_cast<Environment*>(obj)->texture(t), 1.0f);
+    else {
+      const Scene* s = static_cast<Scene*>(obj);
+      c = (index < (int)s->textures.size()) ? s->textures[index].sample(t) : vec4(1.0f);
+    }
+    rgba[4 * i] = c.x; rgba[4 * i + 1] = c.y; rgba[4 * i + 2] = c.z; rgba[4 * i + 3] = c.w;
+  }
+}
+// per instance (= node): objectToWorld, worldToObject as the ray query reports them (mat4x3, 12 + 12 floats, column-major)
+ORC_API int orc_scene_instance_xforms(Scene* s, float* out, int maxInstances) {
+  const int n = (int)s->objectToWorld.size();
+  for (int i = 0; i < n && i < maxInstances; ++i)
+    for (int c = 0; c < 4; ++c) {
+      const vec3 a = s->objectToWorld[i].c[c], b = s->worldToObject[i].c[c];
+      float* o = out + 24 * i;
+      o[3 * c] = a.x; o[3 * c + 1] = a.y; o[3 * c + 2] = a.z; o[12 + 3 * c] = b.x; o[12 + 3 * c + 1] = b.y; o[12 + 3 * c + 2] = b.z;
+    }
+  return n;
+}
+ORC_API int orc_scene_texture_count(Scene* s) { return (int)s->textures.size(); }
 ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; return 0; }
 // RenderOutput::run over the frame rendered last: out = width*height RGBA32F at the allocation pitch
 ORC_API int orc_renderer_run_output(Renderer* r, const Tonemapper* tm, const RtxState* st, float* out) {

@@ -35,13 +35,13 @@ const GltfShadeMaterial* materials; const TrigLight* trigLights; const PuncLight
 PtPayload prd;
 // samplers are NOT the reference's arithmetic (fixed-function hardware): texture() of the environment map goes through a function the
 // test installs (the contract's bilinear sampler); material textures are not bound in these tests
-typedef void (*EnvSamplerFn)(void* env, const float* uv, int n, float* rgb);
-struct sampler2D { EnvSamplerFn fn; void* env; unsigned int width, height; };
+typedef void (*SamplerFn)(void* obj, int index, const float* uv, int n, float* rgba);   // index < 0: the environment map
+struct sampler2D { SamplerFn fn; void* obj; int index; unsigned int width, height; };
 struct uvec2 { unsigned int x, y; };
 sampler2D environmentTexture; sampler2D texturesMap[1];
 #define nonuniformEXT(x) (x)
 static uvec2 textureSize(const sampler2D& s, int) { return uvec2{s.width, s.height}; }
-static vec4 texture(const sampler2D& s, vec2 uv) { float in[2] = {uv.x, uv.y}, o[3] = {0, 0, 0}; if (s.fn) s.fn(s.env, in, 1, o); return vec4(o[0], o[1], o[2], 1.0f); }
+static vec4 texture(const sampler2D& s, vec2 uv) { float in[2] = {uv.x, uv.y}, o[4] = {0, 0, 0, 1}; if (s.fn && s.obj) s.fn(s.obj, s.index, in, 1, o); return vec4(o[0], o[1], o[2], o[3]); }
 static vec4 textureLod(const sampler2D& s, vec2 uv, float) { return texture(s, uv); }
 #include "../_ref/gen/gltf_material.hpp"   // SRGBtoLINEAR only
 #include "../_ref/gen/env_sampling.hpp"    // Environment_sample, EnvSample
@@ -124,7 +124,7 @@ REF_API int ref_fn(int which, const float* in, int n, float* out) {
 REF_API void ref_scene_set(const RtxState* st, const SceneCamera* cam, const SunAndSky* ss, const LightBufInfo* lbi, const GltfShadeMaterial* mats,
                            const TrigLight* trig, const PuncLight* punc, const ImptSampData* envAccel, void* envSamplerFn, void* env, uint32_t envW, uint32_t envH) {
   rtxState = *st; sceneCamera = *cam; _sunAndSky = *ss; lightBufInfo = *lbi; materials = mats; trigLights = trig; puncLights = punc; envSamplingData = envAccel;
-  environmentTexture = sampler2D{(EnvSamplerFn)envSamplerFn, env, envW, envH};
+  environmentTexture = sampler2D{(SamplerFn)envSamplerFn, env, -1, envW, envH};
 }
 // scene-dependent functions (same numbering as orc_ctx_fn): 0 SampleDirectLightNoVisibility (seed, pos -> pdf, Li, wi, dist, seed'),
 // 1 LightEval (matID, dist, dir, ffnormal, area -> Li, pdf), 2 EnvEval (dir -> radiance, pdf), 3 EnvRadiance, 4 raySpawn (coord, size ->

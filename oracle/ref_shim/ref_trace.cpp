@@ -6,7 +6,8 @@
  * Renderer::run (src/renderer.cpp:163-176).  What a shader build binds (layouts.glsl) is provided as plain globals.  The ONE part that
  * is not the reference's text is traceray_rq.glsl: its ray queries run inside the Vulkan driver, so ClosestHit / AnyHit call an
  * intersector the test installs (the oracle's, i.e. the hit contract of DESIGN.md §3); opaque geometry only (HitTest is never reached).
- * Node transforms of the test scenes are identity, so objectToWorld / worldToObject are identity matrices.
+ * texture() / textureLod() are fixed-function hardware in the reference: they call the contract's samplers through a function pointer.
+ * objectToWorld / worldToObject of a hit are what the driver would report for the instance: the test passes the scene's per-node matrices.
  * Compiled with -ftrivial-auto-var-init=zero: a GLSL local that is read before it is written (`LightSample lsample;` of a rejected
  * candidate) is undefined in the shader; the contract defines it as zero.
  */
@@ -52,11 +53,12 @@ static void imageStore(const iimage2D& im, ivec2 c, ivec4 v) {   // a 16-bit sig
 }
 struct Indices { const uvec3* i; explicit Indices(uint64_t a) : i(reinterpret_cast<const uvec3*>(a)) {} };
 struct Vertices { const VertexAttributes* v; explicit Vertices(uint64_t a) : v(reinterpret_cast<const VertexAttributes*>(a)) {} };
-struct sampler2D { void (*fn)(void*, const float*, int, float*); void* env; unsigned int width, height; };
+typedef void (*SamplerFn)(void* obj, int index, const float* uv, int n, float* rgba);   // the contract's samplers (index < 0: environment map)
+struct sampler2D { SamplerFn fn; void* obj; int index; unsigned int width, height; };
 using orc::uvec2;
 struct InvocationId { unsigned int x, y, z; ivec2 xy() const { return ivec2((int)x, (int)y); } };
 static uvec2 textureSize(const sampler2D& s, int) { return uvec2{s.width, s.height}; }
-static vec4 texture(const sampler2D& s, vec2 uv) { float in[2] = {uv.x, uv.y}, o[3] = {0, 0, 0}; if (s.fn) s.fn(s.env, in, 1, o); return vec4(o[0], o[1], o[2], 1.0f); }
+static vec4 texture(const sampler2D& s, vec2 uv) { float in[2] = {uv.x, uv.y}, o[4] = {0, 0, 0, 1}; if (s.fn && s.obj) s.fn(s.obj, s.index, in, 1, o); return vec4(o[0], o[1], o[2], o[3]); }
 static vec4 textureLod(const sampler2D& s, vec2 uv, float) { return texture(s, uv); }
 #define nonuniformEXT(x) (x)
 #define shared static
@@ -67,7 +69,7 @@ static image2D thisDirectResultImage, thisIndirectResultImage, lastDirectResultI
 static uimage2D thisGbuffer, lastGbuffer;
 static iimage2D motionVector;
 static const InstanceData* geoInfo; static SceneCamera sceneCamera; static const GltfShadeMaterial* materials; static const PuncLight* puncLights;
-static const TrigLight* trigLights; static LightBufInfo lightBufInfo; static sampler2D texturesMap[1]; static SunAndSky _sunAndSky;
+static const TrigLight* trigLights; static LightBufInfo lightBufInfo; static sampler2D texturesMap[256]; static SunAndSky _sunAndSky;
 static sampler2D environmentTexture; static const ImptSampData* envSamplingData;
 static DirectReservoir *lastDirectResv, *thisDirectResv, *tempDirectResv;
 static IndirectReservoir *lastIndirectResv, *thisIndirectResv, *tempIndirectResv;
@@ -79,6 +81,7 @@ static unsigned int gl_LocalInvocationIndex;
 struct HitRec { float hitT; int primitiveID, instanceID, instanceCustomIndex; float baryU, baryV; };
 typedef int (*TraceFn)(void* scene, const float* rays, uint32_t n, int anyHit, HitRec* hits);
 static TraceFn g_trace; static void* g_scene;
+static const float* g_xforms;     // per instance: objectToWorld, worldToObject (12 + 12 floats) as the driver's ray query reports them; null = identity
 static unsigned long long g_closest, g_any;
 struct Ray; struct PtPayload;
 }  // namespace reftrace
@@ -113,6 +116,7 @@ struct RefTraceBind {   // everything ref_trace_bind needs, as one C struct (fil
   void* traceFn; void* scene;
   int32_t allocW, allocH;
   void *thisG, *lastG, *motion, *thisDR, *lastDR, *thisIR, *lastIR, *direct, *indirect, *indA;
+  const float* instanceXforms;
 };
 
 template <class F>
@@ -132,8 +136,9 @@ extern "C" __attribute__((visibility("default")))
 void ref_trace_run(const RefTraceBind* b, int runDirect, int runIndirect, unsigned long long* rays) {
   rtxState = *b->state; sceneCamera = *b->camera; _sunAndSky = *b->sunSky; lightBufInfo = *b->lightInfo;
   geoInfo = b->geoInfo; materials = b->materials; trigLights = b->trigLights; puncLights = b->puncLights; envSamplingData = b->envAccel;
-  environmentTexture = sampler2D{(void (*)(void*, const float*, int, float*))b->envSamplerFn, b->env, b->envW, b->envH};
-  g_trace = (TraceFn)b->traceFn; g_scene = b->scene; g_closest = g_any = 0;
+  environmentTexture = sampler2D{(SamplerFn)b->envSamplerFn, b->env, -1, b->envW, b->envH};
+  for (int i = 0; i < 256; ++i) texturesMap[i] = sampler2D{(SamplerFn)b->envSamplerFn, b->scene, i, 1u, 1u};   // material textures: the scene's samplers
+  g_trace = (TraceFn)b->traceFn; g_scene = b->scene; g_xforms = b->instanceXforms; g_closest = g_any = 0;
   auto img = [&](void* p) { return image2D{(vec4*)p, b->allocW, b->allocH, b->allocW}; };
   thisGbuffer = uimage2D{(uvec4*)b->thisG, b->allocW, b->allocH, b->allocW}; lastGbuffer = uimage2D{(uvec4*)b->lastG, b->allocW, b->allocH, b->allocW};
   motionVector = iimage2D{(int16_t*)b->motion, b->allocW, b->allocH, b->allocW};

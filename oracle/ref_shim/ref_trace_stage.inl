@@ -13,8 +13,13 @@ static void ClosestHit(Ray r) {
   ++g_closest;
   prd.hitT = h.hitT; prd.primitiveID = h.primitiveID; prd.instanceID = h.instanceID; prd.instanceCustomIndex = h.instanceCustomIndex;
   prd.baryCoord = vec2(h.baryU, h.baryV);
-  mat4x3 identity; identity.c[0] = vec3(1.0f, 0.0f, 0.0f); identity.c[1] = vec3(0.0f, 1.0f, 0.0f); identity.c[2] = vec3(0.0f, 0.0f, 1.0f); identity.c[3] = vec3(0.0f);
-  prd.objectToWorld = identity; prd.worldToObject = identity;
+  mat4x3 o2w, w2o;
+  o2w.c[0] = w2o.c[0] = vec3(1.0f, 0.0f, 0.0f); o2w.c[1] = w2o.c[1] = vec3(0.0f, 1.0f, 0.0f); o2w.c[2] = w2o.c[2] = vec3(0.0f, 0.0f, 1.0f); o2w.c[3] = w2o.c[3] = vec3(0.0f);
+  if (g_xforms && h.instanceID >= 0) {
+    const float* m = g_xforms + 24 * (size_t)h.instanceID;
+    for (int c = 0; c < 4; ++c) { o2w.c[c] = vec3(m[3 * c], m[3 * c + 1], m[3 * c + 2]); w2o.c[c] = vec3(m[12 + 3 * c], m[12 + 3 * c + 1], m[12 + 3 * c + 2]); }
+  }
+  prd.objectToWorld = o2w; prd.worldToObject = w2o;
 }
 static bool AnyHit(Ray r, float maxDist) {
   const float ray[8] = {r.origin.x, r.origin.y, r.origin.z, maxDist, r.direction.x, r.direction.y, r.direction.z, 0.0f};

@@ -128,7 +128,7 @@ def ref_scene_set(R, osc, env, ss, st, abi):
     """Binds the oracle scene's tables (what layouts.glsl binds) to the reference-GLSL library; returns the arrays to keep alive."""
     tabs = [np.ascontiguousarray(osc.table(t)) for t in (abi.TABLE_CAMERA, abi.TABLE_LIGHT_INFO, abi.TABLE_MATERIALS, abi.TABLE_TRIG_LIGHTS, abi.TABLE_PUNC_LIGHTS)]
     acc = env.accel() if env else np.zeros(1, abi.IMPT_DT)
-    fnp = C.cast(lib().orc_env_texture, C.c_void_p) if env else None     # the sampler is the contract's, not the reference's arithmetic
+    fnp = C.cast(lib().orc_sample, C.c_void_p) if env else None     # the sampler is the contract's, not the reference's arithmetic
     R.ref_scene_set(C.addressof(st), tabs[0].ctypes.data, C.addressof(ss), tabs[1].ctypes.data, tabs[2].ctypes.data, tabs[3].ctypes.data, tabs[4].ctypes.data,
                     acc.ctypes.data, fnp, env._h if env else None, env.w if env else 0, env.h if env else 0)
     return tabs, acc
@@ -138,7 +138,7 @@ class RefTraceBind(C.Structure):      # oracle/ref_shim/ref_trace.cpp
     _fields_ = [(n, C.c_void_p) for n in ("state", "camera", "sunSky", "lightInfo", "geoInfo", "materials", "trigLights", "puncLights", "envAccel",
                                           "envSamplerFn", "env")] + [("envW", C.c_uint32), ("envH", C.c_uint32), ("traceFn", C.c_void_p), ("scene", C.c_void_p),
                                                                      ("allocW", C.c_int32), ("allocH", C.c_int32)] + [
-        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA")]
+        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA", "instanceXforms")]
 
 
 class RefTracer:
@@ -159,6 +159,8 @@ class RefTracer:
             geo[i]["indexAddress"] = self.ibufs[i].ctypes.data
             geo[i]["materialIndex"] = p["materialIndex"]
         self.geo = geo
+        self.xforms = np.zeros((max(1, len(arrays.nodes)), 24), np.float32)      # what the ray query reports per instance
+        assert lib().orc_scene_instance_xforms(osc._h, self.xforms.ctypes.data_as(C.c_void_p), len(arrays.nodes)) == len(arrays.nodes)
         self.ss = sun_sky if sun_sky is not None else abi.default_sun_and_sky(in_use=0)
         self.acc = env.accel() if env else np.zeros(1, abi.IMPT_DT)
         self.G = [np.zeros((h, w, 4), np.uint32) for _ in range(2)]
@@ -175,13 +177,15 @@ class RefTracer:
         b.state, b.camera, b.sunSky, b.lightInfo = C.addressof(st), cam.ctypes.data, C.addressof(self.ss), self.tabs["TABLE_LIGHT_INFO"].ctypes.data
         b.geoInfo, b.materials = self.geo.ctypes.data, self.tabs["TABLE_MATERIALS"].ctypes.data
         b.trigLights, b.puncLights, b.envAccel = self.tabs["TABLE_TRIG_LIGHTS"].ctypes.data, self.tabs["TABLE_PUNC_LIGHTS"].ctypes.data, self.acc.ctypes.data
+        b.envSamplerFn = C.cast(lib().orc_sample, C.c_void_p)      # the contract's samplers: environment map (index < 0) and texturesMap[i]
         if self.env:
-            b.envSamplerFn, b.env, b.envW, b.envH = C.cast(lib().orc_env_texture, C.c_void_p), self.env._h, self.env.w, self.env.h
+            b.env, b.envW, b.envH = self.env._h, self.env.w, self.env.h
         b.traceFn, b.scene = C.cast(lib().orc_accel_trace, C.c_void_p), self.osc._h
         b.allocW, b.allocH = self.size
         b.thisG, b.lastG, b.motion = self.G[1 - s].ctypes.data, self.G[s].ctypes.data, self.motion.ctypes.data
         b.thisDR, b.lastDR, b.thisIR, b.lastIR = self.DR[1 - s].ctypes.data, self.DR[s].ctypes.data, self.IR[1 - s].ctypes.data, self.IR[s].ctypes.data
         b.direct, b.indirect, b.indA = self.direct.ctypes.data, self.indirect.ctypes.data, self.indA.ctypes.data
+        b.instanceXforms = self.xforms.ctypes.data
         self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
         return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
                 "direct": self.direct, "ind_tmp_a": self.indA}

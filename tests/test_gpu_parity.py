@@ -376,6 +376,14 @@ def test_stochastic_alpha_mask_and_blend():
     _run_frames(scenes.alpha_scene(), (128, 96), 2, "alpha-eNone", ReSTIRState=abi.eNone, maxDepth=2)
 
 
+def test_instanced_and_mirrored_nodes():
+    """One prim mesh instanced by three nodes (rotation + non-uniform scale, a mirroring transform), an emissive triangle on a transformed
+    node: GetState's object-to-world handling, facing decided in object space, world-space TrigLight vertices."""
+    worst = _run_frames(scenes.instanced_scene(), (192, 128), 3, "instanced", maxDepth=3)
+    assert max(worst.values()) == 0.0
+    _run_frames(scenes.instanced_scene(), (96, 64), 2, "instanced-mega", wavefront=False, maxDepth=3)
+
+
 def test_c1_cube_direct_only():
     """BASELINE config 0: single cube, 256x256, RIS M=1, no denoise, direct only."""
     _run_frames(scenes.cube_scene(), (256, 256), 1, "C1", ReSTIRState=abi.eRIS, RISSampleNum=1, denoise=0)
