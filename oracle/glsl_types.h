@@ -26,6 +26,7 @@ struct vec2 {
   vec2(float a) : x(a), y(a) {}
   vec2(float a, float b) : x(a), y(b) {}
   explicit vec2(ivec2 v) : x((float)v.x), y((float)v.y) {}   // GLSL vec2(ivec2)
+  vec2 xy() const { return *this; }
 };
 struct vec4;
 struct vec3 {

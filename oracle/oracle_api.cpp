@@ -166,6 +166,16 @@ ORC_API void orc_sample(void* obj, int index, const float* uv, int n, float* rgb
     rgba[4 * i] = c.x; rgba[4 * i + 1] = c.y; rgba[4 * i + 2] = c.z; rgba[4 * i + 3] = c.w;
   }
 }
+// the driver's candidate enumeration as the contract fixes it: the first candidate strictly after `low` in
+// (t, instanceID, primitiveID) order with 0 < t < tmax; rec = {hitT, primitiveID, instanceID, instanceCustomIndex, baryU, baryV, opaque}
+ORC_API int orc_accel_next_candidate(Scene* s, const float* ray, int haveLow, float lowT, int lowInst, int lowPrim, float* rec) {
+  const HitKey key{lowT, lowInst, lowPrim};
+  const Hit h = s->closestHit(vec3(ray[0], ray[1], ray[2]), vec3(ray[4], ray[5], ray[6]), ray[3], nullptr, haveLow ? &key : nullptr);
+  if (!(h.hitT < 1e28f) || h.primitiveID < 0) return 0;
+  rec[0] = h.hitT; rec[1] = intBitsToFloat(h.primitiveID); rec[2] = intBitsToFloat(h.instanceID); rec[3] = intBitsToFloat(h.instanceCustomIndex);
+  rec[4] = h.bary.x; rec[5] = h.bary.y; rec[6] = intBitsToFloat(h.opaque);
+  return 1;
+}
 // per instance (= node): objectToWorld, worldToObject as the ray query reports them (mat4x3, 12 + 12 floats, column-major)
 ORC_API int orc_scene_instance_xforms(Scene* s, float* out, int maxInstances) {
   const int n = (int)s->objectToWorld.size();

@@ -3,9 +3,10 @@
  * The reference's two trace stages — shaders/direct_stage.comp and indirect_stage.comp with everything they include (globals, random,
  * common, pathtrace, pbr_metallicworkflow, gltf_material, env_sampling, sun_and_sky, shade_state, reservoir, compress) — compiled WHOLE,
  * main() included, as C++ from the transliterations of glsl_prep.py, and dispatched over a frame in 8x8 work groups like
- * Renderer::run (src/renderer.cpp:163-176).  What a shader build binds (layouts.glsl) is provided as plain globals.  The ONE part that
- * is not the reference's text is traceray_rq.glsl: its ray queries run inside the Vulkan driver, so ClosestHit / AnyHit call an
- * intersector the test installs (the oracle's, i.e. the hit contract of DESIGN.md §3); opaque geometry only (HitTest is never reached).
+ * Renderer::run (src/renderer.cpp:163-176).  What a shader build binds (layouts.glsl) is provided as plain globals.  traceray_rq.glsl
+ * (ClosestHit, AnyHit, HitTest) is the reference's text too; what stands in for the Vulkan driver is only the rayQuery*EXT built-ins
+ * (ref_trace_stage.inl): candidates come from an intersector the test installs (the oracle's) in the order the contract fixes
+ * (front to back by (t, instanceID, primitiveID); opaque candidates commit at once, others go through HitTest).
  * texture() / textureLod() are fixed-function hardware in the reference: they call the contract's samplers through a function pointer.
  * objectToWorld / worldToObject of a hit are what the driver would report for the instance: the test passes the scene's per-node matrices.
  * Compiled with -ftrivial-auto-var-init=zero: a GLSL local that is read before it is written (`LightSample lsample;` of a rejected
@@ -78,9 +79,9 @@ static InvocationId gl_GlobalInvocationID, gl_LocalInvocationID, gl_WorkGroupID;
 static unsigned int gl_LocalInvocationIndex;
 
 // ---- the intersector (stands in for the driver's ray queries of traceray_rq.glsl) -----------------------------------------------------
-struct HitRec { float hitT; int primitiveID, instanceID, instanceCustomIndex; float baryU, baryV; };
-typedef int (*TraceFn)(void* scene, const float* rays, uint32_t n, int anyHit, HitRec* hits);
-static TraceFn g_trace; static void* g_scene;
+// next candidate strictly after (lowT, lowInst, lowPrim) in front-to-back order; rec = {t, prim, inst, customIndex, u, v, opaque} (ints as bits)
+typedef int (*NextCandidateFn)(void* scene, const float* ray, int haveLow, float lowT, int lowInst, int lowPrim, float* rec);
+static NextCandidateFn g_trace; static void* g_scene;
 static const float* g_xforms;     // per instance: objectToWorld, worldToObject (12 + 12 floats) as the driver's ray query reports them; null = identity
 static unsigned long long g_closest, g_any;
 struct Ray; struct PtPayload;
@@ -138,7 +139,7 @@ void ref_trace_run(const RefTraceBind* b, int runDirect, int runIndirect, unsign
   geoInfo = b->geoInfo; materials = b->materials; trigLights = b->trigLights; puncLights = b->puncLights; envSamplingData = b->envAccel;
   environmentTexture = sampler2D{(SamplerFn)b->envSamplerFn, b->env, -1, b->envW, b->envH};
   for (int i = 0; i < 256; ++i) texturesMap[i] = sampler2D{(SamplerFn)b->envSamplerFn, b->scene, i, 1u, 1u};   // material textures: the scene's samplers
-  g_trace = (TraceFn)b->traceFn; g_scene = b->scene; g_xforms = b->instanceXforms; g_closest = g_any = 0;
+  g_trace = (NextCandidateFn)b->traceFn; g_scene = b->scene; g_xforms = b->instanceXforms; g_closest = g_any = 0;
   auto img = [&](void* p) { return image2D{(vec4*)p, b->allocW, b->allocH, b->allocW}; };
   thisGbuffer = uimage2D{(uvec4*)b->thisG, b->allocW, b->allocH, b->allocW}; lastGbuffer = uimage2D{(uvec4*)b->lastG, b->allocW, b->allocH, b->allocW};
   motionVector = iimage2D{(int16_t*)b->motion, b->allocW, b->allocH, b->allocW};

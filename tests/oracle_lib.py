@@ -180,7 +180,7 @@ class RefTracer:
         b.envSamplerFn = C.cast(lib().orc_sample, C.c_void_p)      # the contract's samplers: environment map (index < 0) and texturesMap[i]
         if self.env:
             b.env, b.envW, b.envH = self.env._h, self.env.w, self.env.h
-        b.traceFn, b.scene = C.cast(lib().orc_accel_trace, C.c_void_p), self.osc._h
+        b.traceFn, b.scene = C.cast(lib().orc_accel_next_candidate, C.c_void_p), self.osc._h      # the driver's candidate enumeration (contract order)
         b.allocW, b.allocH = self.size
         b.thisG, b.lastG, b.motion = self.G[1 - s].ctypes.data, self.G[s].ctypes.data, self.motion.ctypes.data
         b.thisDR, b.lastDR, b.thisIR, b.lastIR = self.DR[1 - s].ctypes.data, self.DR[s].ctypes.data, self.IR[1 - s].ctypes.data, self.IR[s].ctypes.data

@@ -135,7 +135,8 @@ TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth
                  ("cornell_none", "cornell_scene", (40, 24), 2, "none", dict(ReSTIRState=0, maxDepth=2)),
                  ("room_ragged", "small_room", (50, 34), 2, "none", dict(RISSampleNum=2, maxDepth=4, MIS=0)),
                  ("textured", "textured_scene", (64, 48), 2, "none", dict(maxDepth=3)),
-                 ("instanced", "instanced_scene", (64, 48), 2, "none", dict(maxDepth=3))]
+                 ("instanced", "instanced_scene", (64, 48), 2, "none", dict(maxDepth=3)),
+                 ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3))]
 TRACE_KEYS = ("gbuffer", "motion", "direct_resv", "indirect_resv", "direct", "ind_tmp_a")
 
 
