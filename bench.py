@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 MAX_DEPTH = 3
+RESTIR_STATE = 3     # eTemporal: the reference's default (sample_example.hpp:165) and the headline configuration; --restir changes it
 WORKLOAD = "C3: procedural closed room, 707x707-quad noise height-field floor (999,698 tris) + 10 wall tris + 1,000 emissive tris, " \
            "1920x1080, ReSTIR DI+GI temporal, M=4, maxDepth 3, MIS, denoise on (K1..K5), static camera"
 
@@ -54,7 +55,7 @@ def scene_arrays(quick=False):
 def frame_state(info, frame, w=W, h=H):
     from eidola_b200 import abi
     return abi.default_rtx_state(
-        w, h, environmentProb=0.0, time=1000 + 16 * frame, maxDepth=MAX_DEPTH,
+        w, h, environmentProb=0.0, time=1000 + 16 * frame, maxDepth=MAX_DEPTH, ReSTIRState=RESTIR_STATE,
         fireflyClampThreshold=float(np.float32(4 * np.pi)), envMapLuminIntegInv=float(np.float32(1 / np.pi)),
         lightLuminIntegInv=float(np.float32(1.0) / (np.float32(info.trigLightWeight) + np.float32(info.puncLightWeight))))
 
@@ -414,6 +415,7 @@ def run_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[_ACTIVE]["text"] if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
                        "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
+                       "ReSTIRState": ["none", "ris", "spatial", "temporal", "spatiotemporal"][RESTIR_STATE],
                        "parallelism": ("%d interleaved row stripes per rank x%d ranks; exchange 1: all-gather of pre-denoise G-buffer/direct/indirect; %s" % (
                            args.stripe_groups, world, "denoise+compose per band, exchange 2: all-gather of the two final images" if args.post == "sharded"
                            else "denoise+compose replicated on every rank")) if world > 1 else "single GPU",
@@ -472,10 +474,13 @@ def main():
     ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
                     help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
                          "one exchange step, every rank post-processes the full frame")
+    ap.add_argument("--restir", default="temporal", choices=["none", "ris", "spatial", "temporal", "spatiotemporal"],
+                    help="RtxState.ReSTIRState (default temporal = the reference's default and the headline configuration)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = headline (BASELINE.json metric); c4 = 4K; c5 = 10 M triangles")
     args = ap.parse_args()
-    global _ACTIVE
+    global _ACTIVE, RESTIR_STATE
     _ACTIVE = args.workload
+    RESTIR_STATE = ["none", "ris", "spatial", "temporal", "spatiotemporal"].index(args.restir)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -180,7 +180,7 @@ class FrameStats(C.Structure):
 # eid_buffer
 (BUF_THIS_GBUFFER, BUF_LAST_GBUFFER, BUF_MOTION, BUF_THIS_DIRECT_RESV, BUF_LAST_DIRECT_RESV,
  BUF_THIS_INDIRECT_RESV, BUF_LAST_INDIRECT_RESV, BUF_DIRECT, BUF_INDIRECT, BUF_DENOISE_DIR_A,
- BUF_DENOISE_DIR_B, BUF_DENOISE_IND_A, BUF_DENOISE_IND_B, BUF_DISPLAY_F32, BUF_DISPLAY_RGBA8) = range(15)
+ BUF_DENOISE_DIR_B, BUF_DENOISE_IND_A, BUF_DENOISE_IND_B, BUF_DISPLAY_F32, BUF_DISPLAY_RGBA8, BUF_TEMP_DIRECT_RESV) = range(16)
 
 # ---- numpy views of the device tables --------------------------------------------------------------
 IMPT_DT = np.dtype([("alias", "<i4"), ("q", "<f4"), ("pdf", "<f4"), ("aliasPdf", "<f4")])
@@ -227,7 +227,8 @@ BUFFER_DTYPES = {BUF_THIS_GBUFFER: np.dtype("<u4"), BUF_LAST_GBUFFER: np.dtype("
                  BUF_LAST_INDIRECT_RESV: INDIRECT_RESV_DT, BUF_DIRECT: np.dtype("<f4"),
                  BUF_INDIRECT: np.dtype("<f4"), BUF_DENOISE_DIR_A: np.dtype("<f4"),
                  BUF_DENOISE_DIR_B: np.dtype("<f4"), BUF_DENOISE_IND_A: np.dtype("<f4"),
-                 BUF_DENOISE_IND_B: np.dtype("<f4"), BUF_DISPLAY_F32: np.dtype("<f4"), BUF_DISPLAY_RGBA8: np.dtype("u1")}
+                 BUF_DENOISE_IND_B: np.dtype("<f4"), BUF_DISPLAY_F32: np.dtype("<f4"), BUF_DISPLAY_RGBA8: np.dtype("u1"),
+                 BUF_TEMP_DIRECT_RESV: DIRECT_RESV_DT}
 
 
 class SceneArrays:

@@ -59,6 +59,8 @@ struct FrameParams {
   float* thisDR; const float* lastDR;     // DirectReservoir records, 9 floats each, pitch st.size.x
   float* thisIR; const float* lastIR;     // IndirectReservoir records, 19 floats each, pitch st.size.x/2
   float4* directImg; float4* indirectImg;
+  float* tempDR;                          // tempDirectResv (spatial reuse), pitch st.size.x; one buffer, persists across frames
+  float4* spCont;                         // spatial reuse: what k_direct_spatial needs of a pixel's State, 3 planes of pitch*allocH
   float4* dirA; float4* dirB; float4* indA; float4* indB;
   float4* geomPos; float4* geomNrm;       // denoiser geometry planes (full res): pos.xyz + hash bits / normal.xyz
   float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
@@ -188,6 +190,10 @@ DEV void loadDResv(const float* base, size_t i, DResv& r) {
   r.Li = mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); r.wi = mk3(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5));
   r.dist = __ldg(p + 6); r.num = __float_as_uint(__ldg(p + 7)); r.weight = __ldg(p + 8);
 }
+DEV void loadDResvPlain(const float* base, size_t i, DResv& r) {
+  const float* p = base + 9 * i;
+  r.Li = mk3(p[0], p[1], p[2]); r.wi = mk3(p[3], p[4], p[5]); r.dist = p[6]; r.num = __float_as_uint(p[7]); r.weight = p[8];
+}
 DEV void storeDResv(float* base, size_t i, const DResv& r) {
   float* p = base + 9 * i;
   p[0] = r.Li.x; p[1] = r.Li.y; p[2] = r.Li.z; p[3] = r.wi.x; p[4] = r.wi.y; p[5] = r.wi.z; p[6] = r.dist; p[7] = __uint_as_float(r.num); p[8] = r.weight;
@@ -196,10 +202,22 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 // =================================================================================================
 // K1 — direct_stage.comp
 // =================================================================================================
-template <bool STATS, bool TEX>
-__global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P) {
-  const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
+// SPATIAL (eSpatial / eSpatiotemporal, :224-255): the pixel stops where the reference has its first barrier() — it writes
+// tempDirectResv and its continuation record — and k_direct_spatial finishes it once every pixel's entry is written (the race-free
+// reading of the reference).  halo = 1: the launch covers the row above and the row below each owned stripe (multi-GPU),
+// 64 pixels of one row per block; such pixels only write tempDirectResv, which the stripe's edge rows read.
+template <bool STATS, bool TEX, bool SPATIAL>
+__global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P, const int halo) {
+  int x = blockIdx.x * 8 + threadIdx.x, y;
+  if (SPATIAL && halo) {
+    x = blockIdx.x * 64 + threadIdx.y * 8 + threadIdx.x;
+    const int k = blockIdx.y >> 1;
+    y = (blockIdx.y & 1) ? P.sFirst + k * P.sStride + P.sRows : P.sFirst + k * P.sStride - 1;
+    if (y < 0) y = 0x3fffffff;
+  } else {
+    y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
+  }
+  const bool own = !(SPATIAL && halo);
   RayCounters rc = {0, 0, 0, 0, 0};
   const int W = P.st.size.x, H = P.st.size.y;
   if (x < W && y < H) {
@@ -209,10 +227,13 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     const size_t pix = (size_t)y * P.pitch + x;
     f3 radiance;
     Payload prd;
+    bool finished = true;
     if (!closestHit<STATS, TEX>(P, ro, rd, prd, seed, rc)) {                 // :154-158
-      P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
-      P.motion[pix] = make_short2(0, 0);
-      radiance = envRadiance<TEX>(P, rd);
+      if (own) {
+        P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
+        P.motion[pix] = make_short2(0, 0);
+        radiance = envRadiance<TEX>(P, rd);
+      }
     } else {
       rc.primary++;
       State st = getState<TEX>(P.sc, prd, rd);
@@ -222,8 +243,10 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
       mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
       const float mvx = __fadd_rn(__fmul_rn(__fdiv_rn(pr[0], pr[3]), 0.5f), 0.5f), mvy = __fadd_rn(__fmul_rn(__fdiv_rn(pr[1], pr[3]), 0.5f), 0.5f);
       const int mix_ = f2i_sat(__fmul_rn(mvx, (float)W)), miy = f2i_sat(__fmul_rn(mvy, (float)H));
-      P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
-      P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
+      if (own) {
+        P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
+        P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
+      }
 
       if (P.st.debugging_mode > eIndirectStage) {          // DebugInfo (pathtrace.glsl:362-380)
         switch (P.st.debugging_mode) {
@@ -283,8 +306,19 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
             if (resvInvalidW(tmp.weight)) { tmp.num = 0; tmp.weight = 0.f; }
             const int clampN = P.st.RISSampleNum * P.st.reservoirClamp;
             if (tmp.num > (uint32_t)clampN) { tmp.weight = __fmul_rn(tmp.weight, __fdiv_rn((float)clampN, (float)tmp.num)); tmp.num = (uint32_t)clampN; }
-            storeDResv(P.thisDR, (size_t)y * W + x, tmp);
+            if (own) storeDResv(P.thisDR, (size_t)y * W + x, tmp);
           }
+          if (SPATIAL && (P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal)) {   // :224-231, up to the barrier
+            if (resvInvalidW(resv.weight)) { resv.num = 0; resv.weight = 0.f; }                     // resvCheckValidity
+            storeDResv(P.tempDR, (size_t)y * W + x, resv);                                          // cacheTempReservoir
+            if (own) {
+              const size_t plane = (size_t)P.pitch * P.allocH;
+              P.spCont[pix] = make_float4(__uint_as_float(seed), st.mat.roughness, st.mat.metallic, st.mat.emission.z);
+              P.spCont[plane + pix] = make_float4(st.normal.x, st.normal.y, st.normal.z, st.ffnormal.x);
+              P.spCont[2 * plane + pix] = make_float4(st.ffnormal.y, st.ffnormal.z, st.mat.emission.x, st.mat.emission.y);
+            }
+            finished = false;
+          } else
           if (!resvInvalidW(resv.weight)) {                // :256-261 — shading uses the un-clamped reservoir
             f3 LiBsdf = resv.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, resv.wi);
             direct = ((LiBsdf / lum3(LiBsdf)) * resv.weight) / (float)resv.num;
@@ -294,10 +328,90 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
         radiance = hdrToLdr(clampRadiance(st.mat.emission + direct, P.st.fireflyClampThreshold));
       }
     }
-    const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);   // :283
-    P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+    if (!finished) {
+      if (own) P.directImg[pix] = make_float4(0.f, 0.f, 0.f, -1.0f);     // marker: k_direct_spatial completes this pixel
+    } else if (own) {
+      const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);   // :283
+      P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+    }
   }
+  if (!own) rc = RayCounters{0, 0, 0, 0, 0};     // a halo pixel's rays are the owner's, traced twice: not counted
   flushCounters<STATS>(P, rc);
+}
+
+// Second half of direct_stage.comp for eSpatial / eSpatiotemporal (:232-270): mergeSpatialNeighbors twice (5 candidates each, at most one
+// pixel away — toConcentricDisk is never scaled by `Radius`), the final merge and the shading.  Reads the neighbours' tempDirectResv
+// entries, all written by the k_direct_stage launches before it.
+DEV bool mergeSpatialNeighbors(const FrameParams& P, int x, int y, f3 norm, float depth, f3 pnorm, float pdepth, uint32_t& seed, DResv& agg) {   // :110-123
+  const int W = P.st.size.x, H = P.st.size.y;
+  bool valid = false;
+  agg.num = 0; agg.weight = 0.f;                                           // resvReset keeps the light sample
+  for (int i = 0; i < 5; i++) {
+    const float r0 = rnd(seed), r1 = rnd(seed);                            // findSpatialNeighbor :86-108
+    float dx, dy;
+    toConcentricDisk(r0, r1, dx, dy);
+    const int px = f2i_sat(__fadd_rn(__fadd_rn((float)x, dx), 0.5f)), py = f2i_sat(__fadd_rn(__fadd_rn((float)y, dy), 0.5f));
+    if (!(px >= 0 && px < W && py >= 0 && py < H)) continue;
+    if (dot3(norm, pnorm) < 0.5f || fabsf(__fsub_rn(depth, pdepth)) > __fmul_rn(depth, 0.1f)) continue;   // against the pixel's OWN G-buffer entry, as there
+    DResv sp;
+    loadDResvPlain(P.tempDR, (size_t)py * W + px, sp);
+    if (!resvInvalidW(sp.weight)) {
+      const float rv = rnd(seed);
+      agg.weight = __fadd_rn(agg.weight, sp.weight);
+      agg.num += sp.num;
+      if (__fmul_rn(rv, agg.weight) < sp.weight) { agg.Li = sp.Li; agg.wi = sp.wi; agg.dist = sp.dist; }
+      valid = true;
+    }
+  }
+  return valid;
+}
+__global__ void __launch_bounds__(64) k_direct_spatial(const FrameParams P) {
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
+  const int W = P.st.size.x, H = P.st.size.y;
+  if (x >= W || y >= H) return;
+  const size_t pix = (size_t)y * P.pitch + x;
+  if (P.directImg[pix].w != -1.0f) return;                                 // sky, emitter, debug view: finished by k_direct_stage
+  const size_t plane = (size_t)P.pitch * P.allocH;
+  const float4 c0 = P.spCont[pix], c1 = P.spCont[plane + pix], c2 = P.spCont[2 * plane + pix];
+  uint32_t seed = __float_as_uint(c0.x);
+  const float roughness = c0.y, metallic = c0.z;
+  const f3 emission = mk3(c2.z, c2.w, c0.w), normal = mk3(c1.x, c1.y, c1.z), ffnormal = mk3(c1.w, c2.x, c2.y);
+  const uint4 g = P.thisG[pix];                                            // loadThisGeometryInfo(imageCoords): depth is prd.hitT bit for bit
+  const f3 pnorm = octDecode(g.y);
+  const float pdepth = __uint_as_float(g.x), depth = pdepth;
+  f3 ro, rd;
+  raySpawn<true>(P.cam, x, y, W, H, ro, rd);
+  const f3 wo = -rd;
+  DResv resv;
+  loadDResvPlain(P.tempDR, (size_t)y * W + x, resv);                       // the pixel's own entry = its reservoir at the barrier
+  DResv spatial; spatial.Li = mk3(0.f); spatial.wi = mk3(0.f); spatial.dist = 0.f; spatial.num = 0; spatial.weight = 0.f;
+  DResv agg; agg.Li = mk3(0.f); agg.wi = mk3(0.f); agg.dist = 0.f; agg.num = 0; agg.weight = 0.f;
+  for (int round = 0; round < 2; ++round) {                                // :236-252 (the second cacheTempReservoir rewrites the same entry)
+    if (mergeSpatialNeighbors(P, x, y, normal, depth, pnorm, pdepth, seed, agg)) {
+      if (!resvInvalidW(agg.weight)) {
+        const float rv = rnd(seed);
+        spatial.weight = __fadd_rn(spatial.weight, agg.weight);
+        spatial.num += agg.num;
+        if (__fmul_rn(rv, spatial.weight) < agg.weight) { spatial.Li = agg.Li; spatial.wi = agg.wi; spatial.dist = agg.dist; }
+      }
+    }
+  }
+  if (!resvInvalidW(spatial.weight)) {                                     // :253-256
+    const float rv = rnd(seed);
+    resv.weight = __fadd_rn(resv.weight, spatial.weight);
+    resv.num += spatial.num;
+    if (__fmul_rn(rv, resv.weight) < spatial.weight) { resv.Li = spatial.Li; resv.wi = spatial.wi; resv.dist = spatial.dist; }
+  }
+  f3 direct = mk3(0.0f);
+  if (!resvInvalidW(resv.weight)) {                                        // :259-262
+    f3 LiBsdf = resv.Li * bsdfEval(mk3(1.0f), roughness, metallic, ffnormal, wo, resv.wi);
+    direct = ((LiBsdf / lum3(LiBsdf)) * resv.weight) / (float)resv.num;
+  }
+  if (nan3(direct)) direct = mk3(0.0f);
+  const f3 radiance = hdrToLdr(clampRadiance(emission + direct, P.st.fireflyClampThreshold));
+  const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);
+  P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
 }
 
 // =================================================================================================
@@ -1077,6 +1191,7 @@ struct eid_renderer {
   float* directResv[2] = {nullptr, nullptr};
   float* indirectResv[2] = {nullptr, nullptr};
   float4* directImg = nullptr; float4* indirectImg = nullptr;
+  float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
   float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
@@ -1120,6 +1235,7 @@ struct eid_renderer {
 void eid_renderer::release() {
   for (int i = 0; i < 2; ++i) { cudaFree(gbuffer[i]); cudaFree(directResv[i]); cudaFree(indirectResv[i]); gbuffer[i] = nullptr; directResv[i] = nullptr; indirectResv[i] = nullptr; }
   cudaFree(motion); motion = nullptr;
+  cudaFree(tempDirectResv); cudaFree(spatialCont); tempDirectResv = nullptr; spatialCont = nullptr;
   cudaFree(displayF); cudaFree(display8); displayF = nullptr; display8 = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
@@ -1181,8 +1297,6 @@ WaveView eid_renderer::waveView() const {
 static void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
   if (st.size.x <= 0 || st.size.y <= 0 || (uint32_t)st.size.x > r->width || (uint32_t)st.size.y > r->height)
     raise(EID_ERR_INVALID, "RtxState.size %dx%d outside the renderer allocation %ux%u", st.size.x, st.size.y, r->width, r->height);
-  if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal)
-    raise(EID_ERR_UNSUPPORTED, "spatial reuse (direct_stage.comp:224-255) is racy in the reference and outside the parity contract");
   if (st.environmentProb > 0.0f && !r->envMap && r->sunSky.in_use != 1)
     raise(EID_ERR_UNSUPPORTED, "environmentProb > 0 needs an environment to sample: an HDR map (eid_env_create + eid_renderer_set_env) or sun & sky (eid_renderer_set_sun_and_sky with in_use = 1)");
   if (st.RISSampleNum < 0 || st.maxDepth < 0) raise(EID_ERR_INVALID, "negative RISSampleNum / maxDepth");
@@ -1196,6 +1310,13 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
   P.thisDR = r->directResv[!set]; P.lastDR = r->directResv[set];
   P.thisIR = r->indirectResv[!set]; P.lastIR = r->indirectResv[set];
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
+  if ((st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal) && !r->tempDirectResv) {   // m_directTempResv (renderer.cpp:235), on first use
+    const size_t n = (size_t)r->width * r->height;
+    CUDA_CHECK(cudaMalloc((void**)&r->tempDirectResv, n * sizeof(DirectReservoir)));
+    CUDA_CHECK(cudaMemsetAsync(r->tempDirectResv, 0, n * sizeof(DirectReservoir), r->stream));
+    CUDA_CHECK(cudaMalloc((void**)&r->spatialCont, 3 * n * sizeof(float4)));
+  }
+  P.tempDR = r->tempDirectResv; P.spCont = r->spatialCont;
   P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
   P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
   for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
@@ -1229,9 +1350,24 @@ static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) 
     dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
-    if (r->countVisits) { if (tex) k_direct_stage<true, true><<<g, b, 0, st>>>(P); else k_direct_stage<true, false><<<g, b, 0, st>>>(P); }
-    else { if (tex) k_direct_stage<false, true><<<g, b, 0, st>>>(P); else k_direct_stage<false, false><<<g, b, 0, st>>>(P); }
-    r->stats.kernelLaunches[EID_K_DIRECT]++;
+    const bool spatial = P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal;
+    if (!spatial) {
+      if (r->countVisits) { if (tex) k_direct_stage<true, true, false><<<g, b, 0, st>>>(P, 0); else k_direct_stage<true, false, false><<<g, b, 0, st>>>(P, 0); }
+      else { if (tex) k_direct_stage<false, true, false><<<g, b, 0, st>>>(P, 0); else k_direct_stage<false, false, false><<<g, b, 0, st>>>(P, 0); }
+      r->stats.kernelLaunches[EID_K_DIRECT]++;
+    } else {
+      // spatial reuse: every pixel up to its tempDirectResv write (owned stripes, then — when the stripes do not cover the frame — the
+      // row above and the row below each stripe), then the neighbour merge and the shading
+      auto first = [&](dim3 grid, int halo) {
+        if (r->countVisits) { if (tex) k_direct_stage<true, true, true><<<grid, b, 0, st>>>(P, halo); else k_direct_stage<true, false, true><<<grid, b, 0, st>>>(P, halo); }
+        else { if (tex) k_direct_stage<false, true, true><<<grid, b, 0, st>>>(P, halo); else k_direct_stage<false, false, true><<<grid, b, 0, st>>>(P, halo); }
+        r->stats.kernelLaunches[EID_K_DIRECT]++;
+      };
+      first(g, 0);
+      if (P.sFirst > 0 || P.sCount > 1 || P.sFirst + P.sRows < P.st.size.y) first(dim3((P.st.size.x + 63) / 64, 2 * P.sCount), 1);
+      k_direct_spatial<<<g, b, 0, st>>>(P);
+      r->stats.kernelLaunches[EID_K_DIRECT]++;
+    }
   }
   markStop(r, EID_K_DIRECT, st);
 }
@@ -1437,6 +1573,7 @@ static void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
       bytes = n * 16; return r->denoiseTemp[which - EID_BUF_DENOISE_DIR_A];
     case EID_BUF_DISPLAY_F32: bytes = n * 16; return r->displayF;
     case EID_BUF_DISPLAY_RGBA8: bytes = n * 4; return r->display8;
+    case EID_BUF_TEMP_DIRECT_RESV: bytes = n * sizeof(DirectReservoir); return r->tempDirectResv;
     default: return nullptr;
   }
 }

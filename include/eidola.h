@@ -217,7 +217,9 @@ typedef enum eid_buffer {
   EID_BUF_DENOISE_DIR_A = 9, EID_BUF_DENOISE_DIR_B = 10,
   EID_BUF_DENOISE_IND_A = 11, EID_BUF_DENOISE_IND_B = 12,
   EID_BUF_DISPLAY_F32 = 13,        /* output of eid_renderer_run_output: float x4 / pixel    */
-  EID_BUF_DISPLAY_RGBA8 = 14       /* ... and its UNORM8 packing, 4 bytes / pixel            */
+  EID_BUF_DISPLAY_RGBA8 = 14,      /* ... and its UNORM8 packing, 4 bytes / pixel            */
+  EID_BUF_TEMP_DIRECT_RESV = 15    /* tempDirectResv (spatial reuse scratch, one buffer for both sets, renderer.cpp:235);
+                                      exists once a frame has run with eSpatial / eSpatiotemporal */
 } eid_buffer;
 
 /* kernels of one Renderer::run, in launch order */

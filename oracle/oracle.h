@@ -128,6 +128,7 @@ struct Renderer {
   std::vector<uvec4> gbuffer[2];
   std::vector<int16_t> motion;         // 2 per pixel
   std::vector<DirectReservoir> directResv[2];
+  std::vector<DirectReservoir> tempDirectResv;          // spatial reuse scratch (renderer.hpp: m_tempDirectResv); persists across frames
   std::vector<IndirectReservoir> indirectResv[2];
   std::vector<vec4> directResult, indirectResult;       // thisDirectResultImage / thisIndirectResultImage
   std::vector<vec4> denoiseTemp[4];                     // DirTempA, DirTempB, IndTempA, IndTempB

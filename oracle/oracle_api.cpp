@@ -237,6 +237,7 @@ static void* bufPtr(Renderer* r, int which, size_t& bytes) {
     case EID_BUF_INDIRECT: bytes = r->indirectResult.size() * 16; return r->indirectResult.data();
     case EID_BUF_DENOISE_DIR_A: case EID_BUF_DENOISE_DIR_B: case EID_BUF_DENOISE_IND_A: case EID_BUF_DENOISE_IND_B:
       bytes = r->denoiseTemp[which - EID_BUF_DENOISE_DIR_A].size() * 16; return r->denoiseTemp[which - EID_BUF_DENOISE_DIR_A].data();
+    case EID_BUF_TEMP_DIRECT_RESV: bytes = r->tempDirectResv.size() * sizeof(DirectReservoir); return r->tempDirectResv.data();
     default: return nullptr;
   }
 }

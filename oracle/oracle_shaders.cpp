@@ -227,6 +227,7 @@ struct Ctx {
   std::vector<IndirectReservoir>& thisIndirectResv; const std::vector<IndirectReservoir>& lastIndirectResv;
   PtPayload prd; ivec2 imageCoords;
   uint32_t pitch;   // allocation width of the 2-D images
+  bool primeOnly = false;   // spatial reuse, first dispatch: run up to cacheTempReservoir and stop (see Renderer::runDirect)
 
   Ctx(const Scene& s, Renderer& r, const RtxState& st, int set)
       : sc(s), rr(r), rtxState(st), cam(s.camera),
@@ -678,6 +679,39 @@ struct Ctx {
     }
     return false;
   }
+  void loadThisGeometryInfo(ivec2 c, vec3& normal, float& depth) {                            // pathtrace.glsl:247-251
+    uvec4 gInfo = loadG(thisGbuffer, c);
+    normal = decompress_unit_vec(gInfo.y);
+    depth = uintBitsToFloat(gInfo.x);
+  }
+  bool findSpatialNeighbor(vec3 norm, float depth, uint matId, DirectReservoir& resv) {       // :86-108 (Radius is unused there too)
+    (void)matId;
+    const float r0 = rand(), r1 = rand();
+    vec2 p = toConcentricDisk(vec2(r0, r1));
+    int px = f2i(float((float)imageCoords.x + p.x) + 0.5f);
+    int py = f2i(float((float)imageCoords.y + p.y) + 0.5f);
+    int pidx = py * rtxState.size.x + px;
+    vec3 pnorm; float pdepth;
+    loadThisGeometryInfo(imageCoords, pnorm, pdepth);      // the pixel's own G-buffer entry, as in the reference
+    if (!inBound(ivec2(px, py), size())) return false;
+    else if (dot(norm, pnorm) < 0.5f || gabs(depth - pdepth) > depth * 0.1f) return false;
+    resv = rr.tempDirectResv[(size_t)pidx];
+    return true;
+  }
+  bool mergeSpatialNeighbors(vec3 norm, float depth, uint matId, DirectReservoir& resv) {     // :110-123
+    bool valid = false;
+    resvReset(resv);
+    for (int i = 0; i < 5; i++) {
+      DirectReservoir spatial{};
+      if (findSpatialNeighbor(norm, depth, matId, spatial)) {
+        if (!resvInvalid(spatial)) {
+          resvMerge(resv, spatial, rand());
+          valid = true;
+        }
+      }
+    }
+    return valid;
+  }
   ivec2 createMotionIndex(vec3 wpos) {                                                         // :125-139
     const mat4& LPV = *reinterpret_cast<const mat4*>(&cam.lastProjView);
     vec4 proj = mul(LPV, vec4(wpos, 1.0f));
@@ -747,7 +781,27 @@ struct Ctx {
       resvClamp(tempResv, rtxState.RISSampleNum * rtxState.reservoirClamp);
       thisDirectResv[(size_t)imageCoords.y * rtxState.size.x + imageCoords.x] = tempResv;   // saveNewReservoir
 
-      // eSpatial / eSpatiotemporal (:224-255) is racy in the reference and excluded from the contract.
+      if (rtxState.ReSTIRState == eSpatial || rtxState.ReSTIRState == eSpatiotemporal) {       // :224-255
+        // The reference separates its writes of tempDirectResv from the neighbours' reads by barrier(), which only orders one 8x8 work
+        // group.  The contract is the race-free reading: every pixel's write happens before any pixel's read (Renderer::runDirect
+        // dispatches the stage twice; a pixel writes the same value both times, so this is what the reference computes whenever its
+        // neighbours' writes have landed).  Pixels that never get here (sky, emitters, debug views) keep their older entry, as there.
+        DirectReservoir spatial{};
+        resvReset(spatial);
+        resvCheckValidity(resv);
+        rr.tempDirectResv[(size_t)imageCoords.y * rtxState.size.x + imageCoords.x] = resv;      // cacheTempReservoir
+        if (primeOnly) return vec3(0.0f);
+        DirectReservoir spatialAggregate{};
+        if (mergeSpatialNeighbors(state.normal, prd.hitT, state.matID, spatialAggregate)) {
+          if (!resvInvalid(spatialAggregate)) resvMerge(spatial, spatialAggregate, rand());
+        }
+        resvCheckValidity(resv);
+        rr.tempDirectResv[(size_t)imageCoords.y * rtxState.size.x + imageCoords.x] = resv;
+        if (mergeSpatialNeighbors(state.normal, prd.hitT, state.matID, spatialAggregate)) {
+          if (!resvInvalid(spatialAggregate)) resvMerge(spatial, spatialAggregate, rand());
+        }
+        if (!resvInvalid(spatial)) resvMerge(resv, spatial, rand());
+      }
       lsample = resv.lightSample;
       if (!resvInvalid(resv)) {
         vec3 LiBsdf = V(lsample.Li) * Eval(state, wo, state.ffnormal, V(lsample.wi));
@@ -1054,6 +1108,7 @@ void Renderer::create(const Scene* s, uint32_t w, uint32_t h) {    // renderer.c
   for (int i = 0; i < 2; ++i) {
     gbuffer[i].assign(n, uvec4());
     directResv[i].assign(n, DirectReservoir{});
+    if (i == 0) tempDirectResv.assign(n, DirectReservoir{});
     indirectResv[i].assign(ni, IndirectReservoir{});
   }
   motion.assign(2 * n, 0);
@@ -1082,6 +1137,14 @@ static double nowMs() { return std::chrono::duration<double, std::milli>(std::ch
 void Renderer::runDirect(const RtxState& st, int frames, int y0, int y1) {
   int set = (frames + 1) % 2;   // renderer.cpp:157
   double t0 = nowMs();
+  if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal) {
+    // spatial reuse reads tempDirectResv of pixels up to one row / column away: a first dispatch (one halo row beyond the band) carries
+    // every pixel up to its write of tempDirectResv, so the second one reads completed entries whatever the group order.  The first
+    // dispatch's rays are not counted (they are the second one's, traced twice).
+    const uint64_t c0 = closestRays, a0 = anyRays, p0 = primaryHits;
+    dispatch(st.size.x, st.size.y, y0 > 0 ? y0 - 1 : 0, y1 < st.size.y ? y1 + 1 : y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.primeOnly = true; c.directMain(x, y); });
+    closestRays = c0; anyRays = a0; primaryHits = p0;
+  }
   dispatch(st.size.x, st.size.y, y0, y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.directMain(x, y); });
   kernelMs[0] += nowMs() - t0;
 }

@@ -118,6 +118,7 @@ struct RefTraceBind {   // everything ref_trace_bind needs, as one C struct (fil
   int32_t allocW, allocH;
   void *thisG, *lastG, *motion, *thisDR, *lastDR, *thisIR, *lastIR, *direct, *indirect, *indA;
   const float* instanceXforms;
+  void* tempDR;      // tempDirectResv (one buffer for both descriptor sets, renderer.cpp:235, 349); persists across frames
 };
 
 template <class F>
@@ -147,6 +148,15 @@ void ref_trace_run(const RefTraceBind* b, int runDirect, int runIndirect, unsign
   thisDirectResv = (DirectReservoir*)b->thisDR; lastDirectResv = (DirectReservoir*)b->lastDR;
   thisIndirectResv = (IndirectReservoir*)b->thisIR; lastIndirectResv = (IndirectReservoir*)b->lastIR;
   const int W = rtxState.size.x, H = rtxState.size.y;
+  tempDirectResv = (DirectReservoir*)b->tempDR;
+  if (runDirect && (rtxState.ReSTIRState == eSpatial || rtxState.ReSTIRState == eSpatiotemporal)) {
+    // Spatial reuse (direct_stage.comp:224-255) reads the neighbours' tempDirectResv entries behind a barrier() that orders one work group
+    // only.  The contract is its race-free reading — all writes before all reads — obtained from the unmodified text by dispatching the
+    // stage twice: each invocation writes the same entry both times (nothing it writes before the barrier depends on what it reads after
+    // it), so in the second dispatch every read sees the neighbour's completed entry; the first dispatch's image is overwritten.
+    dispatchGroups(W, H, [] { k1::main(); });
+    g_closest = g_any = 0;
+  }
   if (runDirect) dispatchGroups(W, H, [] { k1::main(); });
   if (runIndirect) dispatchGroups(W / 2, H / 2, [] { k2::main(); });
   if (rays) { rays[0] = g_closest; rays[1] = g_any; }

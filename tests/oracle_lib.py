@@ -138,7 +138,7 @@ class RefTraceBind(C.Structure):      # oracle/ref_shim/ref_trace.cpp
     _fields_ = [(n, C.c_void_p) for n in ("state", "camera", "sunSky", "lightInfo", "geoInfo", "materials", "trigLights", "puncLights", "envAccel",
                                           "envSamplerFn", "env")] + [("envW", C.c_uint32), ("envH", C.c_uint32), ("traceFn", C.c_void_p), ("scene", C.c_void_p),
                                                                      ("allocW", C.c_int32), ("allocH", C.c_int32)] + [
-        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA", "instanceXforms")]
+        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA", "instanceXforms", "tempDR")]
 
 
 class RefTracer:
@@ -166,6 +166,7 @@ class RefTracer:
         self.G = [np.zeros((h, w, 4), np.uint32) for _ in range(2)]
         self.DR = [np.zeros(w * h, abi.DIRECT_RESV_DT) for _ in range(2)]
         self.IR = [np.zeros((w // 2) * (h // 2), abi.INDIRECT_RESV_DT) for _ in range(2)]
+        self.tempDR = np.zeros(w * h, abi.DIRECT_RESV_DT)      # tempDirectResv: one buffer, persists across frames (renderer.cpp:235)
         self.motion = np.zeros((h, w, 2), np.int16)
         self.direct, self.indirect, self.indA = (np.zeros((h, w, 4), np.float32) for _ in range(3))
         self.rays = np.zeros(2, np.uint64)
@@ -186,6 +187,7 @@ class RefTracer:
         b.thisDR, b.lastDR, b.thisIR, b.lastIR = self.DR[1 - s].ctypes.data, self.DR[s].ctypes.data, self.IR[1 - s].ctypes.data, self.IR[s].ctypes.data
         b.direct, b.indirect, b.indA = self.direct.ctypes.data, self.indirect.ctypes.data, self.indA.ctypes.data
         b.instanceXforms = self.xforms.ctypes.data
+        b.tempDR = self.tempDR.ctypes.data
         self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
         return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
                 "direct": self.direct, "ind_tmp_a": self.indA}

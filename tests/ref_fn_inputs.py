@@ -136,7 +136,9 @@ TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth
                  ("room_ragged", "small_room", (50, 34), 2, "none", dict(RISSampleNum=2, maxDepth=4, MIS=0)),
                  ("textured", "textured_scene", (64, 48), 2, "none", dict(maxDepth=3)),
                  ("instanced", "instanced_scene", (64, 48), 2, "none", dict(maxDepth=3)),
-                 ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3))]
+                 ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3)),
+                 ("spatial", "cornell_scene", (64, 40), 2, "none", dict(ReSTIRState=2, maxDepth=2)),            # eSpatial (race-free reading)
+                 ("spatiotemporal", "small_room", (50, 34), 3, "none", dict(ReSTIRState=4, maxDepth=2))]      # eSpatiotemporal
 TRACE_KEYS = ("gbuffer", "motion", "direct_resv", "indirect_resv", "direct", "ind_tmp_a")
 
 

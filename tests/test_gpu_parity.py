@@ -137,6 +137,37 @@ def _run_frames(arrays, size, frames, tag, orbit=False, strict=True, env_img=Non
     return worst
 
 
+@pytest.mark.parametrize("restir", [abi.eSpatial, abi.eSpatiotemporal])
+def test_spatial_reuse_matches_oracle(restir):
+    """eSpatial / eSpatiotemporal (direct_stage.comp:224-255) in its race-free reading (every tempDirectResv write before any read,
+    DESIGN.md §3): k_direct_stage<SPATIAL> + k_direct_spatial against the oracle — which the reference's own shader text, dispatched
+    twice, reproduces bit for bit (tests/golden/ref_trace.npz, configurations `spatial` / `spatiotemporal`).  Covers sky pixels and
+    emitters (they never write their tempDirectResv entry), a frame smaller than the allocation, an orbiting camera, both K2 forms."""
+    for arrays, size, frames, tag, kw in ((scenes.small_room(), (256, 144), 4, "room", dict(orbit=True)),
+                                           (scenes.cube_scene(), (96, 64), 3, "cube", dict(wavefront=False)),
+                                           (scenes.cornell_scene(), (200, 120), 3, "cornell", dict(RISSampleNum=2, maxDepth=2))):
+        worst = _run_frames(arrays, size, frames, "%s-restir%d" % (tag, restir), ReSTIRState=restir, **kw)
+        assert max(worst.values()) == 0.0
+    # tempDirectResv itself, and a frame smaller than the allocation (pitch of the reservoir buffers = size.x, of the images = allocation)
+    arrays = scenes.small_room()
+    osc, orr, psc, acc, prr = common.make_pair(arrays, (160, 96))
+    for s in (osc, psc):
+        s.update_camera(120, 80)
+    info = psc.info()
+    for f in range(3):
+        for s in (osc, psc):
+            s.update_camera(120, 80)
+        st = common.frame_state(120, 80, info, f, ReSTIRState=restir)
+        orr.run(st, f); prr.run(st, f); prr.sync()
+        rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "sub-allocation frame %d" % f)
+        assert all(v == 0.0 for v in rep.values()), rep
+        assert prr.read(abi.BUF_TEMP_DIRECT_RESV).tobytes() == orr.read(abi.BUF_TEMP_DIRECT_RESV).tobytes()
+    # the same renderer back on temporal-only reuse: the spatial scratch is simply not touched
+    st = common.frame_state(120, 80, info, 3)
+    orr.run(st, 3); prr.run(st, 3); prr.sync()
+    assert all(v == 0.0 for v in common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "back to temporal").values())
+
+
 def test_fast_math_denoiser_within_tolerance():
     """Default (MUFU ex2) denoiser: images within the 1e-3 contract (measured ~1e-6); ints and reservoirs stay bit-exact."""
     worst = _run_frames(scenes.small_room(), (256, 144), 3, "room-fastmath", strict=False)
@@ -495,9 +526,11 @@ def test_state_size_smaller_than_allocation():
         common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "descaled frame %d" % f)
 
 
-def test_band_sharded_trace_equals_full_frame():
+@pytest.mark.parametrize("restir", [abi.eTemporal, abi.eSpatiotemporal])
+def test_band_sharded_trace_equals_full_frame(restir):
     """Multi-GPU decomposition on one device: two renderers trace disjoint row bands, the exchange buffers are
-    stitched (what the all-gather does), post-processing runs on the full frame -> identical to a single run."""
+    stitched (what the all-gather does), post-processing runs on the full frame -> identical to a single run.  With spatial reuse
+    each band also carries the row above and the row below it up to the tempDirectResv write (the halo launch of k_direct_stage)."""
     arrays = scenes.small_room()
     size = (256, 144)
     psc = eid.Scene(0)
@@ -516,10 +549,12 @@ def test_band_sharded_trace_equals_full_frame():
                 abi.BUF_THIS_INDIRECT_RESV]
     for f in range(3):
         psc.update_camera(*size)
-        st = common.frame_state(size[0], size[1], info, f)
+        st = common.frame_state(size[0], size[1], info, f, ReSTIRState=restir)
         full.run(st, f)
         a.run_trace(st, f)
         b.run_trace(st, f)
+        assert (a.stats().closestHitRays + b.stats().closestHitRays, a.stats().anyHitRays + b.stats().anyHitRays) == (
+            full.stats().closestHitRays, full.stats().anyHitRays)          # halo rows are not counted twice
         for which in exchange:
             ba, bb = a.read(which).view(np.uint8).copy(), b.read(which).view(np.uint8)
             _, off, n = b.band_range(which)
@@ -694,8 +729,6 @@ def test_error_behaviour_gpu():
     psc.update_camera(64, 64)
     with pytest.raises(eid.EidolaError):
         r.run(common.frame_state(128, 64, info, 0), 0)                       # size beyond the allocation
-    with pytest.raises(eid.EidolaError):
-        r.run(common.frame_state(64, 64, info, 0, ReSTIRState=abi.eSpatial), 0)   # outside the contract
     with pytest.raises(eid.EidolaError):
         r.run(common.frame_state(64, 64, info, 0, environmentProb=0.25), 0)  # needs an HDR map (sun & sky not implemented)
     with pytest.raises(eid.EidolaError):
