@@ -1031,8 +1031,26 @@ __global__ void __launch_bounds__(256) k_compose(const FrameParams P, const floa
 // pixel (uvCoords = (pixel + 0.5) / size, tm.zoom = 1, tm.renderingRatio = (1, 1); the reference's sampler is NEAREST, so
 // texture(img, uvCoords) is texel (x, y)), direct + indirect, Uncharted-2 tonemap (tonemapping.glsl:39-95), pcg3d-noise dither at
 // 1/255 (post.frag:50-57, random.glsl:81-92), contrast / brightness / saturation / vignette.  Writes the float colour and its
-// RGBA8 packing (what a UNORM swapchain stores).  tm.autoExposure needs the blit-generated mip chain: not supported.
+// RGBA8 packing (what a UNORM swapchain stores).  tm.autoExposure bit 0: the average colour is the 1x1 level of the mip chain that
+// RenderOutput::genMipmap blits from the result images (k_mip_blit, level by level), then toneExposure (post.frag:65-70).
 // =================================================================================================
+// One level of nvvk::cmdGenerateMipmaps: vkCmdBlitImage with VK_FILTER_LINEAR from (sw x sh) to (dw x dh) = max(1, previous / 2);
+// destination texel (i, j) samples the source at (i + 0.5) * sw / dw - 0.5, bilinear, clamped to the edge
+__global__ void __launch_bounds__(256) k_mip_blit(const float4* __restrict__ src, int sw, int sh, int spitch, float4* __restrict__ dst, int dw, int dh) {
+  const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+  if (i >= dw || j >= dh) return;
+  const float scaleU = (float)sw / (float)dw, scaleV = (float)sh / (float)dh;
+  const float a = ((float)i + 0.5f) * scaleU - 0.5f, b = ((float)j + 0.5f) * scaleV - 0.5f;
+  const float af = eid_floorf(a), bf = eid_floorf(b);
+  const float fa = a - af, fb = b - bf;
+  const int x0 = max(0, min(sw - 1, f2i_sat(af))), x1 = max(0, min(sw - 1, f2i_sat(af) + 1));
+  const int y0 = max(0, min(sh - 1, f2i_sat(bf))), y1 = max(0, min(sh - 1, f2i_sat(bf) + 1));
+  const float4 t00 = src[(size_t)y0 * spitch + x0], t10 = src[(size_t)y0 * spitch + x1], t01 = src[(size_t)y1 * spitch + x0], t11 = src[(size_t)y1 * spitch + x1];
+  float4 o;
+  o.x = mixf(mixf(t00.x, t10.x, fa), mixf(t01.x, t11.x, fa), fb); o.y = mixf(mixf(t00.y, t10.y, fa), mixf(t01.y, t11.y, fa), fb);
+  o.z = mixf(mixf(t00.z, t10.z, fa), mixf(t01.z, t11.z, fa), fb); o.w = mixf(mixf(t00.w, t10.w, fa), mixf(t01.w, t11.w, fa), fb);
+  dst[(size_t)j * dw + i] = o;
+}
 DEV f3 pPow3(f3 c, float e) { return mk3(eid_powf(c.x, e), eid_powf(c.y, e), eid_powf(c.z, e)); }
 DEV f3 pUncharted2(f3 c) {
   const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
@@ -1047,7 +1065,8 @@ DEV f3 pToneMap(f3 hdr, float exposure) {
 }
 DEV f3 pClamp01(f3 c) { return mk3(gmin(gmax(c.x, 0.0f), 1.0f), gmin(gmax(c.y, 0.0f), 1.0f), gmin(gmax(c.z, 0.0f), 1.0f)); }
 
-__global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemapper tm, float4* __restrict__ outF, uchar4* __restrict__ out8) {
+__global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemapper tm, float4* __restrict__ outF, uchar4* __restrict__ out8,
+                                              const float4* __restrict__ avg) {   // avg[0] / avg[1]: 1x1 mip level of the direct / indirect image
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   const int W = P.st.size.x, H = P.st.size.y;
   if (x >= W || y >= H) return;
@@ -1069,6 +1088,18 @@ __global__ void __launch_bounds__(256) k_post(const FrameParams P, const Tonemap
     if (mode == eDirectStage) hdr = mk3(d4.x, d4.y, d4.z);
     else if (mode == eIndirectStage) hdr = mk3(i4.x, i4.y, i4.z);
     else hdr = mk3(d4.x, d4.y, d4.z) + mk3(i4.x, i4.y, i4.z);
+    if (tm.autoExposure & 1) {                                                    // post.frag:133-152, toneExposure :65-70
+      const float4 aD = avg[0], aI = avg[1];
+      f3 av;
+      if (mode == eDirectStage) av = mk3(aD.x, aD.y, aD.z);
+      else if (mode == eIndirectStage) av = mk3(aI.x, aI.y, aI.z);
+      else av = mk3(aD.x, aD.y, aD.z) + mk3(aI.x, aI.y, aI.z);
+      const float avgLum2 = dot3(av, mk3(0.2126f, 0.7152f, 0.0722f));
+      const float XYZy = (0.3575761f * hdr.x + 0.7151522f * hdr.y) + 0.1191920f * hdr.z;   // second row of the column-filled RGB2XYZ, as written
+      const float Y = (tm.key / avgLum2) * XYZy;
+      const float Yd = (Y * (1.0f + Y / (tm.Ywhite * tm.Ywhite))) / (1.0f + Y);
+      hdr = (hdr / XYZy) * Yd;
+    }
     // toneMap (TONEMAP_UNCHARTED): exposure, Uncharted 2 with white scale, linear -> sRGB
     const float GAMMA = 2.2f, INV_GAMMA = 1.0f / 2.2f;
     color = pToneMap(hdr, tm.avgLum);
@@ -1195,6 +1226,7 @@ struct eid_renderer {
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
   float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
+  float4* mipScratch = nullptr;                             // auto exposure: two ping-pong mip levels + the two 1x1 averages
   // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
   void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
   cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
@@ -1237,6 +1269,7 @@ void eid_renderer::release() {
   cudaFree(motion); motion = nullptr;
   cudaFree(tempDirectResv); cudaFree(spatialCont); tempDirectResv = nullptr; spatialCont = nullptr;
   cudaFree(displayF); cudaFree(display8); displayF = nullptr; display8 = nullptr;
+  cudaFree(mipScratch); mipScratch = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
@@ -1733,7 +1766,7 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
   EID_TRY
   if (!r || !tm) raise(EID_ERR_INVALID, "eid_renderer_run_output: null argument");
   if (!r->hasRun) raise(EID_ERR_STATE, "eid_renderer_run_output: no frame has been rendered");
-  if (tm->autoExposure & 1) raise(EID_ERR_UNSUPPORTED, "post.frag auto exposure reads the blit-generated mip chain of the result images: not implemented");
+  if (tm->autoExposure & 2) raise(EID_ERR_UNSUPPORTED, "post.frag toneLocalExposure (autoExposure bit 1) is never selected by the reference's GUI and reads an uninitialised variable there: not implemented");
   CUDA_CHECK(cudaSetDevice(r->device));
   const size_t n = (size_t)r->width * r->height;
   if (!r->displayF) {
@@ -1745,7 +1778,26 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
   P.st = r->lastState; P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
   dim3 b(32, 8), g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
-  k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8);
+  if (tm->autoExposure & 1) {   // RenderOutput::genMipmap (render_output.cpp:243-253): the chain of the whole images (m_size = the allocation) down to 1 x 1
+    if (!r->mipScratch) CUDA_CHECK(cudaMalloc(&r->mipScratch, (2 * ((size_t)(r->width / 2 + 1) * (r->height / 2 + 1)) + 2) * 16));
+    const size_t half = (size_t)(r->width / 2 + 1) * (r->height / 2 + 1);
+    float4* pp[2] = {r->mipScratch, r->mipScratch + half};
+    float4* avg = r->mipScratch + 2 * half;
+    for (int img = 0; img < 2; ++img) {
+      const float4* src = img ? r->indirectImg : r->directImg;
+      int sw = (int)r->width, sh = (int)r->height, spitch = (int)r->width, k = 0;
+      if (sw == 1 && sh == 1) CUDA_CHECK(cudaMemcpyAsync(avg + img, src, 16, cudaMemcpyDeviceToDevice, r->stream));
+      while (sw > 1 || sh > 1) {
+        const int dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
+        float4* dst = (dw == 1 && dh == 1) ? avg + img : pp[k & 1];
+        k_mip_blit<<<dim3((dw + 31) / 32, (dh + 7) / 8), b, 0, r->stream>>>(src, sw, sh, spitch, dst, dw, dh);
+        src = dst; sw = dw; sh = dh; spitch = dw; ++k;
+      }
+    }
+    k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8, avg);
+  } else {
+    k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8, nullptr);
+  }
   CUDA_CHECK(cudaGetLastError());
   return EID_OK;
   EID_CATCH

@@ -293,7 +293,10 @@ EID_API int  eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread);
 /* RenderOutput::run (render_output.cpp:224-240) -> shaders/post.frag as a compute pass over the frame rendered last: direct +
  * indirect (or the debug view selected by that frame's RtxState.debugging_mode), Uncharted-2 tonemap, dither, contrast /
  * brightness / saturation / vignette, evaluated 1:1 (one output pixel per rendered pixel, zoom 1, renderingRatio (1,1) unless set
- * in `tm`).  Enqueued on the renderer's stream; results in EID_BUF_DISPLAY_F32 / EID_BUF_DISPLAY_RGBA8.  tm->autoExposure must be 0. */
+ * in `tm`).  Enqueued on the renderer's stream; results in EID_BUF_DISPLAY_F32 / EID_BUF_DISPLAY_RGBA8.
+ * tm->autoExposure bit 0 (the GUI's "Auto Exposure", sample_gui.cpp:238-259): RenderOutput::genMipmap (render_output.cpp:243-253) runs first —
+ * the mip chain of both result images down to 1 x 1 — and post.frag's toneExposure uses that average; bit 1 (toneLocalExposure) is
+ * EID_ERR_UNSUPPORTED. */
 EID_API int  eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm);
 /* Form of indirect_stage (K2).  enabled = 1 (default): wavefront — the stage is cut at its ray queries into ray queues that a
  * persistent dynamic-fetch traversal kernel drains (every lane takes the next queued ray when its own ends); used whenever the

@@ -128,6 +128,9 @@ struct mat3 {
   vec3 c[3];
   mat3() {}
   mat3(vec3 a, vec3 b, vec3 d) { c[0] = a; c[1] = b; c[2] = d; }
+  mat3(float a0, float a1, float a2, float b0, float b1, float b2, float d0, float d1, float d2) {   // GLSL fills column by column
+    c[0] = vec3(a0, a1, a2); c[1] = vec3(b0, b1, b2); c[2] = vec3(d0, d1, d2);
+  }
 };
 inline vec3 operator*(const mat3& m, vec3 v) { return (m.c[0] * v.x + m.c[1] * v.y) + m.c[2] * v.z; }
 // cofactor inverse, fixed evaluation order (contract)

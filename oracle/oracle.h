@@ -154,7 +154,9 @@ int fn(int which, const float* in, int n, float* out);
 int ctx_fn(Renderer& rr, const RtxState& st, int which, const float* in, int n, float* out);   // scene-dependent taps
 vec3 post_toneMap(vec3 color, float exposure);   // tonemapping.glsl:78-95 (oracle_post.cpp)
 // shaders/post.frag main for one pixel (oracle_post.cpp)
-vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height);
+vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height, vec4 avgDirect = vec4(), vec4 avgIndirect = vec4());
+vec4 mip_chain_average(const vec4* img, int width, int height, int pitch);   // 1x1 level of RenderOutput::genMipmap's chain (oracle_post.cpp)
+vec3 post_toneExposure(const Tonemapper& tm, vec3 RGB, float logAvgLum);      // post.frag:65-70
 // shaders/sun_and_sky.glsl:453-601 (oracle_sunsky.cpp)
 vec3 sun_and_sky(const SunAndSky& ss, vec3 in_direction);
 

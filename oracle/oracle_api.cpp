@@ -192,14 +192,27 @@ ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; retu
 // RenderOutput::run over the frame rendered last: out = width*height RGBA32F at the allocation pitch
 ORC_API int orc_renderer_run_output(Renderer* r, const Tonemapper* tm, const RtxState* st, float* out) {
   const int W = st->size.x, H = st->size.y;
+  vec4 avgD, avgI;
+  if (tm->autoExposure & 1) {   // genMipmap runs over the whole images (m_size = the allocation), render_output.cpp:243-253
+    avgD = mip_chain_average(r->directResult.data(), (int)r->width, (int)r->height, (int)r->width);
+    avgI = mip_chain_average(r->indirectResult.data(), (int)r->width, (int)r->height, (int)r->width);
+  }
 #pragma omp parallel for schedule(static)
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
       const size_t pix = (size_t)y * r->width + x;
-      const vec4 c = post_frag(*tm, st->debugging_mode, r->directResult[pix], r->indirectResult[pix], x, y, W, H);
+      const vec4 c = post_frag(*tm, st->debugging_mode, r->directResult[pix], r->indirectResult[pix], x, y, W, H, avgD, avgI);
       out[4 * pix] = c.x; out[4 * pix + 1] = c.y; out[4 * pix + 2] = c.z; out[4 * pix + 3] = c.w;
     }
   return 0;
+}
+// known-answer taps of the auto-exposure path: the 1x1 mip level of an RGBA32F image, and toneExposure (post.frag:65-70) per item
+ORC_API void orc_mip_chain_average(const float* rgba, int w, int h, float* out4) {
+  const vec4 a = mip_chain_average(reinterpret_cast<const vec4*>(rgba), w, h, w);
+  out4[0] = a.x; out4[1] = a.y; out4[2] = a.z; out4[3] = a.w;
+}
+ORC_API void orc_tone_exposure(const Tonemapper* tm, const float* rgbAndLum, int n, float* out) {
+  for (int i = 0; i < n; ++i) { const vec3 c = post_toneExposure(*tm, vec3(rgbAndLum[4 * i], rgbAndLum[4 * i + 1], rgbAndLum[4 * i + 2]), rgbAndLum[4 * i + 3]); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
 ORC_API int orc_renderer_set_sun_and_sky(Renderer* r, const SunAndSky* ss) { r->sunSky = *ss; return 0; }
 ORC_API void orc_sun_and_sky(const SunAndSky* ss, const float* dirs, int n, float* out) {   // known-answer tap

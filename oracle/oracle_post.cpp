@@ -5,10 +5,14 @@
  * src/render_output.cpp:224-240) with shaders/tonemapping.glsl and pcg3d of shaders/random.glsl:81-92, evaluated once per
  * rendered pixel: uvCoords = (pixel + 0.5) / size, tm.zoom = 1, tm.renderingRatio = (1, 1) — the 1:1 presentation.  The
  * reference's sampler is NEAREST / REPEAT (zero-initialised VkSamplerCreateInfo, render_output.cpp:123-128), so
- * texture(img, uvCoords) is texel (x, y).  autoExposure (needs the blit-generated mip chain) is outside the contract.
- * Numerics: DESIGN.md §3 (fp32, one rounding per operation, pow from eid_detmath.h).  Parity: toneMap is pinned to tonemapping.glsl compiled as C++ (oracle/ref_shim);
- * the rest of post.frag (a fragment shader with samplers) is unpinned.
+ * texture(img, uvCoords) is texel (x, y).  autoExposure bit 0 (the GUI's check box, sample_gui.cpp:238-259): the average colour is the
+ * 1x1 level of the mip chain RenderOutput::genMipmap blits from the result images (mip_chain_average below); bit 1 (toneLocalExposure —
+ * never set by the reference's GUI, reads an uninitialised variable in the default view) is outside the contract.
+ * Numerics: DESIGN.md §3 (fp32, one rounding per operation, pow from eid_detmath.h).  Parity: pinned to post.frag itself — main() and
+ * every function it calls, transliterated and compiled as C++ (oracle/ref_shim/ref_display.cpp) — bit for bit in every view and with auto
+ * exposure (tests/golden/ref_display.npz); what stays contract is the driver's part: the blit chain behind textureLod(img, vec2(0.5), 20).
  */
+#include <vector>
 #include "oracle.h"
 
 namespace orc {
@@ -58,8 +62,51 @@ static void pcg3d(uint& x, uint& y, uint& z) {
   x += y * z; y += z * x; z += x * y;
 }
 
-// post.frag main :107-178 for one pixel; direct / indirect = RGBA of texel (px, py)
-vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height) {
+// RenderOutput::genMipmap (render_output.cpp:243-253) -> nvvk::cmdGenerateMipmaps (nvpro_core, un-vendored): level i is blitted from level
+// i-1 with VK_FILTER_LINEAR, extent max(1, previous / 2) per axis, floor(log2(max(w, h))) + 1 levels, i.e. down to 1 x 1.  A blit with
+// a linear filter (Vulkan spec, "Image Blits"): destination texel (i, j) samples the source at u = (i + 0.5) * (srcW / dstW), v likewise,
+// bilinear between the texels around (u - 0.5, v - 0.5), clamped to the edge.  Contract: fp32, full-float weights,
+// mix(mix(t00, t10, a), mix(t01, t11, a), b).  Returns the single texel of the last level = what textureLod(img, vec2(0.5), 20) reads.
+vec4 mip_chain_average(const vec4* img, int width, int height, int pitch) {
+  std::vector<vec4> src((size_t)width * height), dst;
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) src[(size_t)y * width + x] = img[(size_t)y * pitch + x];
+  int sw = width, sh = height;
+  auto mix4 = [](vec4 a, vec4 b, float t) { return vec4(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t), mix(a.w, b.w, t)); };
+  while (sw > 1 || sh > 1) {
+    const int dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
+    const float scaleU = float(sw) / float(dw), scaleV = float(sh) / float(dh);
+    dst.assign((size_t)dw * dh, vec4());
+    for (int j = 0; j < dh; ++j)
+      for (int i = 0; i < dw; ++i) {
+        const float a = (float(i) + 0.5f) * scaleU - 0.5f, b = (float(j) + 0.5f) * scaleV - 0.5f;
+        const float af = eid_floorf(a), bf = eid_floorf(b);
+        const float fa = a - af, fb = b - bf;
+        const int x0 = imax(0, imin(sw - 1, f2i(af))), x1 = imax(0, imin(sw - 1, f2i(af) + 1));
+        const int y0 = imax(0, imin(sh - 1, f2i(bf))), y1 = imax(0, imin(sh - 1, f2i(bf) + 1));
+        dst[(size_t)j * dw + i] = mix4(mix4(src[(size_t)y0 * sw + x0], src[(size_t)y0 * sw + x1], fa),
+                                       mix4(src[(size_t)y1 * sw + x0], src[(size_t)y1 * sw + x1], fa), fb);
+      }
+    src.swap(dst); sw = dw; sh = dh;
+  }
+  return src[0];
+}
+
+// post.frag:60-62, 65-70
+static float luminancePost(vec3 color) { return dot(color, vec3(0.2126f, 0.7152f, 0.0722f)); }
+static vec3 toneExposure(const Tonemapper& tm, vec3 RGB, float logAvgLum) {
+  // RGB2XYZ = mat3(0.4124564, 0.3575761, 0.1804375, 0.2126729, ...) is filled column by column, so XYZ.y = dot of the SECOND ROW of
+  // that storage = (0.3575761, 0.7151522, 0.1191920) with RGB: kept as written
+  const float XYZy = (0.3575761f * RGB.x + 0.7151522f * RGB.y) + 0.1191920f * RGB.z;
+  const float Y = (tm.key / logAvgLum) * XYZy;
+  const float Yd = (Y * (1.0f + Y / (tm.Ywhite * tm.Ywhite))) / (1.0f + Y);
+  return RGB / XYZy * Yd;
+}
+vec3 post_toneExposure(const Tonemapper& tm, vec3 RGB, float logAvgLum) { return toneExposure(tm, RGB, logAvgLum); }
+
+// post.frag main :107-178 for one pixel; direct / indirect = RGBA of texel (px, py); avgDirect / avgIndirect = the 1x1 mip level of the
+// two result images (only read when tm.autoExposure bit 0 is set)
+vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indirect, int px, int py, int width, int height, vec4 avgDirect, vec4 avgIndirect) {
   const vec2 uvCoords((float(px) + 0.5f) / float(width), (float(py) + 0.5f) / float(height));
   if (debugging_mode == eDepth) {
     float depth = direct.w;
@@ -77,6 +124,15 @@ vec4 post_frag(const Tonemapper& tm, int debugging_mode, vec4 direct, vec4 indir
   else if (debugging_mode == eIndirectStage) hdr = indirect;
   else hdr = vec4(direct.x + indirect.x, direct.y + indirect.y, direct.z + indirect.z, direct.w + indirect.w);
   hdr.w = 1.0f;
+  if (((tm.autoExposure >> 0) & 1) == 1) {              // :133-152
+    vec4 avg;
+    if (debugging_mode == eDirectStage) avg = avgDirect;
+    else if (debugging_mode == eIndirectStage) avg = avgIndirect;
+    else avg = vec4(avgDirect.x + avgIndirect.x, avgDirect.y + avgIndirect.y, avgDirect.z + avgIndirect.z, avgDirect.w + avgIndirect.w);
+    const float avgLum2 = luminancePost(avg.xyz());
+    const vec3 e = toneExposure(tm, hdr.xyz(), avgLum2);
+    hdr = vec4(e, 1.0f);
+  }
 
   vec3 color = toneMap(hdr.xyz(), tm.avgLum);          // tonemap + linear to sRGB
 

@@ -13,6 +13,8 @@ source is stored in the repository).  The transliteration never touches an expre
   * a vector constructor whose arguments are all rand() calls, `vec3(rand(s), rand(s), rand(s))`, becomes a brace initialiser
     `vec3{rand(s), rand(s), rand(s)}`: GLSL evaluates constructor arguments left to right, C++ only guarantees that order inside braces
     (GCC evaluates parenthesised arguments right to left), and the RNG draw order is part of the result
+  * (--swizzle-assign, post.frag only) a statement that assigns to the first three components of a vec4, `v.rgb = e;` / `v.xyz = e;`,
+    becomes `v = vec4(e, v.w);`, and the identity swizzle `.rgba` is dropped
   * `#include`, `precision`, `#extension`, `#version` lines and a stage's interface declarations (`layout(push_constant) uniform ...`,
     `layout(local_size_x ...) in;`) are dropped; optionally only the named top-level functions are kept
 
@@ -58,7 +60,13 @@ def top_level_chunks(src):
     return out
 
 
+SWIZZLE_ASSIGN = False
+
+
 def transliterate(text):
+    if SWIZZLE_ASSIGN:
+        text = re.sub(r"\b(\w+)\.(?:rgb|xyz)\s*=(?!=)\s*([^;]+);", r"\1 = vec4(\2, \1.w);", text)
+        text = re.sub(r"\.rgba\b(?!\s*\()", "", text)
     text = re.sub(r"\b(?:inout|out)\s+(" + TYPES + r")\s+(\w+)", r"\1& \2", text)
     text = re.sub(r"\bin\s+(" + TYPES + r")\s+(\w+)", r"\1 \2", text)
     text = FLOAT_LIT.sub(lambda m: m.group(1) + "f", text)
@@ -81,6 +89,11 @@ def main():
             drop = set(args[1].split(","))
         elif args[0] == "--strip":
             strip = args[1]
+        elif args[0] == "--swizzle-assign":
+            global SWIZZLE_ASSIGN
+            SWIZZLE_ASSIGN = True
+            args = args[1:]
+            continue
         args = args[2:]
     src = strip_comments(open(src_path).read())
     lines = [l for l in src.split("\n") if not re.match(r"\s*#\s*(include|extension|version)\b", l) and not re.match(r"\s*precision\s", l)]

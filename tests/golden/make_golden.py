@@ -181,7 +181,30 @@ def ref_trace_vectors():
     print("wrote ref_trace.npz")
 
 
+def ref_display_vectors():
+    """tests/golden/ref_display.npz: what the reference's post.frag (main() included, compiled as C++ by oracle/ref_shim/ref_display.cpp)
+    makes of the oracle's result images for every tests/ref_fn_inputs.DISPLAY_CONFIGS entry, plus the two 1x1 mip texels it was handed."""
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    R = ol.ref()
+    if R is None:
+        print("oracle/_ref/libref.so unavailable: keeping the committed ref_display.npz")
+        return
+    out, frames = {}, {}
+    for tag, mode, over in fi.DISPLAY_CONFIGS:
+        if mode not in frames:
+            orr, st, osc = ol.display_frames(scenes, abi, common, mode)
+            w, h = fi.DISPLAY_SIZE
+            frames[mode] = (orr.read(abi.BUF_DIRECT).reshape(h, w, 4).copy(), orr.read(abi.BUF_INDIRECT).reshape(h, w, 4).copy())
+        d, i = frames[mode]
+        out["%s_out" % tag] = ol.ref_display_run(R, abi.default_tonemapper(**over), mode, d, i)
+        out["%s_mips" % tag] = np.stack([ol.mip_chain_average(d), ol.mip_chain_average(i)])
+    np.savez_compressed(os.path.join(HERE, "ref_display.npz"), **out)
+    print("wrote ref_display.npz")
+
+
 if __name__ == "__main__":
+    ref_display_vectors()
     ref_vectors()
     ref_post_vectors()
     ref_trace_vectors()

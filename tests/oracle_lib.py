@@ -61,6 +61,7 @@ def lib():
             "orc_renderer_get_stats": (i32, [vp, C.POINTER(abi.FrameStats)]),
             "orc_renderer_buffer_bytes": (C.c_int64, [vp, i32]), "orc_renderer_read": (i32, [vp, i32, vp, sz]),
             "orc_renderer_write": (i32, [vp, i32, vp, sz]),
+            "orc_mip_chain_average": (None, [vp, i32, i32, vp]), "orc_tone_exposure": (None, [vp, vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -88,6 +89,7 @@ def ref():
         L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_trace_run.restype, L.ref_trace_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_post_run.restype, L.ref_post_run.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.ref_display_run.restype, L.ref_display_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.ref_scene_set.restype, L.ref_scene_set.argtypes = None, [C.c_void_p] * 10 + [C.c_uint32, C.c_uint32]
         L.ref_ctx_fn.restype, L.ref_ctx_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref = L
@@ -230,6 +232,43 @@ def ref_post_run(R, abi, camera_table, state, size, pre):
     cam = np.ascontiguousarray(camera_table)
     R.ref_post_run(C.addressof(state), cam.ctypes.data, size[0], size[1], *[bufs[k].ctypes.data for k in POST_BUFS])
     return bufs
+
+
+def mip_chain_average(img):
+    """1x1 level of the mip chain RenderOutput::genMipmap blits from an (h, w, 4) float32 image (the contract's linear blits)."""
+    a = np.ascontiguousarray(img, np.float32)
+    out = np.zeros(4, np.float32)
+    lib().orc_mip_chain_average(a.ctypes.data, a.shape[1], a.shape[0], out.ctypes.data)
+    return out
+
+
+def ref_display_run(R, tm, mode, direct, indirect):
+    """The reference's post.frag (main() included, oracle/ref_shim/ref_display.cpp) over (h, w, 4) float32 images -> (h, w, 4) float32.  The
+    1x1 mip level textureLod(img, vec2(0.5), 20) reads is the driver's blit chain: it is handed in (the contract's value)."""
+    d, i = np.ascontiguousarray(direct, np.float32), np.ascontiguousarray(indirect, np.float32)
+    h, w = d.shape[:2]
+    md, mi = mip_chain_average(d), mip_chain_average(i)
+    out = np.zeros((h, w, 4), np.float32)
+    R.ref_display_run(C.byref(tm), int(mode), w, h, d.ctypes.data, i.ctypes.data, md.ctypes.data, mi.ctypes.data, out.ctypes.data)
+    return out
+
+
+def display_frames(scenes, abi, common, mode):
+    """Oracle renderer after DISPLAY_FRAMES frames of the display-pass scene in debug view `mode` -> (renderer, last RtxState, scene)."""
+    import ref_fn_inputs as fi
+    size = fi.DISPLAY_SIZE
+    osc = OracleScene()
+    osc.load_arrays(getattr(scenes, fi.DISPLAY_SCENE)())
+    orr = OracleRenderer(osc, size)
+    orr.set_env_constant(common.ENV)
+    osc.update_camera(*size)
+    info = osc.info()
+    st = None
+    for f in range(fi.DISPLAY_FRAMES):
+        osc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, maxDepth=3, debugging_mode=mode)
+        orr.run(st, f)
+    return orr, st, osc
 
 
 def _f3(v):

@@ -139,6 +139,16 @@ TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth
                  ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3)),
                  ("spatial", "cornell_scene", (64, 40), 2, "none", dict(ReSTIRState=2, maxDepth=2)),            # eSpatial (race-free reading)
                  ("spatiotemporal", "small_room", (50, 34), 3, "none", dict(ReSTIRState=4, maxDepth=2))]      # eSpatiotemporal
+# display pass (post.frag): (tag, debugging_mode, Tonemapper overrides); rendered on DISPLAY_SCENE at DISPLAY_SIZE, DISPLAY_FRAMES frames
+DISPLAY_SCENE, DISPLAY_SIZE, DISPLAY_FRAMES = "cornell_scene", (72, 44), 2
+DISPLAY_CONFIGS = [("default", 0, dict()),
+                   ("graded", 0, dict(brightness=1.3, contrast=0.8, saturation=0.6, vignette=0.4, avgLum=2.5)),
+                   ("auto", 0, dict(autoExposure=1)),
+                   ("auto_graded", 0, dict(autoExposure=1, Ywhite=0.8, key=0.3, contrast=1.2, vignette=0.2)),
+                   ("direct", 1, dict()), ("direct_auto", 1, dict(autoExposure=1, key=0.7)),
+                   ("indirect", 2, dict(avgLum=1.7)), ("indirect_auto", 2, dict(autoExposure=1)),
+                   ("basecolor", 3, dict()), ("normal", 4, dict()),
+                   ("depth", 5, dict(brightness=0.0, contrast=2.2, saturation=0.0))]       # RenderOutput::m_depthTm (render_output.hpp:56-60)
 TRACE_KEYS = ("gbuffer", "motion", "direct_resv", "indirect_resv", "direct", "ind_tmp_a")
 
 

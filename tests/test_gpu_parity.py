@@ -232,7 +232,8 @@ def test_display_pass_post_frag(mode):
             s_.update_camera(*size)
         st = common.frame_state(size[0], size[1], info, f, maxDepth=3, debugging_mode=mode)
         orr.run(st, f); prr.run(st, f)
-    for tm in (abi.default_tonemapper(), abi.default_tonemapper(brightness=1.3, contrast=0.8, saturation=0.6, vignette=0.4, avgLum=2.5)):
+    for tm in (abi.default_tonemapper(), abi.default_tonemapper(brightness=1.3, contrast=0.8, saturation=0.6, vignette=0.4, avgLum=2.5),
+               abi.default_tonemapper(autoExposure=1), abi.default_tonemapper(autoExposure=1, Ywhite=0.9, key=0.25, vignette=0.3)):   # auto exposure: 1x1 level of the blit chain
         if mode == abi.eDepth:
             tm = abi.default_tonemapper(brightness=0.0, contrast=2.2, saturation=0.0)     # RenderOutput::m_depthTm (render_output.hpp:56-60)
         want = orr.run_output(tm, st)
@@ -245,7 +246,31 @@ def test_display_pass_post_frag(mode):
         want8 = np.floor(c * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
         assert np.array_equal(got8, want8)
     with pytest.raises(eid.EidolaError):
-        prr.run_output(abi.default_tonemapper(autoExposure=1))
+        prr.run_output(abi.default_tonemapper(autoExposure=3))      # toneLocalExposure: never selected by the reference's GUI, outside the contract
+
+
+def test_cuda_display_pass_matches_reference_post_frag():
+    """k_mip_blit + k_post against the committed output of the reference's OWN post.frag (main() included, compiled as C++ by
+    oracle/ref_shim/ref_display.cpp; tests/golden/ref_display.npz): every view and tonemapper of DISPLAY_CONFIGS, auto exposure included."""
+    import ref_fn_inputs as fi
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_display.npz"))
+    size = fi.DISPLAY_SIZE
+    rendered = {}
+    for tag, mode, over in fi.DISPLAY_CONFIGS:
+        if mode not in rendered:
+            psc = eid.Scene(0); psc.load_arrays(getattr(scenes, fi.DISPLAY_SCENE)())
+            acc = eid.AccelStructure(); acc.create(psc)
+            prr = eid.Renderer(); prr.create(size, psc, acc); prr.set_env_constant(common.ENV); prr.set_strict_math(True)
+            psc.update_camera(*size)
+            info = psc.info()
+            for f in range(fi.DISPLAY_FRAMES):
+                psc.update_camera(*size)
+                prr.run(common.frame_state(size[0], size[1], info, f, maxDepth=3, debugging_mode=mode), f)
+            rendered[mode] = (psc, acc, prr)
+        prr = rendered[mode][2]
+        prr.run_output(abi.default_tonemapper(**over)); prr.sync()
+        got = prr.read(abi.BUF_DISPLAY_F32).reshape(size[1], size[0], 4)
+        assert got.view(np.uint32).tobytes() == z["%s_out" % tag].view(np.uint32).tobytes(), tag
 
 
 def test_device_functions_match_reference_glsl_vectors():

@@ -200,6 +200,49 @@ def test_trace_stages_match_reference_shader_mains():
         assert [s.closestHitRays, s.anyHitRays] == [int(v) for v in z["%s_rays" % tag]], tag
 
 
+def test_oracle_display_pass_matches_reference_post_frag():
+    """The oracle's restatement of RenderOutput::run / post.frag against the committed output of the reference's OWN post.frag (main()
+    included, compiled as C++ by oracle/ref_shim/ref_display.cpp): every view and tonemapper of DISPLAY_CONFIGS, auto exposure included,
+    bit for bit.  Committed outputs: tests/golden/ref_display.npz; re-run live where /root/reference exists."""
+    import common
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_display.npz"))
+    R = ol.ref() if os.path.isdir("/root/reference") else None
+    frames = {}
+    for tag, mode, over in fi.DISPLAY_CONFIGS:
+        if mode not in frames:
+            frames[mode] = ol.display_frames(scenes, abi, common, mode)
+        orr, st, osc = frames[mode]
+        tm = abi.default_tonemapper(**over)
+        got = orr.run_output(tm, st)
+        assert got.view(np.uint32).tobytes() == z["%s_out" % tag].view(np.uint32).tobytes(), tag
+        w, h = fi.DISPLAY_SIZE
+        d, i = orr.read(abi.BUF_DIRECT).reshape(h, w, 4), orr.read(abi.BUF_INDIRECT).reshape(h, w, 4)
+        assert np.stack([ol.mip_chain_average(d), ol.mip_chain_average(i)]).tobytes() == z["%s_mips" % tag].tobytes(), tag
+        if R is not None:
+            assert ol.ref_display_run(R, tm, mode, d, i).view(np.uint32).tobytes() == z["%s_out" % tag].view(np.uint32).tobytes(), tag
+    assert not np.array_equal(z["auto_out"], z["default_out"])
+
+
+def test_mip_chain_average_known_answers():
+    """The contract's restatement of nvvk::cmdGenerateMipmaps (linear blits down to 1x1): exact halvings are box filters, an odd extent
+    samples between its texels at (i + 0.5) * src / dst - 0.5, a 1-wide axis is kept."""
+    rng = np.random.default_rng(11)
+    c = np.tile(np.array([0.25, 1.5, 3.0, 1.0], np.float32), (16, 32, 1))
+    assert ol.mip_chain_average(c).tolist() == [0.25, 1.5, 3.0, 1.0]
+    a = rng.random((2, 2, 4)).astype(np.float32)
+    top, bot = a[0, 0] * np.float32(0.5) + a[0, 1] * np.float32(0.5), a[1, 0] * np.float32(0.5) + a[1, 1] * np.float32(0.5)
+    assert ol.mip_chain_average(a).tobytes() == (top * np.float32(0.5) + bot * np.float32(0.5)).astype(np.float32).tobytes()
+    a = rng.random((1, 3, 4)).astype(np.float32)          # 3 -> 1: u = 0.5 * 3 - 0.5 = 1.0, the middle texel
+    assert ol.mip_chain_average(a).tobytes() == a[0, 1].tobytes()
+    a = rng.random((8, 8, 4)).astype(np.float32)          # power of two: the plain mean up to rounding
+    assert np.allclose(ol.mip_chain_average(a), a.reshape(-1, 4).mean(axis=0), rtol=1e-6)
+    a = rng.random((5, 7, 4)).astype(np.float32)
+    m = ol.mip_chain_average(a)
+    assert (m >= a.reshape(-1, 4).min(axis=0)).all() and (m <= a.reshape(-1, 4).max(axis=0)).all()
+
+
 def test_environment_alias_map_matches_reference_vectors():
     """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
     lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
