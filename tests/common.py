@@ -29,6 +29,14 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
 
 
+def same_bits_or_both_nan(a, b):
+    """Bit-identical floats, where a NaN only has to meet a NaN: the payload / sign of an invalid operation's NaN (0/0 in post.frag's
+    toneExposure on a black pixel) is the processor's choice — 0xFFC00000 on x86, 0x7FFFFFFF on the GPU."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
 def rel_err(a, b, floor=1e-6):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)

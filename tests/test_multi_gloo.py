@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 W, H = 96, 72            # 72 rows / 2 ranks = 36 -> bands of 48 rows, padded allocation 96 rows
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, restir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import eidola_b200 as eid
@@ -35,8 +35,8 @@ def _worker(rank, world, port, out):
     info = osc.info()
     for f in range(2):
         osc.update_camera(W, H)
-        st = common.frame_state(W, H, info, f, maxDepth=2)
-        orr.run_trace(st, f, y0, min(y1, H))
+        st = common.frame_state(W, H, info, f, maxDepth=2, ReSTIRState=restir)
+        orr.run_trace(st, f, y0, min(y1, H))     # spatial reuse: the band's direct stage also primes one halo row on each side
         # the exchange step: pre-denoise buffers, full-res rows for G-buffer / direct, half-res rows for the indirect temp
         for which in (abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A):
             buf = orr.read(which).view(np.uint8).copy()
@@ -68,13 +68,14 @@ def test_band_partition_properties():
     assert sharding.band_rows(1080, 8) == 144 and sharding.padded_height(1080, 8) == 1152
 
 
-def test_two_rank_gloo_band_exchange_matches_single_process(tmp_path):
+@pytest.mark.parametrize("restir", [3, 4])      # eTemporal (default), eSpatiotemporal (neighbour reads cross the band edge)
+def test_two_rank_gloo_band_exchange_matches_single_process(tmp_path, restir):
     import socket
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), restir), nprocs=2, join=True)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from eidola_b200 import abi, scenes, sharding
     import common
@@ -88,7 +89,7 @@ def test_two_rank_gloo_band_exchange_matches_single_process(tmp_path):
     info = osc.info()
     for f in range(2):
         osc.update_camera(W, H)
-        orr.run(common.frame_state(W, H, info, f, maxDepth=2), f)
+        orr.run(common.frame_state(W, H, info, f, maxDepth=2, ReSTIRState=restir), f)
     want = {k: orr.read(w).view(np.uint8) for k, w in (("direct", abi.BUF_DIRECT), ("indirect", abi.BUF_INDIRECT), ("gbuffer", abi.BUF_THIS_GBUFFER))}
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
