@@ -578,8 +578,6 @@ def test_band_sharded_trace_equals_full_frame(restir):
         full.run(st, f)
         a.run_trace(st, f)
         b.run_trace(st, f)
-        assert (a.stats().closestHitRays + b.stats().closestHitRays, a.stats().anyHitRays + b.stats().anyHitRays) == (
-            full.stats().closestHitRays, full.stats().anyHitRays)          # halo rows are not counted twice
         for which in exchange:
             ba, bb = a.read(which).view(np.uint8).copy(), b.read(which).view(np.uint8)
             _, off, n = b.band_range(which)
@@ -588,6 +586,8 @@ def test_band_sharded_trace_equals_full_frame(restir):
             b.write(which, ba)
         a.run_post(st, f)
         b.run_post(st, f)
+        assert (a.stats().closestHitRays + b.stats().closestHitRays, a.stats().anyHitRays + b.stats().anyHitRays) == (
+            full.stats().closestHitRays, full.stats().anyHitRays)          # (counters reach the host at the end of a frame) halo rows are not counted twice
         ref = common.snapshot(full)
         for r in (a, b):
             got = common.snapshot(r)
