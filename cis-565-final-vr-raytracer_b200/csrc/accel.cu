@@ -322,6 +322,49 @@ __global__ void k_collapse4(int nIn, const int2* __restrict__ in, int2* __restri
   o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+#if EID_NODE_Q8
+// 128-byte wide node -> 64-byte node with 8-bit child planes (accel.h).  origin = lower corner of the union of the node's child boxes,
+// scale = extent / 255 nudged up until origin + 255 * scale reaches the upper corner; a lower plane is rounded down and an upper plane up,
+// each checked against the value the traversal decodes (fmaf(q, scale, origin)), so the decoded box always contains the exact (padded) one.
+__global__ void k_quantize4(uint32_t n, const float4* __restrict__ wide, uint4* __restrict__ q) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4* w = wide + 8 * (size_t)i;
+  float lo[3][4], hi[3][4];
+  for (int a = 0; a < 3; ++a) {
+    const float4 l = w[a], h = w[3 + a];
+    lo[a][0] = l.x; lo[a][1] = l.y; lo[a][2] = l.z; lo[a][3] = l.w; hi[a][0] = h.x; hi[a][1] = h.y; hi[a][2] = h.z; hi[a][3] = h.w;
+  }
+  const float4 rf = w[6];
+  const int ref[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+  float org[3], scl[3]; uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+  for (int a = 0; a < 3; ++a) {
+    float mn = 3e38f, mx = -3e38f;
+    for (int c = 0; c < 4; ++c) if (ref[c] != ~0) { mn = fminf(mn, lo[a][c]); mx = fmaxf(mx, hi[a][c]); }
+    if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }
+    float sc = (mx - mn) / 255.0f;
+    if (!(sc > 0.0f)) sc = 1e-30f;
+    while (fmaf(255.0f, sc, mn) < mx) sc = __int_as_float(__float_as_int(sc) + 1);
+    org[a] = mn; scl[a] = sc;
+    for (int c = 0; c < 4; ++c) {
+      int l = 255, h = 0;                                          // empty slot: inverted box (the traversal also tests the reference)
+      if (ref[c] != ~0) {
+        l = (int)floorf((lo[a][c] - mn) / sc); l = max(0, min(255, l));
+        while (l > 0 && fmaf((float)l, sc, mn) > lo[a][c]) --l;
+        h = (int)ceilf((hi[a][c] - mn) / sc); h = max(0, min(255, h));
+        while (h < 255 && fmaf((float)h, sc, mn) < hi[a][c]) ++h;
+      }
+      qlo[a] |= (uint32_t)l << (8 * c); qhi[a] |= (uint32_t)h << (8 * c);
+    }
+  }
+  uint4* o = q + 4 * (size_t)i;
+  o[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]), __float_as_uint(scl[0]));
+  o[1] = make_uint4(__float_as_uint(scl[1]), __float_as_uint(scl[2]), qlo[0], qlo[1]);
+  o[2] = make_uint4(qlo[2], qhi[0], qhi[1], qhi[2]);
+  o[3] = make_uint4((uint32_t)ref[0], (uint32_t)ref[1], (uint32_t)ref[2], (uint32_t)ref[3]);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // batch ray query (parity tap for ClosestHit / AnyHit)
 // ------------------------------------------------------------------------------------------------
@@ -416,7 +459,7 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
       // level-by-level collapse into 4-wide nodes; queues hold (binary node, wide node index)
       float4* wideTmp = nullptr; int2 *q0 = nullptr, *q1 = nullptr; unsigned int* counters = nullptr;
       try {
-        CUDA_CHECK(cudaMalloc(&wideTmp, (size_t)nInner * EID_NODE_BYTES));
+        CUDA_CHECK(cudaMalloc(&wideTmp, (size_t)nInner * 128));
         CUDA_CHECK(cudaMalloc(&q0, (size_t)nInner * 8)); CUDA_CHECK(cudaMalloc(&q1, (size_t)nInner * 8));
         CUDA_CHECK(cudaMalloc(&counters, 8));
         const int2 rootItem = make_int2(0, 0);
@@ -434,7 +477,11 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
         unsigned int wideCount = 0;
         CUDA_CHECK(cudaMemcpy(&wideCount, counters + 1, 4, cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)wideCount * EID_NODE_BYTES));      // trim to the live node count
+#if EID_NODE_Q8
+        k_quantize4<<<(wideCount + 127) / 128, 128>>>(wideCount, wideTmp, (uint4*)a->nodes);
+#else
         CUDA_CHECK(cudaMemcpy(a->nodes, wideTmp, (size_t)wideCount * EID_NODE_BYTES, cudaMemcpyDeviceToDevice));
+#endif
         a->rootRef = 0; a->nodeCount = wideCount; a->maxDepth = levels; a->nodeAlloc = wideCount;
         if (3 * levels + 1 >= EID_STACK_SIZE) raise(EID_ERR_UNSUPPORTED, "wide BVH depth %u exceeds the traversal stack (%d)", levels, EID_STACK_SIZE);
       } catch (...) { cudaFree(wideTmp); cudaFree(q0); cudaFree(q1); cudaFree(counters); throw; }
@@ -454,16 +501,16 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
 #if EID_FETCH_TEX
   int maxLinear = 0;
   CUDA_CHECK(cudaDeviceGetAttribute(&maxLinear, cudaDevAttrMaxTexture1DLinearWidth, s->dev.device));
-  auto mkTex = [&](const float4* p, size_t count) {
+  auto mkTex = [&](const float4* p, size_t count, bool asUint = false) {
     if (count > (size_t)maxLinear) raise(EID_ERR_UNSUPPORTED, "eid_accel_build: BVH array of %zu float4 exceeds the linear-texture limit (%d)", count, maxLinear);
     cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = (void*)p;
-    rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = std::max<size_t>(count, 1) * 16;
+    rd.res.linear.desc = asUint ? cudaCreateChannelDesc<uint4>() : cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = std::max<size_t>(count, 1) * 16;
     cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
     cudaTextureObject_t t = 0;
     CUDA_CHECK(cudaCreateTextureObject(&t, &rd, &td, nullptr));
     return t;
   };
-  a->nodeTex = mkTex(a->nodes, (size_t)std::max(a->nodeAlloc, 1u) * (EID_NODE_BYTES / 16));
+  a->nodeTex = mkTex(a->nodes, (size_t)std::max(a->nodeAlloc, 1u) * (EID_NODE_BYTES / 16), EID_NODE_Q8 != 0);
   a->triTex = mkTex(a->tris, (size_t)std::max(nTri, 1u) * 3);
 #endif
 }

@@ -7,7 +7,11 @@
 #ifndef EID_BVH_WIDTH
 #define EID_BVH_WIDTH 4
 #endif
-#define EID_NODE_BYTES (EID_BVH_WIDTH == 4 ? 128 : 64)
+// EID_NODE_Q8 = 1 (BVH4 only): 64-byte node with the child boxes quantised to 8 bits per plane inside the node's own box
+#ifndef EID_NODE_Q8
+#define EID_NODE_Q8 0
+#endif
+#define EID_NODE_BYTES ((EID_BVH_WIDTH == 4 && !EID_NODE_Q8) ? 128 : 64)
 
 namespace eid {
 
@@ -28,6 +32,8 @@ struct DeviceSceneView {
 };
 
 // EID_BVH_WIDTH == 4 (default): 128 B node = 8 x float4: lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4], child refs[4], -
+// EID_NODE_Q8: 64 B = 4 x uint4: (origin.xyz, scale.x) (scale.y, scale.z, lo.x[4 x u8], lo.y[4 x u8]) (lo.z, hi.x, hi.y, hi.z [4 x u8 each])
+//   (child refs[4]); plane = origin + q * scale, lo rounded down / hi rounded up so the decoded box contains the exact one
 // EID_BVH_WIDTH == 2: BVH2 node, 64 B = 4 x float4:
 //   q0 = lo0.xyz, hi0.x   q1 = hi0.yz, lo1.xy   q2 = lo1.z, hi1.xyz   q3 = child0, child1, -, -  (as int bits)
 // child >= 0: inner node index; child < 0: leaf, ~child = (firstTriangle << 3) | count  (count 0..4)

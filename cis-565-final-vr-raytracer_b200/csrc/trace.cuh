@@ -99,6 +99,12 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 
+#ifndef EID_Q8_TEX
+#define EID_Q8_TEX 0
+#endif
+#ifndef EID_Q8_MAGIC
+#define EID_Q8_MAGIC 0
+#endif
 #ifndef EID_FETCH_TEX
 #define EID_FETCH_TEX 2     // 0: every BVH fetch is an LDG; 2: far planes of a node come through tex1Dfetch (default); 1/3/4: experiments
 #endif
@@ -137,6 +143,38 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
   else if (h1) cur = c1;
   else cur = EID_POP();
 #else
+#if EID_NODE_Q8
+  // 64-byte node, child planes quantised to 8 bits (accel.h): 4 loads per visit instead of 7; plane distance t = q * (scale / d) +
+  // (origin - o) / d, near / far byte planes selected by the ray's direction signs.  EID_Q8_TEX: the second half through the TEX pipe.
+  const uint4* n = (const uint4*)A.nodes + 4 * (size_t)cur;
+  const uint4 a0 = __ldg(n), a1 = __ldg(n + 1);
+#if EID_Q8_TEX
+  const uint4 a2 = tex1Dfetch<uint4>(A.nodeTex, 4 * cur + 2), a3 = tex1Dfetch<uint4>(A.nodeTex, 4 * cur + 3);   // (the node texture is uint4 in this build)
+#else
+  const uint4 a2 = __ldg(n + 2), a3 = __ldg(n + 3);
+#endif
+  const float ax = __uint_as_float(a0.w) * rb.ix, ay = __uint_as_float(a1.x) * rb.iy, az = __uint_as_float(a1.y) * rb.iz;
+  const float bx = fmaf(__uint_as_float(a0.x), rb.ix, -rb.ox), by = fmaf(__uint_as_float(a0.y), rb.iy, -rb.oy), bz = fmaf(__uint_as_float(a0.z), rb.iz, -rb.oz);
+  const bool sx = rb.nx != 0, sy = rb.ny != 1, sz = rb.nz != 2;      // direction component negative: the upper plane is the near one
+  const uint32_t nqx = sx ? a2.y : a1.z, fqx = sx ? a1.z : a2.y;
+  const uint32_t nqy = sy ? a2.z : a1.w, fqy = sy ? a1.w : a2.z;
+  const uint32_t nqz = sz ? a2.w : a2.x, fqz = sz ? a2.x : a2.w;
+  float e0, e1, e2, e3;
+#if EID_Q8_MAGIC
+  // byte -> float without the conversion unit: the byte becomes the low mantissa byte of 2^23 (one PRMT), minus 2^23 (exact)
+#define EID_Q8_F(w, sh) (__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | ((sh) >> 3))) - 8388608.0f)
+#else
+#define EID_Q8_F(w, sh) ((float)(((w) >> (sh)) & 255u))
+#endif
+#define EID_Q8_CHILD(e, sh, ref) { \
+    const float tn = fmaxf(fmaxf(fmaf(EID_Q8_F(nqx, sh), ax, bx), fmaf(EID_Q8_F(nqy, sh), ay, by)), fmaxf(fmaf(EID_Q8_F(nqz, sh), az, bz), 0.0f)); \
+    const float tf = fminf(fminf(fmaf(EID_Q8_F(fqx, sh), ax, bx), fmaf(EID_Q8_F(fqy, sh), ay, by)), fminf(fmaf(EID_Q8_F(fqz, sh), az, bz), tbest)); \
+    e = (tn <= tf * 1.0000004f && (ref) != 0xffffffffu) ? tn : INF; }
+  EID_Q8_CHILD(e0, 0, a3.x) EID_Q8_CHILD(e1, 8, a3.y) EID_Q8_CHILD(e2, 16, a3.z) EID_Q8_CHILD(e3, 24, a3.w)
+#undef EID_Q8_CHILD
+#undef EID_Q8_F
+  const float4 rf = make_float4(__uint_as_float(a3.x), __uint_as_float(a3.y), __uint_as_float(a3.z), __uint_as_float(a3.w));
+#else
   const float4* n = A.nodes + 8 * (size_t)cur;
 #ifdef EID_NODE_LDG256
   // the whole 128-byte node in four 256-bit loads (4 L1 wavefronts per lane instead of 7); near/far by min/max
@@ -171,6 +209,7 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
   float e2 = boxEntryNF(rb, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, tbest);
   float e3 = boxEntryNF(rb, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, tbest);
 #endif
+#endif   // EID_NODE_Q8
   int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
   if (ANY) {
     // occlusion rays: order is irrelevant, just visit every child the ray enters
