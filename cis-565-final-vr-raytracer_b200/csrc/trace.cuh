@@ -102,6 +102,9 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 #ifndef EID_Q8_TEX
 #define EID_Q8_TEX 0
 #endif
+#ifndef EID_SORT_NEAREST
+#define EID_SORT_NEAREST 0
+#endif
 #ifndef EID_Q8_MAGIC
 #define EID_Q8_MAGIC 0
 #endif
@@ -220,9 +223,14 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
     if (e3 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c3; } else { next = c3; have = true; } }
     cur = have ? next : EID_POP();
   } else {
-    // sort the four (entry distance, ref) pairs ascending: 5-comparator network
 #define EID_CSWAP(ea, ca, eb, cb) { if (eb < ea) { float te = ea; ea = eb; eb = te; int tc = ca; ca = cb; cb = tc; } }
+#if EID_SORT_NEAREST
+    // only the nearest child is brought to the front (3 comparators); the other entered children are pushed unordered
+    EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2)
+#else
+    // sort the four (entry distance, ref) pairs ascending: 5-comparator network
     EID_CSWAP(e0, c0, e1, c1) EID_CSWAP(e2, c2, e3, c3) EID_CSWAP(e0, c0, e2, c2) EID_CSWAP(e1, c1, e3, c3) EID_CSWAP(e1, c1, e2, c2)
+#endif
 #undef EID_CSWAP
     if (e0 < INF) {
       if (e3 < INF && EID_SP_OK(sp)) stack[sp++] = c3;
