@@ -51,6 +51,23 @@ class AccelStructure {
   eid_accel* m_h = nullptr;
 };
 
+// HdrSampling (src/hdr_sampling.hpp:43-48): the environment map, its importance-sampling alias map, integral and average
+class HdrSampling {
+ public:
+  void setup(int cudaDevice = 0) { m_device = cudaDevice; }
+  // HdrSampling::loadEnvironment(hdrImage) (hdr_sampling.cpp:48-105): Radiance .hdr file -> RGBA32F texels + createEnvironmentAccel
+  void loadEnvironment(const std::string& hdrImage) { destroy(); check(eid_env_load_hdr(&m_h, m_device, hdrImage.c_str())); }
+  void setPixels(const float* rgba, uint32_t width, uint32_t height) { destroy(); check(eid_env_create(&m_h, m_device, rgba, width, height)); }
+  float getIntegral() const { return eid_env_integral(m_h); }   // hdr_sampling.hpp:47
+  float getAverage() const { return eid_env_average(m_h); }     // hdr_sampling.hpp:48
+  void destroy() { if (m_h) { eid_env_destroy(m_h); m_h = nullptr; } }
+  ~HdrSampling() { destroy(); }
+  eid_env* handle() const { return m_h; }
+ private:
+  eid_env* m_h = nullptr;
+  int m_device = 0;
+};
+
 class Renderer {
  public:
   // Renderer::create(size, rtDescSetLayouts, scene) (renderer.cpp:97-148): descriptor-set layouts become the two handles
@@ -64,6 +81,7 @@ class Renderer {
   void update(Extent2D size) { check(eid_renderer_resize(m_h, size.width, size.height)); }
   void sync() { check(eid_renderer_sync(m_h)); }
   void setEnvironmentConstant(const float rgb[3]) { check(eid_renderer_set_env_constant(m_h, rgb)); }
+  void setEnvironment(HdrSampling* env) { check(eid_renderer_set_env(m_h, env ? env->handle() : nullptr)); }   // the S_ENV descriptor set (sample_example.cpp:318)
   void runOutput(const Tonemapper& tm) { check(eid_renderer_run_output(m_h, &tm)); }   // RenderOutput::run -> post.frag (render_output.cpp:224-240)
   void setSunAndSky(const SunAndSky& ss) { check(eid_renderer_set_sun_and_sky(m_h, &ss)); }   // SampleExample::m_sunAndSky (sample_example.cpp:172)
   void setWavefront(bool on, int traceBlocks = 0) { check(eid_renderer_set_wavefront(m_h, on ? 1 : 0, traceBlocks)); }

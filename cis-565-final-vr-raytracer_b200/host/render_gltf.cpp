@@ -1,6 +1,6 @@
 // render_gltf.cpp — headless C++ harness: what SampleExample::loadScene + the main loop do around the hot path
 // (sample_example.cpp:82-92, 164-196, 376-415), minus window/GUI.  Usage:
-//   render_gltf scene.gltf out.pfm [width height frames]
+//   render_gltf scene.gltf out.pfm [width height frames [environment.hdr]]
 // Build: g++ -std=c++17 -I include -I cis-565-final-vr-raytracer_b200/host render_gltf.cpp -L<dir> -leidola
 #include <cstdio>
 #include <cstdlib>
@@ -8,7 +8,7 @@
 #include "eidola.hpp"
 
 int main(int argc, char** argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: %s scene.gltf out.pfm [w h frames]\n", argv[0]); return 2; }
+  if (argc < 3) { std::fprintf(stderr, "usage: %s scene.gltf out.pfm [w h frames [environment.hdr]]\n", argv[0]); return 2; }
   const uint32_t w = argc > 3 ? std::atoi(argv[3]) : 1920, h = argc > 4 ? std::atoi(argv[4]) : 1080;
   const int frames = argc > 5 ? std::atoi(argv[5]) : 16;
   try {
@@ -23,9 +23,18 @@ int main(int argc, char** argv) {
     renderer.setEnvironmentConstant(env);
     const eid_scene_info info = scene.getStat();
     RtxState st = eidola::defaultRtxState(w, h);
-    st.environmentProb = 0.f;                                   // HDR importance sampling: later scope row
-    st.fireflyClampThreshold = 4.f * 3.14159265f;               // integral of the constant environment * 4 (sample_example.cpp:104)
-    st.envMapLuminIntegInv = 1.f / 3.14159265f;
+    eidola::HdrSampling skydome;
+    if (argc > 6) {                                             // SampleExample::loadEnvironmentHdr (sample_example.cpp:97-106)
+      skydome.setup(0);
+      skydome.loadEnvironment(argv[6]);
+      renderer.setEnvironment(&skydome);
+      st.fireflyClampThreshold = skydome.getIntegral() * 4.f;   // "magic" there too; environmentProb stays at its default 0.25
+      st.envMapLuminIntegInv = 1.f / skydome.getIntegral();
+    } else {
+      st.environmentProb = 0.f;                                 // constant environment: nothing to importance-sample
+      st.fireflyClampThreshold = 4.f * 3.14159265f;             // integral of the constant environment * 4 (sample_example.cpp:104)
+      st.envMapLuminIntegInv = 1.f / 3.14159265f;
+    }
     st.lightLuminIntegInv = 1.f / (info.trigLightWeight + info.puncLightWeight);   // sample_example.cpp:87
     std::vector<float> direct((size_t)w * h * 4), indirect((size_t)w * h * 4);
     scene.updateCamera({w, h});
