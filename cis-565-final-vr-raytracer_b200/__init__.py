@@ -16,7 +16,7 @@ from . import abi, scenes, sharding
 from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, SceneArrays, default_rtx_state)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# EIDOLA_LIB selects another build of the same library (kernel-variant sweeps, tools_sweep.sh); never a different backend
+# EIDOLA_LIB selects another build of the same library (kernel-variant sweeps, tools/sweep.sh); never a different backend
 LIB_PATH = os.environ.get("EIDOLA_LIB") or os.path.join(_HERE, "libeidola.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_HERE), "include")
 _lib = None

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools_gpuretry.sh <timeout-seconds> '<command>' — gpurun, retried while the pod answers "transient / busy" (nothing is charged for those)
+# tools/gpuretry.sh <timeout-seconds> '<command>' — gpurun, retried while the pod answers "transient / busy" (nothing is charged for those)
 T=$1; shift
 for i in $(seq 1 20); do
   /usr/local/graft/bin/gpurun --timeout "$T" -- "$@" > /tmp/gpuretry.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (GPU box): tools_k2ncu.sh [-a "<bench args>"] <variant> ...  -> per-kernel ncu lines (one frame) of the trace stages for each prebuilt libeidola_<variant>.so
+# usage (GPU box): tools/k2ncu.sh [-a "<bench args>"] <variant> ...  -> per-kernel ncu lines (one frame) of the trace stages for each prebuilt libeidola_<variant>.so
 ARGS=""
 if [ "$1" = "-a" ]; then ARGS="$2"; shift 2; fi
 for l in "$@"; do

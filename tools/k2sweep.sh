@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (GPU box): tools_k2sweep.sh "<bench args>" ...  -> frame ms + per-stage ms for each argument set
+# usage (GPU box): tools/k2sweep.sh "<bench args>" ...  -> frame ms + per-stage ms for each argument set
 for a in "$@"; do
   timeout 300 python bench.py --steps 16 --warmup 4 --no-cpu-baseline $a 2> gpurun_out/sweep.err | tail -1 > gpurun_out/sweep.json
   python - "$a" <<'PY'

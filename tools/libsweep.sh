@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (on the GPU box): tools_libsweep.sh [-a "<bench args>"] <variant> ...   -> quick parity subset + per-kernel ms of bench.py for each
+# usage (on the GPU box): tools/libsweep.sh [-a "<bench args>"] <variant> ...   -> quick parity subset + per-kernel ms of bench.py for each
 # prebuilt cis-565-final-vr-raytracer_b200/libeidola_<variant>.so (EID_VARIANT=<variant> python .../build.py); "base" = libeidola.so
 ARGS=""
 if [ "$1" = "-a" ]; then ARGS="$2"; shift 2; fi

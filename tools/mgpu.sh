@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (GPU box, N GPUs): tools_mgpu.sh N "<bench args>" ...  -> one line per argument set
+# usage (GPU box, N GPUs): tools/mgpu.sh N "<bench args>" ...  -> one line per argument set
 N=$1; shift
 port=29520
 for a in "$@"; do

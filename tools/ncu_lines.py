@@ -1,4 +1,4 @@
-"""Aggregates an ncu report's source page per CUDA source line: python tools_ncu_lines.py <report.ncu-rep> [top N]
+"""Aggregates an ncu report's source page per CUDA source line: python tools/ncu_lines.py <report.ncu-rep> [top N]
 (instructions executed, stall samples, average active threads per instruction)."""
 import collections, csv, subprocess, sys, io
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40

@@ -1,4 +1,4 @@
-"""Compact per-kernel table from an `ncu --page raw --csv` export: python tools_ncu_summary.py <raw.csv>"""
+"""Compact per-kernel table from an `ncu --page raw --csv` export: python tools/ncu_summary.py <raw.csv>"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, data = rows[0], rows[1], rows[2:]

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (on the GPU box): tools_sweep.sh "<label>|<nvcc extra flags>" ...   -> per-kernel ms of bench.py for each build variant
+# usage (on the GPU box): tools/sweep.sh "<label>|<nvcc extra flags>" ...   -> per-kernel ms of bench.py for each build variant
 for v in "$@"; do
   label="${v%%|*}"; flags="${v#*|}"
   EID_NVCC_EXTRA="$flags" python cis-565-final-vr-raytracer_b200/build.py --force > /dev/null 2> gpurun_out/build_$label.err || { echo "$label BUILD FAILED"; tail -5 gpurun_out/build_$label.err; continue; }
