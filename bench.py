@@ -167,7 +167,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": r["mrays"], "unit": "Mray/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_frame"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[_ACTIVE]["text"], "reference_arm": "CPU oracle (C++/OpenMP restatement of the reference shaders; the Vulkan app cannot run here)",
                    "sample": sample},
         "cpu_baseline": {"value": r["mrays"], "unit": "Mray/s", "cores": r["cores"], "kind": "port", "sample": sample},

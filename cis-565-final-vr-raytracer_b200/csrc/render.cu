@@ -205,7 +205,9 @@ DEV void storeDResv(float* base, size_t i, const DResv& r) {
 // SPATIAL (eSpatial / eSpatiotemporal, :224-255): the pixel stops where the reference has its first barrier() — it writes
 // tempDirectResv and its continuation record — and k_direct_spatial finishes it once every pixel's entry is written (the race-free
 // reading of the reference).  halo = 1: the launch covers the row above and the row below each owned stripe (multi-GPU),
-// 64 pixels of one row per block; such pixels only write tempDirectResv, which the stripe's edge rows read.
+// 64 pixels of one row per block; such pixels write tempDirectResv, which the stripe's edge rows read, and keep their own G-buffer /
+// motion / reservoir history (the values the owning rank computes), so that their temporal reuse matches the owner's next frame; they
+// write no image and their rays are not counted.
 template <bool STATS, bool TEX, bool SPATIAL>
 __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P, const int halo) {
   int x = blockIdx.x * 8 + threadIdx.x, y;
@@ -229,11 +231,9 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
     Payload prd;
     bool finished = true;
     if (!closestHit<STATS, TEX>(P, ro, rd, prd, seed, rc)) {                 // :154-158
-      if (own) {
-        P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
-        P.motion[pix] = make_short2(0, 0);
-        radiance = envRadiance<TEX>(P, rd);
-      }
+      P.thisG[pix] = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
+      P.motion[pix] = make_short2(0, 0);
+      if (own) radiance = envRadiance<TEX>(P, rd);
     } else {
       rc.primary++;
       State st = getState<TEX>(P.sc, prd, rd);
@@ -243,10 +243,8 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
       mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
       const float mvx = __fadd_rn(__fmul_rn(__fdiv_rn(pr[0], pr[3]), 0.5f), 0.5f), mvy = __fadd_rn(__fmul_rn(__fdiv_rn(pr[1], pr[3]), 0.5f), 0.5f);
       const int mix_ = f2i_sat(__fmul_rn(mvx, (float)W)), miy = f2i_sat(__fmul_rn(mvy, (float)H));
-      if (own) {
-        P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
-        P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
-      }
+      P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
+      P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
 
       if (P.st.debugging_mode > eIndirectStage) {          // DebugInfo (pathtrace.glsl:362-380)
         switch (P.st.debugging_mode) {
@@ -306,7 +304,7 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
             if (resvInvalidW(tmp.weight)) { tmp.num = 0; tmp.weight = 0.f; }
             const int clampN = P.st.RISSampleNum * P.st.reservoirClamp;
             if (tmp.num > (uint32_t)clampN) { tmp.weight = __fmul_rn(tmp.weight, __fdiv_rn((float)clampN, (float)tmp.num)); tmp.num = (uint32_t)clampN; }
-            if (own) storeDResv(P.thisDR, (size_t)y * W + x, tmp);
+            storeDResv(P.thisDR, (size_t)y * W + x, tmp);
           }
           if (SPATIAL && (P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal)) {   // :224-231, up to the barrier
             if (resvInvalidW(resv.weight)) { resv.num = 0; resv.weight = 0.f; }                     // resvCheckValidity

@@ -551,8 +551,8 @@ def test_state_size_smaller_than_allocation():
         common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "descaled frame %d" % f)
 
 
-@pytest.mark.parametrize("restir", [abi.eTemporal, abi.eSpatiotemporal])
-def test_band_sharded_trace_equals_full_frame(restir):
+@pytest.mark.parametrize("restir,exchange_history", [(abi.eTemporal, True), (abi.eSpatiotemporal, True), (abi.eSpatiotemporal, False)])
+def test_band_sharded_trace_equals_full_frame(restir, exchange_history):
     """Multi-GPU decomposition on one device: two renderers trace disjoint row bands, the exchange buffers are
     stitched (what the all-gather does), post-processing runs on the full frame -> identical to a single run.  With spatial reuse
     each band also carries the row above and the row below it up to the tempDirectResv write (the halo launch of k_direct_stage)."""
@@ -572,6 +572,10 @@ def test_band_sharded_trace_equals_full_frame(restir):
     psc.update_camera(*size)
     exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_MOTION, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A, abi.BUF_THIS_DIRECT_RESV,
                 abi.BUF_THIS_INDIRECT_RESV]
+    if not exchange_history:
+        # what bench.py exchanges (static camera): no reservoir history crosses the ranks; with spatial reuse the halo rows keep their own
+        # direct-reservoir history, so the rows next to a band edge still see the neighbour's reservoir of the previous frame
+        exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A]
     for f in range(3):
         psc.update_camera(*size)
         st = common.frame_state(size[0], size[1], info, f, ReSTIRState=restir)
@@ -592,6 +596,8 @@ def test_band_sharded_trace_equals_full_frame(restir):
         for r in (a, b):
             got = common.snapshot(r)
             for k in ref:
+                if not exchange_history and k in ("motion", "direct_resv", "indirect_resv"):
+                    continue                      # not gathered in this mode: every rank only holds its own rows (+ halo)
                 assert got[k].tobytes() == ref[k].tobytes(), "band-sharded %s differs from the full-frame run (frame %d)" % (k, f)
 
 
