@@ -203,7 +203,47 @@ def ref_display_vectors():
     print("wrote ref_display.npz")
 
 
+def scene_tables(abi, side, n_prim):
+    """Tables 0..6 of a loaded scene object (reference / oracle / product: same `table(which, index)` call) as raw bytes."""
+    raw = lambda a: np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()
+    out = {"materials": raw(side.table(abi.TABLE_MATERIALS)), "punc": raw(side.table(abi.TABLE_PUNC_LIGHTS)), "trig": raw(side.table(abi.TABLE_TRIG_LIGHTS)),
+           "info": raw(side.table(abi.TABLE_LIGHT_INFO))}
+    out["info"][12:16] = 0            # LightBufInfo.pad: never written by the reference (whatever the Scene object's memory held)
+    for pm in range(n_prim):
+        out["vertices_%d" % pm] = raw(side.table(abi.TABLE_VERTICES, pm))
+        out["indices_%d" % pm] = raw(side.table(abi.TABLE_INDICES, pm))
+    return out
+
+
+def ref_scene_vectors():
+    """tests/golden/ref_scene.npz: the tables the reference's OWN src/scene.cpp (compiled where it lies against the stand-ins of
+    oracle/ref_shim/scene/, run on the injected harness scene) uploads — materials, punctual / triangle lights with their alias maps,
+    LightBufInfo, per-prim-mesh vertex and index buffers, the instance material indices, both light weights — and the SceneCamera after
+    each step of SCENE_CAMERA_STEPS."""
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    if ol.ref_scene_lib() is None:
+        print("oracle/_ref/librefscene.so unavailable: keeping the committed ref_scene.npz")
+        return
+    out = {}
+    for name in fi.SCENE_TABLE_MAKERS:
+        arrays = getattr(scenes, name)()
+        r = ol.RefScene(arrays)
+        for k, v in scene_tables(abi, r, len(arrays.prim_meshes)).items():
+            out["%s_%s" % (name, k)] = v
+        out["%s_inst_material" % name] = r.table(abi.TABLE_INSTANCE_DATA).view(abi.INSTANCE_DT)["materialIndex"].copy()
+        out["%s_weights" % name] = np.array(r.weights(), np.float32)
+        for k, (size, look) in enumerate(fi.SCENE_CAMERA_STEPS):
+            if look is not None:
+                r.set_lookat(*look)
+            r.update_camera(*size)
+            out["%s_camera_%d" % (name, k)] = r.table(abi.TABLE_CAMERA).copy()
+    np.savez_compressed(os.path.join(HERE, "ref_scene.npz"), **out)
+    print("wrote ref_scene.npz")
+
+
 if __name__ == "__main__":
+    ref_scene_vectors()
     ref_display_vectors()
     ref_vectors()
     ref_post_vectors()

@@ -22,7 +22,7 @@ _ref = None
 def build(force=False):
     if force or not os.path.exists(ORACLE_SO):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_SO)):
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_SO) or not os.path.exists(os.path.join(os.path.dirname(REF_SO), "librefscene.so"))):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -94,6 +94,63 @@ def ref():
         L.ref_ctx_fn.restype, L.ref_ctx_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _ref = L
     return _ref
+
+
+_ref_scene = None
+
+
+def ref_scene_lib():
+    """oracle/_ref/librefscene.so — the reference's own src/scene.cpp compiled where it lies (stand-ins: oracle/ref_shim/scene/) — or None."""
+    global _ref_scene
+    if _ref_scene is None:
+        build()
+        path = os.path.join(os.path.dirname(REF_SO), "librefscene.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        L.ref_scene_load.restype, L.ref_scene_load.argtypes = C.c_void_p, [C.c_void_p]
+        L.ref_scene_destroy.restype, L.ref_scene_destroy.argtypes = None, [C.c_void_p]
+        L.ref_scene_table.restype, L.ref_scene_table.argtypes = C.c_long, [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_long]
+        L.ref_scene_weights.restype, L.ref_scene_weights.argtypes = None, [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_scene_set_lookat.restype, L.ref_scene_set_lookat.argtypes = None, [C.c_void_p] * 3 + [C.c_float]
+        L.ref_scene_update_camera.restype, L.ref_scene_update_camera.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
+        _ref_scene = L
+    return _ref_scene
+
+
+class RefScene:
+    """The reference's Scene (src/scene.cpp) loaded with a harness scene: Scene::load's table builders and Scene::updateCamera."""
+
+    def __init__(self, arrays):
+        self.L = ref_scene_lib()
+        self._desc = arrays.desc()
+        self._h = C.c_void_p(self.L.ref_scene_load(C.byref(self._desc)))
+        assert self._h
+
+    def table(self, which, index=0):
+        """Raw bytes of table `which` (eid_scene_table numbering) or None."""
+        n = self.L.ref_scene_table(self._h, which, index, None, 0)
+        if n < 0:
+            return None
+        b = np.zeros(n, np.uint8)
+        self.L.ref_scene_table(self._h, which, index, b.ctypes.data, n)
+        return b
+
+    def weights(self):
+        t, p = C.c_float(), C.c_float()
+        self.L.ref_scene_weights(self._h, C.byref(t), C.byref(p))
+        return t.value, p.value
+
+    def set_lookat(self, eye, center, up, fov_deg):
+        self.L.ref_scene_set_lookat(_f3(eye), _f3(center), _f3(up), float(fov_deg))
+
+    def update_camera(self, w, h):
+        self.L.ref_scene_update_camera(self._h, w, h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_scene_destroy(self._h)
+            self._h = None
 
 
 def call_fn(L, name, which, x, nout):

@@ -139,6 +139,9 @@ TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth
                  ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3)),
                  ("spatial", "cornell_scene", (64, 40), 2, "none", dict(ReSTIRState=2, maxDepth=2)),            # eSpatial (race-free reading)
                  ("spatiotemporal", "small_room", (50, 34), 3, "none", dict(ReSTIRState=4, maxDepth=2))]      # eSpatiotemporal
+# host tables (src/scene.cpp run on an injected scene): scene makers, and the camera sequence (size, optional new look-at) after loading
+SCENE_TABLE_MAKERS = ["cube_scene", "cornell_scene", "small_room", "textured_scene", "instanced_scene", "alpha_scene"]
+SCENE_CAMERA_STEPS = [((640, 360), None), ((640, 360), None), ((333, 200), ((1.5, 2.5, -4.0), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0), 47.0))]
 # display pass (post.frag): (tag, debugging_mode, Tonemapper overrides); rendered on DISPLAY_SCENE at DISPLAY_SIZE, DISPLAY_FRAMES frames
 DISPLAY_SCENE, DISPLAY_SIZE, DISPLAY_FRAMES = "cornell_scene", (72, 44), 2
 DISPLAY_CONFIGS = [("default", 0, dict()),

@@ -243,6 +243,60 @@ def test_mip_chain_average_known_answers():
     assert (m >= a.reshape(-1, 4).min(axis=0)).all() and (m <= a.reshape(-1, 4).max(axis=0)).all()
 
 
+def _zero_sign_free(punc_bytes, abi):
+    """PuncLight table with the sign of zero direction / position components cleared: `worldMatrix * vec4(0, 0, -1, 0)` runs through
+    nvmath's operator* (un-vendored) — whether a zero comes out as +0 or -0 is the stand-in's choice, not the reference's."""
+    a = np.frombuffer(bytes(punc_bytes), abi.PUNC_DT).copy()
+    for f in ("direction", "position"):
+        v = a[f]
+        v[v == 0.0] = 0.0
+        a[f] = v
+    return a.tobytes()
+
+
+def test_host_tables_match_reference_scene_cpp():
+    """Scene::load's table builders and Scene::updateCamera — the reference's OWN src/scene.cpp, compiled where it lies against stand-ins
+    for Vulkan / nvpro_core / tinygltf (oracle/ref_shim/scene/) and run on the injected harness scene — against the oracle's restatement
+    AND the product's host side: materials, punctual and triangle lights with their alias maps, LightBufInfo, every vertex and index
+    buffer, instance material indices, both light weights, and the SceneCamera of a three-step camera sequence, bit for bit.  Committed
+    outputs: tests/golden/ref_scene.npz; re-run live where /root/reference exists."""
+    import ref_fn_inputs as fi
+    import eidola_b200 as eid
+    from eidola_b200 import abi, scenes
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as mg
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_scene.npz"))
+    live = ol.ref_scene_lib() if os.path.isdir("/root/reference") else None
+    for name in fi.SCENE_TABLE_MAKERS:
+        arrays = getattr(scenes, name)()
+        osc = ol.OracleScene(); osc.load_arrays(arrays)
+        psc = eid.Scene(device=-1); psc.load_arrays(arrays)          # host-only product scene: the table builders run on the CPU
+        sides = [("oracle", osc), ("product", psc)]
+        if live is not None:
+            sides.append(("reference (live)", ol.RefScene(arrays)))
+        for tag, side in sides:
+            got = mg.scene_tables(abi, side, len(arrays.prim_meshes))
+            for k, v in got.items():
+                want = z["%s_%s" % (name, k)]
+                if k == "punc":
+                    assert _zero_sign_free(v, abi) == _zero_sign_free(want, abi), (name, tag, k)
+                else:
+                    assert v.tobytes() == want.tobytes(), (name, tag, k)
+            inst = np.ascontiguousarray(side.table(abi.TABLE_INSTANCE_DATA)).view(np.uint8).reshape(-1).view(abi.INSTANCE_DT)["materialIndex"]
+            assert np.array_equal(inst, z["%s_inst_material" % name]), (name, tag)
+            w = side.weights() if hasattr(side, "weights") else (side.info().trigLightWeight, side.info().puncLightWeight)
+            assert np.array(w, np.float32).tobytes() == z["%s_weights" % name].tobytes(), (name, tag)
+            for k, (size, look) in enumerate(fi.SCENE_CAMERA_STEPS):
+                if look is not None:
+                    side.set_lookat(*look)
+                side.update_camera(*size)
+                cam = np.ascontiguousarray(side.table(abi.TABLE_CAMERA)).view(np.uint8).reshape(-1).view(np.uint32).copy()
+                want = z["%s_camera_%d" % (name, k)].view(np.uint32).copy()
+                if k == 0:
+                    cam[80:83] = 0; want[80:83] = 0       # lastPosition of the first update: a function-static in the reference (scene.cpp:780), i.e. the previous scene's eye
+                assert cam.tobytes() == want.tobytes(), (name, tag, "camera step %d" % k)
+
+
 def test_environment_alias_map_matches_reference_vectors():
     """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
     lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
