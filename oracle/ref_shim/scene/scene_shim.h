@@ -41,12 +41,34 @@ typedef void* VkDescriptorSet; typedef uint64_t VkDeviceSize; typedef uint32_t V
 #define VK_NULL_HANDLE nullptr
 #define VK_WHOLE_SIZE (~0ULL)
 struct VkExtent2D { uint32_t width, height; };
+typedef struct VkPipeline_T* VkPipeline; typedef void* VkPipelineLayout; typedef void* VkShaderModule;
+struct VkPipeline_T { int tag; };                                       // a pipeline is the tag of the shader it was created from
+enum VkPipelineBindPoint { VK_PIPELINE_BIND_POINT_COMPUTE = 1 };
+enum VkImageLayout { VK_IMAGE_LAYOUT_UNDEFINED = 0, VK_IMAGE_LAYOUT_GENERAL = 1 };
+enum { VK_IMAGE_USAGE_STORAGE_BIT = 8, VK_IMAGE_USAGE_COLOR_ATTACHMENT_BIT = 0x10 };
+struct VkPushConstantRange { VkFlags stageFlags; uint32_t offset, size; };
+struct VkPipelineLayoutCreateInfo { int sType; const void* pNext; VkFlags flags; uint32_t setLayoutCount; void* const* pSetLayouts; uint32_t pushConstantRangeCount; const VkPushConstantRange* pPushConstantRanges; };
+struct VkPipelineShaderStageCreateInfo { int sType; const void* pNext; VkFlags flags; int stage; VkShaderModule module; const char* pName; const void* pSpecializationInfo; };
+struct VkComputePipelineCreateInfo { int sType; const void* pNext; VkFlags flags; VkPipelineShaderStageCreateInfo stage; VkPipelineLayout layout; VkPipeline basePipelineHandle; int basePipelineIndex; };
+enum { VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO = 18, VK_STRUCTURE_TYPE_COMPUTE_PIPELINE_CREATE_INFO = 29, VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO = 30 };
+// ---- the recording "device": what a command buffer executes and which resource each descriptor names (renderer.cpp) -------------
+struct ShimResource { int kind; int id; uint64_t bytes; uint32_t width, height; int format; };      // kind 0 = buffer, 1 = image
+struct ShimEvent { int what; int a, b, c; std::vector<unsigned char> data; };                        // see ref_renderer.cpp
+struct ShimDevice {
+  std::vector<std::unique_ptr<ShimResource>> resources;
+  std::vector<ShimEvent> log;
+  struct Write { int set, binding, resource; uint64_t range; };
+  std::vector<Write> writes;
+  int nextSet = 0;
+  ShimResource* add(int kind, uint64_t bytes, uint32_t w, uint32_t h, int format) { resources.emplace_back(new ShimResource{kind, (int)resources.size(), bytes, w, h, format}); return resources.back().get(); }
+  static ShimDevice& get() { static ShimDevice d; return d; }
+};
 enum VkStructureType { VK_STRUCTURE_TYPE_SAMPLER_CREATE_INFO = 31, VK_STRUCTURE_TYPE_BUFFER_MEMORY_BARRIER = 44 };
 enum VkFilter { VK_FILTER_NEAREST = 0, VK_FILTER_LINEAR = 1 };
 enum VkSamplerMipmapMode { VK_SAMPLER_MIPMAP_MODE_NEAREST = 0, VK_SAMPLER_MIPMAP_MODE_LINEAR = 1 };
 enum VkSamplerAddressMode { VK_SAMPLER_ADDRESS_MODE_REPEAT = 0, VK_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT = 1, VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE = 2 };
-enum VkFormat { VK_FORMAT_R8G8B8A8_UNORM = 37, VK_FORMAT_B8G8R8A8_UNORM = 44, VK_FORMAT_R32G32B32A32_SFLOAT = 109 };
-enum VkDescriptorType { VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER = 1, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER = 6, VK_DESCRIPTOR_TYPE_STORAGE_BUFFER = 7 };
+enum VkFormat { VK_FORMAT_R8G8B8A8_UNORM = 37, VK_FORMAT_B8G8R8A8_UNORM = 44, VK_FORMAT_R16G16_SINT = 82, VK_FORMAT_R16G16_SFLOAT = 83, VK_FORMAT_R32G32B32A32_UINT = 107, VK_FORMAT_R32G32B32A32_SFLOAT = 109 };
+enum VkDescriptorType { VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER = 1, VK_DESCRIPTOR_TYPE_STORAGE_IMAGE = 3, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER = 6, VK_DESCRIPTOR_TYPE_STORAGE_BUFFER = 7 };
 enum { VK_BUFFER_USAGE_TRANSFER_DST_BIT = 2, VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT = 0x10, VK_BUFFER_USAGE_STORAGE_BUFFER_BIT = 0x20,
        VK_BUFFER_USAGE_SHADER_DEVICE_ADDRESS_BIT = 0x20000, VK_BUFFER_USAGE_ACCELERATION_STRUCTURE_BUILD_INPUT_READ_ONLY_BIT_KHR = 0x80000,
        VK_MEMORY_PROPERTY_DEVICE_LOCAL_BIT = 1, VK_IMAGE_USAGE_SAMPLED_BIT = 4, VK_COMMAND_POOL_CREATE_TRANSIENT_BIT = 1,
@@ -57,9 +79,9 @@ enum { VK_BUFFER_USAGE_TRANSFER_DST_BIT = 2, VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT 
 struct VkSamplerCreateInfo { VkStructureType sType; const void* pNext; VkFlags flags; VkFilter magFilter, minFilter; VkSamplerMipmapMode mipmapMode;
                              VkSamplerAddressMode addressModeU, addressModeV, addressModeW; float mipLodBias, maxAnisotropy, minLod, maxLod; };
 struct VkImageCreateInfo { VkExtent2D extent; VkFormat format; uint32_t mipLevels; };
-struct VkImageViewCreateInfo { VkImage image; };
+struct VkImageViewCreateInfo { VkImage image; };                          // image = the ShimResource of the image
 struct VkDescriptorBufferInfo { VkBuffer buffer; VkDeviceSize offset, range; };
-struct VkDescriptorImageInfo { VkSampler sampler; VkImageView imageView; int imageLayout; };
+struct VkDescriptorImageInfo { VkSampler sampler; VkImageView imageView; int imageLayout; };     // imageView = the ShimResource of the image
 struct VkWriteDescriptorSet { int unused; };
 struct VkBufferMemoryBarrier { VkStructureType sType; const void* pNext; VkFlags srcAccessMask, dstAccessMask; uint32_t srcQueueFamilyIndex, dstQueueFamilyIndex;
                                VkBuffer buffer; VkDeviceSize offset, size; };
@@ -71,11 +93,34 @@ inline void vkCmdPipelineBarrier(VkCommandBuffer, VkFlags, VkFlags, VkFlags, uin
 // vkCmdUpdateBuffer(cmdBuf, deviceUBO, 0, sizeof(SceneCamera), &m_camera): the one Vulkan call with an effect the tests read — defined in ref_scene.cpp
 void vkCmdUpdateBuffer(VkCommandBuffer, VkBuffer dst, VkDeviceSize offset, VkDeviceSize size, const void* data);
 inline void vkCmdBlitImage(...) {}
+inline void vkDestroyPipeline(VkDevice, VkPipeline, const void*) {}
+inline void vkDestroyPipelineLayout(VkDevice, VkPipelineLayout, const void*) {}
+inline void vkDestroyShaderModule(VkDevice, VkShaderModule, const void*) {}
+inline void vkCreatePipelineLayout(VkDevice, const VkPipelineLayoutCreateInfo* ci, const void*, VkPipelineLayout* out) {
+  ShimEvent e{0, (int)ci->setLayoutCount, (int)ci->pushConstantRangeCount, ci->pushConstantRangeCount ? (int)ci->pPushConstantRanges[0].size : 0, {}};
+  ShimDevice::get().log.push_back(e); *out = (VkPipelineLayout)1;
+}
+inline void vkCreateComputePipelines(VkDevice, void*, uint32_t, const VkComputePipelineCreateInfo* ci, const void*, VkPipeline* out) { *out = new VkPipeline_T{(int)(intptr_t)ci->stage.module}; }
+inline void vkCmdBindDescriptorSets(VkCommandBuffer, VkPipelineBindPoint, VkPipelineLayout, uint32_t first, uint32_t n, const VkDescriptorSet* sets, uint32_t, const void*) {
+  ShimEvent e{1, (int)first, (int)n, n ? (int)(intptr_t)sets[n - 1] : -1, {}}; ShimDevice::get().log.push_back(e);   // c = the LAST set bound = the renderer's own (S_RAYQ)
+}
+inline void vkCmdPushConstants(VkCommandBuffer, VkPipelineLayout, VkFlags, uint32_t offset, uint32_t size, const void* data) {
+  ShimEvent e{2, (int)offset, (int)size, 0, std::vector<unsigned char>((const unsigned char*)data, (const unsigned char*)data + size)}; ShimDevice::get().log.push_back(e);
+}
+inline void vkCmdBindPipeline(VkCommandBuffer, VkPipelineBindPoint, VkPipeline p) { ShimEvent e{3, p ? p->tag : -1, 0, 0, {}}; ShimDevice::get().log.push_back(e); }
+inline void vkCmdDispatch(VkCommandBuffer, uint32_t x, uint32_t y, uint32_t z) { ShimEvent e{4, (int)x, (int)y, (int)z, {}}; ShimDevice::get().log.push_back(e); }
 
 // ---- nvmath (un-vendored): contract arithmetic ---------------------------------------------------------------------------------
 namespace nvmath {
 template <class T> struct vector4;
-template <class T> struct vector2 { T x, y; vector2() : x(0), y(0) {} vector2(T a, T b) : x(a), y(b) {} };
+template <class T> struct vector2 {
+  T x, y;
+  vector2() : x(0), y(0) {}
+  vector2(T a, T b) : x(a), y(b) {}
+  T& operator[](int i) { return (&x)[i]; }
+  const T& operator[](int i) const { return (&x)[i]; }
+};
+template <class T> vector2<T> operator/(const vector2<T>& a, T s) { return vector2<T>(a.x / s, a.y / s); }   // ivec2 / 2: C integer division, like nvmath
 template <class T> struct vector3 {
   T x, y, z;
   vector3() : x(0), y(0), z(0) {}
@@ -193,13 +238,16 @@ inline void AddCamera(const nvh::CameraManipulator::Camera&) {}
 }
 
 // ---- nvvk ----------------------------------------------------------------------------------------------------------------------
-struct VkBuffer_T { std::vector<unsigned char> bytes; };               // a "buffer" is the host copy of what was uploaded into it
+struct VkBuffer_T { std::vector<unsigned char> bytes; ShimResource* res = nullptr; };   // a "buffer" is the host copy of what was uploaded into it
 namespace nvvk {
-struct Image { VkImage image = nullptr; };
+struct Image { VkImage image = nullptr; };                                // image = ShimResource* when created through createImage(info)
 struct Texture { VkImage image = nullptr; VkDescriptorImageInfo descriptor{}; };
 struct Buffer { VkBuffer buffer = nullptr; };
 inline VkDeviceAddress getBufferDeviceAddress(VkDevice, VkBuffer b) { return (VkDeviceAddress)(uintptr_t)(b ? b->bytes.data() : nullptr); }   // the shaders' buffer_reference
 inline VkImageCreateInfo makeImage2DCreateInfo(VkExtent2D e, VkFormat f = VK_FORMAT_R8G8B8A8_UNORM, VkFlags = 0, bool = false) { return VkImageCreateInfo{e, f, 1}; }
+inline void cmdBarrierImageLayout(VkCommandBuffer, VkImage, VkImageLayout, VkImageLayout) {}
+inline VkShaderModule createShaderModule(VkDevice, const uint32_t* code, size_t) { return (VkShaderModule)(intptr_t)code[0]; }   // the stand-in "SPIR-V" is one word: the shader's tag
+struct ProfilerVK {};
 inline VkImageViewCreateInfo makeImageViewCreateInfo(VkImage i, const VkImageCreateInfo&) { return VkImageViewCreateInfo{i}; }
 inline void cmdGenerateMipmaps(...) {}
 class ResourceAllocator {
@@ -210,16 +258,18 @@ public:
   void destroy(Image&) {}
   void destroy(Buffer&) {}
   Image createImage(VkCommandBuffer, VkDeviceSize, const void*, const VkImageCreateInfo&) { return Image(); }
+  Image createImage(const VkImageCreateInfo& ci) { const uint64_t texel = ci.format == VK_FORMAT_R16G16_SINT || ci.format == VK_FORMAT_R16G16_SFLOAT ? 4 : 16; return Image{(VkImage)ShimDevice::get().add(1, texel * ci.extent.width * ci.extent.height, ci.extent.width, ci.extent.height, (int)ci.format)}; }
+  Texture createTexture(const Image& im, const VkImageViewCreateInfo& iv) { Texture t; t.image = im.image; t.descriptor.imageView = (VkImageView)iv.image; return t; }
   Texture createTexture(const Image&, const VkImageViewCreateInfo&, const VkSamplerCreateInfo&) { return Texture(); }
   Texture createTexture(VkCommandBuffer, VkDeviceSize, const void*, const VkImageCreateInfo&, const VkSamplerCreateInfo&) { return Texture(); }
   template <class T> Buffer createBuffer(VkCommandBuffer, const std::vector<T>& v, VkFlags) { return make(v.data(), v.size() * sizeof(T)); }
   Buffer createBuffer(VkCommandBuffer, VkDeviceSize n, const void* p, VkFlags) { return make(p, (size_t)n); }
-  Buffer createBuffer(VkDeviceSize n, VkFlags, VkFlags) { return make(nullptr, (size_t)n); }
+  Buffer createBuffer(VkDeviceSize n, VkFlags, VkFlags = 0) { Buffer b = make(nullptr, (size_t)n); b.buffer->res = ShimDevice::get().add(0, n, 0, 0, 0); return b; }
   void finalizeAndReleaseStaging() {}
 };
 struct DebugUtil { void setup(VkDevice) {} template <class T> void setObjectName(T, const std::string&) {} template <class T> void setObjectName(T, const char*) {} };
 struct CommandPool {
-  CommandPool(VkDevice, uint32_t, VkFlags, VkQueue) {}
+  CommandPool(VkDevice, uint32_t, VkFlags = 0, VkQueue = nullptr) {}
   VkCommandBuffer createCommandBuffer() { return nullptr; }
   void submitAndWait(VkCommandBuffer) {}
 };
@@ -228,10 +278,15 @@ struct DescriptorSetBindings {
   void addBinding(Binding) {}
   VkDescriptorPool createPool(VkDevice, uint32_t) { return nullptr; }
   VkDescriptorSetLayout createLayout(VkDevice) { return nullptr; }
-  VkWriteDescriptorSet makeWrite(VkDescriptorSet, int, const void*) { return VkWriteDescriptorSet(); }
+  VkWriteDescriptorSet makeWrite(VkDescriptorSet s, int binding, const VkDescriptorBufferInfo* b) {
+    ShimDevice::get().writes.push_back({(int)(intptr_t)s, binding, b && b->buffer && b->buffer->res ? b->buffer->res->id : -1, b ? b->range : 0}); return VkWriteDescriptorSet();
+  }
+  VkWriteDescriptorSet makeWrite(VkDescriptorSet s, int binding, const VkDescriptorImageInfo* im) {
+    ShimDevice::get().writes.push_back({(int)(intptr_t)s, binding, im && im->imageView ? ((ShimResource*)im->imageView)->id : -1, 0}); return VkWriteDescriptorSet();
+  }
   VkWriteDescriptorSet makeWriteArray(VkDescriptorSet, int, const void*) { return VkWriteDescriptorSet(); }
 };
-inline VkDescriptorSet allocateDescriptorSet(VkDevice, VkDescriptorPool, VkDescriptorSetLayout) { return nullptr; }
+inline VkDescriptorSet allocateDescriptorSet(VkDevice, VkDescriptorPool, VkDescriptorSetLayout) { return (VkDescriptorSet)(intptr_t)(++ShimDevice::get().nextSet); }   // sets are numbered 1, 2, ...
 }  // namespace nvvk
 #define NAME_VK(x) do { } while (0)
 #define NAME_IDX_VK(x, i) do { } while (0)

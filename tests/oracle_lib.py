@@ -114,6 +114,13 @@ def ref_scene_lib():
         L.ref_scene_weights.restype, L.ref_scene_weights.argtypes = None, [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_scene_set_lookat.restype, L.ref_scene_set_lookat.argtypes = None, [C.c_void_p] * 3 + [C.c_float]
         L.ref_scene_update_camera.restype, L.ref_scene_update_camera.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
+        L.ref_renderer_create.restype, L.ref_renderer_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
+        L.ref_renderer_update.restype, L.ref_renderer_update.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
+        L.ref_renderer_destroy.restype, L.ref_renderer_destroy.argtypes = None, [C.c_void_p]
+        L.ref_renderer_roles.restype, L.ref_renderer_roles.argtypes = None, [C.c_void_p, C.c_void_p]
+        L.ref_renderer_resource.restype, L.ref_renderer_resource.argtypes = C.c_int, [C.c_int, C.c_void_p]
+        L.ref_renderer_wiring.restype, L.ref_renderer_wiring.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_renderer_run.restype, L.ref_renderer_run.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _ref_scene = L
     return _ref_scene
 
@@ -150,6 +157,50 @@ class RefScene:
     def __del__(self):
         if getattr(self, "_h", None):
             self.L.ref_scene_destroy(self._h)
+            self._h = None
+
+
+class RefRenderer:
+    """The reference's Renderer (src/renderer.cpp) on the recording stand-in device (oracle/ref_shim/ref_renderer.cpp)."""
+    ROLES = ("gbuffer0", "gbuffer1", "directResv0", "directResv1", "indirectResv0", "indirectResv1", "directTemp", "indirectTemp", "motion",
+             "denoiseTemp0", "denoiseTemp1", "denoiseTemp2", "denoiseTemp3")
+
+    def __init__(self, w, h):
+        self.L = ref_scene_lib()
+        self._h = C.c_void_p(self.L.ref_renderer_create(w, h))
+
+    def update(self, w, h):
+        self.L.ref_renderer_update(self._h, w, h)
+
+    def resources(self):
+        """role -> (resource id, kind 0 buffer / 1 image, bytes, width, height, VkFormat)."""
+        ids = np.zeros(13, np.int32)
+        self.L.ref_renderer_roles(self._h, ids.ctypes.data)
+        out = {}
+        for role, i in zip(self.ROLES, ids):
+            o = np.zeros(5, np.int64)
+            assert self.L.ref_renderer_resource(int(i), o.ctypes.data) == 0
+            out[role] = (int(i),) + tuple(int(v) for v in o)
+        return out
+
+    def wiring(self):
+        """{(set number 1|2, binding): (resource id, range bytes)} of the last updateDescriptorSet."""
+        w = np.zeros((26, 4), np.int64)
+        n = self.L.ref_renderer_wiring(self._h, w.ctypes.data, 26)
+        return {(int(r[0]), int(r[1])): (int(r[2]), int(r[3])) for r in w[:n]}
+
+    def run(self, state, frames):
+        """Command sequence of Renderer::run: list of (what, a, b, c) + the pushed RtxState blobs (bytes)."""
+        rows = np.zeros((64, 4), np.int32)
+        push = np.zeros(64 * C.sizeof(state), np.uint8)
+        n = self.L.ref_renderer_run(self._h, C.byref(state), frames, rows.ctypes.data, 64, push.ctypes.data, push.size)
+        sz = C.sizeof(state)
+        npush = int((rows[:n, 0] == 2).sum())
+        return [tuple(int(v) for v in r) for r in rows[:n]], [push[i * sz:(i + 1) * sz].tobytes() for i in range(npush)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_renderer_destroy(self._h)
             self._h = None
 
 

@@ -297,6 +297,79 @@ def test_host_tables_match_reference_scene_cpp():
                 assert cam.tobytes() == want.tobytes(), (name, tag, "camera step %d" % k)
 
 
+def expected_run_commands(w, h, denoise, frames):
+    """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
+    it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
+    image, then — only when denoise > 0 — 4 direct and 5 indirect A-Trous levels, each with denoiseLevel = i pushed first, then compose.
+    Rows are (what, a, b, c): 1 bind sets (first, count, set number), 2 push (offset, size, push index), 3 bind pipeline (shader tag), 4 dispatch."""
+    cd = lambda x: (x + 7) // 8
+    full, half = (cd(w), cd(h), 1), (cd(w // 2), cd(h // 2), 1)
+    rows, levels = [(1, 0, 1, (frames + 1) % 2 + 1), (2, 0, 100, 0), (3, 1, 0, 0), (4,) + full, (3, 4, 0, 0), (4,) + half, (3, 5, 0, 0)], [None]
+    for i in range(4 if denoise > 0 else 0):
+        rows += [(2, 0, 100, len(levels)), (4,) + full]; levels.append(i)
+    rows.append((3, 6, 0, 0))
+    for i in range(5 if denoise > 0 else 0):
+        rows += [(2, 0, 100, len(levels)), (4,) + half]; levels.append(i)
+    rows += [(3, 7, 0, 0), (4,) + full]
+    return rows, levels
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_renderer_schedule_and_wiring_match_reference_renderer_cpp():
+    """The reference's OWN src/renderer.cpp, compiled where it lies against a recording stand-in for Vulkan (oracle/ref_shim/ref_renderer.cpp):
+    Renderer::create / update allocate exactly the buffer set the oracle and the product allocate (sizes per pixel, full-resolution denoise
+    temporaries, one tempDirectResv), the two descriptor sets are wired last* = [i], this* = [!i] (renderer.cpp:341-375), and
+    Renderer::run records exactly the command sequence both implement (renderer.cpp:154-206), for even / odd sizes, denoise on / off and
+    both frame parities; after a resize the wiring names the new resources."""
+    from eidola_b200 import abi
+    assert ol.ref_scene_lib() is not None
+    LAST_THIS = {0: ("gbuffer", 0), 1: ("gbuffer", 1), 2: ("directResv", 0), 3: ("directResv", 1), 5: ("indirectResv", 0), 6: ("indirectResv", 1)}
+    FIXED = {4: "directTemp", 7: "indirectTemp", 8: "motion", 9: "denoiseTemp0", 10: "denoiseTemp1", 11: "denoiseTemp2", 12: "denoiseTemp3"}
+    rr = ol.RefRenderer(100, 60)
+    for (w, h) in ((100, 60), (1920, 1080), (65, 33)):
+        rr.update(w, h)
+        res = rr.resources()
+        n, ni = w * h, (w // 2) * (h // 2)
+        for k in (0, 1):
+            assert res["gbuffer%d" % k][1:] == (1, 16 * n, w, h, 107)                       # VK_FORMAT_R32G32B32A32_UINT
+            assert res["directResv%d" % k][1:3] == (0, abi.DIRECT_RESV_DT.itemsize * n)
+            assert res["indirectResv%d" % k][1:3] == (0, abi.INDIRECT_RESV_DT.itemsize * ni)
+        assert res["directTemp"][1:3] == (0, 36 * n) and res["indirectTemp"][1:3] == (0, 76 * ni)
+        assert res["motion"][1:] == (1, 4 * n, w, h, 82)                                     # VK_FORMAT_R16G16_SINT
+        for k in range(4):
+            assert res["denoiseTemp%d" % k][1:] == (1, 16 * n, w, h, 109)                    # RGBA32F, full resolution even for the indirect pair
+        if n <= 100 * 60:          # the oracle's renderer allocates the same set, byte for byte
+            from eidola_b200 import scenes
+            osc = ol.OracleScene(); osc.load_arrays(scenes.cube_scene())
+            orr = ol.OracleRenderer(osc, (w, h))
+            for which, role in ((abi.BUF_THIS_GBUFFER, "gbuffer0"), (abi.BUF_LAST_GBUFFER, "gbuffer1"), (abi.BUF_MOTION, "motion"),
+                                (abi.BUF_THIS_DIRECT_RESV, "directResv0"), (abi.BUF_LAST_DIRECT_RESV, "directResv1"),
+                                (abi.BUF_THIS_INDIRECT_RESV, "indirectResv0"), (abi.BUF_LAST_INDIRECT_RESV, "indirectResv1"),
+                                (abi.BUF_TEMP_DIRECT_RESV, "directTemp"), (abi.BUF_DENOISE_DIR_A, "denoiseTemp0"), (abi.BUF_DENOISE_DIR_B, "denoiseTemp1"),
+                                (abi.BUF_DENOISE_IND_A, "denoiseTemp2"), (abi.BUF_DENOISE_IND_B, "denoiseTemp3")):
+                assert orr.read(which).nbytes == res[role][2], role
+        wiring = rr.wiring()
+        assert len(wiring) == 26
+        for i in (0, 1):                                                                     # descriptor set i = set number i + 1
+            for binding, (name, which) in LAST_THIS.items():
+                idx = i if which == 0 else 1 - i                                             # eLast* -> [i], eThis* -> [!i]
+                assert wiring[(i + 1, binding)][0] == res["%s%d" % (name, idx)][0], (i, binding)
+            for binding, name in FIXED.items():
+                assert wiring[(i + 1, binding)][0] == res[name][0], (i, binding)
+        for denoise in (1, 0):
+            for frames in (0, 1, 2, 7):
+                st = abi.default_rtx_state(w, h, denoise=denoise, maxDepth=3, time=1234 + frames)
+                rows, pushes = rr.run(st, frames)
+                want_rows, levels = expected_run_commands(w, h, denoise, frames)
+                assert rows == want_rows, (w, h, denoise, frames)
+                raw = bytes(st)
+                assert pushes[0] == raw
+                off = abi.RtxState.denoiseLevel.offset
+                for p, lvl in zip(pushes[1:], levels[1:]):
+                    assert p[:off] == raw[:off] and p[off + 4:] == raw[off + 4:] and int.from_bytes(p[off:off + 4], "little", signed=True) == lvl
+                # compose runs with the push constants of the last denoise level still bound (no push before it): denoiseLevel 4 when denoise > 0
+
+
 def test_environment_alias_map_matches_reference_vectors():
     """HdrSampling::createEnvironmentAccel / buildAliasmap (src/hdr_sampling.cpp:107-242, the reference's own code compiled where it
     lies) — alias, q, pdf, aliasPdf of every texel, the integral and the average: bit-exact in the oracle AND in the product's host side."""
