@@ -187,6 +187,17 @@ ORC_API int orc_scene_instance_xforms(Scene* s, float* out, int maxInstances) {
     }
   return n;
 }
+// per instance (= node) what accelstruct.cpp:132-162 decides: (VkGeometryInstanceFlagsKHR bits: 4 FORCE_OPAQUE, 1 TRIANGLE_FACING_CULL_DISABLE;
+// instanceCustomIndex; triangles) — read back from the triangle soup the intersector actually walks
+ORC_API int orc_scene_instance_flags(Scene* s, int* out, int maxInstances) {
+  const int n = (int)s->objectToWorld.size();
+  for (int i = 0; i < n && i < maxInstances; ++i) { out[3 * i] = -1; out[3 * i + 1] = -1; out[3 * i + 2] = 0; }
+  for (const auto& t : s->tris) {
+    if (t.inst < 0 || t.inst >= n || t.inst >= maxInstances) continue;
+    out[3 * t.inst] = (t.opaque ? 4 : 0) | (t.cullDisable ? 1 : 0); out[3 * t.inst + 1] = t.customIndex; out[3 * t.inst + 2] += 1;
+  }
+  return n;
+}
 ORC_API int orc_scene_texture_count(Scene* s) { return (int)s->textures.size(); }
 ORC_API int orc_renderer_set_env(Renderer* r, Environment* e) { r->env = e; return 0; }
 // RenderOutput::run over the frame rendered last: out = width*height RGBA32F at the allocation pitch

@@ -4,13 +4,16 @@
  * describes (eid_scene_desc = what nvh::GltfScene holds after the un-vendored nvpro_core import), and hands back the tables it uploads:
  * Scene::load -> createMaterialBuffer, createPuncLightBuffer (+ createPuncLightImptSampAccel), createVertexBuffer, createInstanceDataBuffer,
  * createTrigLightBuffer (+ createTrigLightImptSampAccel, alias_table.hpp), the LightBufInfo block, m_trigLightWeight / m_puncLightWeight;
- * Scene::updateCamera -> SceneCamera (history roll, jitter) with the contract's nvmath stand-ins.  The table numbering is
+ * Scene::updateCamera -> SceneCamera (history roll, jitter) with the contract's nvmath stand-ins; AccelStructure::create (src/accelstruct.cpp,
+ * called like SampleExample::loadScene does, sample_example.cpp:85) -> what it asks the builder to build: per node the instance record
+ * (transform, instanceCustomIndex, mask, flags = FORCE_OPAQUE / TRIANGLE_FACING_CULL_DISABLE rule, BLAS reference), per prim mesh the geometry.  The table numbering is
  * eid_scene_table's (include/eidola.h), so the tests compare the three sides — reference code, oracle, product — table by table.
  */
 #include "scene_shim.h"
 #include "shaders/host_device.h"      // /root/reference/shaders/host_device.h
 #define private public                 // the tables are private members of Scene
 #include "scene.hpp"                   // /root/reference/src/scene.hpp
+#include "accelstruct.hpp"             // /root/reference/src/accelstruct.hpp
 #undef private
 
 static const eidc::eid_scene_desc* g_desc;
@@ -135,3 +138,27 @@ REF_API void ref_scene_set_lookat(const float* eye, const float* center, const f
   CameraManip.setFov(fovDeg);
 }
 REF_API void ref_scene_update_camera(void* h, unsigned w, unsigned hgt) { ((RefScene*)h)->scene.updateCamera(nullptr, VkExtent2D{w, hgt}); }
+
+// AccelStructure::create on the loaded scene.  inst: rows of (instanceCustomIndex, mask, sbtRecordOffset, flags, blas index); xforms: 12 floats
+// per instance, row-major 3x4 (VkTransformMatrixKHR); blas: rows of (primitiveCount, maxVertex, vertexStride, geometry flags, vertexFormat,
+// indexType); build[0..1] = BLAS / TLAS build flags.  Returns the instance count, *nBlas the BLAS count.
+REF_API int ref_scene_accel(void* h, int* inst, float* xforms, int capInst, int* blas, int capBlas, int* nBlas, int* build) {
+  RefScene* r = (RefScene*)h;
+  AccelStructure as;
+  as.setup(nullptr, nullptr, 0u, &r->alloc);
+  as.create(r->scene.getScene(), r->scene.getBuffers(Scene::eVertex), r->scene.getBuffers(Scene::eIndex));
+  const auto& b = as.m_rtBuilder;
+  for (size_t i = 0; i < b.tlas.size() && (int)i < capInst; ++i) {
+    const VkAccelerationStructureInstanceKHR& t = b.tlas[i];
+    inst[5 * i] = (int)t.instanceCustomIndex; inst[5 * i + 1] = (int)t.mask; inst[5 * i + 2] = (int)t.instanceShaderBindingTableRecordOffset;
+    inst[5 * i + 3] = (int)t.flags; inst[5 * i + 4] = (int)(t.accelerationStructureReference - 0x1000u);
+    memcpy(xforms + 12 * i, t.transform.matrix, 48);
+  }
+  for (size_t i = 0; i < b.blas.size() && (int)i < capBlas; ++i) {
+    const auto& g = b.blas[i].asGeometry[0]; const auto& o = b.blas[i].asBuildOffsetInfo[0];
+    blas[6 * i] = (int)o.primitiveCount; blas[6 * i + 1] = (int)g.geometry.triangles.maxVertex; blas[6 * i + 2] = (int)g.geometry.triangles.vertexStride;
+    blas[6 * i + 3] = (int)g.flags; blas[6 * i + 4] = g.geometry.triangles.vertexFormat; blas[6 * i + 5] = g.geometry.triangles.indexType;
+  }
+  *nBlas = (int)b.blas.size(); build[0] = (int)b.blasFlags; build[1] = (int)b.tlasFlags;
+  return (int)b.tlas.size();
+}

@@ -110,6 +110,28 @@ inline void vkCmdPushConstants(VkCommandBuffer, VkPipelineLayout, VkFlags, uint3
 inline void vkCmdBindPipeline(VkCommandBuffer, VkPipelineBindPoint, VkPipeline p) { ShimEvent e{3, p ? p->tag : -1, 0, 0, {}}; ShimDevice::get().log.push_back(e); }
 inline void vkCmdDispatch(VkCommandBuffer, uint32_t x, uint32_t y, uint32_t z) { ShimEvent e{4, (int)x, (int)y, (int)z, {}}; ShimDevice::get().log.push_back(e); }
 
+// ---- VK_KHR_acceleration_structure names (accelstruct.cpp) -----------------------------------------------------------------------
+typedef void* VkAccelerationStructureKHR; typedef VkFlags VkGeometryInstanceFlagsKHR; typedef VkFlags VkBuildAccelerationStructureFlagsKHR;
+enum { VK_STRUCTURE_TYPE_BUFFER_DEVICE_ADDRESS_INFO = 1000244001, VK_STRUCTURE_TYPE_ACCELERATION_STRUCTURE_GEOMETRY_TRIANGLES_DATA_KHR = 1000150005,
+       VK_STRUCTURE_TYPE_ACCELERATION_STRUCTURE_GEOMETRY_KHR = 1000150006, VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET_ACCELERATION_STRUCTURE_KHR = 1000150007,
+       VK_FORMAT_R32G32B32_SFLOAT = 106, VK_INDEX_TYPE_UINT32 = 1, VK_GEOMETRY_TYPE_TRIANGLES_KHR = 0,
+       VK_GEOMETRY_OPAQUE_BIT_KHR = 1, VK_GEOMETRY_NO_DUPLICATE_ANY_HIT_INVOCATION_BIT_KHR = 2,
+       VK_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE_BIT_KHR = 1, VK_GEOMETRY_INSTANCE_FORCE_OPAQUE_BIT_KHR = 4,
+       VK_BUILD_ACCELERATION_STRUCTURE_ALLOW_COMPACTION_BIT_KHR = 2, VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR = 4,
+       VK_DESCRIPTOR_TYPE_ACCELERATION_STRUCTURE_KHR = 1000150000 };
+struct VkBufferDeviceAddressInfo { int sType; const void* pNext; VkBuffer buffer; };
+struct VkDeviceOrHostAddressConstKHR { VkDeviceAddress deviceAddress; };
+struct VkAccelerationStructureGeometryTrianglesDataKHR { int sType; const void* pNext; int vertexFormat; VkDeviceOrHostAddressConstKHR vertexData; VkDeviceSize vertexStride;
+                                                         uint32_t maxVertex; int indexType; VkDeviceOrHostAddressConstKHR indexData, transformData; };
+struct VkAccelerationStructureGeometryDataKHR { VkAccelerationStructureGeometryTrianglesDataKHR triangles; };
+struct VkAccelerationStructureGeometryKHR { int sType; const void* pNext; int geometryType; VkAccelerationStructureGeometryDataKHR geometry; VkFlags flags; };
+struct VkAccelerationStructureBuildRangeInfoKHR { uint32_t primitiveCount, primitiveOffset, firstVertex, transformOffset; };
+struct VkTransformMatrixKHR { float matrix[3][4]; };
+struct VkAccelerationStructureInstanceKHR { VkTransformMatrixKHR transform; uint32_t instanceCustomIndex : 24; uint32_t mask : 8;
+                                            uint32_t instanceShaderBindingTableRecordOffset : 24; uint32_t flags : 8; uint64_t accelerationStructureReference; };
+struct VkWriteDescriptorSetAccelerationStructureKHR { int sType; const void* pNext; uint32_t accelerationStructureCount; const VkAccelerationStructureKHR* pAccelerationStructures; };
+VkDeviceAddress vkGetBufferDeviceAddress(VkDevice, const VkBufferDeviceAddressInfo* info);   // defined after VkBuffer_T
+
 // ---- nvmath (un-vendored): contract arithmetic ---------------------------------------------------------------------------------
 namespace nvmath {
 template <class T> struct vector4;
@@ -239,6 +261,7 @@ inline void AddCamera(const nvh::CameraManipulator::Camera&) {}
 
 // ---- nvvk ----------------------------------------------------------------------------------------------------------------------
 struct VkBuffer_T { std::vector<unsigned char> bytes; ShimResource* res = nullptr; };   // a "buffer" is the host copy of what was uploaded into it
+inline VkDeviceAddress vkGetBufferDeviceAddress(VkDevice, const VkBufferDeviceAddressInfo* info) { return (VkDeviceAddress)(uintptr_t)(info->buffer ? info->buffer->bytes.data() : nullptr); }
 namespace nvvk {
 struct Image { VkImage image = nullptr; };                                // image = ShimResource* when created through createImage(info)
 struct Texture { VkImage image = nullptr; VkDescriptorImageInfo descriptor{}; };
@@ -274,9 +297,10 @@ struct CommandPool {
   void submitAndWait(VkCommandBuffer) {}
 };
 struct DescriptorSetBindings {
-  struct Binding { int binding; VkDescriptorType type; uint32_t count; VkShaderStageFlags flags; };
+  struct Binding { int binding; int type; uint32_t count; VkShaderStageFlags flags; };
   void addBinding(Binding) {}
-  VkDescriptorPool createPool(VkDevice, uint32_t) { return nullptr; }
+  VkDescriptorPool createPool(VkDevice, uint32_t = 1) { return nullptr; }
+  VkWriteDescriptorSet makeWrite(VkDescriptorSet, int, const VkWriteDescriptorSetAccelerationStructureKHR*) { return VkWriteDescriptorSet(); }
   VkDescriptorSetLayout createLayout(VkDevice) { return nullptr; }
   VkWriteDescriptorSet makeWrite(VkDescriptorSet s, int binding, const VkDescriptorBufferInfo* b) {
     ShimDevice::get().writes.push_back({(int)(intptr_t)s, binding, b && b->buffer && b->buffer->res ? b->buffer->res->id : -1, b ? b->range : 0}); return VkWriteDescriptorSet();
@@ -285,6 +309,23 @@ struct DescriptorSetBindings {
     ShimDevice::get().writes.push_back({(int)(intptr_t)s, binding, im && im->imageView ? ((ShimResource*)im->imageView)->id : -1, 0}); return VkWriteDescriptorSet();
   }
   VkWriteDescriptorSet makeWriteArray(VkDescriptorSet, int, const void*) { return VkWriteDescriptorSet(); }
+};
+// nvvk::RaytracingBuilderKHR (nvpro_core): here it only keeps what it is asked to build
+inline VkTransformMatrixKHR toTransformMatrixKHR(const nvmath::mat4f& m) {   // column-major 4x4 -> row-major 3x4
+  VkTransformMatrixKHR t;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) t.matrix[r][c] = m.m[c * 4 + r];
+  return t;
+}
+class RaytracingBuilderKHR {
+public:
+  struct BlasInput { std::vector<VkAccelerationStructureGeometryKHR> asGeometry; std::vector<VkAccelerationStructureBuildRangeInfoKHR> asBuildOffsetInfo; VkFlags flags = 0; };
+  std::vector<BlasInput> blas; VkFlags blasFlags = 0; std::vector<VkAccelerationStructureInstanceKHR> tlas; VkFlags tlasFlags = 0;
+  void setup(VkDevice, ResourceAllocator*, uint32_t) {}
+  void destroy() { blas.clear(); tlas.clear(); }
+  void buildBlas(const std::vector<BlasInput>& in, VkFlags f) { blas = in; blasFlags = f; }
+  void buildTlas(const std::vector<VkAccelerationStructureInstanceKHR>& in, VkFlags f) { tlas = in; tlasFlags = f; }
+  VkDeviceAddress getBlasDeviceAddress(uint32_t i) { return 0x1000u + i; }
+  VkAccelerationStructureKHR getAccelerationStructure() { return (VkAccelerationStructureKHR)this; }
 };
 inline VkDescriptorSet allocateDescriptorSet(VkDevice, VkDescriptorPool, VkDescriptorSetLayout) { return (VkDescriptorSet)(intptr_t)(++ShimDevice::get().nextSet); }   // sets are numbered 1, 2, ...
 }  // namespace nvvk

@@ -61,6 +61,7 @@ def lib():
             "orc_renderer_get_stats": (i32, [vp, C.POINTER(abi.FrameStats)]),
             "orc_renderer_buffer_bytes": (C.c_int64, [vp, i32]), "orc_renderer_read": (i32, [vp, i32, vp, sz]),
             "orc_renderer_write": (i32, [vp, i32, vp, sz]),
+            "orc_scene_instance_flags": (i32, [vp, vp, i32]),
             "orc_mip_chain_average": (None, [vp, i32, i32, vp]), "orc_tone_exposure": (None, [vp, vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
@@ -114,6 +115,7 @@ def ref_scene_lib():
         L.ref_scene_weights.restype, L.ref_scene_weights.argtypes = None, [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_scene_set_lookat.restype, L.ref_scene_set_lookat.argtypes = None, [C.c_void_p] * 3 + [C.c_float]
         L.ref_scene_update_camera.restype, L.ref_scene_update_camera.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
+        L.ref_scene_accel.restype, L.ref_scene_accel.argtypes = C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_renderer_create.restype, L.ref_renderer_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
         L.ref_renderer_update.restype, L.ref_renderer_update.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
         L.ref_renderer_destroy.restype, L.ref_renderer_destroy.argtypes = None, [C.c_void_p]
@@ -153,6 +155,15 @@ class RefScene:
 
     def update_camera(self, w, h):
         self.L.ref_scene_update_camera(self._h, w, h)
+
+    def accel(self, max_inst=4096, max_blas=4096):
+        """AccelStructure::create (src/accelstruct.cpp) on this scene -> (instances (n, 5) int32: instanceCustomIndex, mask, sbt offset, flags,
+        BLAS index; transforms (n, 3, 4) float32 row-major; blas (m, 6) int32: primitiveCount, maxVertex, vertexStride, geometry flags,
+        vertexFormat, indexType; (BLAS build flags, TLAS build flags))."""
+        inst = np.zeros((max_inst, 5), np.int32); xf = np.zeros((max_inst, 3, 4), np.float32); blas = np.zeros((max_blas, 6), np.int32)
+        nb, build = C.c_int(), (C.c_int * 2)()
+        n = self.L.ref_scene_accel(self._h, inst.ctypes.data, xf.ctypes.data, max_inst, blas.ctypes.data, max_blas, C.byref(nb), build)
+        return inst[:n].copy(), xf[:n].copy(), blas[:nb.value].copy(), (build[0], build[1])
 
     def __del__(self):
         if getattr(self, "_h", None):

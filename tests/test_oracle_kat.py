@@ -297,6 +297,39 @@ def test_host_tables_match_reference_scene_cpp():
                 assert cam.tobytes() == want.tobytes(), (name, tag, "camera step %d" % k)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_instances_match_reference_accelstruct_cpp():
+    """The reference's OWN src/accelstruct.cpp (compiled where it lies; nvvk::RaytracingBuilderKHR stands in and keeps what it is asked to
+    build), called like SampleExample::loadScene does: per node the instance record — instanceCustomIndex = prim mesh, mask 0xFF, flags by
+    the FORCE_OPAQUE / TRIANGLE_FACING_CULL_DISABLE rule of accelstruct.cpp:145-149, the node's world matrix as a 3x4 transform — and per prim
+    mesh the geometry (indexCount / 3 triangles, 32-byte vertex stride, NO_DUPLICATE_ANY_HIT): what the oracle's intersector walks."""
+    import ctypes as C
+    import ref_fn_inputs as fi
+    from eidola_b200 import scenes
+    assert ol.ref_scene_lib() is not None
+    for name in fi.SCENE_TABLE_MAKERS:
+        arrays = getattr(scenes, name)()
+        inst, xf, blas, build = ol.RefScene(arrays).accel()
+        osc = ol.OracleScene(); osc.load_arrays(arrays)
+        n = len(arrays.nodes)
+        assert len(inst) == n and len(blas) == len(arrays.prim_meshes)
+        flags = np.zeros((n, 3), np.int32)
+        assert ol.lib().orc_scene_instance_flags(osc._h, flags.ctypes.data_as(C.c_void_p), n) == n
+        oxf = np.zeros((n, 24), np.float32)
+        assert ol.lib().orc_scene_instance_xforms(osc._h, oxf.ctypes.data_as(C.c_void_p), n) == n
+        assert build == (4 | 2, 4)                                  # PREFER_FAST_TRACE | ALLOW_COMPACTION, PREFER_FAST_TRACE
+        for i in range(n):
+            custom, mask, sbt, fl, blas_idx = (int(v) for v in inst[i])
+            assert (custom, mask, sbt, blas_idx) == (arrays.nodes[i]["primMesh"], 0xFF, 0, arrays.nodes[i]["primMesh"]), (name, i)
+            assert (fl, custom) == (int(flags[i, 0]), int(flags[i, 1])), (name, i)
+            assert int(blas[blas_idx, 0]) == int(flags[i, 2]), (name, i)                                # triangles of the instance
+            o2w = oxf[i, :12].reshape(4, 3)                                                             # columns of objectToWorld
+            assert xf[i].T.tobytes() == o2w.tobytes(), (name, i)                                        # row-major 3x4 == the same columns
+        for k, pm in enumerate(arrays.prim_meshes):
+            assert tuple(int(v) for v in blas[k]) == (pm["indexCount"] // 3, pm["vertexCount"], 32, 2, 106, 1), (name, k)   # R32G32B32_SFLOAT, UINT32
+    assert any(int(f) != 4 for f in flags[:, 0])                    # the last scene (alpha) really has non-opaque instances
+
+
 def expected_run_commands(w, h, denoise, frames):
     """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
     it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
