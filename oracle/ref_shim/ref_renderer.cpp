@@ -14,6 +14,15 @@
 #undef private
 
 #define REF_API extern "C" __attribute__((visibility("default")))
+#include "../_ref/gen/defaults.hpp"   // the reference's own initialisers of m_rtxState, m_sunAndSky (sample_example.hpp:154-203), m_tm, m_depthTm (render_output.hpp:44-60)
+// which: 0 RtxState, 1 SunAndSky, 2 Tonemapper m_tm, 3 Tonemapper m_depthTm -> bytes copied
+REF_API int ref_default_state(int which, void* out, int cap) {
+  const void* p = which == 0 ? (const void*)&ref_m_rtxState : which == 1 ? (const void*)&ref_m_sunAndSky : which == 2 ? (const void*)&ref_m_tm : which == 3 ? (const void*)&ref_m_depthTm : nullptr;
+  const int n = which == 0 ? (int)sizeof(RtxState) : which == 1 ? (int)sizeof(SunAndSky) : (int)sizeof(Tonemapper);
+  if (!p || cap < n) return -1;
+  memcpy(out, p, n);
+  return n;
+}
 struct RefRenderer { nvvk::ResourceAllocator alloc; Renderer r; };
 
 REF_API void* ref_renderer_create(unsigned w, unsigned h) {

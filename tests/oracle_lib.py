@@ -116,6 +116,7 @@ def ref_scene_lib():
         L.ref_scene_set_lookat.restype, L.ref_scene_set_lookat.argtypes = None, [C.c_void_p] * 3 + [C.c_float]
         L.ref_scene_update_camera.restype, L.ref_scene_update_camera.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
         L.ref_scene_accel.restype, L.ref_scene_accel.argtypes = C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_default_state.restype, L.ref_default_state.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int]
         L.ref_renderer_create.restype, L.ref_renderer_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
         L.ref_renderer_update.restype, L.ref_renderer_update.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
         L.ref_renderer_destroy.restype, L.ref_renderer_destroy.argtypes = None, [C.c_void_p]
@@ -169,6 +170,15 @@ class RefScene:
         if getattr(self, "_h", None):
             self.L.ref_scene_destroy(self._h)
             self._h = None
+
+
+def ref_default_state(which):
+    """Bytes of the reference's own default objects: 0 RtxState m_rtxState, 1 SunAndSky m_sunAndSky (sample_example.hpp:154-203), 2 Tonemapper m_tm,
+    3 Tonemapper m_depthTm (render_output.hpp:44-60) — their initialisers lifted from the headers and compiled (oracle/ref_shim/defaults_prep.py)."""
+    b = np.zeros(256, np.uint8)
+    n = ref_scene_lib().ref_default_state(which, b.ctypes.data, 256)
+    assert n > 0
+    return b[:n].tobytes()
 
 
 class RefRenderer:

@@ -330,6 +330,31 @@ def test_instances_match_reference_accelstruct_cpp():
     assert any(int(f) != 4 for f in flags[:, 0])                    # the last scene (alpha) really has non-opaque instances
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_default_states_match_reference_initialisers(tmp_path):
+    """The defaults every test, the bench and a drop-in host start from — abi.default_rtx_state / default_sun_and_sky / default_tonemapper and the
+    C++ mirror's eidola::defaultRtxState — against the reference's OWN initialisers of SampleExample::m_rtxState, m_sunAndSky
+    (sample_example.hpp:154-203) and RenderOutput::m_tm / m_depthTm (render_output.hpp:44-60), lifted from the headers and compiled."""
+    import shutil
+    import subprocess
+    from eidola_b200 import abi
+    assert ol.ref_scene_lib() is not None
+    assert bytes(abi.default_rtx_state(0, 0)) == ol.ref_default_state(0)
+    assert bytes(abi.default_sun_and_sky(in_use=0)) == ol.ref_default_state(1)
+    assert bytes(abi.default_tonemapper()) == ol.ref_default_state(2)
+    depth = np.frombuffer(ol.ref_default_state(3), np.float32)
+    assert depth[:3].tolist() == [0.0, np.float32(2.2), 0.0] and not depth[3:].any()          # what test_display_pass_post_frag uses for eDepth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "cis-565-final-vr-raytracer_b200")
+    src = tmp_path / "d.cpp"
+    src.write_text('#include <cstdio>\n#include "eidola.hpp"\nint main() { RtxState s = eidola::defaultRtxState(0, 0); fwrite(&s, sizeof s, 1, stdout); return 0; }\n')
+    exe = str(tmp_path / "d")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    subprocess.check_call([cxx, "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"), str(src), "-L", pkg, "-leidola", "-o", exe])
+    out = subprocess.run([exe], env=dict(os.environ, LD_LIBRARY_PATH=pkg), capture_output=True).stdout
+    assert out == ol.ref_default_state(0)
+
+
 def expected_run_commands(w, h, denoise, frames):
     """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
     it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
