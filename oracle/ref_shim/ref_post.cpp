@@ -81,3 +81,21 @@ void ref_post_run(const RtxState* st, const SceneCamera* cam, int allocW, int al
   rtxState = *st;
   dispatch(W, H, [] { cp::main(); });
 }
+
+// ONE dispatch of a post stage, as a command buffer replays it: stage = the shader tag of ref_renderer.cpp (5 denoise_direct, 6 denoise_indirect,
+// 7 compose), st = the push constants bound at that point, gx x gy work groups of 8 x 8 invocations (vkCmdDispatch(gx, gy, 1)).
+extern "C" __attribute__((visibility("default")))
+int ref_post_dispatch(int stage, const RtxState* st, const SceneCamera* cam, int allocW, int allocH, int gx, int gy, void* gbuffer, void* direct,
+                      void* indirect, void* dirA, void* dirB, void* indA, void* indB) {
+  thisGbuffer = uimage2D{(uvec4*)gbuffer, allocW, allocH, allocW};
+  auto img = [&](void* p) { return image2D{(vec4*)p, allocW, allocH, allocW}; };
+  thisDirectResultImage = img(direct); thisIndirectResultImage = img(indirect);
+  denoiseDirTempA = img(dirA); denoiseDirTempB = img(dirB); denoiseIndTempA = img(indA); denoiseIndTempB = img(indB);
+  sceneCamera = *cam;
+  rtxState = *st;
+  void (*fn)() = stage == 5 ? (void (*)())[] { dd::main(); } : stage == 6 ? (void (*)())[] { di::main(); } : stage == 7 ? (void (*)())[] { cp::main(); } : nullptr;
+  if (!fn) return -1;
+  for (int y = 0; y < gy * 8; ++y)
+    for (int x = 0; x < gx * 8; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; fn(); }
+  return 0;
+}

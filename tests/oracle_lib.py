@@ -90,6 +90,7 @@ def ref():
         L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_trace_run.restype, L.ref_trace_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_post_run.restype, L.ref_post_run.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.ref_post_dispatch.restype, L.ref_post_dispatch.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 7
         L.ref_display_run.restype, L.ref_display_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.ref_scene_set.restype, L.ref_scene_set.argtypes = None, [C.c_void_p] * 10 + [C.c_uint32, C.c_uint32]
         L.ref_ctx_fn.restype, L.ref_ctx_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -302,7 +303,9 @@ class RefTracer:
         self.direct, self.indirect, self.indA = (np.zeros((h, w, 4), np.float32) for _ in range(3))
         self.rays = np.zeros(2, np.uint64)
 
-    def run(self, st, frame, direct=True, indirect=True):
+    def run(self, st, frame, direct=True, indirect=True, bufs=None):
+        """bufs (replay of the reference's own command sequence, test_reference_renderer_replay...): dict of arrays thisG, lastG, motion,
+        thisDR, lastDR, tempDR, thisIR, lastIR, direct, indirect, indA bound explicitly instead of this object's ping-pong."""
         abi, s = self.abi, (frame + 1) % 2
         cam = np.ascontiguousarray(self.osc.table(abi.TABLE_CAMERA))
         b = RefTraceBind()
@@ -319,6 +322,9 @@ class RefTracer:
         b.direct, b.indirect, b.indA = self.direct.ctypes.data, self.indirect.ctypes.data, self.indA.ctypes.data
         b.instanceXforms = self.xforms.ctypes.data
         b.tempDR = self.tempDR.ctypes.data
+        if bufs is not None:
+            for k in ("thisG", "lastG", "motion", "thisDR", "lastDR", "tempDR", "thisIR", "lastIR", "direct", "indirect", "indA"):
+                setattr(b, k, bufs[k].ctypes.data)
         self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
         return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
                 "direct": self.direct, "ind_tmp_a": self.indA}

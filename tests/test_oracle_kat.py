@@ -355,6 +355,65 @@ def test_default_states_match_reference_initialisers(tmp_path):
     assert out == ol.ref_default_state(0)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_reference_renderer_replay_matches_oracle_frames():
+    """The reference end to end on the CPU: its OWN src/renderer.cpp decides what a frame executes — which descriptor set, which push
+    constants, which pipeline, how many work groups (recorded by the stand-in device, ref_renderer.cpp) — and every recorded dispatch is
+    replayed with the reference's OWN shader text (ref_trace.cpp / ref_post.cpp) on the resources its descriptor sets name.  Frame after
+    frame, every buffer equals the oracle's (whose Renderer::run restates the same schedule by hand): G-buffers of both parities, motion,
+    reservoirs, tempDirectResv, denoise temporaries, both result images."""
+    import ctypes as C
+    import common
+    from eidola_b200 import abi, scenes
+    R = ol.ref()
+    assert R is not None and ol.ref_scene_lib() is not None
+    for maker_name, size, frames, over in (("cornell_scene", (64, 40), 3, dict(maxDepth=3)), ("small_room", (50, 34), 3, dict(maxDepth=2, ReSTIRState=abi.eSpatiotemporal)),
+                                           ("cube_scene", (48, 32), 2, dict(maxDepth=2, denoise=0))):
+        w, h = size
+        arrays = getattr(scenes, maker_name)()
+        osc = ol.OracleScene(); osc.load_arrays(arrays)
+        orr = ol.OracleRenderer(osc, size); orr.set_env_constant((0.0, 0.0, 0.0))
+        rt = ol.RefTracer(R, abi, arrays, osc, size)                   # scene tables + intersector binding of the trace stages
+        rr = ol.RefRenderer(w, h)
+        res = rr.resources()
+        store = {}                                                      # resource id -> array, zero-initialised like the contract's history
+        for role, (rid, kind, nbytes, _, _, _) in res.items():
+            store[rid] = np.zeros(nbytes, np.uint8)
+        direct, indirect = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)     # RenderOutput's result images (S_OUT)
+        wiring = rr.wiring()
+        osc.update_camera(w, h)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(w, h)
+            st = common.frame_state(w, h, info, f, **over)
+            orr.run(st, f)
+            rows, pushes = rr.run(st, f)
+            cur_set = cur_push = cur_pipe = None
+            for what, a, b, c in rows:
+                if what == 1: cur_set = c
+                elif what == 2: cur_push = abi.RtxState.from_buffer_copy(pushes[c])
+                elif what == 3: cur_pipe = a
+                elif what == 4:
+                    bound = lambda binding: store[wiring[(cur_set, binding)][0]]
+                    if cur_pipe in (1, 4):                              # direct_stage / indirect_stage
+                        assert (a, b) == ((cur_push.size.x // (1 if cur_pipe == 1 else 2) + 7) // 8, (cur_push.size.y // (1 if cur_pipe == 1 else 2) + 7) // 8)
+                        rt.run(cur_push, f, direct=cur_pipe == 1, indirect=cur_pipe == 4,
+                               bufs=dict(lastG=bound(0), thisG=bound(1), lastDR=bound(2), thisDR=bound(3), tempDR=bound(4), lastIR=bound(5), thisIR=bound(6),
+                                         motion=bound(8), direct=direct, indirect=indirect, indA=bound(11)))
+                    else:                                               # denoise_direct / denoise_indirect / compose
+                        cam = np.ascontiguousarray(osc.table(abi.TABLE_CAMERA))
+                        assert R.ref_post_dispatch(cur_pipe, C.addressof(cur_push), cam.ctypes.data, w, h, a, b, bound(1).ctypes.data, direct.ctypes.data,
+                                                   indirect.ctypes.data, bound(9).ctypes.data, bound(10).ctypes.data, bound(11).ctypes.data, bound(12).ctypes.data) == 0
+            s = (f + 1) % 2 + 1                                         # the set the reference bound this frame
+            for which, binding in ((abi.BUF_THIS_GBUFFER, 1), (abi.BUF_LAST_GBUFFER, 0), (abi.BUF_MOTION, 8), (abi.BUF_THIS_DIRECT_RESV, 3), (abi.BUF_LAST_DIRECT_RESV, 2),
+                                   (abi.BUF_THIS_INDIRECT_RESV, 6), (abi.BUF_LAST_INDIRECT_RESV, 5), (abi.BUF_TEMP_DIRECT_RESV, 4), (abi.BUF_DENOISE_DIR_A, 9),
+                                   (abi.BUF_DENOISE_DIR_B, 10), (abi.BUF_DENOISE_IND_A, 11), (abi.BUF_DENOISE_IND_B, 12)):
+                got = store[wiring[(s, binding)][0]]
+                assert got.tobytes() == np.ascontiguousarray(orr.read(which)).view(np.uint8).reshape(-1).tobytes(), (maker_name, f, which)
+            assert direct.tobytes() == orr.read(abi.BUF_DIRECT).tobytes() and indirect.tobytes() == orr.read(abi.BUF_INDIRECT).tobytes(), (maker_name, f)
+            assert direct[..., :3].max() > 0.0 and store[wiring[(s, 3)][0]].any() and store[wiring[(s, 6)][0]].any()      # (the frames are not trivially empty)
+
+
 def expected_run_commands(w, h, denoise, frames):
     """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
     it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
