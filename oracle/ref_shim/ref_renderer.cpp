@@ -6,11 +6,14 @@
  * per frame the exact command sequence of Renderer::run (renderer.cpp:154-206): descriptor set bound, every push-constant upload
  * (the RtxState bytes), every pipeline bind (shader tag 1..7 = direct_stage, direct_gen, direct_reuse, indirect_stage, denoise_direct,
  * denoise_indirect, compose), every dispatch with its group counts.  The tests hold the oracle's and the product's schedule against it.
+ * The same for src/render_output.cpp (the display pass): the four result images it allocates, how its two S_OUT descriptor sets name them,
+ * what RenderOutput::run pushes / binds / draws (tag 9 = post.frag) and which mip chains RenderOutput::genMipmap asks for.
  */
 #include "scene_shim.h"
 #include "shaders/host_device.h"      // /root/reference/shaders/host_device.h
 #define private public
 #include "renderer.hpp"                // /root/reference/src/renderer.hpp
+#include "render_output.hpp"           // /root/reference/src/render_output.hpp
 #undef private
 
 #define REF_API extern "C" __attribute__((visibility("default")))
@@ -84,6 +87,54 @@ REF_API int ref_renderer_run(void* h, const void* state, int frames, int* rows, 
       if ((np + 1) * (int)sizeof(RtxState) <= capPush && e.data.size() == sizeof(RtxState)) memcpy(pushBytes + np * sizeof(RtxState), e.data.data(), sizeof(RtxState));
       ++np;
     }
+    ++n;
+  }
+  return n;
+}
+
+// ---- RenderOutput (src/render_output.cpp) --------------------------------------------------------------------------------------
+struct RefOutput { nvvk::ResourceAllocator alloc; RenderOutput o; };
+REF_API void* ref_output_create(unsigned w, unsigned h) {
+  RefOutput* r = new RefOutput;
+  r->o.setup(nullptr, nullptr, 0u, &r->alloc, 1u);
+  r->o.create(VkExtent2D{w, h}, nullptr);
+  return r;
+}
+REF_API void ref_output_destroy(void* h) { delete (RefOutput*)h; }
+// resource ids of m_directResult[0], [1], m_indirectResult[0], [1] (details through ref_renderer_resource; out[4..7] = their mip counts)
+REF_API void ref_output_roles(void* h, int* out8) {
+  RenderOutput& o = ((RefOutput*)h)->o;
+  const int ids[4] = {resId(o.m_directResult[0].descriptor.imageView), resId(o.m_directResult[1].descriptor.imageView),
+                      resId(o.m_indirectResult[0].descriptor.imageView), resId(o.m_indirectResult[1].descriptor.imageView)};
+  for (int i = 0; i < 4; ++i) { out8[i] = ids[i]; out8[4 + i] = ids[i] >= 0 ? ShimDevice::get().resources[ids[i]]->mips : -1; }
+}
+static int outSetNumber(const RenderOutput& o, int handle) { return handle == (int)(intptr_t)o.m_postDescSet[0] ? 1 : handle == (int)(intptr_t)o.m_postDescSet[1] ? 2 : -1; }
+// the 12 descriptor writes of createPostDescriptor: rows of (set number 1|2, binding of OutputBindings, resource id)
+REF_API int ref_output_wiring(void* h, int* out, int capRows) {
+  const RenderOutput& o = ((RefOutput*)h)->o;
+  auto& w = ShimDevice::get().writes;
+  int n = 0;
+  for (const auto& x : w) {
+    const int sn = outSetNumber(o, x.set);
+    if (sn < 0 || n >= capRows) continue;
+    out[3 * n] = sn; out[3 * n + 1] = x.binding; out[3 * n + 2] = x.resource; ++n;
+  }
+  return n;
+}
+// RenderOutput::genMipmap (when genMips) then RenderOutput::run: rows of (what, a, b, c) — 5 generate mipmaps (resource id, levels, layers), 2 push
+// (offset, size, 0), 3 bind pipeline (tag), 1 bind sets (first, count, set number), 6 draw (vertices, instances, first) — and the pushed bytes
+REF_API int ref_output_run(void* h, const void* state, float zoom, float ratioX, float ratioY, int frames, int genMips, int* rows, int capRows, unsigned char* push, int capPush) {
+  auto& d = ShimDevice::get();
+  d.log.clear();
+  RenderOutput& o = ((RefOutput*)h)->o;
+  if (genMips) o.genMipmap(nullptr);
+  o.run(nullptr, *(const RtxState*)state, zoom, vec2(ratioX, ratioY), frames);
+  int n = 0;
+  for (const ShimEvent& e : d.log) {
+    if (n >= capRows) break;
+    rows[4 * n] = e.what; rows[4 * n + 1] = e.a; rows[4 * n + 2] = e.b; rows[4 * n + 3] = e.c;
+    if (e.what == 1) rows[4 * n + 3] = outSetNumber(o, e.c);
+    if (e.what == 2 && (int)e.data.size() <= capPush) memcpy(push, e.data.data(), e.data.size());
     ++n;
   }
   return n;

@@ -43,7 +43,10 @@ typedef void* VkDescriptorSet; typedef uint64_t VkDeviceSize; typedef uint32_t V
 struct VkExtent2D { uint32_t width, height; };
 typedef struct VkPipeline_T* VkPipeline; typedef void* VkPipelineLayout; typedef void* VkShaderModule;
 struct VkPipeline_T { int tag; };                                       // a pipeline is the tag of the shader it was created from
-enum VkPipelineBindPoint { VK_PIPELINE_BIND_POINT_COMPUTE = 1 };
+enum VkPipelineBindPoint { VK_PIPELINE_BIND_POINT_GRAPHICS = 0, VK_PIPELINE_BIND_POINT_COMPUTE = 1 };
+typedef void* VkRenderPass;
+enum { VK_SHADER_STAGE_VERTEX_BIT = 1, VK_CULL_MODE_NONE = 0 };
+#define LABEL_SCOPE_VK(cmd) do { } while (0)
 enum VkImageLayout { VK_IMAGE_LAYOUT_UNDEFINED = 0, VK_IMAGE_LAYOUT_GENERAL = 1 };
 enum { VK_IMAGE_USAGE_STORAGE_BIT = 8, VK_IMAGE_USAGE_COLOR_ATTACHMENT_BIT = 0x10 };
 struct VkPushConstantRange { VkFlags stageFlags; uint32_t offset, size; };
@@ -52,7 +55,7 @@ struct VkPipelineShaderStageCreateInfo { int sType; const void* pNext; VkFlags f
 struct VkComputePipelineCreateInfo { int sType; const void* pNext; VkFlags flags; VkPipelineShaderStageCreateInfo stage; VkPipelineLayout layout; VkPipeline basePipelineHandle; int basePipelineIndex; };
 enum { VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO = 18, VK_STRUCTURE_TYPE_COMPUTE_PIPELINE_CREATE_INFO = 29, VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO = 30 };
 // ---- the recording "device": what a command buffer executes and which resource each descriptor names (renderer.cpp) -------------
-struct ShimResource { int kind; int id; uint64_t bytes; uint32_t width, height; int format; };      // kind 0 = buffer, 1 = image
+struct ShimResource { int kind; int id; uint64_t bytes; uint32_t width, height; int format; int mips; };      // kind 0 = buffer, 1 = image
 struct ShimEvent { int what; int a, b, c; std::vector<unsigned char> data; };                        // see ref_renderer.cpp
 struct ShimDevice {
   std::vector<std::unique_ptr<ShimResource>> resources;
@@ -60,14 +63,14 @@ struct ShimDevice {
   struct Write { int set, binding, resource; uint64_t range; };
   std::vector<Write> writes;
   int nextSet = 0;
-  ShimResource* add(int kind, uint64_t bytes, uint32_t w, uint32_t h, int format) { resources.emplace_back(new ShimResource{kind, (int)resources.size(), bytes, w, h, format}); return resources.back().get(); }
+  ShimResource* add(int kind, uint64_t bytes, uint32_t w, uint32_t h, int format, int mips = 1) { resources.emplace_back(new ShimResource{kind, (int)resources.size(), bytes, w, h, format, mips}); return resources.back().get(); }
   static ShimDevice& get() { static ShimDevice d; return d; }
 };
 enum VkStructureType { VK_STRUCTURE_TYPE_SAMPLER_CREATE_INFO = 31, VK_STRUCTURE_TYPE_BUFFER_MEMORY_BARRIER = 44 };
 enum VkFilter { VK_FILTER_NEAREST = 0, VK_FILTER_LINEAR = 1 };
 enum VkSamplerMipmapMode { VK_SAMPLER_MIPMAP_MODE_NEAREST = 0, VK_SAMPLER_MIPMAP_MODE_LINEAR = 1 };
 enum VkSamplerAddressMode { VK_SAMPLER_ADDRESS_MODE_REPEAT = 0, VK_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT = 1, VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE = 2 };
-enum VkFormat { VK_FORMAT_R8G8B8A8_UNORM = 37, VK_FORMAT_B8G8R8A8_UNORM = 44, VK_FORMAT_R16G16_SINT = 82, VK_FORMAT_R16G16_SFLOAT = 83, VK_FORMAT_R32G32B32A32_UINT = 107, VK_FORMAT_R32G32B32A32_SFLOAT = 109 };
+enum VkFormat { VK_FORMAT_X8_D24_UNORM_PACK32 = 125, VK_FORMAT_R8G8B8A8_UNORM = 37, VK_FORMAT_B8G8R8A8_UNORM = 44, VK_FORMAT_R16G16_SINT = 82, VK_FORMAT_R16G16_SFLOAT = 83, VK_FORMAT_R32G32B32A32_UINT = 107, VK_FORMAT_R32G32B32A32_SFLOAT = 109 };
 enum VkDescriptorType { VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER = 1, VK_DESCRIPTOR_TYPE_STORAGE_IMAGE = 3, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER = 6, VK_DESCRIPTOR_TYPE_STORAGE_BUFFER = 7 };
 enum { VK_BUFFER_USAGE_TRANSFER_DST_BIT = 2, VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT = 0x10, VK_BUFFER_USAGE_STORAGE_BUFFER_BIT = 0x20,
        VK_BUFFER_USAGE_SHADER_DEVICE_ADDRESS_BIT = 0x20000, VK_BUFFER_USAGE_ACCELERATION_STRUCTURE_BUILD_INPUT_READ_ONLY_BIT_KHR = 0x80000,
@@ -108,6 +111,7 @@ inline void vkCmdPushConstants(VkCommandBuffer, VkPipelineLayout, VkFlags, uint3
   ShimEvent e{2, (int)offset, (int)size, 0, std::vector<unsigned char>((const unsigned char*)data, (const unsigned char*)data + size)}; ShimDevice::get().log.push_back(e);
 }
 inline void vkCmdBindPipeline(VkCommandBuffer, VkPipelineBindPoint, VkPipeline p) { ShimEvent e{3, p ? p->tag : -1, 0, 0, {}}; ShimDevice::get().log.push_back(e); }
+inline void vkCmdDraw(VkCommandBuffer, uint32_t vertices, uint32_t instances, uint32_t firstVertex, uint32_t firstInstance) { ShimEvent e{6, (int)vertices, (int)instances, (int)(firstVertex + firstInstance), {}}; ShimDevice::get().log.push_back(e); }
 inline void vkCmdDispatch(VkCommandBuffer, uint32_t x, uint32_t y, uint32_t z) { ShimEvent e{4, (int)x, (int)y, (int)z, {}}; ShimDevice::get().log.push_back(e); }
 
 // ---- VK_KHR_acceleration_structure names (accelstruct.cpp) -----------------------------------------------------------------------
@@ -267,12 +271,24 @@ struct Image { VkImage image = nullptr; };                                // ima
 struct Texture { VkImage image = nullptr; VkDescriptorImageInfo descriptor{}; };
 struct Buffer { VkBuffer buffer = nullptr; };
 inline VkDeviceAddress getBufferDeviceAddress(VkDevice, VkBuffer b) { return (VkDeviceAddress)(uintptr_t)(b ? b->bytes.data() : nullptr); }   // the shaders' buffer_reference
-inline VkImageCreateInfo makeImage2DCreateInfo(VkExtent2D e, VkFormat f = VK_FORMAT_R8G8B8A8_UNORM, VkFlags = 0, bool = false) { return VkImageCreateInfo{e, f, 1}; }
+// nvvk::mipLevels (nvpro_core): floor(log2(max(w, h))) + 1 — contract
+inline uint32_t mipLevels(VkExtent2D e) { uint32_t m = e.width > e.height ? e.width : e.height, n = 1; while (m > 1) { m >>= 1; ++n; } return n; }
+inline VkImageCreateInfo makeImage2DCreateInfo(VkExtent2D e, VkFormat f = VK_FORMAT_R8G8B8A8_UNORM, VkFlags = 0, bool mipmaps = false) { return VkImageCreateInfo{e, f, mipmaps ? mipLevels(e) : 1u}; }
+inline VkFormat findDepthFormat(VkPhysicalDevice) { return VK_FORMAT_X8_D24_UNORM_PACK32; }
 inline void cmdBarrierImageLayout(VkCommandBuffer, VkImage, VkImageLayout, VkImageLayout) {}
 inline VkShaderModule createShaderModule(VkDevice, const uint32_t* code, size_t) { return (VkShaderModule)(intptr_t)code[0]; }   // the stand-in "SPIR-V" is one word: the shader's tag
 struct ProfilerVK {};
+struct GraphicsPipelineGeneratorCombined {            // nvvk/pipeline_vk.hpp: the pipeline is the tag of its fragment shader
+  struct { int cullMode = 0; } rasterizationState;
+  int fragTag = -1;
+  GraphicsPipelineGeneratorCombined(VkDevice, VkPipelineLayout, VkRenderPass) {}
+  void addShader(const std::vector<uint32_t>& code, int stage) { if (stage == VK_SHADER_STAGE_FRAGMENT_BIT && !code.empty()) fragTag = (int)code[0]; }
+  VkPipeline createPipeline() { return new VkPipeline_T{fragTag}; }
+};
 inline VkImageViewCreateInfo makeImageViewCreateInfo(VkImage i, const VkImageCreateInfo&) { return VkImageViewCreateInfo{i}; }
-inline void cmdGenerateMipmaps(...) {}
+inline void cmdGenerateMipmaps(VkCommandBuffer, VkImage image, VkFormat, VkExtent2D size, uint32_t levels, uint32_t layers = 1, VkImageLayout = VK_IMAGE_LAYOUT_GENERAL) {
+  ShimEvent e{5, image ? ((ShimResource*)image)->id : -1, (int)levels, (int)layers, {}}; (void)size; ShimDevice::get().log.push_back(e);
+}
 class ResourceAllocator {
 public:
   std::vector<std::unique_ptr<VkBuffer_T>> owned;
@@ -281,9 +297,9 @@ public:
   void destroy(Image&) {}
   void destroy(Buffer&) {}
   Image createImage(VkCommandBuffer, VkDeviceSize, const void*, const VkImageCreateInfo&) { return Image(); }
-  Image createImage(const VkImageCreateInfo& ci) { const uint64_t texel = ci.format == VK_FORMAT_R16G16_SINT || ci.format == VK_FORMAT_R16G16_SFLOAT ? 4 : 16; return Image{(VkImage)ShimDevice::get().add(1, texel * ci.extent.width * ci.extent.height, ci.extent.width, ci.extent.height, (int)ci.format)}; }
+  Image createImage(const VkImageCreateInfo& ci) { const uint64_t texel = ci.format == VK_FORMAT_R16G16_SINT || ci.format == VK_FORMAT_R16G16_SFLOAT ? 4 : 16; return Image{(VkImage)ShimDevice::get().add(1, texel * ci.extent.width * ci.extent.height, ci.extent.width, ci.extent.height, (int)ci.format, (int)ci.mipLevels)}; }
   Texture createTexture(const Image& im, const VkImageViewCreateInfo& iv) { Texture t; t.image = im.image; t.descriptor.imageView = (VkImageView)iv.image; return t; }
-  Texture createTexture(const Image&, const VkImageViewCreateInfo&, const VkSamplerCreateInfo&) { return Texture(); }
+  Texture createTexture(const Image& im, const VkImageViewCreateInfo& iv, const VkSamplerCreateInfo&) { Texture t; t.image = im.image; t.descriptor.imageView = (VkImageView)iv.image; return t; }
   Texture createTexture(VkCommandBuffer, VkDeviceSize, const void*, const VkImageCreateInfo&, const VkSamplerCreateInfo&) { return Texture(); }
   template <class T> Buffer createBuffer(VkCommandBuffer, const std::vector<T>& v, VkFlags) { return make(v.data(), v.size() * sizeof(T)); }
   Buffer createBuffer(VkCommandBuffer, VkDeviceSize n, const void* p, VkFlags) { return make(p, (size_t)n); }

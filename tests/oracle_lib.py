@@ -117,6 +117,11 @@ def ref_scene_lib():
         L.ref_scene_set_lookat.restype, L.ref_scene_set_lookat.argtypes = None, [C.c_void_p] * 3 + [C.c_float]
         L.ref_scene_update_camera.restype, L.ref_scene_update_camera.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
         L.ref_scene_accel.restype, L.ref_scene_accel.argtypes = C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_output_create.restype, L.ref_output_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
+        L.ref_output_destroy.restype, L.ref_output_destroy.argtypes = None, [C.c_void_p]
+        L.ref_output_roles.restype, L.ref_output_roles.argtypes = None, [C.c_void_p, C.c_void_p]
+        L.ref_output_wiring.restype, L.ref_output_wiring.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_output_run.restype, L.ref_output_run.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.ref_default_state.restype, L.ref_default_state.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int]
         L.ref_renderer_create.restype, L.ref_renderer_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
         L.ref_renderer_update.restype, L.ref_renderer_update.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]
@@ -170,6 +175,37 @@ class RefScene:
     def __del__(self):
         if getattr(self, "_h", None):
             self.L.ref_scene_destroy(self._h)
+            self._h = None
+
+
+class RefOutput:
+    """The reference's RenderOutput (src/render_output.cpp) on the recording stand-in device."""
+
+    def __init__(self, w, h):
+        self.L = ref_scene_lib()
+        self._h = C.c_void_p(self.L.ref_output_create(w, h))
+
+    def roles(self):
+        """(resource ids of m_directResult[0], [1], m_indirectResult[0], [1]), (their mip level counts)."""
+        o = np.zeros(8, np.int32)
+        self.L.ref_output_roles(self._h, o.ctypes.data)
+        return tuple(int(v) for v in o[:4]), tuple(int(v) for v in o[4:])
+
+    def wiring(self):
+        w = np.zeros((64, 3), np.int32)
+        n = self.L.ref_output_wiring(self._h, w.ctypes.data, 64)
+        return {(int(r[0]), int(r[1])): int(r[2]) for r in w[:n]}
+
+    def run(self, state, zoom, ratio, frames, gen_mips):
+        """genMipmap (optionally) + run -> (rows (what, a, b, c), pushed bytes: Tonemapper + debugging_mode)."""
+        rows = np.zeros((32, 4), np.int32)
+        push = np.zeros(64, np.uint8)
+        n = self.L.ref_output_run(self._h, C.byref(state), float(zoom), float(ratio[0]), float(ratio[1]), frames, int(gen_mips), rows.ctypes.data, 32, push.ctypes.data, 64)
+        return [tuple(int(v) for v in r) for r in rows[:n]], push.tobytes()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_output_destroy(self._h)
             self._h = None
 
 

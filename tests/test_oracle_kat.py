@@ -414,6 +414,44 @@ def test_reference_renderer_replay_matches_oracle_frames():
             assert direct[..., :3].max() > 0.0 and store[wiring[(s, 3)][0]].any() and store[wiring[(s, 6)][0]].any()      # (the frames are not trivially empty)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_display_pass_host_side_matches_reference_render_output_cpp():
+    """The reference's OWN src/render_output.cpp on the recording stand-in device: four RGBA32F result images with a full mip chain, the two
+    S_OUT descriptor sets wired this = [i] / last = [!i] with the samplers on this, RenderOutput::run = push (m_tm — or m_depthTm in the depth
+    view — with zoom and renderingRatio overwritten, then debugging_mode), post pipeline, set (frames + 1) % 2, one 3-vertex draw, and
+    genMipmap = one chain per result image.  The recorded push constants, replayed through the reference's OWN post.frag on the oracle's result
+    images, give the oracle's display image (with the tonemapper the reference itself selected)."""
+    import ctypes as C
+    import common
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    R = ol.ref()
+    assert R is not None and ol.ref_scene_lib() is not None
+    w, h = fi.DISPLAY_SIZE
+    ro = ol.RefOutput(w, h)
+    ids, mips = ro.roles()
+    levels = int(np.floor(np.log2(max(w, h)))) + 1
+    assert len(set(ids)) == 4 and mips == (levels,) * 4
+    wiring = ro.wiring()
+    for i in (0, 1):                                                    # OutputBindings: 0 eDirectSampler, 1 eIndirectSampler, 2 / 3 eLast*, 4 / 5 eThis*
+        assert [wiring[(i + 1, b)] for b in range(6)] == [ids[i], ids[2 + i], ids[1 - i], ids[3 - i], ids[i], ids[2 + i]]
+    tm_size = C.sizeof(abi.Tonemapper)
+    for mode in (abi.eNoDebug, abi.eDirectStage, abi.eDepth):
+        orr, st, osc = ol.display_frames(scenes, abi, common, mode)
+        d, i_ = orr.read(abi.BUF_DIRECT).reshape(h, w, 4), orr.read(abi.BUF_INDIRECT).reshape(h, w, 4)
+        for frames in (0, 1):
+            rows, push = ro.run(st, 1.0, (1.0, 1.0), frames, gen_mips=True)
+            assert rows == [(5, ids[0], levels, 1), (5, ids[1], levels, 1), (5, ids[2], levels, 1), (5, ids[3], levels, 1),
+                            (2, 0, tm_size + 4, 0), (3, 9, 0, 0), (1, 0, 1, (frames + 1) % 2 + 1), (6, 3, 1, 0)]
+            tm = abi.Tonemapper.from_buffer_copy(push[:tm_size])
+            assert int.from_bytes(push[tm_size:tm_size + 4], "little", signed=True) == mode
+            base = ol.ref_default_state(3 if mode == abi.eDepth else 2)                       # m_depthTm in the depth view, else m_tm
+            want = abi.Tonemapper.from_buffer_copy(base); want.zoom = 1.0; want.renderingRatio = abi.Vec2(1.0, 1.0)
+            assert bytes(tm) == bytes(want)
+            got = ol.ref_display_run(R, tm, mode, d, i_)                                      # the reference's post.frag with the reference's push constants
+            assert common.same_bits_or_both_nan(got, orr.run_output(tm, st)), (mode, frames)
+
+
 def expected_run_commands(w, h, denoise, frames):
     """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
     it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
