@@ -26,6 +26,13 @@ REF_API int ref_default_state(int which, void* out, int cap) {
   memcpy(out, p, n);
   return n;
 }
+// SampleExample::loadScene / loadEnvironmentHdr's derived RtxState fields (sample_example.cpp:87, 104-105), the lifted statements: out = lightLuminIntegInv,
+// fireflyClampThreshold, envMapLuminIntegInv
+REF_API void ref_glue_state(float trigWeight, float puncWeight, float envIntegral, float* out3) {
+  RtxState st = ref_m_rtxState;
+  ref_glue(st, RefGlueScene{trigWeight, puncWeight}, RefGlueSky{envIntegral});
+  out3[0] = st.lightLuminIntegInv; out3[1] = st.fireflyClampThreshold; out3[2] = st.envMapLuminIntegInv;
+}
 struct RefRenderer { nvvk::ResourceAllocator alloc; Renderer r; };
 
 REF_API void* ref_renderer_create(unsigned w, unsigned h) {

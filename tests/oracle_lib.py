@@ -122,6 +122,7 @@ def ref_scene_lib():
         L.ref_output_roles.restype, L.ref_output_roles.argtypes = None, [C.c_void_p, C.c_void_p]
         L.ref_output_wiring.restype, L.ref_output_wiring.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_output_run.restype, L.ref_output_run.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.ref_glue_state.restype, L.ref_glue_state.argtypes = None, [C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.ref_default_state.restype, L.ref_default_state.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int]
         L.ref_renderer_create.restype, L.ref_renderer_create.argtypes = C.c_void_p, [C.c_uint, C.c_uint]
         L.ref_renderer_update.restype, L.ref_renderer_update.argtypes = None, [C.c_void_p, C.c_uint, C.c_uint]

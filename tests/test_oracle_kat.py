@@ -344,6 +344,16 @@ def test_default_states_match_reference_initialisers(tmp_path):
     assert bytes(abi.default_tonemapper()) == ol.ref_default_state(2)
     depth = np.frombuffer(ol.ref_default_state(3), np.float32)
     assert depth[:3].tolist() == [0.0, np.float32(2.2), 0.0] and not depth[3:].any()          # what test_display_pass_post_frag uses for eDepth
+    # the fields SampleExample derives per scene / environment (sample_example.cpp:87, 104-105; statements lifted and compiled) against the
+    # formulas of the test harness (tests/common.py) and of bench.py
+    import common
+    import ctypes as C
+    for trig, punc, integral in ((3.25, 0.0, 3.1415927), (0.0, 125.664, 0.731), (17.5, 2.125, 11.0)):
+        out = (C.c_float * 3)()
+        ol.ref_scene_lib().ref_glue_state(trig, punc, integral, out)
+        info = type("I", (), dict(trigLightWeight=np.float32(trig), puncLightWeight=np.float32(punc)))
+        st = common.frame_state(8, 8, info, 0, **common.env_state_overrides(np.float32(integral)))
+        assert (np.float32(st.lightLuminIntegInv), np.float32(st.fireflyClampThreshold), np.float32(st.envMapLuminIntegInv)) == (np.float32(out[0]), np.float32(out[1]), np.float32(out[2]))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "cis-565-final-vr-raytracer_b200")
     src = tmp_path / "d.cpp"
