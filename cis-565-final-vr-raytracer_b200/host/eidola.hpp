@@ -100,6 +100,20 @@ class Renderer {
   eid_renderer* m_h = nullptr;
 };
 
+// RenderOutput (src/render_output.hpp:44-60, render_output.cpp:224-240): owns the tonemapper settings; run() = post.frag over the renderer's two
+// result images — m_tm, or m_depthTm in the depth view, with zoom and renderingRatio overwritten per call, exactly like the reference
+class RenderOutput {
+ public:
+  Tonemapper m_tm{1.0f, 1.0f, 1.0f, 0.0f, 1.0f, 1.0f, {1.0f, 1.0f}, 0, 0.5f, 0.5f, 0};
+  Tonemapper m_depthTm{0.0f, 2.2f, 0.0f, 0.0f, 0.0f, 0.0f, {0.0f, 0.0f}, 0, 0.0f, 0.0f, 0};
+  void run(Renderer& renderer, const RtxState& state, float zoom = 1.0f, eid_vec2 ratio = eid_vec2{1.0f, 1.0f}) {
+    Tonemapper tm = (state.debugging_mode == eDepth) ? m_depthTm : m_tm;
+    tm.zoom = zoom;
+    tm.renderingRatio = ratio;
+    renderer.runOutput(tm);          // (RenderOutput::genMipmap runs inside when tm.autoExposure bit 0 is set)
+  }
+};
+
 // SampleExample::m_rtxState defaults (sample_example.hpp:154-184)
 inline RtxState defaultRtxState(uint32_t w, uint32_t h) {
   RtxState s{};

@@ -357,12 +357,12 @@ def test_default_states_match_reference_initialisers(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "cis-565-final-vr-raytracer_b200")
     src = tmp_path / "d.cpp"
-    src.write_text('#include <cstdio>\n#include "eidola.hpp"\nint main() { RtxState s = eidola::defaultRtxState(0, 0); fwrite(&s, sizeof s, 1, stdout); return 0; }\n')
+    src.write_text('#include <cstdio>\n#include "eidola.hpp"\nint main() { RtxState s = eidola::defaultRtxState(0, 0); fwrite(&s, sizeof s, 1, stdout); eidola::RenderOutput o; fwrite(&o.m_tm, sizeof o.m_tm, 1, stdout); fwrite(&o.m_depthTm, sizeof o.m_depthTm, 1, stdout); return 0; }\n')
     exe = str(tmp_path / "d")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
     subprocess.check_call([cxx, "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"), str(src), "-L", pkg, "-leidola", "-o", exe])
     out = subprocess.run([exe], env=dict(os.environ, LD_LIBRARY_PATH=pkg), capture_output=True).stdout
-    assert out == ol.ref_default_state(0)
+    assert out == ol.ref_default_state(0) + ol.ref_default_state(2) + ol.ref_default_state(3)      # defaultRtxState, RenderOutput::m_tm, m_depthTm of the C++ mirror
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
