@@ -209,6 +209,8 @@ def scene_tables(abi, side, n_prim):
     out = {"materials": raw(side.table(abi.TABLE_MATERIALS)), "punc": raw(side.table(abi.TABLE_PUNC_LIGHTS)), "trig": raw(side.table(abi.TABLE_TRIG_LIGHTS)),
            "info": raw(side.table(abi.TABLE_LIGHT_INFO))}
     out["info"][12:16] = 0            # LightBufInfo.pad: never written by the reference (whatever the Scene object's memory held)
+    if not out["info"][:8].any():
+        out["info"][8:12] = 0         # no lights at all: trigSampProb is not assigned either (scene.cpp:101-103)
     out["materials"].reshape(-1, 80)[:, 76:80] = 0      # GltfShadeMaterial.pad: `GltfShadeMaterial smat;` is not initialised there (scene.cpp:429)
     for pm in range(n_prim):
         out["vertices_%d" % pm] = raw(side.table(abi.TABLE_VERTICES, pm))

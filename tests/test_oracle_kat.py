@@ -462,6 +462,92 @@ def test_display_pass_host_side_matches_reference_render_output_cpp():
             assert common.same_bits_or_both_nan(got, orr.run_output(tm, st)), (mode, frames)
 
 
+def _random_scene(seed):
+    """A small random scene that exercises the corners of Scene::load's table builders: several meshes under random affine node
+    transforms (some instanced twice, some mirrored), materials with out-of-range ior, weakly / strongly emissive ones on both sides of the
+    1e-2 luminance threshold of createTrigLightBuffer, every alpha mode, and point / directional / spot lights with random cones."""
+    from eidola_b200 import abi as _abi
+    SceneArrays = _abi.SceneArrays
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: np.asarray(a, np.float32)
+    nmat = int(rng.integers(2, 7))
+    mats = []
+    for m in range(nmat):
+        e = rng.choice([0.0, 0.004, 0.02, 3.0, 40.0]) * rng.random(3)
+        mats.append(SceneArrays.material(base=tuple(rng.random(4)), metallic=float(rng.random()), roughness=float(rng.random()), emissive=tuple(float(x) for x in e),
+                                         double_sided=int(rng.integers(0, 2)), ior=float(rng.choice([0.3, 1.0, 1.45, 2.7, 9.0])), transmission=float(rng.random()),
+                                         alpha_mode=int(rng.integers(0, 3)), alpha_cutoff=float(rng.random())))
+    pos, nrm, tan, uv, col, idx, prims, nodes = [], [], [], [], [], [], [], []
+    nv = ni = 0
+    for k in range(int(rng.integers(1, 5))):
+        n = int(rng.integers(3, 9))
+        p = rng.normal(size=(n, 3)); nn = rng.normal(size=(n, 3)); nn /= np.linalg.norm(nn, axis=1, keepdims=True)
+        t = rng.normal(size=(n, 3)); t /= np.linalg.norm(t, axis=1, keepdims=True)
+        tris = rng.integers(0, n, size=(int(rng.integers(1, 6)), 3))
+        pos.append(p); nrm.append(nn); tan.append(np.concatenate([t, rng.choice([-1.0, 1.0], size=(n, 1))], axis=1)); uv.append(rng.random((n, 2)) * 3 - 1)
+        col.append(rng.random((n, 4))); idx.append(tris.reshape(-1))
+        prims.append(dict(firstIndex=ni, indexCount=int(tris.size), vertexOffset=nv, vertexCount=n, materialIndex=int(rng.integers(0, nmat))))
+        for _ in range(int(rng.integers(1, 3))):                        # the mesh is instanced once or twice
+            a = rng.normal(size=(3, 3)) * rng.choice([1.0, -1.0])       # random affine map, mirrored half of the time
+            mtx = np.eye(4); mtx[:3, :3] = a; mtx[:3, 3] = rng.normal(size=3) * 4
+            nodes.append(dict(worldMatrix=[float(v) for v in f32(mtx).T.reshape(-1)], primMesh=k))
+        nv += n; ni += int(tris.size)
+    lights = []
+    for _ in range(int(rng.integers(0, 6))):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        mtx = np.eye(4); mtx[:3, :3] = q; mtx[:3, 3] = rng.normal(size=3) * 5
+        inner = float(rng.random() * 0.6)
+        lights.append(dict(worldMatrix=[float(v) for v in f32(mtx).T.reshape(-1)], type=int(rng.integers(0, 3)), color=tuple(float(v) for v in rng.random(3)),
+                           intensity=float(rng.random() * 50), range=float(rng.random() * 10), innerConeAngle=inner, outerConeAngle=inner + float(rng.random() * 0.7)))
+    cam = dict(eye=(0.0, 1.0, -6.0), center=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), yfov=float(rng.random() + 0.4))
+    return SceneArrays(np.concatenate(pos), np.concatenate(nrm), np.concatenate(tan), np.concatenate(uv), np.concatenate(col), np.concatenate(idx), prims, nodes, mats,
+                       lights, cam, "random%d" % seed)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+def test_random_scenes_host_tables_and_instances_match_reference():
+    """Randomised scenes through the reference's OWN scene.cpp / accelstruct.cpp, the oracle and the product's host side: every table, both
+    light weights, the camera and the instance records agree bit for bit (only the sign of a zero light-direction / position component,
+    which nvmath's un-vendored operator* decides, is left open)."""
+    import ctypes as C
+    import eidola_b200 as eid
+    from eidola_b200 import abi
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as mg
+    assert ol.ref_scene_lib() is not None
+    seen_trig = seen_punc = 0
+    for seed in range(24):
+        arrays = _random_scene(seed)
+        ref = ol.RefScene(arrays)
+        osc = ol.OracleScene(); osc.load_arrays(arrays)
+        psc = eid.Scene(device=-1); psc.load_arrays(arrays)
+        want = mg.scene_tables(abi, ref, len(arrays.prim_meshes))
+        for tag, side in (("oracle", osc), ("product", psc)):
+            got = mg.scene_tables(abi, side, len(arrays.prim_meshes))
+            for k in want:
+                if k == "punc":
+                    assert _zero_sign_free(got[k], abi) == _zero_sign_free(want[k], abi), (seed, tag, k)
+                else:
+                    assert got[k].tobytes() == want[k].tobytes(), (seed, tag, k)
+            assert np.array((side.info().trigLightWeight, side.info().puncLightWeight), np.float32).tobytes() == np.array(ref.weights(), np.float32).tobytes(), (seed, tag)
+        ref.update_camera(320, 200); osc.update_camera(320, 200); psc.update_camera(320, 200)
+        ref.update_camera(320, 200); osc.update_camera(320, 200); psc.update_camera(320, 200)
+        cam = ref.table(abi.TABLE_CAMERA).tobytes()
+        assert np.ascontiguousarray(osc.table(abi.TABLE_CAMERA)).tobytes() == cam and np.ascontiguousarray(psc.table(abi.TABLE_CAMERA)).tobytes() == cam, seed
+        inst, xf, blas, _ = ref.accel()
+        n = len(arrays.nodes)
+        flags = np.zeros((n, 3), np.int32)
+        assert ol.lib().orc_scene_instance_flags(osc._h, flags.ctypes.data_as(C.c_void_p), n) == n
+        oxf = np.zeros((n, 24), np.float32)
+        ol.lib().orc_scene_instance_xforms(osc._h, oxf.ctypes.data_as(C.c_void_p), n)
+        for i in range(n):
+            assert (int(inst[i, 3]), int(inst[i, 0]), int(blas[inst[i, 4], 0])) == tuple(int(v) for v in flags[i]), (seed, i)
+            assert xf[i].T.tobytes() == oxf[i, :12].tobytes(), (seed, i)
+        li = np.frombuffer(want["info"].tobytes(), abi.LIGHTINFO_DT)[0]
+        seen_trig += int(li["trigLightSize"] > 0); seen_punc += int(li["puncLightSize"] > 0)
+    assert seen_trig >= 5 and seen_punc >= 5                            # the generator really produced both kinds of lights
+
+
 def expected_run_commands(w, h, denoise, frames):
     """Renderer::run as the oracle (oracle_shaders.cpp Renderer::run / runPost) and the product (render.cu launchFrame, fillParams) implement
     it: descriptor set (frames + 1) % 2, the caller's RtxState pushed once, K1 over ceil(W/8) x ceil(H/8) groups, K2 over the (W/2) x (H/2)
