@@ -377,10 +377,12 @@ def test_reference_renderer_replay_matches_oracle_frames():
     from eidola_b200 import abi, scenes
     R = ol.ref()
     assert R is not None and ol.ref_scene_lib() is not None
-    for maker_name, size, frames, over in (("cornell_scene", (64, 40), 3, dict(maxDepth=3)), ("small_room", (50, 34), 3, dict(maxDepth=2, ReSTIRState=abi.eSpatiotemporal)),
-                                           ("cube_scene", (48, 32), 2, dict(maxDepth=2, denoise=0))):
+    configs = [("cornell_scene", (64, 40), 3, dict(maxDepth=3)), ("small_room", (50, 34), 3, dict(maxDepth=2, ReSTIRState=abi.eSpatiotemporal)),
+               ("cube_scene", (48, 32), 2, dict(maxDepth=2, denoise=0))]
+    configs += [(seed, (48, 32), 2, dict(maxDepth=2, RISSampleNum=3)) for seed in (1, 2, 3)]      # rooms lit by random directional / spot / point lights
+    for maker_name, size, frames, over in configs:
         w, h = size
-        arrays = getattr(scenes, maker_name)()
+        arrays = _lit_scene(maker_name) if isinstance(maker_name, int) else getattr(scenes, maker_name)()
         osc = ol.OracleScene(); osc.load_arrays(arrays)
         orr = ol.OracleRenderer(osc, size); orr.set_env_constant((0.0, 0.0, 0.0))
         rt = ol.RefTracer(R, abi, arrays, osc, size)                   # scene tables + intersector binding of the trace stages
@@ -502,6 +504,33 @@ def _random_scene(seed):
     cam = dict(eye=(0.0, 1.0, -6.0), center=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), yfov=float(rng.random() + 0.4))
     return SceneArrays(np.concatenate(pos), np.concatenate(nrm), np.concatenate(tan), np.concatenate(uv), np.concatenate(col), np.concatenate(idx), prims, nodes, mats,
                        lights, cam, "random%d" % seed)
+
+
+def _lit_scene(seed):
+    """A visible room (floor, back wall, two boxes) with random materials, lit ONLY by random punctual lights of all three kinds (point,
+    directional, spot with random cones / ranges) and one emissive quad: exercises SamplePuncLight's directional and spot branches."""
+    from eidola_b200 import scenes as sc
+    rng = np.random.default_rng(1000 + seed)
+    b = sc._Builder()
+    mats = [b.add_material(base=tuple(float(v) for v in 0.2 + 0.7 * rng.random(3)) + (1.0,), metallic=float(rng.random() < 0.3) * float(rng.random()),
+                           roughness=float(0.2 + 0.8 * rng.random())) for _ in range(4)]
+    lamp = b.add_material(base=(0, 0, 0, 1), metallic=0.0, roughness=1.0, emissive=(6.0, 5.0, 4.0))
+    b.add_quads(sc._box_quads((-3.0, 0.0, -3.0), (3.0, 3.0, 3.0), "yZx", inward=True), mats[0])
+    b.add_quads(sc._box_quads((-1.6, 0.0, -0.4), (-0.4, 1.3, 0.9), "xXYzZ"), mats[1])
+    b.add_quads(sc._box_quads((0.3, 0.0, -1.0), (1.5, 0.7, 0.2), "xXYzZ"), mats[2])
+    b.add_quads([[(-0.4, 2.9, -0.4), (0.4, 2.9, -0.4), (0.4, 2.9, 0.4), (-0.4, 2.9, 0.4)]], lamp)
+    for k in range(4):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        if k < 3:                                                        # aim the -Z axis (the light's direction) roughly downwards
+            d = np.array([rng.normal() * 0.4, -1.0, rng.normal() * 0.4]); d /= np.linalg.norm(d)
+            x = np.cross([0.0, 0.0, 1.0], d); x /= np.linalg.norm(x); y = np.cross(-d, x)
+            q = np.stack([x, y, -d], axis=1)
+        mtx = np.eye(4); mtx[:3, :3] = q; mtx[:3, 3] = (rng.uniform(-2, 2), rng.uniform(1.5, 2.8), rng.uniform(-2, 2))
+        inner = float(rng.uniform(0.1, 0.5))
+        b.lights.append(dict(worldMatrix=[float(v) for v in np.asarray(mtx, np.float32).T.reshape(-1)], type=[0, 2, 2, 1][k], color=tuple(float(v) for v in 0.5 + 0.5 * rng.random(3)),
+                             intensity=float(rng.uniform(2, 30)), range=float(rng.uniform(0, 8)), innerConeAngle=inner, outerConeAngle=inner + float(rng.uniform(0.05, 0.6))))
+    cam = dict(eye=(0.0, 1.6, -2.8), center=(0.0, 0.9, 0.5), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(70.0)))
+    return b.build(cam, "lit%d" % seed)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
