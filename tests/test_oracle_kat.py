@@ -506,6 +506,29 @@ def _random_scene(seed):
                        lights, cam, "random%d" % seed)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("workload", ["c3", "c5"])
+def test_full_size_host_tables_match_reference_scene_cpp(workload):
+    """BASELINE.json's full-size scenes — C3 (1 000 708 triangles, 1 000 emissive) and C5 (10 009 402 triangles, 10 000 emissive) — through the
+    reference's OWN scene.cpp and through the product's host side: every vertex / index buffer, the materials, the 1 000- / 10 000-entry
+    triangle-light table with its alias map, LightBufInfo and the light weight are bit-identical."""
+    import eidola_b200 as eid
+    from eidola_b200 import abi, scenes
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as mg
+    assert ol.ref_scene_lib() is not None
+    arrays = scenes.heightfield_room() if workload == "c3" else scenes.heightfield_room(quads=2236, n_light_quads=5000, light_seed=567)
+    ref = ol.RefScene(arrays)
+    psc = eid.Scene(device=-1); psc.load_arrays(arrays)
+    want, got = mg.scene_tables(abi, ref, len(arrays.prim_meshes)), mg.scene_tables(abi, psc, len(arrays.prim_meshes))
+    assert sorted(want) == sorted(got)
+    for k in want:
+        assert got[k].tobytes() == want[k].tobytes(), k
+    li = np.frombuffer(want["info"].tobytes(), abi.LIGHTINFO_DT)[0]
+    assert int(li["trigLightSize"]) == (1000 if workload == "c3" else 10000) and psc.info().triangleInstances == (1000708 if workload == "c3" else 10009402)
+    assert np.array((psc.info().trigLightWeight, psc.info().puncLightWeight), np.float32).tobytes() == np.array(ref.weights(), np.float32).tobytes()
+
+
 def _lit_scene(seed):
     """A visible room (floor, back wall, two boxes) with random materials, lit ONLY by random punctual lights of all three kinds (point,
     directional, spot with random cones / ranges) and one emissive quad: exercises SamplePuncLight's directional and spot branches."""
