@@ -238,6 +238,7 @@ def run_cuda(args):
     rr.set_env_constant(ENV)
     rr.set_overlap(not args.no_overlap)
     rr.set_denoise_rows(args.denoise_rows)
+    rr.set_denoise_tiles({"tma": 1, "cpasync": 2, "legacy": 0}[args.denoiser], args.tile_rows)
     rr.set_wavefront({"wavefront": 1, "wavefront-serial": 2, "mega": 0}[args.k2], args.trace_blocks)
     if world > 1:
         rr.set_stripes(rank, world, stripe_rows)
@@ -466,6 +467,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="tiny scene/resolution (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--denoise-rows", type=int, default=2, choices=(1, 2, 4), help="A-Trous pixels per thread (rows of one column sharing tap rows)")
+    ap.add_argument("--denoiser", choices=["tma", "cpasync", "legacy"], default="tma",
+                    help="A-Trous passes: shared-memory tile kernel fed by TMA (default) / by cp.async, or the round-1 L1-served kernel")
+    ap.add_argument("--tile-rows", type=int, default=4, choices=(2, 4), help="tile kernel: lattice rows per thread")
     ap.add_argument("--k2", choices=["wavefront", "wavefront-serial", "mega"], default="wavefront",
                     help="form of indirect_stage: ray queues + persistent dynamic-fetch traversal (default) or one thread per pixel")
     ap.add_argument("--trace-blocks", type=int, default=0, help="grid of the persistent traversal kernel in 128-thread blocks (0 = library default)")

@@ -36,7 +36,7 @@ EXPORTS = [
     "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
-    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_overlap", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_fn_tap", "eid_renderer_fn_tap", "eid_renderer_run_output", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
+    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_denoise_tiles", "eid_renderer_set_overlap", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_fn_tap", "eid_renderer_fn_tap", "eid_renderer_run_output", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_render_host_async", "eid_renderer_wait_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
@@ -87,6 +87,7 @@ def lib():
         "eid_renderer_set_env_constant": (i32, [vp, abi.c_float_p]),
         "eid_renderer_set_strict_math": (i32, [vp, i32]),
         "eid_renderer_set_denoise_rows": (i32, [vp, i32]),
+        "eid_renderer_set_denoise_tiles": (i32, [vp, i32, i32]),
         "eid_renderer_set_wavefront": (i32, [vp, i32, i32]),
         "eid_renderer_set_sun_and_sky": (i32, [vp, vp]),
         "eid_sun_and_sky_eval": (i32, [i32, vp, vp, u32, vp]),
@@ -301,6 +302,9 @@ class Renderer:
 
     def set_env_constant(self, rgb):
         _check(lib().eid_renderer_set_env_constant(self._h, _f3(rgb)))
+
+    def set_denoise_tiles(self, mode, rows=0):   # 1 (default): smem tiles via TMA, 2: via cp.async, 0: legacy L1-served kernel
+        _check(lib().eid_renderer_set_denoise_tiles(self._h, int(mode), int(rows)))
 
     def set_denoise_rows(self, n):        # A-Trous pixels per thread sharing tap rows: 1, 2 (default) or 4
         _check(lib().eid_renderer_set_denoise_rows(self._h, int(n)))

@@ -12,12 +12,10 @@
 // Renderer::run (src/renderer.cpp:154-206) = strict stream order of the above: 1 + 1 + 4 + 5 + 1 launches.
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <vector>
-#include "frame.cuh"
-#include "stage_direct.cuh"
-#include "stage_indirect.cuh"
-#include "stage_post.cuh"
-#include "taps.cuh"
+#include "stages.h"
 
 
 using namespace eid;
@@ -48,7 +46,10 @@ struct eid_renderer {
   int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
   int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
   int smCount = 0;
-  int denoiseRowBlock = 2;    // pixels of one column filtered per thread in the A-Trous passes (1, 2 or 4; 2 measured fastest)
+  int denoiseRowBlock = 2;    // legacy A-Trous kernel: pixels of one column filtered per thread (1, 2 or 4; 2 measured fastest)
+  int denoiseTiles = 1;       // 1 (default): shared-memory tile kernel fed by TMA; 2: same, tiles loaded with cp.async; 0: legacy kernel (L1-served taps)
+  int denoiseTileRows = 4;    // tile kernel: lattice rows per thread (2 or 4)
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;   // (buffer, pitch, rows, level, tile height) -> lattice-view tensor map
   bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
   unsigned long long* counters = nullptr;
   unsigned long long* countersHost = nullptr;   // pinned
@@ -87,6 +88,7 @@ void eid_renderer::release() {
   cudaFree(mipScratch); mipScratch = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
+  tmaps.clear();
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
   for (auto& t : geom) { cudaFree(t); t = nullptr; }
 }
@@ -106,10 +108,14 @@ void eid_renderer::allocate() {
     zalloc((void**)&indirectResv[i], ni * sizeof(IndirectReservoir));
   }
   zalloc((void**)&motion, n * 4);
-  zalloc((void**)&directImg, n * 16); zalloc((void**)&indirectImg, n * 16);
-  for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16);
-  zalloc((void**)&geom[0], n * 16); zalloc((void**)&geom[1], n * 16);
-  zalloc((void**)&geom[2], ni * 16); zalloc((void**)&geom[3], ni * 16);
+  // everything the A-Trous tile kernel reads through a lattice-view tensor map carries 17 rows of slack: the view of level l rounds
+  // the row / column counts up to multiples of 2^l <= 16, so its last lattice row / column may address up to 15 rows + 15 texels
+  // past the image (never used: the kernel invalidates texels outside the rendered size)
+  const size_t slack = (size_t)17 * width * 16;
+  zalloc((void**)&directImg, n * 16 + slack); zalloc((void**)&indirectImg, n * 16 + slack);
+  for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16 + slack);
+  zalloc((void**)&geom[0], n * 16 + slack); zalloc((void**)&geom[1], n * 16 + slack);
+  zalloc((void**)&geom[2], ni * 16 + slack); zalloc((void**)&geom[3], ni * 16 + slack);
   CUDA_CHECK(cudaStreamSynchronize(stream));
   hasRun = false; lastSet = 0;
   if (!stripesSet) { sFirst = 0; sRows = (height + 15) / 16 * 16; sStride = 1u << 20; }
@@ -195,43 +201,39 @@ static void beginFrame(eid_renderer* r) {
 static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_DIRECT, st);
   if (P.sCount > 0) {
-    dim3 b(8, 8), g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
+    dim3 g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     const bool spatial = P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal;
     if (!spatial) {
-      if (r->countVisits) { if (tex) k_direct_stage<true, true, false><<<g, b, 0, st>>>(P, 0); else k_direct_stage<true, false, false><<<g, b, 0, st>>>(P, 0); }
-      else { if (tex) k_direct_stage<false, true, false><<<g, b, 0, st>>>(P, 0); else k_direct_stage<false, false, false><<<g, b, 0, st>>>(P, 0); }
+      launchDirectStage(P, g, st, r->countVisits, tex, false, 0);
       r->stats.kernelLaunches[EID_K_DIRECT]++;
     } else {
       // spatial reuse: every pixel up to its tempDirectResv write (owned stripes, then — when the stripes do not cover the frame — the
       // row above and the row below each stripe), then the neighbour merge and the shading
       auto first = [&](dim3 grid, int halo) {
-        if (r->countVisits) { if (tex) k_direct_stage<true, true, true><<<grid, b, 0, st>>>(P, halo); else k_direct_stage<true, false, true><<<grid, b, 0, st>>>(P, halo); }
-        else { if (tex) k_direct_stage<false, true, true><<<grid, b, 0, st>>>(P, halo); else k_direct_stage<false, false, true><<<grid, b, 0, st>>>(P, halo); }
+        launchDirectStage(P, grid, st, r->countVisits, tex, true, halo);
         r->stats.kernelLaunches[EID_K_DIRECT]++;
       };
       first(g, 0);
       if (P.sFirst > 0 || P.sCount > 1 || P.sFirst + P.sRows < P.st.size.y) first(dim3((P.st.size.x + 63) / 64, 2 * P.sCount), 1);
-      k_direct_spatial<<<g, b, 0, st>>>(P);
+      launchDirectSpatial(P, g, st);
       r->stats.kernelLaunches[EID_K_DIRECT]++;
     }
   }
   markStop(r, EID_K_DIRECT, st);
 }
 
-template <bool ANY>
-static void launchTraceQueue(eid_renderer* r, const FrameParams& P, const float4* rays, const uint32_t* count, uint32_t* cursor, cudaStream_t st) {
+static void traceQueue(eid_renderer* r, bool any, const FrameParams& P, const float4* rays, const uint32_t* count, uint32_t* cursor, cudaStream_t st) {
   const int g = r->traceBlocks > 0 ? r->traceBlocks : r->smCount * EID_TQ_MIN_BLOCKS;
-  if (r->countVisits) k_trace_queue<ANY, true><<<g, 128, 0, st>>>(P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
-  else k_trace_queue<ANY, false><<<g, 128, 0, st>>>(P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
+  launchTraceQueue(any, r->countVisits, g, st, P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
   r->stats.kernelLaunches[EID_K_INDIRECT]++;
 }
 
 static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_INDIRECT, st);
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
-    dim3 b(8, 8), g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
+    dim3 g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
       // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
@@ -239,25 +241,24 @@ static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st
       // of the C3 scene needs ~150 dependent node visits, ~80 us, however few rays there are); join before finish
       cudaStream_t sh = r->waveOverlap ? r->shadowStream : st;
       CUDA_CHECK(cudaMemsetAsync(P.wv.ctr, 0, 128 * sizeof(uint32_t), st));
-      if (tex) k_gi_begin<true><<<g, b, 0, st>>>(P); else k_gi_begin<false><<<g, b, 0, st>>>(P);
+      launchGiBegin(P, g, st, tex);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
       const int gb = r->smCount * 8;
       bool forked = false;
       for (int d = 1; d <= P.st.maxDepth; ++d) {
-        launchTraceQueue<false>(r, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
-        if (tex) k_gi_bounce<true><<<gb, 128, 0, st>>>(P, d); else k_gi_bounce<false><<<gb, 128, 0, st>>>(P, d);
+        traceQueue(r, false, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
+        launchGiBounce(P, gb, st, tex, d);
         r->stats.kernelLaunches[EID_K_INDIRECT]++;
         if (d + 1 <= P.st.maxDepth && P.st.MIS > 0) {
           if (sh != st) { CUDA_CHECK(cudaEventRecord(r->evWave, st)); CUDA_CHECK(cudaStreamWaitEvent(sh, r->evWave, 0)); forked = true; }
-          launchTraceQueue<true>(r, P, P.wv.shadowQ + 2 * (size_t)(d - 1) * P.wv.slots, P.wv.ctr + 32 + d - 1, P.wv.ctr + 96 + d - 1, sh);
+          traceQueue(r, true, P, P.wv.shadowQ + 2 * (size_t)(d - 1) * P.wv.slots, P.wv.ctr + 32 + d - 1, P.wv.ctr + 96 + d - 1, sh);
         }
       }
       if (forked) { CUDA_CHECK(cudaEventRecord(r->evWaveJoin, sh)); CUDA_CHECK(cudaStreamWaitEvent(st, r->evWaveJoin, 0)); }
-      k_gi_finish<<<g, b, 0, st>>>(P);
+      launchGiFinish(P, g, st);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
     } else {
-      if (r->countVisits) { if (tex) k_indirect_stage<true, true><<<g, b, 0, st>>>(P); else k_indirect_stage<true, false><<<g, b, 0, st>>>(P); }
-      else { if (tex) k_indirect_stage<false, true><<<g, b, 0, st>>>(P); else k_indirect_stage<false, false><<<g, b, 0, st>>>(P); }
+      launchIndirectMega(P, g, st, r->countVisits, tex);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
     }
   }
@@ -285,29 +286,89 @@ template <bool INDIRECT>
 static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
                           const PostLayout& L, int first, int stride, int rows, cudaStream_t st);
 
+static bool fastSigmas(const RtxState& st);
 // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4; accounted to the direct denoiser
 static void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
   if (P.st.denoise <= 0 || L.count <= 0) return;
   const int rows = L.srows + 2 * 124, W = P.st.size.x;
-  dim3 b(32, 8), g((W + 31) / 32, gridRows(L, rows, 8));
-  k_denoise_prep<<<g, b, 0, st>>>(P, L.first - 124, L.stride, rows);
+  dim3 g((W + 31) / 32, gridRows(L, rows, 8));
+  launchDenoisePrep(P, g, st, L.first - 124, L.stride, rows, r->denoiseTiles != 0 && !r->strictMath && fastSigmas(P.st));
   r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
 }
 
-template <bool INDIRECT, int R>
-static void launchDenoiseR(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
-                           const PostLayout& L, int first, int stride, int rows, cudaStream_t st) {
-  const int step = 1 << level, vrows = step * ((((rows + step - 1) >> level) + R - 1) / R);
-  dim3 b(32, 4), g((width + 31) / 32, gridRows(L, vrows, 4));
-  if (r->strictMath) k_denoise<INDIRECT, true, R><<<g, b, 0, st>>>(P, src, dst, level, lastLevel, first, stride, rows);
-  else k_denoise<INDIRECT, false, R><<<g, b, 0, st>>>(P, src, dst, level, lastLevel, first, stride, rows);
+// ---- lattice-view tensor maps of the A-Trous tile kernel (stage_denoise.cuh) ------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver-API entry point; it is resolved through the runtime so that libeidola.so does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encodeTiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
 }
+// View of a pitch-linear float4 image (pitch P texels, `rows` rows) as the lattice of A-Trous level l (s = 2^l): 5-D tensor of floats
+// (component 4, phase x s, lattice x ceil(P / s), phase y s, lattice y ceil(rows / s)), box = (4, 1, 36, 1, tileH) = one phase's tile + halo.
+static const CUtensorMap& tensorMapFor(eid_renderer* r, const void* base, int pitch, int rows, int level, int tileH) {
+  const auto key = std::make_tuple(base, pitch, rows, level, tileH);
+  auto it = r->tmaps.find(key);
+  if (it != r->tmaps.end()) return it->second;
+  EncodeTiledFn enc = encodeTiled();
+  if (!enc) raise(EID_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA needs sm_90+ and a CUDA 12 driver)");
+  const cuuint64_t s = 1ull << level;
+  const cuuint64_t dims[5] = {4, s, ((cuuint64_t)pitch + s - 1) / s, s, ((cuuint64_t)rows + s - 1) / s};
+  const cuuint64_t strides[4] = {16, 16 * s, 16ull * pitch, 16ull * pitch * s};
+  const cuuint32_t box[5] = {4, 1, EID_TILE_PW, 1, (cuuint32_t)tileH};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  alignas(64) CUtensorMap m;
+  const CUresult e = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (e != CUDA_SUCCESS) raise(EID_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (pitch %d rows %d level %d)", (int)e, pitch, rows, level);
+  return r->tmaps.emplace(key, m).first->second;
+}
+
+// the fast path pre-scales by sqrt(log2e / sigma): needs finite positive sigmas (anything else runs the reference arithmetic)
+static bool fastSigmas(const RtxState& st) {
+  const float v[6] = {st.sigLuminDirect, st.sigNormalDirect, st.sigDepthDirect, st.sigLuminIndirect, st.sigNormalIndirect, st.sigDepthIndirect};
+  for (float f : v) if (!(f > 1e-12f && f < 1e12f)) return false;
+  return true;
+}
+
 template <bool INDIRECT>
 static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* src, float4* dst, int level, int lastLevel, int width,
                           const PostLayout& L, int first, int stride, int rows, cudaStream_t st) {
-  if (r->denoiseRowBlock == 4) launchDenoiseR<INDIRECT, 4>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
-  else if (r->denoiseRowBlock == 2) launchDenoiseR<INDIRECT, 2>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
-  else launchDenoiseR<INDIRECT, 1>(r, P, src, dst, level, lastLevel, width, L, first, stride, rows, st);
+  if (r->denoiseTiles != 0) {
+    const int R = r->denoiseTileRows, TR = 4 * R, TH = TR + 4, s = 1 << level;
+    const bool strict = r->strictMath || !fastSigmas(P.st);
+    const int gPitch = INDIRECT ? P.pitch / 2 : P.pitch, gRows = INDIRECT ? P.allocH / 2 : P.allocH;
+    const float4* gPos = INDIRECT ? P.geomPosH : P.geomPos;
+    const float4* gNrm = INDIRECT ? P.geomNrmH : P.geomNrm;
+    AtrousArgs a;
+    a.gPos = gPos; a.gNrm = gNrm; a.inImg = src; a.outImg = dst;
+    a.gPitch = gPitch; a.iPitch = P.pitch; a.allocRows = gRows;
+    a.level = level; a.lastLevel = lastLevel; a.first = first; a.stride = stride; a.rows = rows;
+    a.nTy = ((rows - 1) >> level) / TR + 2;                       // upper bound for any stripe alignment; surplus blocks exit at once
+    if (L.count == 1) {                                           // exact for the single-stripe layouts
+      const int bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y, ylo = std::max(first, 0), yhi = std::min(first + rows, bh);
+      if (yhi <= ylo) return;
+      a.nTy = ((yhi - 1) >> level) / TR - (ylo >> level) / TR + 1;
+    }
+    a.useTma = r->denoiseTiles == 1;
+    static const CUtensorMap none{};
+    const CUtensorMap& mp = a.useTma ? tensorMapFor(r, gPos, gPitch, gRows, level, TH) : none;
+    const CUtensorMap& mn = a.useTma ? tensorMapFor(r, gNrm, gPitch, gRows, level, TH) : none;
+    const CUtensorMap& mc = a.useTma ? tensorMapFor(r, src, P.pitch, P.allocH, level, TH) : none;
+    const int latticeW = (width + s - 1) >> level;
+    dim3 g((unsigned)(((latticeW + EID_TILE_W - 1) / EID_TILE_W) << level), (unsigned)((L.count * a.nTy) << level));
+    launchAtrousTile(INDIRECT, strict, R, g, st, P, mp, mn, mc, a);
+    return;
+  }
+  const int R = r->denoiseRowBlock;
+  const int step = 1 << level, vrows = step * ((((rows + step - 1) >> level) + R - 1) / R);
+  dim3 g((width + 31) / 32, gridRows(L, vrows, 4));
+  eid::launchDenoise(INDIRECT, r->strictMath, R, g, st, P, src, dst, level, lastLevel, first, stride, rows);
 }
 
 static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
@@ -341,8 +402,8 @@ static void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const Po
 static void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
   markStart(r, EID_K_COMPOSE, st);
   if (L.count > 0) {
-    dim3 b(32, 8), g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 8));
-    k_compose<<<g, b, 0, st>>>(P, P.st.denoise > 0 ? P.indB : P.indA, L.first, L.stride, L.srows);
+    dim3 g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 8));
+    launchCompose(P, g, st, P.st.denoise > 0 ? P.indB : P.indA, L.first, L.stride, L.srows);
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
   markStop(r, EID_K_COMPOSE, st);
@@ -592,7 +653,7 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
   memset(&P, 0, sizeof(P));
   P.st = r->lastState; P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
-  dim3 b(32, 8), g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
+  dim3 g((P.st.size.x + 31) / 32, (P.st.size.y + 7) / 8);
   if (tm->autoExposure & 1) {   // RenderOutput::genMipmap (render_output.cpp:243-253): the chain of the whole images (m_size = the allocation) down to 1 x 1
     if (!r->mipScratch) CUDA_CHECK(cudaMalloc(&r->mipScratch, (2 * ((size_t)(r->width / 2 + 1) * (r->height / 2 + 1)) + 2) * 16));
     const size_t half = (size_t)(r->width / 2 + 1) * (r->height / 2 + 1);
@@ -605,13 +666,13 @@ int eid_renderer_run_output(eid_renderer* r, const Tonemapper* tm) {
       while (sw > 1 || sh > 1) {
         const int dw = sw > 1 ? sw / 2 : 1, dh = sh > 1 ? sh / 2 : 1;
         float4* dst = (dw == 1 && dh == 1) ? avg + img : pp[k & 1];
-        k_mip_blit<<<dim3((dw + 31) / 32, (dh + 7) / 8), b, 0, r->stream>>>(src, sw, sh, spitch, dst, dw, dh);
+        launchMipBlit(dim3((dw + 31) / 32, (dh + 7) / 8), r->stream, src, sw, sh, spitch, dst, dw, dh);
         src = dst; sw = dw; sh = dh; spitch = dw; ++k;
       }
     }
-    k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8, avg);
+    launchPost(P, g, r->stream, *tm, r->displayF, r->display8, avg);
   } else {
-    k_post<<<g, b, 0, r->stream>>>(P, *tm, r->displayF, r->display8, nullptr);
+    launchPost(P, g, r->stream, *tm, r->displayF, r->display8, nullptr);
   }
   CUDA_CHECK(cudaGetLastError());
   return EID_OK;
@@ -639,7 +700,7 @@ int eid_renderer_fn_tap(eid_renderer* r, const RtxState* st, int which, const fl
   cudaError_t e = cudaMemcpy(din, in, (size_t)n * ni * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(dout, 0, (size_t)n * no * 4);
   if (e == cudaSuccess) {
-    k_ctx_tap<<<(n + 63) / 64, 64>>>(P, which, ni, no, din, n, dout);
+    launchCtxTap(P, which, ni, no, din, n, dout);
     e = cudaMemcpy(out, dout, (size_t)n * no * 4, cudaMemcpyDeviceToHost);
   }
   cudaFree(din); cudaFree(dout);
@@ -662,7 +723,7 @@ int eid_fn_tap(int device, int which, const float* in, uint32_t n, float* out) {
   cudaError_t e = cudaMemcpy(din, in, (size_t)n * ni * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(dout, 0, (size_t)n * no * 4);
   if (e == cudaSuccess) {
-    k_fn_tap<<<(n + 63) / 64, 64>>>(which, ni, no, din, n, dout);
+    launchFnTap(which, ni, no, din, n, dout);
     e = cudaMemcpy(out, dout, (size_t)n * no * 4, cudaMemcpyDeviceToHost);
   }
   cudaFree(din); cudaFree(dout);
@@ -681,7 +742,7 @@ int eid_sun_and_sky_eval(int device, const SunAndSky* ss, const float* dirs, uin
   if (cudaMalloc(&dout, (size_t)n * 12) != cudaSuccess) { cudaFree(dd); raise(EID_ERR_CUDA, "cudaMalloc failed"); }
   cudaError_t e = cudaMemcpy(dd, dirs, (size_t)n * 12, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    k_sun_and_sky<<<(n + 63) / 64, 64>>>(*ss, dd, n, dout);
+    launchSunAndSky(*ss, dd, n, dout);
     e = cudaMemcpy(rgb, dout, (size_t)n * 12, cudaMemcpyDeviceToHost);
   }
   cudaFree(dd); cudaFree(dout);
@@ -892,6 +953,17 @@ int eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread) {
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: null renderer");
   if (rowsPerThread != 1 && rowsPerThread != 2 && rowsPerThread != 4) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_rows: 1, 2 or 4");
   r->denoiseRowBlock = rowsPerThread;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_denoise_tiles(eid_renderer* r, int mode, int rowsPerThread) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_tiles: null renderer");
+  if (mode < 0 || mode > 2) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_tiles: mode 0 (legacy), 1 (TMA tiles) or 2 (cp.async tiles)");
+  if (rowsPerThread != 0 && rowsPerThread != 2 && rowsPerThread != 4) raise(EID_ERR_INVALID, "eid_renderer_set_denoise_tiles: rowsPerThread 2 or 4 (0 = keep)");
+  r->denoiseTiles = mode;
+  if (rowsPerThread) r->denoiseTileRows = rowsPerThread;
   return EID_OK;
   EID_CATCH
 }

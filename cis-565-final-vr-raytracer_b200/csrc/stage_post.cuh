@@ -26,17 +26,33 @@ DEV void thisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, floa
   nrm = make_float4(n.x, n.y, n.z, 0.f);
 }
 
+// FAST (tile kernel, default numerics): the planes are pre-scaled for k_atrous_tile's fast path — position * sqrt(log2e / sigDepth),
+// normal * sqrt(log2e / sigNormal) with w = -|scaled normal|^2 — so that every exponent of a tap weight is a plain squared distance.
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int first, int stride, int rows) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = stripeRow(first, stride, rows, 8);
   const int W = P.st.size.x, H = P.st.size.y, Wi = W / 2, Hi = H / 2;
   if (x >= W || y >= H || y < 0) return;
+  const float LOG2E = 1.44269504088896341f;
   float4 a, b;
   thisGeometry(P, x, y, W, H, a, b);
+  if (FAST) {
+    const float sd = sqrtf(LOG2E / P.st.sigDepthDirect), sn = sqrtf(LOG2E / P.st.sigNormalDirect);
+    a = make_float4(a.x * sd, a.y * sd, a.z * sd, a.w);
+    b = make_float4(b.x * sn, b.y * sn, b.z * sn, 0.f);
+    b.w = -fmaf(b.z, b.z, fmaf(b.y, b.y, b.x * b.x));
+  }
   const size_t pix = (size_t)y * P.pitch + x;
   P.geomPos[pix] = a; P.geomNrm[pix] = b;
   if (!(x & 1) && !(y & 1) && (x >> 1) < Wi && (y >> 1) < Hi) {
     thisGeometry(P, x, y, Wi, Hi, a, b);
+    if (FAST) {
+      const float sd = sqrtf(LOG2E / P.st.sigDepthIndirect), sn = sqrtf(LOG2E / P.st.sigNormalIndirect);
+      a = make_float4(a.x * sd, a.y * sd, a.z * sd, a.w);
+      b = make_float4(b.x * sn, b.y * sn, b.z * sn, 0.f);
+      b.w = -fmaf(b.z, b.z, fmaf(b.y, b.y, b.x * b.x));
+    }
     const size_t hp = (size_t)(y >> 1) * (P.pitch / 2) + (x >> 1);
     P.geomPosH[hp] = a; P.geomNrmH[hp] = b;
   }

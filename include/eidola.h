@@ -290,6 +290,12 @@ EID_API int  eid_renderer_set_strict_math(eid_renderer* r, int enabled);
  * overlapping tap rows: 1 = 25 loads per pixel, 2 (default, measured fastest on B200) = 15, 4 = 10 but 110 registers.
  * Results are bit-identical for every setting. */
 EID_API int  eid_renderer_set_denoise_rows(eid_renderer* r, int rowsPerThread);
+/* Form of the A-Trous passes (denoise_direct.comp / denoise_indirect.comp).  mode 1 (default): shared-memory tile kernel — a block owns a
+ * 32 x (4 rowsPerThread) tile of ONE phase of the level's dilated lattice, its three input planes + halo arrive by TMA
+ * (cp.async.bulk.tensor.5d through a lattice-view tensor map) and every tap is an LDS at an immediate offset; mode 2: the same kernel with
+ * the tiles loaded by cp.async (A/B measurement); mode 0: the round-1 kernel (taps served by L1, eid_renderer_set_denoise_rows applies).
+ * rowsPerThread: 2 or 4 (0 keeps the current value).  With strict math every mode is bit-identical to the oracle. */
+EID_API int  eid_renderer_set_denoise_tiles(eid_renderer* r, int mode, int rowsPerThread);
 /* RenderOutput::run (render_output.cpp:224-240) -> shaders/post.frag as a compute pass over the frame rendered last: direct +
  * indirect (or the debug view selected by that frame's RtxState.debugging_mode), Uncharted-2 tonemap, dither, contrast /
  * brightness / saturation / vignette, evaluated 1:1 (one output pixel per rendered pixel, zoom 1, renderingRatio (1,1) unless set

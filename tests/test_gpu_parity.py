@@ -176,15 +176,22 @@ def test_fast_math_denoiser_within_tolerance():
 
 
 @pytest.mark.parametrize("strict", [True, False])
-@pytest.mark.parametrize("size", [(256, 144), (130, 70), (64, 2)])
-def test_row_blocked_denoiser_equals_per_pixel_kernel(strict, size):
-    """The default A-Trous kernel filters 4 pixels of one column per thread (shared tap rows); every pixel still receives its
-    taps in the reference's order, so it must be BIT-identical to the one-pixel-per-thread kernel in both numerics modes."""
+@pytest.mark.parametrize("size", [(256, 144), (130, 70), (64, 2), (700, 300)])
+def test_denoiser_kernel_forms_agree(strict, size):
+    """The A-Trous passes exist as a shared-memory tile kernel (tiles by TMA = default, or by cp.async; 2 or 4 lattice rows per
+    thread) and as the round-1 kernel (taps through L1; 4, 2 or 1 pixels per thread).  Every form gives each pixel its taps in the
+    reference's order, so with strict math ALL forms are bit-identical; with the default numerics the forms of one kernel are
+    bit-identical among themselves and the two kernels agree to ~1e-6 (different but equivalent fast arithmetic)."""
     arrays = scenes.small_room()
     snaps = []
-    for rows in (4, 2, 1):
+    forms = [(1, 4), (1, 2), (2, 4), (2, 2), (0, 4), (0, 2), (0, 1)]
+    for mode, rows in forms:
         osc, orr, psc, acc, prr = common.make_pair(arrays, size, strict=strict)
-        prr.set_denoise_rows(rows)
+        if mode:
+            prr.set_denoise_tiles(mode, rows)
+        else:
+            prr.set_denoise_tiles(0)
+            prr.set_denoise_rows(rows)
         psc.update_camera(*size)
         for f in range(3):
             psc.update_camera(*size)
@@ -192,9 +199,18 @@ def test_row_blocked_denoiser_equals_per_pixel_kernel(strict, size):
         prr.sync()
         snaps.append(common.snapshot(prr))
     for name in ("direct", "indirect", "ind_tmp_a", "ind_tmp_b"):
-        assert snaps[0][name].tobytes() == snaps[2][name].tobytes() and snaps[1][name].tobytes() == snaps[2][name].tobytes(), name
+        for k in (1, 2, 3):
+            assert snaps[k][name].tobytes() == snaps[0][name].tobytes(), "tile kernel forms differ in %s (%s)" % (name, forms[k])
+        for k in (5, 6):
+            assert snaps[k][name].tobytes() == snaps[4][name].tobytes(), "legacy kernel forms differ in %s (%s)" % (name, forms[k])
+        if strict:
+            assert snaps[4][name].tobytes() == snaps[0][name].tobytes(), "tile kernel != legacy kernel in strict mode (%s)" % name
+        else:
+            assert common.rel_err(snaps[4][name], snaps[0][name]) < 1e-4, name
     with pytest.raises(eid.EidolaError):
         prr.set_denoise_rows(3)
+    with pytest.raises(eid.EidolaError):
+        prr.set_denoise_tiles(1, 3)
 
 
 @pytest.mark.parametrize("maker,size", [(scenes.cube_scene, (192, 192)), (scenes.cornell_scene, (224, 128))])
@@ -548,7 +564,9 @@ def test_state_size_smaller_than_allocation():
         st = common.frame_state(100, 60, info, f)
         orr.run(st, f)
         prr.run(st, f)
-        common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "descaled frame %d" % f)
+        prr.sync()
+        rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "descaled frame %d" % f)
+        assert all(v == 0.0 for v in rep.values()), "strict math must be bit-exact, got %s" % rep
 
 
 @pytest.mark.parametrize("restir,exchange_history", [(abi.eTemporal, True), (abi.eSpatiotemporal, True), (abi.eSpatiotemporal, False)])
@@ -744,7 +762,8 @@ def test_golden_frames():
             disp = prr.read(abi.BUF_DISPLAY_F32).reshape(size[1], size[0], 4)
             assert disp.view(np.uint32).tobytes() == z["display"].view(np.uint32).tobytes(), "golden %s: display pass differs" % name
         want = {k: z[k].view(got[k].dtype) if got[k].dtype.fields is None else np.frombuffer(z[k].tobytes(), got[k].dtype) for k in got}
-        common.compare_snapshots(got, want, "golden " + name)
+        rep = common.compare_snapshots(got, want, "golden " + name)
+        assert all(v == 0.0 for v in rep.values()), "golden %s: strict math must be bit-exact, got %s" % (name, rep)
 
 
 def test_error_behaviour_gpu():
