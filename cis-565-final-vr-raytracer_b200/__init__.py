@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import abi, scenes, sharding
-from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, SceneArrays, default_rtx_state)
+from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, GroupInfo, SceneArrays, default_rtx_state)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # EIDOLA_LIB selects another build of the same library (kernel-variant sweeps, tools/sweep.sh); never a different backend
@@ -40,6 +40,8 @@ EXPORTS = [
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_render_host_async", "eid_renderer_wait_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
+    "eid_group_layout", "eid_group_unique_id", "eid_group_create", "eid_group_destroy", "eid_group_set_mode", "eid_group_run",
+    "eid_group_render_host_async", "eid_group_wait_host", "eid_group_sync", "eid_group_get_info",
 ]
 
 
@@ -116,6 +118,16 @@ def lib():
         "eid_renderer_set_stripes": (i32, [vp, u32, u32, u32]),
         "eid_renderer_exchange_groups": (i32, [vp]),
         "eid_renderer_exchange_range": (i32, [vp, i32, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]),
+        "eid_group_layout": (i32, [u32, i32, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "eid_group_unique_id": (i32, [vp]),
+        "eid_group_create": (i32, [C.POINTER(vp), vp, i32, i32, vp]),
+        "eid_group_destroy": (None, [vp]),
+        "eid_group_set_mode": (i32, [vp, i32, i32, i32]),
+        "eid_group_run": (i32, [vp, C.POINTER(RtxState), i32]),
+        "eid_group_render_host_async": (i32, [vp, C.POINTER(SceneCamera), C.POINTER(RtxState), i32, vp, vp]),
+        "eid_group_wait_host": (i32, [vp]),
+        "eid_group_sync": (i32, [vp]),
+        "eid_group_get_info": (i32, [vp, C.POINTER(GroupInfo)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -271,6 +283,64 @@ class HdrSampling:
     def destroy(self):
         if self._h:
             lib().eid_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Group:
+    """eid_group: this process's rank of an N-GPU frame (include/eidola.h).  `id128` comes from Group.unique_id() on rank 0."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @staticmethod
+    def layout(height, world, rank=0):
+        y0, y1, ph = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().eid_group_layout(height, world, rank, C.byref(y0), C.byref(y1), C.byref(ph)))
+        return y0.value, y1.value, ph.value
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        _check(lib().eid_group_unique_id(buf))
+        return bytes(buf)
+
+    def create(self, renderer, rank, world, id128=None):
+        self.destroy()
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128) if id128 is not None else None
+        _check(lib().eid_group_create(C.byref(self._h), renderer._h, rank, world, buf))
+        self._renderer = renderer
+
+    def set_mode(self, post_sharded=True, history=2, gather_final=True):
+        _check(lib().eid_group_set_mode(self._h, int(post_sharded), int(history), int(gather_final)))
+
+    def run(self, state, frames):
+        _check(lib().eid_group_run(self._h, C.byref(state), frames))
+
+    def render_host_async(self, cam, state, frames, direct_out, indirect_out):
+        _check(lib().eid_group_render_host_async(
+            self._h, C.byref(cam) if cam is not None else None, C.byref(state), frames,
+            C.c_void_p(direct_out) if direct_out else None, C.c_void_p(indirect_out) if indirect_out else None))
+
+    def wait_host(self):
+        _check(lib().eid_group_wait_host(self._h))
+
+    def sync(self):
+        _check(lib().eid_group_sync(self._h))
+
+    def info(self):
+        i = GroupInfo()
+        _check(lib().eid_group_get_info(self._h, C.byref(i)))
+        return i
+
+    def destroy(self):
+        if self._h:
+            lib().eid_group_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

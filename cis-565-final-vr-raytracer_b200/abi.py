@@ -174,6 +174,11 @@ class FrameStats(C.Structure):
                 ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64)]
 
 
+class GroupInfo(C.Structure):   # eid_group_info
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("y0", C.c_uint32), ("y1", C.c_uint32), ("bandRows", C.c_uint32),
+                ("ncclVersion", C.c_int32), ("collectives", C.c_uint64)]
+
+
 # eid_scene_table
 (TABLE_MATERIALS, TABLE_PUNC_LIGHTS, TABLE_TRIG_LIGHTS, TABLE_LIGHT_INFO, TABLE_INSTANCE_DATA, TABLE_VERTICES,
  TABLE_INDICES, TABLE_CAMERA) = range(8)

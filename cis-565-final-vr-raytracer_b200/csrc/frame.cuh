@@ -74,6 +74,17 @@ DEV int stripeRow(int first, int stride, int rows, int bh) {
   return (r < rows) ? first + k * stride + r : 0x3fffffff;
 }
 
+// The quarter-res stage works in 8 x 8 tiles that share one multibounce lottery draw (indirect_stage.comp:283-288), keyed by the ABSOLUTE tile
+// origin.  A band may start in the middle of a tile (bands are multiples of 8 full-res = 4 quarter-res rows): blocks are laid over absolute
+// tile rows from the one containing `first`, and rows outside [first, first + rows) are masked (returned as 0x3fffffff).
+DEV int tileAlignedRow(int first, int stride, int rows) {
+  const int bps = ((first & 7) + rows + 7) >> 3;         // blocks per stripe (stride is a multiple of 8, so every stripe has the same phase)
+  const int k = blockIdx.y / bps, j = blockIdx.y - k * bps;
+  const int base = first + k * stride;
+  const int y = (base & ~7) + j * 8 + (int)threadIdx.y;
+  return (y >= base && y < base + rows) ? y : 0x3fffffff;
+}
+
 template <bool STATS>
 DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
   unsigned int a = c.closest, b = c.any, d = c.primary, n = c.nodes, t = c.tris;

@@ -12,73 +12,7 @@
 // Renderer::run (src/renderer.cpp:154-206) = strict stream order of the above: 1 + 1 + 4 + 5 + 1 launches.
 #include <algorithm>
 #include <cstring>
-#include <map>
-#include <tuple>
-#include <vector>
-#include "stages.h"
-
-
-using namespace eid;
-
-// ------------------------------------------------------------------------------------------------
-// Renderer object
-// ------------------------------------------------------------------------------------------------
-struct eid_renderer {
-  eid_scene* scene = nullptr;
-  eid_accel* accel = nullptr;
-  int device = 0;
-  uint32_t width = 0, height = 0;
-  cudaStream_t stream = nullptr;
-  bool ownStream = false;
-  uint4* gbuffer[2] = {nullptr, nullptr};
-  short2* motion = nullptr;
-  float* directResv[2] = {nullptr, nullptr};
-  float* indirectResv[2] = {nullptr, nullptr};
-  float4* directImg = nullptr; float4* indirectImg = nullptr;
-  float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
-  float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
-  float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
-  float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
-  float4* mipScratch = nullptr;                             // auto exposure: two ping-pong mip levels + the two 1x1 averages
-  // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
-  void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
-  cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
-  int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
-  int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
-  int smCount = 0;
-  int denoiseRowBlock = 2;    // legacy A-Trous kernel: pixels of one column filtered per thread (1, 2 or 4; 2 measured fastest)
-  int denoiseTiles = 1;       // 1 (default): shared-memory tile kernel fed by TMA; 2: same, tiles loaded with cp.async; 0: legacy kernel (L1-served taps)
-  int denoiseTileRows = 4;    // tile kernel: lattice rows per thread (2 or 4)
-  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;   // (buffer, pitch, rows, level, tile height) -> lattice-view tensor map
-  bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
-  unsigned long long* counters = nullptr;
-  unsigned long long* countersHost = nullptr;   // pinned
-  float env[3] = {0.f, 0.f, 0.f};
-  eid_env* envMap = nullptr;
-  SunAndSky sunSky{};         // SampleExample::m_sunAndSky (sample_example.hpp:186-203); in_use = 0 until the host sets it
-  int lastSet = 0;
-  RtxState lastState{};
-  bool hasRun = false;
-  uint32_t sFirst = 0, sStride = 0, sRows = 0; bool stripesSet = false;   // multi-GPU row ownership (see FrameParams)
-  bool profiling = false;
-  bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
-  cudaEvent_t ev[2 * EID_K_COUNT] = {};   // start/stop per stage
-  cudaEvent_t evFork = nullptr, evJoin = nullptr, evPost = nullptr;
-  cudaStream_t aux = nullptr;             // second stream: K3 runs beside K2/K4 (see launchFrame)
-  bool overlap = true;
-  bool postStarted = false;
-  cudaStream_t copyStream = nullptr;      // eid_renderer_render_host_async: D2H of frame f overlaps the kernels of frame f+1
-  cudaEvent_t evFrameDone = nullptr, evCopyDone = nullptr;
-  float4* staging[2] = {nullptr, nullptr};
-  bool copyPending = false;
-  eid_frame_stats stats{};
-  bool statsPending = false;
-
-  void allocate();
-  void release();
-  void ensureWave(int terms);
-  WaveView waveView() const;
-};
+#include "renderer.h"
 
 void eid_renderer::release() {
   for (int i = 0; i < 2; ++i) { cudaFree(gbuffer[i]); cudaFree(directResv[i]); cudaFree(indirectResv[i]); gbuffer[i] = nullptr; directResv[i] = nullptr; indirectResv[i] = nullptr; }
@@ -148,7 +82,7 @@ WaveView eid_renderer::waveView() const {
   return V;
 }
 
-static void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
+void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P) {
   if (st.size.x <= 0 || st.size.y <= 0 || (uint32_t)st.size.x > r->width || (uint32_t)st.size.y > r->height)
     raise(EID_ERR_INVALID, "RtxState.size %dx%d outside the renderer allocation %ux%u", st.size.x, st.size.y, r->width, r->height);
   if (st.environmentProb > 0.0f && !r->envMap && r->sunSky.in_use != 1)
@@ -192,13 +126,13 @@ static void fillParams(eid_renderer* r, const RtxState& st, int frames, FramePar
 static inline void markStart(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage], st)); }
 static inline void markStop(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage + 1], st)); }
 
-static void beginFrame(eid_renderer* r) {
+void beginFrame(eid_renderer* r) {
   CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
   memset(&r->stats, 0, sizeof(r->stats));
   r->postStarted = false;
 }
 
-static void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
+void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_DIRECT, st);
   if (P.sCount > 0) {
     dim3 g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
@@ -230,10 +164,11 @@ static void traceQueue(eid_renderer* r, bool any, const FrameParams& P, const fl
   r->stats.kernelLaunches[EID_K_INDIRECT]++;
 }
 
-static void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
+void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_INDIRECT, st);
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
-    dim3 g((P.st.size.x / 2 + 7) / 8, P.sCount * (P.sRows / 16));
+    // 8 x 8 quarter-res tiles on ABSOLUTE tile rows: a band that starts inside a tile row gets one more (masked) block row
+    dim3 g((P.st.size.x / 2 + 7) / 8, P.sCount * ((((P.sFirst / 2) & 7) + P.sRows / 2 + 7) / 8));
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
       // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
@@ -428,7 +363,7 @@ static void launchTrace(eid_renderer* r, const FrameParams& P) {
   stageIndirect(r, P, r->stream);
 }
 
-static void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
+void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
   const PostLayout L = postLayout(P, sharded);
   if (r->profiling) CUDA_CHECK(cudaEventRecord(r->evPost, r->stream));   // everything between the trace stages and here = exchange
   r->postStarted = true;
@@ -465,7 +400,7 @@ static void launchFrame(eid_renderer* r, const FrameParams& P) {
   endFrame(r);
 }
 
-static void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
+void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
   const size_t n = (size_t)r->width * r->height, ni = (size_t)(r->width / 2) * (r->height / 2);
   const int set = r->lastSet;
   switch (which) {
@@ -1028,7 +963,7 @@ int eid_renderer_set_band(eid_renderer* r, uint32_t y0, uint32_t y1) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_band: null renderer");
   if (y0 > y1 || y1 > r->height) raise(EID_ERR_INVALID, "band [%u,%u) outside 0..%u", y0, y1, r->height);
-  if ((y0 % 16) != 0 || (y1 % 16) != 0) raise(EID_ERR_INVALID, "band edges must be multiples of 16 rows (8x8 half-res tiles must not straddle ranks)");
+  if ((y0 % 8) != 0 || (y1 % 8) != 0) raise(EID_ERR_INVALID, "band edges must be multiples of 8 rows (the direct stage works in 8 x 8 pixel tiles)");
   if (y1 == y0) raise(EID_ERR_INVALID, "empty band");
   r->sFirst = y0; r->sRows = y1 - y0; r->sStride = 1u << 20; r->stripesSet = true;
   return EID_OK;

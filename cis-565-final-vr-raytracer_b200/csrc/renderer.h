@@ -1,0 +1,78 @@
+// renderer.h — the Renderer object (buffers + launch schedule state) shared by render.cu (C-ABI of the reference's Renderer class)
+// and group.cu (multi-GPU group: one renderer per rank + the NCCL exchange steps).
+#pragma once
+#include <map>
+#include <tuple>
+#include <vector>
+#include "stages.h"
+
+using namespace eid;   // internal header of the two translation units that implement the C-ABI
+
+// ------------------------------------------------------------------------------------------------
+// Renderer object
+// ------------------------------------------------------------------------------------------------
+struct eid_renderer {
+  eid_scene* scene = nullptr;
+  eid_accel* accel = nullptr;
+  int device = 0;
+  uint32_t width = 0, height = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  uint4* gbuffer[2] = {nullptr, nullptr};
+  short2* motion = nullptr;
+  float* directResv[2] = {nullptr, nullptr};
+  float* indirectResv[2] = {nullptr, nullptr};
+  float4* directImg = nullptr; float4* indirectImg = nullptr;
+  float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
+  float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
+  float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
+  float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
+  float4* mipScratch = nullptr;                             // auto exposure: two ping-pong mip levels + the two 1x1 averages
+  // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
+  void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
+  cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
+  int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
+  int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
+  int smCount = 0;
+  int denoiseRowBlock = 2;    // legacy A-Trous kernel: pixels of one column filtered per thread (1, 2 or 4; 2 measured fastest)
+  int denoiseTiles = 1;       // 1 (default): shared-memory tile kernel fed by TMA; 2: same, tiles loaded with cp.async; 0: legacy kernel (L1-served taps)
+  int denoiseTileRows = 2;    // tile kernel: lattice rows per thread (2 or 4; 2 measured faster: 66 vs 96 registers)
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> tmaps;   // (buffer, pitch, rows, level, tile height) -> lattice-view tensor map
+  bool strictMath = false;    // bit-reproducible exp in the denoiser (parity runs) instead of MUFU ex2
+  unsigned long long* counters = nullptr;
+  unsigned long long* countersHost = nullptr;   // pinned
+  float env[3] = {0.f, 0.f, 0.f};
+  eid_env* envMap = nullptr;
+  SunAndSky sunSky{};         // SampleExample::m_sunAndSky (sample_example.hpp:186-203); in_use = 0 until the host sets it
+  int lastSet = 0;
+  RtxState lastState{};
+  bool hasRun = false;
+  uint32_t sFirst = 0, sStride = 0, sRows = 0; bool stripesSet = false;   // multi-GPU row ownership (see FrameParams)
+  bool profiling = false;
+  bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
+  cudaEvent_t ev[2 * EID_K_COUNT] = {};   // start/stop per stage
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evPost = nullptr;
+  cudaStream_t aux = nullptr;             // second stream: K3 runs beside K2/K4 (see launchFrame)
+  bool overlap = true;
+  bool postStarted = false;
+  cudaStream_t copyStream = nullptr;      // eid_renderer_render_host_async: D2H of frame f overlaps the kernels of frame f+1
+  cudaEvent_t evFrameDone = nullptr, evCopyDone = nullptr;
+  float4* staging[2] = {nullptr, nullptr};
+  bool copyPending = false;
+  eid_frame_stats stats{};
+  bool statsPending = false;
+
+  void allocate();
+  void release();
+  void ensureWave(int terms);
+  WaveView waveView() const;
+};
+
+
+// per-frame pieces of eid_renderer_run (render.cu), reused by the multi-GPU schedule of group.cu
+void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P);
+void beginFrame(eid_renderer* r);
+void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
+void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
+void launchPost(eid_renderer* r, const FrameParams& P, bool sharded);
+void* bufferPtr(eid_renderer* r, int which, size_t& bytes);

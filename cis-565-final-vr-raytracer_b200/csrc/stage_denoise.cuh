@@ -52,6 +52,20 @@ DEV void cpAsync16(void* smemDst, const void* gsrc, bool valid) {   // 16-byte L
 DEV void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 
+#ifndef EID_DENOISE_PACKED
+#define EID_DENOISE_PACKED 0     // 1: fast path on pixel pairs with FADD2 / FFMA2 (measured: see profiles/README.md)
+#endif
+// ---- Blackwell packed fp32 pairs (FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per issue slot) ---------------------------------
+typedef unsigned long long p2;                         // (lo, hi) in one 64-bit register pair
+DEV p2 pk(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+DEV p2 pkv(float lo, float hi) { p2 r; asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }   // never rematerialised
+DEV void upk(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DEV p2 padd(p2 a, p2 b) { p2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+DEV p2 psub(p2 a, p2 b) { p2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+DEV p2 pmul(p2 a, p2 b) { p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+DEV p2 pfma(p2 a, p2 b, p2 c) { p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+DEV float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // weights of the fast path on pre-scaled planes; returns w * (hash match)
 DEV float fastWeightDirect(float cLum, float4 cN2, float cNN, f3 cPos, uint32_t cHash, const float4& qp, const float4& qn, const float4& qc, float g) {
   float wc, wn, wd;
@@ -209,6 +223,103 @@ __global__ void __launch_bounds__(128) k_atrous_tile(const FrameParams P, const 
         }
       }
     }
+#if EID_DENOISE_PACKED
+  } else {
+    // Fast path on pixel PAIRS (k, k + 1): every tap that serves both pixels of a pair is evaluated once with packed fp32 (the tap's
+    // value is the broadcast scalar operand of FADD2 / FFMA2), so the 19 fp32 operations of a tap weight cost 10 issue slots per pixel;
+    // the three exponentials stay scalar MUFU ex2.  A tap row that serves only one pixel of the pair runs the same code with the
+    // other half's Gaussian weight = 0.
+    constexpr float G[25] = {.0030f, .0133f, .0219f, .0133f, .0030f, .0133f, .0596f, .0983f, .0596f, .0133f, .0219f, .0983f, .1621f,
+                             .0983f, .0219f, .0133f, .0596f, .0983f, .0596f, .0133f, .0030f, .0133f, .0219f, .0133f, .0030f};
+    static_assert(R % 2 == 0, "the fast path works on pixel pairs");
+    constexpr int NP = R / 2;
+    p2 cPx[NP], cPy[NP], cPz[NP], cNx[NP], cNy[NP], cNz[NP], cNN[NP], cC0[NP], cC1[NP], cC2[NP];   // centres; cC0 = lum (direct) or colour.x
+    p2 sx[NP], sy[NP], sz[NP], sw[NP];
+#pragma unroll
+    for (int pr = 0; pr < NP; ++pr) {
+      const float4 p0 = sPos[ly0 + 2 * pr][lx], p1 = sPos[ly0 + 2 * pr + 1][lx];
+      const float4 n0 = sNrm[ly0 + 2 * pr][lx], n1 = sNrm[ly0 + 2 * pr + 1][lx];
+      const float4 c0 = sCol[ly0 + 2 * pr][lx], c1 = sCol[ly0 + 2 * pr + 1][lx];
+      cPx[pr] = pkv(p0.x, p1.x); cPy[pr] = pkv(p0.y, p1.y); cPz[pr] = pkv(p0.z, p1.z);
+      cNx[pr] = pkv(2.0f * n0.x, 2.0f * n1.x); cNy[pr] = pkv(2.0f * n0.y, 2.0f * n1.y); cNz[pr] = pkv(2.0f * n0.z, 2.0f * n1.z);
+      cNN[pr] = pkv(n0.w, n1.w);
+      if (INDIRECT) { cC0[pr] = pkv(c0.x, c1.x); cC1[pr] = pkv(c0.y, c1.y); cC2[pr] = pkv(c0.z, c1.z); }
+      else { cC0[pr] = pkv(c0.w, c1.w); cC1[pr] = cC2[pr] = 0; }
+      sx[pr] = sy[pr] = sz[pr] = sw[pr] = pk(0.f, 0.f);
+    }
+    const p2 c001 = pk(1e-2f, 1e-2f);
+#pragma unroll
+    for (int rr = 0; rr < R + 4; ++rr) {
+#pragma unroll
+      for (int i = -2; i <= 2; i++) {
+        const float4 qp = sPos[ly0 - 2 + rr][lx + i], qn = sNrm[ly0 - 2 + rr][lx + i], qc = sCol[ly0 - 2 + rr][lx + i];
+        const uint32_t hq = __float_as_uint(qp.w);
+#pragma unroll
+        for (int pr = 0; pr < NP; ++pr) {
+          const int j0 = rr - 2 - 2 * pr, j1 = j0 - 1;
+          const bool v0 = j0 >= -2 && j0 <= 2, v1 = j1 >= -2 && j1 <= 2;
+          if (!v0 && !v1) continue;
+          if (v0 != v1) {                                  // the tap serves one pixel of the pair: scalar weight on that half
+            const int k = v0 ? 2 * pr : 2 * pr + 1, j = v0 ? j0 : j1;
+            float a0, a1, ax, ay, az, aw, b0, b1;
+            f3 cp, cc; float4 cn2; float cnn, cl;
+            upk(cPx[pr], a0, a1); cp.x = v0 ? a0 : a1; upk(cPy[pr], a0, a1); cp.y = v0 ? a0 : a1; upk(cPz[pr], a0, a1); cp.z = v0 ? a0 : a1;
+            upk(cNx[pr], a0, a1); ax = v0 ? a0 : a1; upk(cNy[pr], a0, a1); ay = v0 ? a0 : a1; upk(cNz[pr], a0, a1); az = v0 ? a0 : a1;
+            upk(cNN[pr], a0, a1); cnn = v0 ? a0 : a1; aw = 0.f;
+            cn2 = make_float4(ax, ay, az, aw);
+            upk(cC0[pr], a0, a1); cl = v0 ? a0 : a1; cc.x = cl;
+            upk(cC1[pr], a0, a1); cc.y = v0 ? a0 : a1; upk(cC2[pr], a0, a1); cc.z = v0 ? a0 : a1;
+            const float g = G[(i + 2) * 5 + (j + 2)];
+            const float w = INDIRECT ? fastWeightIndirect(cc, cn2, cnn, cp, hash[k], qp, qn, qc, g) : fastWeightDirect(cl, cn2, cnn, cp, hash[k], qp, qn, qc, g);
+            upk(sx[pr], b0, b1); if (v0) b0 = fmaf(qc.x, w, b0); else b1 = fmaf(qc.x, w, b1); sx[pr] = pk(b0, b1);
+            upk(sy[pr], b0, b1); if (v0) b0 = fmaf(qc.y, w, b0); else b1 = fmaf(qc.y, w, b1); sy[pr] = pk(b0, b1);
+            upk(sz[pr], b0, b1); if (v0) b0 = fmaf(qc.z, w, b0); else b1 = fmaf(qc.z, w, b1); sz[pr] = pk(b0, b1);
+            upk(sw[pr], b0, b1); if (v0) b0 += w; else b1 += w; sw[pr] = pk(b0, b1);
+            continue;
+          }
+          const float g0 = G[(i + 2) * 5 + (j0 + 2)], g1 = G[(i + 2) * 5 + (j1 + 2)];
+          // colour term
+          float wc0, wc1;
+          if (INDIRECT) {
+            const p2 dx = psub(cC0[pr], pk(qc.x, qc.x)), dy = psub(cC1[pr], pk(qc.y, qc.y)), dz = psub(cC2[pr], pk(qc.z, qc.z));
+            float e0, e1;
+            upk(pfma(dz, dz, pfma(dy, dy, pfma(dx, dx, pk(qc.w, qc.w)))), e0, e1);   // qc.w = 0, or NaN for a non-finite tap colour
+            wc0 = ex2f(-e0); wc1 = ex2f(-e1);
+          } else {
+            float d0, d1;
+            upk(psub(cC0[pr], pk(qc.w, qc.w)), d0, d1);
+            wc0 = ex2f(-fabsf(d0)); wc1 = ex2f(-fabsf(d1));
+          }
+          // normal term: -(|n|^2 + |q|^2 - 2 n.q) on the pre-scaled normals
+          float en0, en1;
+          upk(pfma(cNx[pr], pk(qn.x, qn.x), pfma(cNy[pr], pk(qn.y, qn.y), pfma(cNz[pr], pk(qn.z, qn.z), padd(cNN[pr], pk(qn.w, qn.w))))), en0, en1);
+          const float wn0 = ex2f(en0), wn1 = ex2f(en1);
+          // depth term
+          const p2 px_ = psub(cPx[pr], pk(qp.x, qp.x)), py_ = psub(cPy[pr], pk(qp.y, qp.y)), pz_ = psub(cPz[pr], pk(qp.z, qp.z));
+          float ep0, ep1;
+          upk(pfma(pz_, pz_, pfma(py_, py_, pmul(px_, px_))), ep0, ep1);
+          const float wd0 = ex2f(-ep0), wd1 = ex2f(-ep1);
+          float w0, w1;
+          upk(pmul(pmul(padd(pk(wc0, wc1), c001), pk(wn0, wn1)), padd(pk(wd0, wd1), c001)), w0, w1);
+          w0 = (hq == hash[2 * pr]) ? w0 * g0 : 0.0f;
+          w1 = (hq == hash[2 * pr + 1]) ? w1 * g1 : 0.0f;
+          const p2 w = pk(w0, w1);
+          sx[pr] = pfma(w, pk(qc.x, qc.x), sx[pr]); sy[pr] = pfma(w, pk(qc.y, qc.y), sy[pr]); sz[pr] = pfma(w, pk(qc.z, qc.z), sz[pr]);
+          sw[pr] = padd(sw[pr], w);
+        }
+      }
+    }
+    const float inv = INDIRECT ? 1.0f / sqrtf(LOG2E / sigL) : 1.0f;   // the indirect colour plane was scaled by sqrt(log2e / sigL) for the distance
+#pragma unroll
+    for (int pr = 0; pr < NP; ++pr) {
+      float a0, a1, b0, b1, c0, c1, d0, d1;
+      upk(sx[pr], a0, a1); upk(sy[pr], b0, b1); upk(sz[pr], c0, c1); upk(sw[pr], d0, d1);
+      sum[2 * pr] = mk3(a0 * inv, b0 * inv, c0 * inv); sum[2 * pr + 1] = mk3(a1 * inv, b1 * inv, c1 * inv);
+      sumW[2 * pr] = d0; sumW[2 * pr + 1] = d1;
+    }
+  }
+
+#else
   } else {
     constexpr float G[25] = {.0030f, .0133f, .0219f, .0133f, .0030f, .0133f, .0596f, .0983f, .0596f, .0133f, .0219f, .0983f, .1621f,
                              .0983f, .0219f, .0133f, .0596f, .0983f, .0596f, .0133f, .0030f, .0133f, .0219f, .0133f, .0030f};
@@ -246,15 +357,20 @@ __global__ void __launch_bounds__(128) k_atrous_tile(const FrameParams P, const 
     }
   }
 
+#endif
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if (!inside[k]) continue;
     f3 res = mk3(0.0f);
     if (hash[k] != EID_INVALID_MAT) {                     // waveletFilter (denoise_direct.comp:19-71 / denoise_indirect.comp:23-75)
-      res = (sumW[k] < 1e-5f) ? mk3(0.0f) : sum[k] / sumW[k];
+      if (STRICT) res = (sumW[k] < 1e-5f) ? mk3(0.0f) : sum[k] / sumW[k];
+      else { const float inv = __fdividef(1.0f, sumW[k]); res = (sumW[k] < 1e-5f) ? mk3(0.0f) : mk3(sum[k].x * inv, sum[k].y * inv, sum[k].z * inv); }
       if (nan3(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = mk3(0.0f);
     }
-    if (level == A.lastLevel) res = ldrToHdr(res);        // denoise_direct.comp:168 / denoise_indirect.comp:169
+    if (level == A.lastLevel) {                           // denoise_direct.comp:168 / denoise_indirect.comp:169
+      if (STRICT) res = ldrToHdr(res);
+      else res = mk3(__fdividef(res.x, 1.01f - res.x), __fdividef(res.y, 1.01f - res.y), __fdividef(res.z, 1.01f - res.z));
+    }
     A.outImg[(size_t)(y0 + k * s) * A.iPitch + x] = make_float4(res.x, res.y, res.z, 1.0f);
   }
 }

@@ -99,7 +99,7 @@ DEV void giFinish(const FrameParams& P, int x, int y, int Wi, int Hi, uint32_t& 
 template <bool STATS, bool TEX>
 __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
+  const int y = tileAlignedRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2);
   RayCounters rc = {0, 0, 0, 0, 0};
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   if (x < Wi && y < Hi) {

@@ -32,7 +32,7 @@ DEV uint32_t warpEnqueue(uint32_t* counter, bool want) {
 template <bool TEX>
 __global__ void __launch_bounds__(64) k_gi_begin(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
+  const int y = tileAlignedRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2);
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   const uint32_t slot = (blockIdx.y * gridDim.x + blockIdx.x) * 64u + threadIdx.y * 8u + threadIdx.x;
   const WaveView& V = P.wv;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) k_gi_bounce(const FrameParams P, int d) {
 
 __global__ void __launch_bounds__(64) k_gi_finish(const FrameParams P) {
   const int x = blockIdx.x * 8 + threadIdx.x;
-  const int y = stripeRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2, 8);
+  const int y = tileAlignedRow(P.sFirst / 2, P.sStride / 2, P.sRows / 2);
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   if (x >= Wi || y >= Hi) return;
   const uint32_t slot = (blockIdx.y * gridDim.x + blockIdx.x) * 64u + threadIdx.y * 8u + threadIdx.x;

@@ -93,6 +93,28 @@ DEV float boxEntryNF(const RayBox& rb, float nx, float ny, float nz, float fx, f
   return (tn <= tf * 1.0000004f) ? tn : __int_as_float(0x7f800000);
 }
 
+// Blackwell packed fp32 (FFMA2 / FMUL2: two IEEE fp32 operations per issue slot; a scalar operand is broadcast for free):
+// (a.x, a.y) * s + t and (a.x, a.y) * s
+DEV float2 ffma2s(float2 a, float s, float t) {
+  unsigned long long ra, rs, rt, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rs) : "f"(s));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rt) : "f"(t));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rs), "l"(rt));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+DEV float2 fmul2s(float2 a, float s) {
+  unsigned long long ra, rs, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rs) : "f"(s));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rs));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 // 256-bit global load (sm_100a LDG.E.256): one L1 wavefront per lane for 32 B instead of two
 DEV void ldg256(const float4* p, float4& a, float4& b) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -107,6 +129,9 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 #endif
 #ifndef EID_Q8_MAGIC
 #define EID_Q8_MAGIC 0
+#endif
+#ifndef EID_TRAV_V1
+#define EID_TRAV_V1 0       // 1: the round-1 node step (scalar FFMA slab tests, 5-comparator child sort) for A/B measurements
 #endif
 #ifndef EID_FETCH_TEX
 #define EID_FETCH_TEX 2     // 0: every BVH fetch is an LDG; 2: far planes of a node come through tex1Dfetch (default); 1/3/4: experiments
@@ -127,11 +152,71 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 
 // One inner-node visit: box tests of the children, `cur` becomes the next reference to look at (nearest entered child, or the
 // top of the stack, or EID_TRAV_DONE), the other entered children go onto the stack.  ANY = occlusion ray: child order is irrelevant.
-template <bool ANY>
+// SORT (closest-hit only): all entered children in front-to-back order (incoherent rays of the ray queues); otherwise only the nearest one is
+// selected (coherent rays of the one-thread-per-pixel kernels, where the full order did not lower the node count).
+template <bool ANY, bool SORT = false>
 DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, int* stack, int& sp) {
   const float INF = __int_as_float(0x7f800000);
 #define EID_POP() (sp ? stack[--sp] : EID_TRAV_DONE)
-#if EID_BVH_WIDTH == 2
+#if EID_BVH_WIDTH == 4 && !EID_NODE_Q8 && !EID_TRAV_V1 && EID_FETCH_TEX == 2 && !defined(EID_NODE_LDG256)
+  // Round-2 node step.  Same slab arithmetic as boxEntryNF (bit-identical entry distances, hence the same visited set), issued as
+  // packed FFMA2 on the child pairs the SoA node layout already provides (12 instead of 24 FMA issue slots), the 1 + 4e-7 slack
+  // as two packed multiplies, and instead of a 5-comparator sort of (distance, ref) pairs only the NEAREST entered child is
+  // selected (min / max / select, 14 instructions); the other entered children are pushed in pair order.  The hit does not
+  // depend on the visiting order (total order on (t, instance, primitive)), and on the C3 scene the full sort did not lower
+  // the node count (13.5 per ray either way, profiles/README.md).
+  const float4* n = A.nodes + 8 * (size_t)cur;
+  const int nb = 8 * cur;
+  const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);
+  const float4 hx = tex1Dfetch<float4>(A.nodeTex, nb + rb.fx), hy = tex1Dfetch<float4>(A.nodeTex, nb + rb.fy), hz = tex1Dfetch<float4>(A.nodeTex, nb + rb.fz);
+  const float4 rf = __ldg(n + 6);
+  const float2 ax = ffma2s(make_float2(lx.x, lx.y), rb.ix, -rb.ox), bx = ffma2s(make_float2(lx.z, lx.w), rb.ix, -rb.ox);
+  const float2 ay = ffma2s(make_float2(ly.x, ly.y), rb.iy, -rb.oy), by = ffma2s(make_float2(ly.z, ly.w), rb.iy, -rb.oy);
+  const float2 az = ffma2s(make_float2(lz.x, lz.y), rb.iz, -rb.oz), bz = ffma2s(make_float2(lz.z, lz.w), rb.iz, -rb.oz);
+  const float2 fax = ffma2s(make_float2(hx.x, hx.y), rb.ix, -rb.ox), fbx = ffma2s(make_float2(hx.z, hx.w), rb.ix, -rb.ox);
+  const float2 fay = ffma2s(make_float2(hy.x, hy.y), rb.iy, -rb.oy), fby = ffma2s(make_float2(hy.z, hy.w), rb.iy, -rb.oy);
+  const float2 faz = ffma2s(make_float2(hz.x, hz.y), rb.iz, -rb.oz), fbz = ffma2s(make_float2(hz.z, hz.w), rb.iz, -rb.oz);
+  const float tn0 = fmaxf(fmaxf(ax.x, ay.x), fmaxf(az.x, 0.0f)), tn1 = fmaxf(fmaxf(ax.y, ay.y), fmaxf(az.y, 0.0f));
+  const float tn2 = fmaxf(fmaxf(bx.x, by.x), fmaxf(bz.x, 0.0f)), tn3 = fmaxf(fmaxf(bx.y, by.y), fmaxf(bz.y, 0.0f));
+  const float2 tfa = fmul2s(make_float2(fminf(fminf(fax.x, fay.x), fminf(faz.x, tbest)), fminf(fminf(fax.y, fay.y), fminf(faz.y, tbest))), 1.0000004f);
+  const float2 tfb = fmul2s(make_float2(fminf(fminf(fbx.x, fby.x), fminf(fbz.x, tbest)), fminf(fminf(fbx.y, fby.y), fminf(fbz.y, tbest))), 1.0000004f);
+  float e0 = (tn0 <= tfa.x) ? tn0 : INF, e1 = (tn1 <= tfa.y) ? tn1 : INF, e2 = (tn2 <= tfb.x) ? tn2 : INF, e3 = (tn3 <= tfb.y) ? tn3 : INF;
+  const int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
+  if (ANY) {
+    int next = 0; bool have = false;
+    if (e0 < INF) { next = c0; have = true; }
+    if (e1 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c1; } else { next = c1; have = true; } }
+    if (e2 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c2; } else { next = c2; have = true; } }
+    if (e3 < INF) { if (have) { if (EID_SP_OK(sp)) stack[sp++] = c3; } else { next = c3; have = true; } }
+    cur = have ? next : EID_POP();
+  } else if (SORT) {
+    // 5-comparator network on (distance, ref) pairs, each comparator = compare + min + max + 2 selects
+    int d0 = c0, d1 = c1, d2 = c2, d3 = c3;
+#define EID_CSWAP2(ea, ca, eb, cb) { const bool s_ = eb < ea; const float lo_ = fminf(ea, eb), hi_ = fmaxf(ea, eb); const int cl_ = s_ ? cb : ca, ch_ = s_ ? ca : cb; ea = lo_; eb = hi_; ca = cl_; cb = ch_; }
+    EID_CSWAP2(e0, d0, e1, d1) EID_CSWAP2(e2, d2, e3, d3) EID_CSWAP2(e0, d0, e2, d2) EID_CSWAP2(e1, d1, e3, d3) EID_CSWAP2(e1, d1, e2, d2)
+#undef EID_CSWAP2
+    if (e0 < INF) {
+      if (e3 < INF && EID_SP_OK(sp)) stack[sp++] = d3;
+      if (e2 < INF && EID_SP_OK(sp)) stack[sp++] = d2;
+      if (e1 < INF && EID_SP_OK(sp)) stack[sp++] = d1;
+      cur = d0;
+    } else cur = EID_POP();
+  } else {
+    // nearest of each pair, then the nearer of the two winners; the three children not chosen are pushed when entered
+    const bool s01 = e1 < e0, s23 = e3 < e2;
+    const float w01 = fminf(e0, e1), l01 = fmaxf(e0, e1), w23 = fminf(e2, e3), l23 = fmaxf(e2, e3);
+    const int cw01 = s01 ? c1 : c0, cl01 = s01 ? c0 : c1, cw23 = s23 ? c3 : c2, cl23 = s23 ? c2 : c3;
+    const bool sw = w23 < w01;
+    const float wn = fminf(w01, w23), wl = fmaxf(w01, w23);
+    const int cn = sw ? cw23 : cw01, cl = sw ? cw01 : cw23;
+    if (wn < INF) {
+      if (l01 < INF && EID_SP_OK(sp)) stack[sp++] = cl01;
+      if (l23 < INF && EID_SP_OK(sp)) stack[sp++] = cl23;
+      if (wl < INF && EID_SP_OK(sp)) stack[sp++] = cl;          // the second winner is popped first
+      cur = cn;
+    } else cur = EID_POP();
+  }
+#elif EID_BVH_WIDTH == 2
   const float4* n = A.nodes + 4 * (size_t)cur;
   const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
   float e0 = boxEntry(rb, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tbest);
@@ -370,7 +455,7 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
       if (!__any_sync(0xffffffffu, inner)) break;
       if (inner) {
         if (STATS) ++nodeVisits;
-        nodeStep<ANY>(A, rb, hit.t, cur, stack, sp);
+        nodeStep<ANY, true>(A, rb, hit.t, cur, stack, sp);
       }
     }
     if (active && cur < 0) {

@@ -1,8 +1,9 @@
 """Screen-space sharding of one frame across the GPUs of a node (no reference analogue).
 
 Rank r traces (direct_stage + indirect_stage) the full-resolution row band [r*B, (r+1)*B), B = rows per rank rounded
-up to a multiple of 16 so that no 8x8 half-resolution tile (and therefore no shared multi-bounce flag,
-indirect_stage.comp:283-288) straddles two ranks.  Every image is allocated with world*B rows, which makes each
+up to a multiple of 8 (the direct stage works in 8x8 pixel tiles; the quarter-res stage lays its 8x8 tiles over ABSOLUTE tile
+rows and masks the rows of a tile that belong to the neighbour, so the shared multi-bounce flag of indirect_stage.comp:283-288
+stays a function of the absolute tile): 1080 rows on 8 ranks = 7 bands of 136 rows + one of 128.  Every image is allocated with world*B rows, which makes each
 rank's slice of every exchange buffer the same size, so ONE exchange step of equal-sized all-gathers (in place:
 rank r's slice already sits at offset r*chunk of the full buffer) gives every rank the complete pre-denoise frame.
 Denoise + compose then run on the full frame on every rank; every rank ends with the complete composed image.
@@ -10,7 +11,7 @@ Denoise + compose then run on the full frame on every rank; every rank ends with
 
 
 def band_rows(height, world):
-    return ((height + world - 1) // world + 15) // 16 * 16
+    return ((height + world - 1) // world + 7) // 8 * 8
 
 
 def padded_height(height, world):

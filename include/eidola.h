@@ -344,7 +344,8 @@ EID_API int  eid_renderer_get_stats(eid_renderer* r, eid_frame_stats* out);
 
 /* ---- multi-GPU band sharding (new; no reference analogue) --------------------
  * Rank `rank` of `world` traces (direct_stage + indirect_stage) only full-res rows
- * [y0, y1) of the frame (band edges multiples of 16 so 8x8 half-res tiles never straddle).
+ * [y0, y1) of the frame (band edges multiples of 8: the direct stage works in 8x8 pixel tiles, the quarter-res stage lays its
+ * 8x8 tiles over absolute tile rows and masks what belongs to the neighbour).
  * eid_renderer_run_trace enqueues the two trace kernels for the band; the caller then
  * all-gathers the three exchange buffers below (the ONE collective) and calls
  * eid_renderer_run_post, which runs denoise+compose on the full frame. */
@@ -368,6 +369,40 @@ EID_API int  eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, 
 /* = eid_renderer_exchange_range(group 0): device pointer + byte range of this rank's band inside buffer `which`
  * (EID_BUF_THIS_GBUFFER, EID_BUF_DIRECT, EID_BUF_DENOISE_IND_A, EID_BUF_MOTION, reservoirs) */
 EID_API int  eid_renderer_band_range(eid_renderer* r, int which, void** dev_base, uint64_t* offset, uint64_t* bytes);
+
+/* ---- eid_group: one frame on the N GPUs of a node (SURVEY.md §8(b) last row, §8(e); new, no reference analogue) -------------------------
+ * One process or thread per GPU.  Every rank creates its scene / accel / renderer on its own device, the renderer with the padded height of
+ * eid_group_layout (N equal bands, multiples of 8 rows), then joins the group: rank 0 obtains a 128-byte id with eid_group_unique_id and
+ * the host hands it to the other ranks by whatever means it has (MPI, a socket, torch.distributed, a file).  The library owns the NCCL
+ * communicator (libnccl.so.2, loaded at the first eid_group call) and a communication stream; eid_group_run enqueues the whole frame —
+ * band trace stages, exchange A (G-buffer + direct image, behind indirect_stage), exchange B (quarter-res indirect image), denoise +
+ * compose, exchange C (all-gather of the composed images) — each exchange ONE NCCL launch.  Every rank ends with the complete composed
+ * frame, bit-identical to eid_renderer_run on one GPU (also with a moving camera: see eid_group_set_mode). */
+typedef struct eid_group eid_group;
+typedef struct eid_group_info {
+  int32_t  rank, world;
+  uint32_t y0, y1;            /* full-res rows this rank owns (y1 may exceed the rendered height on the last rank) */
+  uint32_t bandRows;
+  int32_t  ncclVersion;       /* e.g. 22809 */
+  uint64_t collectives;       /* NCCL launches since creation */
+} eid_group_info;
+EID_API int  eid_group_layout(uint32_t height, int world, int rank, uint32_t* y0, uint32_t* y1, uint32_t* padded_height);
+EID_API int  eid_group_unique_id(void* id128);
+EID_API int  eid_group_create(eid_group** out, eid_renderer* r, int rank, int world, const void* id128);
+EID_API void eid_group_destroy(eid_group* g);
+/* post_sharded 1 (default): every rank denoises + composes its band only; 0: the whole frame on every rank (no exchange C).
+ * history: how last frame's reservoirs cross band edges for temporal reuse.  0: never (exact for a static camera only); 1: gathered every
+ * frame behind the post stages; 2 (default): gathered lazily, before the direct stage of a frame whose camera moved (projView != lastProjView).
+ * gather_final 1 (default): exchange C; 0: every rank keeps only its band of the composed images. */
+EID_API int  eid_group_set_mode(eid_group* g, int post_sharded, int history, int gather_final);
+EID_API int  eid_group_run(eid_group* g, const RtxState* state, int frames);
+/* host delivery without a funnel: every rank copies ITS band of the composed images into the (shared, pinned) host images over its own
+ * PCIe link, pipelined behind the next frame; exchange C is skipped.  Images: size.x * 16 bytes per row, full frame. */
+EID_API int  eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxState* state, int frames,
+                                         float* direct_host, float* indirect_host);
+EID_API int  eid_group_wait_host(eid_group* g);
+EID_API int  eid_group_sync(eid_group* g);
+EID_API int  eid_group_get_info(eid_group* g, eid_group_info* out);
 
 #ifdef __cplusplus
 }

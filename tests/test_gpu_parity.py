@@ -569,8 +569,9 @@ def test_state_size_smaller_than_allocation():
         assert all(v == 0.0 for v in rep.values()), "strict math must be bit-exact, got %s" % rep
 
 
-@pytest.mark.parametrize("restir,exchange_history", [(abi.eTemporal, True), (abi.eSpatiotemporal, True), (abi.eSpatiotemporal, False)])
-def test_band_sharded_trace_equals_full_frame(restir, exchange_history):
+@pytest.mark.parametrize("restir,exchange_history,orbit", [(abi.eTemporal, True, False), (abi.eSpatiotemporal, True, False), (abi.eSpatiotemporal, False, False),
+                                                          (abi.eTemporal, True, True), (abi.eSpatiotemporal, True, True)])
+def test_band_sharded_trace_equals_full_frame(restir, exchange_history, orbit):
     """Multi-GPU decomposition on one device: two renderers trace disjoint row bands, the exchange buffers are
     stitched (what the all-gather does), post-processing runs on the full frame -> identical to a single run.  With spatial reuse
     each band also carries the row above and the row below it up to the tempDirectResv write (the halo launch of k_direct_stage)."""
@@ -584,8 +585,8 @@ def test_band_sharded_trace_equals_full_frame(restir, exchange_history):
     for r in (full, a, b):
         r.create(size, psc, acc)
         r.set_env_constant(common.ENV)
-    a.set_band(0, 80)
-    b.set_band(80, 144)
+    a.set_band(0, 72)            # 72 / 2 = 36 quarter-res rows: the band edge lies in the MIDDLE of an 8x8 quarter-res tile row
+    b.set_band(72, 144)
     info = psc.info()
     psc.update_camera(*size)
     exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_MOTION, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A, abi.BUF_THIS_DIRECT_RESV,
@@ -594,7 +595,12 @@ def test_band_sharded_trace_equals_full_frame(restir, exchange_history):
         # what bench.py exchanges (static camera): no reservoir history crosses the ranks; with spatial reuse the halo rows keep their own
         # direct-reservoir history, so the rows next to a band edge still see the neighbour's reservoir of the previous frame
         exchange = [abi.BUF_THIS_GBUFFER, abi.BUF_DIRECT, abi.BUF_DENOISE_IND_A]
-    for f in range(3):
+    cam = arrays.camera
+    for f in range(4 if orbit else 3):
+        if orbit:                 # moving camera: temporal reprojection crosses the band edge, so the reservoir history must be exchanged too
+            ang = np.deg2rad(1.5 * f)
+            e = np.array(cam["eye"], np.float64)
+            psc.set_lookat((e[0] * np.cos(ang) - e[2] * np.sin(ang), e[1] + 0.15 * f, e[0] * np.sin(ang) + e[2] * np.cos(ang)), cam["center"], cam["up"], np.rad2deg(cam["yfov"]))
         psc.update_camera(*size)
         st = common.frame_state(size[0], size[1], info, f, ReSTIRState=restir)
         full.run(st, f)
@@ -631,7 +637,7 @@ def test_band_sharded_post_equals_full_frame():
     full = eid.Renderer()
     full.create(size, psc, acc)
     full.set_env_constant(common.ENV)
-    bands = [(0, 48), (48, 112), (112, 160)]
+    bands = [(0, 40), (40, 104), (104, 160)]      # multiples of 8 rows; 40 / 2 = 20 and 104 / 2 = 52 are not multiples of 8 (mid-tile edges)
     ranks = []
     for y0, y1 in bands:
         r = eid.Renderer()
@@ -782,7 +788,7 @@ def test_error_behaviour_gpu():
     with pytest.raises(eid.EidolaError):
         r.run(common.frame_state(64, 64, info, 0, environmentProb=0.25), 0)  # needs an HDR map (sun & sky not implemented)
     with pytest.raises(eid.EidolaError):
-        r.set_band(8, 64)                                                     # band edges must be multiples of 16
+        r.set_band(4, 64)                                                     # band edges must be multiples of 8
     r.run(common.frame_state(64, 64, info, 0), 0)                             # still usable after errors
     r.sync()
 
@@ -847,3 +853,42 @@ def test_interleaved_stripes_equal_full_frame(mode):
     # ray counters: the ranks together issue exactly the rays of the single-GPU frame
     tot = [sum(getattr(r.stats(), k) for r in ranks) for k in ("closestHitRays", "anyHitRays")]
     assert tot == [full.stats().closestHitRays, full.stats().anyHitRays]
+
+
+def test_group_of_one_equals_renderer_and_delivers_bands():
+    """eid_group with world = 1 (no NCCL involved): the group schedule == eid_renderer_run, and eid_group_render_host_async delivers the
+    band (here: the whole frame) into host images like eid_renderer_render_host does.  The N > 1 collectives are exercised by bench.py
+    under torchrun (image_crc32 of the N-GPU frame == the 1-GPU frame) and, stage by stage, by the band tests above."""
+    arrays = scenes.cornell_scene()
+    size = (160, 96)
+    psc = eid.Scene(0); psc.load_arrays(arrays)
+    acc = eid.AccelStructure(); acc.create(psc)
+    r1, r2 = eid.Renderer(), eid.Renderer()
+    for r in (r1, r2):
+        r.create(size, psc, acc); r.set_env_constant(common.ENV)
+    assert eid.Group.layout(1080, 8, 7) == (952, 1088, 1088) and eid.Group.layout(1080, 1) == (0, 1080, 1080)
+    assert eid.Group.layout(size[1], 2, 1) == (48, 96, 96)
+    g = eid.Group()
+    g.create(r2, 0, 1)
+    g.set_mode(True, 2, True)
+    info = psc.info()
+    psc.update_camera(*size)
+    d = [np.zeros((size[1], size[0], 4), np.float32) for _ in range(2)]
+    i = [np.zeros_like(d[0]) for _ in range(2)]
+    for f in range(4):
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f)
+        r1.run(st, f)
+        if f < 2:
+            g.run(st, f); g.sync()
+        else:
+            g.render_host_async(psc.get_camera(), st, f, d[f & 1].ctypes.data, i[f & 1].ctypes.data); g.wait_host()
+            assert r1.read(abi.BUF_DIRECT).tobytes() == d[f & 1].tobytes() and r1.read(abi.BUF_INDIRECT).tobytes() == i[f & 1].tobytes()
+        for k, which in common.BUFFERS:
+            assert r1.read(which).tobytes() == r2.read(which).tobytes(), "group frame %d: %s differs" % (f, k)
+    gi = g.info()
+    assert (gi.rank, gi.world, gi.y0, gi.y1, gi.collectives) == (0, 1, 0, size[1], 0)
+    with pytest.raises(eid.EidolaError):
+        eid.Group().create(r1, 0, 2, None)                                    # world > 1 needs the unique id
+    with pytest.raises(eid.EidolaError):
+        eid.Group().create(r1, 3, 2, bytes(128))

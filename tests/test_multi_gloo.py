@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-W, H = 96, 72            # 72 rows / 2 ranks = 36 -> bands of 48 rows, padded allocation 96 rows
+W, H = 96, 72            # 72 rows / 2 ranks = 36 -> bands of 40 rows (a band edge in the middle of a quarter-res tile row), padded allocation 80 rows
 
 
 def _worker(rank, world, port, out, restir):
@@ -60,12 +60,12 @@ def test_band_partition_properties():
     for h in (1080, 2160, 72, 17, 1):
         for world in (1, 2, 4, 8):
             b = sharding.band_rows(h, world)
-            assert b % 16 == 0 and b * world >= h
+            assert b % 8 == 0 and b * world >= h
             rows = [sharding.band_range(r, world, h) for r in range(world)]
             assert rows[0][0] == 0 and all(a[1] == c[0] for a, c in zip(rows, rows[1:]))
             assert rows[-1][1] == sharding.padded_height(h, world) or world == 1
-            assert all((y0 % 16) == 0 for y0, _ in rows)
-    assert sharding.band_rows(1080, 8) == 144 and sharding.padded_height(1080, 8) == 1152
+            assert all((y0 % 8) == 0 for y0, _ in rows)
+    assert sharding.band_rows(1080, 8) == 136 and sharding.padded_height(1080, 8) == 1088
 
 
 @pytest.mark.parametrize("restir", [3, 4])      # eTemporal (default), eSpatiotemporal (neighbour reads cross the band edge)
