@@ -181,7 +181,7 @@ class GroupInfo(C.Structure):   # eid_group_info
 
 # eid_scene_table
 (TABLE_MATERIALS, TABLE_PUNC_LIGHTS, TABLE_TRIG_LIGHTS, TABLE_LIGHT_INFO, TABLE_INSTANCE_DATA, TABLE_VERTICES,
- TABLE_INDICES, TABLE_CAMERA) = range(8)
+ TABLE_INDICES, TABLE_CAMERA, TABLE_TEXELS) = range(9)
 # eid_buffer
 (BUF_THIS_GBUFFER, BUF_LAST_GBUFFER, BUF_MOTION, BUF_THIS_DIRECT_RESV, BUF_LAST_DIRECT_RESV,
  BUF_THIS_INDIRECT_RESV, BUF_LAST_INDIRECT_RESV, BUF_DIRECT, BUF_INDIRECT, BUF_DENOISE_DIR_A,
@@ -225,7 +225,7 @@ for _dt, _n in ((VERTEX_DT, 32), (MATERIAL_DT, 80), (PUNC_DT, 80), (TRIG_DT, 96)
 
 TABLE_DTYPES = {TABLE_MATERIALS: MATERIAL_DT, TABLE_PUNC_LIGHTS: PUNC_DT, TABLE_TRIG_LIGHTS: TRIG_DT,
                 TABLE_LIGHT_INFO: LIGHTINFO_DT, TABLE_INSTANCE_DATA: INSTANCE_DT, TABLE_VERTICES: VERTEX_DT,
-                TABLE_INDICES: np.dtype("<u4"), TABLE_CAMERA: np.dtype("<f4")}
+                TABLE_INDICES: np.dtype("<u4"), TABLE_CAMERA: np.dtype("<f4"), TABLE_TEXELS: np.dtype("u1")}
 BUFFER_DTYPES = {BUF_THIS_GBUFFER: np.dtype("<u4"), BUF_LAST_GBUFFER: np.dtype("<u4"),
                  BUF_MOTION: np.dtype("<i2"), BUF_THIS_DIRECT_RESV: DIRECT_RESV_DT,
                  BUF_LAST_DIRECT_RESV: DIRECT_RESV_DT, BUF_THIS_INDIRECT_RESV: INDIRECT_RESV_DT,

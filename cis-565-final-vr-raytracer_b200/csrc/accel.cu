@@ -663,6 +663,9 @@ static const void* tableSource(eid_scene* s, int table, uint32_t index, size_t& 
         if (index >= H.gltf.primMeshes.size()) return nullptr;
         bytes = (size_t)H.gltf.primMeshes[index].indexCount * 4; return H.indices.data() + H.idxBase[index];
       case EID_TABLE_CAMERA: bytes = sizeof(SceneCamera); return &H.camera;
+      case EID_TABLE_TEXELS:
+        if (index >= H.textures.size()) return nullptr;
+        bytes = (size_t)H.textures[index].width * H.textures[index].height * 4; return H.texels.data() + H.textures[index].texelOffset;
       default: return nullptr;
     }
   }
@@ -679,6 +682,9 @@ static const void* tableSource(eid_scene* s, int table, uint32_t index, size_t& 
       if (index >= H.gltf.primMeshes.size()) return nullptr;
       bytes = (size_t)H.gltf.primMeshes[index].indexCount * 4; return s->dev.indices + H.idxBase[index];
     case EID_TABLE_CAMERA: onDevice = false; bytes = sizeof(SceneCamera); return &H.camera;
+    case EID_TABLE_TEXELS:
+      if (index >= H.textures.size()) return nullptr;
+      onDevice = false; bytes = (size_t)H.textures[index].width * H.textures[index].height * 4; return H.texels.data() + H.textures[index].texelOffset;
     default: return nullptr;
   }
 }

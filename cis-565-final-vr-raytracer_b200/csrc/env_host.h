@@ -25,4 +25,9 @@ struct eid_env {
   int device = 0;
   struct float4* tex = nullptr;          // device copy of pixels (RGBA32F)
   ImptSampData* accel = nullptr;
+  // Renderers that were handed this environment (eid_renderer_set_env) keep it alive: eid_env_destroy on an environment still
+  // in use only marks it, and the last renderer to let go frees it (HdrSampling::loadEnvironment is called again on a live object
+  // by the reference's hosts, sample_example.cpp:97-106, while the renderer still holds the previous map).
+  int users = 0;
+  bool destroyRequested = false;
 };

@@ -4,8 +4,9 @@
 // feeds into the hot path: node hierarchy flattening, TRIANGLES primitives with POSITION / NORMAL /
 // TANGENT / TEXCOORD_0 / COLOR_0 (+ defaults for the missing ones), uint8/16/32 indices, materials with
 // KHR_materials_ior / KHR_materials_transmission, KHR_lights_punctual, cameras; .gltf with external
-// .bin or data: URIs, and .glb.  Textures/images are parsed for their indices only (texture taps are a
-// later scope row).
+// .bin or data: URIs, and .glb; textures / samplers / images, PNG images decoded in place (png_decode.cpp), other formats provided
+// by the host.  Every index and byte range taken from the file is validated: a malformed file is EID_ERR_PARSE, never an
+// out-of-bounds access.
 #include "gltf_import.h"
 #include <cmath>
 #include <cstdlib>
@@ -42,7 +43,23 @@ struct JValue {
   bool boolean(const char* key, bool def) const { auto v = get(key); return (v && v->type == Bool) ? v->b : def; }
   std::string string(const char* key, const char* def) const { auto v = get(key); return (v && v->type == Str) ? v->str : std::string(def); }
   size_t size() const { return type == Arr ? arr.size() : 0; }
-  const JValue& at(size_t i) const { return *arr[i]; }
+  const JValue& at(size_t i) const {
+    if (type != Arr || i >= arr.size()) raise(EID_ERR_PARSE, "glTF: array index %zu out of range (size %zu)", i, size());
+    return *arr[i];
+  }
+  // element i as an index into another glTF array (must be a non-negative integral number)
+  int indexAt(size_t i) const {
+    const JValue& v = at(i);
+    if (v.type != Num || !(v.num >= 0) || v.num > 2147483647.0 || v.num != (double)(int)v.num) raise(EID_ERR_PARSE, "glTF: element %zu is not a valid index", i);
+    return (int)v.num;
+  }
+  // a byte count / offset / element count: non-negative, integral, below 2^48
+  size_t sizeField(const char* key, size_t def) const {
+    auto v = get(key);
+    if (!v) return def;
+    if (v->type != Num || !(v->num >= 0) || v->num > 281474976710656.0 || v->num != (double)(uint64_t)v->num) raise(EID_ERR_PARSE, "glTF: '%s' is not a valid size", key);
+    return (size_t)v->num;
+  }
 };
 
 class JParser {
@@ -57,9 +74,12 @@ class JParser {
 
  private:
   const char *p_, *e_;
+  int depth_ = 0;
+  struct Nest { int& d; explicit Nest(int& x) : d(x) { if (++d > 200) raise(EID_ERR_PARSE, "JSON parse error: nesting deeper than 200 levels"); } ~Nest() { --d; } };
   [[noreturn]] void err(const char* m) { raise(EID_ERR_PARSE, "JSON parse error: %s", m); }
   void ws() { while (p_ < e_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\r' || *p_ == '\t')) ++p_; }
   JPtr value() {
+    Nest nest(depth_);
     ws();
     if (p_ >= e_) err("unexpected end");
     auto v = std::make_shared<JValue>();
@@ -218,6 +238,30 @@ static int typeComponents(const std::string& t) {
   raise(EID_ERR_UNSUPPORTED, "accessor type %s", t.c_str());
 }
 
+// Start of accessor `idx`'s data inside its buffer after validating bufferView / buffer indices and that `count` elements of
+// `elemBytes` at the view's stride lie inside both the bufferView and the buffer (overflow-safe: every quantity is < 2^48).
+static size_t accessorStride(const Doc& d, int bv, size_t packed) {
+  const size_t stride = d.top("bufferViews").at((size_t)bv).sizeField("byteStride", 0);
+  if (stride && (stride < packed || stride > 65536)) raise(EID_ERR_PARSE, "bufferView %d: byteStride %zu is invalid", bv, stride);
+  return stride ? stride : packed;
+}
+static const uint8_t* accessorData(const Doc& d, const JValue& a, int idx, int bv, size_t count, size_t elemBytes, size_t packed) {
+  const JValue& views = d.top("bufferViews");
+  if ((size_t)bv >= views.size()) raise(EID_ERR_PARSE, "accessor %d: bufferView %d out of range", idx, bv);
+  const JValue& view = views.at((size_t)bv);
+  const int buf = view.integer("buffer", -1);
+  if (buf < 0 || (size_t)buf >= d.buffers.size()) raise(EID_ERR_PARSE, "bufferView %d: buffer %d out of range", bv, buf);
+  const auto& B = d.buffers[(size_t)buf];
+  const size_t vOff = view.sizeField("byteOffset", 0), vLen = view.sizeField("byteLength", B.size() > vOff ? B.size() - vOff : 0);
+  const size_t aOff = a.sizeField("byteOffset", 0);
+  const size_t stride = accessorStride(d, bv, packed);
+  if (vOff > B.size() || vLen > B.size() - vOff) raise(EID_ERR_PARSE, "bufferView %d overruns buffer %d", bv, buf);
+  if (count > (size_t)1 << 40) raise(EID_ERR_PARSE, "accessor %d: count %zu is not plausible", idx, count);
+  const size_t need = count ? aOff + (count - 1) * stride + elemBytes : 0;     // < 2^48 + 2^40 * 2^16 + ...: no wrap in 64 bits
+  if (need > vLen) raise(EID_ERR_PARSE, "accessor %d overruns its bufferView", idx);
+  return B.data() + vOff + aOff;
+}
+
 // Reads accessor `idx` as floats with `want` components per element (extra components dropped, missing
 // ones filled with `fill`); integer types are converted (normalized -> [0,1] / [-1,1]).
 static size_t readAccessorFloat(const Doc& d, int idx, int want, float fill, std::vector<float>& out) {
@@ -227,23 +271,17 @@ static size_t readAccessorFloat(const Doc& d, int idx, int want, float fill, std
   if (a.has("sparse")) raise(EID_ERR_UNSUPPORTED, "sparse accessors are not supported");
   int ct = a.integer("componentType", 5126);
   int nc = typeComponents(a.string("type", "SCALAR"));
-  size_t count = (size_t)a.number("count", 0);
+  size_t count = a.sizeField("count", 0);
   bool normalized = a.boolean("normalized", false);
   int bv = a.integer("bufferView", -1);
   if (bv < 0) raise(EID_ERR_UNSUPPORTED, "accessor without bufferView");
-  const JValue& view = d.top("bufferViews").at(bv);
-  int buf = view.integer("buffer", 0);
-  size_t off = (size_t)view.number("byteOffset", 0) + (size_t)a.number("byteOffset", 0);
   int cs = componentSize(ct);
-  size_t stride = (size_t)view.number("byteStride", 0);
-  if (!stride) stride = (size_t)cs * nc;
-  if ((size_t)buf >= d.buffers.size()) raise(EID_ERR_PARSE, "buffer %d out of range", buf);
-  const auto& B = d.buffers[buf];
-  if (count && off + (count - 1) * stride + (size_t)cs * nc > B.size()) raise(EID_ERR_PARSE, "accessor %d overruns its buffer", idx);
+  const uint8_t* data = accessorData(d, a, idx, bv, count, (size_t)cs * nc, (size_t)cs * nc);
+  const size_t stride = accessorStride(d, bv, (size_t)cs * nc);
   size_t base = out.size();
   out.resize(base + count * want);
   for (size_t i = 0; i < count; ++i) {
-    const uint8_t* p = B.data() + off + i * stride;
+    const uint8_t* p = data + i * stride;
     for (int c = 0; c < want; ++c) {
       float v = fill;
       if (c < nc) {
@@ -262,23 +300,21 @@ static size_t readAccessorFloat(const Doc& d, int idx, int want, float fill, std
   return count;
 }
 static size_t readAccessorIndices(const Doc& d, int idx, std::vector<uint32_t>& out) {
-  const JValue& a = d.top("accessors").at(idx);
+  const JValue& accs = d.top("accessors");
+  if (idx < 0 || (size_t)idx >= accs.size()) raise(EID_ERR_PARSE, "index accessor %d out of range", idx);
+  const JValue& a = accs.at(idx);
+  if (a.has("sparse")) raise(EID_ERR_UNSUPPORTED, "sparse accessors are not supported");
   int ct = a.integer("componentType", 5125);
-  size_t count = (size_t)a.number("count", 0);
+  size_t count = a.sizeField("count", 0);
   int bv = a.integer("bufferView", -1);
   if (bv < 0) raise(EID_ERR_UNSUPPORTED, "index accessor without bufferView");
-  const JValue& view = d.top("bufferViews").at(bv);
-  int buf = view.integer("buffer", 0);
-  size_t off = (size_t)view.number("byteOffset", 0) + (size_t)a.number("byteOffset", 0);
   int cs = componentSize(ct);
-  size_t stride = (size_t)view.number("byteStride", 0);
-  if (!stride) stride = cs;
-  const auto& B = d.buffers[buf];
-  if (count && off + (count - 1) * stride + cs > B.size()) raise(EID_ERR_PARSE, "index accessor %d overruns its buffer", idx);
+  const uint8_t* data = accessorData(d, a, idx, bv, count, (size_t)cs, (size_t)cs);
+  const size_t stride = accessorStride(d, bv, (size_t)cs);
   size_t base = out.size();
   out.resize(base + count);
   for (size_t i = 0; i < count; ++i) {
-    const uint8_t* p = B.data() + off + i * stride;
+    const uint8_t* p = data + i * stride;
     uint32_t v = 0;
     if (ct == 5121) v = p[0];
     else if (ct == 5123) { uint16_t u; memcpy(&u, p, 2); v = u; }
@@ -488,7 +524,7 @@ static void processNode(ImportCtx& c, int nodeIdx, const M4& parent, int depth) 
     if (auto p = C.get("perspective")) yfov = (float)p->number("yfov", yfov);
     c.cameras.push_back({world, yfov});
   }
-  if (auto ch = n.get("children")) for (size_t i = 0; i < ch->size(); ++i) processNode(c, (int)ch->at(i).num, world, depth + 1);
+  if (auto ch = n.get("children")) for (size_t i = 0; i < ch->size(); ++i) processNode(c, ch->indexAt(i), world, depth + 1);
 }
 
 void HostGltf::computeDimensions() {
@@ -587,6 +623,33 @@ void importGltfFile(const std::string& path, HostGltf& g, const std::vector<Host
     const JValue& imgs = d.top("images");
     g.images.resize(imgs.size());
     for (size_t i = 0; i < imgs.size() && i < provided.size(); ++i) g.images[i] = provided[i];
+    // images the host did not provide: PNG files / data URIs / bufferViews are decoded here (png_decode.cpp); anything else stays empty
+    for (size_t i = 0; i < imgs.size(); ++i) {
+      if (!g.images[i].rgba8.empty()) continue;
+      const JValue& im = imgs.at(i);
+      std::vector<uint8_t> bytes;
+      const std::string uri = im.string("uri", "");
+      if (!uri.empty()) {
+        if (uri.rfind("data:", 0) == 0) {
+          const size_t k = uri.find(";base64,");
+          if (k != std::string::npos) bytes = base64Decode(uri.c_str() + k + 8, uri.size() - k - 8);
+        } else {
+          try { bytes = readFile(dirOf(path) + "/" + uri); } catch (const Error&) { bytes.clear(); }   // missing file: only an error if the image is used
+        }
+      } else if (im.has("bufferView")) {
+        const int bv = im.integer("bufferView", -1);
+        const JValue& views = d.top("bufferViews");
+        if (bv < 0 || (size_t)bv >= views.size()) raise(EID_ERR_PARSE, "image %zu: bufferView %d out of range", i, bv);
+        const JValue& view = views.at((size_t)bv);
+        const int buf = view.integer("buffer", -1);
+        if (buf < 0 || (size_t)buf >= d.buffers.size()) raise(EID_ERR_PARSE, "bufferView %d: buffer %d out of range", bv, buf);
+        const auto& B = d.buffers[(size_t)buf];
+        const size_t off = view.sizeField("byteOffset", 0), len = view.sizeField("byteLength", 0);
+        if (off > B.size() || len > B.size() - off) raise(EID_ERR_PARSE, "image %zu overruns buffer %d", i, buf);
+        bytes.assign(B.begin() + off, B.begin() + off + len);
+      }
+      if (isPng(bytes.data(), bytes.size())) decodePng(bytes.data(), bytes.size(), g.images[i]);
+    }
     const JValue& texs = d.top("textures");
     const JValue& samps = d.top("samplers");
     for (size_t i = 0; i < texs.size(); ++i) {
@@ -606,8 +669,8 @@ void importGltfFile(const std::string& path, HostGltf& g, const std::vector<Host
       if (tex < 0 || (size_t)tex >= g.textures.size()) return;
       int im = g.textures[tex].image;
       if (im >= 0 && (size_t)im < g.images.size() && g.images[im].rgba8.empty())
-        raise(EID_ERR_UNSUPPORTED, "texture %d uses image %d, which must be decoded by the host first (eid_scene_provide_image): "
-                                   "no PNG/JPEG decoder is available in this build", tex, im);
+        raise(EID_ERR_UNSUPPORTED, "texture %d uses image %d, which is not a PNG (or is missing): decode it on the host and pass the texels "
+                                   "with eid_scene_provide_image before eid_scene_load_gltf (the library decodes PNG only)", tex, im);
     };
     for (const auto& m : g.materials) { used(m.baseColorTexture); used(m.metallicRoughnessTexture); used(m.emissiveTexture); used(m.normalTexture); used(m.transmissionTexture); }
   }
@@ -617,9 +680,15 @@ void importGltfFile(const std::string& path, HostGltf& g, const std::vector<Host
   if (scenes.size()) {
     if (sceneIdx < 0 || (size_t)sceneIdx >= scenes.size()) sceneIdx = 0;
     if (auto roots = scenes.at(sceneIdx).get("nodes"))
-      for (size_t i = 0; i < roots->size(); ++i) processNode(c, (int)roots->at(i).num, identity(), 0);
+      for (size_t i = 0; i < roots->size(); ++i) processNode(c, roots->indexAt(i), identity(), 0);
   } else {
-    for (size_t i = 0; i < d.top("nodes").size(); ++i) processNode(c, (int)i, identity(), 0);   // no scene: every node is a root
+    // no `scenes`: the roots are the nodes that are nobody's child (a child is reached through its parent, with the parent's transform)
+    const JValue& nodes = d.top("nodes");
+    std::vector<char> isChild(nodes.size(), 0);
+    for (size_t i = 0; i < nodes.size(); ++i)
+      if (auto ch = nodes.at(i).get("children"))
+        for (size_t k = 0; k < ch->size(); ++k) { const int ci = ch->indexAt(k); if ((size_t)ci < nodes.size()) isChild[(size_t)ci] = 1; }
+    for (size_t i = 0; i < nodes.size(); ++i) if (!isChild[i]) processNode(c, (int)i, identity(), 0);
   }
   for (const auto& pm : g.primMeshes)
     if ((size_t)pm.materialIndex >= g.materials.size()) raise(EID_ERR_PARSE, "material index %d out of range", pm.materialIndex);

@@ -28,9 +28,13 @@ struct HostGltf {
   void computeDimensions();
 };
 
+// PNG -> RGBA8 with stb_image's conventions (png_decode.cpp); throws eid::Error(EID_ERR_PARSE) on a malformed file
+bool isPng(const uint8_t* data, size_t bytes);
+void decodePng(const uint8_t* data, size_t bytes, HostGltf::Image& out);
+
 // throws eid::Error (EID_ERR_IO / EID_ERR_PARSE / EID_ERR_UNSUPPORTED)
-// `provided` = images the host decoded beforehand (index -> texels); this image has no PNG/JPEG decoder (the reference uses
-// FreeImage / stb through tinygltf), so a file whose used textures reference undecoded images is rejected with EID_ERR_UNSUPPORTED.
+// `provided` = images the host decoded beforehand (index -> texels).  PNG images (files, data URIs, .glb bufferViews) are decoded by the
+// library; a file whose used textures reference any other undecoded image (JPEG ...) is rejected with EID_ERR_UNSUPPORTED.
 void importGltfFile(const std::string& path, HostGltf& out, const std::vector<HostGltf::Image>& provided);
 
 }  // namespace eid

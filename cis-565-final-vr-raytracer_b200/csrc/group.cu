@@ -69,7 +69,7 @@ struct eid_group {
   int rank = 0, world = 1;
   NcclComm comm = nullptr;
   cudaStream_t cs = nullptr;                       // communication stream
-  cudaEvent_t evA = nullptr, evB = nullptr, evX = nullptr, evC = nullptr, evD = nullptr, evH = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evX = nullptr, evC = nullptr, evD = nullptr, evH = nullptr, evA2 = nullptr, evPrep = nullptr, evK3 = nullptr;
   int post = 1;                                    // 1: denoise + compose per band (default), 0: replicated on every rank
   int history = 2;                                 // reservoir history across band edges: 0 never, 1 every frame (behind the post stages), 2 lazily when the camera moved
   int gatherFinal = 1;                             // exchange C
@@ -124,6 +124,17 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
     commAfter(g, g->evA);
     gatherList(g, a, 2);                                    // exchange A, behind indirect_stage
   }
+  // the direct denoiser needs exchange A only: geometry planes + K3 go to the renderer's second stream as soon as it has landed, beside
+  // indirect_stage; the indirect denoiser follows exchange B on the render stream (true dependencies K1 -> {K2, K3}, K2 -> K4, {K3, K4} -> K5)
+  const PostLayout L = postLayout(P, g->world > 1 && g->post == 1);
+  if (g->world > 1) { CUDA_CHECK(cudaEventRecord(g->evA2, g->cs)); CUDA_CHECK(cudaStreamWaitEvent(r->aux, g->evA2, 0)); }
+  else { CUDA_CHECK(cudaEventRecord(g->evA2, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(r->aux, g->evA2, 0)); }
+  markStart(r, EID_K_DENOISE_DIRECT, r->aux);
+  stagePrep(r, P, L, r->aux);
+  CUDA_CHECK(cudaEventRecord(g->evPrep, r->aux));
+  stageDenoiseDirect(r, P, L, r->aux);
+  markStop(r, EID_K_DENOISE_DIRECT, r->aux);
+  CUDA_CHECK(cudaEventRecord(g->evK3, r->aux));
   stageIndirect(r, P, r->stream);
   if (g->world > 1) {
     const int b[1] = {EID_BUF_DENOISE_IND_A};
@@ -136,7 +147,15 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
       g->historyComplete = true;
     }
   }
-  launchPost(r, P, g->world > 1 && g->post == 1);
+  if (r->profiling) CUDA_CHECK(cudaEventRecord(r->evPost, r->stream));   // K2 end .. here = what the render stream waited for exchange B
+  r->postStarted = true;
+  CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evPrep, 0));
+  markStart(r, EID_K_DENOISE_INDIRECT, r->stream);
+  stageDenoiseIndirect(r, P, L, r->stream);
+  markStop(r, EID_K_DENOISE_INDIRECT, r->stream);
+  CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evK3, 0));
+  stageCompose(r, P, L, r->stream);
+  endFrame(r);
   if (g->world > 1 && g->post == 1 && finalGather) {
     const int c[2] = {EID_BUF_DIRECT, EID_BUF_INDIRECT};
     commAfter(g, g->evC);
@@ -182,7 +201,7 @@ int eid_group_create(eid_group** out, eid_renderer* r, int rank, int world, cons
     g->r = r; g->rank = rank; g->world = world; g->bandRows = r->height / world;
     CUDA_CHECK(cudaSetDevice(r->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&g->evA, &g->evB, &g->evX, &g->evC, &g->evD, &g->evH}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&g->evA, &g->evB, &g->evX, &g->evC, &g->evD, &g->evH, &g->evA2, &g->evPrep, &g->evK3}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (world > 1) {
       NcclId id;
       memcpy(&id, id128, sizeof(id));
@@ -201,7 +220,7 @@ void eid_group_destroy(eid_group* g) {
   if (g->cs) cudaStreamSynchronize(g->cs);
   if (g->copyStream) { cudaStreamSynchronize(g->copyStream); cudaStreamDestroy(g->copyStream); }
   if (g->comm) nccl().CommDestroy(g->comm);
-  for (cudaEvent_t e : {g->evA, g->evB, g->evX, g->evC, g->evD, g->evH, g->evFrameDone, g->evCopyDone}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {g->evA, g->evB, g->evX, g->evC, g->evD, g->evH, g->evA2, g->evPrep, g->evK3, g->evFrameDone, g->evCopyDone}) if (e) cudaEventDestroy(e);
   cudaFree(g->staging[0]); cudaFree(g->staging[1]);
   if (g->cs) cudaStreamDestroy(g->cs);
   delete g;
@@ -235,7 +254,6 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
   if (!g || !state) raise(EID_ERR_INVALID, "eid_group_render_host_async: null argument");
   eid_renderer* r = g->r;
   CUDA_CHECK(cudaSetDevice(r->device));
-  if (g->world > 1 && g->post != 1) raise(EID_ERR_STATE, "eid_group_render_host_async delivers per band: needs the sharded post mode");
   if (!g->copyStream) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&g->copyStream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&g->evFrameDone, cudaEventDisableTiming));

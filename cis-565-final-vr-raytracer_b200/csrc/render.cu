@@ -123,8 +123,8 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
 
 // ---- stage launchers -----------------------------------------------------------------------------------------------------------
 // Every stage records a start/stop CUDA-event pair on the stream it runs on when profiling is enabled (stage k: ev[2k], ev[2k+1]).
-static inline void markStart(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage], st)); }
-static inline void markStop(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage + 1], st)); }
+void markStart(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage], st)); }
+void markStop(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage + 1], st)); }
 
 void beginFrame(eid_renderer* r) {
   CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
@@ -206,8 +206,7 @@ void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
 // 0..3; indirect: 60/56/48/32/0 quarter-res rows for levels 0..4); the inputs of level 0 (pre-denoise images, G-buffer) are
 // complete on every rank after the first exchange step.  Values are identical to the full-frame evaluation, only the evaluated
 // row ranges shrink (overlapping ranges of neighbouring stripes recompute identical values).
-struct PostLayout { int first, stride, srows, count; bool sharded; };
-static PostLayout postLayout(const FrameParams& P, bool sharded) {
+PostLayout postLayout(const FrameParams& P, bool sharded) {
   PostLayout L;
   L.sharded = sharded;
   L.first = sharded ? P.sFirst : 0; L.stride = sharded ? P.sStride : (1 << 20);
@@ -223,7 +222,7 @@ static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* s
 
 static bool fastSigmas(const RtxState& st);
 // geometry planes: +-30 full-res rows for K3, +-62 quarter-res rows (= 124 full-res rows) for K4; accounted to the direct denoiser
-static void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
+void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
   if (P.st.denoise <= 0 || L.count <= 0) return;
   const int rows = L.srows + 2 * 124, W = P.st.size.x;
   dim3 g((W + 31) / 32, gridRows(L, rows, 8));
@@ -306,7 +305,7 @@ static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* s
   eid::launchDenoise(INDIRECT, r->strictMath, R, g, st, P, src, dst, level, lastLevel, first, stride, rows);
 }
 
-static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
+void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
   if (P.st.denoise > 0 && L.count > 0) {   // thisDirect -> A -> B -> A -> thisDirect
     const int W = P.st.size.x;
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
@@ -320,7 +319,7 @@ static void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const Post
   }
 }
 
-static void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:191-202
+void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:191-202
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
   if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && L.count > 0) {   // IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
@@ -334,7 +333,7 @@ static void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const Po
   }
 }
 
-static void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
+void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {
   markStart(r, EID_K_COMPOSE, st);
   if (L.count > 0) {
     dim3 g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 8));
@@ -344,7 +343,7 @@ static void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout
   markStop(r, EID_K_COMPOSE, st);
 }
 
-static void endFrame(eid_renderer* r) {
+void endFrame(eid_renderer* r) {
   CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
   r->statsPending = true;
   CUDA_CHECK(cudaGetLastError());
@@ -424,6 +423,8 @@ void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
 
 extern "C" {
 
+static void envRelease(eid_env* e);
+
 int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t width, uint32_t height, void* cuda_stream) {
   EID_TRY
   if (!out || !s || !a) raise(EID_ERR_INVALID, "eid_renderer_create: null argument");
@@ -472,6 +473,7 @@ void eid_renderer_destroy(eid_renderer* r) {
   if (!r) return;
   cudaSetDevice(r->device);
   if (r->stream) cudaStreamSynchronize(r->stream);
+  if (r->envMap) { envRelease(r->envMap); r->envMap = nullptr; }
   r->release();
   cudaFree(r->counters);
   if (r->countersHost) cudaFreeHost(r->countersHost);
@@ -526,8 +528,16 @@ int eid_env_load_hdr(eid_env** out, int device, const char* path) {
   EID_CATCH
 }
 
+static void envFree(eid_env* e);
 void eid_env_destroy(eid_env* e) {
   if (!e) return;
+  if (e->users > 0) { e->destroyRequested = true; return; }     // a renderer still samples it: freed when the last one lets go
+  envFree(e);
+}
+static void envRelease(eid_env* e) {                             // a renderer lets go of `e`
+  if (e && --e->users <= 0 && e->destroyRequested) envFree(e);
+}
+static void envFree(eid_env* e) {
   if (e->tex || e->accel) { cudaSetDevice(e->device); cudaFree(e->tex); cudaFree(e->accel); }
   delete e;
 }
@@ -560,6 +570,9 @@ int eid_renderer_set_env(eid_renderer* r, eid_env* e) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_env: null renderer");
   if (e && (e->device != r->device || !e->tex)) raise(EID_ERR_INVALID, "environment map lives on another device (or is host-only)");
+  if (e == r->envMap) return EID_OK;
+  if (r->envMap) { CUDA_CHECK(cudaSetDevice(r->device)); CUDA_CHECK(cudaStreamSynchronize(r->stream)); envRelease(r->envMap); }   // frames in flight may still sample it
+  if (e) e->users++;
   r->envMap = e;
   return EID_OK;
   EID_CATCH

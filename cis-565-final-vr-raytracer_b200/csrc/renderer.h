@@ -76,3 +76,13 @@ void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
 void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
 void launchPost(eid_renderer* r, const FrameParams& P, bool sharded);
 void* bufferPtr(eid_renderer* r, int which, size_t& bytes);
+// post stages one by one (the multi-GPU schedule starts the direct denoiser as soon as exchange A has landed, beside indirect_stage)
+struct PostLayout { int first, stride, srows, count; bool sharded; };
+PostLayout postLayout(const FrameParams& P, bool sharded);
+void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st);
+void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st);
+void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st);
+void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st);
+void endFrame(eid_renderer* r);
+void markStart(eid_renderer* r, int stage, cudaStream_t st);
+void markStop(eid_renderer* r, int stage, cudaStream_t st);

@@ -139,7 +139,8 @@ typedef enum eid_scene_table {
   EID_TABLE_INSTANCE_DATA = 4, /* InstanceData[primMeshCount]                 scene.cpp:179-195 */
   EID_TABLE_VERTICES = 5,      /* VertexAttributes[] of prim mesh `index`     scene.cpp:209-289 */
   EID_TABLE_INDICES = 6,       /* uint32[] of prim mesh `index`                                  */
-  EID_TABLE_CAMERA = 7         /* SceneCamera                                 scene.cpp:777-826 */
+  EID_TABLE_CAMERA = 7,        /* SceneCamera                                 scene.cpp:777-826 */
+  EID_TABLE_TEXELS = 8         /* RGBA8 texels (uint32 each, row-major) of texture `index` = texturesMap[index], scene.cpp:554-646 */
 } eid_scene_table;
 
 /* Scene::setup + constructor (scene.hpp:60). device = CUDA ordinal, or EID_DEVICE_NONE for a host-only

@@ -292,7 +292,201 @@ def test_texture_table_semantics(tmp_path):
     path.write_text(json.dumps(doc))
     s = eid.Scene(device=-1)
     L = eid.lib()
-    assert L.eid_scene_load_gltf(s._h, str(path).encode()) == -4 and b"eid_scene_provide_image" in L.eid_last_error()
+    assert L.eid_scene_load_gltf(s._h, str(path).encode()) == -4 and b"eid_scene_provide_image" in L.eid_last_error()   # albedo.png does not exist
     s.provide_image(0, np.full((4, 4, 4), 200, np.uint8))
     s.load(str(path))
     assert s.table(abi.TABLE_MATERIALS)["pbrBaseColorTexture"][0] == 0
+
+
+def _png(img, color_type, depth=8, interlace=0, palette=None, trns=None, filters=None):
+    """Minimal PNG writer for the decoder tests: img = (h, w, channels) array of samples (uint8 or uint16), any filter per row."""
+    import struct, zlib
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+
+    def pack_rows(sub):
+        rows = []
+        for r in sub:
+            v = r.reshape(-1)
+            if depth == 16:
+                rows.append(v.astype(">u2").tobytes())
+            elif depth == 8:
+                rows.append(v.astype(np.uint8).tobytes())
+            else:
+                bits = "".join(format(int(x), "0%db" % depth) for x in v)
+                bits += "0" * (-len(bits) % 8)
+                rows.append(bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)))
+        return rows
+
+    def filt(rows, bpp):
+        out, prev = b"", bytes(len(rows[0])) if rows else b""
+        for y, cur in enumerate(rows):
+            ft = (filters[y % len(filters)] if filters else 0)
+            line = bytearray(len(cur))
+            for i in range(len(cur)):
+                a = cur[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                p = a + b - c
+                pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+                pae = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                pred = [0, a, b, (a + b) >> 1, pae][ft]
+                line[i] = (cur[i] - pred) & 255
+            out += bytes([ft]) + bytes(line)
+            prev = cur
+        return out
+
+    bpp = max(1, ch * depth // 8)
+    if interlace:
+        raw = b""
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = img[y0::dy, x0::dx]
+            if sub.shape[0] and sub.shape[1]:
+                raw += filt(pack_rows(sub), bpp)
+    else:
+        raw = filt(pack_rows(img), bpp)
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+    z = zlib.compress(raw, 6)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, interlace))
+    if palette is not None:
+        out += chunk(b"PLTE", bytes(palette))
+    if trns is not None:
+        out += chunk(b"tRNS", bytes(trns))
+    out += chunk(b"IDAT", z[:len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    return out
+
+
+def _gltf_with_image(tmp_path, name, image_entry, extra_buffers=()):
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes()
+    doc = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+           "images": [image_entry], "textures": [{"source": 0}],
+           "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}}}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "material": 0}]}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}] + [dict(buffer=1 + k, byteOffset=0, byteLength=len(b)) for k, b in enumerate(extra_buffers)],
+           "buffers": [{"byteLength": 36, "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}] +
+                      [{"byteLength": len(b), "uri": "data:application/octet-stream;base64," + base64.b64encode(b).decode()} for b in extra_buffers]}
+    path = tmp_path / name
+    path.write_text(json.dumps(doc))
+    return str(path)
+
+
+def test_png_images_are_decoded_by_the_importer(tmp_path):
+    """tinygltf loads texture images through stb_image with 4 requested components (scene.cpp:144-159): the importer decodes PNG with the
+    same conventions — every colour type / bit depth / filter, Adam7, palette + tRNS, 16-bit -> high byte, colour keys — from an external
+    file, a data: URI and a bufferView."""
+    import base64
+    rng = np.random.default_rng(7)
+    cases = []
+    rgba = rng.integers(0, 256, (13, 11, 4), dtype=np.uint8)
+    cases.append(("rgba8 all filters", _png(rgba, 6, filters=[0, 1, 2, 3, 4]), rgba))
+    rgb = rng.integers(0, 256, (9, 17, 3), dtype=np.uint8)
+    want = np.dstack([rgb, np.full(rgb.shape[:2], 255, np.uint8)])
+    cases.append(("rgb8 paeth", _png(rgb, 2, filters=[4]), want))
+    cases.append(("rgb8 interlaced", _png(rgb, 2, interlace=1, filters=[1, 3]), want))
+    key = rgb[2, 3]
+    wk = want.copy(); wk[(rgb == key).all(axis=2), 3] = 0
+    cases.append(("rgb8 colour key", _png(rgb, 2, trns=[0, key[0], 0, key[1], 0, key[2]]), wk))
+    g16 = rng.integers(0, 65536, (5, 7, 2), dtype=np.uint16)
+    w16 = np.dstack([g16[..., 0] >> 8] * 3 + [g16[..., 1] >> 8]).astype(np.uint8)
+    cases.append(("grey+alpha 16", _png(g16, 4, depth=16, filters=[2, 4]), w16))
+    for depth, scale in ((1, 255), (2, 85), (4, 17)):
+        g = rng.integers(0, 1 << depth, (6, 13), dtype=np.uint8)
+        wg = np.dstack([(g * scale).astype(np.uint8)] * 3 + [np.full(g.shape, 255, np.uint8)])
+        cases.append(("grey %d-bit" % depth, _png(g, 0, depth=depth, filters=[0, 2]), wg))
+    pal = rng.integers(0, 256, (16, 3), dtype=np.uint8)
+    idx = rng.integers(0, 16, (8, 9), dtype=np.uint8)
+    tr = [0, 128, 255, 7]
+    wp = np.dstack([pal[idx], np.array(tr + [255] * 12, np.uint8)[idx]])
+    cases.append(("palette 4-bit + tRNS", _png(idx, 3, depth=4, palette=pal.reshape(-1), trns=tr, interlace=1), wp))
+    for k, (name, png, want) in enumerate(cases):
+        if k % 3 == 0:
+            (tmp_path / ("img%d.png" % k)).write_bytes(png)
+            entry = {"uri": "img%d.png" % k}
+            path = _gltf_with_image(tmp_path, "c%d.gltf" % k, entry)
+        elif k % 3 == 1:
+            path = _gltf_with_image(tmp_path, "c%d.gltf" % k, {"uri": "data:image/png;base64," + base64.b64encode(png).decode()})
+        else:
+            path = _gltf_with_image(tmp_path, "c%d.gltf" % k, {"bufferView": 1, "mimeType": "image/png"}, extra_buffers=[png])
+        s = eid.Scene(device=-1)
+        s.load(path)
+        got = s.table(abi.TABLE_TEXELS, 0).reshape(want.shape)
+        assert np.array_equal(got, want), name
+    # a truncated / corrupt PNG is a parse error, not a crash
+    bad = cases[0][1][:60]
+    (tmp_path / "bad.png").write_bytes(bad)
+    L = eid.lib()
+    s = eid.Scene(device=-1)
+    assert L.eid_scene_load_gltf(s._h, _gltf_with_image(tmp_path, "bad.gltf", {"uri": "bad.png"}).encode()) == -3 and b"PNG" in L.eid_last_error()
+    # a JPEG (not decoded by the library) is refused until the host provides the texels
+    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0" + bytes(32))
+    assert L.eid_scene_load_gltf(s._h, _gltf_with_image(tmp_path, "jpg.gltf", {"uri": "x.jpg"}).encode()) == -4
+
+
+def test_malformed_gltf_is_a_parse_error_not_a_crash(tmp_path):
+    """Every index and byte range the importer takes from the file is validated (EID_ERR_PARSE = -3), JSON nesting is capped."""
+    import base64, copy
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    idx = np.array([0, 1, 2], np.uint16)
+    blob = pos.tobytes() + idx.tobytes() + bytes(2)
+    good = {"asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                          {"bufferView": 1, "componentType": 5123, "count": 3, "type": "SCALAR"}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 6}],
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    L = eid.lib()
+    s = eid.Scene(device=-1)
+
+    def rc(doc, name="m.gltf"):
+        p = tmp_path / name
+        p.write_text(doc if isinstance(doc, str) else json.dumps(doc))
+        return L.eid_scene_load_gltf(s._h, str(p).encode())
+    assert rc(good) == 0
+    for mutate in (lambda d: d["meshes"][0]["primitives"][0].__setitem__("indices", 7),                 # accessor index out of range
+                   lambda d: d["meshes"][0]["primitives"][0]["attributes"].__setitem__("POSITION", 9),
+                   lambda d: d["accessors"][1].__setitem__("bufferView", 5),                           # bufferView out of range
+                   lambda d: d["bufferViews"][1].__setitem__("buffer", 3),                             # buffer out of range
+                   lambda d: d["accessors"][0].__setitem__("count", -3),                               # negative count
+                   lambda d: d["accessors"][0].__setitem__("count", 2.5),                              # non-integral count
+                   lambda d: d["accessors"][0].__setitem__("count", 1e30),                             # absurd count (would wrap size_t arithmetic)
+                   lambda d: d["accessors"][1].__setitem__("byteOffset", 1e18),
+                   lambda d: d["bufferViews"][0].__setitem__("byteOffset", -8),
+                   lambda d: d["bufferViews"][0].__setitem__("byteLength", 10**9),                     # view longer than its buffer
+                   lambda d: d["bufferViews"][0].__setitem__("byteStride", 4),                         # stride smaller than the element
+                   lambda d: d["accessors"][0].__setitem__("count", 4),                                # one element past the view
+                   lambda d: d["nodes"][0].__setitem__("children", [5]),                               # child index out of range
+                   lambda d: d["nodes"][0].__setitem__("children", [0]),                               # cycle
+                   lambda d: d["nodes"][0].__setitem__("children", ["x"]),
+                   lambda d: d["scenes"][0].__setitem__("nodes", [-1]),
+                   lambda d: d["nodes"][0].__setitem__("mesh", 4)):
+        bad = copy.deepcopy(good)
+        mutate(bad)
+        assert rc(bad) == -3, (L.eid_last_error(), bad)
+    assert rc("[" * 5000 + "]" * 5000, "deep.gltf") == -3 and b"nesting" in L.eid_last_error()
+    assert rc(good) == 0                                                                               # the scene object is still usable
+
+
+def test_gltf_without_scenes_uses_the_parentless_nodes_as_roots(tmp_path):
+    """No `scenes`: only nodes that are nobody's child are roots; children are reached through their parents (once, with the parent's
+    transform) — the hierarchy is not instanced a second time without it."""
+    import base64
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    blob = pos.tobytes()
+    doc = {"asset": {"version": "2.0"},
+           "nodes": [{"mesh": 0, "translation": [0, 0, 1]}, {"children": [0, 2], "translation": [10, 0, 0]}, {"mesh": 0}],
+           "meshes": [{"primitives": [{"attributes": {"POSITION": 0}}]}],
+           "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}],
+           "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}],
+           "buffers": [{"byteLength": 36, "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}]}
+    p = tmp_path / "noscene.gltf"
+    p.write_text(json.dumps(doc))
+    s = eid.Scene(device=-1)
+    s.load(str(p))
+    info = s.info()
+    assert info.nodeCount == 2 and info.triangleInstances == 2
+    assert np.allclose(info.bboxMin[:], (10, 0, 0)) and np.allclose(info.bboxMax[:], (11, 1, 1))

@@ -892,3 +892,35 @@ def test_group_of_one_equals_renderer_and_delivers_bands():
         eid.Group().create(r1, 0, 2, None)                                    # world > 1 needs the unique id
     with pytest.raises(eid.EidolaError):
         eid.Group().create(r1, 3, 2, bytes(128))
+
+
+def test_environment_reload_keeps_the_renderers_map_alive():
+    """HdrSampling::loadEnvironment on a live object (sample_example.cpp:97-106) destroys and re-creates the map while a renderer still
+    samples the previous one: the library keeps that map alive until the renderer is given the new one (no use-after-free)."""
+    import oracle_lib as ol
+    arrays = scenes.cube_scene()
+    size = (96, 64)
+    sky1, sky2 = scenes.synthetic_sky(), scenes.synthetic_sky(sun=False)
+    osc, orr, psc, acc, prr = common.make_pair(arrays, size, env_img=sky1)
+    penv = prr._env
+    info = psc.info()
+    over1 = common.env_state_overrides(penv.get_integral())
+    for s in (osc, psc):
+        s.update_camera(*size)
+
+    def frame(f, over):
+        for s in (osc, psc):
+            s.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, **over)
+        orr.run(st, f); prr.run(st, f); prr.sync()
+        rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "env reload frame %d" % f)
+        assert all(v == 0.0 for v in rep.values()), rep
+    frame(0, over1)
+    penv.set_pixels(sky2)                       # destroy + create on the same HdrSampling object; the renderer was NOT told
+    frame(1, over1)                             # still the first map, bit for bit
+    oenv2 = ol.OracleEnv(sky2)
+    orr.set_env(oenv2)
+    prr.set_env(penv)                           # now the renderer switches (and the first map is freed)
+    frame(2, common.env_state_overrides(penv.get_integral()))
+    prr.set_env(None)
+    penv.destroy()
