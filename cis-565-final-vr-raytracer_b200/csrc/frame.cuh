@@ -59,10 +59,15 @@ struct FrameParams {
   // so no 8x8 quarter-res tile straddles two ranks).  Single GPU: one stripe covering the frame.
   int sFirst, sStride, sRows, sCount;
   WaveView wv;
-  unsigned long long* counters;           // per frame: [0] closest-hit rays, [1] any-hit rays, [2] primary hits, [3] inner-node
-                                          // visits, [4] triangle tests (STATS kernels only); since creation: [5] closest, [6] any
+  unsigned long long* counters;           // per frame (one set per ping-pong parity, so that frames in flight do not mix): [0] closest-hit
+                                          // rays, [1] any-hit rays, [2] primary hits, [3] inner-node visits, [4] triangle tests (STATS kernels only)
+  unsigned long long* totals;             // since creation: [5] closest, [6] any, [7] worst thread's node visits
+  // What indirect_stage needs of LAST frame's G-buffer and of this frame's motion image (findTemporalNeighbor, indirect_stage.comp:74-108),
+  // gathered by direct_stage for the pixels 2 * coord: the quarter-res stage then reads neither image, so the NEXT frame's direct_stage may
+  // overwrite them while this frame's indirect_stage is still running (frames in flight, eid_renderer_set_pipeline)
+  uint4* k2G; short2* k2Mv;
 };
-#define EID_NUM_COUNTERS 8
+#define EID_NUM_COUNTERS 8            // per set; device layout: set 0 | set 1 | totals
 
 struct RayCounters { unsigned int closest, any, primary, nodes, tris; };
 
@@ -94,12 +99,12 @@ DEV void flushCounters(const FrameParams& P, const RayCounters& c) {
     if (STATS) { n += __shfl_xor_sync(0xffffffffu, n, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
   }
   if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0) {
-    if (a) { atomicAdd(&P.counters[0], (unsigned long long)a); atomicAdd(&P.counters[5], (unsigned long long)a); }
-    if (b) { atomicAdd(&P.counters[1], (unsigned long long)b); atomicAdd(&P.counters[6], (unsigned long long)b); }
+    if (a) { atomicAdd(&P.counters[0], (unsigned long long)a); atomicAdd(&P.totals[5], (unsigned long long)a); }
+    if (b) { atomicAdd(&P.counters[1], (unsigned long long)b); atomicAdd(&P.totals[6], (unsigned long long)b); }
     if (d) atomicAdd(&P.counters[2], (unsigned long long)d);
     if (STATS) { if (n) atomicAdd(&P.counters[3], (unsigned long long)n); if (t) atomicAdd(&P.counters[4], (unsigned long long)t); }
   }
-  if (STATS) atomicMax(&P.counters[7], (unsigned long long)c.nodes);   // worst thread (all its rays) since the renderer was created
+  if (STATS) atomicMax(&P.totals[7], (unsigned long long)c.nodes);   // worst thread (all its rays) since the renderer was created
 }
 
 // image access: out-of-bounds loads return 0 (Vulkan robust image access), stores are dropped

@@ -106,6 +106,7 @@ static bool cameraMoved(const SceneCamera& c) { return memcmp(&c.projView, &c.la
 static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalGather) {
   eid_renderer* r = g->r;
   FrameParams P;
+  strictOrder(r);
   fillParams(r, st, frames, P);
   const bool temporal = temporalReuse(st);
   if (g->world > 1 && temporal && g->history == 2 && cameraMoved(P.cam) && !g->historyComplete) {

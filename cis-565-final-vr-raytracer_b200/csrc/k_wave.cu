@@ -13,13 +13,13 @@ void launchGiBounce(const FrameParams& P, int blocks, cudaStream_t st, bool tex,
 void launchGiFinish(const FrameParams& P, dim3 g, cudaStream_t st) { k_gi_finish<<<g, dim3(8, 8), 0, st>>>(P); }
 
 void launchTraceQueue(bool any, bool stats, int g, cudaStream_t st, const AccelView& A, const float4* rays, const uint32_t* count,
-                      uint32_t* cursor, float4* hits, uint32_t* occl, unsigned long long* counters) {
+                      uint32_t* cursor, float4* hits, uint32_t* occl, unsigned long long* counters, unsigned long long* totals) {
   if (any) {
-    if (stats) k_trace_queue<true, true><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters);
-    else k_trace_queue<true, false><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters);
+    if (stats) k_trace_queue<true, true><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters, totals);
+    else k_trace_queue<true, false><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters, totals);
   } else {
-    if (stats) k_trace_queue<false, true><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters);
-    else k_trace_queue<false, false><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters);
+    if (stats) k_trace_queue<false, true><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters, totals);
+    else k_trace_queue<false, false><<<g, 128, 0, st>>>(A, rays, count, cursor, hits, occl, counters, totals);
   }
 }
 

@@ -21,7 +21,9 @@ void eid_renderer::release() {
   cudaFree(displayF); cudaFree(display8); displayF = nullptr; display8 = nullptr;
   cudaFree(mipScratch); mipScratch = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
-  cudaFree(directImg); cudaFree(indirectImg); directImg = indirectImg = nullptr;
+  for (int i = 0; i < 2; ++i) { cudaFree(directImgs[i]); cudaFree(k2G[i]); cudaFree(k2Mv[i]); directImgs[i] = nullptr; k2G[i] = nullptr; k2Mv[i] = nullptr; }
+  cudaFree(indirectImg); directImg = indirectImg = nullptr;
+  frameDoneValid[0] = frameDoneValid[1] = false;
   tmaps.clear();
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
   for (auto& t : geom) { cudaFree(t); t = nullptr; }
@@ -46,7 +48,9 @@ void eid_renderer::allocate() {
   // the row / column counts up to multiples of 2^l <= 16, so its last lattice row / column may address up to 15 rows + 15 texels
   // past the image (never used: the kernel invalidates texels outside the rendered size)
   const size_t slack = (size_t)17 * width * 16;
-  zalloc((void**)&directImg, n * 16 + slack); zalloc((void**)&indirectImg, n * 16 + slack);
+  for (int i = 0; i < 2; ++i) { zalloc((void**)&directImgs[i], n * 16 + slack); zalloc((void**)&k2G[i], ni * 16); zalloc((void**)&k2Mv[i], ni * 4); }
+  directImg = directImgs[0];
+  zalloc((void**)&indirectImg, n * 16 + slack);
   for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16 + slack);
   zalloc((void**)&geom[0], n * 16 + slack); zalloc((void**)&geom[1], n * 16 + slack);
   zalloc((void**)&geom[2], ni * 16 + slack); zalloc((void**)&geom[3], ni * 16 + slack);
@@ -97,7 +101,9 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   P.motion = r->motion;
   P.thisDR = r->directResv[!set]; P.lastDR = r->directResv[set];
   P.thisIR = r->indirectResv[!set]; P.lastIR = r->indirectResv[set];
+  r->directImg = r->directImgs[set];
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
+  P.k2G = r->k2G[set]; P.k2Mv = r->k2Mv[set];
   if ((st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal) && !r->tempDirectResv) {   // m_directTempResv (renderer.cpp:235), on first use
     const size_t n = (size_t)r->width * r->height;
     CUDA_CHECK(cudaMalloc((void**)&r->tempDirectResv, n * sizeof(DirectReservoir)));
@@ -115,7 +121,7 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   P.pitch = (int)r->width; P.allocH = (int)r->height;
   P.sFirst = (int)r->sFirst; P.sStride = (int)r->sStride; P.sRows = (int)r->sRows;
   P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
-  P.counters = r->counters;
+  P.counters = r->counters + EID_NUM_COUNTERS * set; P.totals = r->counters + 2 * EID_NUM_COUNTERS;
   memset(&P.wv, 0, sizeof(P.wv));
   if (r->wavefront && !P.hasNonOpaque && st.maxDepth <= GI_MAX_WAVE_DEPTH) { r->ensureWave(st.maxDepth - 1); P.wv = r->waveView(); }
   r->lastSet = set; r->lastState = st; r->hasRun = true;
@@ -126,8 +132,8 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
 void markStart(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage], st)); }
 void markStop(eid_renderer* r, int stage, cudaStream_t st) { if (r->profiling) CUDA_CHECK(cudaEventRecord(r->ev[2 * stage + 1], st)); }
 
-void beginFrame(eid_renderer* r) {
-  CUDA_CHECK(cudaMemsetAsync(r->counters, 0, 5 * sizeof(unsigned long long), r->stream));   // per-frame counters only
+void beginFrame(eid_renderer* r, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(r->counters + EID_NUM_COUNTERS * r->lastSet, 0, 5 * sizeof(unsigned long long), st ? st : r->stream));   // this parity's per-frame counters
   memset(&r->stats, 0, sizeof(r->stats));
   r->postStarted = false;
 }
@@ -160,7 +166,7 @@ void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
 
 static void traceQueue(eid_renderer* r, bool any, const FrameParams& P, const float4* rays, const uint32_t* count, uint32_t* cursor, cudaStream_t st) {
   const int g = r->traceBlocks > 0 ? r->traceBlocks : r->smCount * EID_TQ_MIN_BLOCKS;
-  launchTraceQueue(any, r->countVisits, g, st, P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters);
+  launchTraceQueue(any, r->countVisits, g, st, P.accel, rays, count, cursor, P.wv.hitQ, P.wv.occl, P.counters, P.totals);
   r->stats.kernelLaunches[EID_K_INDIRECT]++;
 }
 
@@ -344,7 +350,8 @@ void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cu
 }
 
 void endFrame(eid_renderer* r) {
-  CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
+  CUDA_CHECK(cudaMemcpyAsync(r->countersHost, r->counters + EID_NUM_COUNTERS * r->lastSet, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
+  CUDA_CHECK(cudaMemcpyAsync(r->countersHost + 5, r->counters + 2 * EID_NUM_COUNTERS + 5, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, r->stream));
   r->statsPending = true;
   CUDA_CHECK(cudaGetLastError());
 }
@@ -380,11 +387,34 @@ void launchPost(eid_renderer* r, const FrameParams& P, bool sharded) {
   endFrame(r);
 }
 
+void strictOrder(eid_renderer* r) {
+  if (!r->pipeline) return;
+  CUDA_CHECK(cudaEventRecord(r->evOrder, r->k1Stream));
+  CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evOrder, 0));
+  r->k1MustWaitStream = true;
+}
+
+static void markFrameDone(eid_renderer* r) {     // everything enqueued so far on the render stream belongs to the frame of parity lastSet
+  if (!r->pipeline) return;
+  CUDA_CHECK(cudaEventRecord(r->evFrameDone2[r->lastSet], r->stream));
+  r->frameDoneValid[r->lastSet] = true;
+}
+
 static void launchFrame(eid_renderer* r, const FrameParams& P) {
-  if (!r->overlap) { launchTrace(r, P); launchPost(r, P, false); return; }
+  if (!r->overlap) { strictOrder(r); launchTrace(r, P); launchPost(r, P, false); return; }
   const PostLayout L = postLayout(P, false);
-  beginFrame(r);
-  stageDirect(r, P, r->stream);
+  // Frames in flight: direct_stage goes to its own stream and only waits for the frame before last (which used this parity's G-buffer,
+  // direct image, K2 gather buffers and counters); indirect_stage / denoise / compose follow it on the render stream.  K1 of frame f + 1
+  // therefore overlaps K2 .. K5 of frame f.  Nothing K1 writes is read by a later stage of the PREVIOUS frame (see FrameParams::k2G).
+  cudaStream_t k1 = r->pipeline ? r->k1Stream : r->stream;
+  if (r->pipeline && r->k1MustWaitStream) {          // strictly ordered stages ran on the render stream in between: K1 follows them
+    CUDA_CHECK(cudaEventRecord(r->evOrder, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(k1, r->evOrder, 0));
+    r->k1MustWaitStream = false;
+  }
+  if (r->pipeline && r->frameDoneValid[r->lastSet]) CUDA_CHECK(cudaStreamWaitEvent(k1, r->evFrameDone2[r->lastSet], 0));
+  beginFrame(r, k1);
+  stageDirect(r, P, k1);
+  if (r->pipeline) { CUDA_CHECK(cudaEventRecord(r->evK1Done, k1)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evK1Done, 0)); }
   markStart(r, EID_K_DENOISE_DIRECT, r->stream);
   stagePrep(r, P, L, r->stream);
   forkAux(r);
@@ -397,6 +427,7 @@ static void launchFrame(eid_renderer* r, const FrameParams& P) {
   joinAux(r);
   stageCompose(r, P, L, r->stream);
   endFrame(r);
+  markFrameDone(r);
 }
 
 void* bufferPtr(eid_renderer* r, int which, size_t& bytes) {
@@ -437,8 +468,8 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
     CUDA_CHECK(cudaDeviceGetAttribute(&r->smCount, cudaDevAttrMultiProcessorCount, r->device));
     if (cuda_stream) r->stream = (cudaStream_t)cuda_stream;
     else { CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)); r->ownStream = true; }
-    CUDA_CHECK(cudaMalloc(&r->counters, EID_NUM_COUNTERS * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemset(r->counters, 0, EID_NUM_COUNTERS * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMalloc(&r->counters, 3 * EID_NUM_COUNTERS * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemset(r->counters, 0, 3 * EID_NUM_COUNTERS * sizeof(unsigned long long)));
     CUDA_CHECK(cudaMallocHost(&r->countersHost, EID_NUM_COUNTERS * sizeof(unsigned long long)));
     memset(r->countersHost, 0, EID_NUM_COUNTERS * sizeof(unsigned long long));
     for (auto& e : r->ev) CUDA_CHECK(cudaEventCreate(&e));
@@ -446,6 +477,15 @@ int eid_renderer_create(eid_renderer** out, eid_scene* s, eid_accel* a, uint32_t
     CUDA_CHECK(cudaEventCreate(&r->evPost));
     CUDA_CHECK(cudaStreamCreateWithFlags(&r->aux, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&r->shadowStream, cudaStreamNonBlocking));
+    {   // the K1 stream has the LOWEST priority: with frames in flight, the next frame's direct stage fills what the latency-bound
+        // chain of the current frame's indirect stage leaves idle, never the other way round
+      int lo = 0, hi = 0;
+      CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_CHECK(cudaStreamCreateWithPriority(&r->k1Stream, cudaStreamNonBlocking, lo));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evK1Done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&r->evOrder, cudaEventDisableTiming));
+    for (auto& e : r->evFrameDone2) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&r->evWave, cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&r->evWaveJoin, cudaEventDisableTiming));
     r->allocate();
   } catch (...) { eid_renderer_destroy(r); throw; }
@@ -481,6 +521,10 @@ void eid_renderer_destroy(eid_renderer* r) {
   if (r->evFork) cudaEventDestroy(r->evFork); if (r->evJoin) cudaEventDestroy(r->evJoin); if (r->evPost) cudaEventDestroy(r->evPost);
   if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
   if (r->shadowStream) { cudaStreamSynchronize(r->shadowStream); cudaStreamDestroy(r->shadowStream); }
+  if (r->k1Stream) { cudaStreamSynchronize(r->k1Stream); cudaStreamDestroy(r->k1Stream); }
+  if (r->evK1Done) cudaEventDestroy(r->evK1Done);
+  if (r->evOrder) cudaEventDestroy(r->evOrder);
+  for (auto& e : r->evFrameDone2) if (e) cudaEventDestroy(e);
   if (r->evWave) cudaEventDestroy(r->evWave); if (r->evWaveJoin) cudaEventDestroy(r->evWaveJoin);
   if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
   if (r->evFrameDone) cudaEventDestroy(r->evFrameDone); if (r->evCopyDone) cudaEventDestroy(r->evCopyDone);
@@ -723,6 +767,7 @@ int eid_renderer_run_trace(eid_renderer* r, const RtxState* state, int frames) {
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_trace: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
+  strictOrder(r);
   fillParams(r, *state, frames, P);
   launchTrace(r, P);
   CUDA_CHECK(cudaGetLastError());
@@ -736,6 +781,7 @@ int eid_renderer_run_direct(eid_renderer* r, const RtxState* state, int frames) 
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_direct: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
+  strictOrder(r);
   fillParams(r, *state, frames, P);
   beginFrame(r);
   stageDirect(r, P, r->stream);
@@ -749,6 +795,7 @@ int eid_renderer_run_indirect(eid_renderer* r, const RtxState* state, int frames
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_indirect: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
+  strictOrder(r);
   fillParams(r, *state, frames, P);
   stageIndirect(r, P, r->stream);
   CUDA_CHECK(cudaGetLastError());
@@ -761,6 +808,7 @@ int eid_renderer_run_post(eid_renderer* r, const RtxState* state, int frames) {
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_post: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
+  strictOrder(r);
   fillParams(r, *state, frames, P);
   launchPost(r, P, false);
   return EID_OK;
@@ -772,6 +820,7 @@ int eid_renderer_run_post_band(eid_renderer* r, const RtxState* state, int frame
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_run_post_band: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
   FrameParams P;
+  strictOrder(r);
   fillParams(r, *state, frames, P);
   launchPost(r, P, true);
   return EID_OK;
@@ -782,7 +831,8 @@ int eid_renderer_sync(eid_renderer* r) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_sync: null renderer");
   CUDA_CHECK(cudaSetDevice(r->device));
-  CUDA_CHECK(cudaStreamSynchronize(r->stream));   // the aux stream is always joined into the main stream before a frame ends
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));   // the aux stream is always joined into the main stream before a frame ends,
+  if (r->pipeline) CUDA_CHECK(cudaStreamSynchronize(r->k1Stream));   // ... and every direct_stage is followed by its frame on the main stream
   return EID_OK;
   EID_CATCH
 }
@@ -867,6 +917,7 @@ int eid_renderer_render_host_async(eid_renderer* r, const SceneCamera* cam, cons
   if (r->copyPending) CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evCopyDone, 0));
   if (direct_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[0], r->directImg, n, cudaMemcpyDeviceToDevice, r->stream));
   if (indirect_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[1], r->indirectImg, n, cudaMemcpyDeviceToDevice, r->stream));
+  markFrameDone(r);                                 // the snapshots read this parity's direct image: part of the frame
   CUDA_CHECK(cudaEventRecord(r->evFrameDone, r->stream));
   CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, r->evFrameDone, 0));
   const size_t rowBytes = (size_t)state->size.x * 16;
@@ -923,6 +974,20 @@ int eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks) {
   r->wavefront = enabled != 0;
   r->waveOverlap = enabled != 2;      // 2: wavefront with every queue on the main stream (strictly serial stages)
   r->traceBlocks = traceBlocks;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_pipeline(eid_renderer* r, int framesInFlight) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_pipeline: null renderer");
+  if (framesInFlight < 1 || framesInFlight > 2) raise(EID_ERR_INVALID, "eid_renderer_set_pipeline: 1 (strict) or 2 frames in flight");
+  CUDA_CHECK(cudaSetDevice(r->device));
+  CUDA_CHECK(cudaStreamSynchronize(r->k1Stream));
+  CUDA_CHECK(cudaStreamSynchronize(r->stream));
+  r->pipeline = framesInFlight == 2;
+  r->k1MustWaitStream = true;
+  r->frameDoneValid[0] = r->frameDoneValid[1] = false;
   return EID_OK;
   EID_CATCH
 }

@@ -22,7 +22,18 @@ struct eid_renderer {
   short2* motion = nullptr;
   float* directResv[2] = {nullptr, nullptr};
   float* indirectResv[2] = {nullptr, nullptr};
-  float4* directImg = nullptr; float4* indirectImg = nullptr;
+  float4* directImgs[2] = {nullptr, nullptr};   // thisDirectResultImage, one per ping-pong parity (a frame in flight keeps its own while the next one traces)
+  float4* directImg = nullptr;                  // = directImgs[parity of the frame enqueued last]
+  float4* indirectImg = nullptr;
+  uint4* k2G[2] = {nullptr, nullptr}; short2* k2Mv[2] = {nullptr, nullptr};   // FrameParams::k2G / k2Mv, per parity
+  // frames in flight (eid_renderer_set_pipeline): direct_stage of frame f + 1 runs on `k1Stream` while indirect_stage / denoise / compose of
+  // frame f are still on the render stream; evK1Done orders K2 / K3 after K1, evFrameDone[parity] lets K1 reuse a parity's buffers
+  int pipeline = 0;
+  cudaStream_t k1Stream = nullptr;
+  cudaEvent_t evK1Done = nullptr, evFrameDone2[2] = {nullptr, nullptr};
+  bool frameDoneValid[2] = {false, false};
+  bool k1MustWaitStream = false;     // a strictly ordered entry point (run_trace, run_direct, the group schedule ...) ran on the render stream since the last pipelined frame
+  cudaEvent_t evOrder = nullptr;
   float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
@@ -71,11 +82,13 @@ struct eid_renderer {
 
 // per-frame pieces of eid_renderer_run (render.cu), reused by the multi-GPU schedule of group.cu
 void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P);
-void beginFrame(eid_renderer* r);
+void beginFrame(eid_renderer* r, cudaStream_t st = nullptr);
 void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
 void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
 void launchPost(eid_renderer* r, const FrameParams& P, bool sharded);
 void* bufferPtr(eid_renderer* r, int which, size_t& bytes);
+// called by every entry point that enqueues stages on the render stream in strict order: orders them after any direct_stage still on the K1 stream
+void strictOrder(eid_renderer* r);
 // post stages one by one (the multi-GPU schedule starts the direct denoiser as soon as exchange A has landed, beside indirect_stage)
 struct PostLayout { int first, stride, srows, count; bool sharded; };
 PostLayout postLayout(const FrameParams& P, bool sharded);

@@ -48,7 +48,13 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
       mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
       const float mvx = __fadd_rn(__fmul_rn(__fdiv_rn(pr[0], pr[3]), 0.5f), 0.5f), mvy = __fadd_rn(__fmul_rn(__fdiv_rn(pr[1], pr[3]), 0.5f), 0.5f);
       const int mix_ = f2i_sat(__fmul_rn(mvx, (float)W)), miy = f2i_sat(__fmul_rn(mvy, (float)H));
-      P.motion[pix] = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
+      const short2 mvs = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));   // RG16_SINT store saturates
+      P.motion[pix] = mvs;
+      if (!((x | y) & 1) && (x >> 1) < (W >> 1) && (y >> 1) < (H >> 1)) {     // pixel 2 * coord of the quarter-res stage: its temporal lookup, gathered here
+        const size_t q = (size_t)(y >> 1) * (P.pitch >> 1) + (x >> 1);
+        P.k2Mv[q] = mvs;
+        P.k2G[q] = loadG(P.lastG, P, mvs.x, mvs.y);
+      }
       P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
 
       if (P.st.debugging_mode > eIndirectStage) {          // DebugInfo (pathtrace.glsl:362-380)

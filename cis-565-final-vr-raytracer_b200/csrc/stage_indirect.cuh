@@ -58,9 +58,10 @@ DEV void giFinish(const FrameParams& P, int x, int y, int Wi, int Hi, uint32_t& 
   uint32_t rnum = 0; float rweight = 0.f, rbigW = 0.f;
   if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {   // findTemporalNeighbor :74-108
     const float reprojDepth = len3(ld3(P.cam.lastPosition) - primPos);
-    short2 mv = make_short2(0, 0);
-    if (2 * x < P.pitch && 2 * y < P.allocH) mv = P.motion[(size_t)(2 * y) * P.pitch + 2 * x];
-    const uint4 gl = loadG(P.lastG, P, mv.x, mv.y);
+    // motionVector[2 * coord] and lastGbuffer[that motion index], as direct_stage gathered them for this pixel (FrameParams::k2G)
+    const size_t q = (size_t)y * (P.pitch >> 1) + x;
+    const short2 mv = P.k2Mv[q];
+    const uint4 gl = P.k2G[q];
     const f3 pnorm = octDecode(gl.y);
     const float pdepth = __uint_as_float(gl.x);
     const int cx = mv.x / 2, cy = mv.y / 2;

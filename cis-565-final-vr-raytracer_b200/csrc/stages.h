@@ -19,7 +19,7 @@ void launchGiBegin(const FrameParams& P, dim3 grid, cudaStream_t st, bool tex);
 void launchGiBounce(const FrameParams& P, int blocks, cudaStream_t st, bool tex, int depth);
 void launchGiFinish(const FrameParams& P, dim3 grid, cudaStream_t st);
 void launchTraceQueue(bool any, bool stats, int blocks, cudaStream_t st, const AccelView& A, const float4* rays, const uint32_t* count,
-                      uint32_t* cursor, float4* hits, uint32_t* occl, unsigned long long* counters);
+                      uint32_t* cursor, float4* hits, uint32_t* occl, unsigned long long* counters, unsigned long long* totals);
 
 // K3 / K4 / K5 + display pass + parity taps (k_post.cu)
 void launchDenoisePrep(const FrameParams& P, dim3 grid, cudaStream_t st, int first, int stride, int rows, bool fastPlanes);

@@ -409,11 +409,11 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const AccelView A, const float4* __restrict__ rays, const uint32_t* __restrict__ countPtr,
                                                                         uint32_t* __restrict__ cursor, float4* __restrict__ hits, uint32_t* __restrict__ occl,
-                                                                        unsigned long long* __restrict__ counters) {
+                                                                        unsigned long long* __restrict__ counters, unsigned long long* __restrict__ totals) {
   const uint32_t n = *countPtr;
   const unsigned lane = threadIdx.x & 31u;
   if (blockIdx.x == 0 && threadIdx.x == 0 && n) {   // ray counters of the frame ([0] closest, [1] any) and since creation ([5], [6])
-    atomicAdd(&counters[ANY ? 1 : 0], (unsigned long long)n); atomicAdd(&counters[ANY ? 6 : 5], (unsigned long long)n);
+    atomicAdd(&counters[ANY ? 1 : 0], (unsigned long long)n); atomicAdd(&totals[ANY ? 6 : 5], (unsigned long long)n);
   }
   int stack[EID_STACK_SIZE];
   int sp = 0, cur = EID_TRAV_DONE;

@@ -338,6 +338,13 @@ EID_API int  eid_renderer_wait_host(eid_renderer* r);
  * denoiser (K4) — the reference's true dependencies are K1->{K2,K3}, K2->K4, {K3,K4}->K5.  0: strict K1..K5 order on one stream.
  * Results are identical either way; per-stage times (kernelMs) overlap when enabled. */
 EID_API int  eid_renderer_set_overlap(eid_renderer* r, int enabled);
+/* Frames in flight.  1 (default): a frame's stages only start when the previous eid_renderer_run has finished (the reference records one
+ * command buffer per frame).  2: direct_stage of frame f + 1 runs on an internal stream while indirect_stage / denoise / compose of frame f
+ * are still on the renderer's stream — the direct stage only needs the G-buffer and the direct reservoirs of frame f, both complete after
+ * ITS direct stage; what the later stages of frame f read is double-buffered per ping-pong parity.  Results are bit-identical to mode 1;
+ * the host must call eid_renderer_run with consecutive `frames` values and not modify the cross-frame buffers in between.  Work the host
+ * enqueued on the renderer's stream before a run is NOT waited for by that frame's direct stage in mode 2. */
+EID_API int  eid_renderer_set_pipeline(eid_renderer* r, int framesInFlight);
 /* 0: off (default; ray counters are always kept), 1: per-stage CUDA-event timing,
  * 2: additionally run the instrumented trace kernels that count BVH node visits / triangle tests */
 EID_API int  eid_renderer_set_profiling(eid_renderer* r, int enabled);

@@ -924,3 +924,60 @@ def test_environment_reload_keeps_the_renderers_map_alive():
     frame(2, common.env_state_overrides(penv.get_integral()))
     prr.set_env(None)
     penv.destroy()
+
+
+@pytest.mark.parametrize("restir", [abi.eTemporal, abi.eSpatiotemporal])
+def test_frames_in_flight_are_bit_identical(restir):
+    """eid_renderer_set_pipeline(2): direct_stage of frame f + 1 overlaps indirect_stage / denoise / compose of frame f (its own stream, per-parity
+    direct image / K2 gather buffers / counters).  A burst of frames enqueued without any host synchronisation — moving camera, so every temporal
+    lookup really reads the previous frame — must leave exactly the buffers the strictly ordered renderer leaves, frame after frame."""
+    arrays = scenes.small_room()
+    size = (448, 256)
+    psc = eid.Scene(0); psc.load_arrays(arrays)
+    acc = eid.AccelStructure(); acc.create(psc)
+    strict, piped, hosted = eid.Renderer(), eid.Renderer(), eid.Renderer()
+    for r in (strict, piped, hosted):
+        r.create(size, psc, acc); r.set_env_constant(common.ENV)
+    piped.set_pipeline(2); hosted.set_pipeline(2)
+    info = psc.info()
+    cam = arrays.camera
+    psc.update_camera(*size)
+    bufs = [[np.zeros((size[1], size[0], 4), np.float32) for _ in range(2)] for _ in range(2)]
+    f = 0
+    for burst in (1, 5, 2, 7):
+        cams, states = [], []
+        for _ in range(burst):
+            a = np.deg2rad(0.8 * f)
+            e = np.array(cam["eye"], np.float64)
+            psc.set_lookat((e[0] * np.cos(a) - e[2] * np.sin(a), e[1], e[0] * np.sin(a) + e[2] * np.cos(a)), cam["center"], cam["up"], np.rad2deg(cam["yfov"]))
+            psc.update_camera(*size)
+            st = common.frame_state(size[0], size[1], info, f, ReSTIRState=restir, maxDepth=3)
+            strict.run(st, f); strict.sync()
+            piped.run(st, f)                                        # no sync inside the burst
+            hosted.render_host_async(psc.get_camera(), st, f, bufs[f & 1][0].ctypes.data, bufs[f & 1][1].ctypes.data)
+            f += 1
+        piped.sync(); hosted.wait_host(); hosted.sync()
+        want = common.snapshot(strict)
+        for name, r in (("pipelined", piped), ("pipelined host", hosted)):
+            got = common.snapshot(r)
+            for k in want:
+                assert got[k].tobytes() == want[k].tobytes(), "%s: %s differs after frame %d" % (name, k, f - 1)
+            s0, s1 = strict.stats(), r.stats()
+            assert (s0.closestHitRays, s0.anyHitRays, s0.primaryHits) == (s1.closestHitRays, s1.anyHitRays, s1.primaryHits)
+            assert (s0.totalClosestHitRays, s0.totalAnyHitRays) == (s1.totalClosestHitRays, s1.totalAnyHitRays)
+        k = (f - 1) & 1
+        assert strict.read(abi.BUF_DIRECT).tobytes() == bufs[k][0].tobytes() and strict.read(abi.BUF_INDIRECT).tobytes() == bufs[k][1].tobytes()
+    # strictly ordered entry points mixed in: run_trace + run_post on the pipelined renderer, then pipelined frames again
+    for mixed in range(3):
+        psc.update_camera(*size)
+        st = common.frame_state(size[0], size[1], info, f, ReSTIRState=restir, maxDepth=3)
+        strict.run(st, f)
+        if mixed == 1:
+            piped.run_trace(st, f); piped.run_post(st, f)
+        else:
+            piped.run(st, f)
+        f += 1
+    piped.sync(); strict.sync()
+    want, got = common.snapshot(strict), common.snapshot(piped)
+    for k in want:
+        assert got[k].tobytes() == want[k].tobytes(), "mixed strict / pipelined entry points: %s differs" % k
