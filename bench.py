@@ -333,6 +333,8 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    host_ms = []
+
     def timed(nsteps, first_frame, e2e_bufs=None, profiling=0):
         rr.set_profiling(profiling)
         s0 = rr.stats()
@@ -340,10 +342,12 @@ def run_cuda(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kms = np.zeros(5)
         e0.record(stream)
+        th0 = time.perf_counter()
         for k in range(nsteps):
             step(first_frame + k, e2e_bufs)
             if profiling:
                 kms += np.array(rr.stats().kernelMs[:])     # syncs; only used in the separate per-kernel pass
+        host_ms.append(1e3 * (time.perf_counter() - th0) / nsteps)   # host time to ENQUEUE one frame (no synchronisation inside the loop)
         if e2e_bufs is not None and world == 1:
             rr.wait_host()                           # the last frame's device->host copies are inside the timed region
         if e2e_bufs is not None and world > 1:
@@ -396,6 +400,12 @@ def run_cuda(args):
     _, _, kms = timed(ksteps, frame, None, profiling=1)
     rr.set_overlap(not args.no_overlap)
     frame += ksteps
+    rank_kms = None
+    if dist is not None:                        # every rank's stage times (the frame is as slow as the slowest rank)
+        tk = torch.tensor(kms, device=dev, dtype=torch.float64)
+        allk = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(allk, tk)
+        rank_kms = [[round(float(v), 4) for v in t.cpu().numpy()] for t in allk]
     rr.set_profiling(2)
     step(frame)
     vs = rr.stats()
@@ -485,6 +495,8 @@ def run_cuda(args):
                             + ("run K3 concurrently with K2+K4 on a second stream, so their sum exceeds ms_per_step" if not args.no_overlap else "are serialised too"),
             "exchange1_ms": float(vs.exchangeMs) if world > 1 else None,
             "image_crc32": "%08x" % crc, "frames_rendered": frame,
+            "host_enqueue_ms_per_frame": {"device_timed": host_ms[0], "e2e": host_ms[1]},
+            "stage_ms_per_rank": rank_kms,
             "nccl_launches_per_frame": (3 if args.post == "sharded" else 2) if world > 1 else 0,
             "visits_per_ray": {"nodes": vs.nodeVisits / tot_rays, "triangles": vs.triangleTests / tot_rays},
         }

@@ -74,6 +74,8 @@ struct eid_group {
   int history = 2;                                 // reservoir history across band edges: 0 never, 1 every frame (behind the post stages), 2 lazily when the camera moved
   int gatherFinal = 1;                             // exchange C
   bool historyComplete = false;                    // the LAST reservoirs of the next frame are complete on this rank
+  bool histPending = false, finalPending = false;  // the render stream has not yet been ordered after the eager history gather / exchange C
+  cudaEvent_t evHist = nullptr;
   uint32_t bandRows = 0;
   // host delivery of this rank's band
   cudaStream_t copyStream = nullptr;
@@ -117,6 +119,7 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
     renderAfter(g, g->evH);
   }
   g->historyComplete = false;
+  if (g->histPending) { CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evHist, 0)); g->histPending = false; }   // K1 reprojects into the gathered history
   beginFrame(r);
   stageDirect(r, P, r->stream);
   const bool eager = g->world > 1 && temporal && g->history == 1;
@@ -145,12 +148,16 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
     if (eager) {                                            // history for the NEXT frame: behind the post stages
       const int h[2] = {EID_BUF_THIS_DIRECT_RESV, EID_BUF_THIS_INDIRECT_RESV};
       gatherList(g, h, 2);
-      g->historyComplete = true;
+      CUDA_CHECK(cudaEventRecord(g->evHist, g->cs));
+      g->historyComplete = true; g->histPending = true;
     }
   }
   if (r->profiling) CUDA_CHECK(cudaEventRecord(r->evPost, r->stream));   // K2 end .. here = what the render stream waited for exchange B
   r->postStarted = true;
   CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evPrep, 0));
+  // exchange C of the PREVIOUS frame ran behind this frame's trace stages (it only touches the previous parity's direct image and the
+  // indirect result image); the first stage that writes the indirect result image is ordered after it here
+  if (g->finalPending) { CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evD, 0)); g->finalPending = false; }
   markStart(r, EID_K_DENOISE_INDIRECT, r->stream);
   stageDenoiseIndirect(r, P, L, r->stream);
   markStop(r, EID_K_DENOISE_INDIRECT, r->stream);
@@ -160,10 +167,9 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
   if (g->world > 1 && g->post == 1 && finalGather) {
     const int c[2] = {EID_BUF_DIRECT, EID_BUF_INDIRECT};
     commAfter(g, g->evC);
-    gatherList(g, c, 2);                                    // exchange C: the composed frame on every rank
-    renderAfter(g, g->evD);
-  } else if (eager) {
-    renderAfter(g, g->evD);                                 // the next frame's direct stage must see the gathered history
+    gatherList(g, c, 2);                                    // exchange C: the composed frame on every rank; complete after eid_group_sync
+    CUDA_CHECK(cudaEventRecord(g->evD, g->cs));             // (the render stream is ordered after it when the next frame needs the images)
+    g->finalPending = true;
   }
 }
 
@@ -202,7 +208,8 @@ int eid_group_create(eid_group** out, eid_renderer* r, int rank, int world, cons
     g->r = r; g->rank = rank; g->world = world; g->bandRows = r->height / world;
     CUDA_CHECK(cudaSetDevice(r->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&g->evA, &g->evB, &g->evX, &g->evC, &g->evD, &g->evH, &g->evA2, &g->evPrep, &g->evK3}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    r->groupStream = g->cs;                         // eid_renderer_sync / read / get_stats also wait for the exchanges
+    for (cudaEvent_t* e : {&g->evA, &g->evB, &g->evX, &g->evC, &g->evD, &g->evH, &g->evA2, &g->evPrep, &g->evK3, &g->evHist}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     if (world > 1) {
       NcclId id;
       memcpy(&id, id128, sizeof(id));
@@ -219,9 +226,10 @@ void eid_group_destroy(eid_group* g) {
   if (!g) return;
   if (g->r) cudaSetDevice(g->r->device);
   if (g->cs) cudaStreamSynchronize(g->cs);
+  if (g->r && g->r->groupStream == g->cs) g->r->groupStream = nullptr;
   if (g->copyStream) { cudaStreamSynchronize(g->copyStream); cudaStreamDestroy(g->copyStream); }
   if (g->comm) nccl().CommDestroy(g->comm);
-  for (cudaEvent_t e : {g->evA, g->evB, g->evX, g->evC, g->evD, g->evH, g->evA2, g->evPrep, g->evK3, g->evFrameDone, g->evCopyDone}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {g->evA, g->evB, g->evX, g->evC, g->evD, g->evH, g->evA2, g->evPrep, g->evK3, g->evHist, g->evFrameDone, g->evCopyDone}) if (e) cudaEventDestroy(e);
   cudaFree(g->staging[0]); cudaFree(g->staging[1]);
   if (g->cs) cudaStreamDestroy(g->cs);
   delete g;

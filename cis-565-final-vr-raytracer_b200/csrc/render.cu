@@ -833,6 +833,7 @@ int eid_renderer_sync(eid_renderer* r) {
   CUDA_CHECK(cudaSetDevice(r->device));
   CUDA_CHECK(cudaStreamSynchronize(r->stream));   // the aux stream is always joined into the main stream before a frame ends,
   if (r->pipeline) CUDA_CHECK(cudaStreamSynchronize(r->k1Stream));   // ... and every direct_stage is followed by its frame on the main stream
+  if (r->groupStream) CUDA_CHECK(cudaStreamSynchronize(r->groupStream));   // exchange C of an eid_group frame
   return EID_OK;
   EID_CATCH
 }
@@ -859,6 +860,7 @@ int eid_renderer_read(eid_renderer* r, int which, void* host_dst, size_t bytes) 
   if (!p) raise(EID_ERR_INVALID, "no such buffer %d", which);
   if (bytes > b) raise(EID_ERR_INVALID, "read of %zu bytes from a %zu-byte buffer", bytes, b);
   CUDA_CHECK(cudaSetDevice(r->device));
+  if (r->groupStream) CUDA_CHECK(cudaStreamSynchronize(r->groupStream));
   CUDA_CHECK(cudaMemcpyAsync(host_dst, p, bytes, cudaMemcpyDeviceToHost, r->stream));
   CUDA_CHECK(cudaStreamSynchronize(r->stream));
   return EID_OK;

@@ -34,6 +34,7 @@ struct eid_renderer {
   bool frameDoneValid[2] = {false, false};
   bool k1MustWaitStream = false;     // a strictly ordered entry point (run_trace, run_direct, the group schedule ...) ran on the render stream since the last pipelined frame
   cudaEvent_t evOrder = nullptr;
+  cudaStream_t groupStream = nullptr;   // communication stream of the eid_group this renderer belongs to (synchronised with the render stream by sync / read / get_stats)
   float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
