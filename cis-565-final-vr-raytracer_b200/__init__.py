@@ -36,7 +36,7 @@ EXPORTS = [
     "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
-    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_denoise_tiles", "eid_renderer_set_overlap", "eid_renderer_set_pipeline", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_fn_tap", "eid_renderer_fn_tap", "eid_renderer_run_output", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
+    "eid_renderer_set_strict_math", "eid_renderer_set_denoise_rows", "eid_renderer_set_denoise_tiles", "eid_renderer_set_overlap", "eid_renderer_set_pipeline", "eid_renderer_set_variant", "eid_renderer_set_wavefront", "eid_renderer_set_sun_and_sky", "eid_sun_and_sky_eval", "eid_fn_tap", "eid_renderer_fn_tap", "eid_renderer_run_output", "eid_renderer_run", "eid_renderer_sync", "eid_renderer_get_outputs", "eid_renderer_buffer_bytes",
     "eid_renderer_read", "eid_renderer_write", "eid_renderer_render_host", "eid_renderer_render_host_async", "eid_renderer_wait_host", "eid_renderer_set_profiling",
     "eid_renderer_get_stats", "eid_renderer_set_band", "eid_renderer_run_trace", "eid_renderer_run_post", "eid_renderer_run_post_band", "eid_renderer_run_direct", "eid_renderer_run_indirect",
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
@@ -98,6 +98,7 @@ def lib():
         "eid_renderer_run_output": (i32, [vp, vp]),
         "eid_renderer_set_overlap": (i32, [vp, i32]),
         "eid_renderer_set_pipeline": (i32, [vp, i32]),
+        "eid_renderer_set_variant": (i32, [vp, i32]),
         "eid_renderer_run": (i32, [vp, C.POINTER(RtxState), i32]),
         "eid_renderer_sync": (i32, [vp]),
         "eid_renderer_get_outputs": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
@@ -373,6 +374,9 @@ class Renderer:
 
     def set_env_constant(self, rgb):
         _check(lib().eid_renderer_set_env_constant(self._h, _f3(rgb)))
+
+    def set_variant(self, flags):          # abi.VARIANT_* bits: the reference's compile-time shader switches
+        _check(lib().eid_renderer_set_variant(self._h, int(flags)))
 
     def set_pipeline(self, frames_in_flight):    # 1 strict (default); 2: direct_stage of frame f + 1 overlaps the later stages of frame f
         _check(lib().eid_renderer_set_pipeline(self._h, int(frames_in_flight)))

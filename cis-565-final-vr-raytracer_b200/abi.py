@@ -174,6 +174,9 @@ class FrameStats(C.Structure):
                 ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64)]
 
 
+VARIANT_DIRECT_BILATERAL, VARIANT_INDIRECT_BILATERAL, VARIANT_FETCH_4_SUBPIXELS = 1, 2, 4     # eid_renderer_set_variant
+
+
 class GroupInfo(C.Structure):   # eid_group_info
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("y0", C.c_uint32), ("y1", C.c_uint32), ("bandRows", C.c_uint32),
                 ("ncclVersion", C.c_int32), ("collectives", C.c_uint64)]

@@ -47,6 +47,8 @@ struct FrameParams {
   float* thisDR; const float* lastDR;     // DirectReservoir records, 9 floats each, pitch st.size.x
   float* thisIR; const float* lastIR;     // IndirectReservoir records, 19 floats each, pitch st.size.x/2
   float4* directImg; float4* indirectImg;
+  float4* directOut;                      // where direct_stage stores: directImg, or dirA with EID_VARIANT_DIRECT_BILATERAL (direct_stage.comp:284-288)
+  int variant;                            // EID_VARIANT_* bits (the reference's compile-time shader switches)
   float* tempDR;                          // tempDirectResv (spatial reuse), pitch st.size.x; one buffer, persists across frames
   float4* spCont;                         // spatial reuse: what k_direct_spatial needs of a pixel's State, 3 planes of pitch*allocH
   float4* dirA; float4* dirB; float4* indA; float4* indB;

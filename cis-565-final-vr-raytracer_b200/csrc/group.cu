@@ -124,7 +124,8 @@ static void groupFrame(eid_group* g, const RtxState& st, int frames, bool finalG
   stageDirect(r, P, r->stream);
   const bool eager = g->world > 1 && temporal && g->history == 1;
   if (g->world > 1) {
-    const int a[3] = {EID_BUF_THIS_GBUFFER, EID_BUF_DIRECT, EID_BUF_THIS_DIRECT_RESV};
+    // the pre-denoise direct image lives in denoiseDirTempA with EID_VARIANT_DIRECT_BILATERAL (direct_stage.comp:284-288)
+    const int a[3] = {EID_BUF_THIS_GBUFFER, (r->variant & EID_VARIANT_DIRECT_BILATERAL) ? EID_BUF_DENOISE_DIR_A : EID_BUF_DIRECT, EID_BUF_THIS_DIRECT_RESV};
     commAfter(g, g->evA);
     gatherList(g, a, 2);                                    // exchange A, behind indirect_stage
   }

@@ -6,9 +6,15 @@
 
 namespace eid {
 
-void launchDenoisePrep(const FrameParams& P, dim3 g, cudaStream_t st, int first, int stride, int rows, bool fastPlanes) {
-  if (fastPlanes) k_denoise_prep<true><<<g, dim3(32, 8), 0, st>>>(P, first, stride, rows);
-  else k_denoise_prep<false><<<g, dim3(32, 8), 0, st>>>(P, first, stride, rows);
+void launchDenoisePrep(const FrameParams& P, dim3 g, cudaStream_t st, int first, int stride, int rows, bool fastFull, bool fastQuarter) {
+  const dim3 b(32, 8);
+  if (fastFull) { if (fastQuarter) k_denoise_prep<true, true><<<g, b, 0, st>>>(P, first, stride, rows); else k_denoise_prep<true, false><<<g, b, 0, st>>>(P, first, stride, rows); }
+  else { if (fastQuarter) k_denoise_prep<false, true><<<g, b, 0, st>>>(P, first, stride, rows); else k_denoise_prep<false, false><<<g, b, 0, st>>>(P, first, stride, rows); }
+}
+void launchBilateral(bool indirect, bool strict, dim3 g, cudaStream_t st, const FrameParams& P, const float4* src, float4* dst, int first, int stride, int rows) {
+  const dim3 b(32, 4);
+  if (indirect) { if (strict) k_bilateral<true, true><<<g, b, 0, st>>>(P, src, dst, first, stride, rows); else k_bilateral<true, false><<<g, b, 0, st>>>(P, src, dst, first, stride, rows); }
+  else { if (strict) k_bilateral<false, true><<<g, b, 0, st>>>(P, src, dst, first, stride, rows); else k_bilateral<false, false><<<g, b, 0, st>>>(P, src, dst, first, stride, rows); }
 }
 
 template <bool INDIRECT, bool STRICT>

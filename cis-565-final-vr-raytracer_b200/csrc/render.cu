@@ -104,6 +104,8 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   r->directImg = r->directImgs[set];
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
   P.k2G = r->k2G[set]; P.k2Mv = r->k2Mv[set];
+  P.variant = r->variant;
+  P.directOut = (r->variant & EID_VARIANT_DIRECT_BILATERAL) ? r->denoiseTemp[0] : r->directImg;
   if ((st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal) && !r->tempDirectResv) {   // m_directTempResv (renderer.cpp:235), on first use
     const size_t n = (size_t)r->width * r->height;
     CUDA_CHECK(cudaMalloc((void**)&r->tempDirectResv, n * sizeof(DirectReservoir)));
@@ -232,7 +234,8 @@ void stagePrep(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaS
   if (P.st.denoise <= 0 || L.count <= 0) return;
   const int rows = L.srows + 2 * 124, W = P.st.size.x;
   dim3 g((W + 31) / 32, gridRows(L, rows, 8));
-  launchDenoisePrep(P, g, st, L.first - 124, L.stride, rows, r->denoiseTiles != 0 && !r->strictMath && fastSigmas(P.st));
+  const bool fast = r->denoiseTiles != 0 && !r->strictMath && fastSigmas(P.st);     // pre-scaled planes feed the tile kernel's fast path only
+  launchDenoisePrep(P, g, st, L.first - 124, L.stride, rows, fast && !(P.variant & EID_VARIANT_DIRECT_BILATERAL), fast && !(P.variant & EID_VARIANT_INDIRECT_BILATERAL));
   r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
 }
 
@@ -312,6 +315,11 @@ static void launchDenoise(eid_renderer* r, const FrameParams& P, const float4* s
 }
 
 void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:178-189
+  if (P.st.denoise > 0 && L.count > 0 && (P.variant & EID_VARIANT_DIRECT_BILATERAL)) {   // ONE pass: denoiseDirTempA -> thisDirect (renderer.cpp:186-188)
+    dim3 g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 4));
+    launchBilateral(false, r->strictMath, g, st, P, P.dirA, P.directImg, L.first, L.stride, L.srows);
+    r->stats.kernelLaunches[EID_K_DENOISE_DIRECT]++;
+  } else
   if (P.st.denoise > 0 && L.count > 0) {   // thisDirect -> A -> B -> A -> thisDirect
     const int W = P.st.size.x;
     const float4* src[4] = {P.directImg, P.dirA, P.dirB, P.dirA};
@@ -327,6 +335,11 @@ void stageDenoiseDirect(eid_renderer* r, const FrameParams& P, const PostLayout&
 
 void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayout& L, cudaStream_t st) {   // renderer.cpp:191-202
   const int Wi = P.st.size.x / 2, Hi = P.st.size.y / 2;
+  if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && L.count > 0 && (P.variant & EID_VARIANT_INDIRECT_BILATERAL)) {   // ONE pass: IndA -> IndB
+    dim3 g((Wi + 31) / 32, gridRows(L, L.srows / 2, 4));
+    launchBilateral(true, r->strictMath, g, st, P, P.indA, P.indB, L.first / 2, L.stride / 2, L.srows / 2);
+    r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
+  } else
   if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && L.count > 0) {   // IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
     const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
@@ -976,6 +989,15 @@ int eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks) {
   r->wavefront = enabled != 0;
   r->waveOverlap = enabled != 2;      // 2: wavefront with every queue on the main stream (strictly serial stages)
   r->traceBlocks = traceBlocks;
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_renderer_set_variant(eid_renderer* r, int flags) {
+  EID_TRY
+  if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_variant: null renderer");
+  if (flags & ~(EID_VARIANT_DIRECT_BILATERAL | EID_VARIANT_INDIRECT_BILATERAL | EID_VARIANT_FETCH_4_SUBPIXELS)) raise(EID_ERR_INVALID, "eid_renderer_set_variant: unknown variant bits 0x%x", flags);
+  r->variant = flags;
   return EID_OK;
   EID_CATCH
 }

@@ -28,6 +28,7 @@ struct eid_renderer {
   uint4* k2G[2] = {nullptr, nullptr}; short2* k2Mv[2] = {nullptr, nullptr};   // FrameParams::k2G / k2Mv, per parity
   // frames in flight (eid_renderer_set_pipeline): direct_stage of frame f + 1 runs on `k1Stream` while indirect_stage / denoise / compose of
   // frame f are still on the render stream; evK1Done orders K2 / K3 after K1, evFrameDone[parity] lets K1 reuse a parity's buffers
+  int variant = 0;            // EID_VARIANT_* bits
   int pipeline = 0;
   cudaStream_t k1Stream = nullptr;
   cudaEvent_t evK1Done = nullptr, evFrameDone2[2] = {nullptr, nullptr};

@@ -138,10 +138,10 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
       }
     }
     if (!finished) {
-      if (own) P.directImg[pix] = make_float4(0.f, 0.f, 0.f, -1.0f);     // marker: k_direct_spatial completes this pixel
+      if (own) P.directOut[pix] = make_float4(0.f, 0.f, 0.f, -1.0f);     // marker: k_direct_spatial completes this pixel
     } else if (own) {
       const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);   // :283
-      P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+      P.directOut[pix] = make_float4(px.x, px.y, px.z, 1.0f);   // thisDirectResultImage, or denoiseDirTempA with DENOISER_DIRECT_BILATERAL (:284-288)
     }
   }
   if (!own) rc = RayCounters{0, 0, 0, 0, 0};     // a halo pixel's rays are the owner's, traced twice: not counted
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(64) k_direct_spatial(const FrameParams P) {
   const int W = P.st.size.x, H = P.st.size.y;
   if (x >= W || y >= H) return;
   const size_t pix = (size_t)y * P.pitch + x;
-  if (P.directImg[pix].w != -1.0f) return;                                 // sky, emitter, debug view: finished by k_direct_stage
+  if (P.directOut[pix].w != -1.0f) return;                                 // sky, emitter, debug view: finished by k_direct_stage
   const size_t plane = (size_t)P.pitch * P.allocH;
   const float4 c0 = P.spCont[pix], c1 = P.spCont[plane + pix], c2 = P.spCont[2 * plane + pix];
   uint32_t seed = __float_as_uint(c0.x);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(64) k_direct_spatial(const FrameParams P) {
   if (nan3(direct)) direct = mk3(0.0f);
   const f3 radiance = hdrToLdr(clampRadiance(emission + direct, P.st.fireflyClampThreshold));
   const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);
-  P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+  P.directOut[pix] = make_float4(px.x, px.y, px.z, 1.0f);
 }
 
 }  // namespace eid

@@ -28,24 +28,48 @@ DEV void storeIResv(float* base, size_t i, const GISampleD& g, uint32_t num, flo
 // State of the primary surface rebuilt from the G-buffer texel of full-res pixel 2*coord (getIndirectStateFromGBuffer,
 // pathtrace.glsl:296-313) with the +2e-2 push along ffnormal (indirect_stage.comp:299).  false = sky pixel.
 struct GIPrimary { f3 ro, rd; State st; };
-DEV bool giPrimary(const FrameParams& P, int x, int y, int Wi, int Hi, GIPrimary& pr) {
+DEV f3 unorm3(uint32_t w) { return mk3(unormToFloat(w & 0xffu), unormToFloat((w >> 8) & 0xffu), unormToFloat((w >> 16) & 0xffu)); }
+// seed != nullptr: the caller is at the point of main() where getIndirectStateFromGBuffer runs — the FETCH_GEOM_CHECK_4_SUBPIXELS variant
+// draws the material id there (pathtrace.glsl:346-357).  seed == nullptr (k_gi_finish rebuilding the state): no draw, st.matID is left to the caller.
+DEV bool giPrimary(const FrameParams& P, int x, int y, int Wi, int Hi, GIPrimary& pr, uint32_t* seed) {
   raySpawn<true>(P.cam, x, y, Wi, Hi, pr.ro, pr.rd);
-  const uint4 gi = loadG(P.thisG, P, 2 * x, 2 * y);
-  const float depth = __uint_as_float(gi.x);
-  if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) return false;
   State& st = pr.st;
-  st.position = pr.ro + pr.rd * depth;
-  st.normal = octDecode(gi.y);
-  st.ffnormal = dot3(st.normal, pr.rd) <= 0.0f ? st.normal : -st.normal;
-  st.mat.albedo = mk3(unormToFloat(gi.w & 0xffu), unormToFloat((gi.w >> 8) & 0xffu), unormToFloat((gi.w >> 16) & 0xffu));
-  st.mat.metallic = unormToFloat(gi.z & 0xffu);
-  st.mat.roughness = unormToFloat((gi.z >> 8) & 0xffu);
-  st.mat.ior = __fadd_rn(__fmul_rn(unormToFloat((gi.z >> 16) & 0xffu), MAX_IOR_MINUS_ONE), 1.f);
-  st.mat.transmission = unormToFloat(gi.z >> 24);
   st.mat.emission = mk3(0.f);
-  st.matID = gi.w >> 24;                                // hashed material id
   st.isEmitter = false; st.area = 0.f; st.eta = 0.f; st.u = st.v = 0.f;
   st.tangent = mk3(0.f); st.bitangent = mk3(0.f);
+  if (P.variant & EID_VARIANT_FETCH_4_SUBPIXELS) {                  // pathtrace.glsl:314-358
+    const uint4 g00 = loadG(P.thisG, P, 2 * x, 2 * y), g10 = loadG(P.thisG, P, 2 * x + 1, 2 * y);
+    const uint4 g11 = loadG(P.thisG, P, 2 * x + 1, 2 * y + 1), g01 = loadG(P.thisG, P, 2 * x, 2 * y + 1);
+    const float depth = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__uint_as_float(g00.x), __uint_as_float(g10.x)), __uint_as_float(g11.x)), __uint_as_float(g01.x)), 0.25f);
+    if (depth >= __fsub_rn(EID_INFINITY, __fmul_rn(0.0001f, 10.0f))) return false;
+    st.position = pr.ro + pr.rd * depth;
+    st.normal = (((octDecode(g00.y) + octDecode(g10.y)) + octDecode(g11.y)) + octDecode(g01.y)) * 0.25f;
+    st.ffnormal = dot3(st.normal, pr.rd) <= 0.0f ? st.normal : -st.normal;
+    st.mat.albedo = (((unorm3(g00.w) + unorm3(g10.w)) + unorm3(g11.w)) + unorm3(g01.w)) * 0.25f;
+    auto ch = [](uint32_t w, int k) { return unormToFloat((w >> (8 * k)) & 0xffu); };
+    st.mat.metallic = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(ch(g00.z, 0), ch(g10.z, 0)), ch(g11.z, 0)), ch(g01.z, 0)), 0.25f);
+    st.mat.roughness = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(ch(g00.z, 1), ch(g10.z, 1)), ch(g11.z, 1)), ch(g01.z, 1)), 0.25f);
+    st.mat.ior = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(ch(g00.z, 2), ch(g10.z, 2)), ch(g11.z, 2)), ch(g01.z, 2)), 0.25f), MAX_IOR_MINUS_ONE), 1.f);
+    st.mat.transmission = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(ch(g00.z, 3), ch(g01.z, 3)), ch(g11.z, 3)), ch(g10.z, 3)), 0.25f);
+    st.matID = 0;
+    if (seed) {
+      const float r = rnd(*seed);
+      st.matID = (r < 0.25f ? g00.w : r < 0.5f ? g10.w : r < 0.75f ? g11.w : g01.w) >> 24;
+    }
+  } else {
+    const uint4 gi = loadG(P.thisG, P, 2 * x, 2 * y);
+    const float depth = __uint_as_float(gi.x);
+    if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) return false;
+    st.position = pr.ro + pr.rd * depth;
+    st.normal = octDecode(gi.y);
+    st.ffnormal = dot3(st.normal, pr.rd) <= 0.0f ? st.normal : -st.normal;
+    st.mat.albedo = unorm3(gi.w);
+    st.mat.metallic = unormToFloat(gi.z & 0xffu);
+    st.mat.roughness = unormToFloat((gi.z >> 8) & 0xffu);
+    st.mat.ior = __fadd_rn(__fmul_rn(unormToFloat((gi.z >> 16) & 0xffu), MAX_IOR_MINUS_ONE), 1.f);
+    st.mat.transmission = unormToFloat(gi.z >> 24);
+    st.matID = gi.w >> 24;                                // hashed material id
+  }
   st.position = st.position + st.ffnormal * 2e-2f;      // :299
   return true;
 }
@@ -114,7 +138,7 @@ __global__ void __launch_bounds__(64, EID_K2_MIN_BLOCKS) k_indirect_stage(const 
       multiBounce = rnd(s0) < 0.25f;
     }
     GIPrimary pr;
-    if (!giPrimary(P, x, y, Wi, Hi, pr)) {
+    if (!giPrimary(P, x, y, Wi, Hi, pr, &seed)) {
       P.indA[(size_t)y * P.pitch + x] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
     } else {
       State st = pr.st;

@@ -28,7 +28,7 @@ DEV void thisGeometry(const FrameParams& P, int gx, int gy, int sw, int sh, floa
 
 // FAST (tile kernel, default numerics): the planes are pre-scaled for k_atrous_tile's fast path — position * sqrt(log2e / sigDepth),
 // normal * sqrt(log2e / sigNormal) with w = -|scaled normal|^2 — so that every exponent of a tap weight is a plain squared distance.
-template <bool FAST>
+template <bool FAST, bool FASTQ>
 __global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int first, int stride, int rows) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = stripeRow(first, stride, rows, 8);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_denoise_prep(const FrameParams P, int f
   P.geomPos[pix] = a; P.geomNrm[pix] = b;
   if (!(x & 1) && !(y & 1) && (x >> 1) < Wi && (y >> 1) < Hi) {
     thisGeometry(P, x, y, Wi, Hi, a, b);
-    if (FAST) {
+    if (FASTQ) {
       const float sd = sqrtf(LOG2E / P.st.sigDepthIndirect), sn = sqrtf(LOG2E / P.st.sigNormalIndirect);
       a = make_float4(a.x * sd, a.y * sd, a.z * sd, a.w);
       b = make_float4(b.x * sn, b.y * sn, b.z * sn, 0.f);
@@ -211,6 +211,81 @@ __global__ void __launch_bounds__(128) k_denoise(const FrameParams P, const floa
   const int lr0 = (v & (step - 1)) + ((v >> level) * R) * step;     // row of pixel 0 inside the stripe
   if (interior) atrousBody<INDIRECT, STRICT, R, false>(P, inImg, outImg, level, lastLevel, x, base + lr0, lr0, rows, bw, bh);
   else if (x < bw && v < vrows) atrousBody<INDIRECT, STRICT, R, true>(P, inImg, outImg, level, lastLevel, x, base + lr0, lr0, rows, bw, bh);
+}
+
+// =================================================================================================
+// DENOISER_DIRECT_BILATERAL / DENOISER_INDIRECT_BILATERAL (host_device.h:28-29; EID_VARIANT_*): ONE cross-bilateral pass instead of the
+// A-Trous levels — denoise_direct.comp:73-137 (9 x 9, spatial term exp(-(i^2 + j^2) / 10) + .01) and denoise_indirect.comp:77-130
+// (11 x 11, no spatial term).  Colour distance is the squared RGB difference in both.  Reads the RAW geometry planes of k_denoise_prep.
+// STRICT: the reference's arithmetic and tap order; otherwise MUFU ex2 on pre-scaled exponents and fused multiply-adds.
+// =================================================================================================
+template <bool INDIRECT, bool STRICT>
+__global__ void __launch_bounds__(128) k_bilateral(const FrameParams P, const float4* __restrict__ inImg, float4* __restrict__ outImg, int first, int stride, int rows) {
+  constexpr int RADIUS = INDIRECT ? 5 : 4;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = stripeRow(first, stride, rows, 4);
+  const int bw = INDIRECT ? P.st.size.x / 2 : P.st.size.x, bh = INDIRECT ? P.st.size.y / 2 : P.st.size.y;
+  if (x >= bw || y >= bh || y < 0) return;
+  const float sigL = INDIRECT ? P.st.sigLuminIndirect : P.st.sigLuminDirect;
+  const float sigN = INDIRECT ? P.st.sigNormalIndirect : P.st.sigNormalDirect;
+  const float sigD = INDIRECT ? P.st.sigDepthIndirect : P.st.sigDepthDirect;
+  const float LOG2E = 1.44269504088896341f;
+  const float nL = -LOG2E / sigL, nN = -LOG2E / sigN, nD = -LOG2E / sigD, nS = -LOG2E / 10.0f;
+  const float4* __restrict__ gPos = INDIRECT ? P.geomPosH : P.geomPos;
+  const float4* __restrict__ gNrm = INDIRECT ? P.geomNrmH : P.geomNrm;
+  const unsigned gp = INDIRECT ? P.pitch / 2 : P.pitch, ip = P.pitch;
+  const float4 cp = __ldg(gPos + ((unsigned)y * gp + (unsigned)x)), cn = __ldg(gNrm + ((unsigned)y * gp + (unsigned)x));
+  const float4 c4 = inImg[(unsigned)y * ip + (unsigned)x];
+  const uint32_t hash = __float_as_uint(cp.w);
+  const f3 pos = mk3(cp.x, cp.y, cp.z), norm = mk3(cn.x, cn.y, cn.z), color = mk3(c4.x, c4.y, c4.z);
+  f3 sum = mk3(0.0f);
+  float sumW = 0.0f;
+  if (!(INDIRECT && hash == EID_INVALID_MAT)) {           // the indirect variant returns 0 for sky pixels at once; the direct one runs (and finds no matching tap)
+    for (int j = -RADIUS; j <= RADIUS; j++) {
+      const int qy = y + j;
+      if (qy >= bh || qy < 0) continue;
+      for (int i = -RADIUS; i <= RADIUS; i++) {
+        const int qx = x + i;
+        if (qx >= bw || qx < 0) continue;
+        const float4 qp = __ldg(gPos + ((unsigned)qy * gp + (unsigned)qx));
+        const uint32_t hq = __float_as_uint(qp.w);
+        if (hash != hq || hq == EID_INVALID_MAT) continue;
+        const float4 qn = __ldg(gNrm + ((unsigned)qy * gp + (unsigned)qx)), q4 = inImg[(unsigned)qy * ip + (unsigned)qx];
+        const f3 cq = mk3(q4.x, q4.y, q4.z);
+        float w;
+        if (STRICT) {
+          const f3 dc = color - cq;
+          const float wColor = __fadd_rn(eid_expf(__fdiv_rn(-dot3(dc, dc), sigL)), 1e-2f);
+          const f3 dn = norm - mk3(qn.x, qn.y, qn.z);
+          const float wNorm = gmin(1.0f, eid_expf(__fdiv_rn(-dot3(dn, dn), sigN)));
+          const f3 dp = pos - mk3(qp.x, qp.y, qp.z);
+          const float wDepth = __fadd_rn(eid_expf(__fdiv_rn(-dot3(dp, dp), sigD)), 1e-2f);
+          w = __fmul_rn(__fmul_rn(wColor, wNorm), wDepth);
+          if (!INDIRECT) {
+            const float dist2 = (float)(i * i + j * j);
+            w = __fmul_rn(w, __fadd_rn(eid_expf(__fdiv_rn(-dist2, 10.0f)), 1e-2f));
+          }
+          sum = sum + cq * w;
+          sumW = __fadd_rn(sumW, w);
+        } else {
+          const float dx = color.x - cq.x, dy = color.y - cq.y, dz = color.z - cq.z;
+          const float nx = norm.x - qn.x, ny = norm.y - qn.y, nz = norm.z - qn.z;
+          const float px = pos.x - qp.x, py = pos.y - qp.y, pz = pos.z - qp.z;
+          const float wColor = edgeExp<false>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), sigL, nL) + 1e-2f;
+          const float wNorm = edgeExp<false>(fmaf(nz, nz, fmaf(ny, ny, nx * nx)), sigN, nN);
+          const float wDepth = edgeExp<false>(fmaf(pz, pz, fmaf(py, py, px * px)), sigD, nD) + 1e-2f;
+          w = (wColor * wNorm) * wDepth;
+          if (!INDIRECT) w *= edgeExp<false>((float)(i * i + j * j), 10.0f, nS) + 1e-2f;
+          sum = mk3(fmaf(cq.x, w, sum.x), fmaf(cq.y, w, sum.y), fmaf(cq.z, w, sum.z));
+          sumW += w;
+        }
+      }
+    }
+  }
+  f3 res = (sumW < 1e-5f) ? mk3(0.0f) : sum / sumW;
+  if (nan3(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = mk3(0.0f);
+  res = ldrToHdr(res);                                    // denoise_direct.comp:168 / denoise_indirect.comp:169
+  outImg[(unsigned)y * ip + (unsigned)x] = make_float4(res.x, res.y, res.z, 1.0f);
 }
 
 // =================================================================================================

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(64) k_gi_begin(const FrameParams P) {
       multiBounce = rnd(s0) < 0.25f;
     }
     GIPrimary pr;
-    if (!giPrimary(P, x, y, Wi, Hi, pr)) {
+    if (!giPrimary(P, x, y, Wi, Hi, pr, &seed)) {
       P.indA[(size_t)y * P.pitch + x] = make_float4(0.f, 0.f, 0.f, 0.f);      // :292-295
     } else {
       State& st = pr.st;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(64) k_gi_begin(const FrameParams P) {
         }
       }
       const float t0 = multiBounce ? 4.0f : 1.0f;
-      V.misc[slot] = make_uint4(seed, multiBounce ? GI_MULTIBOUNCE : 0u, 0u, 0u);
+      V.misc[slot] = make_uint4(seed, multiBounce ? GI_MULTIBOUNCE : 0u, st.matID, 0u);   // .z: the primary material id (drawn, with the 4-subpixel fetch)
       V.thr[slot] = make_float4(t0, t0, t0, 0.f);
       V.gsXv[slot] = make_float4(xv.x, xv.y, xv.z, primSamplePdf);
       V.gsNv[slot] = make_float4(nv.x, nv.y, nv.z, 0.f);
@@ -195,8 +195,9 @@ __global__ void __launch_bounds__(64) k_gi_finish(const FrameParams P) {
   const uint32_t slot = (blockIdx.y * gridDim.x + blockIdx.x) * 64u + threadIdx.y * 8u + threadIdx.x;
   const WaveView& V = P.wv;
   GIPrimary pr;
-  if (!giPrimary(P, x, y, Wi, Hi, pr)) return;              // sky: k_gi_begin wrote the pixel
+  if (!giPrimary(P, x, y, Wi, Hi, pr, nullptr)) return;     // sky: k_gi_begin wrote the pixel
   const uint4 misc = V.misc[slot];
+  pr.st.matID = misc.z;
   uint32_t seed = misc.x;
   const float4 xv = V.gsXv[slot], nv = V.gsNv[slot], xs = V.gsXs[slot], ns = V.gsNs[slot];
   GISampleD gs;

@@ -22,7 +22,8 @@ void launchTraceQueue(bool any, bool stats, int blocks, cudaStream_t st, const A
                       uint32_t* cursor, float4* hits, uint32_t* occl, unsigned long long* counters, unsigned long long* totals);
 
 // K3 / K4 / K5 + display pass + parity taps (k_post.cu)
-void launchDenoisePrep(const FrameParams& P, dim3 grid, cudaStream_t st, int first, int stride, int rows, bool fastPlanes);
+void launchDenoisePrep(const FrameParams& P, dim3 grid, cudaStream_t st, int first, int stride, int rows, bool fastFull, bool fastQuarter);
+void launchBilateral(bool indirect, bool strict, dim3 grid, cudaStream_t st, const FrameParams& P, const float4* src, float4* dst, int first, int stride, int rows);
 #define EID_TILE_W 32                  // lattice points per tile row = lanes of a warp
 #define EID_TILE_PW (EID_TILE_W + 4)   // + 2-point halo on both sides
 // one level of the shared-memory tile A-Trous kernel (stage_denoise.cuh)

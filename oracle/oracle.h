@@ -135,6 +135,7 @@ struct Renderer {
   vec3 envConstant;
   SunAndSky sunSky{};                  // _sunAndSky uniform (layouts.glsl:53); in_use == 1 replaces the HDR map
   int lastSet = 0;
+  int variant = 0;                     // EID_VARIANT_* bits: the reference's compile-time switches (host_device.h:27-29, indirect_stage.comp:35)
   std::atomic<uint64_t> closestRays{0}, anyRays{0}, primaryHits{0};
   double kernelMs[5] = {0, 0, 0, 0, 0};
 

@@ -226,6 +226,7 @@ ORC_API void orc_tone_exposure(const Tonemapper* tm, const float* rgbAndLum, int
   for (int i = 0; i < n; ++i) { const vec3 c = post_toneExposure(*tm, vec3(rgbAndLum[4 * i], rgbAndLum[4 * i + 1], rgbAndLum[4 * i + 2]), rgbAndLum[4 * i + 3]); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }
 ORC_API int orc_renderer_set_sun_and_sky(Renderer* r, const SunAndSky* ss) { r->sunSky = *ss; return 0; }
+ORC_API int orc_renderer_set_variant(Renderer* r, int flags) { r->variant = flags; return 0; }
 ORC_API void orc_sun_and_sky(const SunAndSky* ss, const float* dirs, int n, float* out) {   // known-answer tap
   for (int i = 0; i < n; ++i) { vec3 c = sun_and_sky(*ss, vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])); out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z; }
 }

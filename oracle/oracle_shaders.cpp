@@ -19,6 +19,7 @@
 namespace orc {
 
 static const float INFINITY_ = 1e28f;   // globals.glsl:29
+static const float EPS = 0.0001f;       // globals.glsl:30
 static const float M_PI_F = 3.14159265358979323846f;
 static const float InvalidPdf = -1.0f;  // common.glsl:30
 static const uint InvalidMatId = 0xff000000u;   // globals.glsl:106
@@ -626,6 +627,29 @@ struct Ctx {
     return r;
   }
   bool getIndirectStateFromGBuffer(const std::vector<uvec4>& gBuffer, const Ray& ray, State& state, float& depth) {   // :296-313
+    if (rr.variant & EID_VARIANT_FETCH_4_SUBPIXELS) {                                            // #if FETCH_GEOM_CHECK_4_SUBPIXELS (:314-358)
+      uvec4 gInfo00 = loadG(gBuffer, imageCoords * 2 + ivec2(0, 0));
+      uvec4 gInfo10 = loadG(gBuffer, imageCoords * 2 + ivec2(1, 0));
+      uvec4 gInfo11 = loadG(gBuffer, imageCoords * 2 + ivec2(1, 1));
+      uvec4 gInfo01 = loadG(gBuffer, imageCoords * 2 + ivec2(0, 1));
+      depth = (uintBitsToFloat(gInfo00.x) + uintBitsToFloat(gInfo10.x) + uintBitsToFloat(gInfo11.x) + uintBitsToFloat(gInfo01.x)) * 0.25f;
+      if (depth >= INFINITY_ - EPS * 10.0f) return false;
+      state.position = ray.origin + ray.direction * depth;
+      state.normal = (decompress_unit_vec(gInfo00.y) + decompress_unit_vec(gInfo10.y) + decompress_unit_vec(gInfo11.y) + decompress_unit_vec(gInfo01.y)) * 0.25f;
+      state.ffnormal = dot(state.normal, ray.direction) <= 0.0f ? state.normal : -state.normal;
+      state.mat.albedo = (unpackUnorm4x8(gInfo00.w).xyz() + unpackUnorm4x8(gInfo10.w).xyz() + unpackUnorm4x8(gInfo11.w).xyz() + unpackUnorm4x8(gInfo01.w).xyz()) * 0.25f;
+      vec4 matInfo00 = unpackUnorm4x8(gInfo00.z), matInfo10 = unpackUnorm4x8(gInfo10.z), matInfo11 = unpackUnorm4x8(gInfo11.z), matInfo01 = unpackUnorm4x8(gInfo01.z);
+      state.mat.metallic = (matInfo00.x + matInfo10.x + matInfo11.x + matInfo01.x) * 0.25f;
+      state.mat.roughness = (matInfo00.y + matInfo10.y + matInfo11.y + matInfo01.y) * 0.25f;
+      state.mat.ior = (matInfo00.z + matInfo10.z + matInfo11.z + matInfo01.z) * 0.25f * MAX_IOR_MINUS_ONE + 1.f;
+      state.mat.transmission = (matInfo00.w + matInfo01.w + matInfo11.w + matInfo10.w) * 0.25f;
+      float r = rand();
+      if (r < 0.25f) state.matID = gInfo00.w >> 24;
+      else if (r < 0.5f) state.matID = gInfo10.w >> 24;
+      else if (r < 0.75f) state.matID = gInfo11.w >> 24;
+      else state.matID = gInfo01.w >> 24;
+      return true;
+    }
     uvec4 gInfo = loadG(gBuffer, imageCoords * 2);
     depth = uintBitsToFloat(gInfo.x);
     if (depth >= INFINITY_ * 0.8f) return false;
@@ -822,7 +846,8 @@ struct Ctx {
     Ray ray = raySpawn(imageCoords, imageRes);
     vec3 radiance = ReSTIRDirect(ray);
     vec3 pixelColor = clampRadiance(radiance);
-    storeImg(rr.directResult, imageCoords, vec4(pixelColor, 1));
+    if (rr.variant & EID_VARIANT_DIRECT_BILATERAL) storeImg(rr.denoiseTemp[0], imageCoords, vec4(pixelColor, 1));   // #if DENOISER_DIRECT_BILATERAL (:284-288)
+    else storeImg(rr.directResult, imageCoords, vec4(pixelColor, 1));
   }
 
   // ---- indirect_stage.comp ----------------------------------------------------------------------
@@ -1050,6 +1075,46 @@ struct Ctx {
     if (hasNan(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = vec3(0.0f);
     return res;
   }
+  // #if DENOISER_DIRECT_BILATERAL (denoise_direct.comp:73-137, Radius 4, with the spatial term) / #if DENOISER_INDIRECT_BILATERAL
+  // (denoise_indirect.comp:77-130, Radius 5, no spatial term, sky pixels return 0 at once)
+  vec3 bilateralFilter(const std::vector<vec4>& inImage, ivec2 coord, vec3 norm, vec3 pos, uint matHash,
+                       float sigLumin, float sigNormal, float sigDepth, bool indirectMode) {
+    const int Radius = indirectMode ? 5 : 4;
+    if (indirectMode && matHash == InvalidMatId) return vec3(0.0f);
+    vec3 sum = vec3(0.0f);
+    float sumWeight = 0.0f;
+    vec3 color = loadImg(inImage, coord).xyz();
+    ivec2 bound = indirectMode ? indSize() : size();
+    for (int j = -Radius; j <= Radius; j++) {
+      for (int i = -Radius; i <= Radius; i++) {
+        ivec2 q = coord + ivec2(i, j);
+        if (q.x >= bound.x || q.y >= bound.y || q.x < 0 || q.y < 0) continue;
+        vec3 normQ, posQ; uint matHashQ;
+        if (indirectMode) loadThisGeometry(q * 2, normQ, posQ, matHashQ, indSize());
+        else loadThisGeometry(q, normQ, posQ, matHashQ, size());
+        vec3 colorQ = loadImg(inImage, q).xyz();
+        if (matHash != matHashQ || matHashQ == InvalidMatId) continue;
+        float var = sigLumin;
+        float distColor = dot(color - colorQ, color - colorQ);
+        float wColor = eid_expf(-distColor / var) + 1e-2f;
+        float distNorm2 = dot(norm - normQ, norm - normQ);
+        float wNorm = gmin(1.0f, eid_expf(-distNorm2 / sigNormal));
+        float distPos2 = dot(pos - posQ, pos - posQ);
+        float wDepth = eid_expf(-distPos2 / sigDepth) + 1e-2f;
+        float weight = wColor * wNorm * wDepth;
+        if (!indirectMode) {
+          float dist2 = float(i * i + j * j);
+          float wDist = eid_expf(-dist2 / 10.0f) + 1e-2f;
+          weight = weight * wDist;
+        }
+        sum += colorQ * weight;
+        sumWeight += weight;
+      }
+    }
+    vec3 res = (sumWeight < 1e-5f) ? vec3(0.0f) : sum / sumWeight;
+    if (hasNan(res) || res.x < 0 || res.y < 0 || res.z < 0 || res.x > 1e8f || res.y > 1e8f || res.z > 1e8f) res = vec3(0.0f);
+    return res;
+  }
   void denoiseDirectMain(int gx, int gy) {                                                       // denoise_direct.comp:139-173
     ivec2 coord(gx, gy);
     if (!inBound(coord, size())) return;
@@ -1057,6 +1122,12 @@ struct Ctx {
     loadThisGeometry(coord, norm, pos, matHash, size());
     const float sl = rtxState.sigLuminDirect, sn = rtxState.sigNormalDirect, sd = rtxState.sigDepthDirect;
     auto& A = rr.denoiseTemp[0]; auto& B = rr.denoiseTemp[1];
+    if (rr.variant & EID_VARIANT_DIRECT_BILATERAL) {
+      vec3 res = bilateralFilter(A, coord, norm, pos, matHash, sl, sn, sd, false);
+      res = LDRToHDR(res);
+      storeImg(rr.directResult, coord, vec4(res, 1.0f));
+      return;
+    }
     if (rtxState.denoiseLevel == 0) storeImg(A, coord, vec4(waveletFilter(rr.directResult, coord, norm, pos, matHash, sl, sn, sd, 0, false), 1.0f));
     else if (rtxState.denoiseLevel == 1) storeImg(B, coord, vec4(waveletFilter(A, coord, norm, pos, matHash, sl, sn, sd, 1, false), 1.0f));
     else if (rtxState.denoiseLevel == 2) storeImg(A, coord, vec4(waveletFilter(B, coord, norm, pos, matHash, sl, sn, sd, 2, false), 1.0f));
@@ -1073,6 +1144,12 @@ struct Ctx {
     loadThisGeometry(coord * 2, norm, pos, matHash, indSize());
     const float sl = rtxState.sigLuminIndirect, sn = rtxState.sigNormalIndirect, sd = rtxState.sigDepthIndirect;
     auto& A = rr.denoiseTemp[2]; auto& B = rr.denoiseTemp[3];
+    if (rr.variant & EID_VARIANT_INDIRECT_BILATERAL) {
+      vec3 res = bilateralFilter(A, coord, norm, pos, matHash, sl, sn, sd, true);
+      res = LDRToHDR(res);
+      storeImg(B, coord, vec4(res, 1.0f));
+      return;
+    }
     if (rtxState.denoiseLevel == 0) storeImg(B, coord, vec4(waveletFilter(A, coord, norm, pos, matHash, sl, sn, sd, 0, true), 1.0f));
     else if (rtxState.denoiseLevel == 1) storeImg(A, coord, vec4(waveletFilter(B, coord, norm, pos, matHash, sl, sn, sd, 1, true), 1.0f));
     else if (rtxState.denoiseLevel == 2) storeImg(rr.indirectResult, coord, vec4(waveletFilter(A, coord, norm, pos, matHash, sl, sn, sd, 2, true), 1.0f));
@@ -1158,7 +1235,9 @@ void Renderer::runPost(const RtxState& st, int frames) {
   int set = (frames + 1) % 2;
   RtxState cState = st;
   double t0 = nowMs();
-  if (st.denoise > 0) {
+  if (st.denoise > 0 && (variant & EID_VARIANT_DIRECT_BILATERAL)) {   // #if DENOISER_DIRECT_BILATERAL: one dispatch, the caller's push constants (renderer.cpp:186-188)
+    dispatch(st.size.x, st.size.y, 0, st.size.y, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.denoiseDirectMain(x, y); });
+  } else if (st.denoise > 0) {
     for (int i = 0; i < 4; i++) {   // renderer.cpp:178-189
       cState.denoiseLevel = i;
       dispatch(st.size.x, st.size.y, 0, st.size.y, [&](int x, int y) { Ctx c(*scene, *this, cState, set); c.denoiseDirectMain(x, y); });
@@ -1166,7 +1245,9 @@ void Renderer::runPost(const RtxState& st, int frames) {
   }
   double t1 = nowMs();
   kernelMs[2] += t1 - t0;
-  if (st.denoise > 0) {
+  if (st.denoise > 0 && (variant & EID_VARIANT_INDIRECT_BILATERAL)) {
+    dispatch(st.size.x / 2, st.size.y / 2, 0, st.size.y / 2, [&](int x, int y) { Ctx c(*scene, *this, cState, set); c.denoiseIndirectMain(x, y); });
+  } else if (st.denoise > 0) {
     for (int i = 0; i < 5; i++) {   // renderer.cpp:191-202
       cState.denoiseLevel = i;
       dispatch(st.size.x / 2, st.size.y / 2, 0, st.size.y / 2, [&](int x, int y) { Ctx c(*scene, *this, cState, set); c.denoiseIndirectMain(x, y); });

@@ -11,6 +11,21 @@
 #include <cstring>
 #include "glsl/glsl_builtins.h"
 #include "host_device.h"          // /root/reference/shaders/host_device.h (C++ branch)
+// REF_VARIANT: a second build with DENOISER_DIRECT_BILATERAL / DENOISER_INDIRECT_BILATERAL = 1 (host_device.h:28-29): the bilateralFilter
+// branches of denoise_direct.comp / denoise_indirect.comp and the one-dispatch schedule of renderer.cpp:186-188, 199-201; exported with
+// the suffix _variant.  `which` of ref_post_run_variant: bit 0 = the direct stage is the bilateral build, bit 1 = the indirect one
+// (the other stage then runs its A-Trous levels from the regular build's schedule — see the wrapper at the end of this file).
+#ifdef REF_VARIANT
+#undef DENOISER_DIRECT_BILATERAL
+#undef DENOISER_INDIRECT_BILATERAL
+#define DENOISER_DIRECT_BILATERAL 1
+#define DENOISER_INDIRECT_BILATERAL 1
+#define refpost refpost_v
+#define refpost_compress refpost_compress_v
+#define ref_post_run ref_post_run_variant_all
+#define ref_post_dispatch ref_post_dispatch_variant
+#define shared static
+#endif
 namespace refpost_compress {      // (its non-inline functions also exist in ref_wrap.cpp's translation unit)
 #include "compress.glsl"          // /root/reference/shaders/compress.glsl: decompress_unit_vec as the shaders see it
 }
@@ -36,7 +51,7 @@ static uimage2D thisGbuffer;
 static image2D thisDirectResultImage, thisIndirectResultImage, denoiseDirTempA, denoiseDirTempB, denoiseIndTempA, denoiseIndTempB;
 static RtxState rtxState;
 static SceneCamera sceneCamera;
-static GlobalId gl_GlobalInvocationID;
+static GlobalId gl_GlobalInvocationID, gl_LocalInvocationID;
 
 #include "../_ref/gen/globals.hpp"
 #include "../_ref/gen/common_post.hpp"
@@ -57,7 +72,7 @@ template <class F>
 static void dispatch(int w, int h, F&& mainFn) {   // vkCmdDispatch(CEIL_DIV(w, 8), CEIL_DIV(h, 8), 1) of 8x8 groups
   const int gw = (w + 7) / 8 * 8, gh = (h + 7) / 8 * 8;
   for (int y = 0; y < gh; ++y)
-    for (int x = 0; x < gw; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; mainFn(); }
+    for (int x = 0; x < gw; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; gl_LocalInvocationID = GlobalId{(unsigned)(x & 7), (unsigned)(y & 7), 0u}; mainFn(); }
 }
 }  // namespace refpost
 
@@ -74,10 +89,15 @@ void ref_post_run(const RtxState* st, const SceneCamera* cam, int allocW, int al
   sceneCamera = *cam;
   rtxState = *st;
   const int W = st->size.x, H = st->size.y;
+#ifdef REF_VARIANT
+  if (st->denoise > 0) dispatch(W, H, [] { dd::main(); });            // renderer.cpp:186-188: ONE dispatch, the caller's push constants
+  if (st->denoise > 0) dispatch(W / 2, H / 2, [] { di::main(); });    // renderer.cpp:199-201
+#else
   if (st->denoise > 0)
     for (int i = 0; i < 4; ++i) { rtxState.denoiseLevel = i; dispatch(W, H, [] { dd::main(); }); }
   if (st->denoise > 0)
     for (int i = 0; i < 5; ++i) { rtxState.denoiseLevel = i; dispatch(W / 2, H / 2, [] { di::main(); }); }
+#endif
   rtxState = *st;
   dispatch(W, H, [] { cp::main(); });
 }
@@ -96,6 +116,6 @@ int ref_post_dispatch(int stage, const RtxState* st, const SceneCamera* cam, int
   void (*fn)() = stage == 5 ? (void (*)())[] { dd::main(); } : stage == 6 ? (void (*)())[] { di::main(); } : stage == 7 ? (void (*)())[] { cp::main(); } : nullptr;
   if (!fn) return -1;
   for (int y = 0; y < gy * 8; ++y)
-    for (int x = 0; x < gx * 8; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; fn(); }
+    for (int x = 0; x < gx * 8; ++x) { gl_GlobalInvocationID = GlobalId{(unsigned)x, (unsigned)y, 0u}; gl_LocalInvocationID = GlobalId{(unsigned)(x & 7), (unsigned)(y & 7), 0u}; fn(); }
   return 0;
 }

@@ -17,6 +17,17 @@
 #include <cstring>
 #include "glsl/glsl_builtins.h"
 #include "host_device.h"          // /root/reference/shaders/host_device.h (C++ branch)
+// REF_VARIANT: a second build of this file with the reference's compile-time switches flipped (Makefile: ref_trace_v.o) — DENOISER_DIRECT_BILATERAL
+// (direct_stage.comp:284-288 stores to denoiseDirTempA) and FETCH_GEOM_CHECK_4_SUBPIXELS (indirect_stage_4sp.hpp = indirect_stage.comp without its
+// own `#define FETCH_GEOM_CHECK_4_SUBPIXELS 0`, the macro is 1 on the command line).  Own namespaces, exported as ref_trace_run_variant.
+#ifdef REF_VARIANT
+#undef DENOISER_DIRECT_BILATERAL
+#define DENOISER_DIRECT_BILATERAL 1
+#define reftrace reftrace_v
+#define reftrace_compress reftrace_compress_v
+#define ref_trace_run ref_trace_run_variant
+#define RefTraceBind RefTraceBindV
+#endif
 namespace reftrace_compress {
 #include "compress.glsl"          // /root/reference/shaders/compress.glsl
 }
@@ -106,7 +117,11 @@ namespace reftrace { namespace k1 {
 namespace reftrace { namespace k2 {
 #include "../_ref/gen/globals.hpp"
 #include "ref_trace_stage.inl"
+#ifdef REF_VARIANT
+#include "../_ref/gen/indirect_stage_4sp.hpp"
+#else
 #include "../_ref/gen/indirect_stage.hpp"
+#endif
 } }
 
 using namespace reftrace;
@@ -119,6 +134,7 @@ struct RefTraceBind {   // everything ref_trace_bind needs, as one C struct (fil
   void *thisG, *lastG, *motion, *thisDR, *lastDR, *thisIR, *lastIR, *direct, *indirect, *indA;
   const float* instanceXforms;
   void* tempDR;      // tempDirectResv (one buffer for both descriptor sets, renderer.cpp:235, 349); persists across frames
+  void* dirA;        // denoiseDirTempA: what direct_stage stores to with DENOISER_DIRECT_BILATERAL (null = not bound)
 };
 
 template <class F>
@@ -145,6 +161,7 @@ void ref_trace_run(const RefTraceBind* b, int runDirect, int runIndirect, unsign
   thisGbuffer = uimage2D{(uvec4*)b->thisG, b->allocW, b->allocH, b->allocW}; lastGbuffer = uimage2D{(uvec4*)b->lastG, b->allocW, b->allocH, b->allocW};
   motionVector = iimage2D{(int16_t*)b->motion, b->allocW, b->allocH, b->allocW};
   thisDirectResultImage = img(b->direct); thisIndirectResultImage = img(b->indirect); denoiseIndTempA = img(b->indA);
+  if (b->dirA) denoiseDirTempA = img(b->dirA);
   thisDirectResv = (DirectReservoir*)b->thisDR; lastDirectResv = (DirectReservoir*)b->lastDR;
   thisIndirectResv = (IndirectReservoir*)b->thisIR; lastIndirectResv = (IndirectReservoir*)b->lastIR;
   const int W = rtxState.size.x, H = rtxState.size.y;

@@ -181,6 +181,60 @@ def ref_trace_vectors():
     print("wrote ref_trace.npz")
 
 
+def variant_replay(R, abi, scenes, cfgv, check=True):
+    """One VARIANT_CONFIGS entry: every frame is rendered by the oracle (variant switched on) AND by the reference's own shader text from the
+    variant builds (trace stages, then the post schedule) on its own buffers; returns the reference's buffers after the last frame.  With
+    `check`, every buffer of every frame must agree between the two."""
+    tag, maker_name, size, frames, variant, over = cfgv
+    arrays, osc, orr, env, ss, over = ol.trace_setup(scenes, abi, common, (tag, maker_name, size, frames, "none", over))   # (black constant environment)
+    orr.set_variant(variant)
+    rt = ol.RefTracer(R, abi, arrays, osc, size, variant=variant)
+    osc.update_camera(*size)
+    info = osc.info()
+    w, h = size
+    ref = {}
+    dirB, indB = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    for f in range(frames):
+        osc.update_camera(*size)
+        st = common.frame_state(w, h, info, f, **over)
+        orr.run(st, f)
+        got = rt.run(st, f)
+        pre = {"BUF_THIS_GBUFFER": got["gbuffer"], "BUF_DIRECT": rt.direct, "BUF_INDIRECT": rt.indirect, "BUF_DENOISE_DIR_A": rt.dirA,
+               "BUF_DENOISE_DIR_B": dirB, "BUF_DENOISE_IND_A": rt.indA, "BUF_DENOISE_IND_B": indB}
+        post = ol.ref_post_run_variant(R, abi, osc.table(abi.TABLE_CAMERA), st, size, pre, variant)
+        rt.direct[...] = post["BUF_DIRECT"].reshape(rt.direct.shape); rt.indirect[...] = post["BUF_INDIRECT"].reshape(rt.indirect.shape)
+        rt.dirA[...] = post["BUF_DENOISE_DIR_A"].reshape(rt.dirA.shape); rt.indA[...] = post["BUF_DENOISE_IND_A"].reshape(rt.indA.shape)
+        dirB[...] = post["BUF_DENOISE_DIR_B"].reshape(dirB.shape); indB[...] = post["BUF_DENOISE_IND_B"].reshape(indB.shape)
+        ref = {"BUF_THIS_GBUFFER": got["gbuffer"], "BUF_MOTION": got["motion"], "BUF_THIS_DIRECT_RESV": got["direct_resv"],
+               "BUF_THIS_INDIRECT_RESV": got["indirect_resv"], "BUF_DIRECT": rt.direct, "BUF_INDIRECT": rt.indirect, "BUF_DENOISE_DIR_A": rt.dirA,
+               "BUF_DENOISE_IND_A": rt.indA, "BUF_DENOISE_IND_B": indB}
+        if check:
+            for k, v in ref.items():
+                a = np.ascontiguousarray(v).view(np.uint8).reshape(-1)
+                b = np.ascontiguousarray(orr.read(getattr(abi, k))).view(np.uint8).reshape(-1)
+                assert a.tobytes() == b.tobytes(), "variant %s frame %d: %s differs between the reference text and the oracle" % (tag, f, k)
+            s = orr.stats()
+            assert [s.closestHitRays, s.anyHitRays] == [int(v) for v in rt.rays], (tag, f)
+    return {k: np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy() for k, v in ref.items()}
+
+
+def ref_variant_vectors():
+    """tests/golden/ref_variants.npz: the reference's compile-time variants (bilateral denoisers, FETCH_GEOM_CHECK_4_SUBPIXELS) run from the
+    variant builds of its own shader text (oracle/_ref, -DREF_VARIANT): every buffer after the last frame of each VARIANT_CONFIGS entry."""
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    R = ol.ref()
+    if R is None:
+        print("oracle/_ref/libref.so unavailable: keeping the committed ref_variants.npz")
+        return
+    out = {}
+    for c in fi.VARIANT_CONFIGS:
+        for k, v in variant_replay(R, abi, scenes, c).items():
+            out["%s_%s" % (c[0], k)] = v
+    np.savez_compressed(os.path.join(HERE, "ref_variants.npz"), **out)
+    print("wrote ref_variants.npz")
+
+
 def ref_display_vectors():
     """tests/golden/ref_display.npz: what the reference's post.frag (main() included, compiled as C++ by oracle/ref_shim/ref_display.cpp)
     makes of the oracle's result images for every tests/ref_fn_inputs.DISPLAY_CONFIGS entry, plus the two 1x1 mip texels it was handed."""
@@ -251,4 +305,5 @@ if __name__ == "__main__":
     ref_vectors()
     ref_post_vectors()
     ref_trace_vectors()
+    ref_variant_vectors()
     frame_dumps()

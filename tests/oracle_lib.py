@@ -54,7 +54,7 @@ def lib():
             "orc_renderer_create": (vp, [vp, u32, u32]), "orc_renderer_destroy": (None, [vp]),
             "orc_renderer_set_env_constant": (i32, [vp, fp]),
             "orc_fn": (i32, [i32, vp, i32, vp]), "orc_ctx_fn": (i32, [vp, vp, i32, vp, i32, vp]),
-            "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_renderer_run_output": (i32, [vp, vp, vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
+            "orc_renderer_set_sun_and_sky": (i32, [vp, vp]), "orc_renderer_set_variant": (i32, [vp, i32]), "orc_renderer_run_output": (i32, [vp, vp, vp, vp]), "orc_sun_and_sky": (None, [vp, vp, i32, vp]),
             "orc_renderer_run": (i32, [vp, C.POINTER(abi.RtxState), i32]),
             "orc_renderer_run_trace": (i32, [vp, C.POINTER(abi.RtxState), i32, i32, i32]),
             "orc_renderer_run_post": (i32, [vp, C.POINTER(abi.RtxState), i32]),
@@ -89,6 +89,8 @@ def ref():
         L.ref_fn.restype, L.ref_fn.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_sun_and_sky.restype, L.ref_sun_and_sky.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_trace_run.restype, L.ref_trace_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_trace_run_variant.restype, L.ref_trace_run_variant.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_post_dispatch_variant.restype, L.ref_post_dispatch_variant.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 7
         L.ref_post_run.restype, L.ref_post_run.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.ref_post_dispatch.restype, L.ref_post_dispatch.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 7
         L.ref_display_run.restype, L.ref_display_run.argtypes = None, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
@@ -307,7 +309,7 @@ class RefTraceBind(C.Structure):      # oracle/ref_shim/ref_trace.cpp
     _fields_ = [(n, C.c_void_p) for n in ("state", "camera", "sunSky", "lightInfo", "geoInfo", "materials", "trigLights", "puncLights", "envAccel",
                                           "envSamplerFn", "env")] + [("envW", C.c_uint32), ("envH", C.c_uint32), ("traceFn", C.c_void_p), ("scene", C.c_void_p),
                                                                      ("allocW", C.c_int32), ("allocH", C.c_int32)] + [
-        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA", "instanceXforms", "tempDR")]
+        (n, C.c_void_p) for n in ("thisG", "lastG", "motion", "thisDR", "lastDR", "thisIR", "lastIR", "direct", "indirect", "indA", "instanceXforms", "tempDR", "dirA")]
 
 
 class RefTracer:
@@ -315,8 +317,9 @@ class RefTracer:
     tables of an oracle scene, with the oracle's intersector standing in for the driver's ray queries.  Buffers ping-pong like
     Renderer::run (frame f uses descriptor set (f+1)%2: last* = [set], this* = [!set])."""
 
-    def __init__(self, R, abi, arrays, osc, size, env=None, sun_sky=None):
+    def __init__(self, R, abi, arrays, osc, size, env=None, sun_sky=None, variant=0):
         self.R, self.abi, self.osc, self.size, self.env = R, abi, osc, size, env
+        self.variant = variant      # abi.VARIANT_* bits: the stage whose compile-time switch is flipped runs from the variant build (ref_trace_run_variant)
         w, h = size
         self.tabs = {k: np.ascontiguousarray(osc.table(getattr(abi, k))) for k in ("TABLE_MATERIALS", "TABLE_TRIG_LIGHTS", "TABLE_PUNC_LIGHTS", "TABLE_LIGHT_INFO")}
         # one vertex / index buffer per prim mesh (scene.cpp:209-289), addressed through InstanceData like the shaders do
@@ -337,7 +340,7 @@ class RefTracer:
         self.IR = [np.zeros((w // 2) * (h // 2), abi.INDIRECT_RESV_DT) for _ in range(2)]
         self.tempDR = np.zeros(w * h, abi.DIRECT_RESV_DT)      # tempDirectResv: one buffer, persists across frames (renderer.cpp:235)
         self.motion = np.zeros((h, w, 2), np.int16)
-        self.direct, self.indirect, self.indA = (np.zeros((h, w, 4), np.float32) for _ in range(3))
+        self.direct, self.indirect, self.indA, self.dirA = (np.zeros((h, w, 4), np.float32) for _ in range(4))
         self.rays = np.zeros(2, np.uint64)
 
     def run(self, st, frame, direct=True, indirect=True, bufs=None):
@@ -359,12 +362,22 @@ class RefTracer:
         b.direct, b.indirect, b.indA = self.direct.ctypes.data, self.indirect.ctypes.data, self.indA.ctypes.data
         b.instanceXforms = self.xforms.ctypes.data
         b.tempDR = self.tempDR.ctypes.data
+        b.dirA = self.dirA.ctypes.data
         if bufs is not None:
             for k in ("thisG", "lastG", "motion", "thisDR", "lastDR", "tempDR", "thisIR", "lastIR", "direct", "indirect", "indA"):
                 setattr(b, k, bufs[k].ctypes.data)
-        self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
+        if not self.variant:
+            self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
+        else:       # per stage: the regular build, or the one with DENOISER_DIRECT_BILATERAL (direct) / FETCH_GEOM_CHECK_4_SUBPIXELS (indirect) flipped
+            total = np.zeros(2, np.uint64)
+            for want, is_direct, bit in ((direct, True, 1), (indirect, False, 4)):
+                if want:
+                    fn = self.R.ref_trace_run_variant if (self.variant & bit) else self.R.ref_trace_run
+                    fn(C.byref(b), int(is_direct), int(not is_direct), self.rays.ctypes.data)
+                    total += self.rays
+            self.rays[:] = total
         return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
-                "direct": self.direct, "ind_tmp_a": self.indA}
+                "direct": self.direct, "ind_tmp_a": self.indA, "dir_tmp_a": self.dirA}
 
 
 def trace_setup(scenes, abi, common, cfg):
@@ -403,6 +416,36 @@ def ref_post_run(R, abi, camera_table, state, size, pre):
     bufs = {k: np.ascontiguousarray(pre[k].copy()) for k in POST_BUFS}
     cam = np.ascontiguousarray(camera_table)
     R.ref_post_run(C.addressof(state), cam.ctypes.data, size[0], size[1], *[bufs[k].ctypes.data for k in POST_BUFS])
+    return bufs
+
+
+def ref_post_run_variant(R, abi, camera_table, state, size, pre, variant):
+    """Renderer::run's post schedule (renderer.cpp:178-205) with the bilateral switches of `variant` (abi.VARIANT_* bits): a stage whose
+    switch is set runs ONCE from the variant build of the reference's shader text (oracle/ref_shim/ref_post.cpp, -DREF_VARIANT), the other
+    runs its A-Trous levels from the regular build; compose follows.  pre / result: dicts keyed by POST_BUFS."""
+    import copy
+    bufs = {k: np.ascontiguousarray(pre[k].copy()) for k in POST_BUFS}
+    cam = np.ascontiguousarray(camera_table)
+    w, h = size
+    ptrs = [bufs[k].ctypes.data for k in POST_BUFS]
+    sw, sh = state.size.x, state.size.y
+
+    def disp(fn, stage, st, gw, gh):
+        assert fn(stage, C.addressof(st), cam.ctypes.data, w, h, (gw + 7) // 8, (gh + 7) // 8, *ptrs) == 0
+    if state.denoise > 0:
+        if variant & 1:
+            disp(R.ref_post_dispatch_variant, 5, state, sw, sh)
+        else:
+            for i in range(4):
+                st = copy.copy(state); st.denoiseLevel = i
+                disp(R.ref_post_dispatch, 5, st, sw, sh)
+        if variant & 2:
+            disp(R.ref_post_dispatch_variant, 6, state, sw // 2, sh // 2)
+        else:
+            for i in range(5):
+                st = copy.copy(state); st.denoiseLevel = i
+                disp(R.ref_post_dispatch, 6, st, sw // 2, sh // 2)
+    disp(R.ref_post_dispatch, 7, state, sw, sh)
     return bufs
 
 
@@ -537,6 +580,9 @@ class OracleRenderer:
 
     def set_sun_and_sky(self, ss):
         lib().orc_renderer_set_sun_and_sky(self._h, C.byref(ss))
+
+    def set_variant(self, flags):
+        lib().orc_renderer_set_variant(self._h, int(flags))
 
     def run_output(self, tm, state):
         out = np.zeros((self.size[1], self.size[0], 4), np.float32)

@@ -139,6 +139,15 @@ TRACE_CONFIGS = [("cornell", "cornell_scene", (64, 40), 3, "none", dict(maxDepth
                  ("alpha", "alpha_scene", (64, 40), 2, "none", dict(maxDepth=3)),
                  ("spatial", "cornell_scene", (64, 40), 2, "none", dict(ReSTIRState=2, maxDepth=2)),            # eSpatial (race-free reading)
                  ("spatiotemporal", "small_room", (50, 34), 3, "none", dict(ReSTIRState=4, maxDepth=2))]      # eSpatiotemporal
+# the reference's compile-time variants (eid_renderer_set_variant; abi.VARIANT_* bits): (tag, scene maker, size, frames, variant bits, RtxState overrides)
+VARIANT_CONFIGS = [("bil_direct", "cornell_scene", (48, 32), 2, 1, dict(maxDepth=2)),
+                   ("bil_indirect", "small_room", (48, 32), 2, 2, dict(maxDepth=3)),
+                   ("sub4", "small_room", (50, 34), 3, 4, dict(maxDepth=3)),
+                   ("sub4_cube_sky", "cube_scene", (40, 24), 2, 4, dict(maxDepth=2)),
+                   ("all_three", "cornell_scene", (40, 24), 2, 7, dict(maxDepth=3)),
+                   ("bil_nodenoise", "cornell_scene", (32, 24), 2, 3, dict(maxDepth=2, denoise=0))]
+VARIANT_KEYS = ("BUF_THIS_GBUFFER", "BUF_MOTION", "BUF_THIS_DIRECT_RESV", "BUF_THIS_INDIRECT_RESV", "BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_DIR_A",
+                "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B")
 # host tables (src/scene.cpp run on an injected scene): scene makers, and the camera sequence (size, optional new look-at) after loading
 SCENE_TABLE_MAKERS = ["cube_scene", "cornell_scene", "small_room", "textured_scene", "instanced_scene", "alpha_scene"]
 SCENE_CAMERA_STEPS = [((640, 360), None), ((640, 360), None), ((333, 200), ((1.5, 2.5, -4.0), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0), 47.0))]

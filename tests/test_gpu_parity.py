@@ -981,3 +981,54 @@ def test_frames_in_flight_are_bit_identical(restir):
     want, got = common.snapshot(strict), common.snapshot(piped)
     for k in want:
         assert got[k].tobytes() == want[k].tobytes(), "mixed strict / pipelined entry points: %s differs" % k
+
+
+@pytest.mark.parametrize("variant", [abi.VARIANT_DIRECT_BILATERAL, abi.VARIANT_INDIRECT_BILATERAL, abi.VARIANT_FETCH_4_SUBPIXELS,
+                                     abi.VARIANT_DIRECT_BILATERAL | abi.VARIANT_INDIRECT_BILATERAL | abi.VARIANT_FETCH_4_SUBPIXELS])
+@pytest.mark.parametrize("wavefront", [True, False])
+def test_reference_compile_time_variants(variant, wavefront):
+    """Scope row (f.4): the reference's dormant compile-time variants as run-time switches (eid_renderer_set_variant) — the bilateral
+    denoisers (DENOISER_DIRECT_BILATERAL: direct_stage.comp:284-288, denoise_direct.comp:73-137, renderer.cpp:186-188;
+    DENOISER_INDIRECT_BILATERAL: denoise_indirect.comp:77-130) and FETCH_GEOM_CHECK_4_SUBPIXELS (pathtrace.glsl:314-358, one more RNG
+    draw per quarter-res pixel) — bit-identical to the oracle with strict math, both K2 forms, moving camera, sky pixels included."""
+    for maker, size, kw in ((scenes.small_room, (200, 120), dict(orbit=True)), (scenes.cube_scene, (96, 64), dict()), (scenes.cornell_scene, (130, 70), dict(denoise=0))):
+        arrays = maker()
+        osc, orr, psc, acc, prr = common.make_pair(arrays, size)
+        prr.set_wavefront(wavefront)
+        orr.set_variant(variant); prr.set_variant(variant)
+        for s in (osc, psc):
+            s.update_camera(*size)
+        info = psc.info()
+        cam = arrays.camera
+        over = {k: v for k, v in kw.items() if k != "orbit"}
+        for f in range(3):
+            if kw.get("orbit"):
+                a = np.deg2rad(0.7 * f)
+                e = np.array(cam["eye"], np.float64)
+                for s in (osc, psc):
+                    s.set_lookat((e[0] * np.cos(a) - e[2] * np.sin(a), e[1], e[0] * np.sin(a) + e[2] * np.cos(a)), cam["center"], cam["up"], np.rad2deg(cam["yfov"]))
+            for s in (osc, psc):
+                s.update_camera(*size)
+            st = common.frame_state(size[0], size[1], info, f, maxDepth=3, **over)
+            orr.run(st, f); prr.run(st, f); prr.sync()
+            got, want = common.snapshot(prr), common.snapshot(orr)
+            rep = common.compare_snapshots(got, want, "variant %d %s frame %d" % (variant, maker.__name__, f))
+            assert all(v == 0.0 for v in rep.values()), rep
+            assert prr.read(abi.BUF_DENOISE_DIR_A).tobytes() == orr.read(abi.BUF_DENOISE_DIR_A).tobytes()
+            so, sp = orr.stats(), prr.stats()
+            assert (so.closestHitRays, so.anyHitRays) == (sp.closestHitRays, sp.anyHitRays)
+    # default numerics: within the 1e-3 contract
+    arrays = scenes.small_room()
+    osc, orr, psc, acc, prr = common.make_pair(arrays, (200, 120), strict=False)
+    orr.set_variant(variant); prr.set_variant(variant)
+    for s in (osc, psc):
+        s.update_camera(200, 120)
+    for f in range(2):
+        for s in (osc, psc):
+            s.update_camera(200, 120)
+        st = common.frame_state(200, 120, psc.info(), f, maxDepth=3)
+        orr.run(st, f); prr.run(st, f); prr.sync()
+        rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "variant %d fast frame %d" % (variant, f))
+        assert max(rep.values()) <= 1e-3
+    with pytest.raises(eid.EidolaError):
+        prr.set_variant(8)

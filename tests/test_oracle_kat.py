@@ -200,6 +200,35 @@ def test_trace_stages_match_reference_shader_mains():
         assert [s.closestHitRays, s.anyHitRays] == [int(v) for v in z["%s_rays" % tag]], tag
 
 
+def test_compile_time_variants_match_reference_shader_text():
+    """The reference's dormant compile-time variants — DENOISER_DIRECT_BILATERAL (direct_stage.comp:284-288, denoise_direct.comp:73-137,
+    renderer.cpp:186-188), DENOISER_INDIRECT_BILATERAL (denoise_indirect.comp:77-130) and FETCH_GEOM_CHECK_4_SUBPIXELS (pathtrace.glsl:314-358)
+    — compiled from the reference's OWN shader text with the switches flipped (oracle/ref_shim, -DREF_VARIANT) and replayed frame by frame:
+    the oracle with the same variant bits leaves exactly those buffers (committed: tests/golden/ref_variants.npz; live where /root/reference exists)."""
+    import common
+    import ref_fn_inputs as fi
+    from eidola_b200 import abi, scenes
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_variants.npz"))
+    for c in fi.VARIANT_CONFIGS:
+        tag, maker_name, size, frames, variant, over = c
+        arrays, osc, orr, env, ss, over = ol.trace_setup(scenes, abi, common, (tag, maker_name, size, frames, "none", over))
+        orr.set_variant(variant)
+        info = osc.info()
+        for f in range(frames):
+            osc.update_camera(*size)
+            orr.run(common.frame_state(size[0], size[1], info, f, **over), f)
+        for k in fi.VARIANT_KEYS:
+            got = np.ascontiguousarray(orr.read(getattr(abi, k))).view(np.uint8).reshape(-1)
+            assert got.tobytes() == z["%s_%s" % (tag, k)].tobytes(), (tag, k)
+    R = ol.ref()
+    if R is not None:      # live: every buffer of EVERY frame, reference text vs oracle, and the committed vectors are what it produces
+        sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+        import make_golden as mg
+        for c in fi.VARIANT_CONFIGS:
+            for k, v in mg.variant_replay(R, abi, scenes, c, check=True).items():
+                assert v.tobytes() == z["%s_%s" % (c[0], k)].tobytes(), (c[0], k)
+
+
 def test_oracle_display_pass_matches_reference_post_frag():
     """The oracle's restatement of RenderOutput::run / post.frag against the committed output of the reference's OWN post.frag (main()
     included, compiled as C++ by oracle/ref_shim/ref_display.cpp): every view and tonemapper of DISPLAY_CONFIGS, auto exposure included,
