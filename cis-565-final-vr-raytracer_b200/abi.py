@@ -174,7 +174,7 @@ class FrameStats(C.Structure):
                 ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64)]
 
 
-VARIANT_DIRECT_BILATERAL, VARIANT_INDIRECT_BILATERAL, VARIANT_FETCH_4_SUBPIXELS = 1, 2, 4     # eid_renderer_set_variant
+VARIANT_DIRECT_BILATERAL, VARIANT_INDIRECT_BILATERAL, VARIANT_FETCH_4_SUBPIXELS, VARIANT_DIRECT_SPLIT = 1, 2, 4, 8     # eid_renderer_set_variant
 
 
 class GroupInfo(C.Structure):   # eid_group_info

@@ -16,6 +16,13 @@ void launchDirectStage(const FrameParams& P, dim3 g, cudaStream_t st, bool stats
   else { if (tex) directVariant<false, true>(P, g, st, spatial, halo); else directVariant<false, false>(P, g, st, spatial, halo); }
 }
 
+void launchDirectSplit(const FrameParams& P, dim3 g, cudaStream_t st, bool stats, bool tex) {
+  const dim3 b(8, 8);
+  if (stats) { if (tex) k_direct_gen<true, true><<<g, b, 0, st>>>(P); else k_direct_gen<true, false><<<g, b, 0, st>>>(P); }
+  else { if (tex) k_direct_gen<false, true><<<g, b, 0, st>>>(P); else k_direct_gen<false, false><<<g, b, 0, st>>>(P); }
+  k_direct_reuse<<<g, b, 0, st>>>(P);
+}
+
 void launchDirectSpatial(const FrameParams& P, dim3 g, cudaStream_t st) { k_direct_spatial<<<g, dim3(8, 8), 0, st>>>(P); }
 
 }  // namespace eid

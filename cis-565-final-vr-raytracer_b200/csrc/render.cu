@@ -147,7 +147,10 @@ void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
     const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
     const bool spatial = P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal;
-    if (!spatial) {
+    if (P.variant & EID_VARIANT_DIRECT_SPLIT) {
+      launchDirectSplit(P, g, st, r->countVisits, tex);
+      r->stats.kernelLaunches[EID_K_DIRECT] += 2;
+    } else if (!spatial) {
       launchDirectStage(P, g, st, r->countVisits, tex, false, 0);
       r->stats.kernelLaunches[EID_K_DIRECT]++;
     } else {
@@ -996,7 +999,7 @@ int eid_renderer_set_wavefront(eid_renderer* r, int enabled, int traceBlocks) {
 int eid_renderer_set_variant(eid_renderer* r, int flags) {
   EID_TRY
   if (!r) raise(EID_ERR_INVALID, "eid_renderer_set_variant: null renderer");
-  if (flags & ~(EID_VARIANT_DIRECT_BILATERAL | EID_VARIANT_INDIRECT_BILATERAL | EID_VARIANT_FETCH_4_SUBPIXELS)) raise(EID_ERR_INVALID, "eid_renderer_set_variant: unknown variant bits 0x%x", flags);
+  if (flags & ~(EID_VARIANT_DIRECT_BILATERAL | EID_VARIANT_INDIRECT_BILATERAL | EID_VARIANT_FETCH_4_SUBPIXELS | EID_VARIANT_DIRECT_SPLIT)) raise(EID_ERR_INVALID, "eid_renderer_set_variant: unknown variant bits 0x%x", flags);
   r->variant = flags;
   return EID_OK;
   EID_CATCH

@@ -13,6 +13,19 @@ namespace eid {
 // 64 pixels of one row per block; such pixels write tempDirectResv, which the stripe's edge rows read, and keep their own G-buffer /
 // motion / reservoir history (the values the owning rank computes), so that their temporal reuse matches the owner's next frame; they
 // write no image and their rays are not counted.
+DEV f3 debugInfo(const State& st, int mode) {          // DebugInfo (pathtrace.glsl:362-380)
+  switch (mode) {
+    case eMetallic: return mk3(st.mat.metallic);
+    case eNormal: return (st.normal + mk3(1.0f)) * .5f;
+    case eDepth: return mk3(0.0f);
+    case eBaseColor: return st.mat.albedo;
+    case eEmissive: return st.mat.emission;
+    case eRoughness: return mk3(st.mat.roughness);
+    case eTexcoord: return mk3(st.u, st.v, 0.f);
+    default: return mk3(1000.f, 0.f, 0.f);
+  }
+}
+
 template <bool STATS, bool TEX, bool SPATIAL>
 __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const FrameParams P, const int halo) {
   int x = blockIdx.x * 8 + threadIdx.x, y;
@@ -57,17 +70,8 @@ __global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_stage(const Fr
       }
       P.thisG[pix] = encodeGeometryInfo(st, prd.hitT);
 
-      if (P.st.debugging_mode > eIndirectStage) {          // DebugInfo (pathtrace.glsl:362-380)
-        switch (P.st.debugging_mode) {
-          case eMetallic: radiance = mk3(st.mat.metallic); break;
-          case eNormal: radiance = (st.normal + mk3(1.0f)) * .5f; break;
-          case eDepth: radiance = mk3(0.0f); break;
-          case eBaseColor: radiance = st.mat.albedo; break;
-          case eEmissive: radiance = st.mat.emission; break;
-          case eRoughness: radiance = mk3(st.mat.roughness); break;
-          case eTexcoord: radiance = mk3(st.u, st.v, 0.f); break;
-          default: radiance = mk3(1000.f, 0.f, 0.f);
-        }
+      if (P.st.debugging_mode > eIndirectStage) {
+        radiance = debugInfo(st, P.st.debugging_mode);
       } else if (st.isEmitter) {
         radiance = st.mat.emission;                        // :172-174
       } else {
@@ -221,6 +225,116 @@ __global__ void __launch_bounds__(64) k_direct_spatial(const FrameParams P) {
   const f3 radiance = hdrToLdr(clampRadiance(emission + direct, P.st.fireflyClampThreshold));
   const f3 px = clampRadiance(radiance, P.st.fireflyClampThreshold);
   P.directOut[pix] = make_float4(px.x, px.y, px.z, 1.0f);
+}
+
+// =================================================================================================
+// EID_VARIANT_DIRECT_SPLIT — direct_gen.comp + direct_reuse.comp (the reference builds both pipelines, renderer.cpp:129-132, and never
+// dispatches them): the direct stage cut in two at the reservoir, reproduced as written.
+// =================================================================================================
+// updateGeometryAlbedo (direct_gen.comp:62-65)
+DEV void updateGeometryAlbedo(uint4& g, f3 albedo) { g.w = (packUnorm4(albedo.x, albedo.y, albedo.z, 1.0f) & 0x00ffffffu) | (g.w & 0xff000000u); }
+
+template <bool STATS, bool TEX>
+__global__ void __launch_bounds__(64, EID_K1_MIN_BLOCKS) k_direct_gen(const FrameParams P) {      // generateGeometryAndReservoir :77-137, main :139-149
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
+  RayCounters rc = {0, 0, 0, 0, 0};
+  const int W = P.st.size.x, H = P.st.size.y;
+  if (x < W && y < H) {
+    uint32_t seed = tea((uint32_t)W * (uint32_t)y + (uint32_t)x, P.st.time);
+    f3 ro, rd;
+    raySpawn<true>(P.cam, x, y, W, H, ro, rd);
+    const size_t pix = (size_t)y * P.pitch + x, index = (size_t)y * W + x;
+    DResv resv; resv.Li = mk3(0.f); resv.wi = mk3(0.f); resv.dist = 0.f; resv.num = 0; resv.weight = 0.f;
+    Payload prd;
+    const bool hit = closestHit<STATS, TEX>(P, ro, rd, prd, seed, rc);
+    if (!hit || prd.hitT >= __fmul_rn(EID_INFINITY, 0.8f)) {
+      uint4 g = make_uint4(__float_as_uint(EID_INFINITY), 0u, 0u, EID_INVALID_MAT);
+      updateGeometryAlbedo(g, envRadiance<TEX>(P, rd));
+      P.thisG[pix] = g;
+      P.motion[pix] = make_short2(0, 0);
+      storeDResv(P.thisDR, index, resv);
+    } else {
+      rc.primary++;
+      State st = getState<TEX>(P.sc, prd, rd);
+      getMaterials<TEX>(P.sc, st, rd);
+      float pr[4];
+      mat4MulV(P.cam.lastProjView, st.position.x, st.position.y, st.position.z, 1.0f, pr);
+      const float mvx = __fadd_rn(__fmul_rn(__fdiv_rn(pr[0], pr[3]), 0.5f), 0.5f), mvy = __fadd_rn(__fmul_rn(__fdiv_rn(pr[1], pr[3]), 0.5f), 0.5f);
+      const int mix_ = f2i_sat(__fmul_rn(mvx, (float)W)), miy = f2i_sat(__fmul_rn(mvy, (float)H));
+      const short2 mvs = make_short2((short)max(-32768, min(32767, mix_)), (short)max(-32768, min(32767, miy)));
+      P.motion[pix] = mvs;
+      if (!((x | y) & 1) && (x >> 1) < (W >> 1) && (y >> 1) < (H >> 1)) {     // the quarter-res stage's temporal lookup, gathered here (FrameParams::k2G)
+        const size_t q = (size_t)(y >> 1) * (P.pitch >> 1) + (x >> 1);
+        P.k2Mv[q] = mvs;
+        P.k2G[q] = loadG(P.lastG, P, mvs.x, mvs.y);
+      }
+      uint4 g = encodeGeometryInfo(st, prd.hitT);
+      if (P.st.debugging_mode > eIndirectStage) updateGeometryAlbedo(g, debugInfo(st, P.st.debugging_mode));
+      else if (st.isEmitter) updateGeometryAlbedo(g, st.mat.emission);
+      else {
+        const f3 wo = -rd, one = mk3(1.0f);
+        for (int i = 0; i < P.st.RISSampleNum; i++) {
+          LightSampleD ls; ls.Li = mk3(0.f); ls.wi = mk3(0.f); ls.dist = 0.f;
+          float p = sampleDirectLightNoVisibility<TEX>(P.sc, P.env, P.st, st.position, seed, ls);
+          f3 pHat = (ls.Li * bsdfEval(one, st.mat.roughness, st.mat.metallic, st.ffnormal, wo, ls.wi)) * fabsf(dot3(st.ffnormal, ls.wi));
+          float weight = lum3(pHat / p);
+          if (isPdfInvalid(p) || weight != weight) weight = 0.0f;
+          resvUpdate(resv, ls.Li, ls.wi, ls.dist, weight, rnd(seed));
+        }
+        if (occlusion<STATS, TEX>(P, offsetRay(st.position, st.ffnormal), resv.wi, st.position, resv.dist, seed, rc)) resv.weight = 0.0f;
+      }
+      P.thisG[pix] = g;
+      storeDResv(P.thisDR, index, resv);
+    }
+  }
+  flushCounters<STATS>(P, rc);
+}
+
+__global__ void __launch_bounds__(64) k_direct_reuse(const FrameParams P) {                       // direct_reuse.comp:102-153
+  const int x = blockIdx.x * 8 + threadIdx.x;
+  const int y = stripeRow(P.sFirst, P.sStride, P.sRows, 8);
+  const int W = P.st.size.x, H = P.st.size.y;
+  if (x >= W || y >= H) return;
+  const size_t pix = (size_t)y * P.pitch + x, index = (size_t)y * W + x;
+  uint32_t seed = tea((uint32_t)((int)index + W * H), P.st.time);
+  f3 ro, rd;
+  raySpawn<true>(P.cam, x, y, W, H, ro, rd);
+  const uint4 g = P.thisG[pix];                                        // getDirectStateFromGBuffer (pathtrace.glsl:277-294)
+  const float depth = __uint_as_float(g.x);
+  if (depth >= __fmul_rn(EID_INFINITY, 0.8f)) { P.directImg[pix] = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // (always thisDirectResultImage: no bilateral switch in this shader)
+  const f3 position = ro + rd * depth, normal = octDecode(g.y);
+  const uint32_t matID = g.w >> 24;
+  DResv resv;
+  loadDResvPlain(P.thisDR, index, resv);
+  const f3 Li0 = resv.Li;                                              // LightSample lsample = resv.lightSample: taken BEFORE the merge
+  const short2 mv = P.motion[pix];
+  if (P.st.ReSTIRState == eTemporal || P.st.ReSTIRState == eSpatiotemporal) {
+    const float reprojDepth = len3(ld3(P.cam.lastPosition) - position);
+    const int mix_ = mv.x, miy = mv.y;
+    if (mix_ >= 2 && mix_ < W && miy >= 0 && miy < H) {                // findTemporalNeighbor :47-84 (same text as direct_stage.comp)
+      const uint4 gl = loadG(P.lastG, P, mix_, miy);
+      if (hash8(matID) == (gl.w & 0xFF000000u) && dot3(normal, octDecode(gl.y)) > 0.9f && reprojDepth < __fmul_rn(__uint_as_float(gl.x), 1.05f)) {
+        DResv t;
+        loadDResv(P.lastDR, (size_t)miy * W + mix_, t);
+        if (!resvInvalidW(t.weight)) {
+          const float rv = rnd(seed);
+          resv.weight = __fadd_rn(resv.weight, t.weight);
+          resv.num += t.num;
+          if (__fmul_rn(rv, resv.weight) < t.weight) { resv.Li = t.Li; resv.wi = t.wi; resv.dist = t.dist; }
+        }
+      }
+    }
+  }
+  f3 direct = mk3(0.0f);
+  if (!resvInvalidW(resv.weight)) direct = Li0;                        // `direct = lsample.Li` (:138; the LiBSDF above it is unused)
+  const int clampN = P.st.RISSampleNum * P.st.reservoirClamp;          // resvClamp, then resvCheckValidity
+  if (resv.num > (uint32_t)clampN) { resv.weight = __fmul_rn(resv.weight, __fdiv_rn((float)clampN, (float)resv.num)); resv.num = (uint32_t)clampN; }
+  if (resvInvalidW(resv.weight)) { resv.num = 0; resv.weight = 0.f; }
+  if (nan3(direct)) direct = mk3(0.0f);
+  storeDResv(P.thisDR, index, resv);
+  const f3 px = hdrToLdr(clampRadiance(direct, P.st.fireflyClampThreshold));
+  P.directImg[pix] = make_float4(px.x, px.y, px.z, 1.0f);
 }
 
 }  // namespace eid

@@ -10,6 +10,7 @@ namespace eid {
 // K1 — direct_stage.comp (k_direct.cu)
 void launchDirectStage(const FrameParams& P, dim3 grid, cudaStream_t st, bool stats, bool tex, bool spatial, int halo);
 void launchDirectSpatial(const FrameParams& P, dim3 grid, cudaStream_t st);
+void launchDirectSplit(const FrameParams& P, dim3 grid, cudaStream_t st, bool stats, bool tex);   // direct_gen.comp + direct_reuse.comp
 
 // K2 — indirect_stage.comp, one thread per pixel (k_indirect.cu)
 void launchIndirectMega(const FrameParams& P, dim3 grid, cudaStream_t st, bool stats, bool tex);

@@ -334,18 +334,23 @@ EID_API int  eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, c
 EID_API int  eid_renderer_render_host_async(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames,
                                             float* direct_host, float* indirect_host);
 EID_API int  eid_renderer_wait_host(eid_renderer* r);
-/* 1 (default): run the direct denoiser (K3) on a second CUDA stream concurrently with indirect_stage (K2) + the indirect
- * denoiser (K4) — the reference's true dependencies are K1->{K2,K3}, K2->K4, {K3,K4}->K5.  0: strict K1..K5 order on one stream.
- * Results are identical either way; per-stage times (kernelMs) overlap when enabled. */
 /* The reference's compile-time shader variants as run-time switches (all 0 = the reference as shipped):
  *   EID_VARIANT_DIRECT_BILATERAL    #define DENOISER_DIRECT_BILATERAL 1 (host_device.h:28): direct_stage writes denoiseDirTempA (direct_stage.comp:284-288),
  *                                   ONE 9 x 9 cross-bilateral pass with a spatial term replaces the four A-Trous levels (denoise_direct.comp:73-137, renderer.cpp:186-188)
  *   EID_VARIANT_INDIRECT_BILATERAL  #define DENOISER_INDIRECT_BILATERAL 1 (host_device.h:29): ONE 11 x 11 pass at quarter resolution (denoise_indirect.comp:77-130)
  *   EID_VARIANT_FETCH_4_SUBPIXELS   #define FETCH_GEOM_CHECK_4_SUBPIXELS 1 (indirect_stage.comp:35): the quarter-res stage averages the four G-buffer texels of
  *                                   its 2 x 2 footprint and draws the material id among them (pathtrace.glsl:314-358; one more RNG draw per pixel)
+ *   EID_VARIANT_DIRECT_SPLIT        the two-kernel form of the direct stage, direct_gen.comp (:77-149: primary ray, G-buffer — sky / emitter /
+ *                                   debug radiance parked in its albedo bits —, RIS candidates, shadow ray, reservoir) followed by direct_reuse.comp
+ *                                   (:102-153: state rebuilt from the G-buffer, temporal merge, clamp, `direct = Li` of the pre-merge sample), in place
+ *                                   of direct_stage.comp.  The reference builds both pipelines (renderer.cpp:129-132) and never dispatches them; the
+ *                                   pair is reproduced as written (it is visibly work in progress there).  No spatial reuse in this form.
  * (INDIRECT_PRE_UPSCALE, host_device.h:27, is defined but referenced nowhere in the reference: there is nothing to switch.) */
-enum { EID_VARIANT_DIRECT_BILATERAL = 1, EID_VARIANT_INDIRECT_BILATERAL = 2, EID_VARIANT_FETCH_4_SUBPIXELS = 4 };
+enum { EID_VARIANT_DIRECT_BILATERAL = 1, EID_VARIANT_INDIRECT_BILATERAL = 2, EID_VARIANT_FETCH_4_SUBPIXELS = 4, EID_VARIANT_DIRECT_SPLIT = 8 };
 EID_API int  eid_renderer_set_variant(eid_renderer* r, int flags);
+/* 1 (default): run the direct denoiser (K3) on a second CUDA stream concurrently with indirect_stage (K2) + the indirect
+ * denoiser (K4) — the reference's true dependencies are K1->{K2,K3}, K2->K4, {K3,K4}->K5.  0: strict K1..K5 order on one stream.
+ * Results are identical either way; per-stage times (kernelMs) overlap when enabled. */
 EID_API int  eid_renderer_set_overlap(eid_renderer* r, int enabled);
 /* Frames in flight.  1 (default): a frame's stages only start when the previous eid_renderer_run has finished (the reference records one
  * command buffer per frame).  2: direct_stage of frame f + 1 runs on an internal stream while indirect_stage / denoise / compose of frame f

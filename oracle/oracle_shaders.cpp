@@ -838,6 +838,108 @@ struct Ctx {
     return res;
   }
 
+  // ---- direct_gen.comp / direct_reuse.comp: the two-kernel form of the direct stage (pipelines created at renderer.cpp:129-132, never
+  // dispatched by Renderer::run; EID_VARIANT_DIRECT_SPLIT runs them in place of direct_stage) ---------------------------------------
+  void updateGeometryAlbedo(uvec4& gInfo, vec3 albedo) {                                       // direct_gen.comp:62-65
+    uint matId = gInfo.w & 0xff000000u;
+    gInfo.w = (packUnorm4x8(vec4(albedo, 1.0f)) & 0x00ffffffu) | matId;
+  }
+  void directGenMain(int gx, int gy) {                                                          // direct_gen.comp:77-137 + main :139-149
+    ivec2 imageRes = size();
+    imageCoords = ivec2(gx, gy);
+    if (imageCoords.x >= imageRes.x || imageCoords.y >= imageRes.y) return;
+    prd.seed = tea((uint)rtxState.size.x * (uint)gy + (uint)gx, rtxState.time);
+    Ray r = raySpawn(imageCoords, imageRes);
+    const size_t index = (size_t)imageCoords.y * rtxState.size.x + imageCoords.x;
+    ClosestHit(r);
+    DirectReservoir resv{};
+    resvReset(resv);
+    if (prd.hitT >= INFINITY_ * 0.8f) {
+      uvec4 gInfo = uvec4(floatBitsToUint(INFINITY_), 0, 0, InvalidMatId);
+      updateGeometryAlbedo(gInfo, EnvRadiance(r.direction));
+      thisGbuffer[(size_t)imageCoords.y * pitch + imageCoords.x] = gInfo;
+      storeMotion(imageCoords, ivec2(0, 0));
+      thisDirectResv[index] = resv;
+      return;
+    }
+    rr.primaryHits.fetch_add(1, std::memory_order_relaxed);
+    State state = GetState(prd, r.direction);
+    GetMaterials(state, r);
+    ivec2 motionIdx = createMotionIndex(state.position);
+    storeMotion(imageCoords, motionIdx);
+    uvec4 gInfo = encodeGeometryInfo(state, prd.hitT);
+    if (rtxState.debugging_mode > eIndirectStage) updateGeometryAlbedo(gInfo, DebugInfo(state));
+    else if (state.isEmitter) updateGeometryAlbedo(gInfo, state.mat.emission);
+    else {
+      vec3 wo = -r.direction;
+      state.mat.albedo = vec3(1.0f);
+      for (int i = 0; i < rtxState.RISSampleNum; i++) {
+        LightSample lsample{};
+        float p = SampleDirectLightNoVisibility(state.position, lsample);
+        vec3 pHat = V(lsample.Li) * Eval(state, wo, state.ffnormal, V(lsample.wi)) * gabs(dot(state.ffnormal, V(lsample.wi)));
+        float weight = resvToScalar(pHat / p);
+        if (IsPdfInvalid(p) || gisnan(weight)) weight = 0.0f;
+        resvUpdate(resv, lsample, weight, rand());
+      }
+      LightSample lsample = resv.lightSample;
+      Ray shadowRay;
+      shadowRay.origin = OffsetRay(state.position, state.ffnormal);
+      shadowRay.direction = V(lsample.wi);
+      if (Occlusion(shadowRay, state, lsample.dist)) resv.weight = 0.0f;
+    }
+    thisGbuffer[(size_t)imageCoords.y * pitch + imageCoords.x] = gInfo;
+    thisDirectResv[index] = resv;
+  }
+  bool getDirectStateFromGBuffer(const std::vector<uvec4>& gBuffer, const Ray& ray, State& state, float& depth) {   // pathtrace.glsl:277-294
+    uvec4 gInfo = loadG(gBuffer, imageCoords);
+    depth = uintBitsToFloat(gInfo.x);
+    if (depth >= INFINITY_ * 0.8f) return false;
+    state.position = ray.origin + ray.direction * depth;
+    state.normal = decompress_unit_vec(gInfo.y);
+    state.ffnormal = dot(state.normal, ray.direction) <= 0.0f ? state.normal : -state.normal;
+    state.mat.albedo = unpackUnorm4x8(gInfo.w).xyz();
+    vec4 matInfo = unpackUnorm4x8(gInfo.z);
+    state.mat.metallic = matInfo.x;
+    state.mat.roughness = matInfo.y;
+    state.mat.ior = matInfo.z * MAX_IOR_MINUS_ONE + 1.f;
+    state.mat.transmission = matInfo.w;
+    state.matID = gInfo.w >> 24;
+    return true;
+  }
+  void directReuseMain(int gx, int gy) {                                                        // direct_reuse.comp:102-153
+    imageCoords = ivec2(gx, gy);
+    if (imageCoords.x >= rtxState.size.x || imageCoords.y >= rtxState.size.y) return;
+    int index = imageCoords.y * rtxState.size.x + imageCoords.x;
+    prd.seed = tea((uint)(index + rtxState.size.x * rtxState.size.y), rtxState.time);
+    Ray ray = raySpawn(imageCoords, size());
+    State state{};
+    float depth;
+    if (!getDirectStateFromGBuffer(thisGbuffer, ray, state, depth)) {
+      storeImg(rr.directResult, imageCoords, vec4(0.0f));
+      return;
+    }
+    state.mat.albedo = vec3(1.0f);
+    vec3 direct = vec3(0.0f);
+    DirectReservoir resv = thisDirectResv[(size_t)index];
+    LightSample lsample = resv.lightSample;
+    ivec2 motionIdx(0, 0);
+    if (imageCoords.x < (int)rr.width && imageCoords.y < (int)rr.height)
+      motionIdx = ivec2(rr.motion[2 * ((size_t)imageCoords.y * pitch + imageCoords.x)], rr.motion[2 * ((size_t)imageCoords.y * pitch + imageCoords.x) + 1]);
+    if (rtxState.ReSTIRState == eTemporal || rtxState.ReSTIRState == eSpatiotemporal) {
+      float reprojDepth = length(V(cam.lastPosition) - state.position);
+      DirectReservoir temporal{};
+      if (findTemporalNeighborDirect(state.normal, depth, reprojDepth, state.matID, motionIdx, temporal)) {
+        if (!resvInvalid(temporal)) resvMerge(resv, temporal, rand());
+      }
+    }
+    if (!resvInvalid(resv)) direct = V(lsample.Li);      // (the LiBSDF of :134 is computed and not used)
+    resvClamp(resv, rtxState.RISSampleNum * rtxState.reservoirClamp);
+    resvCheckValidity(resv);
+    if (gisnan(direct.x) || gisnan(direct.y) || gisnan(direct.z)) direct = vec3(0.0f);
+    thisDirectResv[(size_t)index] = resv;
+    storeImg(rr.directResult, imageCoords, vec4(HDRToLDR(clampRadiance(direct)), 1.0f));
+  }
+
   void directMain(int gx, int gy) {                                                            // :272-289
     ivec2 imageRes = size();
     imageCoords = ivec2(gx, gy);
@@ -1221,6 +1323,12 @@ void Renderer::runDirect(const RtxState& st, int frames, int y0, int y1) {
     const uint64_t c0 = closestRays, a0 = anyRays, p0 = primaryHits;
     dispatch(st.size.x, st.size.y, y0 > 0 ? y0 - 1 : 0, y1 < st.size.y ? y1 + 1 : y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.primeOnly = true; c.directMain(x, y); });
     closestRays = c0; anyRays = a0; primaryHits = p0;
+  }
+  if (variant & EID_VARIANT_DIRECT_SPLIT) {     // direct_gen.comp then direct_reuse.comp in place of direct_stage.comp
+    dispatch(st.size.x, st.size.y, y0, y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.directGenMain(x, y); });
+    dispatch(st.size.x, st.size.y, y0, y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.directReuseMain(x, y); });
+    kernelMs[0] += nowMs() - t0;
+    return;
   }
   dispatch(st.size.x, st.size.y, y0, y1, [&](int x, int y) { Ctx c(*scene, *this, st, set); c.directMain(x, y); });
   kernelMs[0] += nowMs() - t0;

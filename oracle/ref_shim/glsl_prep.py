@@ -26,7 +26,7 @@ import sys
 BUILTINS = ["abs", "acos", "asin", "atan", "clamp", "cos", "cross", "dot", "exp", "floor", "inverse", "isnan", "isinf", "length", "max", "min",
             "mix", "normalize", "pow", "reflect", "sin", "smoothstep", "sqrt", "tan", "intBitsToFloat", "floatBitsToInt", "uintBitsToFloat",
             "floatBitsToUint", "unpackUnorm4x8", "packUnorm4x8"]
-TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|ivec2|ivec3|uvec2|uvec3|mat3|mat4|State|Material|Ray|SunAndSky|DirectReservoir|IndirectReservoir|LightSample|GISample|RngStateType|sampler2D|GltfShadeMaterial|TrigLight|PuncLight|PtPayload|uimage2D|image2D|rayQueryEXT|ShadeState)"
+TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|ivec2|ivec3|uvec2|uvec3|uvec4|ivec4|mat3|mat4|State|Material|Ray|SunAndSky|DirectReservoir|IndirectReservoir|LightSample|GISample|RngStateType|sampler2D|GltfShadeMaterial|TrigLight|PuncLight|PtPayload|uimage2D|image2D|rayQueryEXT|ShadeState)"
 FLOAT_LIT = re.compile(r"(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
 
 

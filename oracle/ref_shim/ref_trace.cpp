@@ -124,6 +124,43 @@ namespace reftrace { namespace k2 {
 #endif
 } }
 
+#ifdef REF_VARIANT
+// direct_gen.comp / direct_reuse.comp: two more shader modules of the variant build (EID_VARIANT_DIRECT_SPLIT)
+#define REF_UNDEF_GUARDS
+#undef GLOBALS_GLSL
+#undef RANDOM_GLSL
+#undef RAYCOMMON_GLSL
+#undef PBR_METALLICWORKFLOW_GLSL
+#undef GLTFMATERIAL_GLSL
+#undef ENV_SAMPLING_GLSL
+#undef SUN_AND_SKY_GLSL
+#undef SHADE_STATE_GLSL
+#undef RESERVOIR_GLSL
+#undef M_PI
+namespace reftrace { namespace kg {
+#include "../_ref/gen/globals.hpp"
+#include "ref_trace_stage.inl"
+#include "../_ref/gen/pathtrace_gd.hpp"
+#include "../_ref/gen/direct_gen.hpp"
+} }
+#undef GLOBALS_GLSL
+#undef RANDOM_GLSL
+#undef RAYCOMMON_GLSL
+#undef PBR_METALLICWORKFLOW_GLSL
+#undef GLTFMATERIAL_GLSL
+#undef ENV_SAMPLING_GLSL
+#undef SUN_AND_SKY_GLSL
+#undef SHADE_STATE_GLSL
+#undef RESERVOIR_GLSL
+#undef M_PI
+namespace reftrace { namespace kr {
+#include "../_ref/gen/globals.hpp"
+#include "ref_trace_stage.inl"
+#include "../_ref/gen/pathtrace_gd.hpp"
+#include "../_ref/gen/direct_reuse.hpp"
+} }
+#endif
+
 using namespace reftrace;
 struct RefTraceBind {   // everything ref_trace_bind needs, as one C struct (filled by tests/oracle_lib.py)
   const RtxState* state; const SceneCamera* camera; const SunAndSky* sunSky; const LightBufInfo* lightInfo;
@@ -174,6 +211,10 @@ void ref_trace_run(const RefTraceBind* b, int runDirect, int runIndirect, unsign
     dispatchGroups(W, H, [] { k1::main(); });
     g_closest = g_any = 0;
   }
+#ifdef REF_VARIANT
+  if (runDirect == 2) { dispatchGroups(W, H, [] { kg::main(); }); dispatchGroups(W, H, [] { kr::main(); }); }   // direct_gen.comp, then direct_reuse.comp
+  else
+#endif
   if (runDirect) dispatchGroups(W, H, [] { k1::main(); });
   if (runIndirect) dispatchGroups(W / 2, H / 2, [] { k2::main(); });
   if (rays) { rays[0] = g_closest; rays[1] = g_any; }

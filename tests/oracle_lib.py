@@ -370,11 +370,15 @@ class RefTracer:
             self.R.ref_trace_run(C.byref(b), int(direct), int(indirect), self.rays.ctypes.data)
         else:       # per stage: the regular build, or the one with DENOISER_DIRECT_BILATERAL (direct) / FETCH_GEOM_CHECK_4_SUBPIXELS (indirect) flipped
             total = np.zeros(2, np.uint64)
-            for want, is_direct, bit in ((direct, True, 1), (indirect, False, 4)):
-                if want:
-                    fn = self.R.ref_trace_run_variant if (self.variant & bit) else self.R.ref_trace_run
-                    fn(C.byref(b), int(is_direct), int(not is_direct), self.rays.ctypes.data)
-                    total += self.rays
+            if direct:      # bit 8: direct_gen.comp + direct_reuse.comp (variant build, mode 2); bit 1: direct_stage.comp with DENOISER_DIRECT_BILATERAL
+                if self.variant & 8:
+                    self.R.ref_trace_run_variant(C.byref(b), 2, 0, self.rays.ctypes.data)
+                else:
+                    (self.R.ref_trace_run_variant if (self.variant & 1) else self.R.ref_trace_run)(C.byref(b), 1, 0, self.rays.ctypes.data)
+                total += self.rays
+            if indirect:    # bit 4: indirect_stage.comp with FETCH_GEOM_CHECK_4_SUBPIXELS
+                (self.R.ref_trace_run_variant if (self.variant & 4) else self.R.ref_trace_run)(C.byref(b), 0, 1, self.rays.ctypes.data)
+                total += self.rays
             self.rays[:] = total
         return {"gbuffer": self.G[1 - s], "motion": self.motion, "direct_resv": self.DR[1 - s], "indirect_resv": self.IR[1 - s],
                 "direct": self.direct, "ind_tmp_a": self.indA, "dir_tmp_a": self.dirA}

@@ -145,7 +145,11 @@ VARIANT_CONFIGS = [("bil_direct", "cornell_scene", (48, 32), 2, 1, dict(maxDepth
                    ("sub4", "small_room", (50, 34), 3, 4, dict(maxDepth=3)),
                    ("sub4_cube_sky", "cube_scene", (40, 24), 2, 4, dict(maxDepth=2)),
                    ("all_three", "cornell_scene", (40, 24), 2, 7, dict(maxDepth=3)),
-                   ("bil_nodenoise", "cornell_scene", (32, 24), 2, 3, dict(maxDepth=2, denoise=0))]
+                   ("bil_nodenoise", "cornell_scene", (32, 24), 2, 3, dict(maxDepth=2, denoise=0)),
+                   ("split", "cornell_scene", (48, 32), 3, 8, dict(maxDepth=2)),                 # direct_gen.comp + direct_reuse.comp
+                   ("split_cube_sky", "cube_scene", (40, 24), 2, 8, dict(maxDepth=2)),
+                   ("split_room_ris", "small_room", (40, 28), 2, 8 | 4, dict(maxDepth=2, ReSTIRState=1, RISSampleNum=2)),
+                   ("split_debug", "cornell_scene", (32, 24), 1, 8, dict(debugging_mode=6))]
 VARIANT_KEYS = ("BUF_THIS_GBUFFER", "BUF_MOTION", "BUF_THIS_DIRECT_RESV", "BUF_THIS_INDIRECT_RESV", "BUF_DIRECT", "BUF_INDIRECT", "BUF_DENOISE_DIR_A",
                 "BUF_DENOISE_IND_A", "BUF_DENOISE_IND_B")
 # host tables (src/scene.cpp run on an injected scene): scene makers, and the camera sequence (size, optional new look-at) after loading

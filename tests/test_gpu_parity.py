@@ -984,10 +984,12 @@ def test_frames_in_flight_are_bit_identical(restir):
 
 
 @pytest.mark.parametrize("variant", [abi.VARIANT_DIRECT_BILATERAL, abi.VARIANT_INDIRECT_BILATERAL, abi.VARIANT_FETCH_4_SUBPIXELS,
-                                     abi.VARIANT_DIRECT_BILATERAL | abi.VARIANT_INDIRECT_BILATERAL | abi.VARIANT_FETCH_4_SUBPIXELS])
+                                     abi.VARIANT_DIRECT_BILATERAL | abi.VARIANT_INDIRECT_BILATERAL | abi.VARIANT_FETCH_4_SUBPIXELS,
+                                     abi.VARIANT_DIRECT_SPLIT, abi.VARIANT_DIRECT_SPLIT | abi.VARIANT_INDIRECT_BILATERAL | abi.VARIANT_FETCH_4_SUBPIXELS])
 @pytest.mark.parametrize("wavefront", [True, False])
 def test_reference_compile_time_variants(variant, wavefront):
-    """Scope row (f.4): the reference's dormant compile-time variants as run-time switches (eid_renderer_set_variant) — the bilateral
+    """Scope row (f.4): the reference's dormant variants as run-time switches (eid_renderer_set_variant) — the two-kernel direct stage
+    direct_gen.comp + direct_reuse.comp (built by the reference, renderer.cpp:129-132, never dispatched), the bilateral
     denoisers (DENOISER_DIRECT_BILATERAL: direct_stage.comp:284-288, denoise_direct.comp:73-137, renderer.cpp:186-188;
     DENOISER_INDIRECT_BILATERAL: denoise_indirect.comp:77-130) and FETCH_GEOM_CHECK_4_SUBPIXELS (pathtrace.glsl:314-358, one more RNG
     draw per quarter-res pixel) — bit-identical to the oracle with strict math, both K2 forms, moving camera, sky pixels included."""
@@ -1031,4 +1033,4 @@ def test_reference_compile_time_variants(variant, wavefront):
         rep = common.compare_snapshots(common.snapshot(prr), common.snapshot(orr), "variant %d fast frame %d" % (variant, f))
         assert max(rep.values()) <= 1e-3
     with pytest.raises(eid.EidolaError):
-        prr.set_variant(8)
+        prr.set_variant(16)
