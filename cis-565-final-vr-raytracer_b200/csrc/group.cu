@@ -264,29 +264,22 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
   if (!g || !state) raise(EID_ERR_INVALID, "eid_group_render_host_async: null argument");
   eid_renderer* r = g->r;
   CUDA_CHECK(cudaSetDevice(r->device));
-  if (!g->copyStream) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&g->copyStream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&g->evFrameDone, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&g->evCopyDone, cudaEventDisableTiming));
-  }
-  const size_t bandBytes = (size_t)r->width * g->bandRows * 16;
-  if (!g->staging[0]) { CUDA_CHECK(cudaMalloc(&g->staging[0], bandBytes)); CUDA_CHECK(cudaMalloc(&g->staging[1], bandBytes)); }
+  ensureCopyStream(r);
   if (cam) r->scene->host.camera = *cam;
-  groupFrame(g, *state, frames, false);
+  groupFrame(g, *state, frames, false);             // (fillParams waits for the copy that read this parity's images two frames ago)
   const uint32_t y0 = g->world > 1 ? (uint32_t)g->rank * g->bandRows : 0;
   const uint32_t y1 = std::min<uint32_t>(y0 + g->bandRows, (uint32_t)state->size.y);
   if (y1 > y0) {
+    // the band is copied IN PLACE from this parity's result images on the renderer's copy stream, behind the next frame (other parity)
+    const int set = r->lastSet;
     const size_t first = (size_t)y0 * r->width;
-    if (g->copyPending) CUDA_CHECK(cudaStreamWaitEvent(r->stream, g->evCopyDone, 0));
-    if (direct_host) CUDA_CHECK(cudaMemcpyAsync(g->staging[0], r->directImg + first, (size_t)(y1 - y0) * r->width * 16, cudaMemcpyDeviceToDevice, r->stream));
-    if (indirect_host) CUDA_CHECK(cudaMemcpyAsync(g->staging[1], r->indirectImg + first, (size_t)(y1 - y0) * r->width * 16, cudaMemcpyDeviceToDevice, r->stream));
-    CUDA_CHECK(cudaEventRecord(g->evFrameDone, r->stream));
-    CUDA_CHECK(cudaStreamWaitEvent(g->copyStream, g->evFrameDone, 0));
+    CUDA_CHECK(cudaEventRecord(r->evFrameDone, r->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, r->evFrameDone, 0));
     const size_t rowBytes = (size_t)state->size.x * 16;
-    if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)direct_host + (size_t)y0 * rowBytes, rowBytes, g->staging[0], (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, g->copyStream));
-    if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)indirect_host + (size_t)y0 * rowBytes, rowBytes, g->staging[1], (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, g->copyStream));
-    CUDA_CHECK(cudaEventRecord(g->evCopyDone, g->copyStream));
-    g->copyPending = true;
+    if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)direct_host + (size_t)y0 * rowBytes, rowBytes, r->directImg + first, (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, r->copyStream));
+    if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)indirect_host + (size_t)y0 * rowBytes, rowBytes, r->indirectImg + first, (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, r->copyStream));
+    CUDA_CHECK(cudaEventRecord(r->evCopyDone2[set], r->copyStream));
+    r->copyPending2[set] = true;
   }
   return EID_OK;
   EID_CATCH
@@ -296,8 +289,7 @@ int eid_group_wait_host(eid_group* g) {
   EID_TRY
   if (!g) raise(EID_ERR_INVALID, "eid_group_wait_host: null group");
   CUDA_CHECK(cudaSetDevice(g->r->device));
-  if (g->copyStream) CUDA_CHECK(cudaStreamSynchronize(g->copyStream));
-  g->copyPending = false;
+  if (g->r->copyStream) CUDA_CHECK(cudaStreamSynchronize(g->r->copyStream));
   return EID_OK;
   EID_CATCH
 }

@@ -22,7 +22,9 @@ void eid_renderer::release() {
   cudaFree(mipScratch); mipScratch = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
   for (int i = 0; i < 2; ++i) { cudaFree(directImgs[i]); cudaFree(k2G[i]); cudaFree(k2Mv[i]); directImgs[i] = nullptr; k2G[i] = nullptr; k2Mv[i] = nullptr; }
-  cudaFree(indirectImg); directImg = indirectImg = nullptr;
+  for (int i = 0; i < 2; ++i) { cudaFree(indirectImgs[i]); indirectImgs[i] = nullptr; }
+  directImg = indirectImg = nullptr;
+  copyPending2[0] = copyPending2[1] = false;
   frameDoneValid[0] = frameDoneValid[1] = false;
   tmaps.clear();
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
@@ -50,7 +52,8 @@ void eid_renderer::allocate() {
   const size_t slack = (size_t)17 * width * 16;
   for (int i = 0; i < 2; ++i) { zalloc((void**)&directImgs[i], n * 16 + slack); zalloc((void**)&k2G[i], ni * 16); zalloc((void**)&k2Mv[i], ni * 4); }
   directImg = directImgs[0];
-  zalloc((void**)&indirectImg, n * 16 + slack);
+  for (int i = 0; i < 2; ++i) zalloc((void**)&indirectImgs[i], n * 16 + slack);
+  indirectImg = indirectImgs[0];
   for (auto& t : denoiseTemp) zalloc((void**)&t, n * 16 + slack);
   zalloc((void**)&geom[0], n * 16 + slack); zalloc((void**)&geom[1], n * 16 + slack);
   zalloc((void**)&geom[2], ni * 16 + slack); zalloc((void**)&geom[3], ni * 16 + slack);
@@ -101,7 +104,12 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   P.motion = r->motion;
   P.thisDR = r->directResv[!set]; P.lastDR = r->directResv[set];
   P.thisIR = r->indirectResv[!set]; P.lastIR = r->indirectResv[set];
-  r->directImg = r->directImgs[set];
+  r->directImg = r->directImgs[set]; r->indirectImg = r->indirectImgs[set];
+  if (r->copyPending2[set]) {        // a device-to-host copy of this parity's result images (two frames ago) must have drained before they are rewritten
+    CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evCopyDone2[set], 0));
+    if (r->pipeline) CUDA_CHECK(cudaStreamWaitEvent(r->k1Stream, r->evCopyDone2[set], 0));
+    r->copyPending2[set] = false;
+  }
   P.directImg = r->directImg; P.indirectImg = r->indirectImg;
   P.k2G = r->k2G[set]; P.k2Mv = r->k2Mv[set];
   P.variant = r->variant;
@@ -544,6 +552,7 @@ void eid_renderer_destroy(eid_renderer* r) {
   if (r->evWave) cudaEventDestroy(r->evWave); if (r->evWaveJoin) cudaEventDestroy(r->evWaveJoin);
   if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
   if (r->evFrameDone) cudaEventDestroy(r->evFrameDone); if (r->evCopyDone) cudaEventDestroy(r->evCopyDone);
+  for (auto& e : r->evCopyDone2) if (e) cudaEventDestroy(e);
   cudaFree(r->staging[0]); cudaFree(r->staging[1]);
   if (r->ownStream && r->stream) cudaStreamDestroy(r->stream);
   delete r;
@@ -912,36 +921,37 @@ int eid_renderer_render_host(eid_renderer* r, const SceneCamera* cam, const RtxS
   EID_CATCH
 }
 
-// Pipelined variant: the frame is enqueued, its two result images are snapshotted device-to-device into staging buffers (so the
-// next frame may overwrite the live images at once) and the device-to-host copies run on a dedicated copy stream, overlapping the
-// next frame's kernels.  The host buffers are complete after eid_renderer_wait_host (or the next *_async call for the SAME
-// buffers, which waits first).  Use two host buffer pairs alternately for full overlap.
+// Pipelined variant: the frame is enqueued and its two result images — which exist once per ping-pong parity, so the next frame
+// renders into the other pair — are copied to the host IN PLACE on a dedicated copy stream while the next frame's kernels run; the
+// frame after that (same parity) waits for this copy before it rewrites them.  The host buffers are complete after
+// eid_renderer_wait_host.  Use two host buffer pairs alternately.
+extern "C++" {
+void ensureCopyStream(eid_renderer* r) {
+  if (r->copyStream) return;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&r->evFrameDone, cudaEventDisableTiming));
+  for (auto& e : r->evCopyDone2) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+}
+
 int eid_renderer_render_host_async(eid_renderer* r, const SceneCamera* cam, const RtxState* state, int frames, float* direct_host, float* indirect_host) {
   EID_TRY
   if (!r || !state) raise(EID_ERR_INVALID, "eid_renderer_render_host_async: null argument");
   CUDA_CHECK(cudaSetDevice(r->device));
-  if (!r->copyStream) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&r->evFrameDone, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&r->evCopyDone, cudaEventDisableTiming));
-  }
-  const size_t n = (size_t)r->width * r->height * 16;
-  if (!r->staging[0]) { CUDA_CHECK(cudaMalloc(&r->staging[0], n)); CUDA_CHECK(cudaMalloc(&r->staging[1], n)); }
+  ensureCopyStream(r);
   if (cam) r->scene->host.camera = *cam;
   FrameParams P;
-  fillParams(r, *state, frames, P);
+  fillParams(r, *state, frames, P);                 // (waits for the copy that read this parity's images two frames ago)
   launchFrame(r, P);
-  // the previous frame's D2H copies must have drained the staging buffers before they are overwritten
-  if (r->copyPending) CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->evCopyDone, 0));
-  if (direct_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[0], r->directImg, n, cudaMemcpyDeviceToDevice, r->stream));
-  if (indirect_host) CUDA_CHECK(cudaMemcpyAsync(r->staging[1], r->indirectImg, n, cudaMemcpyDeviceToDevice, r->stream));
-  markFrameDone(r);                                 // the snapshots read this parity's direct image: part of the frame
+  // the result images are per ping-pong parity: the copy stream reads them in place while the next frame renders into the other pair
+  const int set = r->lastSet;
   CUDA_CHECK(cudaEventRecord(r->evFrameDone, r->stream));
   CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, r->evFrameDone, 0));
   const size_t rowBytes = (size_t)state->size.x * 16;
-  if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->staging[0], (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
-  if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->staging[1], (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
-  CUDA_CHECK(cudaEventRecord(r->evCopyDone, r->copyStream));
+  if (direct_host) CUDA_CHECK(cudaMemcpy2DAsync(direct_host, rowBytes, r->directImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
+  if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync(indirect_host, rowBytes, r->indirectImg, (size_t)r->width * 16, rowBytes, state->size.y, cudaMemcpyDeviceToHost, r->copyStream));
+  CUDA_CHECK(cudaEventRecord(r->evCopyDone2[set], r->copyStream));
+  r->copyPending2[set] = true;
   r->copyPending = true;
   return EID_OK;
   EID_CATCH

@@ -24,7 +24,8 @@ struct eid_renderer {
   float* indirectResv[2] = {nullptr, nullptr};
   float4* directImgs[2] = {nullptr, nullptr};   // thisDirectResultImage, one per ping-pong parity (a frame in flight keeps its own while the next one traces)
   float4* directImg = nullptr;                  // = directImgs[parity of the frame enqueued last]
-  float4* indirectImg = nullptr;
+  float4* indirectImgs[2] = {nullptr, nullptr};
+  float4* indirectImg = nullptr;                // = indirectImgs[parity of the frame enqueued last]
   uint4* k2G[2] = {nullptr, nullptr}; short2* k2Mv[2] = {nullptr, nullptr};   // FrameParams::k2G / k2Mv, per parity
   // frames in flight (eid_renderer_set_pipeline): direct_stage of frame f + 1 runs on `k1Stream` while indirect_stage / denoise / compose of
   // frame f are still on the render stream; evK1Done orders K2 / K3 after K1, evFrameDone[parity] lets K1 reuse a parity's buffers
@@ -33,6 +34,9 @@ struct eid_renderer {
   cudaStream_t k1Stream = nullptr;
   cudaEvent_t evK1Done = nullptr, evFrameDone2[2] = {nullptr, nullptr};
   bool frameDoneValid[2] = {false, false};
+  // host delivery straight from a parity's result images (no staging copy): the next frame of the same parity waits for that copy
+  cudaEvent_t evCopyDone2[2] = {nullptr, nullptr};
+  bool copyPending2[2] = {false, false};
   bool k1MustWaitStream = false;     // a strictly ordered entry point (run_trace, run_direct, the group schedule ...) ran on the render stream since the last pipelined frame
   cudaEvent_t evOrder = nullptr;
   cudaStream_t groupStream = nullptr;   // communication stream of the eid_group this renderer belongs to (synchronised with the render stream by sync / read / get_stats)
@@ -91,6 +95,7 @@ void launchPost(eid_renderer* r, const FrameParams& P, bool sharded);
 void* bufferPtr(eid_renderer* r, int which, size_t& bytes);
 // called by every entry point that enqueues stages on the render stream in strict order: orders them after any direct_stage still on the K1 stream
 void strictOrder(eid_renderer* r);
+void ensureCopyStream(eid_renderer* r);
 // post stages one by one (the multi-GPU schedule starts the direct denoiser as soon as exchange A has landed, beside indirect_stage)
 struct PostLayout { int first, stride, srows, count; bool sharded; };
 PostLayout postLayout(const FrameParams& P, bool sharded);
