@@ -86,6 +86,10 @@ class Renderer {
   void setSunAndSky(const SunAndSky& ss) { check(eid_renderer_set_sun_and_sky(m_h, &ss)); }   // SampleExample::m_sunAndSky (sample_example.cpp:172)
   void setWavefront(bool on, int traceBlocks = 0) { check(eid_renderer_set_wavefront(m_h, on ? 1 : 0, traceBlocks)); }
   void setStrictMath(bool on) { check(eid_renderer_set_strict_math(m_h, on ? 1 : 0)); }
+  // the reference's compile-time shader switches (host_device.h:27-29, indirect_stage.comp:35, the never-dispatched direct_gen / direct_reuse pair)
+  void setVariant(int flags) { check(eid_renderer_set_variant(m_h, flags)); }
+  void setFramesInFlight(int n) { check(eid_renderer_set_pipeline(m_h, n)); }          // 2: direct_stage of frame f + 1 beside the later stages of frame f
+  void setDenoiseTiles(int mode, int rowsPerThread = 0) { check(eid_renderer_set_denoise_tiles(m_h, mode, rowsPerThread)); }
   // the two RGBA32F images RenderOutput hands to post.frag (render_output.cpp:195-215): device pointers
   std::pair<const float*, const float*> outputs() const { const float *d, *i; check(eid_renderer_get_outputs(m_h, &d, &i)); return {d, i}; }
   void renderToHost(const SceneCamera* cam, const RtxState& st, int frames, float* direct, float* indirect) {
@@ -98,6 +102,28 @@ class Renderer {
   eid_renderer* handle() const { return m_h; }
  private:
   eid_renderer* m_h = nullptr;
+};
+
+// One rank of an N-GPU frame (eid_group, include/eidola.h): the renderer must have been created with the padded height of Group::layout.
+// Rank 0 calls Group::uniqueId() and hands the 128 bytes to the other ranks (MPI_Bcast, a socket, a file ...).
+class Group {
+ public:
+  struct Layout { uint32_t y0, y1, paddedHeight; };
+  static Layout layout(uint32_t height, int world, int rank = 0) { Layout l{}; check(eid_group_layout(height, world, rank, &l.y0, &l.y1, &l.paddedHeight)); return l; }
+  static void uniqueId(unsigned char id[128]) { check(eid_group_unique_id(id)); }
+  void create(Renderer& r, int rank, int world, const unsigned char* id128 = nullptr) { destroy(); check(eid_group_create(&m_h, r.handle(), rank, world, id128)); }
+  void setMode(bool postSharded, int history, bool gatherFinal) { check(eid_group_set_mode(m_h, postSharded, history, gatherFinal)); }
+  void run(const RtxState& state, int frames) { check(eid_group_run(m_h, &state, frames)); }       // the whole multi-GPU frame, asynchronous
+  void renderToHostAsync(const SceneCamera* cam, const RtxState& st, int frames, float* direct, float* indirect) {
+    check(eid_group_render_host_async(m_h, cam, &st, frames, direct, indirect));                  // every rank delivers ITS band into the shared host images
+  }
+  void waitHost() { check(eid_group_wait_host(m_h)); }
+  void sync() { check(eid_group_sync(m_h)); }
+  eid_group_info info() const { eid_group_info i; check(eid_group_get_info(m_h, &i)); return i; }
+  void destroy() { if (m_h) { eid_group_destroy(m_h); m_h = nullptr; } }
+  ~Group() { destroy(); }
+ private:
+  eid_group* m_h = nullptr;
 };
 
 // RenderOutput (src/render_output.hpp:44-60, render_output.cpp:224-240): owns the tonemapper settings; run() = post.frag over the renderer's two
