@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import abi, scenes, sharding
-from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, GroupInfo, SceneArrays, default_rtx_state)
+from .abi import (SceneCamera, RtxState, SceneInfo, AccelInfo, FrameStats, GroupInfo, PipelineLayout, SceneArrays, default_rtx_state)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # EIDOLA_LIB selects another build of the same library (kernel-variant sweeps, tools/sweep.sh); never a different backend
@@ -42,6 +42,7 @@ EXPORTS = [
     "eid_renderer_band_range", "eid_renderer_set_stripes", "eid_renderer_exchange_groups", "eid_renderer_exchange_range",
     "eid_group_layout", "eid_group_unique_id", "eid_group_create", "eid_group_destroy", "eid_group_set_mode", "eid_group_run",
     "eid_group_render_host_async", "eid_group_wait_host", "eid_group_sync", "eid_group_get_info",
+    "eid_group_pipeline_layout", "eid_group_random_id", "eid_group_create_pipeline",
 ]
 
 
@@ -130,6 +131,9 @@ def lib():
         "eid_group_wait_host": (i32, [vp]),
         "eid_group_sync": (i32, [vp]),
         "eid_group_get_info": (i32, [vp, C.POINTER(GroupInfo)]),
+        "eid_group_pipeline_layout": (i32, [u32, i32, i32, i32, i32, i32, C.POINTER(PipelineLayout)]),
+        "eid_group_random_id": (i32, [vp]),
+        "eid_group_create_pipeline": (i32, [C.POINTER(vp), vp, i32, i32, vp, u32, i32, i32, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -316,6 +320,26 @@ class Group:
         self.destroy()
         buf = (C.c_ubyte * 128).from_buffer_copy(id128) if id128 is not None else None
         _check(lib().eid_group_create(C.byref(self._h), renderer._h, rank, world, buf))
+        self._renderer = renderer
+
+    @staticmethod
+    def pipeline_layout(height, world, rank=0, stages=(0, 0, 0)):
+        """eid_group_pipeline_layout: who runs which stage on which rows (stages = ranks per stage, zeros = default split)."""
+        out = PipelineLayout()
+        _check(lib().eid_group_pipeline_layout(height, world, rank, stages[0], stages[1], stages[2], C.byref(out)))
+        return out
+
+    @staticmethod
+    def random_id():
+        buf = (C.c_ubyte * 128)()
+        _check(lib().eid_group_random_id(buf))
+        return bytes(buf)
+
+    def create_pipeline(self, renderer, rank, world, id128, height, stages=(0, 0, 0)):
+        """Stage pipeline over CUDA-IPC peer mappings (one process per rank); the renderer must have pipeline_layout().paddedHeight rows."""
+        self.destroy()
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128)
+        _check(lib().eid_group_create_pipeline(C.byref(self._h), renderer._h, rank, world, buf, height, stages[0], stages[1], stages[2]))
         self._renderer = renderer
 
     def set_mode(self, post_sharded=True, history=2, gather_final=True):

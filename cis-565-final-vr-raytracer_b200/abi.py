@@ -179,7 +179,17 @@ VARIANT_DIRECT_BILATERAL, VARIANT_INDIRECT_BILATERAL, VARIANT_FETCH_4_SUBPIXELS,
 
 class GroupInfo(C.Structure):   # eid_group_info
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("y0", C.c_uint32), ("y1", C.c_uint32), ("bandRows", C.c_uint32),
-                ("ncclVersion", C.c_int32), ("collectives", C.c_uint64)]
+                ("ncclVersion", C.c_int32), ("collectives", C.c_uint64),
+                ("stages", C.c_int32), ("nDirect", C.c_int32), ("nIndirect", C.c_int32), ("nPost", C.c_int32),
+                ("streamMemOps", C.c_int32), ("pad_", C.c_int32), ("peerCopies", C.c_uint64), ("peerBytes", C.c_uint64)]
+
+
+class PipelineLayout(C.Structure):   # eid_pipeline_layout
+    _fields_ = [("nDirect", C.c_int32), ("nIndirect", C.c_int32), ("nPost", C.c_int32), ("stages", C.c_int32),
+                ("index", C.c_int32), ("count", C.c_int32), ("y0", C.c_uint32), ("y1", C.c_uint32), ("paddedHeight", C.c_uint32)]
+
+
+STAGE_DIRECT, STAGE_INDIRECT, STAGE_POST = 1, 2, 4
 
 
 # eid_scene_table

@@ -52,6 +52,8 @@ struct FrameParams {
   float* tempDR;                          // tempDirectResv (spatial reuse), pitch st.size.x; one buffer, persists across frames
   float4* spCont;                         // spatial reuse: what k_direct_spatial needs of a pixel's State, 3 planes of pitch*allocH
   float4* dirA; float4* dirB; float4* indA; float4* indB;
+  const float4* indIn;                    // what the indirect denoiser / compose read as the pre-denoise indirect image: indA, or (stage pipeline, post ranks) the
+                                          // per-parity buffer the indirect ranks write into over NVLink
   float4* geomPos; float4* geomNrm;       // denoiser geometry planes (full res): pos.xyz + hash bits / normal.xyz
   float4* geomPosH; float4* geomNrmH;     // same at quarter res (pitch/2), see k_denoise_prep
   EnvView env;                            // HDR lat-long map + alias table, or the constant environment

@@ -17,12 +17,11 @@
 // post stages) so that a moving camera stays bit-identical to the single-GPU frame.
 #include <dlfcn.h>
 #include <cstdlib>
-#include "renderer.h"
+#include "group.h"
 
 namespace {
 
 struct NcclId { char internal[128]; };   // ncclUniqueId
-typedef void* NcclComm;
 struct Nccl {
   void* lib = nullptr;
   int (*GetUniqueId)(NcclId*) = nullptr;
@@ -63,27 +62,6 @@ Nccl& nccl() {
   } while (0)
 
 }  // namespace
-
-struct eid_group {
-  eid_renderer* r = nullptr;
-  int rank = 0, world = 1;
-  NcclComm comm = nullptr;
-  cudaStream_t cs = nullptr;                       // communication stream
-  cudaEvent_t evA = nullptr, evB = nullptr, evX = nullptr, evC = nullptr, evD = nullptr, evH = nullptr, evA2 = nullptr, evPrep = nullptr, evK3 = nullptr;
-  int post = 1;                                    // 1: denoise + compose per band (default), 0: replicated on every rank
-  int history = 2;                                 // reservoir history across band edges: 0 never, 1 every frame (behind the post stages), 2 lazily when the camera moved
-  int gatherFinal = 1;                             // exchange C
-  bool historyComplete = false;                    // the LAST reservoirs of the next frame are complete on this rank
-  bool histPending = false, finalPending = false;  // the render stream has not yet been ordered after the eager history gather / exchange C
-  cudaEvent_t evHist = nullptr;
-  uint32_t bandRows = 0;
-  // host delivery of this rank's band
-  cudaStream_t copyStream = nullptr;
-  cudaEvent_t evFrameDone = nullptr, evCopyDone = nullptr;
-  float4* staging[2] = {nullptr, nullptr};
-  bool copyPending = false;
-  unsigned long long collectives = 0;              // NCCL launches since creation
-};
 
 static void gatherList(eid_group* g, const int* which, int n) {
   if (g->world == 1 || n == 0) return;
@@ -226,7 +204,10 @@ int eid_group_create(eid_group** out, eid_renderer* r, int rank, int world, cons
 void eid_group_destroy(eid_group* g) {
   if (!g) return;
   if (g->r) cudaSetDevice(g->r->device);
+  if (g->r && g->r->stream) cudaStreamSynchronize(g->r->stream);
+  if (g->r && g->r->copyStream) cudaStreamSynchronize(g->r->copyStream);
   if (g->cs) cudaStreamSynchronize(g->cs);
+  if (g->pipe) pipelineDestroy(g);
   if (g->r && g->r->groupStream == g->cs) g->r->groupStream = nullptr;
   if (g->copyStream) { cudaStreamSynchronize(g->copyStream); cudaStreamDestroy(g->copyStream); }
   if (g->comm) nccl().CommDestroy(g->comm);
@@ -240,6 +221,7 @@ int eid_group_set_mode(eid_group* g, int post_sharded, int history, int gather_f
   EID_TRY
   if (!g) raise(EID_ERR_INVALID, "eid_group_set_mode: null group");
   if (history < 0 || history > 2) raise(EID_ERR_INVALID, "eid_group_set_mode: history 0 (never), 1 (every frame) or 2 (when the camera moved)");
+  if (g->pipe) { g->history = history; return EID_OK; }     // a stage pipeline has no post / gather modes: only the history policy applies
   g->post = post_sharded != 0; g->history = history; g->gatherFinal = gather_final != 0;
   g->historyComplete = false;
   return EID_OK;
@@ -250,6 +232,7 @@ int eid_group_run(eid_group* g, const RtxState* state, int frames) {
   EID_TRY
   if (!g || !state) raise(EID_ERR_INVALID, "eid_group_run: null argument");
   CUDA_CHECK(cudaSetDevice(g->r->device));
+  if (g->pipe) { pipelineFrame(g, *state, frames, true); return EID_OK; }
   groupFrame(g, *state, frames, g->gatherFinal != 0);
   CUDA_CHECK(cudaGetLastError());
   return EID_OK;
@@ -266,9 +249,17 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
   CUDA_CHECK(cudaSetDevice(r->device));
   ensureCopyStream(r);
   if (cam) r->scene->host.camera = *cam;
-  groupFrame(g, *state, frames, false);             // (fillParams waits for the copy that read this parity's images two frames ago)
-  const uint32_t y0 = g->world > 1 ? (uint32_t)g->rank * g->bandRows : 0;
-  const uint32_t y1 = std::min<uint32_t>(y0 + g->bandRows, (uint32_t)state->size.y);
+  uint32_t y0 = 0, y1 = 0;
+  if (g->pipe) {
+    // stage pipeline: only the post ranks hold composed rows; the acknowledgement that lets the direct ranks overwrite this parity's
+    // landing buffers follows the device-to-host copy
+    pipelineFrame(g, *state, frames, false);
+    if (pipelineDelivers(g, &y0, &y1)) y1 = std::min<uint32_t>(y1, (uint32_t)state->size.y); else y1 = y0 = 0;
+  } else {
+    groupFrame(g, *state, frames, false);           // (fillParams waits for the copy that read this parity's images two frames ago)
+    y0 = g->world > 1 ? (uint32_t)g->rank * g->bandRows : 0;
+    y1 = std::min<uint32_t>(y0 + g->bandRows, (uint32_t)state->size.y);
+  }
   if (y1 > y0) {
     // the band is copied IN PLACE from this parity's result images on the renderer's copy stream, behind the next frame (other parity)
     const int set = r->lastSet;
@@ -280,7 +271,8 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
     if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)indirect_host + (size_t)y0 * rowBytes, rowBytes, r->indirectImg + first, (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, r->copyStream));
     CUDA_CHECK(cudaEventRecord(r->evCopyDone2[set], r->copyStream));
     r->copyPending2[set] = true;
-  }
+    if (g->pipe) pipelineAck(g, r->copyStream);
+  } else if (g->pipe) pipelineAck(g, r->stream);
   return EID_OK;
   EID_CATCH
 }
@@ -308,6 +300,7 @@ int eid_group_get_info(eid_group* g, eid_group_info* out) {
   EID_TRY
   if (!g || !out) raise(EID_ERR_INVALID, "eid_group_get_info: null argument");
   memset(out, 0, sizeof(*out));
+  if (g->pipe) { pipelineInfo(g, out); return EID_OK; }
   out->rank = g->rank; out->world = g->world; out->bandRows = g->bandRows;
   out->y0 = g->world > 1 ? (uint32_t)g->rank * g->bandRows : 0; out->y1 = out->y0 + g->bandRows;
   out->collectives = g->collectives;

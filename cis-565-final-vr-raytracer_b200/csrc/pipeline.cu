@@ -1,0 +1,529 @@
+// pipeline.cu — eid_group as a STAGE PIPELINE over NVLink peer memory (no reference analogue: the reference renders on one GPU).
+//
+// Row bands (group.cu) split ONE frame over N GPUs; every band still pays the latency floor of indirect_stage (three dependent ray
+// queries of ~80 us worst-case latency each, whatever the band height) and two or three exchange steps, so the frame rate saturates
+// near 2.2 x at N = 8 (profiles/README.md).  The stages of Renderer::run, however, only depend on their OWN history:
+//
+//     direct_stage(f)    reads  direct_stage(f-1)            (last G-buffer, last direct reservoirs)
+//     indirect_stage(f)  reads  direct_stage(f), indirect_stage(f-1)   (this G-buffer; last indirect reservoirs)
+//     denoise/compose(f) reads  direct_stage(f), indirect_stage(f)     (no history at all)
+//
+// so the N ranks form a pipeline instead: nDirect ranks run direct_stage on row bands, nIndirect ranks run indirect_stage on row
+// bands, nPost ranks run denoise + compose on row bands — each group one frame behind the previous one.  Throughput is set by the
+// slowest STAGE (e.g. 3 | 3 | 2 ranks at N = 8), not by the sum of all stages plus exchanges; every frame is bit-identical to
+// eid_renderer_run on one GPU (the stages run the same kernels on the same buffers; rows travel verbatim).  Latency per frame grows
+// by the two hand-overs; the band mode of group.cu stays the low-latency alternative.
+//
+// Transport: no collective.  At creation every rank exports its buffers as CUDA IPC handles through a rendezvous file in /dev/shm
+// (keyed by the group's 128-byte id) and maps its peers' buffers.  A producer writes the rows a consumer needs STRAIGHT INTO THE
+// CONSUMER'S BUFFERS with peer copies on its communication stream (copy engines over NVLink / NVSwitch: no SM is taken from the
+// kernels), then raises a sequence flag in the consumer's memory; the consumer's stream waits for the flag with a stream memory
+// operation (cuStreamWaitValue32: no host round trip, no spinning SM).  Back-pressure is the same mechanism in the other direction:
+// a consumer acknowledges a frame once it has read it, and a producer only overwrites a (per-parity) buffer after that.
+//
+//   direct rank d  --[G-buffer rows, pre-denoise direct rows, K2's gathered temporal lookups]-->  indirect ranks, post ranks
+//   indirect rank  --[quarter-res pre-denoise indirect rows]-->  post ranks
+//   same-stage ranks exchange their band of the G-buffer / reservoirs only when temporal reuse can cross a band edge (moving camera)
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <algorithm>
+#include <string>
+#include <cuda.h>
+#include "group.h"
+
+namespace {
+
+constexpr int MAXW = 16;
+enum { ROLE_D = EID_STAGE_DIRECT, ROLE_I = EID_STAGE_INDIRECT, ROLE_P = EID_STAGE_POST };
+enum FlagKind { F_READY_D, F_READY_I, F_READY_H, F_ACK_D, F_ACK_I, F_ACK_H, F_KINDS };
+enum BufIdx { B_G0, B_G1, B_DIR0, B_DIR1, B_K2G0, B_K2G1, B_K2MV0, B_K2MV1, B_INDIN0, B_INDIN1, B_DR0, B_DR1, B_IR0, B_IR1, B_FLAGS, B_COUNT };
+
+struct RankLayout { int role = 0, index = 0, count = 1; uint32_t y0 = 0, y1 = 0; };
+
+// ---- layout: who runs what on which rows ------------------------------------------------------------------------------------
+uint32_t bandRowsOf(uint32_t height, int n) { return ((height + n - 1) / n + 7) / 8 * 8; }
+
+void stageCounts(int world, int& nD, int& nI, int& nP) {
+  if (nD == 0 && nI == 0 && nP == 0) {
+    // default split by the measured stage times of the 1080p workload (direct 0.89 ms, indirect 0.60 ms with a ~0.28 ms floor per band,
+    // denoise + compose 0.48 ms): 2: 1|-|1 (post rank also traces the indirect stage), 3: 1|1|1, 4: 2|1|1, 5: 2|2|1, 8: 3|3|2
+    nP = std::max(1, world / 4);
+    nD = (world - nP + 1) / 2;
+    nI = world - nP - nD;
+  }
+  if (nD < 1 || nP < 1 || nI < 0 || nD + nI + nP != world) raise(EID_ERR_INVALID, "pipeline stages %d | %d | %d do not add up to %d ranks (direct >= 1, post >= 1)", nD, nI, nP, world);
+  if (nI == 0 && nP != 1) raise(EID_ERR_INVALID, "pipeline without indirect ranks needs exactly one post rank (it runs indirect_stage, denoise and compose on the whole frame)");
+  if (world > MAXW) raise(EID_ERR_INVALID, "pipeline supports at most %d ranks", MAXW);
+}
+
+RankLayout rankLayout(uint32_t height, int rank, int nD, int nI, int nP) {
+  RankLayout L;
+  if (rank < nD) { L.role = ROLE_D; L.index = rank; L.count = nD; }
+  else if (rank < nD + nI) { L.role = ROLE_I; L.index = rank - nD; L.count = nI; }
+  else { L.role = nI == 0 ? (ROLE_I | ROLE_P) : ROLE_P; L.index = rank - nD - nI; L.count = nP; }
+  const uint32_t b = bandRowsOf(height, L.count);
+  L.y0 = (uint32_t)L.index * b; L.y1 = L.y0 + b;
+  return L;
+}
+uint32_t paddedHeightOf(uint32_t height, int nD, int nI, int nP) {
+  uint32_t p = (height + 7) / 8 * 8;
+  for (int n : {nD, nI, nP}) if (n > 0) p = std::max(p, bandRowsOf(height, n) * (uint32_t)n);
+  return p;
+}
+
+// rows [a, b) of a buffer that a consumer needs from the producers of a stage, in the buffer's own row units
+struct Range { int a = 0, b = 0; bool empty() const { return b <= a; } };
+Range clampRange(int a, int b, int lo, int hi) { Range r; r.a = std::max(a, lo); r.b = std::min(b, hi); return r; }
+Range intersect(Range x, int a, int b) { return clampRange(x.a, x.b, a, b); }
+// what a consumer needs of direct_stage's outputs: G-buffer rows, pre-denoise direct rows (full res), gathered lookups (quarter-res rows)
+struct DirectNeeds { Range g, d, q; };
+DirectNeeds directNeeds(const RankLayout& c, int padded) {
+  DirectNeeds n;
+  if ((c.role & ROLE_I) && (c.role & ROLE_P)) { n.g = n.d = clampRange(0, padded, 0, padded); n.q = clampRange(0, padded / 2, 0, padded / 2); }
+  else if (c.role & ROLE_I) { n.g = clampRange((int)c.y0, (int)c.y1, 0, padded); n.q = clampRange((int)c.y0 / 2, (int)c.y1 / 2, 0, padded / 2); }
+  else if (c.role & ROLE_P) {
+    // denoise_prep evaluates the geometry planes on the band +- 124 rows (render.cu: stagePrep), A-Trous level 0 of the direct image on the
+    // band +- 28 rows with taps +- 2 rows beyond
+    n.g = clampRange((int)c.y0 - 124, (int)c.y1 + 124, 0, padded);
+    n.d = clampRange((int)c.y0 - 32, (int)c.y1 + 32, 0, padded);
+  }
+  return n;
+}
+// quarter-res rows of the pre-denoise indirect image a post rank needs: band / 2 +- 60 rows (level 0) + 2 rows of taps
+Range indirectNeeds(const RankLayout& c, int padded) {
+  if (!(c.role & ROLE_P) || (c.role & ROLE_I)) return Range{};
+  return clampRange((int)c.y0 / 2 - 64, (int)c.y1 / 2 + 64, 0, padded / 2);
+}
+
+// ---- rendezvous through a file in /dev/shm ----------------------------------------------------------------------------------------
+struct ShmBuf { cudaIpcMemHandle_t h; unsigned long long offset, bytes; };
+struct ShmRank {
+  uint32_t ready, opened, closed, pad;
+  int32_t pid, device;
+  uint32_t width, height;
+  ShmBuf buf[B_COUNT];
+};
+struct ShmHdr { ShmRank ranks[MAXW]; };
+
+double nowSec() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+uint32_t loadAcq(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+void storeRel(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+
+// driver-API entry points resolved through the runtime (libeidola.so does not link libcuda)
+typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*AddrRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+void* driverEntry(const char* name) {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+  if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+  return f;
+}
+
+__global__ void k_flag_set(uint32_t* flag, uint32_t value) {       // release: everything this stream did before is visible before the flag
+  __threadfence_system();
+  *(volatile uint32_t*)flag = value;
+}
+__global__ void k_flag_wait(const uint32_t* flag, uint32_t value) {   // fallback when stream memory operations are unavailable
+  while ((int32_t)(*(volatile const uint32_t*)flag - value) < 0) __nanosleep(200);
+  __threadfence_system();
+}
+
+}  // namespace
+
+struct EidPipe {
+  int nD = 0, nI = 0, nP = 0;
+  uint32_t height = 0, padded = 0;
+  RankLayout me;
+  RankLayout ranks[MAXW];
+  void* peer[MAXW][B_COUNT] = {};          // peer[j][b]: rank j's buffer b in THIS process's address space (own rank: the local pointers)
+  std::vector<void*> openedBases;
+  std::vector<std::pair<std::string, void*>> openedByHandle;
+  uint32_t* flags = nullptr;               // local: [kind][peer]
+  uint32_t seq = 0;                        // frames enqueued so far
+  int lastSeqOfParity[2] = {-1, -1};
+  cudaEvent_t evStage = nullptr, evPush[2] = {nullptr, nullptr}, evPushI = nullptr, evPrep = nullptr, evK3 = nullptr, evFork = nullptr;
+  bool pushValid[2] = {false, false}, pushIValid = false;
+  bool historyComplete = false;            // the LAST buffers of the next frame already hold the peers' rows
+  bool ackPending = false;                 // eid_group_run: the frame's acknowledgement is enqueued with the NEXT frame (see pipelineFrame)
+  ShmHdr* shm = nullptr;
+  std::string shmPath;
+  WaitValueFn waitValue = nullptr;
+  unsigned long long peerCopies = 0, peerBytes = 0;
+};
+
+namespace {
+
+uint32_t* flagOf(EidPipe* p, int owner, int kind, int from) { return (uint32_t*)p->peer[owner][B_FLAGS] + kind * MAXW + from; }
+
+void waitFlag(eid_group* g, cudaStream_t st, int kind, int from, uint32_t value) {
+  EidPipe* p = g->pipe;
+  uint32_t* f = p->flags + kind * MAXW + from;
+  if (p->waitValue) {
+    const CUresult e = p->waitValue((CUstream)st, (CUdeviceptr)(uintptr_t)f, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (e == CUDA_SUCCESS) return;
+    p->waitValue = nullptr;                // not supported on this device / driver: fall back to the polling kernel for good
+  }
+  k_flag_wait<<<1, 1, 0, st>>>(f, value);
+}
+void setFlag(eid_group* g, cudaStream_t st, int owner, int kind, uint32_t value) {
+  k_flag_set<<<1, 1, 0, st>>>(flagOf(g->pipe, owner, kind, g->rank), value);
+}
+void pushRows(eid_group* g, int to, int buf, size_t rowBytes, Range r) {
+  if (r.empty()) return;
+  EidPipe* p = g->pipe;
+  const size_t off = (size_t)r.a * rowBytes, bytes = (size_t)(r.b - r.a) * rowBytes;
+  CUDA_CHECK(cudaMemcpyAsync((char*)p->peer[to][buf] + off, (const char*)p->peer[g->rank][buf] + off, bytes, cudaMemcpyDeviceToDevice, g->cs));
+  p->peerCopies++; p->peerBytes += bytes;
+}
+// a local buffer pushed under another index at the consumer (indA -> the consumer's per-parity indIn)
+void pushRowsFrom(eid_group* g, int to, int dstBuf, const void* src, size_t rowBytes, Range r) {
+  if (r.empty()) return;
+  EidPipe* p = g->pipe;
+  const size_t off = (size_t)r.a * rowBytes, bytes = (size_t)(r.b - r.a) * rowBytes;
+  CUDA_CHECK(cudaMemcpyAsync((char*)p->peer[to][dstBuf] + off, (const char*)src + off, bytes, cudaMemcpyDeviceToDevice, g->cs));
+  p->peerCopies++; p->peerBytes += bytes;
+}
+
+bool temporalReuse(const RtxState& st) { return st.ReSTIRState == eTemporal || st.ReSTIRState == eSpatiotemporal; }
+bool cameraMoved(const SceneCamera& c) { return memcmp(&c.projView, &c.lastProjView, sizeof(c.projView)) != 0; }
+
+// Same-stage history (moving camera): this rank's band of the buffers the NEXT frame reprojects into goes to the other ranks of the stage.
+// `last` = false: the buffers this frame wrote (eager, behind the stage); true: the LAST buffers of this frame (lazy, before the stage).
+void pushHistory(eid_group* g, const FrameParams& P, int set, bool last, uint32_t readyValue) {
+  EidPipe* p = g->pipe;
+  const RankLayout& me = p->me;
+  const int thisIdx = last ? set : !set;                      // fillParams: last* = [set], this* = [!set]
+  const size_t sw = (size_t)P.st.size.x;
+  for (int j = 0; j < g->world; ++j) {
+    if (j == g->rank || p->ranks[j].role != me.role) continue;
+    // the peer read these rows' buffer (as `last`) in every frame up to the previous one: wait until it has finished that stage
+    if (p->seq > 0) waitFlag(g, g->cs, F_ACK_H, j, p->seq);
+    if (me.role & ROLE_D) {
+      pushRows(g, j, B_G0 + thisIdx, (size_t)P.pitch * 16, Range{(int)me.y0, (int)me.y1});
+      pushRows(g, j, B_DR0 + thisIdx, sw * sizeof(DirectReservoir), Range{(int)me.y0, (int)me.y1});
+    } else {
+      pushRows(g, j, B_IR0 + thisIdx, (sw / 2) * sizeof(IndirectReservoir), Range{(int)me.y0 / 2, (int)me.y1 / 2});
+    }
+    setFlag(g, g->cs, j, F_READY_H, readyValue);
+  }
+}
+
+}  // namespace
+
+// ---- the frame --------------------------------------------------------------------------------------------------------------
+void pipelineAck(eid_group* g, cudaStream_t st) {
+  EidPipe* p = g->pipe;
+  const uint32_t v = p->seq;               // = index of the frame just enqueued + 1
+  if (p->me.role & ROLE_P) {
+    for (int j = 0; j < g->world; ++j) {
+      const int role = p->ranks[j].role;
+      if (role == ROLE_D) {
+        const DirectNeeds n = directNeeds(p->me, (int)p->padded);
+        const RankLayout& d = p->ranks[j];
+        if (!intersect(n.g, (int)d.y0, (int)d.y1).empty() || !intersect(n.d, (int)d.y0, (int)d.y1).empty()) setFlag(g, st, j, F_ACK_D, v);
+      } else if (role == ROLE_I) {
+        const RankLayout& i = p->ranks[j];
+        if (!intersect(indirectNeeds(p->me, (int)p->padded), (int)i.y0 / 2, (int)i.y1 / 2).empty()) setFlag(g, st, j, F_ACK_I, v);
+      }
+    }
+  }
+}
+
+void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
+  eid_renderer* r = g->r;
+  EidPipe* p = g->pipe;
+  if (r->variant) raise(EID_ERR_UNSUPPORTED, "the stage pipeline runs the reference's live shaders only (eid_renderer_set_variant must be 0)");
+  if (st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal) {
+    if (p->nD > 1) raise(EID_ERR_UNSUPPORTED, "spatial reuse across the bands of several direct ranks is not built for the stage pipeline (use one direct rank, or the band mode of eid_group_create)");
+  }
+  if ((uint32_t)st.size.y > p->height) raise(EID_ERR_INVALID, "RtxState.size.y %d exceeds the height %u the pipeline was laid out for", st.size.y, p->height);
+  // A post rank's composed images live in the buffers its producers write into, so the acknowledgement that frees them for the frame
+  // after next is only enqueued now, with the next frame: until then eid_renderer_read / get_outputs see the finished frame.  (Stream
+  // order is unchanged — the acknowledgement follows that frame's compose —, and a host that enqueues ahead loses nothing.)
+  if (p->ackPending) { pipelineAck(g, r->stream); p->ackPending = false; }
+  FrameParams P;
+  strictOrder(r);
+  fillParams(r, st, frames, P);
+  if (p->me.role & ROLE_I) P.indIn = P.indA;                  // this rank traces indirect_stage itself: its denoiser reads the local image
+  const int set = r->lastSet;
+  const uint32_t n = p->seq;                                  // index of this frame
+  const int prev = p->lastSeqOfParity[set];                   // last frame that used this parity's buffers
+  const RankLayout& me = p->me;
+  const int padded = (int)p->padded;
+  const bool temporal = temporalReuse(st);
+  const int stagePeers = me.count;
+  const bool needHistory = stagePeers > 1 && temporal && g->history != 0 && (g->history == 1 || cameraMoved(P.cam)) && !(me.role & ROLE_P);
+  const bool eagerHistory = stagePeers > 1 && temporal && (g->history == 1 || (g->history == 2 && cameraMoved(P.cam))) && !(me.role & ROLE_P);
+  const size_t rowG = (size_t)P.pitch * 16;
+
+  if (me.role == ROLE_D) {
+    // K1 rewrites this parity's G-buffer / direct image / gathered lookups: the peer copies of the frame that used them last must have drained
+    if (p->pushValid[set]) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPush[set], 0));
+    if (needHistory) {
+      if (!p->historyComplete) {                              // lazily: first frame, or the camera started moving
+        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+        pushHistory(g, P, set, true, n + 1);
+        // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
+        CUDA_CHECK(cudaEventRecord(p->evPrep, g->cs)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
+      }
+      for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) waitFlag(g, r->stream, F_READY_H, j, n + 1);
+    }
+    beginFrame(r);
+    stageDirect(r, P, r->stream);
+    if (stagePeers > 1) for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) setFlag(g, r->stream, j, F_ACK_H, n + 1);
+    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+    for (int j = 0; j < g->world; ++j) {
+      const RankLayout& c = p->ranks[j];
+      if (c.role == ROLE_D) continue;
+      const DirectNeeds need = directNeeds(c, padded);
+      const Range rg = intersect(need.g, (int)me.y0, (int)me.y1), rd = intersect(need.d, (int)me.y0, (int)me.y1), rq = intersect(need.q, (int)me.y0 / 2, (int)me.y1 / 2);
+      if (rg.empty() && rd.empty() && rq.empty()) continue;
+      if (prev >= 0) waitFlag(g, g->cs, F_ACK_D, j, (uint32_t)prev + 1);
+      pushRows(g, j, B_G0 + !set, rowG, rg);
+      pushRows(g, j, B_DIR0 + set, rowG, rd);
+      pushRows(g, j, B_K2G0 + set, (size_t)(P.pitch / 2) * 16, rq);
+      pushRows(g, j, B_K2MV0 + set, (size_t)(P.pitch / 2) * 4, rq);
+      setFlag(g, g->cs, j, F_READY_D, n + 1);
+    }
+    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
+    CUDA_CHECK(cudaEventRecord(p->evPush[set], g->cs)); p->pushValid[set] = true;
+    endFrame(r);
+  } else if (me.role == ROLE_I) {
+    if (p->pushIValid) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushI, 0));     // indA is one buffer: its last peer copy must have drained
+    if (needHistory) {
+      if (!p->historyComplete) {
+        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+        pushHistory(g, P, set, true, n + 1);
+        // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
+        CUDA_CHECK(cudaEventRecord(p->evPrep, g->cs)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
+      }
+      for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_I) waitFlag(g, r->stream, F_READY_H, j, n + 1);
+    }
+    const DirectNeeds need = directNeeds(me, padded);
+    for (int j = 0; j < g->world; ++j) {
+      const RankLayout& d = p->ranks[j];
+      if (d.role != ROLE_D) continue;
+      if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
+      waitFlag(g, r->stream, F_READY_D, j, n + 1);
+    }
+    beginFrame(r);
+    stageIndirect(r, P, r->stream);
+    for (int j = 0; j < g->world; ++j) {
+      const RankLayout& d = p->ranks[j];
+      if (d.role == ROLE_D && !(intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty())) setFlag(g, r->stream, j, F_ACK_D, n + 1);
+      if (d.role == ROLE_I && j != g->rank) setFlag(g, r->stream, j, F_ACK_H, n + 1);
+    }
+    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+    for (int j = 0; j < g->world; ++j) {
+      const RankLayout& c = p->ranks[j];
+      const Range ri = intersect(indirectNeeds(c, padded), (int)me.y0 / 2, (int)me.y1 / 2);
+      if (ri.empty()) continue;
+      if (prev >= 0) waitFlag(g, g->cs, F_ACK_I, j, (uint32_t)prev + 1);
+      pushRowsFrom(g, j, B_INDIN0 + set, P.indA, rowG, ri);              // quarter-res rows at the full-res pitch (renderer.cpp:267-281)
+      setFlag(g, g->cs, j, F_READY_I, n + 1);
+    }
+    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
+    CUDA_CHECK(cudaEventRecord(p->evPushI, g->cs)); p->pushIValid = true;
+    endFrame(r);
+  } else {
+    // post rank (denoise + compose on its band), or — without indirect ranks — indirect_stage + denoise + compose on the whole frame
+    const bool alsoIndirect = (me.role & ROLE_I) != 0;
+    const DirectNeeds need = directNeeds(me, padded);
+    for (int j = 0; j < g->world; ++j) {
+      const RankLayout& d = p->ranks[j];
+      if (d.role != ROLE_D) continue;
+      if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.d, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
+      waitFlag(g, r->stream, F_READY_D, j, n + 1);
+    }
+    beginFrame(r);
+    const PostLayout L = postLayout(P, me.count > 1);
+    markStart(r, EID_K_DENOISE_DIRECT, r->stream);
+    stagePrep(r, P, L, r->stream);
+    CUDA_CHECK(cudaEventRecord(p->evFork, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(r->aux, p->evFork, 0));
+    stageDenoiseDirect(r, P, L, r->aux);
+    markStop(r, EID_K_DENOISE_DIRECT, r->aux);
+    CUDA_CHECK(cudaEventRecord(p->evK3, r->aux));
+    if (alsoIndirect) stageIndirect(r, P, r->stream);
+    else {
+      const Range ni = indirectNeeds(me, padded);
+      for (int j = 0; j < g->world; ++j) {
+        const RankLayout& i = p->ranks[j];
+        if (i.role == ROLE_I && !intersect(ni, (int)i.y0 / 2, (int)i.y1 / 2).empty()) waitFlag(g, r->stream, F_READY_I, j, n + 1);
+      }
+    }
+    r->postStarted = true;
+    markStart(r, EID_K_DENOISE_INDIRECT, r->stream);
+    stageDenoiseIndirect(r, P, L, r->stream);
+    markStop(r, EID_K_DENOISE_INDIRECT, r->stream);
+    CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evK3, 0));
+    stageCompose(r, P, L, r->stream);
+    endFrame(r);
+  }
+  p->lastSeqOfParity[set] = (int)n;
+  p->seq = n + 1;
+  if (ackNow) p->ackPending = true;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+bool pipelineDelivers(eid_group* g, uint32_t* y0, uint32_t* y1) {
+  EidPipe* p = g->pipe;
+  if (!(p->me.role & ROLE_P)) return false;
+  *y0 = p->me.y0; *y1 = p->me.y1;
+  return true;
+}
+
+void pipelineInfo(eid_group* g, eid_group_info* out) {
+  EidPipe* p = g->pipe;
+  out->rank = g->rank; out->world = g->world;
+  out->y0 = p->me.y0; out->y1 = p->me.y1; out->bandRows = p->me.y1 - p->me.y0;
+  out->collectives = 0;
+  out->stages = p->me.role; out->nDirect = p->nD; out->nIndirect = p->nI; out->nPost = p->nP;
+  out->peerCopies = p->peerCopies; out->peerBytes = p->peerBytes;
+  out->streamMemOps = p->waitValue ? 1 : 0;
+}
+
+void pipelineDestroy(eid_group* g) {
+  EidPipe* p = g->pipe;
+  if (!p) return;
+  // nobody may free memory a peer can still write a flag into: every rank announces that its streams have drained and waits for the others
+  if (p->shm) {
+    storeRel(&p->shm->ranks[g->rank].closed, 1u);
+    const double t0 = nowSec();
+    for (int j = 0; j < g->world; ++j) while (!loadAcq(&p->shm->ranks[j].closed) && nowSec() - t0 < 20.0) usleep(200);
+  }
+  for (void* b : p->openedBases) cudaIpcCloseMemHandle(b);
+  for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI, p->evPrep, p->evK3, p->evFork}) if (e) cudaEventDestroy(e);
+  cudaFree(p->flags);
+  if (p->shm) munmap(p->shm, sizeof(ShmHdr));
+  if (!p->shmPath.empty() && g->rank == 0) unlink(p->shmPath.c_str());
+  delete p;
+  g->pipe = nullptr;
+}
+
+extern "C" {
+
+int eid_group_pipeline_layout(uint32_t height, int world, int rank, int n_direct, int n_indirect, int n_post, eid_pipeline_layout* out) {
+  EID_TRY
+  if (!out || !height || world < 2 || rank < 0 || rank >= world) raise(EID_ERR_INVALID, "eid_group_pipeline_layout: bad height / world (>= 2) / rank, or null output");
+  int nD = n_direct, nI = n_indirect, nP = n_post;
+  stageCounts(world, nD, nI, nP);
+  const RankLayout L = rankLayout(height, rank, nD, nI, nP);
+  memset(out, 0, sizeof(*out));
+  out->nDirect = nD; out->nIndirect = nI; out->nPost = nP;
+  out->stages = L.role; out->index = L.index; out->count = L.count; out->y0 = L.y0; out->y1 = L.y1;
+  out->paddedHeight = paddedHeightOf(height, nD, nI, nP);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_group_random_id(void* id128) {
+  EID_TRY
+  if (!id128) raise(EID_ERR_INVALID, "eid_group_random_id: null argument");
+  const int fd = open("/dev/urandom", O_RDONLY);
+  if (fd < 0 || read(fd, id128, 128) != 128) { if (fd >= 0) close(fd); raise(EID_ERR_IO, "cannot read /dev/urandom"); }
+  close(fd);
+  return EID_OK;
+  EID_CATCH
+}
+
+int eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int world, const void* id128, uint32_t height, int n_direct, int n_indirect, int n_post) {
+  EID_TRY
+  if (!out || !r || !id128) raise(EID_ERR_INVALID, "eid_group_create_pipeline: null argument");
+  if (world < 2 || rank < 0 || rank >= world) raise(EID_ERR_INVALID, "eid_group_create_pipeline: rank %d outside world %d (a pipeline needs at least 2 ranks)", rank, world);
+  int nD = n_direct, nI = n_indirect, nP = n_post;
+  stageCounts(world, nD, nI, nP);
+  const uint32_t padded = paddedHeightOf(height, nD, nI, nP);
+  if (!height || r->height < padded) raise(EID_ERR_INVALID, "eid_group_create_pipeline: the renderer's allocation height %u is below the padded height %u of this layout (eid_group_pipeline_layout)", r->height, padded);
+  eid_group* g = new eid_group();
+  EidPipe* p = new EidPipe();
+  g->pipe = p;
+  try {
+    g->r = r; g->rank = rank; g->world = world;
+    p->nD = nD; p->nI = nI; p->nP = nP; p->height = height; p->padded = padded;
+    for (int j = 0; j < world; ++j) p->ranks[j] = rankLayout(height, j, nD, nI, nP);
+    p->me = p->ranks[rank];
+    g->bandRows = p->me.y1 - p->me.y0;
+    CUDA_CHECK(cudaSetDevice(r->device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking));
+    r->groupStream = g->cs;
+    for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI, &p->evPrep, &p->evK3, &p->evFork}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (eid_renderer_set_band(r, p->me.y0, std::min(p->me.y1, r->height)) != EID_OK) raise(EID_ERR_INVALID, "%s", eid_last_error());
+    // per-parity landing buffers of the pre-denoise indirect image (post ranks read them in place of denoiseIndTempA)
+    const size_t nImg = (size_t)r->width * r->height * 16 + (size_t)17 * r->width * 16;
+    for (int k = 0; k < 2; ++k) if (!r->indIn[k]) { CUDA_CHECK(cudaMalloc((void**)&r->indIn[k], nImg)); CUDA_CHECK(cudaMemsetAsync(r->indIn[k], 0, nImg, r->stream)); }
+    CUDA_CHECK(cudaMalloc((void**)&p->flags, F_KINDS * MAXW * sizeof(uint32_t)));
+    CUDA_CHECK(cudaMemsetAsync(p->flags, 0, F_KINDS * MAXW * sizeof(uint32_t), r->stream));
+    CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    p->waitValue = getenv("EID_PIPE_NO_MEMOPS") ? nullptr : (WaitValueFn)driverEntry("cuStreamWaitValue32");
+    AddrRangeFn addrRange = (AddrRangeFn)driverEntry("cuMemGetAddressRange");
+
+    void* local[B_COUNT] = {r->gbuffer[0], r->gbuffer[1], r->directImgs[0], r->directImgs[1], r->k2G[0], r->k2G[1], r->k2Mv[0], r->k2Mv[1],
+                            r->indIn[0], r->indIn[1], r->directResv[0], r->directResv[1], r->indirectResv[0], r->indirectResv[1], p->flags};
+    for (int b = 0; b < B_COUNT; ++b) p->peer[rank][b] = local[b];
+
+    // ---- rendezvous: publish this rank's IPC handles, wait for everybody's, map them ----
+    char name[64];
+    const unsigned char* id = (const unsigned char*)id128;
+    snprintf(name, sizeof(name), "/dev/shm/eidola_pipe_%02x%02x%02x%02x%02x%02x%02x%02x%02x%02x%02x%02x", id[0] ^ id[12], id[1] ^ id[13], id[2] ^ id[14], id[3] ^ id[15],
+             id[4], id[5], id[6], id[7], id[8], id[9], id[10], id[11]);
+    p->shmPath = name;
+    const int fd = open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) raise(EID_ERR_IO, "cannot create the rendezvous file %s", name);
+    if (ftruncate(fd, sizeof(ShmHdr)) != 0) { close(fd); raise(EID_ERR_IO, "cannot size the rendezvous file %s", name); }
+    void* m = mmap(nullptr, sizeof(ShmHdr), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) raise(EID_ERR_IO, "cannot map the rendezvous file %s", name);
+    p->shm = (ShmHdr*)m;
+    ShmRank& mine = p->shm->ranks[rank];
+    mine.pid = (int32_t)getpid(); mine.device = r->device; mine.width = r->width; mine.height = r->height;
+    for (int b = 0; b < B_COUNT; ++b) {
+      CUdeviceptr base = (CUdeviceptr)(uintptr_t)local[b]; size_t size = 0;
+      if (addrRange && addrRange(&base, &size, (CUdeviceptr)(uintptr_t)local[b]) != CUDA_SUCCESS) base = (CUdeviceptr)(uintptr_t)local[b];
+      CUDA_CHECK(cudaIpcGetMemHandle(&mine.buf[b].h, (void*)(uintptr_t)base));
+      mine.buf[b].offset = (unsigned long long)((uintptr_t)local[b] - (uintptr_t)base);
+      mine.buf[b].bytes = size;
+    }
+    storeRel(&mine.ready, 1u);
+    const double t0 = nowSec();
+    const double timeout = getenv("EID_PIPE_TIMEOUT") ? atof(getenv("EID_PIPE_TIMEOUT")) : 120.0;
+    for (int j = 0; j < world; ++j) {
+      while (!loadAcq(&p->shm->ranks[j].ready)) {
+        if (nowSec() - t0 > timeout) raise(EID_ERR_IO, "eid_group_create_pipeline: rank %d did not join within %.0f s", j, timeout);
+        usleep(200);
+      }
+    }
+    for (int j = 0; j < world; ++j) {
+      if (j == rank) continue;
+      const ShmRank& o = p->shm->ranks[j];
+      if (o.pid == mine.pid) raise(EID_ERR_UNSUPPORTED, "the stage pipeline needs one PROCESS per rank (CUDA IPC cannot map memory of the same process)");
+      if (o.width != r->width || o.height != r->height) raise(EID_ERR_INVALID, "rank %d allocated %ux%u, this rank %ux%u: every rank must use the padded height", j, o.width, o.height, r->width, r->height);
+      for (int b = 0; b < B_COUNT; ++b) {
+        const std::string key((const char*)&o.buf[b].h, sizeof(cudaIpcMemHandle_t));
+        void* base = nullptr;
+        for (auto& kv : p->openedByHandle) if (kv.first == key) base = kv.second;
+        if (!base) {
+          CUDA_CHECK(cudaIpcOpenMemHandle(&base, o.buf[b].h, cudaIpcMemLazyEnablePeerAccess));
+          p->openedBases.push_back(base);
+          p->openedByHandle.emplace_back(key, base);
+        }
+        p->peer[j][b] = (char*)base + o.buf[b].offset;
+      }
+    }
+    storeRel(&mine.opened, 1u);
+    for (int j = 0; j < world; ++j) {
+      while (!loadAcq(&p->shm->ranks[j].opened)) {
+        if (nowSec() - t0 > timeout) raise(EID_ERR_IO, "eid_group_create_pipeline: rank %d did not finish mapping within %.0f s", j, timeout);
+        usleep(200);
+      }
+    }
+    if (rank == 0) unlink(name);                              // every rank holds its mapping; the name can go
+  } catch (...) { eid_group_destroy(g); throw; }
+  *out = g;
+  return EID_OK;
+  EID_CATCH
+}
+
+}  // extern "C"

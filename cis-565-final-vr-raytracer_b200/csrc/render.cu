@@ -28,6 +28,7 @@ void eid_renderer::release() {
   frameDoneValid[0] = frameDoneValid[1] = false;
   tmaps.clear();
   for (auto& t : denoiseTemp) { cudaFree(t); t = nullptr; }
+  for (auto& t : indIn) { cudaFree(t); t = nullptr; }
   for (auto& t : geom) { cudaFree(t); t = nullptr; }
 }
 
@@ -122,6 +123,7 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   }
   P.tempDR = r->tempDirectResv; P.spCont = r->spatialCont;
   P.dirA = r->denoiseTemp[0]; P.dirB = r->denoiseTemp[1]; P.indA = r->denoiseTemp[2]; P.indB = r->denoiseTemp[3];
+  P.indIn = r->indIn[set] ? r->indIn[set] : P.indA;
   P.geomPos = r->geom[0]; P.geomNrm = r->geom[1]; P.geomPosH = r->geom[2]; P.geomNrmH = r->geom[3];
   for (int k = 0; k < 3; ++k) P.env.constant[k] = r->env[k];
   P.env.sunSky = r->sunSky;
@@ -352,7 +354,7 @@ void stageDenoiseIndirect(eid_renderer* r, const FrameParams& P, const PostLayou
     r->stats.kernelLaunches[EID_K_DENOISE_INDIRECT]++;
   } else
   if (P.st.denoise > 0 && Wi > 0 && Hi > 0 && L.count > 0) {   // IndA -> IndB -> IndA -> thisIndirect -> IndA -> IndB
-    const float4* src[5] = {P.indA, P.indB, P.indA, P.indirectImg, P.indA};
+    const float4* src[5] = {P.indIn, P.indB, P.indA, P.indirectImg, P.indA};
     float4* dst[5] = {P.indB, P.indA, P.indirectImg, P.indA, P.indB};
     const int halo[5] = {60, 56, 48, 32, 0};
     for (int i = 0; i < 5; ++i) {
@@ -367,7 +369,7 @@ void stageCompose(eid_renderer* r, const FrameParams& P, const PostLayout& L, cu
   markStart(r, EID_K_COMPOSE, st);
   if (L.count > 0) {
     dim3 g((P.st.size.x + 31) / 32, gridRows(L, L.srows, 8));
-    launchCompose(P, g, st, P.st.denoise > 0 ? P.indB : P.indA, L.first, L.stride, L.srows);
+    launchCompose(P, g, st, P.st.denoise > 0 ? P.indB : P.indIn, L.first, L.stride, L.srows);
     r->stats.kernelLaunches[EID_K_COMPOSE]++;
   }
   markStop(r, EID_K_COMPOSE, st);

@@ -42,6 +42,7 @@ struct eid_renderer {
   cudaStream_t groupStream = nullptr;   // communication stream of the eid_group this renderer belongs to (synchronised with the render stream by sync / read / get_stats)
   float* tempDirectResv = nullptr; float4* spatialCont = nullptr;   // spatial reuse (eSpatial / eSpatiotemporal), allocated on first use
   float4* denoiseTemp[4] = {nullptr, nullptr, nullptr, nullptr};
+  float4* indIn[2] = {nullptr, nullptr};        // stage pipeline (pipeline.cu): pre-denoise indirect image received from the indirect ranks, per parity
   float4* geom[4] = {nullptr, nullptr, nullptr, nullptr};   // geomPos, geomNrm, geomPosH, geomNrmH
   float4* displayF = nullptr; uchar4* display8 = nullptr;   // output of the display pass (post.frag), allocated on first use
   float4* mipScratch = nullptr;                             // auto exposure: two ping-pong mip levels + the two 1x1 averages

@@ -407,6 +407,13 @@ typedef struct eid_group_info {
   uint32_t bandRows;
   int32_t  ncclVersion;       /* e.g. 22809 */
   uint64_t collectives;       /* NCCL launches since creation */
+  /* stage pipeline (eid_group_create_pipeline) only; zero otherwise */
+  int32_t  stages;            /* EID_STAGE_* bits this rank runs */
+  int32_t  nDirect, nIndirect, nPost;
+  int32_t  streamMemOps;      /* 1: flags are awaited with cuStreamWaitValue32, 0: with a polling kernel */
+  int32_t  pad_;
+  uint64_t peerCopies;        /* peer (NVLink) copies enqueued since creation, and their bytes */
+  uint64_t peerBytes;
 } eid_group_info;
 EID_API int  eid_group_layout(uint32_t height, int world, int rank, uint32_t* y0, uint32_t* y1, uint32_t* padded_height);
 EID_API int  eid_group_unique_id(void* id128);
@@ -425,6 +432,33 @@ EID_API int  eid_group_render_host_async(eid_group* g, const SceneCamera* cam, c
 EID_API int  eid_group_wait_host(eid_group* g);
 EID_API int  eid_group_sync(eid_group* g);
 EID_API int  eid_group_get_info(eid_group* g, eid_group_info* out);
+
+/* ---- eid_group as a STAGE PIPELINE (csrc/pipeline.cu; new, no reference analogue) -------------------------------------------------------
+ * The stages of Renderer::run (renderer.cpp:154-206) only depend on their own history: direct_stage(f) on direct_stage(f-1), indirect_stage(f)
+ * on direct_stage(f) + indirect_stage(f-1), denoise / compose(f) on the two trace stages of f.  The N ranks therefore form a pipeline:
+ * n_direct ranks run direct_stage on row bands, n_indirect ranks indirect_stage, n_post ranks denoise + compose, each group one frame behind
+ * the one before it — throughput is set by the slowest stage instead of by the whole frame plus exchanges, every frame stays bit-identical
+ * to eid_renderer_run, and latency grows by the two hand-overs (eid_group_create's row bands remain the low-latency mode).
+ * There is no collective: ranks map each other's buffers (CUDA IPC handles, exchanged once through a rendezvous file in /dev/shm that is
+ * keyed by id128), producers write the rows a consumer needs straight into the consumer's buffers with peer copies over NVLink and raise a
+ * sequence flag the consumer's stream waits for (cuStreamWaitValue32); acknowledgements flow back the same way.  One PROCESS per rank.
+ * n_direct = n_indirect = n_post = 0 selects the default split (2: 1|0|1 — the post rank also runs indirect_stage —, 4: 2|1|1, 8: 3|3|2).
+ * Every rank creates its renderer with eid_pipeline_layout.paddedHeight rows; `height` is the rendered height the bands are cut from.
+ * eid_group_run / render_host_async / wait_host / sync / get_info / destroy work on such a group; eid_group_set_mode only uses `history`.
+ * After the last frame, direct ranks hold the G-buffer / direct reservoirs of their band, indirect ranks the indirect reservoirs, post
+ * ranks their band of the two composed images. */
+enum { EID_STAGE_DIRECT = 1, EID_STAGE_INDIRECT = 2, EID_STAGE_POST = 4 };
+typedef struct eid_pipeline_layout {
+  int32_t  nDirect, nIndirect, nPost;
+  int32_t  stages;            /* EID_STAGE_* bits of this rank */
+  int32_t  index, count;      /* this rank's band: `index` of `count` within its stage */
+  uint32_t y0, y1;            /* full-res rows of that band (y1 may exceed the rendered height) */
+  uint32_t paddedHeight;      /* allocation height for eid_renderer_create on every rank */
+} eid_pipeline_layout;
+EID_API int  eid_group_pipeline_layout(uint32_t height, int world, int rank, int n_direct, int n_indirect, int n_post, eid_pipeline_layout* out);
+EID_API int  eid_group_random_id(void* id128);      /* 128 random bytes: a group id that does not need NCCL */
+EID_API int  eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int world, const void* id128, uint32_t height,
+                                       int n_direct, int n_indirect, int n_post);
 
 #ifdef __cplusplus
 }

@@ -490,3 +490,30 @@ def test_gltf_without_scenes_uses_the_parentless_nodes_as_roots(tmp_path):
     info = s.info()
     assert info.nodeCount == 2 and info.triangleInstances == 2
     assert np.allclose(info.bboxMin[:], (10, 0, 0)) and np.allclose(info.bboxMax[:], (11, 1, 1))
+
+
+def test_pipeline_layout_host_logic():
+    """eid_group_pipeline_layout (csrc/pipeline.cu): ranks per stage, bands of multiples of 8 rows that cover the frame, padded height."""
+    from eidola_b200 import abi
+    expect = {2: (1, 0, 1), 3: (1, 1, 1), 4: (2, 1, 1), 5: (2, 2, 1), 8: (3, 3, 2)}
+    for world, (nd, ni, np_) in expect.items():
+        lays = [eid.Group.pipeline_layout(1080, world, r) for r in range(world)]
+        assert all((l.nDirect, l.nIndirect, l.nPost) == (nd, ni, np_) for l in lays)
+        assert len({l.paddedHeight for l in lays}) == 1 and lays[0].paddedHeight >= 1080 and lays[0].paddedHeight % 8 == 0
+        for stage in (abi.STAGE_DIRECT, abi.STAGE_INDIRECT, abi.STAGE_POST):
+            bands = sorted((l.y0, l.y1) for l in lays if l.stages & stage)
+            assert bands, "every stage runs somewhere"
+            assert bands[0][0] == 0 and bands[-1][1] >= 1080 and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            assert all(y0 % 8 == 0 and y1 % 8 == 0 and y1 <= lays[0].paddedHeight for y0, y1 in bands)
+        # without indirect ranks the single post rank traces the indirect stage too
+        if ni == 0:
+            assert lays[-1].stages == abi.STAGE_INDIRECT | abi.STAGE_POST
+    l = eid.Group.pipeline_layout(1080, 8, 3)
+    assert (l.stages, l.index, l.count, l.y0, l.y1, l.paddedHeight) == (abi.STAGE_INDIRECT, 0, 3, 0, 360, 1088)
+    l = eid.Group.pipeline_layout(144, 4, 3, (1, 1, 2))
+    assert (l.stages, l.index, l.count, l.y0, l.y1) == (abi.STAGE_POST, 1, 2, 72, 144)
+    for bad in [(1080, 1, 0, (0, 0, 0)), (1080, 4, 4, (0, 0, 0)), (1080, 4, 0, (1, 1, 1)), (1080, 4, 0, (2, 0, 2)), (0, 2, 0, (0, 0, 0)), (1080, 4, 0, (0, 2, 2))]:
+        with pytest.raises(eid.EidolaError):
+            eid.Group.pipeline_layout(bad[0], bad[1], bad[2], bad[3])
+    a, b = eid.Group.random_id(), eid.Group.random_id()
+    assert len(a) == 128 and a != b
