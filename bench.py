@@ -272,8 +272,12 @@ def run_cuda(args):
     ainfo = accel.info()
     info = scene.info()
 
-    # band partition (eid_group_layout): rows per rank rounded up to 8, allocation padded to N equal bands
-    _, _, alloc_h = eid.Group.layout(h, world)
+    # band partition (eid_group_layout): rows per rank rounded up to 8, allocation padded to N equal bands;
+    # stage pipeline (eid_group_pipeline_layout): ranks per stage, bands per stage, allocation padded for the widest split
+    pipe = world > 1 and args.mgpu == "pipeline"
+    stages = tuple(int(x) for x in args.stages.split(",")) if args.stages else (0, 0, 0)
+    lay = eid.Group.pipeline_layout(h, world, rank, stages) if pipe else None
+    alloc_h = lay.paddedHeight if pipe else eid.Group.layout(h, world)[2]
     rr = eid.Renderer()
     rr.create((w, alloc_h), scene, accel, stream=stream.cuda_stream)
     rr.set_env_constant(ENV)
@@ -288,10 +292,14 @@ def run_cuda(args):
         # the library owns the NCCL communicator; the host only carries rank 0's 128-byte id to the other ranks
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(eid.Group.unique_id()), dtype=torch.uint8))
+            idt.copy_(torch.frombuffer(bytearray(eid.Group.random_id() if pipe else eid.Group.unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         grp = eid.Group()
-        grp.create(rr, rank, world, bytes(idt.cpu().numpy().tobytes()))
+        if pipe:
+            # stage pipeline: direct | indirect | post ranks joined by peer copies over NVLink (CUDA IPC mappings), no collective
+            grp.create_pipeline(rr, rank, world, bytes(idt.cpu().numpy().tobytes()), h, stages)
+        else:
+            grp.create(rr, rank, world, bytes(idt.cpu().numpy().tobytes()))
         grp.set_mode(post_sharded=(args.post == "sharded"), history={"never": 0, "always": 1, "auto": 2}[args.history], gather_final=True)
         # ONE host image pair set shared by all ranks (POSIX shared memory, page-locked in every process): each rank delivers its own band
         shm_path = "/dev/shm/eidola_bench_%s" % os.environ.get("MASTER_PORT", "0")
@@ -406,6 +414,13 @@ def run_cuda(args):
         allk = [torch.zeros_like(tk) for _ in range(world)]
         dist.all_gather(allk, tk)
         rank_kms = [[round(float(v), 4) for v in t.cpu().numpy()] for t in allk]
+    # latency of ONE frame in isolation (enqueue to the last rank's last kernel): equals the frame time for row bands, the sum of the
+    # stages plus two hand-overs for the stage pipeline
+    lat = []
+    for _ in range(3):
+        lms, _, _ = timed(1, frame)
+        lat.append(lms)
+        frame += 1
     rr.set_profiling(2)
     step(frame)
     vs = rr.stats()
@@ -414,7 +429,25 @@ def run_cuda(args):
     # checksum of the last composed frame (rows of the rendered size): equal for every N when the sharded frame is bit-identical
     import zlib
     crc = 0
-    if rank == 0:
+    pinfo = None
+    if pipe:
+        # the composed frame is spread over the post ranks: each writes its band into the shared host images, rank 0 checksums the whole
+        gi = grp.info()
+        grp.sync()
+        imgs = shm[:2 * w * h * 16].view(np.float32).reshape(2, h, w, 4)
+        if gi.stages & abi.STAGE_POST:
+            y0, y1 = gi.y0, min(gi.y1, h)
+            for k, which in enumerate((abi.BUF_DIRECT, abi.BUF_INDIRECT)):
+                imgs[k, y0:y1] = rr.read(which).reshape(alloc_h, w, 4)[y0:y1]
+        tp = torch.tensor([gi.peerCopies, gi.peerBytes] + [int(v) for v in vs.kernelLaunches[:]], device=dev, dtype=torch.int64)
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        dist.barrier()
+        if rank == 0:
+            crc = zlib.crc32(np.ascontiguousarray(imgs).tobytes(), 0)
+            pinfo = {"stages": [gi.nDirect, gi.nIndirect, gi.nPost], "peer_copies_per_frame": int(tp[0].item()) / frame,
+                     "peer_MB_per_frame": int(tp[1].item()) / frame / 1e6, "stream_mem_ops": bool(gi.streamMemOps),
+                     "launches_per_frame_all_ranks": [int(v) for v in tp[2:].cpu().numpy()]}
+    elif rank == 0:
         for which in (abi.BUF_DIRECT, abi.BUF_INDIRECT):
             img = rr.read(which).reshape(alloc_h, w, 4)[:h]
             crc = zlib.crc32(np.ascontiguousarray(img).tobytes(), crc)
@@ -424,23 +457,32 @@ def run_cuda(args):
         n_px = w * h
         peak, peak_src = measured_peak_hbm()
         names = abi.KERNEL_NAMES
-        launches = [max(1, int(v)) for v in vs.kernelLaunches[:]]   # 1, 1, 1 prep + 4 passes, 5 passes, 1
-        dom = int(np.argmax(kms))
+        launches = [max(1, int(v)) for v in (pinfo["launches_per_frame_all_ranks"] if pipe else vs.kernelLaunches[:])]   # 1, 10, 1 prep + 4 passes, 5 passes, 1
         screen = {k: SCREEN_BYTES_PER_PX[k] * n_px for k in names}
         band_frac = 1.0 / world                                       # this rank's share of the trace stages ...
         post_frac = band_frac if args.post == "sharded" else 1.0      # ... and of denoise + compose (mode B: per band; mode A: replicated)
+        fracs = [band_frac, band_frac, post_frac, post_frac, post_frac]
+        if pipe:
+            # every stage runs on its own ranks: report the slowest rank of each stage and that rank's share of the rows
+            kms = np.max(np.array(rank_kms), axis=0)
+            nD, nI, nP = pinfo["stages"]
+            fracs = [1.0 / nD, 1.0 / max(nI, 1), 1.0 / nP, 1.0 / nP, 1.0 / nP]
+        lpr = launches                                                # launches of ONE rank per frame and stage
+        if pipe:
+            lpr = [max(1, launches[i] // n) for i, n in enumerate((nD, max(nI, 1), nP, nP, nP))]
+        dom = int(np.argmax(kms))
         tot_rays = max(1, vs.closestHitRays + vs.anyHitRays)
         # BVH fetches counted by the STATS kernels: served by L1 / L2 (the scene is cache-resident at 1 M triangles), reported apart
         trace_bytes = vs.nodeVisits * NODE_BYTES + vs.triangleTests * TRI_BYTES + (vs.closestHitRays * HIT_GATHER_BYTES)
-        k1_rays = min(vs.closestHitRays, int(n_px * band_frac)) + vs.primaryHits
+        k1_rays = min(vs.closestHitRays, int(n_px * fracs[0])) + vs.primaryHits
         cache_served = {names[0]: trace_bytes * k1_rays / tot_rays, names[1]: trace_bytes * (tot_rays - k1_rays) / tot_rays}
         prof = load_traffic_profile(_ACTIVE) if (world == 1 and not args.quick) else None
         kernels = {}
         for i, k in enumerate(names):
-            algo = screen[k] * (band_frac if i < 2 else post_frac)    # compulsory screen-space bytes of SURVEY 8(d), this rank's rows
+            algo = screen[k] * fracs[i]                                # compulsory screen-space bytes of SURVEY 8(d), this rank's rows
             t = kms[i] * 1e-3
-            e = {"ms_per_frame": float(kms[i]), "launches": launches[i], "algorithmic_MB_per_frame": algo / 1e6,
-                 "algorithmic_MB_per_launch": algo / launches[i] / 1e6,
+            e = {"ms_per_frame": float(kms[i]), "launches": lpr[i], "algorithmic_MB_per_frame": algo / 1e6,
+                 "algorithmic_MB_per_launch": algo / lpr[i] / 1e6,
                  "achieved_GBps": (algo / t / 1e9) if t > 0 else None, "frac_of_hbm_peak": (algo / t / 1e9 / peak) if t > 0 else None,
                  "limiter": STAGE_LIMITER[k]}
             if k in cache_served:
@@ -454,11 +496,11 @@ def run_cuda(args):
                 e["ncu_traffic_over_algorithmic"] = q["dram_bytes"] / algo if algo > 0 else None
             kernels[k] = e
         kd = kernels[names[dom]]
-        dom_launch_ms = kms[dom] / launches[dom]
+        dom_launch_ms = kms[dom] / lpr[dom]
         achieved = kd["algorithmic_MB_per_launch"] * 1e6 / (dom_launch_ms * 1e-3) / 1e9 if dom_launch_ms > 0 else 0.0
         traffic = None
         if prof and names[dom] in prof.get("stages", {}):
-            traffic = prof["stages"][names[dom]]["dram_bytes"] / launches[dom]
+            traffic = prof["stages"][names[dom]]["dram_bytes"] / lpr[dom]
         line = {
             "metric": "Mray/s (ClosestHit+AnyHit rays per second, full Renderer::run frame)", "value": value, "unit": "Mray/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -466,7 +508,10 @@ def run_cuda(args):
             "config": {"workload": WORKLOADS[_ACTIVE]["text"] if not args.quick else "QUICK smoke variant (not a benchmark number)", "width": w, "height": h,
                        "triangles": int(ainfo.triangleCount), "emissive_triangles": int(info.trigLightCount), "maxDepth": MAX_DEPTH,
                        "ReSTIRState": ["none", "ris", "spatial", "temporal", "spatiotemporal"][RESTIR_STATE],
-                       "parallelism": ("eid_group: %d row bands of %d rows (multiples of 8), one rank per GPU; exchange A (G-buffer + direct image, behind "
+                       "parallelism": ("eid_group stage pipeline: %d direct | %d indirect | %d post ranks (row bands per stage, one rank per GPU), frames handed over "
+                                       "by peer copies over NVLink into the consumer's buffers (CUDA IPC mappings) + stream-ordered flags, no collective; "
+                                       "reservoir history: %s" % (pinfo["stages"][0], pinfo["stages"][1], pinfo["stages"][2], args.history)) if pipe else
+                                      ("eid_group: %d row bands of %d rows (multiples of 8), one rank per GPU; exchange A (G-buffer + direct image, behind "
                                        "indirect_stage) and B (quarter-res indirect image): one NCCL launch each; %s; reservoir history: %s" % (
                                            world, grp.info().bandRows, "denoise+compose per band, exchange C: all-gather of the composed images (1 NCCL launch)"
                                            if args.post == "sharded" else "denoise+compose replicated on every rank", args.history)) if world > 1 else "single GPU",
@@ -477,7 +522,7 @@ def run_cuda(args):
             "fps": 1e3 / (ms / args.steps),
             "rays_per_frame": rays / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mray/s", "h2d_bytes_per_step": C.sizeof(abi.SceneCamera) + C.sizeof(abi.RtxState),
-                    "d2h_bytes_per_step": 2 * w * h * 16, "pipelined": "D2H of frame f overlaps the kernels of frame f+1 (copy stream, 2 pinned buffer pairs)" if world == 1 else "every rank copies ITS band of the composed images into one shared pinned host image pair over its own PCIe link (eid_group_render_host_async); no exchange C",
+                    "d2h_bytes_per_step": 2 * w * h * 16, "pipelined": "D2H of frame f overlaps the kernels of frame f+1 (copy stream, 2 pinned buffer pairs)" if world == 1 else ("every post rank copies ITS band of the composed images into one shared pinned host image pair over its own PCIe link (eid_group_render_host_async)" if pipe else "every rank copies ITS band of the composed images into one shared pinned host image pair over its own PCIe link (eid_group_render_host_async); no exchange C"),
                     "ms_per_step": ems / e2e_steps, "fps": 1e3 / (ems / e2e_steps), "steps": e2e_steps},
             "gpu_launches": int(sum(launches)) * args.steps, "launches_per_frame": launches,
             "clocks": clocks,
@@ -497,7 +542,9 @@ def run_cuda(args):
             "image_crc32": "%08x" % crc, "frames_rendered": frame,
             "host_enqueue_ms_per_frame": {"device_timed": host_ms[0], "e2e": host_ms[1]},
             "stage_ms_per_rank": rank_kms,
-            "nccl_launches_per_frame": (3 if args.post == "sharded" else 2) if world > 1 else 0,
+            "nccl_launches_per_frame": 0 if (pipe or world == 1) else (3 if args.post == "sharded" else 2),
+            "pipeline": pinfo,
+            "frame_latency_ms": float(min(lat)),
             "visits_per_ray": {"nodes": vs.nodeVisits / tot_rays, "triangles": vs.triangleTests / tot_rays},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -542,6 +589,10 @@ def main():
     ap.add_argument("--post", default="sharded", choices=["sharded", "replicated"],
                     help="N>1 only. sharded (mode B): each rank denoises/composes its band, 2 exchange steps; replicated (mode A): "
                          "one exchange step, every rank post-processes the full frame")
+    ap.add_argument("--mgpu", default="pipeline", choices=["pipeline", "bands"],
+                    help="N>1: pipeline = direct | indirect | post ranks, one frame behind each other (throughput set by the slowest stage; default); "
+                         "bands = every rank renders one row band of the same frame (lowest latency)")
+    ap.add_argument("--stages", default="", help="N>1, --mgpu pipeline: ranks per stage as d,i,p (default: the library's split, e.g. 3,3,2 at N=8)")
     ap.add_argument("--restir", default="temporal", choices=["none", "ris", "spatial", "temporal", "spatiotemporal"],
                     help="RtxState.ReSTIRState (default temporal = the reference's default and the headline configuration)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="c3 = headline (BASELINE.json metric); c4 = 4K; c5 = 10 M triangles")

@@ -251,10 +251,10 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
   if (cam) r->scene->host.camera = *cam;
   uint32_t y0 = 0, y1 = 0;
   if (g->pipe) {
-    // stage pipeline: only the post ranks hold composed rows; the acknowledgement that lets the direct ranks overwrite this parity's
-    // landing buffers follows the device-to-host copy
+    // stage pipeline: the composed rows exist on the post ranks only, and they leave through every rank's PCIe link (pipeline.cu)
     pipelineFrame(g, *state, frames, false);
-    if (pipelineDelivers(g, &y0, &y1)) y1 = std::min<uint32_t>(y1, (uint32_t)state->size.y); else y1 = y0 = 0;
+    pipelineDeliver(g, *state, direct_host, indirect_host);
+    return EID_OK;
   } else {
     groupFrame(g, *state, frames, false);           // (fillParams waits for the copy that read this parity's images two frames ago)
     y0 = g->world > 1 ? (uint32_t)g->rank * g->bandRows : 0;
@@ -271,8 +271,7 @@ int eid_group_render_host_async(eid_group* g, const SceneCamera* cam, const RtxS
     if (indirect_host) CUDA_CHECK(cudaMemcpy2DAsync((char*)indirect_host + (size_t)y0 * rowBytes, rowBytes, r->indirectImg + first, (size_t)r->width * 16, rowBytes, y1 - y0, cudaMemcpyDeviceToHost, r->copyStream));
     CUDA_CHECK(cudaEventRecord(r->evCopyDone2[set], r->copyStream));
     r->copyPending2[set] = true;
-    if (g->pipe) pipelineAck(g, r->copyStream);
-  } else if (g->pipe) pipelineAck(g, r->stream);
+  }
   return EID_OK;
   EID_CATCH
 }

@@ -38,8 +38,8 @@ namespace {
 
 constexpr int MAXW = 16;
 enum { ROLE_D = EID_STAGE_DIRECT, ROLE_I = EID_STAGE_INDIRECT, ROLE_P = EID_STAGE_POST };
-enum FlagKind { F_READY_D, F_READY_I, F_READY_H, F_ACK_D, F_ACK_I, F_ACK_H, F_KINDS };
-enum BufIdx { B_G0, B_G1, B_DIR0, B_DIR1, B_K2G0, B_K2G1, B_K2MV0, B_K2MV1, B_INDIN0, B_INDIN1, B_DR0, B_DR1, B_IR0, B_IR1, B_FLAGS, B_COUNT };
+enum FlagKind { F_READY_D, F_READY_I, F_READY_H, F_ACK_D, F_ACK_I, F_ACK_H, F_READY_V, F_ACK_V, F_KINDS };
+enum BufIdx { B_G0, B_G1, B_DIR0, B_DIR1, B_K2G0, B_K2G1, B_K2MV0, B_K2MV1, B_INDIN0, B_INDIN1, B_DR0, B_DR1, B_IR0, B_IR1, B_FLAGS, B_DELIV, B_COUNT };
 
 struct RankLayout { int role = 0, index = 0, count = 1; uint32_t y0 = 0, y1 = 0; };
 
@@ -147,6 +147,11 @@ struct EidPipe {
   cudaEvent_t evStage = nullptr, evPush[2] = {nullptr, nullptr}, evPushI = nullptr, evPrep = nullptr, evK3 = nullptr, evFork = nullptr;
   bool pushValid[2] = {false, false}, pushIValid = false;
   bool historyComplete = false;            // the LAST buffers of the next frame already hold the peers' rows
+  // host delivery spread over every rank's PCIe link: post ranks write the composed rows of rank k's delivery band into k's staging
+  // buffer ([parity][direct | indirect][delivRows x width] float4), k copies them to the host
+  float4* deliv = nullptr;
+  uint32_t delivRows = 0, dseq = 0;
+  cudaEvent_t evDelivPush = nullptr, evDone = nullptr;
   bool ackPending = false;                 // eid_group_run: the frame's acknowledgement is enqueued with the NEXT frame (see pipelineFrame)
   ShmHdr* shm = nullptr;
   std::string shmPath;
@@ -368,6 +373,67 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+// Host delivery of the frame just enqueued (eid_group_render_host_async).  The composed rows only exist on the post ranks, and one PCIe
+// link moves a 1080p image pair (66 MB) in ~1.6 ms — longer than a pipeline stage.  So the frame leaves through ALL links: rank k owns the
+// delivery band [k B, (k + 1) B); a post rank copies its rows of its own band to the host itself and writes the rest into the owners'
+// staging buffers over NVLink; every owner copies what it received to the (shared, pinned) host images on its copy stream.
+void pipelineDeliver(eid_group* g, const RtxState& st, float* directHost, float* indirectHost) {
+  eid_renderer* r = g->r;
+  EidPipe* p = g->pipe;
+  const int H = st.size.y, set = r->lastSet;
+  const uint32_t d = p->dseq, par = d & 1u;
+  const size_t pitchB = (size_t)r->width * 16, rowBytes = (size_t)st.size.x * 16, img = (size_t)p->delivRows * r->width;
+  float* hostImg[2] = {directHost, indirectHost};
+  auto delivBand = [&](int k) { return clampRange(k * (int)p->delivRows, (k + 1) * (int)p->delivRows, 0, H); };
+  const bool post = (p->me.role & ROLE_P) != 0;
+  if (post) {
+    const float4* srcImg[2] = {r->directImg, r->indirectImg};
+    CUDA_CHECK(cudaEventRecord(p->evDone, r->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evDone, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, p->evDone, 0));
+    for (int j = 0; j < g->world; ++j) {
+      const Range b = delivBand(j);
+      const Range rows = intersect(b, (int)p->me.y0, (int)p->me.y1);
+      if (rows.empty()) continue;
+      if (j == g->rank) {
+        for (int k = 0; k < 2; ++k)
+          if (hostImg[k]) CUDA_CHECK(cudaMemcpy2DAsync((char*)hostImg[k] + (size_t)rows.a * rowBytes, rowBytes, srcImg[k] + (size_t)rows.a * r->width, pitchB, rowBytes,
+                                                        rows.b - rows.a, cudaMemcpyDeviceToHost, r->copyStream));
+        continue;
+      }
+      if (d >= 2) waitFlag(g, g->cs, F_ACK_V, j, d - 1);              // the owner has sent the frame that used this staging parity last
+      for (int k = 0; k < 2; ++k) {
+        float4* dst = (float4*)p->peer[j][B_DELIV] + (2 * par + k) * img + (size_t)(rows.a - j * (int)p->delivRows) * r->width;
+        CUDA_CHECK(cudaMemcpyAsync(dst, srcImg[k] + (size_t)rows.a * r->width, (size_t)(rows.b - rows.a) * pitchB, cudaMemcpyDeviceToDevice, g->cs));
+        p->peerCopies++; p->peerBytes += (size_t)(rows.b - rows.a) * pitchB;
+      }
+      setFlag(g, g->cs, j, F_READY_V, d + 1);
+    }
+    CUDA_CHECK(cudaEventRecord(p->evDelivPush, g->cs));
+  }
+  // rows of MY delivery band that other post ranks composed
+  const Range mine = delivBand(g->rank);
+  for (int j = 0; j < g->world; ++j) {
+    if (j == g->rank || !(p->ranks[j].role & ROLE_P)) continue;
+    const Range rows = intersect(mine, (int)p->ranks[j].y0, (int)p->ranks[j].y1);
+    if (rows.empty()) continue;
+    waitFlag(g, r->copyStream, F_READY_V, j, d + 1);
+    for (int k = 0; k < 2; ++k) {
+      const float4* src = p->deliv + (2 * par + k) * img + (size_t)(rows.a - g->rank * (int)p->delivRows) * r->width;
+      if (hostImg[k]) CUDA_CHECK(cudaMemcpy2DAsync((char*)hostImg[k] + (size_t)rows.a * rowBytes, rowBytes, src, pitchB, rowBytes, rows.b - rows.a, cudaMemcpyDeviceToHost, r->copyStream));
+    }
+    setFlag(g, r->copyStream, j, F_ACK_V, d + 1);
+  }
+  if (post) {
+    // this parity's images (the producers' landing buffers) are free once the local copy AND the pushes have read them
+    CUDA_CHECK(cudaStreamWaitEvent(r->copyStream, p->evDelivPush, 0));
+    CUDA_CHECK(cudaEventRecord(r->evCopyDone2[set], r->copyStream));
+    r->copyPending2[set] = true;
+    pipelineAck(g, r->copyStream);
+  }
+  p->dseq = d + 1;
+}
+
 bool pipelineDelivers(eid_group* g, uint32_t* y0, uint32_t* y1) {
   EidPipe* p = g->pipe;
   if (!(p->me.role & ROLE_P)) return false;
@@ -395,8 +461,8 @@ void pipelineDestroy(eid_group* g) {
     for (int j = 0; j < g->world; ++j) while (!loadAcq(&p->shm->ranks[j].closed) && nowSec() - t0 < 20.0) usleep(200);
   }
   for (void* b : p->openedBases) cudaIpcCloseMemHandle(b);
-  for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI, p->evPrep, p->evK3, p->evFork}) if (e) cudaEventDestroy(e);
-  cudaFree(p->flags);
+  for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI, p->evPrep, p->evK3, p->evFork, p->evDelivPush, p->evDone}) if (e) cudaEventDestroy(e);
+  cudaFree(p->flags); cudaFree(p->deliv);
   if (p->shm) munmap(p->shm, sizeof(ShmHdr));
   if (!p->shmPath.empty() && g->rank == 0) unlink(p->shmPath.c_str());
   delete p;
@@ -449,7 +515,9 @@ int eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int wo
     CUDA_CHECK(cudaSetDevice(r->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking));
     r->groupStream = g->cs;
-    for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI, &p->evPrep, &p->evK3, &p->evFork}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI, &p->evPrep, &p->evK3, &p->evFork, &p->evDelivPush, &p->evDone}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    p->delivRows = bandRowsOf(height, world);
+    CUDA_CHECK(cudaMalloc((void**)&p->deliv, (size_t)4 * p->delivRows * r->width * 16));
     if (eid_renderer_set_band(r, p->me.y0, std::min(p->me.y1, r->height)) != EID_OK) raise(EID_ERR_INVALID, "%s", eid_last_error());
     // per-parity landing buffers of the pre-denoise indirect image (post ranks read them in place of denoiseIndTempA)
     const size_t nImg = (size_t)r->width * r->height * 16 + (size_t)17 * r->width * 16;
@@ -461,7 +529,7 @@ int eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int wo
     AddrRangeFn addrRange = (AddrRangeFn)driverEntry("cuMemGetAddressRange");
 
     void* local[B_COUNT] = {r->gbuffer[0], r->gbuffer[1], r->directImgs[0], r->directImgs[1], r->k2G[0], r->k2G[1], r->k2Mv[0], r->k2Mv[1],
-                            r->indIn[0], r->indIn[1], r->directResv[0], r->directResv[1], r->indirectResv[0], r->indirectResv[1], p->flags};
+                            r->indIn[0], r->indIn[1], r->directResv[0], r->directResv[1], r->indirectResv[0], r->indirectResv[1], p->flags, p->deliv};
     for (int b = 0; b < B_COUNT; ++b) p->peer[rank][b] = local[b];
 
     // ---- rendezvous: publish this rank's IPC handles, wait for everybody's, map them ----

@@ -15,10 +15,10 @@ owned, _ = pw.owned_tables()
 print("rays", rays, [(int(r["meta"][3]), int(r["meta"][4])) for r in ranks], "memops", [int(r["meta"][7]) for r in ranks])
 for rank, r in enumerate(ranks):
     role, y0, y1 = int(r["meta"][0]), int(r["meta"][1]), int(r["meta"][2])
-    for key in sorted(k for k in r if k != "meta"):
+    for key in sorted(k for k in r if k != "meta" and not k.startswith("rows_")):
         name, f = key.rsplit("_", 1)
         which, row_bytes, half = owned[name]
-        a, b = (y0 // 2, y1 // 2) if half else (y0, y1)
+        a, b = (int(v) for v in r["rows_" + name])
         rb = row_bytes(w)
         ref = want[int(f)][name][a * rb:b * rb].reshape(b - a, rb)
         got = r[key].reshape(b - a, rb)

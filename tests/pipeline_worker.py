@@ -67,6 +67,7 @@ def main():
     if cfg.get("host"):
         host = [np.zeros((h, w, 4), np.float32) for _ in range(4)]        # two pairs; page-locking is not required for correctness
     y0, y1 = lay.y0, min(lay.y1, h)
+    dband = ((h + world - 1) // world + 7) // 8 * 8
     for f in range(int(cfg["frames"])):
         if cfg.get("orbit"):
             orbit_camera(psc, arrays.camera, f)
@@ -82,14 +83,18 @@ def main():
                 grp.wait_host()
             grp.sync()
             for name, (which, row_bytes, half) in OWNED.items():
-                if not (lay.stages & STAGE_OF[name]):
-                    continue
                 if host is not None and name in ("direct", "indirect"):
-                    out["%s_%d" % (name, f)] = pair[0 if name == "direct" else 1][y0:y1].view(np.uint8).reshape(-1).copy()
+                    # host delivery: EVERY rank copies the rows of its delivery band (rank k of n: rows k B .. (k + 1) B, B = ceil8(ceil(h / n))) to the host
+                    a, b = min(rank * dband, h), min((rank + 1) * dband, h)
+                    out["%s_%d" % (name, f)] = pair[0 if name == "direct" else 1][a:b].view(np.uint8).reshape(-1).copy()
+                    out["rows_%s" % name] = np.array([a, b])
+                    continue
+                if not (lay.stages & STAGE_OF[name]):
                     continue
                 a, b = (y0 // 2, y1 // 2) if half else (y0, y1)
                 rb = row_bytes(w)
                 out["%s_%d" % (name, f)] = rr.read(which).view(np.uint8).reshape(-1)[a * rb:b * rb].copy()
+                out["rows_%s" % name] = np.array([a, b])
     s = rr.stats()
     gi = grp.info()
     out["meta"] = np.array([lay.stages, y0, y1, s.totalClosestHitRays, s.totalAnyHitRays, gi.peerCopies, gi.peerBytes, gi.streamMemOps], np.int64)

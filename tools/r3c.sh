@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_pipeline.py -q -x > gpurun_out/r3c_pytest.log 2>&1
+tail -15 gpurun_out/r3c_pytest.log | cut -c1-250
+bash tools/r3b.sh "$@"
