@@ -207,7 +207,7 @@ void eid_group_destroy(eid_group* g) {
   if (g->r && g->r->stream) cudaStreamSynchronize(g->r->stream);
   if (g->r && g->r->copyStream) cudaStreamSynchronize(g->r->copyStream);
   if (g->cs) cudaStreamSynchronize(g->cs);
-  if (g->pipe) pipelineDestroy(g);
+  if (g->pipe) { try { pipelineSync(g); } catch (...) {} pipelineDestroy(g); }
   if (g->r && g->r->groupStream == g->cs) g->r->groupStream = nullptr;
   if (g->copyStream) { cudaStreamSynchronize(g->copyStream); cudaStreamDestroy(g->copyStream); }
   if (g->comm) nccl().CommDestroy(g->comm);
@@ -291,6 +291,7 @@ int eid_group_sync(eid_group* g) {
   CUDA_CHECK(cudaSetDevice(g->r->device));
   CUDA_CHECK(cudaStreamSynchronize(g->r->stream));
   CUDA_CHECK(cudaStreamSynchronize(g->cs));
+  if (g->pipe) pipelineSync(g);
   return EID_OK;
   EID_CATCH
 }

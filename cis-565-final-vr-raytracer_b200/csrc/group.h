@@ -32,6 +32,7 @@ struct eid_group {
 void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow);
 void pipelineAck(eid_group* g, cudaStream_t st);
 void pipelineDestroy(eid_group* g);
+void pipelineSync(eid_group* g);
 void pipelineInfo(eid_group* g, eid_group_info* out);
 bool pipelineDelivers(eid_group* g, uint32_t* y0, uint32_t* y1);
 void pipelineDeliver(eid_group* g, const RtxState& st, float* directHost, float* indirectHost);

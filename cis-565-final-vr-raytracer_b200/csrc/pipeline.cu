@@ -126,6 +126,12 @@ __global__ void k_flag_set(uint32_t* flag, uint32_t value) {       // release: e
   __threadfence_system();
   *(volatile uint32_t*)flag = value;
 }
+// Peer copy by the SMs (16-byte stores over NVLink).  The copy engines move a band at ~0.25 TB/s; that is fine for the hand-overs that
+// run beside the next frame's kernels, but the same-stage history is ON the critical path (the peer's next direct_stage waits for it) while
+// this rank's SMs are idle anyway: a grid-stride copy kernel delivers it at NVLink speed.
+__global__ void __launch_bounds__(256) k_peer_copy(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 __global__ void k_flag_wait(const uint32_t* flag, uint32_t value) {   // fallback when stream memory operations are unavailable
   while ((int32_t)(*(volatile const uint32_t*)flag - value) < 0) __nanosleep(200);
   __threadfence_system();
@@ -144,8 +150,14 @@ struct EidPipe {
   uint32_t* flags = nullptr;               // local: [kind][peer]
   uint32_t seq = 0;                        // frames enqueued so far
   int lastSeqOfParity[2] = {-1, -1};
-  cudaEvent_t evStage = nullptr, evPush[2] = {nullptr, nullptr}, evPushI = nullptr, evPrep = nullptr, evK3 = nullptr, evFork = nullptr;
-  bool pushValid[2] = {false, false}, pushIValid = false;
+  // Communication streams: pushes to different consumer GROUPS must not queue behind each other — a push waits for its consumer's
+  // acknowledgement of the frame before last, and the post ranks (two stages behind) acknowledge just in time, so on one stream the
+  // next frame's rows for the indirect ranks (or the history the peer's next direct_stage waits for) would stall behind them.
+  // g->cs: to the indirect ranks (direct ranks) / to the post ranks (indirect ranks, post ranks' delivery); csP: direct -> post; csH: history
+  cudaStream_t csP = nullptr, csH = nullptr;
+  cudaEvent_t evStage = nullptr, evPush[2] = {nullptr, nullptr}, evPushP[2] = {nullptr, nullptr}, evPushH[2] = {nullptr, nullptr}, evPushI[2] = {nullptr, nullptr},
+              evPrep = nullptr, evK3 = nullptr, evFork = nullptr;
+  bool pushValid[2] = {false, false}, pushHValid[2] = {false, false}, pushIValid[2] = {false, false};
   bool historyComplete = false;            // the LAST buffers of the next frame already hold the peers' rows
   // host delivery spread over every rank's PCIe link: post ranks write the composed rows of rank k's delivery band into k's staging
   // buffer ([parity][direct | indirect][delivRows x width] float4), k copies them to the host
@@ -176,11 +188,19 @@ void waitFlag(eid_group* g, cudaStream_t st, int kind, int from, uint32_t value)
 void setFlag(eid_group* g, cudaStream_t st, int owner, int kind, uint32_t value) {
   k_flag_set<<<1, 1, 0, st>>>(flagOf(g->pipe, owner, kind, g->rank), value);
 }
-void pushRows(eid_group* g, int to, int buf, size_t rowBytes, Range r) {
+void pushRows(eid_group* g, cudaStream_t cs, int to, int buf, size_t rowBytes, Range r) {
   if (r.empty()) return;
   EidPipe* p = g->pipe;
   const size_t off = (size_t)r.a * rowBytes, bytes = (size_t)(r.b - r.a) * rowBytes;
-  CUDA_CHECK(cudaMemcpyAsync((char*)p->peer[to][buf] + off, (const char*)p->peer[g->rank][buf] + off, bytes, cudaMemcpyDeviceToDevice, g->cs));
+  CUDA_CHECK(cudaMemcpyAsync((char*)p->peer[to][buf] + off, (const char*)p->peer[g->rank][buf] + off, bytes, cudaMemcpyDeviceToDevice, cs));
+  p->peerCopies++; p->peerBytes += bytes;
+}
+void pushRowsSM(eid_group* g, cudaStream_t cs, int to, int buf, size_t rowBytes, Range r) {
+  if (r.empty()) return;
+  EidPipe* p = g->pipe;
+  const size_t off = (size_t)r.a * rowBytes, bytes = (size_t)(r.b - r.a) * rowBytes;
+  if ((off | bytes) & 15) { pushRows(g, cs, to, buf, rowBytes, r); return; }
+  k_peer_copy<<<g->r->smCount * 2, 256, 0, cs>>>((uint4*)((char*)p->peer[to][buf] + off), (const uint4*)((const char*)p->peer[g->rank][buf] + off), bytes / 16);
   p->peerCopies++; p->peerBytes += bytes;
 }
 // a local buffer pushed under another index at the consumer (indA -> the consumer's per-parity indIn)
@@ -205,14 +225,14 @@ void pushHistory(eid_group* g, const FrameParams& P, int set, bool last, uint32_
   for (int j = 0; j < g->world; ++j) {
     if (j == g->rank || p->ranks[j].role != me.role) continue;
     // the peer read these rows' buffer (as `last`) in every frame up to the previous one: wait until it has finished that stage
-    if (p->seq > 0) waitFlag(g, g->cs, F_ACK_H, j, p->seq);
+    if (p->seq > 0) waitFlag(g, p->csH, F_ACK_H, j, p->seq);
     if (me.role & ROLE_D) {
-      pushRows(g, j, B_G0 + thisIdx, (size_t)P.pitch * 16, Range{(int)me.y0, (int)me.y1});
-      pushRows(g, j, B_DR0 + thisIdx, sw * sizeof(DirectReservoir), Range{(int)me.y0, (int)me.y1});
+      pushRowsSM(g, p->csH, j, B_G0 + thisIdx, (size_t)P.pitch * 16, Range{(int)me.y0, (int)me.y1});
+      pushRowsSM(g, p->csH, j, B_DR0 + thisIdx, sw * sizeof(DirectReservoir), Range{(int)me.y0, (int)me.y1});
     } else {
-      pushRows(g, j, B_IR0 + thisIdx, (sw / 2) * sizeof(IndirectReservoir), Range{(int)me.y0 / 2, (int)me.y1 / 2});
+      pushRowsSM(g, p->csH, j, B_IR0 + thisIdx, (sw / 2) * sizeof(IndirectReservoir), Range{(int)me.y0 / 2, (int)me.y1 / 2});
     }
-    setFlag(g, g->cs, j, F_READY_H, readyValue);
+    setFlag(g, p->csH, j, F_READY_H, readyValue);
   }
 }
 
@@ -266,44 +286,52 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
 
   if (me.role == ROLE_D) {
     // K1 rewrites this parity's G-buffer / direct image / gathered lookups: the peer copies of the frame that used them last must have drained
-    if (p->pushValid[set]) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPush[set], 0));
+    if (p->pushValid[set]) { CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPush[set], 0)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushP[set], 0)); }
+    if (p->pushHValid[set]) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushH[set], 0));
     if (needHistory) {
       if (!p->historyComplete) {                              // lazily: first frame, or the camera started moving
-        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
         pushHistory(g, P, set, true, n + 1);
         // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
-        CUDA_CHECK(cudaEventRecord(p->evPrep, g->cs)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
+        CUDA_CHECK(cudaEventRecord(p->evPrep, p->csH)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
       }
       for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) waitFlag(g, r->stream, F_READY_H, j, n + 1);
     }
     beginFrame(r);
     stageDirect(r, P, r->stream);
     if (stagePeers > 1) for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) setFlag(g, r->stream, j, F_ACK_H, n + 1);
-    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csP, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
+    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;   // the peer's next direct_stage waits for it: first
     for (int j = 0; j < g->world; ++j) {
       const RankLayout& c = p->ranks[j];
       if (c.role == ROLE_D) continue;
       const DirectNeeds need = directNeeds(c, padded);
       const Range rg = intersect(need.g, (int)me.y0, (int)me.y1), rd = intersect(need.d, (int)me.y0, (int)me.y1), rq = intersect(need.q, (int)me.y0 / 2, (int)me.y1 / 2);
       if (rg.empty() && rd.empty() && rq.empty()) continue;
-      if (prev >= 0) waitFlag(g, g->cs, F_ACK_D, j, (uint32_t)prev + 1);
-      pushRows(g, j, B_G0 + !set, rowG, rg);
-      pushRows(g, j, B_DIR0 + set, rowG, rd);
-      pushRows(g, j, B_K2G0 + set, (size_t)(P.pitch / 2) * 16, rq);
-      pushRows(g, j, B_K2MV0 + set, (size_t)(P.pitch / 2) * 4, rq);
-      setFlag(g, g->cs, j, F_READY_D, n + 1);
+      cudaStream_t cs = (c.role & ROLE_I) ? g->cs : p->csP;
+      if (prev >= 0) waitFlag(g, cs, F_ACK_D, j, (uint32_t)prev + 1);
+      pushRows(g, cs, j, B_G0 + !set, rowG, rg);
+      pushRows(g, cs, j, B_DIR0 + set, rowG, rd);
+      pushRows(g, cs, j, B_K2G0 + set, (size_t)(P.pitch / 2) * 16, rq);
+      pushRows(g, cs, j, B_K2MV0 + set, (size_t)(P.pitch / 2) * 4, rq);
+      setFlag(g, cs, j, F_READY_D, n + 1);
     }
-    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
-    CUDA_CHECK(cudaEventRecord(p->evPush[set], g->cs)); p->pushValid[set] = true;
+    CUDA_CHECK(cudaEventRecord(p->evPush[set], g->cs)); CUDA_CHECK(cudaEventRecord(p->evPushP[set], p->csP)); p->pushValid[set] = true;
+    CUDA_CHECK(cudaEventRecord(p->evPushH[set], p->csH)); p->pushHValid[set] = true;
     endFrame(r);
   } else if (me.role == ROLE_I) {
-    if (p->pushIValid) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushI, 0));     // indA is one buffer: its last peer copy must have drained
+    // indirect_stage writes its image into this rank's own (otherwise unused) per-parity landing buffer instead of the single denoiseIndTempA,
+    // so that only the peer copy of the frame before last has to have drained — not the one the post ranks may still be acknowledging
+    P.indA = r->indIn[set];
+    if (p->pushIValid[set]) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushI[set], 0));
+    if (p->pushHValid[set]) CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPushH[set], 0));   // ... and the history push that read this parity's reservoirs
     if (needHistory) {
       if (!p->historyComplete) {
-        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
         pushHistory(g, P, set, true, n + 1);
         // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
-        CUDA_CHECK(cudaEventRecord(p->evPrep, g->cs)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
+        CUDA_CHECK(cudaEventRecord(p->evPrep, p->csH)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
       }
       for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_I) waitFlag(g, r->stream, F_READY_H, j, n + 1);
     }
@@ -321,7 +349,8 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
       if (d.role == ROLE_D && !(intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty())) setFlag(g, r->stream, j, F_ACK_D, n + 1);
       if (d.role == ROLE_I && j != g->rank) setFlag(g, r->stream, j, F_ACK_H, n + 1);
     }
-    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0));
+    CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
+    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
     for (int j = 0; j < g->world; ++j) {
       const RankLayout& c = p->ranks[j];
       const Range ri = intersect(indirectNeeds(c, padded), (int)me.y0 / 2, (int)me.y1 / 2);
@@ -330,8 +359,8 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
       pushRowsFrom(g, j, B_INDIN0 + set, P.indA, rowG, ri);              // quarter-res rows at the full-res pitch (renderer.cpp:267-281)
       setFlag(g, g->cs, j, F_READY_I, n + 1);
     }
-    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
-    CUDA_CHECK(cudaEventRecord(p->evPushI, g->cs)); p->pushIValid = true;
+    CUDA_CHECK(cudaEventRecord(p->evPushI[set], g->cs)); p->pushIValid[set] = true;
+    CUDA_CHECK(cudaEventRecord(p->evPushH[set], p->csH)); p->pushHValid[set] = true;
     endFrame(r);
   } else {
     // post rank (denoise + compose on its band), or — without indirect ranks — indirect_stage + denoise + compose on the whole frame
@@ -441,6 +470,12 @@ bool pipelineDelivers(eid_group* g, uint32_t* y0, uint32_t* y1) {
   return true;
 }
 
+void pipelineSync(eid_group* g) {
+  EidPipe* p = g->pipe;
+  CUDA_CHECK(cudaStreamSynchronize(p->csP));
+  CUDA_CHECK(cudaStreamSynchronize(p->csH));
+}
+
 void pipelineInfo(eid_group* g, eid_group_info* out) {
   EidPipe* p = g->pipe;
   out->rank = g->rank; out->world = g->world;
@@ -461,7 +496,9 @@ void pipelineDestroy(eid_group* g) {
     for (int j = 0; j < g->world; ++j) while (!loadAcq(&p->shm->ranks[j].closed) && nowSec() - t0 < 20.0) usleep(200);
   }
   for (void* b : p->openedBases) cudaIpcCloseMemHandle(b);
-  for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI, p->evPrep, p->evK3, p->evFork, p->evDelivPush, p->evDone}) if (e) cudaEventDestroy(e);
+  for (cudaStream_t* st : {&p->csP, &p->csH}) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+  for (cudaEvent_t e : {p->evPushP[0], p->evPushP[1], p->evPushH[0], p->evPushH[1]}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI[0], p->evPushI[1], p->evPrep, p->evK3, p->evFork, p->evDelivPush, p->evDone}) if (e) cudaEventDestroy(e);
   cudaFree(p->flags); cudaFree(p->deliv);
   if (p->shm) munmap(p->shm, sizeof(ShmHdr));
   if (!p->shmPath.empty() && g->rank == 0) unlink(p->shmPath.c_str());
@@ -515,7 +552,10 @@ int eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int wo
     CUDA_CHECK(cudaSetDevice(r->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g->cs, cudaStreamNonBlocking));
     r->groupStream = g->cs;
-    for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI, &p->evPrep, &p->evK3, &p->evFork, &p->evDelivPush, &p->evDone}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&p->csP, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&p->csH, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&p->evPushP[0], &p->evPushP[1], &p->evPushH[0], &p->evPushH[1]}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI[0], &p->evPushI[1], &p->evPrep, &p->evK3, &p->evFork, &p->evDelivPush, &p->evDone}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     p->delivRows = bandRowsOf(height, world);
     CUDA_CHECK(cudaMalloc((void**)&p->deliv, (size_t)4 * p->delivRows * r->width * 16));
     if (eid_renderer_set_band(r, p->me.y0, std::min(p->me.y1, r->height)) != EID_OK) raise(EID_ERR_INVALID, "%s", eid_last_error());
