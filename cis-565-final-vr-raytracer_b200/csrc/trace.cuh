@@ -406,6 +406,28 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
 #ifndef EID_TQ_REFILL
 #define EID_TQ_REFILL 1          // idle lanes that trigger a queue fetch
 #endif
+#ifndef EID_TQ_STEAL
+#define EID_TQ_STEAL 0           // 1: warp-level work stealing once the queue has drained (see k_trace_queue).  Built, bit-identical, and
+                                 // measured SLOWER (indirect_stage 0.602 -> 0.633-0.658 ms for every threshold tried, profiles/README.md): the
+                                 // queue launches are bound by the latency of TYPICAL rays on under-filled SMs, not by a few very long ones
+#endif
+#ifndef EID_TQ_STEALS_PER_ROUND
+#define EID_TQ_STEALS_PER_ROUND 4
+#endif
+#ifndef EID_TQ_STEAL_MIN_IDLE
+#define EID_TQ_STEAL_MIN_IDLE 16      // lanes of the warp that must be idle before anything is stolen (the tail, not the bulk)
+#endif
+#ifndef EID_TQ_STEAL_MIN_AGE
+#define EID_TQ_STEAL_MIN_AGE 24       // node visits a piece must have behind it before it can be robbed (only long rays are worth splitting)
+#endif
+// Active-lane re-balancing for the tail.  A small queue is latency-bound: the longest ray of the C3 scene needs ~150 dependent node
+// visits while the mean is 13.5, so once the queue has drained a warp sits on one or two long rays with 30 idle lanes, and every queue
+// launch of the wavefront stages pays that tail.  From the moment a warp can fetch no more rays, an idle lane STEALS the oldest stack
+// entry (the largest pending subtree) of the lane with the most pending entries, together with the ray and its best hit so far, and
+// walks that subtree itself; thieves can be robbed in turn.  Every finished piece is sent to the lane that OWNS the ray (warp
+// shuffles), which keeps the best hit under the total order (t, instance, primitive) — the result is the one an undivided walk finds,
+// whatever the split — and writes it when its last piece has arrived.  Occlusion rays stop all their pieces at the first hit.
+struct StealSlot { float t, u, v; int tri, prim, inst; int outstanding; int pad; };
 template <bool ANY, bool STATS>
 __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const AccelView A, const float4* __restrict__ rays, const uint32_t* __restrict__ countPtr,
                                                                         uint32_t* __restrict__ cursor, float4* __restrict__ hits, uint32_t* __restrict__ occl,
@@ -415,8 +437,17 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
   if (blockIdx.x == 0 && threadIdx.x == 0 && n) {   // ray counters of the frame ([0] closest, [1] any) and since creation ([5], [6])
     atomicAdd(&counters[ANY ? 1 : 0], (unsigned long long)n); atomicAdd(&totals[ANY ? 6 : 5], (unsigned long long)n);
   }
+#if EID_TQ_STEAL
+  __shared__ StealSlot s_slot[128];
+  StealSlot& mySlot = s_slot[threadIdx.x];
+  StealSlot* warpSlots = s_slot + (threadIdx.x & ~31u);
+  bool finalPhase = false;
+  int owner = (int)lane;           // lane of this warp that owns the ray whose piece this lane is walking
+  uint32_t ownDst = 0;             // where the ray this lane OWNS reports to: hits[entry] / occl[id]
+#endif
   int stack[EID_STACK_SIZE];
-  int sp = 0, cur = EID_TRAV_DONE;
+  int sp = 0, sb = 0, cur = EID_TRAV_DONE;   // valid stack entries: stack[sb .. sb + sp)
+  int age = 0;                               // node visits of the piece this lane is walking
   bool active = false, more = true;
   uint32_t entry = 0, id = 0;
   f3 o = mk3(0.f), d = mk3(0.f);
@@ -442,33 +473,106 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
           tmax = ANY ? r0.w : 1e28f;
           hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
           rb = makeRayBox(o, d);
-          sp = 0; active = true;
+          sp = 0; sb = 0; active = true; age = 0;
           // no triangles, or a direction with NaN / zero length (det can never be != 0): finished at once, as in traverse()
           cur = (A.triCount == 0 || !(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) ? EID_TRAV_DONE : A.rootRef;
         }
       }
     }
     if (!__ballot_sync(0xffffffffu, active)) break;
+#if EID_TQ_STEAL
+    if (!more) {                                       // warp-uniform: this warp fetches no more rays
+      if (!finalPhase) {                               // every ray in flight is owned by the lane that fetched it
+        finalPhase = true;
+        owner = (int)lane; ownDst = ANY ? id : entry;
+        mySlot.t = 0.f; mySlot.u = mySlot.v = 0.f; mySlot.tri = -1; mySlot.prim = mySlot.inst = 0x7fffffff; mySlot.outstanding = active ? 1 : 0;
+        __syncwarp();
+      }
+      if (ANY && active && warpSlots[owner].tri >= 0) cur = EID_TRAV_DONE;      // another piece of this occlusion ray already hit something
+#pragma unroll 1
+      for (int s = 0; s < EID_TQ_STEALS_PER_ROUND; ++s) {
+        const unsigned idleM = __ballot_sync(0xffffffffu, !active);
+        if (__popc(idleM) < EID_TQ_STEAL_MIN_IDLE) break;
+        const int avail = (active && cur != EID_TRAV_DONE && age >= EID_TQ_STEAL_MIN_AGE) ? sp : 0;
+        const int best = __reduce_max_sync(0xffffffffu, (avail << 5) | (int)lane);
+        if ((best >> 5) < 1) break;
+        const int donor = best & 31, thief = __ffs(idleM) - 1;
+        int ref = 0;
+        if ((int)lane == donor) { ref = stack[sb]; ++sb; --sp; }                // the oldest entry = the largest pending subtree
+        ref = __shfl_sync(0xffffffffu, ref, donor);
+        const int ow = __shfl_sync(0xffffffffu, owner, donor);
+        const float ox = __shfl_sync(0xffffffffu, o.x, donor), oy = __shfl_sync(0xffffffffu, o.y, donor), oz = __shfl_sync(0xffffffffu, o.z, donor);
+        const float dx = __shfl_sync(0xffffffffu, d.x, donor), dy = __shfl_sync(0xffffffffu, d.y, donor), dz = __shfl_sync(0xffffffffu, d.z, donor);
+        const float tm = __shfl_sync(0xffffffffu, tmax, donor);
+        const float ht = __shfl_sync(0xffffffffu, hit.t, donor), hu = __shfl_sync(0xffffffffu, hit.u, donor), hv = __shfl_sync(0xffffffffu, hit.v, donor);
+        const int htri = __shfl_sync(0xffffffffu, hit.tri, donor), hprim = __shfl_sync(0xffffffffu, hit.prim, donor), hinst = __shfl_sync(0xffffffffu, hit.inst, donor);
+        if ((int)lane == thief) {
+          o = mk3(ox, oy, oz); d = mk3(dx, dy, dz); tmax = tm;
+          hit.t = ht; hit.u = hu; hit.v = hv; hit.tri = htri; hit.prim = hprim; hit.inst = hinst; hit.flags = 0;   // only better candidates are taken
+          rb = makeRayBox(o, d);
+          owner = ow; cur = ref; sp = 0; sb = 0; active = true; age = EID_TQ_STEAL_MIN_AGE;   // a piece of a long ray may be split again at once
+        }
+        if ((int)lane == ow) mySlot.outstanding++;
+        __syncwarp();
+      }
+    }
+#endif
 #pragma unroll 1
     for (int it = 0; it < EID_TQ_NODE_STEPS; ++it) {
       const bool inner = active && cur >= 0;
       if (!__any_sync(0xffffffffu, inner)) break;
       if (inner) {
         if (STATS) ++nodeVisits;
-        nodeStep<ANY, true>(A, rb, hit.t, cur, stack, sp);
+        ++age;
+        nodeStep<ANY, true>(A, rb, hit.t, cur, stack + sb, sp);
       }
     }
     if (active && cur < 0) {
       if (cur != EID_TRAV_DONE) {
         if (leafStep<ANY, STATS, false>(A, cur, o, d, tmax, hit, &triTests, low)) cur = EID_TRAV_DONE;
-        else cur = EID_POP();
+        else cur = (sp ? stack[sb + --sp] : EID_TRAV_DONE);
       }
+#if EID_TQ_STEAL
+      if (cur == EID_TRAV_DONE && !finalPhase) {
+#else
       if (cur == EID_TRAV_DONE) {
+#endif
         if (ANY) occl[id] = hit.tri >= 0 ? 1u : 0u;
         else hits[entry] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
         active = false;
       }
     }
+#if EID_TQ_STEAL
+    if (finalPhase) {
+      // finished pieces report to the lane that owns their ray; the owner writes once its last piece is in
+      bool fin = active && cur == EID_TRAV_DONE;
+      if (fin && owner == (int)lane && mySlot.outstanding == 1 && mySlot.tri < 0) {
+        // the common case — a ray that was never robbed (and is no thief's piece): written at once, like before the queue drained
+        if (ANY) occl[ownDst] = hit.tri >= 0 ? 1u : 0u;
+        else hits[ownDst] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+        mySlot.outstanding = 0;
+        active = false; fin = false;
+      }
+      unsigned finM = __ballot_sync(0xffffffffu, fin);
+      while (finM) {
+        const int src = __ffs(finM) - 1;
+        finM &= finM - 1;
+        const int ow = __shfl_sync(0xffffffffu, owner, src);
+        const float ht = __shfl_sync(0xffffffffu, hit.t, src), hu = __shfl_sync(0xffffffffu, hit.u, src), hv = __shfl_sync(0xffffffffu, hit.v, src);
+        const int htri = __shfl_sync(0xffffffffu, hit.tri, src), hprim = __shfl_sync(0xffffffffu, hit.prim, src), hinst = __shfl_sync(0xffffffffu, hit.inst, src);
+        if ((int)lane == ow) {
+          const bool better = htri >= 0 && (mySlot.tri < 0 || ht < mySlot.t || (ht == mySlot.t && (hinst < mySlot.inst || (hinst == mySlot.inst && hprim < mySlot.prim))));
+          if (better) { mySlot.t = ht; mySlot.u = hu; mySlot.v = hv; mySlot.tri = htri; mySlot.prim = hprim; mySlot.inst = hinst; }
+          if (--mySlot.outstanding == 0) {
+            if (ANY) occl[ownDst] = mySlot.tri >= 0 ? 1u : 0u;
+            else hits[ownDst] = make_float4(mySlot.tri >= 0 ? mySlot.t : 1e28f, mySlot.u, mySlot.v, __int_as_float(mySlot.tri));
+          }
+        }
+        __syncwarp();
+      }
+      if (fin) active = false;
+    }
+#endif
   }
   if (STATS) {
 #pragma unroll

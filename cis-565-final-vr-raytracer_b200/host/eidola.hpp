@@ -112,6 +112,14 @@ class Group {
   static Layout layout(uint32_t height, int world, int rank = 0) { Layout l{}; check(eid_group_layout(height, world, rank, &l.y0, &l.y1, &l.paddedHeight)); return l; }
   static void uniqueId(unsigned char id[128]) { check(eid_group_unique_id(id)); }
   void create(Renderer& r, int rank, int world, const unsigned char* id128 = nullptr) { destroy(); check(eid_group_create(&m_h, r.handle(), rank, world, id128)); }
+  // stage pipeline (csrc/pipeline.cu): direct | indirect | post ranks joined by NVLink peer copies; the renderer needs pipelineLayout().paddedHeight rows
+  static eid_pipeline_layout pipelineLayout(uint32_t height, int world, int rank, int nDirect = 0, int nIndirect = 0, int nPost = 0) {
+    eid_pipeline_layout l{}; check(eid_group_pipeline_layout(height, world, rank, nDirect, nIndirect, nPost, &l)); return l;
+  }
+  static void randomId(unsigned char id[128]) { check(eid_group_random_id(id)); }
+  void createPipeline(Renderer& r, int rank, int world, const unsigned char* id128, uint32_t height, int nDirect = 0, int nIndirect = 0, int nPost = 0) {
+    destroy(); check(eid_group_create_pipeline(&m_h, r.handle(), rank, world, id128, height, nDirect, nIndirect, nPost));
+  }
   void setMode(bool postSharded, int history, bool gatherFinal) { check(eid_group_set_mode(m_h, postSharded, history, gatherFinal)); }
   void run(const RtxState& state, int frames) { check(eid_group_run(m_h, &state, frames)); }       // the whole multi-GPU frame, asynchronous
   void renderToHostAsync(const SceneCamera* cam, const RtxState& st, int frames, float* direct, float* indirect) {
