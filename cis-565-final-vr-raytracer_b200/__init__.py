@@ -32,7 +32,7 @@ EXPORTS = [
     "eid_scene_create", "eid_scene_load_gltf", "eid_scene_load_desc", "eid_scene_provide_image", "eid_scene_destroy", "eid_scene_set_lookat",
     "eid_scene_update_camera", "eid_scene_set_camera", "eid_scene_get_camera", "eid_scene_get_info",
     "eid_scene_table_bytes", "eid_scene_read_table",
-    "eid_accel_build", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
+    "eid_accel_build", "eid_accel_build_ex", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
     "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
@@ -73,6 +73,7 @@ def lib():
         "eid_scene_table_bytes": (C.c_int64, [vp, i32, u32]),
         "eid_scene_read_table": (i32, [vp, i32, u32, vp, sz]),
         "eid_accel_build": (i32, [vp, C.POINTER(vp)]),
+        "eid_accel_build_ex": (i32, [vp, i32, C.POINTER(vp)]),
         "eid_accel_destroy": (None, [vp]),
         "eid_accel_get_info": (i32, [vp, C.POINTER(AccelInfo)]),
         "eid_accel_trace": (i32, [vp, vp, u32, i32, vp]),
@@ -218,9 +219,9 @@ class AccelStructure:
     def __init__(self):
         self._h = C.c_void_p()
 
-    def create(self, scene):             # AccelStructure::create(gltfScene, vertexBufs, indexBufs)
+    def create(self, scene, mode=abi.ACCEL_AUTO):   # AccelStructure::create(gltfScene, vertexBufs, indexBufs); mode: flat / two-level (BLAS + TLAS)
         self.destroy()
-        _check(lib().eid_accel_build(scene._h, C.byref(self._h)))
+        _check(lib().eid_accel_build_ex(scene._h, int(mode), C.byref(self._h)))
         self._scene = scene
 
     def info(self):

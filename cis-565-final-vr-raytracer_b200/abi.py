@@ -159,7 +159,11 @@ class SceneInfo(C.Structure):
 
 class AccelInfo(C.Structure):
     _fields_ = [("triangleCount", C.c_uint64), ("nodeCount", C.c_uint32), ("maxDepth", C.c_uint32),
-                ("nodeBytes", C.c_uint64), ("triBytes", C.c_uint64), ("buildMs", C.c_float)]
+                ("nodeBytes", C.c_uint64), ("triBytes", C.c_uint64), ("buildMs", C.c_float),
+                ("twoLevel", C.c_int32), ("blasCount", C.c_uint32), ("tlasNodeCount", C.c_uint32), ("instanceCount", C.c_uint32)]
+
+
+ACCEL_AUTO, ACCEL_FLAT, ACCEL_TWO_LEVEL = 0, 1, 2
 
 
 EID_K_COUNT = 5

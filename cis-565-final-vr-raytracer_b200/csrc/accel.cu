@@ -377,14 +377,250 @@ __global__ void k_trace_batch(AccelView A, const InstanceXform* __restrict__ ins
   RayHit h;
   eid_hit out;
   if (anyHit) {
-    bool occ = traverse<true>(A, o, d, r[3], h);
+    bool occ = A.twoLevel ? traverse2<true>(A, o, d, r[3], h) : traverse<true>(A, o, d, r[3], h);
     out.hitT = occ ? 0.f : 1e28f; out.primitiveID = out.instanceID = out.instanceCustomIndex = -1; out.baryU = out.baryV = 0.f;
   } else {
-    bool ok = traverse<false>(A, o, d, r[3], h);
+    bool ok = A.twoLevel ? traverse2<false>(A, o, d, r[3], h) : traverse<false>(A, o, d, r[3], h);
     if (ok) { out.hitT = h.t; out.primitiveID = h.prim; out.instanceID = h.inst; out.instanceCustomIndex = instances[h.inst].primMesh; out.baryU = h.u; out.baryV = h.v; }
     else { out.hitT = 1e28f; out.primitiveID = out.instanceID = out.instanceCustomIndex = -1; out.baryU = out.baryV = 0.f; }
   }
   hits[i] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-level build (AccelStructure::create, accelstruct.cpp:55-162: one BLAS per prim mesh, one TLAS instance per node)
+// ------------------------------------------------------------------------------------------------
+// object-space triangles of ONE prim mesh: 48-byte records (p0, p1, p2, primitiveID), unpadded boxes, mesh bounds
+__global__ void k_emit_object(DeviceSceneView sc, int primMesh, uint32_t nTri, float4* __restrict__ triOut, float* __restrict__ boxLo, float* __restrict__ boxHi,
+                              BuildBounds* bounds) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  if (t < nTri) {
+    const InstanceData gi = sc.geoInfo[primMesh];
+    const uint32_t* idx = (const uint32_t*)(uintptr_t)gi.indexAddress;
+    const VertexAttributes* vtx = (const VertexAttributes*)(uintptr_t)gi.vertexAddress;
+    f3 p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = ld3(vtx[idx[3 * t + k]].position);
+    triOut[3 * (size_t)t + 0] = make_float4(p[0].x, p[0].y, p[0].z, p[1].x);
+    triOut[3 * (size_t)t + 1] = make_float4(p[1].y, p[1].z, p[2].x, p[2].y);
+    triOut[3 * (size_t)t + 2] = make_float4(p[2].z, __int_as_float((int)t), 0.f, 0.f);
+    lo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); hi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x));
+    lo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); hi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y));
+    lo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z)); hi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { boxLo[3 * (size_t)t + k] = lo[k]; boxHi[3 * (size_t)t + k] = hi[k]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float l = lo[k], h = hi[k];
+    for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o)); h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&bounds->lo[k], floatFlip(l)); atomicMax(&bounds->hi[k], floatFlip(h)); }
+  }
+}
+// a tree that was built on its own is appended to the shared arrays: inner references move by nodeBase, leaf ranges by primBase
+__global__ void k_rebase(float4* __restrict__ nodes, uint32_t count, int nodeBase, int primBase) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float4 rf = nodes[8 * (size_t)i + 6];
+  int r[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+  for (int k = 0; k < 4; ++k) {
+    if (r[k] >= 0) r[k] += nodeBase;
+    else { const uint32_t u = ~(uint32_t)r[k]; if (u & 7u) r[k] = ~(int)((((u >> 3) + (uint32_t)primBase) << 3) | (u & 7u)); }
+  }
+  nodes[8 * (size_t)i + 6] = make_float4(__int_as_float(r[0]), __int_as_float(r[1]), __int_as_float(r[2]), __int_as_float(r[3]));
+}
+static int rebaseRef(int r, int nodeBase, int primBase) {
+  if (r >= 0) return r + nodeBase;
+  const uint32_t u = ~(uint32_t)r;
+  return (u & 7u) ? ~(int)((((u >> 3) + (uint32_t)primBase) << 3) | (u & 7u)) : r;
+}
+
+struct TreeBuild { float4* nodes = nullptr; uint32_t nodeCount = 0, levels = 0; int32_t rootRef = ~0; };
+
+// The flat builder's pipeline (Morton keys of the padded boxes, radix sort, Karras tree, refit, 4-wide collapse) over ANY list of
+// 48-byte primitive records with boxes: the triangles of one prim mesh (BLAS) or the instances (TLAS).  primOut receives the records in
+// Morton order (what the leaves index); lo0 / hi0 are padded in place; `bounds` must hold the union of the boxes.
+static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0, const BuildBounds* bounds, float4* primOut, TreeBuild& T) {
+#if EID_BVH_WIDTH != 4 || EID_NODE_Q8
+  raise(EID_ERR_UNSUPPORTED, "the two-level build needs the default 128-byte BVH4 node");
+#else
+  const int B = 256;
+  const uint32_t G = (n + B - 1) / B;
+  float *lo1 = nullptr, *hi1 = nullptr; unsigned long long *keys = nullptr, *keysSorted = nullptr; uint32_t *vals = nullptr, *valsSorted = nullptr;
+  int *left = nullptr, *right = nullptr, *parI = nullptr, *parL = nullptr, *rf = nullptr, *rl = nullptr, *height = nullptr;
+  float *nlo = nullptr, *nhi = nullptr; unsigned int *arrived = nullptr; void* tmp = nullptr;
+  float4* wideTmp = nullptr; int2 *q0 = nullptr, *q1 = nullptr; unsigned int* counters = nullptr;
+  auto freeAll = [&]() {
+    cudaFree(lo1); cudaFree(hi1); cudaFree(keys); cudaFree(keysSorted); cudaFree(vals); cudaFree(valsSorted); cudaFree(left); cudaFree(right); cudaFree(parI);
+    cudaFree(parL); cudaFree(rf); cudaFree(rl); cudaFree(height); cudaFree(nlo); cudaFree(nhi); cudaFree(arrived); cudaFree(tmp); cudaFree(wideTmp); cudaFree(q0);
+    cudaFree(q1); cudaFree(counters);
+  };
+  try {
+    CUDA_CHECK(cudaMalloc(&lo1, (size_t)n * 12)); CUDA_CHECK(cudaMalloc(&hi1, (size_t)n * 12));
+    CUDA_CHECK(cudaMalloc(&keys, (size_t)n * 8)); CUDA_CHECK(cudaMalloc(&keysSorted, (size_t)n * 8));
+    CUDA_CHECK(cudaMalloc(&vals, (size_t)n * 4)); CUDA_CHECK(cudaMalloc(&valsSorted, (size_t)n * 4));
+    k_morton<<<G, B>>>(n, lo0, hi0, bounds, keys, vals);
+    size_t tmpBytes = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
+    CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
+    k_reorder<<<G, B>>>(n, valsSorted, primTmp, lo0, hi0, primOut, lo1, hi1);
+    if (n == 1) { T.nodes = nullptr; T.nodeCount = 0; T.levels = 0; T.rootRef = ~((0 << 3) | 1); freeAll(); return; }
+    const uint32_t nInner = n - 1;
+    CUDA_CHECK(cudaMalloc(&left, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&right, (size_t)nInner * 4));
+    CUDA_CHECK(cudaMalloc(&parI, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&parL, (size_t)n * 4));
+    CUDA_CHECK(cudaMalloc(&rf, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&rl, (size_t)nInner * 4));
+    CUDA_CHECK(cudaMalloc(&height, (size_t)nInner * 4));
+    CUDA_CHECK(cudaMalloc(&nlo, (size_t)nInner * 12)); CUDA_CHECK(cudaMalloc(&nhi, (size_t)nInner * 12));
+    CUDA_CHECK(cudaMalloc(&arrived, (size_t)nInner * 4));
+    CUDA_CHECK(cudaMemset(arrived, 0, (size_t)nInner * 4));
+    k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)n, keysSorted, left, right, parI, parL, rf, rl);
+    k_refit<<<G, B>>>((int)n, left, right, parI, parL, lo1, hi1, nlo, nhi, height, arrived);
+    if (n <= LEAF_MAX) { T.nodes = nullptr; T.nodeCount = 0; T.levels = 0; T.rootRef = ~(int)((0u << 3) | n); freeAll(); return; }   // the whole list is one leaf
+    CUDA_CHECK(cudaMalloc(&wideTmp, (size_t)nInner * 128));
+    CUDA_CHECK(cudaMalloc(&q0, (size_t)nInner * 8)); CUDA_CHECK(cudaMalloc(&q1, (size_t)nInner * 8));
+    CUDA_CHECK(cudaMalloc(&counters, 8));
+    const int2 rootItem = make_int2(0, 0);
+    const unsigned int init[2] = {0u, 1u};
+    CUDA_CHECK(cudaMemcpy(q0, &rootItem, 8, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(counters, init, 8, cudaMemcpyHostToDevice));
+    unsigned int nIn = 1, levels = 0;
+    while (nIn) {
+      CUDA_CHECK(cudaMemsetAsync(counters, 0, 4));
+      k_collapse4<<<(nIn + 127) / 128, 128>>>((int)nIn, q0, q1, counters, left, right, rf, rl, lo1, hi1, nlo, nhi, wideTmp);
+      CUDA_CHECK(cudaMemcpy(&nIn, counters, 4, cudaMemcpyDeviceToHost));
+      std::swap(q0, q1);
+      if (++levels > 200) raise(EID_ERR_UNSUPPORTED, "BVH collapse did not terminate");
+    }
+    unsigned int wideCount = 0;
+    CUDA_CHECK(cudaMemcpy(&wideCount, counters + 1, 4, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMalloc(&T.nodes, (size_t)wideCount * 128));
+    CUDA_CHECK(cudaMemcpy(T.nodes, wideTmp, (size_t)wideCount * 128, cudaMemcpyDeviceToDevice));
+    T.nodeCount = wideCount; T.levels = levels; T.rootRef = 0;
+  } catch (...) { freeAll(); throw; }
+  freeAll();
+#endif
+}
+
+static void buildAccelTwoLevel(eid_scene* s, eid_accel* a) {
+  const SceneHost& H = s->host;
+  CUDA_CHECK(cudaSetDevice(s->dev.device));
+  const size_t nMesh = H.gltf.primMeshes.size(), nInst = H.instances.size();
+  a->scene = s; a->twoLevel = true;
+  cudaEvent_t ev0, ev1;
+  CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
+  CUDA_CHECK(cudaEventRecord(ev0, 0));
+  // ---- bottom level: one tree per prim mesh that some instance uses ----
+  std::vector<uint32_t> meshTris(nMesh, 0);
+  std::vector<char> used(nMesh, 0);
+  for (const InstanceXform& X : H.instances) { used[X.primMesh] = 1; meshTris[X.primMesh] = X.triangleCount; }
+  uint64_t unique = 0;
+  for (size_t m = 0; m < nMesh; ++m) if (used[m]) unique += meshTris[m];
+  if (unique >= (1ull << 28) - 8) raise(EID_ERR_UNSUPPORTED, "eid_accel_build: more than 2^28 - 8 unique triangles");
+  a->triCount = (uint32_t)unique; a->uniqueTriangles = unique;
+  struct Blas { TreeBuild T; uint32_t primBase = 0, nodeBase = 0; float lo[3], hi[3]; bool valid = false; };
+  std::vector<Blas> blas(nMesh);
+  float4* triTmp = nullptr; float *lo0 = nullptr, *hi0 = nullptr; BuildBounds* bounds = nullptr;
+  auto freeTmp = [&]() { cudaFree(triTmp); cudaFree(lo0); cudaFree(hi0); triTmp = nullptr; lo0 = hi0 = nullptr; };
+  try {
+    CUDA_CHECK(cudaMalloc(&a->tris, std::max<size_t>(1, unique) * 48));
+    CUDA_CHECK(cudaMalloc(&bounds, sizeof(BuildBounds)));
+    uint32_t primBase = 0, nodeTotal = 0, maxBlasLevels = 0;
+    for (size_t m = 0; m < nMesh; ++m) {
+      if (!used[m] || meshTris[m] == 0) continue;
+      const uint32_t n = meshTris[m];
+      CUDA_CHECK(cudaMalloc(&triTmp, (size_t)n * 48)); CUDA_CHECK(cudaMalloc(&lo0, (size_t)n * 12)); CUDA_CHECK(cudaMalloc(&hi0, (size_t)n * 12));
+      k_init_bounds<<<1, 1>>>(bounds);
+      k_emit_object<<<(n + 255) / 256, 256>>>(s->dev.view(H), (int)m, n, triTmp, lo0, hi0, bounds);
+      BuildBounds hb;
+      CUDA_CHECK(cudaMemcpy(&hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost));
+      Blas& b = blas[m];
+      for (int k = 0; k < 3; ++k) {
+        const int l = hb.lo[k], h = hb.hi[k];
+        int li = l >= 0 ? l : l ^ 0x7fffffff, hi_ = h >= 0 ? h : h ^ 0x7fffffff;
+        memcpy(&b.lo[k], &li, 4); memcpy(&b.hi[k], &hi_, 4);
+      }
+      buildTree(n, triTmp, lo0, hi0, bounds, a->tris + 3 * (size_t)primBase, b.T);
+      b.primBase = primBase; b.nodeBase = nodeTotal; b.valid = true;
+      primBase += n; nodeTotal += b.T.nodeCount; maxBlasLevels = std::max(maxBlasLevels, b.T.levels);
+      a->blasCount++;
+      freeTmp();
+    }
+    CUDA_CHECK(cudaMalloc(&a->nodes, std::max<size_t>(1, nodeTotal) * 128));
+    for (size_t m = 0; m < nMesh; ++m) {
+      Blas& b = blas[m];
+      if (!b.valid) continue;
+      if (b.T.nodeCount) {
+        k_rebase<<<(b.T.nodeCount + 127) / 128, 128>>>(b.T.nodes, b.T.nodeCount, (int)b.nodeBase, (int)b.primBase);
+        CUDA_CHECK(cudaMemcpy(a->nodes + 8 * (size_t)b.nodeBase, b.T.nodes, (size_t)b.T.nodeCount * 128, cudaMemcpyDeviceToDevice));
+        cudaFree(b.T.nodes); b.T.nodes = nullptr;
+      }
+      b.T.rootRef = rebaseRef(b.T.rootRef, (int)b.nodeBase, (int)b.primBase);
+    }
+    a->nodeCount = nodeTotal; a->nodeAlloc = nodeTotal; a->rootRef = ~0;
+    // ---- top level: the instances' world boxes (the object bounds through objectToWorld, 8 corners, padded) ----
+    std::vector<float> ilo, ihi; std::vector<float4> irec;
+    float slo[3] = {3e38f, 3e38f, 3e38f}, shi[3] = {-3e38f, -3e38f, -3e38f};
+    for (size_t i = 0; i < nInst; ++i) {
+      const InstanceXform& X = H.instances[i];
+      const Blas& b = blas[X.primMesh];
+      if (!b.valid) continue;
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int c = 0; c < 8; ++c) {
+        const double p[3] = {(c & 1) ? b.hi[0] : b.lo[0], (c & 2) ? b.hi[1] : b.lo[1], (c & 4) ? b.hi[2] : b.lo[2]};
+        for (int k = 0; k < 3; ++k) {
+          const double w = (double)X.objectToWorld[k] * p[0] + (double)X.objectToWorld[3 + k] * p[1] + (double)X.objectToWorld[6 + k] * p[2] + (double)X.objectToWorld[9 + k];
+          lo[k] = std::min(lo[k], w); hi[k] = std::max(hi[k], w);
+        }
+      }
+      for (int k = 0; k < 3; ++k) {
+        // the flat build transforms every vertex in fp32: pad by a few ulps of the largest coordinate plus a fraction of the extent
+        const double pad = 1e-5 * (hi[k] - lo[k]) + 2e-6 * std::max(std::fabs(lo[k]), std::fabs(hi[k])) + 1e-7;
+        const float l = (float)(lo[k] - pad), h = (float)(hi[k] + pad);
+        ilo.push_back(l); ihi.push_back(h);
+        slo[k] = std::min(slo[k], l); shi[k] = std::max(shi[k], h);
+      }
+      float fi, fr; const int ii = (int)i, rr = b.T.rootRef;
+      memcpy(&fi, &ii, 4); memcpy(&fr, &rr, 4);
+      irec.push_back(make_float4(fi, fr, 0.f, 0.f));
+      irec.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); irec.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    const uint32_t nTop = (uint32_t)(ilo.size() / 3);
+    a->tlasPrimCount = nTop;
+    CUDA_CHECK(cudaMalloc(&a->tlasPrims, std::max<size_t>(1, nTop) * 48));
+    uint32_t tlasLevels = 0;
+    if (nTop) {
+      BuildBounds hb;
+      for (int k = 0; k < 3; ++k) {
+        int li, hi_; memcpy(&li, &slo[k], 4); memcpy(&hi_, &shi[k], 4);
+        hb.lo[k] = li >= 0 ? li : li ^ 0x7fffffff; hb.hi[k] = hi_ >= 0 ? hi_ : hi_ ^ 0x7fffffff;
+      }
+      CUDA_CHECK(cudaMemcpy(bounds, &hb, sizeof(hb), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMalloc(&triTmp, (size_t)nTop * 48)); CUDA_CHECK(cudaMalloc(&lo0, (size_t)nTop * 12)); CUDA_CHECK(cudaMalloc(&hi0, (size_t)nTop * 12));
+      CUDA_CHECK(cudaMemcpy(triTmp, irec.data(), (size_t)nTop * 48, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(lo0, ilo.data(), (size_t)nTop * 12, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(hi0, ihi.data(), (size_t)nTop * 12, cudaMemcpyHostToDevice));
+      TreeBuild T;
+      buildTree(nTop, triTmp, lo0, hi0, bounds, a->tlasPrims, T);
+      a->tlasNodes = T.nodes; a->tlasNodeCount = T.nodeCount; a->tlasRootRef = T.rootRef; tlasLevels = T.levels;
+      freeTmp();
+    }
+    if (!a->tlasNodes) CUDA_CHECK(cudaMalloc(&a->tlasNodes, 128));
+    a->maxDepth = tlasLevels + maxBlasLevels;
+    if (3 * (tlasLevels + maxBlasLevels) + 8 >= EID_STACK_SIZE) raise(EID_ERR_UNSUPPORTED, "two-level BVH depth %u + %u exceeds the traversal stack (%d)", tlasLevels, maxBlasLevels, EID_STACK_SIZE);
+    CUDA_CHECK(cudaEventRecord(ev1, 0));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventElapsedTime(&a->buildMs, ev0, ev1));
+  } catch (...) {
+    freeTmp(); cudaFree(bounds);
+    for (Blas& b : blas) cudaFree(b.T.nodes);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    throw;
+  }
+  cudaFree(bounds);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
 }
 
 static void buildAccel(eid_scene* s, eid_accel* a) {
@@ -709,24 +945,37 @@ int eid_scene_read_table(eid_scene* s, int table, uint32_t index, void* dst, siz
   EID_CATCH
 }
 
-int eid_accel_build(eid_scene* s, eid_accel** out) {
+int eid_accel_build_ex(eid_scene* s, int mode, eid_accel** out) {
   EID_TRY
   if (!s || !out) raise(EID_ERR_INVALID, "eid_accel_build: null argument");
+  if (mode < EID_ACCEL_AUTO || mode > EID_ACCEL_TWO_LEVEL) raise(EID_ERR_INVALID, "eid_accel_build_ex: mode must be EID_ACCEL_AUTO, _FLAT or _TWO_LEVEL");
   if (!s->loaded) raise(EID_ERR_STATE, "eid_accel_build before a scene was loaded");
   if (s->dev.device == EID_DEVICE_NONE) raise(EID_ERR_CUDA, "eid_accel_build on a host-only scene: the BVH build and every kernel need a CUDA device (no CPU fallback)");
+  bool two = mode == EID_ACCEL_TWO_LEVEL;
+  if (mode == EID_ACCEL_AUTO) {
+    // instancing pays once the flattened list would be at least twice the unique triangles (the flat tree traces faster: one level, FFMA2 walk)
+    const SceneHost& H = s->host;
+    std::vector<uint32_t> meshTris(H.gltf.primMeshes.size(), 0);
+    for (const InstanceXform& X : H.instances) meshTris[X.primMesh] = X.triangleCount;
+    uint64_t unique = 0;
+    for (uint32_t t : meshTris) unique += t;
+    two = unique > 0 && H.triangleInstances >= 2 * unique;
+  }
   eid_accel* a = new eid_accel();
-  try { buildAccel(s, a); }
-  catch (...) { cudaFree(a->nodes); cudaFree(a->tris); delete a; throw; }
+  try { if (two) buildAccelTwoLevel(s, a); else buildAccel(s, a); }
+  catch (...) { cudaFree(a->nodes); cudaFree(a->tris); cudaFree(a->tlasNodes); cudaFree(a->tlasPrims); delete a; throw; }
   *out = a;
   return EID_OK;
   EID_CATCH
 }
 
+int eid_accel_build(eid_scene* s, eid_accel** out) { return eid_accel_build_ex(s, EID_ACCEL_AUTO, out); }
+
 void eid_accel_destroy(eid_accel* a) {
   if (!a) return;
   if (a->nodeTex) cudaDestroyTextureObject(a->nodeTex);
   if (a->triTex) cudaDestroyTextureObject(a->triTex);
-  cudaFree(a->nodes); cudaFree(a->tris);
+  cudaFree(a->nodes); cudaFree(a->tris); cudaFree(a->tlasNodes); cudaFree(a->tlasPrims);
   delete a;
 }
 
@@ -736,6 +985,8 @@ int eid_accel_get_info(eid_accel* a, eid_accel_info* o) {
   o->triangleCount = a->triCount; o->nodeCount = a->nodeCount; o->maxDepth = a->maxDepth;
   o->nodeBytes = (uint64_t)std::max<uint32_t>(1u, a->nodeAlloc) * EID_NODE_BYTES; o->triBytes = (uint64_t)a->triCount * 48;
   o->buildMs = a->buildMs;
+  o->twoLevel = a->twoLevel ? 1 : 0; o->blasCount = a->blasCount; o->tlasNodeCount = a->tlasNodeCount; o->instanceCount = a->twoLevel ? a->tlasPrimCount : (uint32_t)a->scene->host.instances.size();
+  if (a->twoLevel) o->nodeBytes += (uint64_t)std::max<uint32_t>(1u, a->tlasNodeCount) * 128 + (uint64_t)a->tlasPrimCount * 48;
   return EID_OK;
   EID_CATCH
 }

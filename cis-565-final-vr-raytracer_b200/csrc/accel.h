@@ -45,6 +45,13 @@ struct AccelView {
   uint32_t triCount;
   int32_t rootRef;      // child-style reference of the root
   cudaTextureObject_t nodeTex, triTex;   // the same two arrays as linear float4 textures (TEX-pipe fetch experiments, EID_FETCH_TEX)
+  // two-level form (trace.cuh: traverse2): `nodes` / `tris` then hold the bottom-level trees (object-space triangles) of all prim meshes
+  int32_t twoLevel;
+  int32_t tlasRootRef;
+  uint32_t tlasPrimCount;
+  const float4* tlasNodes;
+  const float4* tlasPrims;               // per TLAS primitive: (instance index, BLAS root reference, -, -) x 3 float4 (48-byte records like triangles)
+  const InstanceXform* instances;
 };
 
 struct SceneDevice {
@@ -84,5 +91,15 @@ struct eid_accel {
   int32_t rootRef = -1;
   float buildMs = 0.f;
   cudaTextureObject_t nodeTex = 0, triTex = 0;
-  eid::AccelView view() const { return eid::AccelView{nodes, tris, triCount, rootRef, nodeTex, triTex}; }
+  // two-level form: BLAS per prim mesh (nodes / tris above hold all of them) + TLAS over the instances
+  bool twoLevel = false;
+  float4* tlasNodes = nullptr;
+  float4* tlasPrims = nullptr;
+  uint32_t tlasPrimCount = 0, tlasNodeCount = 0, blasCount = 0;
+  int32_t tlasRootRef = -1;
+  uint64_t uniqueTriangles = 0;
+  eid::AccelView view() const {
+    return eid::AccelView{nodes, tris, triCount, rootRef, nodeTex, triTex, twoLevel ? 1 : 0, tlasRootRef, tlasPrimCount, tlasNodes, tlasPrims,
+                          scene ? scene->dev.instances : nullptr};
+  }
 };

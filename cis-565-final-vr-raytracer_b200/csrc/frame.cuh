@@ -148,11 +148,12 @@ DEV bool hitTest(const FrameParams& P, const RayHit& c, uint32_t& seed) {
 // others go through HitTest; a rejected candidate becomes the exclusive lower bound of the next query.
 template <bool STATS>
 DEV bool firstAcceptedHit(const FrameParams& P, f3 o, f3 d, float tmax, uint32_t& seed, RayHit& h, RayCounters& rc) {
-  if (!traverse<false, STATS>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris)) return false;
+  const bool two = P.accel.twoLevel != 0;          // instanced scenes: BLAS per prim mesh + TLAS (trace.cuh: traverse2), same hits
+  if (!(two ? traverse2<false, STATS>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris) : traverse<false, STATS>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris))) return false;
   while (!(h.flags & INST_FORCE_OPAQUE)) {
     if (hitTest(P, h, seed)) return true;
     const HitKey low = {h.t, h.inst, h.prim};
-    if (!traverse<false, STATS, true>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris, low)) return false;
+    if (!(two ? traverse2<false, STATS, true>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris, low) : traverse<false, STATS, true>(P.accel, o, d, tmax, h, &rc.nodes, &rc.tris, low))) return false;
   }
   return true;
 }
@@ -163,7 +164,8 @@ DEV bool closestHit(const FrameParams& P, f3 o, f3 d, Payload& prd, uint32_t& se
   rc.closest++;
   RayHit h;
   const bool hit = (FULL && P.hasNonOpaque) ? firstAcceptedHit<STATS>(P, o, d, EID_INFINITY, seed, h, rc)
-                                            : traverse<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris);
+                   : (FULL && P.accel.twoLevel) ? traverse2<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris)
+                                                : traverse<false, STATS>(P.accel, o, d, EID_INFINITY, h, &rc.nodes, &rc.tris);
   if (!hit) { prd.hitT = EID_INFINITY; return false; }
   prd.hitT = h.t; prd.baryU = h.u; prd.baryV = h.v; prd.primitiveID = h.prim; prd.instanceID = h.inst;
   prd.instanceCustomIndex = P.sc.instances[h.inst].primMesh;
@@ -177,6 +179,7 @@ DEV bool occlusion(const FrameParams& P, f3 origin, f3 dir, f3 surfacePos, float
                          fabsf(__fsub_rn(origin.z, surfacePos.z)));
   RayHit h;
   if (FULL && P.hasNonOpaque) return firstAcceptedHit<STATS>(P, origin, dir, tmax, seed, h, rc);
+  if (FULL && P.accel.twoLevel) return traverse2<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
   return traverse<true, STATS>(P.accel, origin, dir, tmax, h, &rc.nodes, &rc.tris);
 }
 

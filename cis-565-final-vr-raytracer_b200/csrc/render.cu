@@ -135,7 +135,7 @@ void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P)
   P.sCount = ((int)r->sFirst < st.size.y) ? (st.size.y - 1 - (int)r->sFirst) / (int)r->sStride + 1 : 0;   // stripes that start inside the frame
   P.counters = r->counters + EID_NUM_COUNTERS * set; P.totals = r->counters + 2 * EID_NUM_COUNTERS;
   memset(&P.wv, 0, sizeof(P.wv));
-  if (r->wavefront && !P.hasNonOpaque && st.maxDepth <= GI_MAX_WAVE_DEPTH) { r->ensureWave(st.maxDepth - 1); P.wv = r->waveView(); }
+  if (r->wavefront && !P.hasNonOpaque && !P.accel.twoLevel && st.maxDepth <= GI_MAX_WAVE_DEPTH) { r->ensureWave(st.maxDepth - 1); P.wv = r->waveView(); }
   r->lastSet = set; r->lastState = st; r->hasRun = true;
 }
 
@@ -155,7 +155,7 @@ void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   if (P.sCount > 0) {
     dim3 g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
-    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1 || P.accel.twoLevel;   // (the two-level walk lives in the full variants)
     const bool spatial = P.st.ReSTIRState == eSpatial || P.st.ReSTIRState == eSpatiotemporal;
     if (P.variant & EID_VARIANT_DIRECT_SPLIT) {
       launchDirectSplit(P, g, st, r->countVisits, tex);
@@ -190,7 +190,7 @@ void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
     // 8 x 8 quarter-res tiles on ABSOLUTE tile rows: a band that starts inside a tile row gets one more (masked) block row
     dim3 g((P.st.size.x / 2 + 7) / 8, P.sCount * ((((P.sFirst / 2) & 7) + P.sRows / 2 + 7) / 8));
-    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1;
+    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1 || P.accel.twoLevel;   // (the two-level walk lives in the full variants)
     if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
       // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
       // `shadow` stream while the main stream goes on with the next depth (small queues are latency-bound: the longest ray

@@ -386,6 +386,126 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
+// Two-level traversal (AccelStructure::create builds one BLAS per prim mesh and one TLAS instance per glTF node,
+// accelstruct.cpp:55-162): a top-level BVH4 over the instances' world boxes, and per prim mesh ONE bottom-level BVH4 over its
+// object-space triangles, shared by all its instances — memory no longer grows with the instance count.  The walk enters an instance
+// by taking the ray to object space (box tests only: conservative, with a slack per axis that covers the rounding of that transform) and
+// leaves it through a sentinel on the stack.  What DECIDES a hit is unchanged: the triangle's object-space vertices are taken to world
+// space with the instance matrix in the contract arithmetic (exactly what the flat build bakes, accel.cu: k_emit_triangles) and
+// Moller-Trumbore runs on the WORLD ray — so every hit, barycentric and tie-break is bit-identical to the flat BVH's.
+// Object triangle record (48 B): t0 = p0.xyz, p1.x   t1 = p1.yz, p2.xy   t2 = p2.z, primitiveID, -, -
+// TLAS primitive record (48 B):  t0 = instance index, BLAS root reference (as int bits), -, -
+// ------------------------------------------------------------------------------------------------------------------------------
+#define EID_TRAV_LEAVE_INSTANCE ((int)0x80000001)      // stack sentinel (like EID_TRAV_DONE never a valid reference)
+
+DEV float boxEntrySlack(const RayBox& rb, f3 sl, float nx, float ny, float nz, float fx, float fy, float fz, float tbest) {
+  const float tn = fmaxf(fmaxf(fmaf(nx, rb.ix, -rb.ox) - sl.x, fmaf(ny, rb.iy, -rb.oy) - sl.y), fmaxf(fmaf(nz, rb.iz, -rb.oz) - sl.z, 0.0f));
+  const float tf = fminf(fminf(fmaf(fx, rb.ix, -rb.ox) + sl.x, fmaf(fy, rb.iy, -rb.oy) + sl.y), fminf(fmaf(fz, rb.iz, -rb.oz) + sl.z, tbest));
+  return (tn <= tf * 1.000002f) ? tn : __int_as_float(0x7f800000);
+}
+// one inner-node visit of either level: the entered children are pushed far to near (closest hit) / in slot order (occlusion)
+template <bool ANY>
+DEV void nodeStep2(const float4* __restrict__ nodes, const RayBox& rb, f3 sl, float tbest, int& cur, int* stack, int& sp) {
+  const float INF = __int_as_float(0x7f800000);
+  const float4* n = nodes + 8 * (size_t)cur;
+  const float4 lx = __ldg(n + rb.nx), ly = __ldg(n + rb.ny), lz = __ldg(n + rb.nz);
+  const float4 hx = __ldg(n + rb.fx), hy = __ldg(n + rb.fy), hz = __ldg(n + rb.fz);
+  const float4 rf = __ldg(n + 6);
+  float e[4] = {boxEntrySlack(rb, sl, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, tbest), boxEntrySlack(rb, sl, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, tbest),
+                boxEntrySlack(rb, sl, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, tbest), boxEntrySlack(rb, sl, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, tbest)};
+  int c[4] = {__float_as_int(rf.x), __float_as_int(rf.y), __float_as_int(rf.z), __float_as_int(rf.w)};
+  if (!ANY) {
+#define EID_CSWAP(a, b) { if (e[b] < e[a]) { const float te = e[a]; e[a] = e[b]; e[b] = te; const int tc = c[a]; c[a] = c[b]; c[b] = tc; } }
+    EID_CSWAP(0, 1) EID_CSWAP(2, 3) EID_CSWAP(0, 2) EID_CSWAP(1, 3) EID_CSWAP(1, 2)
+#undef EID_CSWAP
+  }
+  int next = EID_TRAV_DONE; bool have = false;
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    if (e[k] < INF) {
+      if (have) stack[sp++] = next;               // what was found so far is farther (or, for occlusion rays, just another child)
+      next = c[k]; have = true;
+    }
+  }
+  cur = have ? next : stack[--sp];                // the stack always holds at least the bottom sentinel
+}
+
+// (not inlined: the callers are the already register-starved full variants of the stage kernels, whose flat path must not pay for this one)
+template <bool ANY, bool STATS = false, bool LOWER = false>
+__device__ __noinline__ bool traverse2(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsigned int* nodeVisits = nullptr, unsigned int* triTests = nullptr,
+                   HitKey low = HitKey{0.f, 0, 0}) {
+  hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
+  if (A.tlasPrimCount == 0) return false;
+  if (!(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) return false;
+  int stack[EID_STACK_SIZE];
+  int sp = 0;
+  stack[sp++] = EID_TRAV_DONE;                    // bottom sentinel: popping it ends the walk
+  RayBox rb = makeRayBox(o, d);
+  f3 sl = mk3(0.f);                               // box-test slack of the current level (0 in world space)
+  const float4* nodes = A.tlasNodes;
+  int inst = -1;                                  // instance the walk is inside of (-1: top level)
+  uint32_t iflags = 0;
+  int cur = A.tlasRootRef;
+  for (;;) {
+    while (cur >= 0) {
+      if (STATS) ++*nodeVisits;
+      nodeStep2<ANY>(nodes, rb, sl, hit.t, cur, stack, sp);
+    }
+    if (cur == EID_TRAV_DONE) break;
+    if (cur == EID_TRAV_LEAVE_INSTANCE) {         // back to the top level
+      inst = -1; nodes = A.tlasNodes; rb = makeRayBox(o, d); sl = mk3(0.f);
+      cur = stack[--sp];
+      continue;
+    }
+    const uint32_t ref = ~(uint32_t)cur;
+    const uint32_t first = ref >> 3, count = ref & 7u;
+    if (inst < 0) {
+      // top-level leaf: `count` instances.  Enter the first one now, leave the others on the stack as single-instance leaves.
+      if (count == 0) { cur = stack[--sp]; continue; }
+      for (uint32_t k = count - 1; k >= 1; --k) stack[sp++] = ~(int)(((first + k) << 3) | 1u);
+      const float4 rec = __ldg(A.tlasPrims + 3 * (size_t)first);
+      inst = __float_as_int(rec.x);
+      const InstanceXform& X = A.instances[inst];
+      iflags = X.flags & (INST_CULL_DISABLE | INST_MIRROR | INST_FORCE_OPAQUE);
+      // the ray in object space, for box tests only: plain fmaf arithmetic + a slack per axis that bounds its rounding error
+      // (|error of a transformed point| <= 4 ulp * sum |W_kj| |o_j| + |W_k3|; times 1 / |d_k| in the slab parameter; 16x safety)
+      const float* W = X.worldToObject;
+      const f3 oo = mk3(fmaf(W[0], o.x, fmaf(W[3], o.y, fmaf(W[6], o.z, W[9]))), fmaf(W[1], o.x, fmaf(W[4], o.y, fmaf(W[7], o.z, W[10]))),
+                        fmaf(W[2], o.x, fmaf(W[5], o.y, fmaf(W[8], o.z, W[11]))));
+      const f3 dd = mk3(fmaf(W[0], d.x, fmaf(W[3], d.y, W[6] * d.z)), fmaf(W[1], d.x, fmaf(W[4], d.y, W[7] * d.z)), fmaf(W[2], d.x, fmaf(W[5], d.y, W[8] * d.z)));
+      const f3 mag = mk3(fabsf(W[0] * o.x) + fabsf(W[3] * o.y) + fabsf(W[6] * o.z) + fabsf(W[9]), fabsf(W[1] * o.x) + fabsf(W[4] * o.y) + fabsf(W[7] * o.z) + fabsf(W[10]),
+                         fabsf(W[2] * o.x) + fabsf(W[5] * o.y) + fabsf(W[8] * o.z) + fabsf(W[11]));
+      rb = makeRayBox(oo, dd);
+      sl = mk3(4e-6f * mag.x * fabsf(rb.ix), 4e-6f * mag.y * fabsf(rb.iy), 4e-6f * mag.z * fabsf(rb.iz));
+      nodes = A.nodes;
+      stack[sp++] = EID_TRAV_LEAVE_INSTANCE;
+      cur = __float_as_int(rec.y);                // root of the prim mesh's bottom-level tree (an inner node or a leaf)
+      continue;
+    }
+    // bottom-level leaf: object-space triangles -> world space (contract arithmetic) -> Moller-Trumbore on the world ray
+    const InstanceXform& X = A.instances[inst];
+    bool done = false;
+    for (uint32_t k = 0; k < count; ++k) {
+      const float4* tp = A.tris + 3 * (size_t)(first + k);
+      if (STATS) ++*triTests;
+      const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+      const f3 p0 = xfPoint(X.objectToWorld, mk3(a.x, a.y, a.z)), p1 = xfPoint(X.objectToWorld, mk3(a.w, b.x, b.y)), p2 = xfPoint(X.objectToWorld, mk3(b.z, b.w, c.x));
+      float t, u, v;
+      if (triangleTest(p0, p1 - p0, p2 - p0, iflags, o, d, tmax, t, u, v)) {
+        if (ANY) { hit.t = t; hit.tri = (int)(first + k); done = true; break; }
+        const int prim = __float_as_int(c.y);
+        if (LOWER && (t < low.t || (t == low.t && (inst < low.inst || (inst == low.inst && prim <= low.prim))))) continue;
+        const bool better = t < hit.t || (t == hit.t && (inst < hit.inst || (inst == hit.inst && prim < hit.prim)));
+        if (hit.tri < 0 || better) { hit.t = t; hit.u = u; hit.v = v; hit.tri = (int)(first + k); hit.prim = prim; hit.inst = inst; hit.flags = iflags; }
+      }
+    }
+    if (done) return true;
+    cur = stack[--sp];
+  }
+  return hit.tri >= 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
 // Ray-queue traversal with dynamic fetch (wavefront stages): a persistent grid; every lane walks one ray of the queue at a
 // time and, when its ray ends, takes the next queue entry, so a warp keeps (nearly) all lanes busy although the rays' visit
 // counts differ by 10x (mean 13.5 nodes, worst ~150 on the C3 scene; in the one-ray-per-thread kernels a warp runs as long as

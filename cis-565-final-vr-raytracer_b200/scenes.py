@@ -173,6 +173,53 @@ def instanced_scene():
     return b.build(cam, "instanced_box")
 
 
+def instanced_grid(n=7, seed=11, offset=(0.0, 0.0, 0.0)):
+    """Heavy instancing: a room plus ONE noisy-blob prim mesh (12 x 12 x 2 triangles) instanced n x n times with random rotations,
+    non-uniform scales and every fourth one mirrored (negative determinant); `offset` moves the whole scene away from the origin (large
+    coordinates are the hard case for an object-space walk).  The flat BVH holds n * n copies of the blob, the two-level one a single tree."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    b = _Builder()
+    ox, oy, oz = offset
+    white = b.add_material(base=(0.8, 0.8, 0.8, 1), metallic=0.0, roughness=1.0)
+    red = b.add_material(base=(0.8, 0.25, 0.2, 1), metallic=0.2, roughness=0.6)
+    lamp = b.add_material(base=(0, 0, 0, 1), metallic=0.0, roughness=1.0, emissive=(14.0, 13.0, 11.0))
+    half = 0.9 * n
+    b.add_quads(_box_quads((ox - half, oy, oz - half), (ox + half, oy + 3.0, oz + half), "yYZxX", inward=True), white)
+    # the blob: a latitude / longitude grid on a unit sphere with radial noise, as independent triangles
+    m = 12
+    th = np.linspace(0.0, np.pi, m + 1)
+    ph = np.linspace(0.0, 2 * np.pi, m + 1)
+    rad = 0.35 + 0.12 * rng.random((m + 1, m + 1))
+    rad[:, -1] = rad[:, 0]
+    rad[0, :] = rad[0, 0]
+    rad[-1, :] = rad[-1, 0]
+    P = np.stack([rad * np.sin(th)[:, None] * np.cos(ph)[None, :], rad * np.cos(th)[:, None] + 0.5, rad * np.sin(th)[:, None] * np.sin(ph)[None, :]], axis=-1)
+    tris = []
+    for i in range(m):
+        for j in range(m):
+            a, bb, c, d = P[i, j], P[i + 1, j], P[i + 1, j + 1], P[i, j + 1]
+            for t in ([a, c, bb], [a, d, c]):
+                if np.linalg.norm(np.cross(t[1] - t[0], t[2] - t[0])) > 1e-9:       # (the pole rows collapse one edge)
+                    tris.append([tuple(v) for v in t])
+    first = True
+    blob = None
+    for i in range(n):
+        for j in range(n):
+            sx, sy, sz = 0.6 + 0.8 * rng.random(3)
+            if (i * n + j) % 4 == 3:
+                sx = -sx
+            mtx = _trs((ox + (i - (n - 1) / 2) * 1.6, oy + 0.05, oz + (j - (n - 1) / 2) * 1.6), float(rng.uniform(0, 360)), float(rng.uniform(-25, 25)), (sx, sy, sz))
+            if first:
+                b.add_tris(tris, red, matrix=mtx)
+                blob = len(b.prims) - 1
+                first = False
+            else:
+                b.nodes.append(dict(worldMatrix=mtx, primMesh=blob))
+    b.add_quads(_box_quads((ox - 0.8, oy + 2.9, oz - 0.8), (ox + 0.8, oy + 2.95, oz + 0.8), "y"), lamp)
+    cam = dict(eye=(ox + 0.2, oy + 2.2, oz - 0.85 * n), center=(ox, oy + 0.6, oz), up=(0.0, 1.0, 0.0), yfov=float(np.deg2rad(50.0)))
+    return b.build(cam, "instanced_grid")
+
+
 def _procedural_images(seed=21):
     """Five small RGBA8 images: colour checker, metallic-roughness map, tangent-space normal map, emissive pattern, transmission."""
     rng = np.random.Generator(np.random.PCG64(seed))

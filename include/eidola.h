@@ -183,6 +183,8 @@ typedef struct eid_accel_info {
   uint32_t maxDepth;
   uint64_t nodeBytes, triBytes;
   float    buildMs;
+  int32_t  twoLevel;           /* 1: BLAS per prim mesh + TLAS over the instances (triangleCount = unique triangles) */
+  uint32_t blasCount, tlasNodeCount, instanceCount;
 } eid_accel_info;
 
 typedef struct eid_hit {       /* PtPayload subset (globals.glsl:48-58) */
@@ -193,8 +195,15 @@ typedef struct eid_hit {       /* PtPayload subset (globals.glsl:48-58) */
   float   baryU, baryV;
 } eid_hit;
 
-/* AccelStructure::create(gltfScene, vertexBufs, indexBufs) */
+/* AccelStructure::create(gltfScene, vertexBufs, indexBufs) (accelstruct.cpp:55-162).
+ * EID_ACCEL_FLAT: every instance's triangles baked into ONE world-space BVH (fastest walk; memory x instance count).
+ * EID_ACCEL_TWO_LEVEL: the reference's structure — one bottom-level tree per prim mesh over object-space triangles, shared by all its
+ * instances, + a top-level tree over the instances; hits are bit-identical to the flat form (the triangle test runs on the same
+ * world-space triangle, computed from the instance matrix at test time).  EID_ACCEL_AUTO (eid_accel_build): two-level once the flat list
+ * would hold at least twice the unique triangles. */
+enum { EID_ACCEL_AUTO = 0, EID_ACCEL_FLAT = 1, EID_ACCEL_TWO_LEVEL = 2 };
 EID_API int  eid_accel_build(eid_scene* s, eid_accel** out);
+EID_API int  eid_accel_build_ex(eid_scene* s, int mode, eid_accel** out);
 EID_API void eid_accel_destroy(eid_accel* a);
 EID_API int  eid_accel_get_info(eid_accel* a, eid_accel_info* out);
 /* Batch ray query with HOST buffers (ClosestHit / AnyHit of traceray_rq.glsl:108-185).
