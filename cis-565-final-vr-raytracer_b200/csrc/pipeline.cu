@@ -37,6 +37,9 @@
 namespace {
 
 constexpr int MAXW = 16;
+#ifndef EID_PIPE_HISTORY_CHUNKS
+#define EID_PIPE_HISTORY_CHUNKS 4      // row chunks of direct_stage when its band's history is on the peers' critical path (moving camera)
+#endif
 enum { ROLE_D = EID_STAGE_DIRECT, ROLE_I = EID_STAGE_INDIRECT, ROLE_P = EID_STAGE_POST };
 enum FlagKind { F_READY_D, F_READY_I, F_READY_H, F_ACK_D, F_ACK_I, F_ACK_H, F_READY_V, F_ACK_V, F_KINDS };
 enum BufIdx { B_G0, B_G1, B_DIR0, B_DIR1, B_K2G0, B_K2G1, B_K2MV0, B_K2MV1, B_INDIN0, B_INDIN1, B_DR0, B_DR1, B_IR0, B_IR1, B_FLAGS, B_DELIV, B_COUNT };
@@ -164,6 +167,11 @@ struct EidPipe {
   float4* deliv = nullptr;
   uint32_t delivRows = 0, dseq = 0;
   cudaEvent_t evDelivPush = nullptr, evDone = nullptr;
+  // indirect ranks: the path tracing of frame f + 1 (k_gi_begin .. k_gi_bounce; needs this frame's G-buffer only) runs on its own stream
+  // and scratch while frame f is still in flight; only k_gi_finish (temporal reuse) is ordered after the previous frame's
+  cudaStream_t k2Stream[2] = {nullptr, nullptr};
+  cudaEvent_t evTrace[2] = {nullptr, nullptr}, evFinish[2] = {nullptr, nullptr};
+  bool finishValid[2] = {false, false};
   bool ackPending = false;                 // eid_group_run: the frame's acknowledgement is enqueued with the NEXT frame (see pipelineFrame)
   ShmHdr* shm = nullptr;
   std::string shmPath;
@@ -217,23 +225,69 @@ bool cameraMoved(const SceneCamera& c) { return memcmp(&c.projView, &c.lastProjV
 
 // Same-stage history (moving camera): this rank's band of the buffers the NEXT frame reprojects into goes to the other ranks of the stage.
 // `last` = false: the buffers this frame wrote (eager, behind the stage); true: the LAST buffers of this frame (lazy, before the stage).
-void pushHistory(eid_group* g, const FrameParams& P, int set, bool last, uint32_t readyValue) {
+// `rows` (full-res rows, a part of the band): direct_stage runs in row chunks when the history is on the critical path, and every chunk leaves
+// as soon as it is done; `first` waits for the peers' acknowledgement, `final` raises their flag.  Chunks that leave while the stage is
+// still running use the copy engines (the SMs are busy); a whole band behind an idle stage uses the SM copy kernel.
+void pushHistory(eid_group* g, const FrameParams& P, int set, bool last, uint32_t readyValue, Range rows, bool first = true, bool final = true, bool sm = true) {
   EidPipe* p = g->pipe;
   const RankLayout& me = p->me;
   const int thisIdx = last ? set : !set;                      // fillParams: last* = [set], this* = [!set]
   const size_t sw = (size_t)P.st.size.x;
+  auto push = [&](int j, int buf, size_t rowBytes, Range r) { if (sm) pushRowsSM(g, p->csH, j, buf, rowBytes, r); else pushRows(g, p->csH, j, buf, rowBytes, r); };
   for (int j = 0; j < g->world; ++j) {
     if (j == g->rank || p->ranks[j].role != me.role) continue;
     // the peer read these rows' buffer (as `last`) in every frame up to the previous one: wait until it has finished that stage
-    if (p->seq > 0) waitFlag(g, p->csH, F_ACK_H, j, p->seq);
+    if (first && p->seq > 0) waitFlag(g, p->csH, F_ACK_H, j, p->seq);
     if (me.role & ROLE_D) {
-      pushRowsSM(g, p->csH, j, B_G0 + thisIdx, (size_t)P.pitch * 16, Range{(int)me.y0, (int)me.y1});
-      pushRowsSM(g, p->csH, j, B_DR0 + thisIdx, sw * sizeof(DirectReservoir), Range{(int)me.y0, (int)me.y1});
+      push(j, B_G0 + thisIdx, (size_t)P.pitch * 16, rows);
+      push(j, B_DR0 + thisIdx, sw * sizeof(DirectReservoir), rows);
     } else {
-      pushRowsSM(g, p->csH, j, B_IR0 + thisIdx, (sw / 2) * sizeof(IndirectReservoir), Range{(int)me.y0 / 2, (int)me.y1 / 2});
+      push(j, B_IR0 + thisIdx, (sw / 2) * sizeof(IndirectReservoir), Range{rows.a / 2, rows.b / 2});
     }
-    setFlag(g, p->csH, j, F_READY_H, readyValue);
+    if (final) setFlag(g, p->csH, j, F_READY_H, readyValue);
   }
+}
+
+// indirect_stage of frame n on a rank that traces it: the path-tracing half on the stream / scratch of the frame's parity — it only waits
+// for this frame's G-buffer rows (`waitInputs` enqueues those waits) and for the frame before last to have left that scratch —, then
+// k_gi_finish on the render stream, behind the previous frame's.  Falls back to the one-stream form when the wavefront form is not in use.
+template <class WaitInputs>
+bool indirectTraceAsync(eid_group* g, FrameParams& P, uint32_t n, WaitInputs waitInputs) {
+  eid_renderer* r = g->r;
+  EidPipe* p = g->pipe;
+  const int par = (int)(n & 1u);
+  const bool serial = getenv("EID_PIPE_K2_SERIAL") != nullptr;
+  if (P.wv.slots && !serial && par) { r->ensureWave(P.st.maxDepth - 1, 1); P.wv = r->waveView(1); }
+  if (serial || !indirectIsWavefront(r, P)) {
+    waitInputs(r->stream);
+    beginFrame(r);
+    return false;
+  }
+  cudaStream_t ts = p->k2Stream[par];
+  // what the render stream did up to here (history waits, acknowledgements of earlier frames) need not hold the tracing back; what must:
+  // the inputs, and finish(n - 2) — it read this scratch, and its frame's ray counters went to the host after it
+  if (p->finishValid[par]) CUDA_CHECK(cudaStreamWaitEvent(ts, p->evFinish[par], 0));
+  waitInputs(ts);
+  beginFrame(r, ts);
+  markStart(r, EID_K_INDIRECT, ts);
+  stageIndirectTrace(r, P, ts, par);
+  CUDA_CHECK(cudaEventRecord(p->evTrace[par], ts));
+  return true;
+}
+void indirectFinish(eid_group* g, const FrameParams& P, uint32_t n, bool split) {
+  eid_renderer* r = g->r;
+  EidPipe* p = g->pipe;
+  if (!split) { stageIndirect(r, P, r->stream); return; }
+  CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evTrace[n & 1u], 0));
+  stageIndirectFinish(r, P, r->stream);
+  markStop(r, EID_K_INDIRECT, r->stream);
+}
+void indirectDone(eid_group* g, uint32_t n) {        // after endFrame: the scratch of this parity and its counters are free again
+  EidPipe* p = g->pipe;
+  const int par = (int)(n & 1u);
+  if (!p->evFinish[par]) return;
+  CUDA_CHECK(cudaEventRecord(p->evFinish[par], g->r->stream));
+  p->finishValid[par] = true;
 }
 
 }  // namespace
@@ -291,18 +345,39 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
     if (needHistory) {
       if (!p->historyComplete) {                              // lazily: first frame, or the camera started moving
         CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
-        pushHistory(g, P, set, true, n + 1);
+        pushHistory(g, P, set, true, n + 1, Range{(int)me.y0, (int)me.y1});
         // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
         CUDA_CHECK(cudaEventRecord(p->evPrep, p->csH)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
       }
       for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) waitFlag(g, r->stream, F_READY_H, j, n + 1);
     }
     beginFrame(r);
-    stageDirect(r, P, r->stream);
+    const bool spatial = st.ReSTIRState == eSpatial || st.ReSTIRState == eSpatiotemporal;
+    const int chunks = (eagerHistory && !spatial) ? EID_PIPE_HISTORY_CHUNKS : 1;
+    if (chunks <= 1) {
+      stageDirect(r, P, r->stream);
+    } else {
+      // The peers' next direct_stage waits for this band's G-buffer / reservoir rows: the band is traced in row chunks and every chunk is
+      // on its way (copy engines) while the next one is still being traced; only the last chunk's copy is exposed.
+      const int rc = (((int)me.y1 - (int)me.y0 + chunks - 1) / chunks + 7) / 8 * 8;
+      markStart(r, EID_K_DIRECT, r->stream);
+      bool firstChunk = true;
+      for (int a = (int)me.y0; a < (int)me.y1; a += rc) {
+        const int b = std::min(a + rc, (int)me.y1);
+        FrameParams Pk = P;
+        Pk.sFirst = a; Pk.sRows = b - a; Pk.sStride = 1 << 20; Pk.sCount = a < st.size.y ? 1 : 0;
+        stageDirect(r, Pk, r->stream, false);
+        CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
+        pushHistory(g, P, set, false, n + 2, Range{a, b}, firstChunk, b >= (int)me.y1, false);
+        firstChunk = false;
+      }
+      markStop(r, EID_K_DIRECT, r->stream);
+    }
     if (stagePeers > 1) for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_D) setFlag(g, r->stream, j, F_ACK_H, n + 1);
     CUDA_CHECK(cudaEventRecord(p->evStage, r->stream));
     CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csP, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
-    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;   // the peer's next direct_stage waits for it: first
+    if (eagerHistory && chunks <= 1) pushHistory(g, P, set, false, n + 2, Range{(int)me.y0, (int)me.y1});   // the peer's next direct_stage waits for it: first
+    p->historyComplete = eagerHistory;
     for (int j = 0; j < g->world; ++j) {
       const RankLayout& c = p->ranks[j];
       if (c.role == ROLE_D) continue;
@@ -329,28 +404,30 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
     if (needHistory) {
       if (!p->historyComplete) {
         CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
-        pushHistory(g, P, set, true, n + 1);
+        pushHistory(g, P, set, true, n + 1, Range{(int)me.y0, (int)me.y1});
         // the rows just sent are rewritten by the NEXT frame's stage, which is only ordered after the pushes of its own parity: order this one too
         CUDA_CHECK(cudaEventRecord(p->evPrep, p->csH)); CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evPrep, 0));
       }
       for (int j = 0; j < g->world; ++j) if (j != g->rank && p->ranks[j].role == ROLE_I) waitFlag(g, r->stream, F_READY_H, j, n + 1);
     }
     const DirectNeeds need = directNeeds(me, padded);
-    for (int j = 0; j < g->world; ++j) {
-      const RankLayout& d = p->ranks[j];
-      if (d.role != ROLE_D) continue;
-      if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
-      waitFlag(g, r->stream, F_READY_D, j, n + 1);
-    }
-    beginFrame(r);
-    stageIndirect(r, P, r->stream);
+    const bool split = indirectTraceAsync(g, P, n, [&](cudaStream_t s) {
+      for (int j = 0; j < g->world; ++j) {
+        const RankLayout& d = p->ranks[j];
+        if (d.role != ROLE_D) continue;
+        if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
+        waitFlag(g, s, F_READY_D, j, n + 1);
+      }
+    });
+    indirectFinish(g, P, n, split);
     for (int j = 0; j < g->world; ++j) {
       const RankLayout& d = p->ranks[j];
       if (d.role == ROLE_D && !(intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty())) setFlag(g, r->stream, j, F_ACK_D, n + 1);
       if (d.role == ROLE_I && j != g->rank) setFlag(g, r->stream, j, F_ACK_H, n + 1);
     }
     CUDA_CHECK(cudaEventRecord(p->evStage, r->stream)); CUDA_CHECK(cudaStreamWaitEvent(g->cs, p->evStage, 0)); CUDA_CHECK(cudaStreamWaitEvent(p->csH, p->evStage, 0));
-    if (eagerHistory) { pushHistory(g, P, set, false, n + 2); p->historyComplete = true; } else p->historyComplete = false;
+    if (eagerHistory) pushHistory(g, P, set, false, n + 2, Range{(int)me.y0, (int)me.y1});
+    p->historyComplete = eagerHistory;
     for (int j = 0; j < g->world; ++j) {
       const RankLayout& c = p->ranks[j];
       const Range ri = intersect(indirectNeeds(c, padded), (int)me.y0 / 2, (int)me.y1 / 2);
@@ -362,17 +439,29 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
     CUDA_CHECK(cudaEventRecord(p->evPushI[set], g->cs)); p->pushIValid[set] = true;
     CUDA_CHECK(cudaEventRecord(p->evPushH[set], p->csH)); p->pushHValid[set] = true;
     endFrame(r);
+    indirectDone(g, n);
   } else {
     // post rank (denoise + compose on its band), or — without indirect ranks — indirect_stage + denoise + compose on the whole frame
     const bool alsoIndirect = (me.role & ROLE_I) != 0;
     const DirectNeeds need = directNeeds(me, padded);
-    for (int j = 0; j < g->world; ++j) {
-      const RankLayout& d = p->ranks[j];
-      if (d.role != ROLE_D) continue;
-      if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.d, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
-      waitFlag(g, r->stream, F_READY_D, j, n + 1);
+    auto waitDirect = [&](cudaStream_t s) {
+      for (int j = 0; j < g->world; ++j) {
+        const RankLayout& d = p->ranks[j];
+        if (d.role != ROLE_D) continue;
+        if (intersect(need.g, (int)d.y0, (int)d.y1).empty() && intersect(need.d, (int)d.y0, (int)d.y1).empty() && intersect(need.q, (int)d.y0 / 2, (int)d.y1 / 2).empty()) continue;
+        waitFlag(g, s, F_READY_D, j, n + 1);
+      }
+    };
+    bool split = false;
+    if (alsoIndirect) {
+      // the path tracing of this frame starts on its own stream as soon as the direct ranks' rows are here — also while the previous frame
+      // is still being denoised on the render stream
+      split = indirectTraceAsync(g, P, n, waitDirect);
+      if (split) waitDirect(r->stream);             // (the denoiser reads the same rows)
+    } else {
+      waitDirect(r->stream);
+      beginFrame(r);
     }
-    beginFrame(r);
     const PostLayout L = postLayout(P, me.count > 1);
     markStart(r, EID_K_DENOISE_DIRECT, r->stream);
     stagePrep(r, P, L, r->stream);
@@ -380,7 +469,7 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
     stageDenoiseDirect(r, P, L, r->aux);
     markStop(r, EID_K_DENOISE_DIRECT, r->aux);
     CUDA_CHECK(cudaEventRecord(p->evK3, r->aux));
-    if (alsoIndirect) stageIndirect(r, P, r->stream);
+    if (alsoIndirect) indirectFinish(g, P, n, split);
     else {
       const Range ni = indirectNeeds(me, padded);
       for (int j = 0; j < g->world; ++j) {
@@ -395,6 +484,7 @@ void pipelineFrame(eid_group* g, const RtxState& st, int frames, bool ackNow) {
     CUDA_CHECK(cudaStreamWaitEvent(r->stream, p->evK3, 0));
     stageCompose(r, P, L, r->stream);
     endFrame(r);
+    if (alsoIndirect) indirectDone(g, n);
   }
   p->lastSeqOfParity[set] = (int)n;
   p->seq = n + 1;
@@ -474,6 +564,7 @@ void pipelineSync(eid_group* g) {
   EidPipe* p = g->pipe;
   CUDA_CHECK(cudaStreamSynchronize(p->csP));
   CUDA_CHECK(cudaStreamSynchronize(p->csH));
+  for (cudaStream_t st : p->k2Stream) if (st) CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 void pipelineInfo(eid_group* g, eid_group_info* out) {
@@ -496,7 +587,8 @@ void pipelineDestroy(eid_group* g) {
     for (int j = 0; j < g->world; ++j) while (!loadAcq(&p->shm->ranks[j].closed) && nowSec() - t0 < 20.0) usleep(200);
   }
   for (void* b : p->openedBases) cudaIpcCloseMemHandle(b);
-  for (cudaStream_t* st : {&p->csP, &p->csH}) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+  for (cudaStream_t* st : {&p->csP, &p->csH, &p->k2Stream[0], &p->k2Stream[1]}) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+  for (cudaEvent_t e : {p->evTrace[0], p->evTrace[1], p->evFinish[0], p->evFinish[1]}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {p->evPushP[0], p->evPushP[1], p->evPushH[0], p->evPushH[1]}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {p->evStage, p->evPush[0], p->evPush[1], p->evPushI[0], p->evPushI[1], p->evPrep, p->evK3, p->evFork, p->evDelivPush, p->evDone}) if (e) cudaEventDestroy(e);
   cudaFree(p->flags); cudaFree(p->deliv);
@@ -556,6 +648,15 @@ int eid_group_create_pipeline(eid_group** out, eid_renderer* r, int rank, int wo
     CUDA_CHECK(cudaStreamCreateWithFlags(&p->csH, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&p->evPushP[0], &p->evPushP[1], &p->evPushH[0], &p->evPushH[1]}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (cudaEvent_t* e : {&p->evStage, &p->evPush[0], &p->evPush[1], &p->evPushI[0], &p->evPushI[1], &p->evPrep, &p->evK3, &p->evFork, &p->evDelivPush, &p->evDone}) CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (p->me.role & ROLE_I) {
+      for (int k = 0; k < 2; ++k) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&p->k2Stream[k], cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&p->evTrace[k], cudaEventDisableTiming)); CUDA_CHECK(cudaEventCreateWithFlags(&p->evFinish[k], cudaEventDisableTiming));
+      }
+      if (!r->shadowStream2) CUDA_CHECK(cudaStreamCreateWithFlags(&r->shadowStream2, cudaStreamNonBlocking));
+      if (!r->evWave2) CUDA_CHECK(cudaEventCreateWithFlags(&r->evWave2, cudaEventDisableTiming));
+      if (!r->evWaveJoin2) CUDA_CHECK(cudaEventCreateWithFlags(&r->evWaveJoin2, cudaEventDisableTiming));
+    }
     p->delivRows = bandRowsOf(height, world);
     CUDA_CHECK(cudaMalloc((void**)&p->deliv, (size_t)4 * p->delivRows * r->width * 16));
     if (eid_renderer_set_band(r, p->me.y0, std::min(p->me.y1, r->height)) != EID_OK) raise(EID_ERR_INVALID, "%s", eid_last_error());

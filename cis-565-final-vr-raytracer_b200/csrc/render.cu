@@ -21,6 +21,7 @@ void eid_renderer::release() {
   cudaFree(displayF); cudaFree(display8); displayF = nullptr; display8 = nullptr;
   cudaFree(mipScratch); mipScratch = nullptr;
   cudaFree(waveMem); waveMem = nullptr; cudaFree(waveCtr); waveCtr = nullptr; waveSlots = 0; waveTerms = 0;
+  cudaFree(waveMem2); waveMem2 = nullptr; cudaFree(waveCtr2); waveCtr2 = nullptr; waveSlots2 = 0; waveTerms2 = 0;
   for (int i = 0; i < 2; ++i) { cudaFree(directImgs[i]); cudaFree(k2G[i]); cudaFree(k2Mv[i]); directImgs[i] = nullptr; k2G[i] = nullptr; k2Mv[i] = nullptr; }
   for (int i = 0; i < 2; ++i) { cudaFree(indirectImgs[i]); indirectImgs[i] = nullptr; }
   directImg = indirectImg = nullptr;
@@ -66,27 +67,29 @@ void eid_renderer::allocate() {
 // Scratch of the wavefront K2: planes of `waveSlots` float4 (one slot per thread of the largest possible K2 grid of this
 // allocation).  Layout of waveMem in float4 units: rayQ0 2S | rayQ1 2S | hitQ S | misc S | thr S | gsXv S | gsNv S | gsXs S |
 // gsNs S | hitL S | neeTerm T*S | shadowQ 2*T*S | occl (T*S uint32).  1080p, maxDepth 3: ~125 MB.
-void eid_renderer::ensureWave(int terms) {
+void eid_renderer::ensureWave(int terms, int which) {
   terms = std::max(terms, 1);
   const uint32_t tilesX = (width / 2 + 7) / 8, tilesY = ((height + 15) / 16 * 16 / 2 + 7) / 8 + 1;
   const uint32_t S = tilesX * tilesY * 64u;
-  if (waveMem && waveSlots == S && waveTerms >= terms) return;
-  CUDA_CHECK(cudaStreamSynchronize(stream));
-  cudaFree(waveMem); waveMem = nullptr;
+  void*& mem = which ? waveMem2 : waveMem; uint32_t*& ctr = which ? waveCtr2 : waveCtr;
+  uint32_t& slots = which ? waveSlots2 : waveSlots; int& have = which ? waveTerms2 : waveTerms;
+  if (mem && slots == S && have >= terms) return;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  cudaFree(mem); mem = nullptr;
   const size_t f4 = (size_t)S * (12 + 3 * (size_t)terms);
-  CUDA_CHECK(cudaMalloc(&waveMem, f4 * 16 + (size_t)S * terms * 4));
-  if (!waveCtr) CUDA_CHECK(cudaMalloc(&waveCtr, 128 * sizeof(uint32_t)));
-  waveSlots = S; waveTerms = terms;
+  CUDA_CHECK(cudaMalloc(&mem, f4 * 16 + (size_t)S * terms * 4));
+  if (!ctr) CUDA_CHECK(cudaMalloc(&ctr, 128 * sizeof(uint32_t)));
+  slots = S; have = terms;
 }
-WaveView eid_renderer::waveView() const {
+WaveView eid_renderer::waveView(int which) const {
   WaveView V;
-  const size_t S = waveSlots, T = (size_t)waveTerms;
-  float4* b = (float4*)waveMem;
-  V.slots = waveSlots;
+  const size_t S = which ? waveSlots2 : waveSlots, T = (size_t)(which ? waveTerms2 : waveTerms);
+  float4* b = (float4*)(which ? waveMem2 : waveMem);
+  V.slots = (uint32_t)S;
   V.rayQ[0] = b; V.rayQ[1] = b + 2 * S; V.hitQ = b + 4 * S; V.misc = (uint4*)(b + 5 * S); V.thr = b + 6 * S;
   V.gsXv = b + 7 * S; V.gsNv = b + 8 * S; V.gsXs = b + 9 * S; V.gsNs = b + 10 * S; V.hitL = b + 11 * S;
   V.neeTerm = b + 12 * S; V.shadowQ = b + (12 + T) * S; V.occl = (uint32_t*)(b + (12 + 3 * T) * S);
-  V.ctr = waveCtr;
+  V.ctr = which ? waveCtr2 : waveCtr;
   return V;
 }
 
@@ -150,8 +153,8 @@ void beginFrame(eid_renderer* r, cudaStream_t st) {
   r->postStarted = false;
 }
 
-void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
-  markStart(r, EID_K_DIRECT, st);
+void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st, bool mark) {
+  if (mark) markStart(r, EID_K_DIRECT, st);
   if (P.sCount > 0) {
     dim3 g((P.st.size.x + 7) / 8, P.sCount * (P.sRows / 8));
     // TEX = false: lean variant for scenes without a single textured material (no texture branches, no tangent frame)
@@ -176,7 +179,7 @@ void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
       r->stats.kernelLaunches[EID_K_DIRECT]++;
     }
   }
-  markStop(r, EID_K_DIRECT, st);
+  if (mark) markStop(r, EID_K_DIRECT, st);
 }
 
 static void traceQueue(eid_renderer* r, bool any, const FrameParams& P, const float4* rays, const uint32_t* count, uint32_t* cursor, cudaStream_t st) {
@@ -185,36 +188,55 @@ static void traceQueue(eid_renderer* r, bool any, const FrameParams& P, const fl
   r->stats.kernelLaunches[EID_K_INDIRECT]++;
 }
 
+static dim3 indirectGrid(const FrameParams& P) {
+  // 8 x 8 quarter-res tiles on ABSOLUTE tile rows: a band that starts inside a tile row gets one more (masked) block row
+  return dim3((P.st.size.x / 2 + 7) / 8, P.sCount * ((((P.sFirst / 2) & 7) + P.sRows / 2 + 7) / 8));
+}
+static bool indirectHasWork(const FrameParams& P) { return P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0; }
+bool indirectIsWavefront(eid_renderer* r, const FrameParams& P) {
+  const dim3 g = indirectGrid(P);
+  return indirectHasWork(P) && P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots;
+}
+
+// wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
+// `shadow` stream while the main stream goes on with the next depth (small queues are latency-bound: the longest ray
+// of the C3 scene needs ~150 dependent node visits, ~80 us, however few rays there are); join before finish
+void stageIndirectTrace(eid_renderer* r, const FrameParams& P, cudaStream_t st, int ctx) {
+  const dim3 g = indirectGrid(P);
+  const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1 || P.accel.twoLevel;
+  cudaStream_t shadow = ctx ? r->shadowStream2 : r->shadowStream;
+  cudaEvent_t evWave = ctx ? r->evWave2 : r->evWave, evJoin = ctx ? r->evWaveJoin2 : r->evWaveJoin;
+  cudaStream_t sh = r->waveOverlap ? shadow : st;
+  CUDA_CHECK(cudaMemsetAsync(P.wv.ctr, 0, 128 * sizeof(uint32_t), st));
+  launchGiBegin(P, g, st, tex);
+  r->stats.kernelLaunches[EID_K_INDIRECT]++;
+  const int gb = r->smCount * 8;
+  bool forked = false;
+  for (int d = 1; d <= P.st.maxDepth; ++d) {
+    traceQueue(r, false, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
+    launchGiBounce(P, gb, st, tex, d);
+    r->stats.kernelLaunches[EID_K_INDIRECT]++;
+    if (d + 1 <= P.st.maxDepth && P.st.MIS > 0) {
+      if (sh != st) { CUDA_CHECK(cudaEventRecord(evWave, st)); CUDA_CHECK(cudaStreamWaitEvent(sh, evWave, 0)); forked = true; }
+      traceQueue(r, true, P, P.wv.shadowQ + 2 * (size_t)(d - 1) * P.wv.slots, P.wv.ctr + 32 + d - 1, P.wv.ctr + 96 + d - 1, sh);
+    }
+  }
+  if (forked) { CUDA_CHECK(cudaEventRecord(evJoin, sh)); CUDA_CHECK(cudaStreamWaitEvent(st, evJoin, 0)); }
+}
+void stageIndirectFinish(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
+  launchGiFinish(P, indirectGrid(P), st);
+  r->stats.kernelLaunches[EID_K_INDIRECT]++;
+}
+
 void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st) {
   markStart(r, EID_K_INDIRECT, st);
-  if (P.sCount > 0 && P.st.size.x / 2 > 0 && P.st.size.y / 2 > 0) {
-    // 8 x 8 quarter-res tiles on ABSOLUTE tile rows: a band that starts inside a tile row gets one more (masked) block row
-    dim3 g((P.st.size.x / 2 + 7) / 8, P.sCount * ((((P.sFirst / 2) & 7) + P.sRows / 2 + 7) / 8));
-    const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1 || P.accel.twoLevel;   // (the two-level walk lives in the full variants)
-    if (P.wv.slots && (size_t)g.x * g.y * 64 <= P.wv.slots) {
-      // wavefront form: begin, then per depth (closest-hit queue, bounce); the shadow queue a bounce fills is traced on the
-      // `shadow` stream while the main stream goes on with the next depth (small queues are latency-bound: the longest ray
-      // of the C3 scene needs ~150 dependent node visits, ~80 us, however few rays there are); join before finish
-      cudaStream_t sh = r->waveOverlap ? r->shadowStream : st;
-      CUDA_CHECK(cudaMemsetAsync(P.wv.ctr, 0, 128 * sizeof(uint32_t), st));
-      launchGiBegin(P, g, st, tex);
-      r->stats.kernelLaunches[EID_K_INDIRECT]++;
-      const int gb = r->smCount * 8;
-      bool forked = false;
-      for (int d = 1; d <= P.st.maxDepth; ++d) {
-        traceQueue(r, false, P, P.wv.rayQ[d & 1], P.wv.ctr + d, P.wv.ctr + 64 + d, st);
-        launchGiBounce(P, gb, st, tex, d);
-        r->stats.kernelLaunches[EID_K_INDIRECT]++;
-        if (d + 1 <= P.st.maxDepth && P.st.MIS > 0) {
-          if (sh != st) { CUDA_CHECK(cudaEventRecord(r->evWave, st)); CUDA_CHECK(cudaStreamWaitEvent(sh, r->evWave, 0)); forked = true; }
-          traceQueue(r, true, P, P.wv.shadowQ + 2 * (size_t)(d - 1) * P.wv.slots, P.wv.ctr + 32 + d - 1, P.wv.ctr + 96 + d - 1, sh);
-        }
-      }
-      if (forked) { CUDA_CHECK(cudaEventRecord(r->evWaveJoin, sh)); CUDA_CHECK(cudaStreamWaitEvent(st, r->evWaveJoin, 0)); }
-      launchGiFinish(P, g, st);
-      r->stats.kernelLaunches[EID_K_INDIRECT]++;
+  if (indirectHasWork(P)) {
+    if (indirectIsWavefront(r, P)) {
+      stageIndirectTrace(r, P, st, 0);
+      stageIndirectFinish(r, P, st);
     } else {
-      launchIndirectMega(P, g, st, r->countVisits, tex);
+      const bool tex = r->scene->host.hasTextures || r->scene->host.hasNonOpaque || P.env.sunSky.in_use == 1 || P.accel.twoLevel;
+      launchIndirectMega(P, indirectGrid(P), st, r->countVisits, tex);
       r->stats.kernelLaunches[EID_K_INDIRECT]++;
     }
   }
@@ -547,6 +569,9 @@ void eid_renderer_destroy(eid_renderer* r) {
   if (r->evFork) cudaEventDestroy(r->evFork); if (r->evJoin) cudaEventDestroy(r->evJoin); if (r->evPost) cudaEventDestroy(r->evPost);
   if (r->aux) { cudaStreamSynchronize(r->aux); cudaStreamDestroy(r->aux); }
   if (r->shadowStream) { cudaStreamSynchronize(r->shadowStream); cudaStreamDestroy(r->shadowStream); }
+  if (r->shadowStream2) { cudaStreamSynchronize(r->shadowStream2); cudaStreamDestroy(r->shadowStream2); }
+  if (r->evWave2) cudaEventDestroy(r->evWave2);
+  if (r->evWaveJoin2) cudaEventDestroy(r->evWaveJoin2);
   if (r->k1Stream) { cudaStreamSynchronize(r->k1Stream); cudaStreamDestroy(r->k1Stream); }
   if (r->evK1Done) cudaEventDestroy(r->evK1Done);
   if (r->evOrder) cudaEventDestroy(r->evOrder);

@@ -49,6 +49,10 @@ struct eid_renderer {
   // wavefront K2 scratch (WaveView): sized for the allocation and for `waveTerms` NEE depths; (re)allocated on demand
   void* waveMem = nullptr; uint32_t waveSlots = 0; int waveTerms = 0; uint32_t* waveCtr = nullptr;
   cudaStream_t shadowStream = nullptr; cudaEvent_t evWave = nullptr, evWaveJoin = nullptr; bool waveOverlap = true;
+  // a second scratch + shadow stream: the stage pipeline's indirect ranks trace the paths of frame f + 1 while frame f is still in flight
+  // (only k_gi_finish depends on the previous frame), pipeline.cu
+  void* waveMem2 = nullptr; uint32_t waveSlots2 = 0; int waveTerms2 = 0; uint32_t* waveCtr2 = nullptr;
+  cudaStream_t shadowStream2 = nullptr; cudaEvent_t evWave2 = nullptr, evWaveJoin2 = nullptr;
   int wavefront = 1;          // 1 (default): K2 runs as ray queues + dynamic-fetch traversal when the scene allows it; 0: one mega-kernel
   int traceBlocks = 0;        // grid of k_trace_queue (blocks of 128 threads); 0 = EID_TQ_MIN_BLOCKS per SM
   int smCount = 0;
@@ -82,16 +86,21 @@ struct eid_renderer {
 
   void allocate();
   void release();
-  void ensureWave(int terms);
-  WaveView waveView() const;
+  void ensureWave(int terms, int which = 0);
+  WaveView waveView(int which = 0) const;
 };
 
 
 // per-frame pieces of eid_renderer_run (render.cu), reused by the multi-GPU schedule of group.cu
 void fillParams(eid_renderer* r, const RtxState& st, int frames, FrameParams& P);
 void beginFrame(eid_renderer* r, cudaStream_t st = nullptr);
-void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
+void stageDirect(eid_renderer* r, const FrameParams& P, cudaStream_t st, bool mark = true);
 void stageIndirect(eid_renderer* r, const FrameParams& P, cudaStream_t st);
+// indirect_stage in two halves (wavefront form only): the path tracing (k_gi_begin, ray queues, k_gi_bounce; needs this frame's G-buffer only) and
+// k_gi_finish (temporal reuse: needs the previous frame's reservoirs).  `ctx` selects the shadow stream / events of scratch 0 or 1.
+bool indirectIsWavefront(eid_renderer* r, const FrameParams& P);
+void stageIndirectTrace(eid_renderer* r, const FrameParams& P, cudaStream_t st, int ctx);
+void stageIndirectFinish(eid_renderer* r, const FrameParams& P, cudaStream_t st);
 void launchPost(eid_renderer* r, const FrameParams& P, bool sharded);
 void* bufferPtr(eid_renderer* r, int which, size_t& bytes);
 // called by every entry point that enqueues stages on the render stream in strict order: orders them after any direct_stage still on the K1 stream
