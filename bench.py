@@ -518,7 +518,9 @@ def run_cuda(args):
                        "camera": ("orbit %.2f deg/frame" % args.orbit) if args.orbit else "static",
                        "l2": "inputs larger than L2: each frame streams ~1.0 GB of screen-space buffers + ~0.14 GB of BVH/triangles/vertices (L2 = 126 MB)",
                        "bvh": {"nodes": int(ainfo.nodeCount), "node_MB": ainfo.nodeBytes / 1e6, "tri_MB": ainfo.triBytes / 1e6,
-                               "height": int(ainfo.maxDepth), "build_ms": float(ainfo.buildMs)}},
+                               "height": int(ainfo.maxDepth), "build_ms": float(ainfo.buildMs),
+                               "build": "binned SAH on the host threads + refit / 4-wide collapse on the GPU (EID_ACCEL_FAST_TRACE)" if ainfo.fastTrace
+                               else "Morton LBVH on the GPU (EID_ACCEL_FAST_BUILD)"}},
             "fps": 1e3 / (ms / args.steps),
             "rays_per_frame": rays / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mray/s", "h2d_bytes_per_step": C.sizeof(abi.SceneCamera) + C.sizeof(abi.RtxState),

@@ -160,10 +160,12 @@ class SceneInfo(C.Structure):
 class AccelInfo(C.Structure):
     _fields_ = [("triangleCount", C.c_uint64), ("nodeCount", C.c_uint32), ("maxDepth", C.c_uint32),
                 ("nodeBytes", C.c_uint64), ("triBytes", C.c_uint64), ("buildMs", C.c_float),
-                ("twoLevel", C.c_int32), ("blasCount", C.c_uint32), ("tlasNodeCount", C.c_uint32), ("instanceCount", C.c_uint32)]
+                ("twoLevel", C.c_int32), ("blasCount", C.c_uint32), ("tlasNodeCount", C.c_uint32), ("instanceCount", C.c_uint32),
+                ("fastTrace", C.c_int32)]
 
 
 ACCEL_AUTO, ACCEL_FLAT, ACCEL_TWO_LEVEL = 0, 1, 2
+ACCEL_FAST_TRACE, ACCEL_FAST_BUILD = 0x100, 0x200    # build quality, or-ed into the mode (default: FAST_TRACE, the reference's flag)
 
 
 EID_K_COUNT = 5

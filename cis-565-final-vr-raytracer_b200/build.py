@@ -19,7 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 _VARIANT = os.environ.get("EID_VARIANT", "")         # EID_VARIANT=x -> libeidola_x.so from build_x/ (kernel-variant sweeps)
 OUT = os.path.join(HERE, "libeidola%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 OBJ = os.path.join(HERE, "build" + ("_" + _VARIANT if _VARIANT else ""))
-SOURCES = ["accel.cu", "render.cu", "k_direct.cu", "k_indirect.cu", "k_wave.cu", "k_post.cu", "group.cu", "pipeline.cu", "gltf_import.cpp", "png_decode.cpp", "scene_host.cpp", "env_host.cpp"]
+SOURCES = ["accel.cu", "render.cu", "k_direct.cu", "k_indirect.cu", "k_wave.cu", "k_post.cu", "group.cu", "pipeline.cu", "gltf_import.cpp", "png_decode.cpp", "scene_host.cpp", "env_host.cpp", "sah_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall,-Wno-unused-function",
@@ -58,7 +58,7 @@ def build_library(force=False, verbose=False, extra=()):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or force or _newer(objs, OUT):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-ldl", "-lz"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-ldl", "-lz", "-lpthread"]
         subprocess.check_call(cmd)
     return OUT
 

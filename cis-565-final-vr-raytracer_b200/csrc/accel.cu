@@ -14,8 +14,11 @@
 //                         triangles become leaves.  (EID_BVH_WIDTH=2 keeps the binary tree: k_pack_nodes, 64 B two-box nodes)
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "accel.h"
+#include "sah_host.h"
 #include "common.h"
 #include "trace.cuh"
 
@@ -438,10 +441,26 @@ static int rebaseRef(int r, int nodeBase, int primBase) {
 
 struct TreeBuild { float4* nodes = nullptr; uint32_t nodeCount = 0, levels = 0; int32_t rootRef = ~0; };
 
+// PREFER_FAST_TRACE build (sah_host.h): the padded boxes go to the host, the binned-SAH builder returns the primitive order and the
+// binary tree in the arrays k_hierarchy would have filled; refit and the 4-wide collapse run on the GPU as for the Morton build.
+static void sahOrder(uint32_t n, const float* lo0, const float* hi0, uint32_t* valsSorted, BinaryTreeHost& H) {
+  std::vector<float> hlo(3 * (size_t)n), hhi(3 * (size_t)n);
+  CUDA_CHECK(cudaMemcpy(hlo.data(), lo0, hlo.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaMemcpy(hhi.data(), hi0, hhi.size() * 4, cudaMemcpyDeviceToHost));
+  buildSahTree(n, hlo.data(), hhi.data(), H);
+  CUDA_CHECK(cudaMemcpy(valsSorted, H.order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+}
+static void sahUpload(const BinaryTreeHost& H, int* left, int* right, int* parI, int* parL, int* rf, int* rl) {
+  const size_t ni = H.left.size() * 4;
+  CUDA_CHECK(cudaMemcpy(left, H.left.data(), ni, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(right, H.right.data(), ni, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(parI, H.parentInner.data(), ni, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(parL, H.parentLeaf.data(), H.parentLeaf.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(rf, H.rangeFirst.data(), ni, cudaMemcpyHostToDevice)); CUDA_CHECK(cudaMemcpy(rl, H.rangeLast.data(), ni, cudaMemcpyHostToDevice));
+}
+
 // The flat builder's pipeline (Morton keys of the padded boxes, radix sort, Karras tree, refit, 4-wide collapse) over ANY list of
 // 48-byte primitive records with boxes: the triangles of one prim mesh (BLAS) or the instances (TLAS).  primOut receives the records in
 // Morton order (what the leaves index); lo0 / hi0 are padded in place; `bounds` must hold the union of the boxes.
-static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0, const BuildBounds* bounds, float4* primOut, TreeBuild& T) {
+static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0, const BuildBounds* bounds, float4* primOut, TreeBuild& T, bool sah) {
 #if EID_BVH_WIDTH != 4 || EID_NODE_Q8
   raise(EID_ERR_UNSUPPORTED, "the two-level build needs the default 128-byte BVH4 node");
 #else
@@ -461,10 +480,15 @@ static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0,
     CUDA_CHECK(cudaMalloc(&keys, (size_t)n * 8)); CUDA_CHECK(cudaMalloc(&keysSorted, (size_t)n * 8));
     CUDA_CHECK(cudaMalloc(&vals, (size_t)n * 4)); CUDA_CHECK(cudaMalloc(&valsSorted, (size_t)n * 4));
     k_morton<<<G, B>>>(n, lo0, hi0, bounds, keys, vals);
-    size_t tmpBytes = 0;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
-    CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
+    BinaryTreeHost H;
+    sah = sah && n > 1;
+    if (sah) sahOrder(n, lo0, hi0, valsSorted, H);
+    else {
+      size_t tmpBytes = 0;
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
+      CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)n, 0, 63));
+    }
     k_reorder<<<G, B>>>(n, valsSorted, primTmp, lo0, hi0, primOut, lo1, hi1);
     if (n == 1) { T.nodes = nullptr; T.nodeCount = 0; T.levels = 0; T.rootRef = ~((0 << 3) | 1); freeAll(); return; }
     const uint32_t nInner = n - 1;
@@ -475,7 +499,8 @@ static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0,
     CUDA_CHECK(cudaMalloc(&nlo, (size_t)nInner * 12)); CUDA_CHECK(cudaMalloc(&nhi, (size_t)nInner * 12));
     CUDA_CHECK(cudaMalloc(&arrived, (size_t)nInner * 4));
     CUDA_CHECK(cudaMemset(arrived, 0, (size_t)nInner * 4));
-    k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)n, keysSorted, left, right, parI, parL, rf, rl);
+    if (sah) sahUpload(H, left, right, parI, parL, rf, rl);
+    else k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)n, keysSorted, left, right, parI, parL, rf, rl);
     k_refit<<<G, B>>>((int)n, left, right, parI, parL, lo1, hi1, nlo, nhi, height, arrived);
     if (n <= LEAF_MAX) { T.nodes = nullptr; T.nodeCount = 0; T.levels = 0; T.rootRef = ~(int)((0u << 3) | n); freeAll(); return; }   // the whole list is one leaf
     CUDA_CHECK(cudaMalloc(&wideTmp, (size_t)nInner * 128));
@@ -503,7 +528,7 @@ static void buildTree(uint32_t n, const float4* primTmp, float* lo0, float* hi0,
 #endif
 }
 
-static void buildAccelTwoLevel(eid_scene* s, eid_accel* a) {
+static void buildAccelTwoLevel(eid_scene* s, eid_accel* a, bool sah) {
   const SceneHost& H = s->host;
   CUDA_CHECK(cudaSetDevice(s->dev.device));
   const size_t nMesh = H.gltf.primMeshes.size(), nInst = H.instances.size();
@@ -541,7 +566,7 @@ static void buildAccelTwoLevel(eid_scene* s, eid_accel* a) {
         int li = l >= 0 ? l : l ^ 0x7fffffff, hi_ = h >= 0 ? h : h ^ 0x7fffffff;
         memcpy(&b.lo[k], &li, 4); memcpy(&b.hi[k], &hi_, 4);
       }
-      buildTree(n, triTmp, lo0, hi0, bounds, a->tris + 3 * (size_t)primBase, b.T);
+      buildTree(n, triTmp, lo0, hi0, bounds, a->tris + 3 * (size_t)primBase, b.T, sah);
       b.primBase = primBase; b.nodeBase = nodeTotal; b.valid = true;
       primBase += n; nodeTotal += b.T.nodeCount; maxBlasLevels = std::max(maxBlasLevels, b.T.levels);
       a->blasCount++;
@@ -602,7 +627,7 @@ static void buildAccelTwoLevel(eid_scene* s, eid_accel* a) {
       CUDA_CHECK(cudaMemcpy(lo0, ilo.data(), (size_t)nTop * 12, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy(hi0, ihi.data(), (size_t)nTop * 12, cudaMemcpyHostToDevice));
       TreeBuild T;
-      buildTree(nTop, triTmp, lo0, hi0, bounds, a->tlasPrims, T);
+      buildTree(nTop, triTmp, lo0, hi0, bounds, a->tlasPrims, T, sah);
       a->tlasNodes = T.nodes; a->tlasNodeCount = T.nodeCount; a->tlasRootRef = T.rootRef; tlasLevels = T.levels;
       freeTmp();
     }
@@ -623,7 +648,7 @@ static void buildAccelTwoLevel(eid_scene* s, eid_accel* a) {
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
 }
 
-static void buildAccel(eid_scene* s, eid_accel* a) {
+static void buildAccel(eid_scene* s, eid_accel* a, bool sah) {
   const SceneHost& H = s->host;
   CUDA_CHECK(cudaSetDevice(s->dev.device));
   // leaf references carry (firstTriangle << 3 | count) in 31 bits, and 0x80000000 is the traversal's "done" sentinel
@@ -661,10 +686,15 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
     k_init_bounds<<<1, 1>>>(bounds);
     k_emit_triangles<<<G, B>>>(s->dev.view(H), s->dev.instFirstTri, (uint32_t)H.instances.size(), nTri, triTmp, lo0, hi0, bounds);
     k_morton<<<G, B>>>(nTri, lo0, hi0, bounds, keys, vals);
-    size_t tmpBytes = 0;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
-    CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
+    BinaryTreeHost H;
+    sah = sah && nTri > 1;
+    if (sah) sahOrder(nTri, lo0, hi0, valsSorted, H);
+    else {
+      size_t tmpBytes = 0;
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
+      CUDA_CHECK(cudaMalloc(&tmp, tmpBytes));
+      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, valsSorted, (int)nTri, 0, 63));
+    }
     k_reorder<<<G, B>>>(nTri, valsSorted, triTmp, lo0, hi0, a->tris, lo1, hi1);
     const uint32_t nInner = nTri > 1 ? nTri - 1 : 1;
     if (nTri == 1) {
@@ -680,7 +710,8 @@ static void buildAccel(eid_scene* s, eid_accel* a) {
       CUDA_CHECK(cudaMalloc(&nlo, (size_t)nInner * 12)); CUDA_CHECK(cudaMalloc(&nhi, (size_t)nInner * 12));
       CUDA_CHECK(cudaMalloc(&arrived, (size_t)nInner * 4)); CUDA_CHECK(cudaMalloc(&live, 4));
       CUDA_CHECK(cudaMemset(arrived, 0, (size_t)nInner * 4)); CUDA_CHECK(cudaMemset(live, 0, 4));
-      k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)nTri, keysSorted, left, right, parI, parL, rf, rl);
+      if (sah) sahUpload(H, left, right, parI, parL, rf, rl);
+      else k_hierarchy<<<(nInner + B - 1) / B, B>>>((int)nTri, keysSorted, left, right, parI, parL, rf, rl);
       k_refit<<<G, B>>>((int)nTri, left, right, parI, parL, lo1, hi1, nlo, nhi, height, arrived);
 #if EID_BVH_WIDTH == 2
       CUDA_CHECK(cudaMalloc(&a->nodes, (size_t)nInner * 64));
@@ -948,7 +979,14 @@ int eid_scene_read_table(eid_scene* s, int table, uint32_t index, void* dst, siz
 int eid_accel_build_ex(eid_scene* s, int mode, eid_accel** out) {
   EID_TRY
   if (!s || !out) raise(EID_ERR_INVALID, "eid_accel_build: null argument");
-  if (mode < EID_ACCEL_AUTO || mode > EID_ACCEL_TWO_LEVEL) raise(EID_ERR_INVALID, "eid_accel_build_ex: mode must be EID_ACCEL_AUTO, _FLAT or _TWO_LEVEL");
+  const int build = mode & (EID_ACCEL_FAST_TRACE | EID_ACCEL_FAST_BUILD);
+  mode &= ~(EID_ACCEL_FAST_TRACE | EID_ACCEL_FAST_BUILD);
+  if (mode < EID_ACCEL_AUTO || mode > EID_ACCEL_TWO_LEVEL) raise(EID_ERR_INVALID, "eid_accel_build_ex: mode must be EID_ACCEL_AUTO, _FLAT or _TWO_LEVEL (| EID_ACCEL_FAST_TRACE or _FAST_BUILD)");
+  if (build == (EID_ACCEL_FAST_TRACE | EID_ACCEL_FAST_BUILD)) raise(EID_ERR_INVALID, "eid_accel_build_ex: EID_ACCEL_FAST_TRACE and EID_ACCEL_FAST_BUILD exclude each other");
+  // neither flag: the reference's choice (PREFER_FAST_TRACE, accelstruct.cpp:125-126,161) unless EIDOLA_ACCEL_BUILD=lbvh|sah says otherwise (A/B runs)
+  bool sah = build != EID_ACCEL_FAST_BUILD;
+  if (!build) { const char* e = getenv("EIDOLA_ACCEL_BUILD"); if (e && !strcmp(e, "lbvh")) sah = false; }
+  if (EID_BVH_WIDTH != 4) sah = false;
   if (!s->loaded) raise(EID_ERR_STATE, "eid_accel_build before a scene was loaded");
   if (s->dev.device == EID_DEVICE_NONE) raise(EID_ERR_CUDA, "eid_accel_build on a host-only scene: the BVH build and every kernel need a CUDA device (no CPU fallback)");
   bool two = mode == EID_ACCEL_TWO_LEVEL;
@@ -962,8 +1000,9 @@ int eid_accel_build_ex(eid_scene* s, int mode, eid_accel** out) {
     two = unique > 0 && H.triangleInstances >= 2 * unique;
   }
   eid_accel* a = new eid_accel();
-  try { if (two) buildAccelTwoLevel(s, a); else buildAccel(s, a); }
+  try { if (two) buildAccelTwoLevel(s, a, sah); else buildAccel(s, a, sah); }
   catch (...) { cudaFree(a->nodes); cudaFree(a->tris); cudaFree(a->tlasNodes); cudaFree(a->tlasPrims); delete a; throw; }
+  a->sahBuild = sah;
   *out = a;
   return EID_OK;
   EID_CATCH
@@ -985,6 +1024,7 @@ int eid_accel_get_info(eid_accel* a, eid_accel_info* o) {
   o->triangleCount = a->triCount; o->nodeCount = a->nodeCount; o->maxDepth = a->maxDepth;
   o->nodeBytes = (uint64_t)std::max<uint32_t>(1u, a->nodeAlloc) * EID_NODE_BYTES; o->triBytes = (uint64_t)a->triCount * 48;
   o->buildMs = a->buildMs;
+  o->fastTrace = a->sahBuild ? 1 : 0;
   o->twoLevel = a->twoLevel ? 1 : 0; o->blasCount = a->blasCount; o->tlasNodeCount = a->tlasNodeCount; o->instanceCount = a->twoLevel ? a->tlasPrimCount : (uint32_t)a->scene->host.instances.size();
   if (a->twoLevel) o->nodeBytes += (uint64_t)std::max<uint32_t>(1u, a->tlasNodeCount) * 128 + (uint64_t)a->tlasPrimCount * 48;
   return EID_OK;

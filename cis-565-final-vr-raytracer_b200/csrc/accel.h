@@ -98,6 +98,7 @@ struct eid_accel {
   uint32_t tlasPrimCount = 0, tlasNodeCount = 0, blasCount = 0;
   int32_t tlasRootRef = -1;
   uint64_t uniqueTriangles = 0;
+  bool sahBuild = false;                 // tree topology from the host binned-SAH builder (EID_ACCEL_FAST_TRACE) instead of the Morton build
   eid::AccelView view() const {
     return eid::AccelView{nodes, tris, triCount, rootRef, nodeTex, triTex, twoLevel ? 1 : 0, tlasRootRef, tlasPrimCount, tlasNodes, tlasPrims,
                           scene ? scene->dev.instances : nullptr};

@@ -42,7 +42,8 @@ class Scene {
 class AccelStructure {
  public:
   // AccelStructure::create(gltfScene, vertexBuffers, indexBuffers) (accelstruct.cpp:55-65): the buffers live in the Scene
-  // mode: EID_ACCEL_AUTO (default), EID_ACCEL_FLAT (one world-space BVH), EID_ACCEL_TWO_LEVEL (BLAS per prim mesh + TLAS, as the reference builds)
+  // mode: EID_ACCEL_AUTO (default), EID_ACCEL_FLAT (one world-space BVH), EID_ACCEL_TWO_LEVEL (BLAS per prim mesh + TLAS, as the reference builds),
+  // optionally | EID_ACCEL_FAST_BUILD (Morton build on the GPU) instead of the default EID_ACCEL_FAST_TRACE (binned SAH, the reference's build flag)
   void create(Scene& scene, int mode = EID_ACCEL_AUTO) { destroy(); check(eid_accel_build_ex(scene.handle(), mode, &m_h)); }
   eid_accel_info info() const { eid_accel_info i; check(eid_accel_get_info(m_h, &i)); return i; }
   void destroy() { if (m_h) { eid_accel_destroy(m_h); m_h = nullptr; } }
