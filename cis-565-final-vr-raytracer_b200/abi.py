@@ -177,7 +177,7 @@ class FrameStats(C.Structure):
                 ("launches", C.c_uint32), ("kernelMs", C.c_float * EID_K_COUNT),
                 ("kernelLaunches", C.c_uint32 * EID_K_COUNT), ("nodeVisits", C.c_uint64),
                 ("triangleTests", C.c_uint64), ("totalClosestHitRays", C.c_uint64), ("totalAnyHitRays", C.c_uint64),
-                ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64)]
+                ("exchangeMs", C.c_float), ("maxNodeVisitsPerThread", C.c_uint64), ("maxNodeVisitsPerQueuedRay", C.c_uint64 * 2)]
 
 
 VARIANT_DIRECT_BILATERAL, VARIANT_INDIRECT_BILATERAL, VARIANT_FETCH_4_SUBPIXELS, VARIANT_DIRECT_SPLIT = 1, 2, 4, 8     # eid_renderer_set_variant

@@ -65,13 +65,14 @@ struct FrameParams {
   WaveView wv;
   unsigned long long* counters;           // per frame (one set per ping-pong parity, so that frames in flight do not mix): [0] closest-hit
                                           // rays, [1] any-hit rays, [2] primary hits, [3] inner-node visits, [4] triangle tests (STATS kernels only)
-  unsigned long long* totals;             // since creation: [5] closest, [6] any, [7] worst thread's node visits
+  unsigned long long* totals;             // since creation: [5] closest, [6] any, [7] worst thread's node visits, [8] / [9] longest queued closest-hit / any-hit ray
   // What indirect_stage needs of LAST frame's G-buffer and of this frame's motion image (findTemporalNeighbor, indirect_stage.comp:74-108),
   // gathered by direct_stage for the pixels 2 * coord: the quarter-res stage then reads neither image, so the NEXT frame's direct_stage may
   // overwrite them while this frame's indirect_stage is still running (frames in flight, eid_renderer_set_pipeline)
   uint4* k2G; short2* k2Mv;
 };
-#define EID_NUM_COUNTERS 8            // per set; device layout: set 0 | set 1 | totals
+#define EID_NUM_COUNTERS 8            // per set; device layout: set 0 | set 1 | totals (EID_NUM_TOTALS entries)
+#define EID_NUM_TOTALS 10
 
 struct RayCounters { unsigned int closest, any, primary, nodes, tris; };
 

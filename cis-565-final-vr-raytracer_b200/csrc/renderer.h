@@ -1,6 +1,9 @@
 // renderer.h — the Renderer object (buffers + launch schedule state) shared by render.cu (C-ABI of the reference's Renderer class)
 // and group.cu (multi-GPU group: one renderer per rank + the NCCL exchange steps).
 #pragma once
+#ifndef EID_L2_PERSIST_DEFAULT
+#define EID_L2_PERSIST_DEFAULT 0   // access-policy window of the acceleration structure (render.cu: applyL2Policy); EIDOLA_L2_PERSIST overrides
+#endif
 #include <map>
 #include <tuple>
 #include <vector>
@@ -71,6 +74,7 @@ struct eid_renderer {
   bool hasRun = false;
   uint32_t sFirst = 0, sStride = 0, sRows = 0; bool stripesSet = false;   // multi-GPU row ownership (see FrameParams)
   bool profiling = false;
+  size_t l2PersistBytes = 0;  // L2 set-aside holding the acceleration structure (applyL2Policy), 0 = none
   bool countVisits = false;   // profiling level 2: STATS kernels (node / triangle visit counters)
   cudaEvent_t ev[2 * EID_K_COUNT] = {};   // start/stop per stage
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evPost = nullptr;

@@ -130,6 +130,15 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 #ifndef EID_Q8_MAGIC
 #define EID_Q8_MAGIC 0
 #endif
+#ifndef EID_K1_SORT
+#define EID_K1_SORT 0          // one-ray-per-thread walks: 1 = all entered children front to back, 0 = only the nearest selected
+#endif
+#ifndef EID_TQ_SORT
+#define EID_TQ_SORT 1          // the same choice for the ray-queue kernel
+#endif
+#ifndef EID_SPECULATIVE
+#define EID_SPECULATIVE 0     // one-ray-per-thread walks: postponed leaves (see traverse)
+#endif
 #ifndef EID_TRAV_V1
 #define EID_TRAV_V1 0       // 1: the round-1 node step (scalar FFMA slab tests, 5-comparator child sort) for A/B measurements
 #endif
@@ -154,8 +163,12 @@ DEV void ldg256(const float4* p, float4& a, float4& b) {
 // top of the stack, or EID_TRAV_DONE), the other entered children go onto the stack.  ANY = occlusion ray: child order is irrelevant.
 // SORT (closest-hit only): all entered children in front-to-back order (incoherent rays of the ray queues); otherwise only the nearest one is
 // selected (coherent rays of the one-thread-per-pixel kernels, where the full order did not lower the node count).
+// pf (ray-queue kernel only): prefetch the 128-byte line of every entered child node (and the first triangle of an entered leaf) into L1, so that
+// the next visit of this ray is an L1 hit instead of an L2 round trip — for rays walked with few lanes active (the drained tail of a queue, where
+// the dependent-visit latency is all that is left) the extra LSU traffic is free.
+DEV void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 template <bool ANY, bool SORT = false>
-DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, int* stack, int& sp) {
+DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, int* stack, int& sp, const bool pf = false) {
   const float INF = __int_as_float(0x7f800000);
 #define EID_POP() (sp ? stack[--sp] : EID_TRAV_DONE)
 #if EID_BVH_WIDTH == 4 && !EID_NODE_Q8 && !EID_TRAV_V1 && EID_FETCH_TEX == 2 && !defined(EID_NODE_LDG256)
@@ -182,6 +195,11 @@ DEV void nodeStep(const AccelView& A, const RayBox& rb, float tbest, int& cur, i
   const float2 tfb = fmul2s(make_float2(fminf(fminf(fbx.x, fby.x), fminf(fbz.x, tbest)), fminf(fminf(fbx.y, fby.y), fminf(fbz.y, tbest))), 1.0000004f);
   float e0 = (tn0 <= tfa.x) ? tn0 : INF, e1 = (tn1 <= tfa.y) ? tn1 : INF, e2 = (tn2 <= tfb.x) ? tn2 : INF, e3 = (tn3 <= tfb.y) ? tn3 : INF;
   const int c0 = __float_as_int(rf.x), c1 = __float_as_int(rf.y), c2 = __float_as_int(rf.z), c3 = __float_as_int(rf.w);
+  if (pf) {
+#define EID_PF(e, c) if (e < INF) { if (c >= 0) prefetchL1(A.nodes + 8 * (size_t)c); else prefetchL1(A.tris + 3 * (size_t)((~(uint32_t)c) >> 3)); }
+    EID_PF(e0, c0) EID_PF(e1, c1) EID_PF(e2, c2) EID_PF(e3, c3)
+#undef EID_PF
+  }
   if (ANY) {
     int next = 0; bool have = false;
     if (e0 < INF) { next = c0; have = true; }
@@ -373,16 +391,40 @@ DEV bool traverse(const AccelView& A, f3 o, f3 d, float tmax, RayHit& hit, unsig
   int cur = A.rootRef;
   // "while-while" walk: every lane first descends inner nodes until it holds a leaf (or is done); the warp then reconverges
   // and intersects leaves together.  In the interleaved form the triangle tests ran with ~5 of 32 lanes active (ncu source page).
+#if EID_SPECULATIVE
+  // Speculative while-while (Aila & Laine 2009): a lane that reaches a leaf postpones it and keeps descending, so it does useful node work
+  // while the other lanes of the warp are still looking for theirs; the warp switches to the leaf phase when every lane holds a leaf
+  // (EID_SPECULATIVE & 1: decided by a vote) or when the lane meets its second leaf.  & 2: closest-hit rays only (an occlusion ray that
+  // postpones a leaf may walk on past its terminating hit).  The visiting order never changes a result.
+  const bool spec = !(ANY && (EID_SPECULATIVE & 2));
+  for (;;) {
+    int leaf = EID_TRAV_DONE;                                  // the postponed leaf (EID_TRAV_DONE = none)
+    while (cur >= 0) {
+      if (STATS) ++*nodeVisits;
+      nodeStep<ANY, EID_K1_SORT != 0>(A, rb, hit.t, cur, stack, sp);
+      if (spec && cur < 0 && cur != EID_TRAV_DONE && leaf == EID_TRAV_DONE) { leaf = cur; cur = EID_POP(); }
+      if ((EID_SPECULATIVE & 1) && spec && !__any_sync(__activemask(), leaf == EID_TRAV_DONE)) break;
+    }
+    if (leaf != EID_TRAV_DONE && leafStep<ANY, STATS, LOWER>(A, leaf, o, d, tmax, hit, triTests, low)) return true;
+    if (cur < 0) {
+      if (cur == EID_TRAV_DONE) break;
+      if (leafStep<ANY, STATS, LOWER>(A, cur, o, d, tmax, hit, triTests, low)) return true;
+      cur = EID_POP();
+    }
+  }
+  return hit.tri >= 0;
+#else
   for (;;) {
     while (cur >= 0) {
       if (STATS) ++*nodeVisits;
-      nodeStep<ANY>(A, rb, hit.t, cur, stack, sp);
+      nodeStep<ANY, EID_K1_SORT != 0>(A, rb, hit.t, cur, stack, sp);
     }
     if (cur == EID_TRAV_DONE) break;
     if (leafStep<ANY, STATS, LOWER>(A, cur, o, d, tmax, hit, triTests, low)) return true;
     cur = EID_POP();
   }
   return hit.tri >= 0;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -531,6 +573,15 @@ __device__ __noinline__ bool traverse2(const AccelView& A, f3 o, f3 d, float tma
                                  // measured SLOWER (indirect_stage 0.602 -> 0.633-0.658 ms for every threshold tried, profiles/README.md): the
                                  // queue launches are bound by the latency of TYPICAL rays on under-filled SMs, not by a few very long ones
 #endif
+#ifndef EID_TQ_STATIC_FIRST
+#define EID_TQ_STATIC_FIRST 1    // first batch of every warp assigned statically, no atomic (see k_trace_queue)
+#endif
+#ifndef EID_TQ_SPREAD
+#define EID_TQ_SPREAD 0          // n > 0: small queues are spread over all warps, at least n rays per warp (see k_trace_queue)
+#endif
+#ifndef EID_TQ_PREFETCH
+#define EID_TQ_PREFETCH 0        // 1: L1 prefetch of the entered children once the warp can fetch no more rays (tail), 2: always (see nodeStep)
+#endif
 #ifndef EID_TQ_STEALS_PER_ROUND
 #define EID_TQ_STEALS_PER_ROUND 4
 #endif
@@ -565,6 +616,11 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
   int owner = (int)lane;           // lane of this warp that owns the ray whose piece this lane is walking
   uint32_t ownDst = 0;             // where the ray this lane OWNS reports to: hits[entry] / occl[id]
 #endif
+  // rays a warp holds at a time: 32, or (EID_TQ_SPREAD = s > 0) a queue smaller than the grid spread over ALL warps, at least s rays each
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  const int per = EID_TQ_SPREAD ? (int)min(32u, max((uint32_t)EID_TQ_SPREAD, (n + warps - 1u) / warps)) : 32;
+  const uint32_t firstBatch = EID_TQ_STATIC_FIRST ? warps * (uint32_t)per : 0u;
+  bool first = true;
   int stack[EID_STACK_SIZE];
   int sp = 0, sb = 0, cur = EID_TRAV_DONE;   // valid stack entries: stack[sb .. sb + sp)
   int age = 0;                               // node visits of the piece this lane is walking
@@ -574,30 +630,39 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
   float tmax = 0.f;
   RayBox rb = makeRayBox(o, mk3(1.f));
   RayHit hit; hit.t = 0.f; hit.tri = -1; hit.prim = hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
-  unsigned int nodeVisits = 0, triTests = 0;
+  unsigned int nodeVisits = 0, triTests = 0, rayVisits = 0;
   const HitKey low = {0.f, 0, 0};
   for (;;) {
     const unsigned idle = __ballot_sync(0xffffffffu, !active);
-    if (more && __popc(idle) >= EID_TQ_REFILL) {
-      const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+    uint32_t my = n;                                   // the queue entry this lane takes now (n = none)
+    if (EID_TQ_STATIC_FIRST && first) {
+      // The first batch is assigned statically (warp w takes the entries [w * per, (w + 1) * per)): 3552 warps hitting ONE cursor word with
+      // an atomicAdd at the same moment serialise in the L2 — a floor of every queue launch, however few rays it holds.  The cursor only
+      // counts the entries fetched dynamically after that grid-wide batch.
+      first = false;
+      const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+      more = firstBatch < n;
+      if (lane < (unsigned)per) my = wid * (uint32_t)per + lane;
+    } else if (more && 32 - __popc(idle) < per) {
+      // dynamic fetch: one atomicAdd per warp and refill round tops the warp up to `per` rays
+      const int nIdle = per - (32 - __popc(idle)), leader = __ffs(idle) - 1;
       uint32_t base = 0;
       if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)nIdle);
-      base = __shfl_sync(0xffffffffu, base, leader);
+      base = __shfl_sync(0xffffffffu, base, leader) + firstBatch;
       if (base + (uint32_t)nIdle >= n) more = false;
-      if (!active) {
-        const uint32_t my = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-        if (my < n) {
-          const float4 r0 = __ldg(rays + 2 * (size_t)my), r1 = __ldg(rays + 2 * (size_t)my + 1);
-          entry = my; id = __float_as_uint(r1.w);
-          o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z);
-          tmax = ANY ? r0.w : 1e28f;
-          hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
-          rb = makeRayBox(o, d);
-          sp = 0; sb = 0; active = true; age = 0;
-          // no triangles, or a direction with NaN / zero length (det can never be != 0): finished at once, as in traverse()
-          cur = (A.triCount == 0 || !(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) ? EID_TRAV_DONE : A.rootRef;
-        }
-      }
+      const uint32_t rank = (uint32_t)__popc(idle & ((1u << lane) - 1u));
+      if (!active && rank < (uint32_t)nIdle) my = base + rank;
+    }
+    if (my < n) {
+      const float4 r0 = __ldg(rays + 2 * (size_t)my), r1 = __ldg(rays + 2 * (size_t)my + 1);
+      entry = my; id = __float_as_uint(r1.w);
+      o = mk3(r0.x, r0.y, r0.z); d = mk3(r1.x, r1.y, r1.z);
+      tmax = ANY ? r0.w : 1e28f;
+      hit.t = tmax; hit.tri = -1; hit.prim = 0x7fffffff; hit.inst = 0x7fffffff; hit.u = hit.v = 0.f; hit.flags = 0;
+      rb = makeRayBox(o, d);
+      sp = 0; sb = 0; active = true; age = 0; rayVisits = 0;
+      // no triangles, or a direction with NaN / zero length (det can never be != 0): finished at once, as in traverse()
+      cur = (A.triCount == 0 || !(fabsf(d.x) + fabsf(d.y) + fabsf(d.z) > 0.0f)) ? EID_TRAV_DONE : A.rootRef;
     }
     if (!__ballot_sync(0xffffffffu, active)) break;
 #if EID_TQ_STEAL
@@ -642,9 +707,9 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
       const bool inner = active && cur >= 0;
       if (!__any_sync(0xffffffffu, inner)) break;
       if (inner) {
-        if (STATS) ++nodeVisits;
+        if (STATS) { ++nodeVisits; ++rayVisits; }
         ++age;
-        nodeStep<ANY, true>(A, rb, hit.t, cur, stack + sb, sp);
+        nodeStep<ANY, EID_TQ_SORT != 0>(A, rb, hit.t, cur, stack + sb, sp, EID_TQ_PREFETCH == 2 || (EID_TQ_PREFETCH == 1 && !more));
       }
     }
     if (active && cur < 0) {
@@ -659,6 +724,7 @@ __global__ void __launch_bounds__(128, EID_TQ_MIN_BLOCKS) k_trace_queue(const Ac
 #endif
         if (ANY) occl[id] = hit.tri >= 0 ? 1u : 0u;
         else hits[entry] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.tri));
+        if (STATS) atomicMax(&totals[ANY ? 9 : 8], (unsigned long long)rayVisits);   // longest queued ray since creation (the tail every queue launch waits for)
         active = false;
       }
     }

@@ -256,6 +256,7 @@ typedef struct eid_frame_stats {
   uint64_t totalAnyHitRays;
   float    exchangeMs;             /* profiling: gap between the end of run_trace and the start of run_post* (multi-GPU exchange 1) */
   uint64_t maxNodeVisitsPerThread; /* profiling level 2: most inner-node visits any single thread (pixel) needed so far */
+  uint64_t maxNodeVisitsPerQueuedRay[2]; /* profiling level 2, wavefront indirect stage: longest closest-hit / any-hit ray of the queues so far */
 } eid_frame_stats;
 
 /* Renderer::setup + create(size, layouts, scene) (renderer.cpp:50-57, 97-148).
