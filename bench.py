@@ -584,7 +584,7 @@ def main():
     ap.add_argument("--trace-blocks", type=int, default=0, help="grid of the persistent traversal kernel in 128-thread blocks (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="strict K1..K5 order on one stream (default: K3 runs beside K2/K4 on a second stream)")
     ap.add_argument("--frames-in-flight", type=int, default=1, choices=(1, 2),
-                    help="eid_renderer_set_pipeline: 2 lets direct_stage of frame f+1 overlap indirect_stage/denoise/compose of frame f (measured +2 %: the stages compete for the register file, profiles/README.md)")
+                    help="eid_renderer_set_pipeline: 2 lets direct_stage of frame f+1 overlap indirect_stage/denoise/compose of frame f (measured +2 %%: the stages compete for the register file, profiles/README.md)")
     ap.add_argument("--orbit", type=float, default=0.0, help="degrees per frame the camera orbits the scene centre (SURVEY 8(d): 0.5); default static")
     ap.add_argument("--history", default="auto", choices=["never", "always", "auto"],
                     help="N>1: how last frame's reservoirs cross band edges (eid_group_set_mode): auto = gathered when the camera moved")

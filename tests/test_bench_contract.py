@@ -41,3 +41,9 @@ def test_cuda_arm_has_no_cpu_fallback():
         pytest.skip("a GPU is present: the CUDA arm would simply run")
     p = _run(["--quick", "--steps", "1", "--warmup", "3", "--no-cpu-baseline"])
     assert p.returncode != 0 and p.stdout.strip() == ""      # fails loudly, prints no bench line
+
+
+def test_help_renders():
+    """argparse expands % in help strings: an unescaped one only fails when somebody asks for --help."""
+    p = _run(["--help"])
+    assert p.returncode == 0 and "--gpus" in p.stdout, p.stderr[-1000:]
