@@ -32,7 +32,7 @@ EXPORTS = [
     "eid_scene_create", "eid_scene_load_gltf", "eid_scene_load_desc", "eid_scene_provide_image", "eid_scene_destroy", "eid_scene_set_lookat",
     "eid_scene_update_camera", "eid_scene_set_camera", "eid_scene_get_camera", "eid_scene_get_info",
     "eid_scene_table_bytes", "eid_scene_read_table",
-    "eid_accel_build", "eid_accel_build_ex", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace",
+    "eid_accel_build", "eid_accel_build_ex", "eid_accel_destroy", "eid_accel_get_info", "eid_accel_trace", "eid_accel_sah_tap",
     "eid_env_create", "eid_env_load_hdr", "eid_env_destroy", "eid_env_integral", "eid_env_average", "eid_env_get_size", "eid_env_read",
     "eid_renderer_set_env",
     "eid_renderer_create", "eid_renderer_resize", "eid_renderer_destroy", "eid_renderer_set_env_constant",
@@ -77,6 +77,7 @@ def lib():
         "eid_accel_destroy": (None, [vp]),
         "eid_accel_get_info": (i32, [vp, C.POINTER(AccelInfo)]),
         "eid_accel_trace": (i32, [vp, vp, u32, i32, vp]),
+        "eid_accel_sah_tap": (i32, [vp, vp, u32, i32, vp, vp, vp, vp, vp, vp, vp]),
         "eid_env_create": (i32, [C.POINTER(vp), i32, vp, u32, u32]),
         "eid_env_load_hdr": (i32, [C.POINTER(vp), i32, C.c_char_p]),
         "eid_env_destroy": (None, [vp]),
@@ -245,6 +246,20 @@ class AccelStructure:
             self.destroy()
         except Exception:
             pass
+
+
+def sah_tree(lo, hi, threads=0):
+    """Tap of the EID_ACCEL_FAST_TRACE topology builder (csrc/sah_host.cpp; host only): dict of order / left / right / parentInner /
+    parentLeaf / rangeFirst / rangeLast for the boxes lo, hi (n x 3 float32)."""
+    lo = np.ascontiguousarray(lo, np.float32).reshape(-1, 3)
+    hi = np.ascontiguousarray(hi, np.float32).reshape(-1, 3)
+    n = lo.shape[0]
+    ni = max(n - 1, 0)
+    out = dict(order=np.zeros(n, np.uint32), left=np.zeros(ni, np.int32), right=np.zeros(ni, np.int32), parentInner=np.zeros(ni, np.int32),
+               parentLeaf=np.zeros(n, np.int32), rangeFirst=np.zeros(ni, np.int32), rangeLast=np.zeros(ni, np.int32))
+    _check(lib().eid_accel_sah_tap(lo.ctypes.data, hi.ctypes.data, n, int(threads), *[out[k].ctypes.data for k in
+                                   ("order", "left", "right", "parentInner", "parentLeaf", "rangeFirst", "rangeLast")]))
+    return out
 
 
 class HdrSampling:

@@ -5,10 +5,13 @@
 // m - 1 (every gap between two neighbouring positions belongs to exactly one inner node), with the root swapped to index 0 — so node
 // indices need no allocation and subtrees can be built by independent threads.
 #include "sah_host.h"
+#include "common.h"
+#include "eidola.h"
 
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <exception>
 #include <thread>
 
 namespace eid {
@@ -167,3 +170,19 @@ void buildSahTree(uint32_t n, const float* lo, const float* hi, BinaryTreeHost& 
 }
 
 }  // namespace eid
+
+extern "C" int eid_accel_sah_tap(const float* lo, const float* hi, uint32_t n, int threads, uint32_t* order, int32_t* left, int32_t* right,
+                                 int32_t* parentInner, int32_t* parentLeaf, int32_t* rangeFirst, int32_t* rangeLast) {
+  EID_TRY
+  if (!lo || !hi || !order || !parentLeaf || (n > 1 && (!left || !right || !parentInner || !rangeFirst || !rangeLast))) eid::raise(EID_ERR_INVALID, "eid_accel_sah_tap: null argument");
+  if (n >= (1u << 28)) eid::raise(EID_ERR_UNSUPPORTED, "eid_accel_sah_tap: more than 2^28 boxes");
+  eid::BinaryTreeHost T;
+  eid::buildSahTree(n, lo, hi, T, threads);
+  std::copy(T.order.begin(), T.order.end(), order);
+  std::copy(T.parentLeaf.begin(), T.parentLeaf.end(), parentLeaf);
+  std::copy(T.left.begin(), T.left.end(), left); std::copy(T.right.begin(), T.right.end(), right);
+  std::copy(T.parentInner.begin(), T.parentInner.end(), parentInner);
+  std::copy(T.rangeFirst.begin(), T.rangeFirst.end(), rangeFirst); std::copy(T.rangeLast.begin(), T.rangeLast.end(), rangeLast);
+  return EID_OK;
+  EID_CATCH
+}

@@ -217,6 +217,12 @@ EID_API int  eid_accel_get_info(eid_accel* a, eid_accel_info* out);
  * rays: 8 floats each {ox,oy,oz,tmax, dx,dy,dz,unused}.  any_hit != 0 -> hits[i].hitT is 0 when
  * occluded and 1e28 when free, other fields undefined. */
 EID_API int  eid_accel_trace(eid_accel* a, const float* rays, uint32_t n, int any_hit, eid_hit* hits);
+/* Tap of the EID_ACCEL_FAST_TRACE topology builder (host only, needs no device; test infrastructure like the eid_*_tap functions below):
+ * the binary tree over n boxes (lo / hi: n x 3 floats) exactly as the build hands it to the GPU refit + collapse.  order[n]: position ->
+ * source box; per inner node (n - 1 of them, root = 0) left / right (>= 0 inner node, < 0 leaf ~position), parentInner, rangeFirst,
+ * rangeLast; parentLeaf[n].  threads <= 0: all hardware threads.  The result does not depend on `threads`. */
+EID_API int  eid_accel_sah_tap(const float* lo, const float* hi, uint32_t n, int threads, uint32_t* order, int32_t* left, int32_t* right,
+                               int32_t* parentInner, int32_t* parentLeaf, int32_t* rangeFirst, int32_t* rangeLast);
 
 /* ---------------------------------------------------------------------------------------------
  * Renderer (renderer.hpp:52-61; renderer.cpp:97-375)
