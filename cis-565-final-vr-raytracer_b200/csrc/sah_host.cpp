@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <exception>
+#include <mutex>
 #include <thread>
 
 namespace eid {
@@ -48,9 +49,15 @@ struct Builder {
     const int per = (count + chunks - 1) / chunks;
     auto forChunks = [&](auto&& fn) {
       if (chunks == 1) { fn(0, first, first + count); return; }
+      // (fn only reads the boxes and writes its own chunk's slot: it cannot throw; a chunk whose thread could not be created runs here)
       std::vector<std::thread> pool;
-      for (int c = 1; c < chunks; ++c) pool.emplace_back([&, c]() { fn(c, std::min(first + count, first + c * per), std::min(first + count, first + (c + 1) * per)); });
+      int started = 1;
+      try {
+        for (; started < chunks; ++started) { const int c = started; pool.emplace_back([&, c]() { fn(c, std::min(first + count, first + c * per), std::min(first + count, first + (c + 1) * per)); }); }
+      } catch (...) {
+      }
       fn(0, first, std::min(first + count, first + per));
+      for (int c = started; c < chunks; ++c) fn(c, std::min(first + count, first + c * per), std::min(first + count, first + (c + 1) * per));
       for (std::thread& t : pool) t.join();
     };
     std::vector<float> cbLo(3 * (size_t)chunks, 3.0e38f), cbHi(3 * (size_t)chunks, -3.0e38f);
@@ -162,11 +169,26 @@ void buildSahTree(uint32_t n, const float* lo, const float* hi, BinaryTreeHost& 
   std::sort(tasks.begin(), tasks.end(), [](const Item& a, const Item& b) { return a.count > b.count; });
   if (threads == 1 || tasks.size() < 2) { for (const Item& it : tasks) B.subtree(it); return; }
   std::atomic<size_t> next{0};
-  auto work = [&]() { for (;;) { const size_t i = next.fetch_add(1); if (i >= tasks.size()) break; B.subtree(tasks[i]); } };
+  std::atomic<bool> failed{false};
+  std::exception_ptr error;                        // an exception must not leave a worker thread (std::terminate): the first one is rethrown here
+  std::mutex errorLock;
+  auto work = [&]() {
+    try {
+      for (;;) { const size_t i = next.fetch_add(1); if (i >= tasks.size() || failed.load()) break; B.subtree(tasks[i]); }
+    } catch (...) {
+      std::lock_guard<std::mutex> g(errorLock);
+      if (!error) error = std::current_exception();
+      failed.store(true);
+    }
+  };
   std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  try {
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  } catch (...) {                                  // no more threads to be had: the ones that started, and this one, do the work
+  }
   work();
   for (std::thread& t : pool) t.join();
+  if (error) std::rethrow_exception(error);
 }
 
 }  // namespace eid
