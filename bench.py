@@ -68,7 +68,10 @@ NODE_BYTES, TRI_BYTES, HIT_GATHER_BYTES = 64, 48, 108 + 80
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe).  The timed region of the headline workload
+    is ~60 ms, shorter than nvidia-smi's start-up: the sampler is started BEFORE the warm-up frames, polls every 20 ms, and every row carries the
+    host time at which it arrived; finish(t0, t1) keeps the rows of the timed region [t0, t1] (and says so), else the rows taken under the same
+    load just around it (warm-up frames before, end-to-end frames after)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,16 +82,21 @@ class ClockSampler(threading.Thread):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
                 if self.stop_flag:
                     break
         except Exception:
             pass
 
-    def finish(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout and self.is_alive():
+            time.sleep(0.01)
+
+    def finish(self, t0=None, t1=None):
         self.stop_flag = True
         if self.proc is not None:
             try:
@@ -96,17 +104,29 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         self.join(timeout=2)
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+        def parse(rows):
+            sm, mx, reasons = [], 0, set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0]))
+                    mx = max(mx, float(r[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+        window = "timed region"
+        rows = [r for r in self.rows if t0 is not None and t0 <= r[0] <= t1 + 0.02]
+        sm, mx, reasons = parse(rows)
+        if not sm and t0 is not None:      # none landed inside: the rows taken under the same load around it (warm-up before, e2e frames after)
+            window = "under load around the timed region (warm-up / end-to-end frames)"
+            sm, mx, reasons = parse([r for r in self.rows if t0 - 1.0 <= r[0] <= t1 + 1.0])
+        if not sm:
+            window = "whole run"
+            sm, mx, reasons = parse(self.rows)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ncu DRAM / L2 bytes per frame and stage come from a committed capture of THIS workload (tools/ncu_traffic.py writes the file from
@@ -375,16 +395,17 @@ def run_cuda(args):
         return ms, rays, kms / max(1, nsteps)
 
     frame = 0
-    for _ in range(max(3, args.warmup)):
-        step(frame)
-        frame += 1
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.15)
+        sampler.wait_first()                         # nvidia-smi is up and streaming before any frame runs
+    for _ in range(max(3, args.warmup)):
+        step(frame)
+        frame += 1
+    t_clk0 = time.perf_counter()
     ms, rays, _ = timed(args.steps, frame)
+    t_clk1 = time.perf_counter()
     frame += args.steps
-    clocks = sampler.finish() if sampler else None
     value = rays / (ms * 1e-3) / 1e6
 
     # end to end: host buffers, H2D of the per-frame inputs + D2H of both result images inside the timed region
@@ -401,6 +422,7 @@ def run_cuda(args):
     ems, erays, _ = timed(e2e_steps, frame, pinned)
     frame += e2e_steps
     e2e_value = erays / (ems * 1e-3) / 1e6
+    clocks = sampler.finish(t_clk0, t_clk1) if sampler else None     # rows of the device-timed region; stopped here, after the end-to-end frames
 
     # per-kernel pass (CUDA events inside the library around every stage, same frames/state sequence) + visit counters
     ksteps = max(3, min(args.steps, 16))
