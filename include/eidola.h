@@ -175,7 +175,8 @@ EID_API int  eid_scene_read_table(eid_scene* s, int table, uint32_t index, void*
 
 /* ---------------------------------------------------------------------------------------------
  * AccelStructure (accelstruct.hpp:40-46; accelstruct.cpp:55-162).  The Vulkan driver BVH is
- * replaced by a CUDA LBVH -> 8-wide BVH build over world-space triangles.
+ * replaced by a 4-wide BVH (binned-SAH or Morton topology; one flat world-space tree, or BLAS per
+ * prim mesh + TLAS) built by csrc/accel.cu and walked in software (csrc/trace.cuh).
  * ------------------------------------------------------------------------------------------- */
 typedef struct eid_accel_info {
   uint64_t triangleCount;
