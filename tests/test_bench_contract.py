@@ -47,3 +47,36 @@ def test_help_renders():
     """argparse expands % in help strings: an unescaped one only fails when somebody asks for --help."""
     p = _run(["--help"])
     assert p.returncode == 0 and "--gpus" in p.stdout, p.stderr[-1000:]
+
+
+def test_clock_sampler_keeps_the_rows_of_the_timed_region(tmp_path, monkeypatch):
+    """bench.ClockSampler against a stand-in nvidia-smi that needs 0.2 s to come up and then prints a row every 20 ms: rows are stamped on
+    arrival, finish(t0, t1) keeps those of the timed region and parses clocks + throttle reasons."""
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.2\nwhile true; do echo '1965, 1980, 400.0, Not Active, Not Active, Not Active, Active'; sleep 0.02; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    s.wait_first()
+    assert s.rows, "the sampler must be streaming before the first frame"
+    time.sleep(0.05)
+    t0 = time.perf_counter()
+    time.sleep(0.1)
+    t1 = time.perf_counter()
+    time.sleep(0.05)
+    c = s.finish(t0, t1)
+    assert c["window"] == "timed region" and 2 <= c["samples"] <= 8, c
+    assert c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1980.0 and c["reasons"] == ["sw_power_cap"]
+    # a region too short for any row falls back to the rows taken under load around it, and says so
+    s = bench.ClockSampler(0)
+    s.start()
+    s.wait_first()
+    time.sleep(0.03)
+    now = time.perf_counter()
+    c = s.finish(now - 0.0005, now - 0.0004)
+    assert c["samples"] >= 1 and c["sm_mhz"] == 1965.0 and c["window"] in ("timed region", "under load around the timed region (warm-up / end-to-end frames)")
